@@ -1,0 +1,177 @@
+/* molclr_b200 -- C ABI of the B200-native MolCLR pre-training hot path.
+ *
+ * The reference (CameronDiao/MolCLR) is pure Python and has no FFI boundary of its own; what this
+ * library replaces are the ATen / torch-scatter / cuBLAS calls its Python hot path reaches
+ * (SURVEY.md section 2b, rows K1-K18).  Each entry point cites the reference line(s) whose work it
+ * does.  The Python classes in molclr_b200/ (GINet, GCN, NTXentLoss -- same constructor signatures
+ * and state_dict keys as the reference) call these through ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current device unless marked "host";
+ *   - the caller owns every buffer, including workspaces; nothing here allocates or frees;
+ *   - work is enqueued on `stream`; no entry point synchronises the device or the stream;
+ *   - return 0 on success, negative on error; molclr_last_error() (thread-local) has the message;
+ *   - feature matrices are row-major fp32 [rows][D] with D % 4 == 0 and 16-byte aligned bases;
+ *   - "tf32-rounded" means rounded to nearest to 10 mantissa bits (cvt.rna.tf32.f32): such a tensor is
+ *     consumed by the tensor cores without further loss.
+ */
+#ifndef MOLCLR_B200_H
+#define MOLCLR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define MOLCLR_ABI_VERSION 1
+
+/* ---- library ------------------------------------------------------------------------------- */
+int molclr_abi_version(void);
+const char* molclr_last_error(void);
+/* host out-params; cc = compute capability major*10+minor */
+int molclr_device_info(int* sm_count, int* cc);
+
+/* ---- batch -> CSR plan (once per batch) ----------------------------------------------------------
+ * Replaces, for all layers at once: add_self_loops + self_loop_attr + cat (ginet_molclr.py:31-37,
+ * gcn_molclr.py:64-70) and the COO gather/scatter bookkeeping of PyG's MessagePassing.propagate.
+ * Inputs are the int64 tensors of a PyG Batch (dataset.py:93-109 layout):
+ *   x [N,2] (atom 0..118, chirality 0..2), edge_index [2,E], edge_attr [E,2] (type 0..4, dir 0..2),
+ *   batch [N] (graph id 0..G-1).
+ * Outputs (all int32 unless noted):
+ *   xpacked[N] = atom | chirality << 8;  node2graph[N];
+ *   rowptr[N+1], col[E] (source of each in-edge), eattr[E] uint8 = type*3+dir: destination-sorted,
+ *     in-edges in INPUT order; the self loop is implicit (summed last by the aggregation kernel);
+ *   rowptr_t[N+1], col_t[E] (destination of each out-edge): source-sorted transpose for backward;
+ *   cnt[N][8] uint16: in-edge counts per bond type (0..4, self loop = type 4) and direction (5..7);
+ *   gptr[G+1], gperm[N]: nodes grouped by graph (identity permutation for sorted `batch`).
+ *   status[4]: [0] = error bits (1 node feature, 2 edge endpoint, 4 edge attr, 8 batch id out of
+ *              range, 16 degree overflow); [1] = 1 if `batch` was not sorted.
+ */
+size_t molclr_plan_workspace_bytes(int64_t N, int64_t E, int64_t G);
+int molclr_plan_build(const int64_t* x, const int64_t* edge_index, const int64_t* edge_attr, const int64_t* batch,
+                      int64_t N, int64_t E, int64_t G, int32_t* xpacked, int32_t* node2graph, int32_t* rowptr,
+                      int32_t* col, uint8_t* eattr, int32_t* rowptr_t, int32_t* col_t, uint16_t* cnt, int32_t* gptr,
+                      int32_t* gperm, void* workspace, size_t workspace_bytes, int32_t* status, cudaStream_t stream);
+
+/* ---- node embedding: ginet_molclr.py:103 / gcn_molclr.py:144 ------------------------------------- */
+int molclr_embed_nodes_fwd(const int32_t* xpacked, const float* E1, const float* E2, int64_t N, int D, float* out,
+                           cudaStream_t stream);
+/* dE is ONE buffer [(119+3)][D]: rows 0..118 = grad of x_embedding1, 119..121 = grad of x_embedding2.
+ * partials: [molclr_embed_nodes_bwd_blocks(D)][(119+3)*D] floats. */
+int molclr_embed_nodes_bwd_blocks(int D);
+int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, int64_t N, int D, float* dE, float* partials,
+                           cudaStream_t stream);
+
+/* ---- GINE neighbour aggregation: ginet_molclr.py:39-44 + PyG propagate (index_select, add, scatter_add_) ----
+ * out[i] = sum_{in-edges e of i, input order}( f(src[col[e]]) + (B1[t_e] + B2[d_e]) ) + ( f(src[i]) + (B1[4] + B2[0]) )
+ * f = identity if bn_coef == NULL, else f(v) = [relu](v*scale + shift) with scale = bn_coef[0..D), shift = bn_coef[D..2D)
+ * (the previous layer's BatchNorm + ReLU, ginet_molclr.py:107-111, applied on the fly). */
+int molclr_gine_aggregate_fwd(const float* src, const float* bn_coef, int relu, const int32_t* rowptr, const int32_t* col,
+                              const uint8_t* eattr, const float* B1, const float* B2, int64_t N, int D, float* out,
+                              int round_tf32_out, cudaStream_t stream);
+/* Backward (autograd of index_select/scatter_add_): gy[j] = sum_{out-edges e of j} ga[col_t[e]] + ga[j].
+ * If z_prev != NULL additionally fuses the previous layer's ReLU backward and BatchNorm statistics:
+ *   gy[j] *= [z_prev[j]*scale+shift > 0] (if relu);  partials[b][0] += gy, partials[b][1] += gy * (z_prev-mean)*invstd
+ * with bn_coef = [scale, shift, mean, invstd][D].  partials: [molclr_rowwise_max_blocks()][2][D]; *num_partials
+ * (host) receives the number of partial rows written. */
+int molclr_rowwise_max_blocks(void);
+int molclr_gine_aggregate_bwd(const float* ga, const int32_t* rowptr_t, const int32_t* col_t, const float* z_prev,
+                              const float* bn_coef, int relu, int64_t N, int D, float* gy, float* partials,
+                              int* num_partials, cudaStream_t stream);
+/* Gradients of edge_embedding1/2 (embedding_dense_backward over E' rows in the reference):
+ * dB [8][D]: rows 0..4 = d edge_embedding1, rows 5..7 = d edge_embedding2.  partials: [max_blocks][8][D]. */
+int molclr_edge_table_grad(const float* ga, const uint16_t* cnt, int64_t N, int D, float* dB, float* partials,
+                           cudaStream_t stream);
+
+/* out[c] (+)= scale * sum_p partials[p][c], p in increasing order (deterministic). */
+int molclr_reduce_partials(const float* partials, int P, int len, float scale, int accumulate, float* out,
+                           cudaStream_t stream);
+
+/* ---- BatchNorm1d: ginet_molclr.py:79-81,107 (torch defaults eps 1e-5, momentum 0.1) ----------------
+ * tile_stats [T][2][D]: per tile of `tile_rows` rows, column mean and M2 (from the GEMM epilogue).
+ * coef [4][D] = scale, shift, mean, invstd.  Updates running stats (unbiased var) and num_batches_tracked. */
+int molclr_bn_fwd_finalize(const float* tile_stats, int T, int tile_rows, int64_t N, int D, const float* gamma,
+                           const float* beta, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                           float momentum, float eps, float* coef, cudaStream_t stream);
+int molclr_bn_eval_coef(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                        float eps, int D, float* coef, cudaStream_t stream);
+/* partials [P][2][D] = (sum gy, sum gy*xhat).  Writes dgamma, dbeta and bcoef [3][D] = (k1, A, B) with
+ * gz = k1*gy + A + B*z. */
+int molclr_bn_bwd_finalize(const float* partials, int P, int64_t N, int D, const float* gamma, const float* coef,
+                           int use_batch_stats, float* dgamma, float* dbeta, float* bcoef, cudaStream_t stream);
+/* gz (tf32-rounded) = k1*gy + A + B*z.  gy from memory, or (gp != NULL) gy[n] = gp[node2graph[n]] * w_graph
+ * (backward of global_mean/add_pool).  dbias (optional) = column sums of gz.  partials [max_blocks][D]. */
+int molclr_bn_bwd_apply(const float* gy, const float* gp, const int32_t* node2graph, const int32_t* gptr, int pool_mean,
+                        const float* z, const float* bcoef, int64_t N, int D, float* gz, float* dbias, float* partials,
+                        cudaStream_t stream);
+
+/* ---- global_mean_pool / global_add_pool: ginet_molclr.py:83-88,113 (pool_mode 0 = mean, 1 = add) ----
+ * out[g] = w_g * sum_{n in graph g, node order} [relu](z[n]*scale + shift) */
+int molclr_pool_fwd(const float* z, const float* bn_coef, int relu, const int32_t* gptr, const int32_t* gperm,
+                    int pool_mode, int64_t G, int D, float* out, int round_tf32_out, cudaStream_t stream);
+int molclr_pool_bwd_stats(const float* gp, const int32_t* node2graph, const int32_t* gptr, int pool_mode, const float* z,
+                          const float* bn_coef, int64_t N, int D, float* partials, int* num_partials, cudaStream_t stream);
+
+/* ---- dense contractions: the nn.Linear / matmul calls of ginet_molclr.py:19-23,46-47,90-96,114-115,
+ * gcn_molclr.py:76 and their autograd backward, on tcgen05 tensor cores (TF32 in, FP32 accumulate) ----
+ * C[M][N] = sum_k A(m,k) * B(n,k).
+ *   a_mn = 0: A is row-major [M][K] (ld = lda);  a_mn = 1: A is row-major [K][M].   Same for B with N.
+ * Epilogue, in this order: + bias[n]; + addend[m][n]; relu; * (mask[m][n] > 0); column statistics of the
+ * result per 128-row tile (colstat_mode 1: sums -> colstat[tile][N]; 2: mean and M2 -> colstat[tile][2][N]);
+ * out = (round_out ? tf32-rounded : exact); out2 = tf32-rounded copy.
+ * split_k > 1 or transpose_out: raw products accumulated atomically into out (zeroed here first);
+ * transpose_out stores C^T (out[n][m]).  No other epilogue option is allowed in that mode. */
+typedef struct {
+  const float* A; int64_t lda; int32_t a_mn;
+  const float* B; int64_t ldb; int32_t b_mn;
+  int64_t M, N, K;
+  float* out; int64_t ldo; int32_t transpose_out;
+  float* out2; int64_t ldo2;
+  const float* bias;
+  const float* addend; int64_t ldadd;
+  const float* mask; int64_t ldmask;
+  int32_t relu, round_out;
+  float* colstat; int32_t colstat_mode;
+  int32_t split_k;
+} molclr_gemm_args;
+int molclr_gemm_colstat_tiles(int64_t M);
+int molclr_gemm_tf32(const molclr_gemm_args* args /* host */, cudaStream_t stream);
+
+/* ---- small elementwise ops ---------------------------------------------------------------------- */
+int molclr_round_tf32(const float* src, float* dst, int64_t n, cudaStream_t stream);
+/* F.normalize(z, dim=1), molclr.py:63-64 (eps 1e-12) and its backward */
+int molclr_l2_normalize_fwd(const float* z, int64_t R, int C, float eps, float* y, float* inv_norm, cudaStream_t stream);
+int molclr_l2_normalize_bwd(const float* gy, const float* y, const float* inv_norm, int64_t R, int C, float eps, float* gz,
+                            cudaStream_t stream);
+
+/* ---- NT-Xent: utils/nt_xent.py:47-65 -------------------------------------------------------------
+ * rep [R][C] fp32, R = 2N rows ordered [zjs; zis] (nt_xent.py:48), already L2-normalised when
+ * use_cosine (the cosine similarity's own normalisation is applied by the caller-side kernels
+ * molclr_l2_normalize_*).  `cols` [Rc][C] are the candidate rows (== rep for one GPU; the all-gathered
+ * projections of every rank for global negatives), row r of rep is row r + row_offset of cols and its
+ * positive is column (r + row_offset + Rc/2) mod Rc.
+ *   forward : row_lse[r] = log sum_{k != self} exp(S[r][k]/tau),  row_pos[r] = S[r][pos(r)]/tau,
+ *             loss[0] = sum_r (row_lse[r] - row_pos[r]) / Rc  (this rank's share of the mean over Rc anchors).
+ *   backward: g_rep[r] = (gscale/tau) * sum_k (P[r][k] + P[k][r] - 2*[k = pos(r)]) * cols[k],
+ *             P[i][k] = exp(S[i][k]/tau - lse[i]) for k != i; col_lse[Rc] holds the log-sum-exp of every
+ *             candidate row (== row_lse on one GPU, all-gathered for global negatives); gscale = 1/Rc.
+ * The Rc x Rc similarity matrix is never written to memory: backward works in L2-resident stripes of
+ * 1024 candidate columns.  Requires Rc % 4 == 0 and C % 4 == 0. */
+size_t molclr_ntxent_workspace_bytes(int64_t R, int64_t Rc, int C);
+int molclr_ntxent_fwd(const float* rep, const float* cols, int64_t R, int64_t Rc, int C, int64_t row_offset,
+                      float inv_temperature, float* row_lse, float* row_pos, float* loss /* [1], optional */,
+                      void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int molclr_ntxent_bwd(const float* rep, const float* cols, int64_t R, int64_t Rc, int C, int64_t row_offset,
+                      float inv_temperature, const float* row_lse, const float* col_lse, float gscale, float* g_rep,
+                      void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOLCLR_B200_H */

@@ -1,0 +1,66 @@
+// Common helpers for the molclr_b200 CUDA kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+#ifndef __CUDA_ARCH__
+#define MOLCLR_HOST 1
+#endif
+
+namespace molclr {
+
+// ---------------------------------------------------------------- error reporting (host)
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define MOLCLR_CHECK_LAUNCH(what)                                  \
+  do {                                                             \
+    cudaError_t _e = cudaGetLastError();                           \
+    if (_e != cudaSuccess) return ::molclr::cuda_fail(_e, what);   \
+  } while (0)
+
+#define MOLCLR_REQUIRE(cond, ...)                                  \
+  do {                                                             \
+    if (!(cond)) { ::molclr::set_error(__VA_ARGS__); return -2; }  \
+  } while (0)
+
+int sm_count();   // cached multiprocessor count of the current device
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ float round_tf32(float x) {
+  // round-to-nearest (ties away) to 10 mantissa bits; low 13 bits of the result are zero, so the
+  // tensor core's operand truncation is exact on it.
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// streaming (read-once) 128-bit load: do not pollute L1
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int kNumAtomType = 119;   // ginet_molclr.py:9
+constexpr int kNumChirality = 3;    // ginet_molclr.py:10
+constexpr int kNumBondType = 5;     // ginet_molclr.py:12 (4 = self loop)
+constexpr int kNumBondDir = 3;      // ginet_molclr.py:13
+constexpr int kSelfLoopAttr = 4 * 3 + 0;   // packed (type 4, dir 0)
+constexpr int kNumEdgeClass = 15;
+
+}  // namespace molclr

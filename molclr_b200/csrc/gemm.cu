@@ -1,0 +1,450 @@
+// TF32 tensor-core GEMM for the dense contractions of the hot path (GIN MLP 300->600->300 forward
+// and backward, GCN 300x300, projection head), written directly against tcgen05 / TMEM / TMA:
+//
+//   * operands are the fp32 tensors themselves (pre-rounded to TF32 by their producers), staged by
+//     TMA into 128B-swizzled shared-memory tiles; out-of-range rows/columns are zero-filled by TMA so
+//     the awkward extents (300, 600, ragged node counts) need no padding in HBM;
+//   * one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) into a TMEM accumulator;
+//   * both operands may be K-major ([rows][K]) or MN-major ([K][rows]) so that Y = X W^T, dX = dY W
+//     and dW = dY^T X all read the row-major activations/weights in place (no transposed copies);
+//   * the epilogue (4 warps) drains TMEM through a shared staging tile and fuses bias, addend, ReLU,
+//     ReLU-mask, TF32 rounding, BatchNorm tile statistics / column sums and coalesced stores.
+//
+// A scalar-FMA kernel with the same argument struct (MOLCLR_GEMM_IMPL=simt) exists for debugging
+// the tensor-core path on the GPU; it is never selected implicitly.
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "molclr_b200.h"
+#include "ptx.cuh"
+#include "gemm.cuh"
+
+namespace molclr {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 32;          // 32 tf32 = one 128-byte swizzle row
+constexpr int GEMM_THREADS = 192;    // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int GEMM_TMEM_COLS = 256;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = 3;
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 4;
+  static constexpr int B_BYTES = BN * GEMM_BK * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int LDS = BN + 4;                         // staging pitch (floats): conflict-free float4 rows
+  static constexpr int STAGING_BYTES = GEMM_BM * LDS * 4;
+  static constexpr int MAIN_BYTES = PIPE_BYTES > STAGING_BYTES ? PIPE_BYTES : STAGING_BYTES;
+  static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /* alignment slack */ + 128 /* barriers + tmem ptr */;
+  static_assert(BN % 32 == 0 && BN <= 256, "BN must be a multiple of 32 (MN-major B blocks) and <= 256");
+  static_assert(STAGE_BYTES % 1024 == 0, "stage bases must stay 1024B aligned for SWIZZLE_128B");
+};
+
+
+__device__ __forceinline__ float ntx_w_elem(float acc, const GemmParams& p, float lse_r, long long grow_g, long long gcol) {
+  // W[r][k] = P[r][k] + P[k][r] - 2*[k == pos(r)],  P[i][k] = exp(l - lse_i) for k != i   (nt_xent.py:53-65 differentiated)
+  if (gcol == grow_g) return 0.f;
+  const float l = acc * p.inv_tau;
+  float w = __expf(l - lse_r) + __expf(l - __ldg(p.col_lse + gcol));
+  long long pos = grow_g + p.num_cand / 2;
+  if (pos >= p.num_cand) pos -= p.num_cand;
+  if (gcol == pos) w -= 2.f;
+  return w;
+}
+
+__device__ __forceinline__ float4 epilogue_apply(float4 v, const GemmParams& p, int grow, int col) {
+  if (p.epi == EPI_NTX_W) {
+    const float lse_r = __ldg(p.row_lse + grow);
+    const long long gr = grow + p.row_offset, gc = col + p.col_offset;
+    v.x = ntx_w_elem(v.x, p, lse_r, gr, gc); v.y = ntx_w_elem(v.y, p, lse_r, gr, gc + 1);
+    v.z = ntx_w_elem(v.z, p, lse_r, gr, gc + 2); v.w = ntx_w_elem(v.w, p, lse_r, gr, gc + 3);
+    return v;
+  }
+  if (p.alpha != 1.f) { v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha; }
+  if (p.bias) { const float4 b = ldg_f4(p.bias + col); v = f4_add(v, b); }
+  if (p.addend) { const float4 a = *reinterpret_cast<const float4*>(p.addend + (size_t)grow * p.ldadd + col); v = f4_add(v, a); }
+  if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+  if (p.mask) {
+    const float4 m = ldg_f4(p.mask + (size_t)grow * p.ldmask + col);
+    if (!(m.x > 0.f)) v.x = 0.f;
+    if (!(m.y > 0.f)) v.y = 0.f;
+    if (!(m.z > 0.f)) v.z = 0.f;
+    if (!(m.w > 0.f)) v.w = 0.f;
+  }
+  return v;
+}
+__device__ __forceinline__ float4 f4_round(float4 v) {
+  return make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+}
+
+// Column statistics of the finished tile held in `stage` (rows_valid x BN): mode 1 = sums,
+// mode 2 = (mean, M2) for the BatchNorm merge.  `tid` in [0, nthreads).
+__device__ __forceinline__ void tile_colstat(const float* stage, int lds, int bn, int rows_valid, int n0, int m_tile,
+                                             const GemmParams& p, int tid, int nthreads) {
+  for (int c = tid; c < bn; c += nthreads) {
+    const int col = n0 + c;
+    if (col >= p.N) continue;
+    float s = 0.f;
+    for (int r = 0; r < rows_valid; ++r) s += stage[r * lds + c];
+    if (p.colstat_mode == 1) {
+      p.colstat[(size_t)m_tile * p.N + col] = s;
+    } else {
+      const float mean = s / (float)rows_valid;
+      float m2 = 0.f;
+      for (int r = 0; r < rows_valid; ++r) { const float d = stage[r * lds + c] - mean; m2 = fmaf(d, d, m2); }
+      p.colstat[((size_t)m_tile * 2) * p.N + col] = mean;
+      p.colstat[((size_t)m_tile * 2 + 1) * p.N + col] = m2;
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, (BN <= 160) ? 2 : 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::MAIN_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m_tile = blockIdx.y, m0 = m_tile * GEMM_BM;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int nkb = min(p.num_kb, kb0 + p.kb_per_split) - kb0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) { ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1); }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+  }
+  if (warp == 1) { ptx::tmem_alloc(tmem_slot, GEMM_TMEM_COLS); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % Cfg::STAGES;
+        ptx::mbar_wait(empty_bar + s, ((i / Cfg::STAGES) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(full_bar + s, Cfg::STAGE_BYTES);
+        uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
+        uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+        const int kc = (kb0 + i) * GEMM_BK;
+        if (!p.a_mn) ptx::tma_load_2d(a_dst, &tmA, full_bar + s, kc, m0);
+        else
+          for (int j = 0; j < GEMM_BM / 32; ++j) ptx::tma_load_2d(a_dst + j * 4096, &tmA, full_bar + s, m0 + 32 * j, kc);
+        if (!p.b_mn) ptx::tma_load_2d(b_dst, &tmB, full_bar + s, kc, n0);
+        else
+          for (int j = 0; j < BN / 32; ++j) ptx::tma_load_2d(b_dst + j * 4096, &tmB, full_bar + s, n0 + 32 * j, kc);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_tf32(BN, p.a_mn != 0, p.b_mn != 0);
+      const uint32_t a_lbo = p.a_mn ? 4096u : 16u, b_lbo = p.b_mn ? 4096u : 16u;
+      const uint32_t a_kstep = p.a_mn ? 1024u : 32u, b_kstep = p.b_mn ? 1024u : 32u;   // bytes per K=8 slice
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % Cfg::STAGES;
+        ptx::mbar_wait(full_bar + s, (i / Cfg::STAGES) & 1);
+        ptx::tc_fence_after();
+        const uint32_t a_base = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES), b_base = a_base + Cfg::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < GEMM_BK / 8; ++k) {
+          const uint64_t ad = ptx::make_smem_desc(a_base + k * a_kstep, a_lbo, 1024u);
+          const uint64_t bd = ptx::make_smem_desc(b_base + k * b_kstep, b_lbo, 1024u);
+          ptx::mma_tf32_ss(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        ptx::mma_commit(empty_bar + s);          // frees the smem slot once these MMAs have read it
+      }
+      ptx::mma_commit(tmem_full_bar);            // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue (128 threads, thread <-> accumulator row)
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane, grow = m0 + row;
+    const int rows_valid = min(GEMM_BM, p.M - m0);
+    const int et = threadIdx.x - 64;              // 0..127
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (p.epi == EPI_NTX_FWD) {
+      // per-row (max, sum exp) of this column tile, own column masked; thread <-> row straight from TMEM
+      const long long gr = grow + p.row_offset;
+      long long pos = gr + p.num_cand / 2;
+      if (pos >= p.num_cand) pos -= p.num_cand;
+      float mx = -INFINITY;
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        ptx::tmem_ld_x16(taddr + c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const long long gc = n0 + c0 + j + p.col_offset;
+          if (n0 + c0 + j < p.N && gc != gr) mx = fmaxf(mx, v[j] * p.inv_tau);
+          if (gc == pos && n0 + c0 + j < p.N && grow < p.M) p.row_pos[grow] = v[j] * p.inv_tau;
+        }
+      }
+      float sum = 0.f;
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        ptx::tmem_ld_x16(taddr + c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const long long gc = n0 + c0 + j + p.col_offset;
+          if (n0 + c0 + j < p.N && gc != gr) sum += __expf(v[j] * p.inv_tau - mx);
+        }
+      }
+      if (grow < p.M) {
+        p.part_max[(size_t)blockIdx.x * p.M + grow] = mx;
+        p.part_sum[(size_t)blockIdx.x * p.M + grow] = sum;
+      }
+    } else if (p.atomic_out) {
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        ptx::tmem_ld_x16(taddr + c0, v);
+        if (grow < p.M) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = n0 + c0 + j;
+            if (col < p.N)
+              atomicAdd(p.transpose_out ? p.out + (size_t)col * p.ldo + grow : p.out + (size_t)grow * p.ldo + col, v[j]);
+          }
+        }
+      }
+    } else {
+      float* stage = reinterpret_cast<float*>(smem);   // pipeline buffers are idle once tmem_full fired
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        ptx::tmem_ld_x16(taddr + c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) st_f4(stage + row * Cfg::LDS + c0 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+      }
+      ptx::named_bar_sync(1, 128);
+      for (int r = warp - 2; r < rows_valid; r += 4) {
+        const int gr = m0 + r;
+        for (int c4 = lane; c4 < BN / 4; c4 += 32) {
+          const int col = n0 + 4 * c4;
+          if (col >= p.N) continue;
+          float4 v = *reinterpret_cast<const float4*>(stage + r * Cfg::LDS + 4 * c4);
+          v = epilogue_apply(v, p, gr, col);
+          if (p.colstat) st_f4(stage + r * Cfg::LDS + 4 * c4, v);
+          if (p.out) st_f4(p.out + (size_t)gr * p.ldo + col, p.round_out ? f4_round(v) : v);
+          if (p.out2) st_f4(p.out2 + (size_t)gr * p.ldo2 + col, f4_round(v));
+        }
+      }
+      if (p.colstat) {
+        ptx::named_bar_sync(1, 128);
+        tile_colstat(stage, Cfg::LDS, BN, rows_valid, n0, m_tile, p, et, 128);
+      }
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, GEMM_TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Debug implementation: plain fp32 FMA, one thread per output row, 32 columns per block.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gemm_simt_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B,
+                                                        long long ldb, const GemmParams p) {
+  __shared__ float stage[GEMM_BM * 33];
+  const int n0 = blockIdx.x * 32, m_tile = blockIdx.y, m0 = m_tile * GEMM_BM;
+  const int row = threadIdx.x, grow = m0 + row;
+  const int rows_valid = min(GEMM_BM, p.M - m0);
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  if (grow < p.M) {
+    for (int k = 0; k < p.K; ++k) {
+      const float a = p.a_mn ? A[(size_t)k * lda + grow] : A[(size_t)grow * lda + k];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = n0 + j;
+        if (col < p.N) acc[j] = fmaf(a, p.b_mn ? B[(size_t)k * ldb + col] : B[(size_t)col * ldb + k], acc[j]);
+      }
+    }
+  }
+  if (p.epi == EPI_NTX_FWD) {
+    if (grow < p.M) {
+      const long long gr = grow + p.row_offset;
+      long long pos = gr + p.num_cand / 2;
+      if (pos >= p.num_cand) pos -= p.num_cand;
+      float mx = -INFINITY, sum = 0.f;
+      for (int j = 0; j < 32; ++j) {
+        const long long gc = n0 + j + p.col_offset;
+        if (n0 + j < p.N && gc != gr) mx = fmaxf(mx, acc[j] * p.inv_tau);
+        if (n0 + j < p.N && gc == pos) p.row_pos[grow] = acc[j] * p.inv_tau;
+      }
+      for (int j = 0; j < 32; ++j) {
+        const long long gc = n0 + j + p.col_offset;
+        if (n0 + j < p.N && gc != gr) sum += __expf(acc[j] * p.inv_tau - mx);
+      }
+      p.part_max[(size_t)blockIdx.x * p.M + grow] = mx;
+      p.part_sum[(size_t)blockIdx.x * p.M + grow] = sum;
+    }
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const int col = n0 + j;
+    float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+    if (grow < p.M && col < p.N) {
+      if (p.atomic_out) {
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+        for (int t = 0; t < 4; ++t)
+          atomicAdd(p.transpose_out ? p.out + (size_t)(col + t) * p.ldo + grow : p.out + (size_t)grow * p.ldo + col + t, vv[t]);
+      } else {
+        v = epilogue_apply(v, p, grow, col);
+        if (p.out) st_f4(p.out + (size_t)grow * p.ldo + col, p.round_out ? f4_round(v) : v);
+        if (p.out2) st_f4(p.out2 + (size_t)grow * p.ldo2 + col, f4_round(v));
+      }
+    }
+    stage[row * 33 + j] = v.x; stage[row * 33 + j + 1] = v.y; stage[row * 33 + j + 2] = v.z; stage[row * 33 + j + 3] = v.w;
+  }
+  if (p.colstat && !p.atomic_out) {
+    __syncthreads();
+    tile_colstat(stage, 33, 32, rows_valid, n0, m_tile, p, threadIdx.x, 128);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// Tensor map over a row-major fp32 matrix [outer][inner] with leading dimension ld (elements),
+// box = [box_outer][32 inner elements], 128-byte swizzle, zero fill out of bounds.
+static int make_tmap(CUtensorMap* m, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_outer) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  MOLCLR_REQUIRE(enc != nullptr, "gemm: cuTensorMapEncodeTiled not available from the driver");
+  MOLCLR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "gemm: operand base pointer must be 16-byte aligned");
+  MOLCLR_REQUIRE(ld % 4 == 0, "gemm: leading dimension %lld must be a multiple of 4 floats (TMA 16-byte stride)", (long long)ld);
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MOLCLR_REQUIRE(r == CUDA_SUCCESS, "gemm: cuTensorMapEncodeTiled failed with CUresult %d (inner=%lld outer=%lld ld=%lld)", (int)r,
+                 (long long)inner, (long long)outer, (long long)ld);
+  return 0;
+}
+
+template <int BN>
+static int launch_tc(const GemmJob& j, const GemmParams& p, int n_tiles, int m_tiles, int splits, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap tmA, tmB;
+  int rc;
+  // K-major operand [rows][K]: inner = K, outer = rows, box = rows-per-tile x 32.  MN-major [K][rows]: inner = rows, outer = K, box 32 x 32.
+  rc = p.a_mn ? make_tmap(&tmA, j.A, p.M, p.K, j.lda, 32) : make_tmap(&tmA, j.A, p.K, p.M, j.lda, GEMM_BM);
+  if (rc) return rc;
+  rc = p.b_mn ? make_tmap(&tmB, j.B, p.N, p.K, j.ldb, 32) : make_tmap(&tmB, j.B, p.K, p.N, j.ldb, BN);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return cuda_fail(e, "gemm: cudaFuncSetAttribute");
+    attr_set = true;
+  }
+  gemm_tf32_kernel<BN><<<dim3(n_tiles, m_tiles, splits), GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  MOLCLR_CHECK_LAUNCH("gemm_tf32");
+  return 0;
+}
+
+static int gemm_impl_simt() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MOLCLR_GEMM_IMPL"); v = (e && strcmp(e, "simt") == 0) ? 1 : 0; }
+  return v;
+}
+
+static int gemm_bn(long long N) { return (N % 256 == 0 || N > 640) ? 256 : 160; }
+
+int gemm_n_tiles(long long N) {
+  if (gemm_impl_simt()) return (int)((N + 31) / 32);
+  const int bn = gemm_bn(N);
+  return (int)((N + bn - 1) / bn);
+}
+
+int gemm_run(const GemmJob& job, cudaStream_t stream) {
+  GemmParams p = job.p;
+  MOLCLR_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
+  MOLCLR_REQUIRE(p.N % 4 == 0, "gemm: N=%d must be a multiple of 4", p.N);
+  const bool atomic = job.split_k > 1 || p.transpose_out;
+  if (atomic)
+    MOLCLR_REQUIRE(p.epi == EPI_GENERIC && !p.bias && !p.addend && !p.mask && !p.relu && !p.round_out && !p.out2 && !p.colstat && p.out &&
+                       p.alpha == 1.f,
+                   "gemm: split-K / transposed output supports no fused epilogue");
+  else if (p.epi != EPI_NTX_FWD) {
+    MOLCLR_REQUIRE(p.out != nullptr || p.out2 != nullptr || p.colstat != nullptr, "gemm: no output requested");
+    MOLCLR_REQUIRE((!p.out || p.ldo % 4 == 0) && (!p.out2 || p.ldo2 % 4 == 0), "gemm: output leading dimensions must be multiples of 4");
+    MOLCLR_REQUIRE((!p.addend || p.ldadd % 4 == 0) && (!p.mask || p.ldmask % 4 == 0), "gemm: addend/mask leading dimensions must be multiples of 4");
+  }
+  p.num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  int splits = job.split_k > 1 ? job.split_k : 1;
+  if (splits > p.num_kb) splits = p.num_kb;
+  p.kb_per_split = (p.num_kb + splits - 1) / splits;
+  splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;          // no empty split
+  p.atomic_out = atomic ? 1 : 0;
+  const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+  if (atomic) {
+    const size_t w = (size_t)(p.transpose_out ? p.M : p.N) * sizeof(float), h = (size_t)(p.transpose_out ? p.N : p.M);
+    cudaError_t e = cudaMemset2DAsync(p.out, (size_t)p.ldo * sizeof(float), 0, w, h, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "gemm: zeroing split-K output");
+  }
+  if (gemm_impl_simt()) {
+    p.kb_per_split = p.num_kb;
+    gemm_simt_kernel<<<dim3((unsigned)((p.N + 31) / 32), m_tiles, 1), 128, 0, stream>>>(job.A, job.lda, job.B, job.ldb, p);
+    MOLCLR_CHECK_LAUNCH("gemm_simt");
+    return 0;
+  }
+  if (gemm_bn(p.N) == 256) return launch_tc<256>(job, p, (p.N + 255) / 256, m_tiles, splits, stream);
+  return launch_tc<160>(job, p, (p.N + 159) / 160, m_tiles, splits, stream);
+}
+
+}  // namespace molclr
+
+using namespace molclr;
+
+extern "C" int molclr_gemm_colstat_tiles(int64_t M) { return (int)((M + GEMM_BM - 1) / GEMM_BM); }
+
+extern "C" int molclr_gemm_tf32(const molclr_gemm_args* args, cudaStream_t stream) {
+  const molclr_gemm_args& a = *args;
+  MOLCLR_REQUIRE(a.M < (1ll << 31) && a.N < (1ll << 31) && a.K < (1ll << 31), "gemm: extent exceeds int32");
+  GemmJob j;
+  memset(&j, 0, sizeof(j));
+  j.A = a.A; j.lda = a.lda; j.B = a.B; j.ldb = a.ldb; j.split_k = a.split_k;
+  GemmParams& p = j.p;
+  p.M = (int)a.M; p.N = (int)a.N; p.K = (int)a.K; p.a_mn = a.a_mn; p.b_mn = a.b_mn;
+  p.out = a.out; p.ldo = a.ldo; p.transpose_out = a.transpose_out; p.out2 = a.out2; p.ldo2 = a.ldo2;
+  p.bias = a.bias; p.addend = a.addend; p.ldadd = a.ldadd; p.mask = a.mask; p.ldmask = a.ldmask;
+  p.relu = a.relu; p.round_out = a.round_out; p.colstat = a.colstat; p.colstat_mode = a.colstat_mode;
+  p.alpha = 1.f; p.epi = EPI_GENERIC;
+  return gemm_run(j, stream);
+}

@@ -1,0 +1,45 @@
+// Internal GEMM job description shared by gemm.cu and ntxent.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace molclr {
+
+enum GemmEpilogue : int { EPI_GENERIC = 0, EPI_NTX_FWD = 1, EPI_NTX_W = 2 };
+
+struct GemmParams {
+  int M, N, K;
+  int a_mn, b_mn;
+  int num_kb, kb_per_split;
+  float* out; long long ldo; int transpose_out;
+  float* out2; long long ldo2;
+  const float* bias;
+  const float* addend; long long ldadd;
+  const float* mask; long long ldmask;
+  int relu, round_out;
+  float* colstat; int colstat_mode;
+  int atomic_out;
+  float alpha;                 // out = alpha * acc (+ bias + addend ...)
+  // ---- NT-Xent epilogues (nt_xent.py:47-65); logits l = acc * inv_tau
+  int epi;
+  float inv_tau;
+  long long row_offset;        // global candidate index of A row r is r + row_offset (its own column: masked out)
+  long long col_offset;        // global candidate index of B row n is n + col_offset
+  long long num_cand;          // Rc; positive of global row g is (g + Rc/2) mod Rc
+  const float* row_lse;        // [M]   (EPI_NTX_W)
+  const float* col_lse;        // [num_cand] indexed by global candidate index (EPI_NTX_W)
+  float* part_max; float* part_sum;   // [n_tiles][M] (EPI_NTX_FWD)
+  float* row_pos;              // [M] logit of the positive (EPI_NTX_FWD)
+};
+
+struct GemmJob {
+  const float* A; long long lda; const float* B; long long ldb;
+  int split_k;
+  GemmParams p;                // M,N,K,a_mn,b_mn and the epilogue fields filled by the caller
+};
+
+// Validates, builds the tensor maps and launches.  Returns 0 or a negative error code.
+int gemm_run(const GemmJob& job, cudaStream_t stream);
+int gemm_n_tiles(long long N);   // number of column tiles the launcher will use for this N
+
+}  // namespace molclr

@@ -1,0 +1,183 @@
+// Batch -> destination-sorted CSR (+ source-sorted transpose) conversion, once per batch.
+//
+// Replaces what the reference re-does in every layer of every forward
+// (ginet_molclr.py:31-37: add_self_loops + CPU-built self_loop_attr + H2D copy + cat) and the
+// COO gather/scatter PyG performs (MessagePassing.propagate -> index_select / scatter_add_).
+// Ordering contract (bit-exact vs oracle/csr.py): a row lists its in-edges in INPUT order; the
+// self-loop is implicit and is summed LAST by the aggregation kernel, which is the order the
+// reference's CPU scatter_add_ uses (self-loops are appended at the end of edge_index).
+#include "common.cuh"
+#include "molclr_b200.h"
+
+namespace molclr {
+
+enum : int { ERR_NODE = 1, ERR_EDGE = 2, ERR_ATTR = 4, ERR_BATCH = 8, ERR_DEGREE = 16 };
+
+__global__ void plan_count_kernel(const int64_t* __restrict__ x, const int64_t* __restrict__ ei,
+                                  const int64_t* __restrict__ ea, const int64_t* __restrict__ batch,
+                                  int64_t N, int64_t E, int64_t G, int32_t* __restrict__ xpacked,
+                                  int32_t* __restrict__ node2graph, int32_t* deg_in, int32_t* deg_out,
+                                  int32_t* gcount, int32_t* status) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int err = 0;
+  for (int64_t n = i; n < N; n += stride) {
+    int64_t t = x[2 * n], c = x[2 * n + 1];
+    if (t < 0 || t >= kNumAtomType || c < 0 || c >= kNumChirality) { err |= ERR_NODE; t = 0; c = 0; }
+    xpacked[n] = (int32_t)t | ((int32_t)c << 8);
+    int64_t g = batch[n];
+    if (g < 0 || g >= G) { err |= ERR_BATCH; g = 0; }
+    node2graph[n] = (int32_t)g;
+    atomicAdd(&gcount[g], 1);
+    if (n > 0 && batch[n - 1] > batch[n]) atomicOr(&status[1], 1);   // batch vector not sorted
+  }
+  for (int64_t e = i; e < E; e += stride) {
+    int64_t s = ei[e], d = ei[E + e];
+    if (s < 0 || s >= N || d < 0 || d >= N) { err |= ERR_EDGE; continue; }
+    atomicAdd(&deg_in[d], 1);
+    atomicAdd(&deg_out[s], 1);
+    int64_t t = ea[2 * e], r = ea[2 * e + 1];
+    if (t < 0 || t >= kNumBondType || r < 0 || r >= kNumBondDir) err |= ERR_ATTR;
+  }
+  if (err) atomicOr(&status[0], err);
+}
+
+// Exclusive scan of `cnt[0..n)` into `ptr[0..n]`, one block per array (blockIdx.x selects).
+struct ScanJob { const int32_t* cnt; int32_t* ptr; int64_t n; };
+struct ScanJobs { ScanJob j[3]; };
+
+__global__ void plan_scan_kernel(ScanJobs jobs) {
+  const ScanJob job = jobs.j[blockIdx.x];
+  __shared__ int32_t part[1024];
+  const int t = threadIdx.x;
+  const int64_t chunk = (job.n + blockDim.x - 1) / blockDim.x;
+  const int64_t b = t * chunk, e = min(job.n, b + chunk);
+  int32_t s = 0;
+  for (int64_t k = b; k < e; ++k) s += job.cnt[k];
+  part[t] = s;
+  __syncthreads();
+  for (int off = 1; off < (int)blockDim.x; off <<= 1) {       // Hillis-Steele inclusive scan
+    int32_t v = (t >= off) ? part[t - off] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  int32_t run = part[t] - s;                                    // exclusive prefix of this chunk
+  for (int64_t k = b; k < e; ++k) { job.ptr[k] = run; run += job.cnt[k]; }
+  if (t == (int)blockDim.x - 1) job.ptr[job.n] = part[t];
+}
+
+__global__ void plan_fill_kernel(const int64_t* __restrict__ ei, int64_t N, int64_t E,
+                                 const int32_t* __restrict__ node2graph,
+                                 const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rowptr_t,
+                                 const int32_t* __restrict__ gptr, int32_t* deg_in, int32_t* deg_out,
+                                 int32_t* gcount, int32_t* col, int32_t* col_t, int32_t* gperm) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = i; e < E; e += stride) {
+    int64_t s = ei[e], d = ei[E + e];
+    if (s < 0 || s >= N || d < 0 || d >= N) continue;
+    // slots are claimed from the back of each row; rows are sorted by edge id afterwards
+    col[rowptr[d] + atomicSub(&deg_in[d], 1) - 1] = (int32_t)e;
+    col_t[rowptr_t[s] + atomicSub(&deg_out[s], 1) - 1] = (int32_t)e;
+  }
+  for (int64_t n = i; n < N; n += stride) {
+    int g = node2graph[n];
+    gperm[gptr[g] + atomicSub(&gcount[g], 1) - 1] = (int32_t)n;
+  }
+}
+
+__device__ __forceinline__ void insertion_sort(int32_t* a, int n) {
+  for (int i = 1; i < n; ++i) {
+    int32_t v = a[i];
+    int j = i - 1;
+    while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; --j; }
+    a[j + 1] = v;
+  }
+}
+
+__global__ void plan_rows_kernel(const int64_t* __restrict__ ei, const int64_t* __restrict__ ea,
+                                 int64_t N, int64_t E, int64_t G, const int32_t* __restrict__ rowptr,
+                                 const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ gptr,
+                                 int32_t* col, uint8_t* __restrict__ eattr, int32_t* col_t,
+                                 uint16_t* __restrict__ cnt, int32_t* gperm, int32_t* status) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t n = i; n < N; n += stride) {
+    int b = rowptr[n], e = rowptr[n + 1];
+    insertion_sort(col + b, e - b);                       // stable order == input edge order
+    int c[8] = {0, 0, 0, 0, 1, 1, 0, 0};                  // implicit self loop: type 4, direction 0
+    for (int p = b; p < e; ++p) {
+      int32_t id = col[p];
+      int t = (int)ea[2 * (int64_t)id], r = (int)ea[2 * (int64_t)id + 1];
+      t = min(max(t, 0), kNumBondType - 1);
+      r = min(max(r, 0), kNumBondDir - 1);
+      col[p] = (int32_t)ei[id];                           // source node of the in-edge
+      eattr[p] = (uint8_t)(t * 3 + r);
+      c[t]++; c[5 + r]++;
+    }
+    bool over = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { over |= c[k] > 65535; cnt[n * 8 + k] = (uint16_t)min(c[k], 65535); }
+    if (over) atomicOr(&status[0], ERR_DEGREE);
+    b = rowptr_t[n]; e = rowptr_t[n + 1];
+    insertion_sort(col_t + b, e - b);
+    for (int p = b; p < e; ++p) col_t[p] = (int32_t)ei[E + col_t[p]];   // destination of the out-edge
+  }
+  const bool sorted = (status[1] == 0);
+  for (int64_t g = i; g < G; g += stride) {
+    int b = gptr[g], e = gptr[g + 1];
+    if (sorted) { for (int p = b; p < e; ++p) gperm[p] = p; }            // PyG batches: identity
+    else insertion_sort(gperm + b, e - b);
+  }
+}
+
+}  // namespace molclr
+
+using namespace molclr;
+
+extern "C" size_t molclr_plan_workspace_bytes(int64_t N, int64_t E, int64_t G) {
+  (void)E;
+  return sizeof(int32_t) * (size_t)(2 * N + G + 16);
+}
+
+extern "C" int molclr_plan_build(const int64_t* x, const int64_t* edge_index, const int64_t* edge_attr,
+                                 const int64_t* batch, int64_t N, int64_t E, int64_t G, int32_t* xpacked,
+                                 int32_t* node2graph, int32_t* rowptr, int32_t* col, uint8_t* eattr,
+                                 int32_t* rowptr_t, int32_t* col_t, uint16_t* cnt, int32_t* gptr,
+                                 int32_t* gperm, void* workspace, size_t workspace_bytes, int32_t* status,
+                                 cudaStream_t stream) {
+  MOLCLR_REQUIRE(N >= 0 && E >= 0 && G >= 0, "plan_build: negative size");
+  MOLCLR_REQUIRE(N < (1ll << 31) - 2 && E < (1ll << 31) - 2, "plan_build: N/E exceed int32 CSR range");
+  MOLCLR_REQUIRE(workspace_bytes >= molclr_plan_workspace_bytes(N, E, G), "plan_build: workspace too small");
+  int32_t* deg_in = reinterpret_cast<int32_t*>(workspace);
+  int32_t* deg_out = deg_in + N;
+  int32_t* gcount = deg_out + N;
+  cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(int32_t) * (size_t)(2 * N + G), stream);
+  if (e != cudaSuccess) return cuda_fail(e, "plan_build memset");
+  e = cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), stream);
+  if (e != cudaSuccess) return cuda_fail(e, "plan_build memset status");
+  const int threads = 256;
+  int64_t work = N > E ? N : E;
+  int blocks = (int)((work + threads - 1) / threads);
+  blocks = blocks < 1 ? 1 : (blocks > 8 * sm_count() ? 8 * sm_count() : blocks);
+  plan_count_kernel<<<blocks, threads, 0, stream>>>(x, edge_index, edge_attr, batch, N, E, G, xpacked,
+                                                    node2graph, deg_in, deg_out, gcount, status);
+  MOLCLR_CHECK_LAUNCH("plan_count");
+  ScanJobs jobs;
+  jobs.j[0] = {deg_in, rowptr, N};
+  jobs.j[1] = {deg_out, rowptr_t, N};
+  jobs.j[2] = {gcount, gptr, G};
+  plan_scan_kernel<<<3, 1024, 0, stream>>>(jobs);
+  MOLCLR_CHECK_LAUNCH("plan_scan");
+  plan_fill_kernel<<<blocks, threads, 0, stream>>>(edge_index, N, E, node2graph, rowptr, rowptr_t, gptr,
+                                                   deg_in, deg_out, gcount, col, col_t, gperm);
+  MOLCLR_CHECK_LAUNCH("plan_fill");
+  int64_t work2 = N > G ? N : G;
+  int blocks2 = (int)((work2 + threads - 1) / threads);
+  blocks2 = blocks2 < 1 ? 1 : blocks2;
+  plan_rows_kernel<<<blocks2, threads, 0, stream>>>(edge_index, edge_attr, N, E, G, rowptr, rowptr_t, gptr,
+                                                    col, eattr, col_t, cnt, gperm, status);
+  MOLCLR_CHECK_LAUNCH("plan_rows");
+  return 0;
+}

@@ -1,0 +1,800 @@
+// Row-wise (HBM-bound) kernels of the encoder: node embedding, GINE neighbour aggregation
+// forward/backward, BatchNorm finalisation / backward apply, segmented pooling, table gradients.
+//
+// All of them use one mapping: a warp owns a node (or graph) row of D fp32 features and its lanes
+// stride over the D/4 float4 chunks, so every global access is a coalesced 128-bit load/store and
+// a row is summed in a fixed order without atomics (deterministic, and bit-exact against the CPU
+// reference order where that matters).  Grids are persistent: (#SM x resident CTAs) blocks that
+// grid-stride over rows.
+#include "common.cuh"
+#include "molclr_b200.h"
+
+namespace molclr {
+
+constexpr int kRowThreads = 256;
+constexpr int kRowWarps = kRowThreads / 32;
+
+template <typename K>
+static int persistent_grid(K kernel, int threads, size_t smem, int64_t rows_per_block_iter, int64_t rows) {
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+  if (per_sm < 1) per_sm = 1;
+  int64_t want = (rows + rows_per_block_iter - 1) / rows_per_block_iter;
+  int64_t cap = (int64_t)per_sm * sm_count();
+  int64_t g = want < cap ? want : cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+#define NCH_DISPATCH(D4, ...)                                                    \
+  do {                                                                           \
+    if ((D4) <= 32) { constexpr int NCH = 1; __VA_ARGS__; }                             \
+    else if ((D4) <= 64) { constexpr int NCH = 2; __VA_ARGS__; }                        \
+    else if ((D4) <= 96) { constexpr int NCH = 3; __VA_ARGS__; }                        \
+    else if ((D4) <= 128) { constexpr int NCH = 4; __VA_ARGS__; }                       \
+    else { set_error("feature width %d not supported (D <= 512, D %% 4 == 0)", 4 * (D4)); return -2; } \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Node embedding  h0[n] = E1[x[n,0]] + E2[x[n,1]]            (ginet_molclr.py:103, gcn_molclr.py:144)
+// ------------------------------------------------------------------------------------------------
+template <int NCH>
+__global__ void __launch_bounds__(kRowThreads) embed_nodes_fwd_kernel(
+    const int32_t* __restrict__ xpacked, const float* __restrict__ E1, const float* __restrict__ E2,
+    int N, int D, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, D4 = D >> 2;
+  const int warp = blockIdx.x * kRowWarps + (threadIdx.x >> 5), nwarps = gridDim.x * kRowWarps;
+  for (int n = warp; n < N; n += nwarps) {
+    const int xp = xpacked[n];
+    const float* r1 = E1 + (size_t)(xp & 0xff) * D;
+    const float* r2 = E2 + (size_t)(xp >> 8) * D;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int q = lane + 32 * j;
+      if (q < D4) st_f4(out + (size_t)n * D + 4 * q, f4_add(ldg_f4(r1 + 4 * q), ldg_f4(r2 + 4 * q)));
+    }
+  }
+}
+
+// Backward of the node embedding: dE1[t] = sum_{n: x[n,0]=t} g[n], dE2[c] likewise.  Each block
+// accumulates a private (119+3) x D table in shared memory (spread-address shared atomics), then
+// writes it as one partial; partials are summed in block order by reduce_partials.
+__global__ void __launch_bounds__(512) embed_nodes_bwd_kernel(
+    const int32_t* __restrict__ xpacked, const float* __restrict__ g, int N, int D,
+    float* __restrict__ partials) {
+  extern __shared__ float tab[];                     // [(119+3) * D]
+  const int rows = kNumAtomType + kNumChirality;
+  for (int i = threadIdx.x; i < rows * D; i += blockDim.x) tab[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int warp = blockIdx.x * wpb + (threadIdx.x >> 5), nwarps = gridDim.x * wpb;
+  for (int n = warp; n < N; n += nwarps) {
+    const int xp = xpacked[n];
+    float* t1 = tab + (xp & 0xff) * D;
+    float* t2 = tab + (kNumAtomType + (xp >> 8)) * D;
+    const float* gr = g + (size_t)n * D;
+    for (int f = lane; f < D; f += 32) {
+      const float v = __ldg(gr + f);
+      atomicAdd(t1 + f, v);
+      atomicAdd(t2 + f, v);
+    }
+  }
+  __syncthreads();
+  float* dst = partials + (size_t)blockIdx.x * rows * D;
+  for (int i = threadIdx.x; i < rows * D; i += blockDim.x) dst[i] = tab[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// GINE neighbour aggregation, forward.
+//   a[i] = sum_{e in row i, input order} ( f(src[col[e]]) + (B1[t_e] + B2[d_e]) )  +  ( f(src[i]) + (B1[4] + B2[0]) )
+// (ginet_molclr.py:29-44 + PyG propagate/scatter-add).  f is the identity for layer 0 and the
+// previous layer's BatchNorm + ReLU otherwise (ginet_molclr.py:107-111), applied on the fly from
+// per-feature (scale, shift) so the normalised activations never round-trip through HBM.
+// Both bond tables are folded into one 15-row table staged in shared memory.
+// ------------------------------------------------------------------------------------------------
+template <int NCH, bool HAS_BN>
+__global__ void __launch_bounds__(kRowThreads) gine_aggregate_fwd_kernel(
+    const float* __restrict__ src, const float* __restrict__ coef, int relu,
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const uint8_t* __restrict__ eattr,
+    const float* __restrict__ B1, const float* __restrict__ B2, int N, int D, float* __restrict__ out,
+    int round_out) {
+  extern __shared__ float4 sm4[];
+  const int D4 = D >> 2;
+  float4* ee = sm4;                       // [15][D4]
+  float4* sc = ee + kNumEdgeClass * D4;   // [D4] scale
+  float4* sh = sc + D4;                   // [D4] shift
+  for (int i = threadIdx.x; i < kNumEdgeClass * D4; i += blockDim.x) {
+    const int cls = i / D4, q = i - cls * D4;
+    ee[i] = f4_add(ldg_f4(B1 + (size_t)(cls / 3) * D + 4 * q), ldg_f4(B2 + (size_t)(cls % 3) * D + 4 * q));
+  }
+  if (HAS_BN)
+    for (int i = threadIdx.x; i < D4; i += blockDim.x) { sc[i] = ldg_f4(coef + 4 * i); sh[i] = ldg_f4(coef + D + 4 * i); }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * kRowWarps + (threadIdx.x >> 5), nwarps = gridDim.x * kRowWarps;
+  auto act = [&](float4 v, int q) -> float4 {
+    if (HAS_BN) {
+      const float4 s = sc[q], b = sh[q];
+      v.x = fmaf(v.x, s.x, b.x); v.y = fmaf(v.y, s.y, b.y); v.z = fmaf(v.z, s.z, b.z); v.w = fmaf(v.w, s.w, b.w);
+      if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    }
+    return v;
+  };
+  for (int i = warp; i < N; i += nwarps) {
+    const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
+    float4 acc[NCH], self[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int q = lane + 32 * j;
+      acc[j] = f4_zero();
+      self[j] = (q < D4) ? ldg_f4(src + (size_t)i * D + 4 * q) : f4_zero();
+    }
+    for (int e = beg; e < end; e += 2) {                 // two neighbour rows in flight per step
+      const bool two = (e + 1 < end);
+      const int s0 = __ldg(col + e), a0 = __ldg(eattr + e);
+      const int s1 = two ? __ldg(col + e + 1) : s0, a1 = two ? __ldg(eattr + e + 1) : a0;
+      float4 v0[NCH], v1[NCH];
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const int q = lane + 32 * j;
+        v0[j] = (q < D4) ? ldg_f4(src + (size_t)s0 * D + 4 * q) : f4_zero();
+        v1[j] = (q < D4 && two) ? ldg_f4(src + (size_t)s1 * D + 4 * q) : f4_zero();
+      }
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const int q = lane + 32 * j;
+        if (q < D4) {
+          acc[j] = f4_add(acc[j], f4_add(act(v0[j], q), ee[a0 * D4 + q]));
+          if (two) acc[j] = f4_add(acc[j], f4_add(act(v1[j], q), ee[a1 * D4 + q]));
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int q = lane + 32 * j;
+      if (q < D4) {
+        float4 r = f4_add(acc[j], f4_add(act(self[j], q), ee[kSelfLoopAttr * D4 + q]));   // self loop LAST
+        if (round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
+        st_f4(out + (size_t)i * D + 4 * q, r);
+      }
+    }
+  }
+}
+
+// Writes per-lane accumulators `acc[NV][NCH]` of every warp to shared memory and reduces them over
+// the block's warps in warp order; block partial goes to partials[blockIdx.x][NV][D].
+template <int NCH, int NV>
+__device__ __forceinline__ void block_reduce_rows(float4 (&acc)[NV][NCH], float4* red /* [kRowWarps][NV][D4] */,
+                                                  int D4, float* __restrict__ partials) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int q = lane + 32 * j;
+      if (q < D4) red[(w * NV + v) * D4 + q] = acc[v][j];
+    }
+  __syncthreads();
+  float* dst = partials + (size_t)blockIdx.x * NV * D4 * 4;
+  for (int i = threadIdx.x; i < NV * D4; i += blockDim.x) {
+    float4 s = red[i];
+    for (int ww = 1; ww < kRowWarps; ++ww) s = f4_add(s, red[ww * NV * D4 + i]);
+    st_f4(dst + 4 * i, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GINE aggregation, backward (transposed gather over the source-sorted CSR):
+//   g_h[j] = sum_{e: src_e = j} g_a[dst_e] + g_a[j]
+// fused with the backward of the previous layer's ReLU and the BatchNorm batch statistics:
+//   g_y[j] = g_h[j] * [z[j]*scale + shift > 0];  s1 += g_y;  s2 += g_y * xhat,  xhat = (z - mean) * invstd
+// MODE 0: plain (layer 0: g_h feeds the node-embedding backward).  MODE 1: fused as above.
+// ------------------------------------------------------------------------------------------------
+template <int NCH, int MODE>
+__global__ void __launch_bounds__(kRowThreads) gine_aggregate_bwd_kernel(
+    const float* __restrict__ ga, const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ col_t,
+    const float* __restrict__ z, const float* __restrict__ coef, int relu, int N, int D,
+    float* __restrict__ gy, float* __restrict__ partials) {
+  extern __shared__ float4 sm4[];
+  const int D4 = D >> 2;
+  float4* cf = sm4;                          // [4][D4] scale, shift, mean, invstd
+  float4* red = sm4 + 4 * D4;                // [kRowWarps][2][D4]
+  if (MODE == 1) {
+    for (int i = threadIdx.x; i < 4 * D4; i += blockDim.x) cf[i] = ldg_f4(coef + 4 * i);
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * kRowWarps + (threadIdx.x >> 5), nwarps = gridDim.x * kRowWarps;
+  float4 st[2][NCH];
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) { st[0][j] = f4_zero(); st[1][j] = f4_zero(); }
+  for (int i = warp; i < N; i += nwarps) {
+    const int beg = __ldg(rowptr_t + i), end = __ldg(rowptr_t + i + 1);
+    float4 acc[NCH], zz[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int q = lane + 32 * j;
+      acc[j] = f4_zero();
+      zz[j] = (MODE == 1 && q < D4) ? ld_stream_f4(z + (size_t)i * D + 4 * q) : f4_zero();
+    }
+    for (int e = beg; e < end; e += 2) {
+      const bool two = (e + 1 < end);
+      const int d0 = __ldg(col_t + e), d1 = two ? __ldg(col_t + e + 1) : d0;
+      float4 v0[NCH], v1[NCH];
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const int q = lane + 32 * j;
+        v0[j] = (q < D4) ? ldg_f4(ga + (size_t)d0 * D + 4 * q) : f4_zero();
+        v1[j] = (q < D4 && two) ? ldg_f4(ga + (size_t)d1 * D + 4 * q) : f4_zero();
+      }
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) acc[j] = f4_add(acc[j], f4_add(v0[j], v1[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int q = lane + 32 * j;
+      if (q < D4) {
+        float4 r = f4_add(acc[j], ldg_f4(ga + (size_t)i * D + 4 * q));       // self loop
+        if (MODE == 1) {
+          const float4 s = cf[q], b = cf[D4 + q], m = cf[2 * D4 + q], is = cf[3 * D4 + q], zv = zz[j];
+          if (relu) {
+            if (!(fmaf(zv.x, s.x, b.x) > 0.f)) r.x = 0.f;
+            if (!(fmaf(zv.y, s.y, b.y) > 0.f)) r.y = 0.f;
+            if (!(fmaf(zv.z, s.z, b.z) > 0.f)) r.z = 0.f;
+            if (!(fmaf(zv.w, s.w, b.w) > 0.f)) r.w = 0.f;
+          }
+          st[0][j] = f4_add(st[0][j], r);
+          st[1][j].x = fmaf(r.x, (zv.x - m.x) * is.x, st[1][j].x);
+          st[1][j].y = fmaf(r.y, (zv.y - m.y) * is.y, st[1][j].y);
+          st[1][j].z = fmaf(r.z, (zv.z - m.z) * is.z, st[1][j].z);
+          st[1][j].w = fmaf(r.w, (zv.w - m.w) * is.w, st[1][j].w);
+        }
+        st_f4(gy + (size_t)i * D + 4 * q, r);
+      }
+    }
+  }
+  if (MODE == 1) block_reduce_rows<NCH, 2>(st, red, D4, partials);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bond-embedding table gradients.  dB1[t] = sum_i cnt[i][t] * g_a[i], dB2[d] = sum_i cnt[i][5+d] * g_a[i]
+// where cnt[i][.] counts node i's in-edges per bond type / direction (self loop included), i.e. the
+// E' x D embedding_dense_backward of the reference collapsed to one pass over g_a.
+// ------------------------------------------------------------------------------------------------
+template <int NCH>
+__global__ void __launch_bounds__(kRowThreads) edge_table_grad_kernel(
+    const float* __restrict__ ga, const uint16_t* __restrict__ cnt, int N, int D, float* __restrict__ partials) {
+  extern __shared__ float4 sm4[];            // [kRowWarps][8][D4]
+  const int D4 = D >> 2, lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * kRowWarps + (threadIdx.x >> 5), nwarps = gridDim.x * kRowWarps;
+  float4 acc[8][NCH];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) acc[k][j] = f4_zero();
+  for (int i = warp; i < N; i += nwarps) {
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(cnt) + i);
+    const float w[8] = {(float)(c.x & 0xffff), (float)(c.x >> 16), (float)(c.y & 0xffff), (float)(c.y >> 16),
+                        (float)(c.z & 0xffff), (float)(c.z >> 16), (float)(c.w & 0xffff), (float)(c.w >> 16)};
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int q = lane + 32 * j;
+      if (q < D4) {
+        const float4 g = ld_stream_f4(ga + (size_t)i * D + 4 * q);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          acc[k][j].x = fmaf(w[k], g.x, acc[k][j].x); acc[k][j].y = fmaf(w[k], g.y, acc[k][j].y);
+          acc[k][j].z = fmaf(w[k], g.z, acc[k][j].z); acc[k][j].w = fmaf(w[k], g.w, acc[k][j].w);
+        }
+      }
+    }
+  }
+  block_reduce_rows<NCH, 8>(acc, sm4, D4, partials);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Deterministic reduction of partial rows:  out[c] (+)= scale * sum_p partials[p][c], p in order.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ partials, int P, int len,
+                                                               float scale, int accumulate, float* __restrict__ out) {
+  __shared__ float red[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (c < len)
+    for (int p = threadIdx.y; p < P; p += 32) s += partials[(size_t)p * len + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < len) {
+    float t = red[0][threadIdx.x];
+    for (int k = 1; k < 32; ++k) t += red[k][threadIdx.x];
+    t *= scale;
+    out[c] = accumulate ? out[c] + t : t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm1d, training mode (ginet_molclr.py:107; torch.nn.BatchNorm1d defaults eps=1e-5,
+// momentum=0.1).  The producing GEMM epilogue leaves per-128-row-tile column (mean, M2); this
+// merges them (Chan et al.) into batch mean / biased variance, writes the per-feature
+// coefficients the consumers use, and updates the running statistics exactly once.
+//   coef[0]=scale=gamma*invstd  coef[1]=shift=beta-mean*scale  coef[2]=mean  coef[3]=invstd
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) bn_fwd_finalize_kernel(
+    const float* __restrict__ tile_stats /* [T][2][D] */, int T, int tile_rows, int N, int D,
+    const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean, float* running_var,
+    long long* num_batches_tracked, float momentum, float eps, float* __restrict__ coef) {
+  __shared__ double s_n[16][33], s_mean[16][33], s_m2[16][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double n = 0.0, mean = 0.0, m2 = 0.0;
+  if (c < D) {
+    for (int t = threadIdx.y; t < T; t += 16) {
+      const int rows = min(tile_rows, N - t * tile_rows);
+      const double nb = rows, mb = tile_stats[((size_t)t * 2) * D + c], qb = tile_stats[((size_t)t * 2 + 1) * D + c];
+      const double tot = n + nb, delta = mb - mean;
+      mean += delta * (nb / tot);
+      m2 += qb + delta * delta * (n * nb / tot);
+      n = tot;
+    }
+  }
+  s_n[threadIdx.y][threadIdx.x] = n; s_mean[threadIdx.y][threadIdx.x] = mean; s_m2[threadIdx.y][threadIdx.x] = m2;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < D) {
+    for (int k = 1; k < 16; ++k) {
+      const double nb = s_n[k][threadIdx.x];
+      if (nb == 0.0) continue;
+      const double tot = n + nb, delta = s_mean[k][threadIdx.x] - mean;
+      mean += delta * (nb / tot);
+      m2 += s_m2[k][threadIdx.x] + delta * delta * (n * nb / tot);
+      n = tot;
+    }
+    const double var = (n > 0.0) ? m2 / n : 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float scale = gamma[c] * invstd;
+    coef[c] = scale;
+    coef[D + c] = beta[c] - (float)mean * scale;
+    coef[2 * D + c] = (float)mean;
+    coef[3 * D + c] = invstd;
+    if (running_mean) {
+      const double unbiased = (n > 1.0) ? m2 / (n - 1.0) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  }
+  if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0) *num_batches_tracked += 1;
+}
+
+// Eval mode (molclr.py:163): coefficients from the running statistics.
+__global__ void bn_eval_coef_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                    float eps, int D, float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  const float is = 1.0f / sqrtf(running_var[c] + eps);
+  const float scale = gamma[c] * is;
+  coef[c] = scale;
+  coef[D + c] = beta[c] - running_mean[c] * scale;
+  coef[2 * D + c] = running_mean[c];
+  coef[3 * D + c] = is;
+}
+
+// BatchNorm backward, step 1: reduce the (s1, s2) partials and emit
+//   dgamma = s2, dbeta = s1, and the apply coefficients so that  g_z = k1*g_y + A + B*z :
+//   k1 = gamma*invstd,  A = -k1*s1/N + k1*(s2/N)*invstd*mean,  B = -k1*(s2/N)*invstd
+// In eval mode (use_batch_stats=0) BN is a fixed affine map: g_z = k1*g_y.
+__global__ void __launch_bounds__(512) bn_bwd_finalize_kernel(
+    const float* __restrict__ partials /* [P][2][D] */, int P, int N, int D, const float* __restrict__ gamma,
+    const float* __restrict__ coef, int use_batch_stats, float* __restrict__ dgamma, float* __restrict__ dbeta,
+    float* __restrict__ bcoef /* [3][D] */) {
+  __shared__ float r1[16][33], r2[16][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s1 = 0.f, s2 = 0.f;
+  if (c < D)
+    for (int p = threadIdx.y; p < P; p += 16) { s1 += partials[((size_t)p * 2) * D + c]; s2 += partials[((size_t)p * 2 + 1) * D + c]; }
+  r1[threadIdx.y][threadIdx.x] = s1; r2[threadIdx.y][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < D) {
+    for (int k = 1; k < 16; ++k) { s1 += r1[k][threadIdx.x]; s2 += r2[k][threadIdx.x]; }
+    dgamma[c] = s2; dbeta[c] = s1;
+    const float mean = coef[2 * D + c], invstd = coef[3 * D + c];
+    const float k1 = gamma[c] * invstd;
+    if (use_batch_stats) {
+      const float c1 = s1 / (float)N, c2 = s2 / (float)N;
+      bcoef[c] = k1;
+      bcoef[D + c] = -k1 * c1 + k1 * c2 * invstd * mean;
+      bcoef[2 * D + c] = -k1 * c2 * invstd;
+    } else {
+      bcoef[c] = k1; bcoef[D + c] = 0.f; bcoef[2 * D + c] = 0.f;
+    }
+  }
+}
+
+// BatchNorm backward, step 2 (elementwise): g_z = k1*g_y + A + B*z, written tf32-rounded because g_z
+// is only ever a tensor-core operand; also leaves per-block column sums of g_z (the bias gradient
+// of the Linear in front of the BN).  SRC 0: g_y from memory.  SRC 1: g_y[n] = g_p[graph(n)] * w[graph(n)]
+// (the backward of global_mean/add_pool feeding the last layer's BN, ginet_molclr.py:113).
+template <int NCH, int SRC>
+__global__ void __launch_bounds__(kRowThreads) bn_bwd_apply_kernel(
+    const float* __restrict__ gy, const float* __restrict__ gp, const int32_t* __restrict__ node2graph,
+    const int32_t* __restrict__ gptr, int pool_mean, const float* __restrict__ z, const float* __restrict__ bcoef,
+    int N, int D, float* __restrict__ gz, float* __restrict__ partials) {
+  extern __shared__ float4 sm4[];
+  const int D4 = D >> 2;
+  float4* cf = sm4;                 // [3][D4]
+  float4* red = sm4 + 3 * D4;       // [kRowWarps][1][D4]
+  for (int i = threadIdx.x; i < 3 * D4; i += blockDim.x) cf[i] = ldg_f4(bcoef + 4 * i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * kRowWarps + (threadIdx.x >> 5), nwarps = gridDim.x * kRowWarps;
+  float4 st[1][NCH];
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) st[0][j] = f4_zero();
+  for (int i = warp; i < N; i += nwarps) {
+    float w = 1.f;
+    const float* grow;
+    if (SRC == 1) {
+      const int g = __ldg(node2graph + i);
+      if (pool_mean) w = 1.f / (float)max(__ldg(gptr + g + 1) - __ldg(gptr + g), 1);
+      grow = gp + (size_t)g * D;
+    } else {
+      grow = gy + (size_t)i * D;
+    }
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int q = lane + 32 * j;
+      if (q < D4) {
+        float4 g = (SRC == 1) ? ldg_f4(grow + 4 * q) : ld_stream_f4(grow + 4 * q);
+        const float4 zv = ld_stream_f4(z + (size_t)i * D + 4 * q);
+        const float4 k1 = cf[q], A = cf[D4 + q], B = cf[2 * D4 + q];
+        if (SRC == 1) { g.x *= w; g.y *= w; g.z *= w; g.w *= w; }
+        float4 r;
+        r.x = fmaf(k1.x, g.x, fmaf(B.x, zv.x, A.x)); r.y = fmaf(k1.y, g.y, fmaf(B.y, zv.y, A.y));
+        r.z = fmaf(k1.z, g.z, fmaf(B.z, zv.z, A.z)); r.w = fmaf(k1.w, g.w, fmaf(B.w, zv.w, A.w));
+        st[0][j] = f4_add(st[0][j], r);
+        r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w);
+        st_f4(gz + (size_t)i * D + 4 * q, r);
+      }
+    }
+  }
+  block_reduce_rows<NCH, 1>(st, red, D4, partials);
+}
+
+// ------------------------------------------------------------------------------------------------
+// global_mean_pool / global_add_pool (ginet_molclr.py:83-88,113) as a segmented reduction fused with
+// the last layer's BatchNorm apply:  p[g] = w_g * sum_{n in graph g, node order} (z[n]*scale + shift)
+// ------------------------------------------------------------------------------------------------
+template <int NCH>
+__global__ void __launch_bounds__(kRowThreads) pool_fwd_kernel(
+    const float* __restrict__ z, const float* __restrict__ coef, int relu, const int32_t* __restrict__ gptr,
+    const int32_t* __restrict__ gperm, int pool_mean, int G, int D, float* __restrict__ out, int round_out) {
+  extern __shared__ float4 sm4[];
+  const int D4 = D >> 2;
+  float4* sc = sm4; float4* sh = sm4 + D4;
+  for (int i = threadIdx.x; i < D4; i += blockDim.x) { sc[i] = ldg_f4(coef + 4 * i); sh[i] = ldg_f4(coef + D + 4 * i); }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * kRowWarps + (threadIdx.x >> 5), nwarps = gridDim.x * kRowWarps;
+  for (int g = warp; g < G; g += nwarps) {
+    const int beg = __ldg(gptr + g), end = __ldg(gptr + g + 1);
+    float4 acc[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) acc[j] = f4_zero();
+    for (int p = beg; p < end; ++p) {
+      const int n = __ldg(gperm + p);
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const int q = lane + 32 * j;
+        if (q < D4) {
+          float4 v = ld_stream_f4(z + (size_t)n * D + 4 * q);
+          const float4 s = sc[q], b = sh[q];
+          v.x = fmaf(v.x, s.x, b.x); v.y = fmaf(v.y, s.y, b.y); v.z = fmaf(v.z, s.z, b.z); v.w = fmaf(v.w, s.w, b.w);
+          if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          acc[j] = f4_add(acc[j], v);
+        }
+      }
+    }
+    const float cntf = (float)max(end - beg, 1);             // count.clamp(min=1)
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int q = lane + 32 * j;
+      if (q < D4) {
+        float4 r = acc[j];
+        if (pool_mean) { r.x /= cntf; r.y /= cntf; r.z /= cntf; r.w /= cntf; }
+        if (round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
+        st_f4(out + (size_t)g * D + 4 * q, r);
+      }
+    }
+  }
+}
+
+// Backward of the pool into the last layer's BatchNorm statistics:
+//   g_y[n] = g_p[graph(n)] * w,  s1 += g_y,  s2 += g_y * xhat[n]      (g_y is never materialised)
+template <int NCH>
+__global__ void __launch_bounds__(kRowThreads) pool_bwd_stats_kernel(
+    const float* __restrict__ gp, const int32_t* __restrict__ node2graph, const int32_t* __restrict__ gptr,
+    int pool_mean, const float* __restrict__ z, const float* __restrict__ coef, int N, int D,
+    float* __restrict__ partials) {
+  extern __shared__ float4 sm4[];
+  const int D4 = D >> 2;
+  float4* cf = sm4;                 // mean, invstd
+  float4* red = sm4 + 2 * D4;
+  for (int i = threadIdx.x; i < 2 * D4; i += blockDim.x) cf[i] = ldg_f4(coef + 2 * D + 4 * i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * kRowWarps + (threadIdx.x >> 5), nwarps = gridDim.x * kRowWarps;
+  float4 st[2][NCH];
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) { st[0][j] = f4_zero(); st[1][j] = f4_zero(); }
+  for (int i = warp; i < N; i += nwarps) {
+    const int g = __ldg(node2graph + i);
+    const float w = pool_mean ? 1.f / (float)max(__ldg(gptr + g + 1) - __ldg(gptr + g), 1) : 1.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int q = lane + 32 * j;
+      if (q < D4) {
+        float4 r = ldg_f4(gp + (size_t)g * D + 4 * q);
+        const float4 zv = ld_stream_f4(z + (size_t)i * D + 4 * q), m = cf[q], is = cf[D4 + q];
+        r.x *= w; r.y *= w; r.z *= w; r.w *= w;
+        st[0][j] = f4_add(st[0][j], r);
+        st[1][j].x = fmaf(r.x, (zv.x - m.x) * is.x, st[1][j].x); st[1][j].y = fmaf(r.y, (zv.y - m.y) * is.y, st[1][j].y);
+        st[1][j].z = fmaf(r.z, (zv.z - m.z) * is.z, st[1][j].z); st[1][j].w = fmaf(r.w, (zv.w - m.w) * is.w, st[1][j].w);
+      }
+    }
+  }
+  block_reduce_rows<NCH, 2>(st, red, D4, partials);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small elementwise helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = round_tf32(src[i]);
+}
+
+// F.normalize(z, dim=1) (molclr.py:63-64; eps = 1e-12): y = z / max(||z||, eps).  One warp per row.
+__global__ void l2_normalize_fwd_kernel(const float* __restrict__ z, int R, int C, float eps, float* __restrict__ y,
+                                        float* __restrict__ inv_norm) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= R) return;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) { const float v = z[(size_t)row * C + c]; s = fmaf(v, v, s); }
+  s = warp_sum(s);
+  const float inv = 1.f / fmaxf(sqrtf(s), eps);
+  for (int c = lane; c < C; c += 32) y[(size_t)row * C + c] = z[(size_t)row * C + c] * inv;
+  if (lane == 0 && inv_norm) inv_norm[row] = inv;
+}
+
+// backward: g_z = (g_y - y * <g_y, y>) * inv_norm          (rows with ||z|| < eps: g_z = g_y * inv_norm)
+__global__ void l2_normalize_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ y,
+                                        const float* __restrict__ inv_norm, int R, int C, float eps,
+                                        float* __restrict__ gz) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= R) return;
+  float d = 0.f;
+  for (int c = lane; c < C; c += 32) d = fmaf(gy[(size_t)row * C + c], y[(size_t)row * C + c], d);
+  d = warp_sum(d);
+  const float inv = inv_norm[row];
+  if (inv >= 1.f / eps) d = 0.f;          // clamped norm: y = z / eps is linear in z
+  for (int c = lane; c < C; c += 32) gz[(size_t)row * C + c] = (gy[(size_t)row * C + c] - y[(size_t)row * C + c] * d) * inv;
+}
+
+}  // namespace molclr
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using namespace molclr;
+
+#define REQUIRE_D(D) MOLCLR_REQUIRE((D) > 0 && (D) % 4 == 0 && (D) <= 512, "feature width D=%d must be a multiple of 4, <= 512", (int)(D))
+
+extern "C" int molclr_embed_nodes_fwd(const int32_t* xpacked, const float* E1, const float* E2, int64_t N, int D,
+                                      float* out, cudaStream_t stream) {
+  REQUIRE_D(D);
+  if (N == 0) return 0;
+  NCH_DISPATCH(D / 4, {
+    auto k = embed_nodes_fwd_kernel<NCH>;
+    k<<<persistent_grid(k, kRowThreads, 0, kRowWarps, N), kRowThreads, 0, stream>>>(xpacked, E1, E2, (int)N, D, out);
+  });
+  MOLCLR_CHECK_LAUNCH("embed_nodes_fwd");
+  return 0;
+}
+
+extern "C" int molclr_reduce_partials(const float* partials, int P, int len, float scale, int accumulate, float* out,
+                                      cudaStream_t stream) {
+  if (len == 0) return 0;
+  reduce_partials_kernel<<<(len + 31) / 32, dim3(32, 32), 0, stream>>>(partials, P, len, scale, accumulate, out);
+  MOLCLR_CHECK_LAUNCH("reduce_partials");
+  return 0;
+}
+
+extern "C" int molclr_embed_nodes_bwd_blocks(int D) {
+  (void)D;
+  return sm_count();
+}
+
+extern "C" int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, int64_t N, int D, float* dE, float* partials,
+                                      cudaStream_t stream) {
+  REQUIRE_D(D);
+  const int rows = kNumAtomType + kNumChirality;
+  const size_t smem = (size_t)rows * D * sizeof(float);
+  MOLCLR_REQUIRE(smem <= 200 * 1024, "embed_nodes_bwd: D=%d too wide for the shared-memory table", D);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(embed_nodes_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  const int blocks = molclr_embed_nodes_bwd_blocks(D);
+  embed_nodes_bwd_kernel<<<blocks, 512, smem, stream>>>(xpacked, g, (int)N, D, partials);
+  MOLCLR_CHECK_LAUNCH("embed_nodes_bwd");
+  return molclr_reduce_partials(partials, blocks, rows * D, 1.f, 0, dE, stream);
+}
+
+extern "C" int molclr_gine_aggregate_fwd(const float* src, const float* bn_coef, int relu, const int32_t* rowptr,
+                                         const int32_t* col, const uint8_t* eattr, const float* B1, const float* B2,
+                                         int64_t N, int D, float* out, int round_tf32_out, cudaStream_t stream) {
+  REQUIRE_D(D);
+  if (N == 0) return 0;
+  const size_t smem = (size_t)(kNumEdgeClass + 2) * D * sizeof(float);
+  NCH_DISPATCH(D / 4, {
+    if (bn_coef) {
+      auto k = gine_aggregate_fwd_kernel<NCH, true>;
+      k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
+          src, bn_coef, relu, rowptr, col, eattr, B1, B2, (int)N, D, out, round_tf32_out);
+    } else {
+      auto k = gine_aggregate_fwd_kernel<NCH, false>;
+      k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
+          src, nullptr, 0, rowptr, col, eattr, B1, B2, (int)N, D, out, round_tf32_out);
+    }
+  });
+  MOLCLR_CHECK_LAUNCH("gine_aggregate_fwd");
+  return 0;
+}
+
+// Number of partial rows the persistent row-wise kernels with block partials emit (upper bound on
+// their grid): callers size `partials` as [molclr_rowwise_max_blocks()][NV][D].
+extern "C" int molclr_rowwise_max_blocks(void) { return 8 * sm_count(); }
+
+extern "C" int molclr_gine_aggregate_bwd(const float* ga, const int32_t* rowptr_t, const int32_t* col_t, const float* z_prev,
+                                         const float* bn_coef, int relu, int64_t N, int D, float* gy, float* partials,
+                                         int* num_partials, cudaStream_t stream) {
+  REQUIRE_D(D);
+  if (num_partials) *num_partials = 0;
+  if (N == 0) return 0;
+  const int D4 = D / 4;
+  NCH_DISPATCH(D4, {
+    if (z_prev) {
+      const size_t smem = (size_t)(4 + 2 * kRowWarps) * D * sizeof(float);
+      auto k = gine_aggregate_bwd_kernel<NCH, 1>;
+      const int grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
+      k<<<grid, kRowThreads, smem, stream>>>(ga, rowptr_t, col_t, z_prev, bn_coef, relu, (int)N, D, gy, partials);
+      if (num_partials) *num_partials = grid;
+    } else {
+      auto k = gine_aggregate_bwd_kernel<NCH, 0>;
+      k<<<persistent_grid(k, kRowThreads, 0, kRowWarps, N), kRowThreads, 0, stream>>>(ga, rowptr_t, col_t, nullptr, nullptr, 0,
+                                                                                        (int)N, D, gy, nullptr);
+    }
+  });
+  MOLCLR_CHECK_LAUNCH("gine_aggregate_bwd");
+  return 0;
+}
+
+extern "C" int molclr_edge_table_grad(const float* ga, const uint16_t* cnt, int64_t N, int D, float* dB /* [8][D]: 5 type rows then 3 direction rows */,
+                                      float* partials, cudaStream_t stream) {
+  REQUIRE_D(D);
+  const size_t smem = (size_t)kRowWarps * 8 * D * sizeof(float);
+  int grid = 1;
+  NCH_DISPATCH(D / 4, {
+    auto k = edge_table_grad_kernel<NCH>;
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_set = true; }
+    MOLCLR_REQUIRE(smem <= 160 * 1024, "edge_table_grad: D too wide");
+    grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N > 0 ? N : 1);
+    k<<<grid, kRowThreads, smem, stream>>>(ga, cnt, (int)N, D, partials);
+  });
+  MOLCLR_CHECK_LAUNCH("edge_table_grad");
+  return molclr_reduce_partials(partials, grid, 8 * D, 1.f, 0, dB, stream);
+}
+
+extern "C" int molclr_bn_fwd_finalize(const float* tile_stats, int T, int tile_rows, int64_t N, int D, const float* gamma,
+                                      const float* beta, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                                      float momentum, float eps, float* coef, cudaStream_t stream) {
+  bn_fwd_finalize_kernel<<<(D + 31) / 32, dim3(32, 16), 0, stream>>>(tile_stats, T, tile_rows, (int)N, D, gamma, beta, running_mean,
+                                                                       running_var, reinterpret_cast<long long*>(num_batches_tracked),
+                                                                       momentum, eps, coef);
+  MOLCLR_CHECK_LAUNCH("bn_fwd_finalize");
+  return 0;
+}
+
+extern "C" int molclr_bn_eval_coef(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                                   float eps, int D, float* coef, cudaStream_t stream) {
+  bn_eval_coef_kernel<<<(D + 127) / 128, 128, 0, stream>>>(gamma, beta, running_mean, running_var, eps, D, coef);
+  MOLCLR_CHECK_LAUNCH("bn_eval_coef");
+  return 0;
+}
+
+extern "C" int molclr_bn_bwd_finalize(const float* partials, int P, int64_t N, int D, const float* gamma, const float* coef,
+                                      int use_batch_stats, float* dgamma, float* dbeta, float* bcoef, cudaStream_t stream) {
+  bn_bwd_finalize_kernel<<<(D + 31) / 32, dim3(32, 16), 0, stream>>>(partials, P, (int)N, D, gamma, coef, use_batch_stats, dgamma,
+                                                                       dbeta, bcoef);
+  MOLCLR_CHECK_LAUNCH("bn_bwd_finalize");
+  return 0;
+}
+
+extern "C" int molclr_bn_bwd_apply(const float* gy, const float* gp, const int32_t* node2graph, const int32_t* gptr, int pool_mean,
+                                   const float* z, const float* bcoef, int64_t N, int D, float* gz, float* dbias,
+                                   float* partials, cudaStream_t stream) {
+  REQUIRE_D(D);
+  if (N == 0) return 0;
+  const size_t smem = (size_t)(3 + kRowWarps) * D * sizeof(float);
+  int grid = 1;
+  NCH_DISPATCH(D / 4, {
+    if (gp) {
+      auto k = bn_bwd_apply_kernel<NCH, 1>;
+      grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
+      k<<<grid, kRowThreads, smem, stream>>>(nullptr, gp, node2graph, gptr, pool_mean, z, bcoef, (int)N, D, gz, partials);
+    } else {
+      auto k = bn_bwd_apply_kernel<NCH, 0>;
+      grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
+      k<<<grid, kRowThreads, smem, stream>>>(gy, nullptr, nullptr, nullptr, 0, z, bcoef, (int)N, D, gz, partials);
+    }
+  });
+  MOLCLR_CHECK_LAUNCH("bn_bwd_apply");
+  if (dbias) return molclr_reduce_partials(partials, grid, D, 1.f, 0, dbias, stream);
+  return 0;
+}
+
+extern "C" int molclr_pool_fwd(const float* z, const float* bn_coef, int relu, const int32_t* gptr, const int32_t* gperm,
+                               int pool_mode, int64_t G, int D, float* out, int round_tf32_out, cudaStream_t stream) {
+  REQUIRE_D(D);
+  MOLCLR_REQUIRE(pool_mode == 0 || pool_mode == 1, "pool mode %d not supported (0 = mean, 1 = add)", pool_mode);
+  if (G == 0) return 0;
+  const size_t smem = (size_t)2 * D * sizeof(float);
+  NCH_DISPATCH(D / 4, {
+    auto k = pool_fwd_kernel<NCH>;
+    k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, G), kRowThreads, smem, stream>>>(z, bn_coef, relu, gptr, gperm,
+                                                                                          pool_mode == 0, (int)G, D, out, round_tf32_out);
+  });
+  MOLCLR_CHECK_LAUNCH("pool_fwd");
+  return 0;
+}
+
+extern "C" int molclr_pool_bwd_stats(const float* gp, const int32_t* node2graph, const int32_t* gptr, int pool_mode, const float* z,
+                                     const float* bn_coef, int64_t N, int D, float* partials, int* num_partials, cudaStream_t stream) {
+  REQUIRE_D(D);
+  if (num_partials) *num_partials = 0;
+  if (N == 0) return 0;
+  const size_t smem = (size_t)(2 + 2 * kRowWarps) * D * sizeof(float);
+  NCH_DISPATCH(D / 4, {
+    auto k = pool_bwd_stats_kernel<NCH>;
+    const int grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
+    k<<<grid, kRowThreads, smem, stream>>>(gp, node2graph, gptr, pool_mode == 0, z, bn_coef, (int)N, D, partials);
+    if (num_partials) *num_partials = grid;
+  });
+  MOLCLR_CHECK_LAUNCH("pool_bwd_stats");
+  return 0;
+}
+
+extern "C" int molclr_round_tf32(const float* src, float* dst, int64_t n, cudaStream_t stream) {
+  if (n == 0) return 0;
+  int64_t blocks = (n + 1023) / 1024;
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  round_tf32_kernel<<<(int)blocks, 256, 0, stream>>>(src, dst, n);
+  MOLCLR_CHECK_LAUNCH("round_tf32");
+  return 0;
+}
+
+extern "C" int molclr_l2_normalize_fwd(const float* z, int64_t R, int C, float eps, float* y, float* inv_norm, cudaStream_t stream) {
+  if (R == 0) return 0;
+  l2_normalize_fwd_kernel<<<(int)((R + 7) / 8), 256, 0, stream>>>(z, (int)R, C, eps, y, inv_norm);
+  MOLCLR_CHECK_LAUNCH("l2_normalize_fwd");
+  return 0;
+}
+
+extern "C" int molclr_l2_normalize_bwd(const float* gy, const float* y, const float* inv_norm, int64_t R, int C, float eps, float* gz,
+                                       cudaStream_t stream) {
+  if (R == 0) return 0;
+  l2_normalize_bwd_kernel<<<(int)((R + 7) / 8), 256, 0, stream>>>(gy, y, inv_norm, (int)R, C, eps, gz);
+  MOLCLR_CHECK_LAUNCH("l2_normalize_bwd");
+  return 0;
+}
