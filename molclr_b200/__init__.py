@@ -1,2 +1,10 @@
-"""molclr_b200 -- B200-native MolCLR pre-training hot path."""
+"""molclr_b200 -- B200-native MolCLR pre-training hot path.
+
+Drop-in classes with the reference's API: ``GINet``, ``NTXentLoss`` (and ``GCN``), backed by
+hand-written sm_100a CUDA kernels behind the C ABI in ``include/molclr_b200.h``.
+"""
 from .batch import Batch  # noqa: F401
+from .ginet import GINet, GINEConv  # noqa: F401
+from .nt_xent import NTXentLoss  # noqa: F401
+from .graph import GraphPlan, get_plan  # noqa: F401
+from .functional import normalize, pretrain_loss  # noqa: F401

@@ -1,0 +1,105 @@
+"""ctypes binding of libmolclr_b200.so (the C ABI declared in include/molclr_b200.h).
+
+There is no fallback: if the shared object is missing or a call fails, this raises.  PyTorch is used
+only for device memory (``tensor.data_ptr()``) and the current CUDA stream.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmolclr_b200.so")
+
+vp, i64, i32, f32, sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
+
+
+class GemmArgs(C.Structure):
+    """Mirror of ``molclr_gemm_args`` (include/molclr_b200.h)."""
+    _fields_ = [
+        ("A", vp), ("lda", i64), ("a_mn", C.c_int32),
+        ("B", vp), ("ldb", i64), ("b_mn", C.c_int32),
+        ("M", i64), ("N", i64), ("K", i64),
+        ("out", vp), ("ldo", i64), ("transpose_out", C.c_int32),
+        ("out2", vp), ("ldo2", i64),
+        ("bias", vp),
+        ("addend", vp), ("ldadd", i64),
+        ("mask", vp), ("ldmask", i64),
+        ("relu", C.c_int32), ("round_out", C.c_int32),
+        ("colstat", vp), ("colstat_mode", C.c_int32),
+        ("split_k", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/molclr_b200.h declares
+SIGNATURES = {
+    "molclr_abi_version": (i32, []),
+    "molclr_last_error": (C.c_char_p, []),
+    "molclr_device_info": (i32, [C.POINTER(i32), C.POINTER(i32)]),
+    "molclr_plan_workspace_bytes": (sz, [i64, i64, i64]),
+    "molclr_plan_build": (i32, [vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp]),
+    "molclr_embed_nodes_fwd": (i32, [vp, vp, vp, i64, i32, vp, vp]),
+    "molclr_embed_nodes_bwd_blocks": (i32, [i32]),
+    "molclr_embed_nodes_bwd": (i32, [vp, vp, i64, i32, vp, vp, vp]),
+    "molclr_gine_aggregate_fwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, i64, i32, vp, i32, vp]),
+    "molclr_rowwise_max_blocks": (i32, []),
+    "molclr_gine_aggregate_bwd": (i32, [vp, vp, vp, vp, vp, i32, i64, i32, vp, vp, C.POINTER(i32), vp]),
+    "molclr_edge_table_grad": (i32, [vp, vp, i64, i32, vp, vp, vp]),
+    "molclr_reduce_partials": (i32, [vp, i32, i32, f32, i32, vp, vp]),
+    "molclr_bn_fwd_finalize": (i32, [vp, i32, i32, i64, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp]),
+    "molclr_bn_eval_coef": (i32, [vp, vp, vp, vp, f32, i32, vp, vp]),
+    "molclr_bn_bwd_finalize": (i32, [vp, i32, i64, i32, vp, vp, i32, vp, vp, vp, vp]),
+    "molclr_bn_bwd_apply": (i32, [vp, vp, vp, vp, i32, vp, vp, i64, i32, vp, vp, vp, vp]),
+    "molclr_pool_fwd": (i32, [vp, vp, i32, vp, vp, i32, i64, i32, vp, i32, vp]),
+    "molclr_pool_bwd_stats": (i32, [vp, vp, vp, i32, vp, vp, i64, i32, vp, C.POINTER(i32), vp]),
+    "molclr_gemm_colstat_tiles": (i32, [i64]),
+    "molclr_gemm_tf32": (i32, [C.POINTER(GemmArgs), vp]),
+    "molclr_round_tf32": (i32, [vp, vp, i64, vp]),
+    "molclr_l2_normalize_fwd": (i32, [vp, i64, i32, f32, vp, vp, vp]),
+    "molclr_l2_normalize_bwd": (i32, [vp, vp, vp, i64, i32, f32, vp, vp]),
+    "molclr_ntxent_workspace_bytes": (sz, [i64, i64, i32]),
+    "molclr_ntxent_fwd": (i32, [vp, vp, i64, i64, i32, i64, f32, vp, vp, vp, vp, sz, vp]),
+    "molclr_ntxent_bwd": (i32, [vp, vp, i64, i64, i32, i64, f32, vp, vp, f32, vp, vp, sz, vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads the library once; raises if it has not been built (python -m molclr_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"molclr_b200: {LIB_PATH} not found -- build it with `python -m molclr_b200.build` "
+                               "(there is no CPU or PyTorch fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)         # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        if lib.molclr_abi_version() != 1:
+            raise RuntimeError("molclr_b200: ABI version mismatch between _lib.py and libmolclr_b200.so")
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().molclr_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"molclr_b200.{what} failed ({rc}): {msg}")
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t, dtype=torch.float32):
+    """Device pointer of a contiguous CUDA tensor of the expected dtype (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("molclr_b200: expected a CUDA tensor (no CPU path exists)")
+    if t.dtype != dtype:
+        raise TypeError(f"molclr_b200: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError("molclr_b200: expected a contiguous tensor")
+    return t.data_ptr()

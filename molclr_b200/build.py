@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "libmolclr_b200.so")
 SOURCES = ["api.cu", "plan.cu", "rowwise.cu", "gemm.cu", "ntxent.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
     "-I", os.path.join(ROOT, "include"), "-I", CSRC,
 ]
 

@@ -1,0 +1,238 @@
+"""GINet: drop-in for ``models/ginet_molclr.py`` (same constructor, ``forward(data) -> (h, out)``,
+``state_dict`` keys) whose forward AND backward run entirely on the hand-written sm_100a kernels.
+
+Per view the kernel sequence is (N nodes, D=emb_dim, H=2D):
+
+    plan (once per batch)      CSR + transpose + bond-class counts + graph segments
+    embed_nodes_fwd            h0 = E1[x0] + E2[x1]                                   ginet_molclr.py:103
+    per layer l:
+      gine_aggregate_fwd       a_l = sum_j f(z_{l-1})[j] + bond table, self loop last   :29-44  (f = BN+ReLU of l-1, fused)
+      gemm (bias, ReLU)        u_l = relu(a_l W1^T + b1)                               :19-23,46-47
+      gemm (bias, tile stats)  z_l = u_l W2^T + b2, column mean/M2 per 128-row tile
+      bn_fwd_finalize          batch statistics -> (scale, shift, mean, invstd); running stats   :107
+    pool_fwd                   p = mean_g( BN_L(z_L) )                                 :113
+    gemm x3                    h = feat_lin(p); out = out_lin(h)                       :114-115
+
+and the backward mirrors it (see ``_backward``).  Nothing here falls back to PyTorch operators.
+"""
+import torch
+from torch import nn
+
+from . import ops
+from .graph import get_plan
+
+num_atom_type = 119      # including the extra mask token   (ginet_molclr.py:9)
+num_chirality_tag = 3
+num_bond_type = 5        # including aromatic and self-loop  (ginet_molclr.py:12)
+num_bond_direction = 3
+
+
+class GINEConv(nn.Module):
+    """Parameter container with the reference's names (ginet_molclr.py:16-27); the computation lives in
+    the fused kernels driven by ``GINet``."""
+
+    def __init__(self, emb_dim):
+        super().__init__()
+        self.mlp = nn.Sequential(nn.Linear(emb_dim, 2 * emb_dim), nn.ReLU(), nn.Linear(2 * emb_dim, emb_dim))
+        self.edge_embedding1 = nn.Embedding(num_bond_type, emb_dim)
+        self.edge_embedding2 = nn.Embedding(num_bond_direction, emb_dim)
+        nn.init.xavier_uniform_(self.edge_embedding1.weight.data)
+        nn.init.xavier_uniform_(self.edge_embedding2.weight.data)
+
+
+class _RoundedWeights:
+    """TF32-rounded shadow copies of the GEMM weights, refreshed only when a parameter changed
+    (tracked through the tensor version counter the optimizer bumps)."""
+
+    def __init__(self):
+        self._cache = {}
+
+    def get(self, p):
+        key = id(p)
+        hit = self._cache.get(key)
+        if hit is not None and hit[0] == p._version and hit[1].data_ptr() != 0 and hit[2] == p.data_ptr():
+            return hit[1]
+        r = ops.round_tf32(p.detach())
+        self._cache[key] = (p._version, r, p.data_ptr())
+        return r
+
+
+class _EncoderBase(nn.Module):
+    """Shared plumbing of the GINet / GCN drop-ins."""
+
+    def _check_input(self, data):
+        if self.training and self.drop_ratio > 0:
+            raise NotImplementedError("molclr_b200: drop_ratio > 0 in training mode is not implemented yet "
+                                      "(pre-training uses drop_ratio 0, config.yaml:20)")
+        if self.pool_name not in ops.POOL_MODES:
+            if self.pool_name == "max":
+                raise NotImplementedError("molclr_b200: pool='max' is not implemented yet")
+            # the reference leaves self.pool unset for unknown names and fails at forward (ginet_molclr.py:83-88,113)
+            raise AttributeError(f"'{type(self).__name__}' object has no attribute 'pool'")
+
+
+class GINet(_EncoderBase):
+    """ginet_molclr.py:50-117.
+
+    Args:
+        num_layer (int): the number of GNN layers
+        emb_dim (int): dimensionality of embeddings
+        feat_dim (int): dimensionality of the returned representation ``h``
+        drop_ratio (float): dropout rate
+        pool (str): 'mean' | 'add' | 'max'
+    """
+
+    def __init__(self, num_layer=5, emb_dim=300, feat_dim=256, drop_ratio=0, pool="mean"):
+        super().__init__()
+        self.num_layer, self.emb_dim, self.feat_dim, self.drop_ratio = num_layer, emb_dim, feat_dim, drop_ratio
+        self.pool_name = pool
+        self.x_embedding1 = nn.Embedding(num_atom_type, emb_dim)
+        self.x_embedding2 = nn.Embedding(num_chirality_tag, emb_dim)
+        nn.init.xavier_uniform_(self.x_embedding1.weight.data)
+        nn.init.xavier_uniform_(self.x_embedding2.weight.data)
+        self.gnns = nn.ModuleList([GINEConv(emb_dim) for _ in range(num_layer)])
+        self.batch_norms = nn.ModuleList([nn.BatchNorm1d(emb_dim) for _ in range(num_layer)])
+        self.feat_lin = nn.Linear(emb_dim, feat_dim)
+        self.out_lin = nn.Sequential(nn.Linear(feat_dim, feat_dim), nn.ReLU(inplace=True), nn.Linear(feat_dim, feat_dim // 2))
+        self._rounded = _RoundedWeights()
+
+    # parameter order used by the autograd function
+    def _params(self):
+        ps = [self.x_embedding1.weight, self.x_embedding2.weight]
+        for g, bn in zip(self.gnns, self.batch_norms):
+            ps += [g.mlp[0].weight, g.mlp[0].bias, g.mlp[2].weight, g.mlp[2].bias,
+                   g.edge_embedding1.weight, g.edge_embedding2.weight, bn.weight, bn.bias]
+        ps += [self.feat_lin.weight, self.feat_lin.bias, self.out_lin[0].weight, self.out_lin[0].bias,
+               self.out_lin[2].weight, self.out_lin[2].bias]
+        return ps
+
+    def forward(self, data):
+        self._check_input(data)
+        plan = get_plan(data)
+        h, out = _GINetFunction.apply(self, plan, *self._params())
+        return h, out
+
+
+def _head_forward(m, p, rw):
+    """h = feat_lin(p); out = out_lin(h)   (ginet_molclr.py:114-115).  Returns h, out and what backward needs."""
+    G, D, Fd = p.shape[0], m.emb_dim, m.feat_dim
+    dev = p.device
+    Wf, W0, W2 = rw.get(m.feat_lin.weight), rw.get(m.out_lin[0].weight), rw.get(m.out_lin[2].weight)
+    h = torch.empty(G, Fd, device=dev)
+    h_r = torch.empty(G, Fd, device=dev)
+    ops.gemm(p, Wf, G, Fd, D, out=h, out2=h_r, bias=m.feat_lin.bias.detach())
+    r = torch.empty(G, Fd, device=dev)
+    ops.gemm(h_r, W0, G, Fd, Fd, out=r, bias=m.out_lin[0].bias.detach(), relu=True, round_out=True)
+    out = torch.empty(G, Fd // 2, device=dev)
+    ops.gemm(r, W2, G, Fd // 2, Fd, out=out, bias=m.out_lin[2].bias.detach())
+    return h, out, (h_r, r, Wf, W0, W2)
+
+
+def _head_backward(m, p, saved, g_h, g_out):
+    """Returns g_p and the six head parameter gradients (autograd of ginet_molclr.py:90-96,114-115)."""
+    h_r, r, Wf, W0, W2 = saved
+    G, D, Fd = p.shape[0], m.emb_dim, m.feat_dim
+    dev = p.device
+    g_out = g_out.contiguous()
+    g_out_r = ops.round_tf32(g_out)
+    dW2 = ops.gemm_dw(g_out_r, r)
+    db2 = ops.colsum(g_out)
+    T = ops.colstat_tiles(G)
+    # g_r = (g_out W2) * [r > 0]
+    g_r = torch.empty(G, Fd, device=dev)
+    part = torch.empty(T, Fd, device=dev)
+    ops.gemm(g_out_r, W2, G, Fd, Fd // 2, b_mn=True, out=g_r, mask=r, round_out=True, colstat=part, colstat_mode=1)
+    db0 = ops.reduce_partials(part, T, Fd, torch.empty(Fd, device=dev))
+    dW0 = ops.gemm_dw(g_r, h_r)
+    # g_h(total) = g_r W0 (+ the gradient arriving on the returned representation h)
+    g_hh_r = torch.empty(G, Fd, device=dev)
+    part2 = torch.empty(T, Fd, device=dev)
+    ops.gemm(g_r, W0, G, Fd, Fd, b_mn=True, out2=g_hh_r, addend=None if g_h is None else g_h.contiguous(),
+             colstat=part2, colstat_mode=1)
+    dbf = ops.reduce_partials(part2, T, Fd, torch.empty(Fd, device=dev))
+    dWf = ops.gemm_dw(g_hh_r, p)
+    g_p = torch.empty(G, D, device=dev)
+    ops.gemm(g_hh_r, Wf, G, D, Fd, b_mn=True, out=g_p)
+    return g_p, (dWf, dbf, dW0, db0, dW2, db2)
+
+
+class _GINetFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, m, plan, *params):
+        L, D, H, N = m.num_layer, m.emb_dim, 2 * m.emb_dim, plan.N
+        dev = params[0].device
+        rw = m._rounded
+        training = m.training
+        pool_mode = ops.POOL_MODES[m.pool_name]
+        h0 = ops.embed_nodes_fwd(plan, m.x_embedding1.weight.detach(), m.x_embedding2.weight.detach())
+        src, coef_prev = h0, None
+        layers = []
+        T = ops.colstat_tiles(N)
+        for l in range(L):
+            g, bn = m.gnns[l], m.batch_norms[l]
+            a = ops.gine_aggregate_fwd(plan, src, g.edge_embedding1.weight.detach(), g.edge_embedding2.weight.detach(),
+                                       bn_coef=coef_prev, relu=True, round_out=True)
+            W1, W2 = rw.get(g.mlp[0].weight), rw.get(g.mlp[2].weight)
+            u = torch.empty(N, H, device=dev)
+            ops.gemm(a, W1, N, H, D, out=u, bias=g.mlp[0].bias.detach(), relu=True, round_out=True)
+            z = torch.empty(N, D, device=dev)
+            if training:
+                stats = torch.empty(T, 2, D, device=dev)
+                ops.gemm(u, W2, N, D, H, out=z, bias=g.mlp[2].bias.detach(), colstat=stats, colstat_mode=2)
+                momentum = 0.1 if bn.momentum is None else bn.momentum
+                coef = ops.bn_fwd_finalize(stats, T, N, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
+                                           bn.num_batches_tracked, momentum, bn.eps)
+            else:
+                ops.gemm(u, W2, N, D, H, out=z, bias=g.mlp[2].bias.detach())
+                coef = ops.bn_eval_coef(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
+            layers.append((a, u, z, coef, W1, W2))
+            src, coef_prev = z, coef
+        p = ops.pool_fwd(plan, src, coef_prev, pool_mode, relu=False, round_out=True)
+        h, out, head_saved = _head_forward(m, p, rw)
+        ctx.m, ctx.plan, ctx.layers, ctx.p, ctx.head_saved = m, plan, layers, p, head_saved
+        ctx.training, ctx.pool_mode = training, pool_mode
+        return h, out
+
+    @staticmethod
+    def backward(ctx, g_h, g_out):
+        m, plan, layers, p = ctx.m, ctx.plan, ctx.layers, ctx.p
+        L, D, H, N = m.num_layer, m.emb_dim, 2 * m.emb_dim, plan.N
+        dev = p.device
+        if g_out is None:
+            g_out = torch.zeros(p.shape[0], m.feat_dim // 2, device=dev)
+        g_p, head_grads = _head_backward(m, p, ctx.head_saved, g_h, g_out)
+        pool_mean = ctx.pool_mode == 0
+        grads = [None] * (2 + 8 * L)
+        # last layer: BatchNorm backward fed by the pool backward (g_y is never materialised)
+        a, u, z, coef, W1, W2 = layers[L - 1]
+        bn = m.batch_norms[L - 1]
+        partials, P = ops.pool_bwd_stats(plan, g_p, z, coef, ctx.pool_mode)
+        dgamma, dbeta, bcoef = ops.bn_bwd_finalize(partials, P, N, bn.weight.detach(), coef, ctx.training)
+        g_z, db2 = ops.bn_bwd_apply(z, bcoef, gp=g_p, plan=plan, pool_mean=pool_mean)
+        T = ops.colstat_tiles(N)
+        for l in range(L - 1, -1, -1):
+            a, u, z, coef, W1, W2 = layers[l]
+            base = 2 + 8 * l
+            grads[base + 6], grads[base + 7], grads[base + 3] = dgamma, dbeta, db2
+            # g_u = (g_z W2) * [u > 0];  db1 = colsum(g_u)
+            g_u = torch.empty(N, H, device=dev)
+            part = torch.empty(T, H, device=dev)
+            ops.gemm(g_z, W2, N, H, D, b_mn=True, out=g_u, mask=u, round_out=True, colstat=part, colstat_mode=1)
+            grads[base + 1] = ops.reduce_partials(part, T, H, torch.empty(H, device=dev))
+            grads[base + 2] = ops.gemm_dw(g_z, u)                 # dW2 [D, H]
+            g_a = torch.empty(N, D, device=dev)
+            ops.gemm(g_u, W1, N, D, H, b_mn=True, out=g_a)
+            grads[base + 0] = ops.gemm_dw(g_u, a)                 # dW1 [H, D]
+            grads[base + 4], grads[base + 5] = ops.edge_table_grad(plan, g_a)
+            if l > 0:
+                _, _, zp, coefp, _, _ = layers[l - 1]
+                bnp = m.batch_norms[l - 1]
+                g_y, partials, P = ops.gine_aggregate_bwd(plan, g_a, z_prev=zp, bn_coef=coefp, relu=True)
+                dgamma, dbeta, bcoef = ops.bn_bwd_finalize(partials, P, N, bnp.weight.detach(), coefp, ctx.training)
+                g_z, db2 = ops.bn_bwd_apply(zp, bcoef, gy=g_y)
+            else:
+                g_h0, _, _ = ops.gine_aggregate_bwd(plan, g_a)
+                grads[0], grads[1] = ops.embed_nodes_bwd(plan, g_h0)
+        ctx.layers = None
+        return (None, None, *grads, *head_grads)

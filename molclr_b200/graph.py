@@ -1,0 +1,86 @@
+"""GraphPlan: the destination-sorted CSR (+ source-sorted transpose, per-node bond-class counts and
+graph segments) built ONCE per batch on the device and shared by all layers, forward and backward.
+
+This replaces the per-layer, per-forward ``add_self_loops`` / CPU-built ``self_loop_attr`` / H2D copy /
+``cat`` of the reference (ginet_molclr.py:31-37, gcn_molclr.py:64-70) and the ``batch.max().item()``
+device sync inside ``global_mean_pool``.
+"""
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream
+
+_ERR_BITS = {1: "node feature out of range (atom type must be < 119, chirality < 3; ginet_molclr.py:9-10)",
+             2: "edge_index endpoint out of range", 4: "edge_attr out of range (bond type < 5, direction < 3)",
+             8: "batch id out of range", 16: "node in-degree above 65535"}
+
+
+def _al(n, a=4):
+    return (n + a - 1) // a * a
+
+
+class GraphPlan:
+    """Device-resident int32 index structures for one batch (see include/molclr_b200.h: molclr_plan_build)."""
+
+    __slots__ = ("N", "E", "G", "xpacked", "node2graph", "rowptr", "col", "eattr", "rowptr_t", "col_t", "cnt",
+                 "gptr", "gperm", "status", "_buf", "_checked")
+
+    def __init__(self, data, validate=True):
+        x, ei, ea, batch = data.x, data.edge_index, data.edge_attr, data.batch
+        if not x.is_cuda:
+            raise RuntimeError("molclr_b200: batch tensors must be on a CUDA device (call data.to(device) first; "
+                               "there is no CPU path)")
+        for name, t in (("x", x), ("edge_index", ei), ("edge_attr", ea), ("batch", batch)):
+            if t.dtype != torch.int64:
+                raise TypeError(f"molclr_b200: data.{name} must be int64 (as produced by the reference's dataset), got {t.dtype}")
+        N, E = x.size(0), ei.size(1)
+        G = getattr(data, "num_graphs", None)
+        if G is None:
+            G = int(batch.max().item()) + 1 if N else 0       # what global_mean_pool does in the reference
+        self.N, self.E, self.G = int(N), int(E), int(G)
+        lib = _lib.load()
+        ws_bytes = lib.molclr_plan_workspace_bytes(N, E, G)
+        # one allocation, carved into 16-byte aligned int32 views
+        sizes = [_al(N), _al(N), _al(N + 1), _al(E), _al((E + 3) // 4), _al(N + 1), _al(E), _al(4 * N), _al(G + 1), _al(N),
+                 _al((ws_bytes + 3) // 4), 4]
+        buf = torch.empty(sum(sizes), dtype=torch.int32, device=x.device)
+        views, off = [], 0
+        for s in sizes:
+            views.append(buf[off:off + s]); off += s
+        (self.xpacked, self.node2graph, self.rowptr, self.col, eattr32, self.rowptr_t, self.col_t, cnt32, self.gptr,
+         self.gperm, ws, self.status) = views
+        self.eattr = eattr32.view(torch.uint8)
+        self.cnt = cnt32.view(torch.uint16)
+        self._buf = buf
+        x, ei, ea, batch = x.contiguous(), ei.contiguous(), ea.contiguous(), batch.contiguous()
+        check(lib.molclr_plan_build(ptr(x, torch.int64), ptr(ei, torch.int64), ptr(ea, torch.int64), ptr(batch, torch.int64),
+                                    N, E, G, ptr(self.xpacked, torch.int32), ptr(self.node2graph, torch.int32),
+                                    ptr(self.rowptr, torch.int32), ptr(self.col, torch.int32), ptr(self.eattr, torch.uint8),
+                                    ptr(self.rowptr_t, torch.int32), ptr(self.col_t, torch.int32), ptr(self.cnt, torch.uint16),
+                                    ptr(self.gptr, torch.int32), ptr(self.gperm, torch.int32), ptr(ws, torch.int32), ws_bytes,
+                                    ptr(self.status, torch.int32), stream()), "plan_build")
+        self._checked = False
+        if validate:
+            self.check()
+
+    def check(self):
+        """Raises IndexError for out-of-range inputs (one 16-byte D2H read; the reference's embedding
+        lookups raise the same way on CPU)."""
+        if not self._checked:
+            bits = int(self.status[0].item())
+            if bits:
+                raise IndexError("molclr_b200: invalid batch: " + "; ".join(m for b, m in _ERR_BITS.items() if bits & b))
+            self._checked = True
+        return self
+
+
+def get_plan(data, validate=True):
+    """Returns the cached plan of a batch object, building it on first use."""
+    plan = getattr(data, "_molclr_plan", None)
+    if plan is None or plan.xpacked.device != data.x.device:
+        plan = GraphPlan(data, validate=validate)
+        try:
+            data._molclr_plan = plan
+        except AttributeError:
+            pass
+    return plan

@@ -1,0 +1,59 @@
+"""NTXentLoss: drop-in for ``utils/nt_xent.py`` (same constructor and ``forward(zis, zjs)``), computed by
+the fused similarity-GEMM + masked log-sum-exp kernels; the 2N x 2N matrix is never materialised.
+
+With ``torch.distributed`` initialised and ``global_negatives=True`` the projections of all ranks are
+all-gathered (NCCL) so every anchor sees the negatives of the whole global batch.
+"""
+import torch
+
+from . import ops
+
+
+class _NTXentFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, zis, zjs, temperature, use_cosine, group):
+        n = zis.shape[0]
+        rep = torch.cat([zjs, zis], dim=0).contiguous().float()          # nt_xent.py:48 (zjs FIRST)
+        if use_cosine:
+            # torch.nn.CosineSimilarity(dim=-1), eps 1e-8 (nt_xent.py:19,44): x.y / (max(|x|,eps) max(|y|,eps))
+            rep_n, inv = ops.l2_normalize_fwd(rep, 1e-8)
+        else:
+            rep_n, inv = rep, None
+        rep_r = ops.round_tf32(rep_n)
+        cols, row_offset = rep_r, 0
+        loss, row_lse, _row_pos = ops.ntxent_fwd(rep_r, cols, row_offset, 1.0 / temperature)
+        ctx.save_for_backward(rep_n, inv, rep_r, row_lse)
+        ctx.n, ctx.temperature, ctx.use_cosine = n, temperature, use_cosine
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        rep_n, inv, rep_r, row_lse = ctx.saved_tensors
+        g = ops.ntxent_bwd(rep_r, rep_r, 0, 1.0 / ctx.temperature, row_lse, row_lse)
+        g = g * g_loss
+        if ctx.use_cosine:
+            g = ops.l2_normalize_bwd(g.contiguous(), rep_n, inv, 1e-8)
+        n = ctx.n
+        return g[n:], g[:n], None, None, None
+
+
+class NTXentLoss(torch.nn.Module):
+    """nt_xent.py:5-65.  ``loss = CrossEntropy(sum)([pos | negatives]/T, 0) / 2N`` over the rows
+    ``[zjs; zis]`` with the cosine (or dot, nt_xent.py:32-38) similarity."""
+
+    def __init__(self, device, batch_size, temperature, use_cosine_similarity):
+        super().__init__()
+        self.batch_size = batch_size
+        self.temperature = temperature
+        self.device = device
+        self.use_cosine_similarity = bool(use_cosine_similarity)
+
+    def forward(self, zis, zjs):
+        if zis.shape != zjs.shape or zis.dim() != 2:
+            raise RuntimeError(f"NTXentLoss: zis {tuple(zis.shape)} and zjs {tuple(zjs.shape)} must be equal 2-D shapes")
+        if zis.shape[0] != self.batch_size:
+            # the reference bakes batch_size into its mask and fails in .view() (nt_xent.py:55-57)
+            raise RuntimeError(f"NTXentLoss: got {zis.shape[0]} rows but batch_size={self.batch_size} "
+                               "(the reference requires drop_last=True, dataset.py:180)")
+        return _NTXentFunction.apply(zis, zjs, float(self.temperature), self.use_cosine_similarity, None)

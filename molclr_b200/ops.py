@@ -1,0 +1,243 @@
+"""Thin Python wrappers over the C ABI: allocate outputs with torch, pass raw pointers, raise on error.
+
+Nothing here computes on the CPU or with PyTorch operators; every function enqueues hand-written
+sm_100a kernels on the current CUDA stream.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, check, ptr, stream
+
+F32 = torch.float32
+
+
+def _empty(*shape, device):
+    return torch.empty(*shape, dtype=F32, device=device)
+
+
+def max_blocks():
+    return _lib.load().molclr_rowwise_max_blocks()
+
+
+# ------------------------------------------------------------------------------------------- GEMM
+def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, out=None, out2=None, bias=None, addend=None, mask=None,
+         relu=False, round_out=False, colstat=None, colstat_mode=0, transpose_out=False, split_k=1,
+         lda=None, ldb=None):
+    """C[M,N] = sum_k A(m,k) B(n,k) on tcgen05 (TF32 in, FP32 accumulate) with the fused epilogue of
+    ``molclr_gemm_tf32`` (see include/molclr_b200.h)."""
+    lib = _lib.load()
+    a = GemmArgs()
+    a.A, a.lda, a.a_mn = ptr(A), (A.stride(0) if lda is None else lda), int(a_mn)
+    a.B, a.ldb, a.b_mn = ptr(B), (B.stride(0) if ldb is None else ldb), int(b_mn)
+    a.M, a.N, a.K = M, N, K
+    a.out, a.ldo, a.transpose_out = ptr(out), (out.stride(0) if out is not None else 0), int(transpose_out)
+    a.out2, a.ldo2 = ptr(out2), (out2.stride(0) if out2 is not None else 0)
+    a.bias = ptr(bias)
+    a.addend, a.ldadd = ptr(addend), (addend.stride(0) if addend is not None else 0)
+    a.mask, a.ldmask = ptr(mask), (mask.stride(0) if mask is not None else 0)
+    a.relu, a.round_out = int(relu), int(round_out)
+    a.colstat, a.colstat_mode = ptr(colstat), int(colstat_mode)
+    a.split_k = int(split_k)
+    check(lib.molclr_gemm_tf32(C.byref(a), stream()), "gemm_tf32")
+    return out
+
+
+def colstat_tiles(M):
+    return _lib.load().molclr_gemm_colstat_tiles(M)
+
+
+def _sm_count():
+    if not hasattr(_sm_count, "v"):
+        _sm_count.v = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    return _sm_count.v
+
+
+def gemm_dw(dY, X):
+    """dW[O,I] = dY^T X for row-major dY [R,O], X [R,I] (both tf32-rounded): the weight gradient of a
+    Linear (autograd of ginet_molclr.py:19-23,90-96).  Both operands are consumed MN-major in place;
+    the reduction over R is split across CTAs and accumulated atomically."""
+    R, O = dY.shape
+    I = X.shape[1]
+    dW = _empty(O, I, device=dY.device)
+
+    def padded(m, n):
+        bn = 256 if (n % 256 == 0 or n > 640) else 160
+        return (-(-m // 128) * 128) * (-(-n // bn) * bn), (-(-m // 128)) * (-(-n // bn))
+
+    (area_a, tiles_a), (area_b, tiles_b) = padded(O, I), padded(I, O)
+    swap = area_b < area_a
+    tiles = tiles_b if swap else tiles_a
+    num_kb = -(-R // 32)
+    split = max(1, min(-(-2 * _sm_count() // tiles), max(1, num_kb // 8)))
+    if swap:    # compute dW^T = X^T dY with the wider operand on M, store transposed
+        gemm(X, dY, I, O, R, a_mn=True, b_mn=True, out=dW, transpose_out=True, split_k=split)
+    else:
+        gemm(dY, X, O, I, R, a_mn=True, b_mn=True, out=dW, split_k=split)
+    return dW
+
+
+def colsum(Mx):
+    """Column sums of a small row-major matrix (deterministic)."""
+    R, Cc = Mx.shape
+    out = _empty(Cc, device=Mx.device)
+    check(_lib.load().molclr_reduce_partials(ptr(Mx), R, Cc, 1.0, 0, ptr(out), stream()), "reduce_partials")
+    return out
+
+
+def reduce_partials(partials, P, length, out):
+    check(_lib.load().molclr_reduce_partials(ptr(partials), P, length, 1.0, 0, ptr(out), stream()), "reduce_partials")
+    return out
+
+
+def round_tf32(x):
+    out = torch.empty_like(x)
+    check(_lib.load().molclr_round_tf32(ptr(x), ptr(out), x.numel(), stream()), "round_tf32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------- row-wise
+def embed_nodes_fwd(plan, E1, E2):
+    D = E1.shape[1]
+    out = _empty(plan.N, D, device=E1.device)
+    check(_lib.load().molclr_embed_nodes_fwd(ptr(plan.xpacked, torch.int32), ptr(E1), ptr(E2), plan.N, D, ptr(out), stream()),
+          "embed_nodes_fwd")
+    return out
+
+
+def embed_nodes_bwd(plan, g):
+    lib = _lib.load()
+    D = g.shape[1]
+    dE = _empty(119 + 3, D, device=g.device)
+    partials = _empty(lib.molclr_embed_nodes_bwd_blocks(D), (119 + 3) * D, device=g.device)
+    check(lib.molclr_embed_nodes_bwd(ptr(plan.xpacked, torch.int32), ptr(g), plan.N, D, ptr(dE), ptr(partials), stream()),
+          "embed_nodes_bwd")
+    return dE[:119], dE[119:]
+
+
+def gine_aggregate_fwd(plan, src, B1, B2, bn_coef=None, relu=True, round_out=True):
+    D = src.shape[1]
+    out = torch.empty_like(src)
+    check(_lib.load().molclr_gine_aggregate_fwd(ptr(src), ptr(bn_coef), int(relu), ptr(plan.rowptr, torch.int32),
+                                                ptr(plan.col, torch.int32), ptr(plan.eattr, torch.uint8), ptr(B1), ptr(B2),
+                                                plan.N, D, ptr(out), int(round_out), stream()), "gine_aggregate_fwd")
+    return out
+
+
+def gine_aggregate_bwd(plan, ga, z_prev=None, bn_coef=None, relu=True):
+    """Returns (gy, partials, P): partials/P are None/0 when z_prev is None."""
+    D = ga.shape[1]
+    gy = torch.empty_like(ga)
+    partials = _empty(max_blocks(), 2, D, device=ga.device) if z_prev is not None else None
+    n = C.c_int(0)
+    check(_lib.load().molclr_gine_aggregate_bwd(ptr(ga), ptr(plan.rowptr_t, torch.int32), ptr(plan.col_t, torch.int32),
+                                                ptr(z_prev), ptr(bn_coef), int(relu), plan.N, D, ptr(gy), ptr(partials),
+                                                C.byref(n), stream()), "gine_aggregate_bwd")
+    return gy, partials, n.value
+
+
+def edge_table_grad(plan, ga):
+    D = ga.shape[1]
+    dB = _empty(8, D, device=ga.device)
+    partials = _empty(max_blocks(), 8 * D, device=ga.device)
+    check(_lib.load().molclr_edge_table_grad(ptr(ga), ptr(plan.cnt, torch.uint16), plan.N, D, ptr(dB), ptr(partials), stream()),
+          "edge_table_grad")
+    return dB[:5], dB[5:]
+
+
+def bn_fwd_finalize(tile_stats, T, N, gamma, beta, running_mean, running_var, nbt, momentum, eps):
+    D = gamma.shape[0]
+    coef = _empty(4, D, device=gamma.device)
+    check(_lib.load().molclr_bn_fwd_finalize(ptr(tile_stats), T, 128, N, D, ptr(gamma), ptr(beta), ptr(running_mean),
+                                             ptr(running_var), ptr(nbt, torch.int64), momentum, eps, ptr(coef), stream()),
+          "bn_fwd_finalize")
+    return coef
+
+
+def bn_eval_coef(gamma, beta, running_mean, running_var, eps):
+    D = gamma.shape[0]
+    coef = _empty(4, D, device=gamma.device)
+    check(_lib.load().molclr_bn_eval_coef(ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), eps, D, ptr(coef), stream()),
+          "bn_eval_coef")
+    return coef
+
+
+def bn_bwd_finalize(partials, P, N, gamma, coef, use_batch_stats):
+    D = gamma.shape[0]
+    dgamma, dbeta, bcoef = _empty(D, device=gamma.device), _empty(D, device=gamma.device), _empty(3, D, device=gamma.device)
+    check(_lib.load().molclr_bn_bwd_finalize(ptr(partials), P, N, D, ptr(gamma), ptr(coef), int(use_batch_stats), ptr(dgamma),
+                                             ptr(dbeta), ptr(bcoef), stream()), "bn_bwd_finalize")
+    return dgamma, dbeta, bcoef
+
+
+def bn_bwd_apply(z, bcoef, gy=None, gp=None, plan=None, pool_mean=True):
+    N, D = z.shape
+    gz = torch.empty_like(z)
+    dbias = _empty(D, device=z.device)
+    partials = _empty(max_blocks(), D, device=z.device)
+    n2g = ptr(plan.node2graph, torch.int32) if gp is not None else None
+    gptr = ptr(plan.gptr, torch.int32) if gp is not None else None
+    check(_lib.load().molclr_bn_bwd_apply(ptr(gy), ptr(gp), n2g, gptr, int(pool_mean), ptr(z), ptr(bcoef), N, D, ptr(gz),
+                                          ptr(dbias), ptr(partials), stream()), "bn_bwd_apply")
+    return gz, dbias
+
+
+POOL_MODES = {"mean": 0, "add": 1}
+
+
+def pool_fwd(plan, z, bn_coef, pool_mode, relu=False, round_out=True):
+    D = z.shape[1]
+    out = _empty(plan.G, D, device=z.device)
+    check(_lib.load().molclr_pool_fwd(ptr(z), ptr(bn_coef), int(relu), ptr(plan.gptr, torch.int32), ptr(plan.gperm, torch.int32),
+                                      pool_mode, plan.G, D, ptr(out), int(round_out), stream()), "pool_fwd")
+    return out
+
+
+def pool_bwd_stats(plan, gp, z, bn_coef, pool_mode):
+    D = z.shape[1]
+    partials = _empty(max_blocks(), 2, D, device=z.device)
+    n = C.c_int(0)
+    check(_lib.load().molclr_pool_bwd_stats(ptr(gp), ptr(plan.node2graph, torch.int32), ptr(plan.gptr, torch.int32), pool_mode,
+                                            ptr(z), ptr(bn_coef), plan.N, D, ptr(partials), C.byref(n), stream()), "pool_bwd_stats")
+    return partials, n.value
+
+
+# ------------------------------------------------------------------------------------------- normalize / NT-Xent
+def l2_normalize_fwd(z, eps):
+    R, Cc = z.shape
+    y, inv = torch.empty_like(z), _empty(R, device=z.device)
+    check(_lib.load().molclr_l2_normalize_fwd(ptr(z), R, Cc, eps, ptr(y), ptr(inv), stream()), "l2_normalize_fwd")
+    return y, inv
+
+
+def l2_normalize_bwd(gy, y, inv, eps):
+    R, Cc = y.shape
+    gz = torch.empty_like(y)
+    check(_lib.load().molclr_l2_normalize_bwd(ptr(gy), ptr(y), ptr(inv), R, Cc, eps, ptr(gz), stream()), "l2_normalize_bwd")
+    return gz
+
+
+def ntxent_fwd(rep, cols, row_offset, inv_temperature):
+    """Returns (loss[1], row_lse[R], row_pos[R]) for local rows `rep` against candidates `cols`."""
+    lib = _lib.load()
+    R, Cc = rep.shape
+    Rc = cols.shape[0]
+    nbytes = lib.molclr_ntxent_workspace_bytes(R, Rc, Cc)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=rep.device)
+    row_lse, row_pos, loss = _empty(R, device=rep.device), _empty(R, device=rep.device), _empty(1, device=rep.device)
+    check(lib.molclr_ntxent_fwd(ptr(rep), ptr(cols), R, Rc, Cc, row_offset, inv_temperature, ptr(row_lse), ptr(row_pos), ptr(loss),
+                                ptr(ws, torch.uint8), nbytes, stream()), "ntxent_fwd")
+    return loss, row_lse, row_pos
+
+
+def ntxent_bwd(rep, cols, row_offset, inv_temperature, row_lse, col_lse):
+    lib = _lib.load()
+    R, Cc = rep.shape
+    Rc = cols.shape[0]
+    nbytes = lib.molclr_ntxent_workspace_bytes(R, Rc, Cc)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=rep.device)
+    g = torch.empty_like(rep)
+    check(lib.molclr_ntxent_bwd(ptr(rep), ptr(cols), R, Rc, Cc, row_offset, inv_temperature, ptr(row_lse), ptr(col_lse), 1.0 / Rc,
+                                ptr(g), ptr(ws, torch.uint8), nbytes, stream()), "ntxent_bwd")
+    return g
