@@ -34,6 +34,8 @@ typedef struct CUstream_st* cudaStream_t;
 /* ---- library ------------------------------------------------------------------------------- */
 int molclr_abi_version(void);
 const char* molclr_last_error(void);
+/* number of kernels this library has launched so far in this process (diagnostics) */
+uint64_t molclr_launch_count(void);
 /* host out-params; cc = compute capability major*10+minor */
 int molclr_device_info(int* sm_count, int* cc);
 
@@ -74,7 +76,8 @@ int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, int64_t N, in
  * (the previous layer's BatchNorm + ReLU, ginet_molclr.py:107-111, applied on the fly). */
 int molclr_gine_aggregate_fwd(const float* src, const float* bn_coef, int relu, const int32_t* rowptr, const int32_t* col,
                               const uint8_t* eattr, const float* B1, const float* B2, int64_t N, int D, float* out,
-                              int round_tf32_out, cudaStream_t stream);
+                              int round_tf32_out, float* out_lo /* optional: tf32 residual of the exact sum */,
+                              cudaStream_t stream);
 /* Backward (autograd of index_select/scatter_add_): gy[j] = sum_{out-edges e of j} ga[col_t[e]] + ga[j].
  * If z_prev != NULL additionally fuses the previous layer's ReLU backward and BatchNorm statistics:
  *   gy[j] *= [z_prev[j]*scale+shift > 0] (if relu);  partials[b][0] += gy, partials[b][1] += gy * (z_prev-mean)*invstd
@@ -114,7 +117,8 @@ int molclr_bn_bwd_apply(const float* gy, const float* gp, const int32_t* node2gr
 /* ---- global_mean_pool / global_add_pool: ginet_molclr.py:83-88,113 (pool_mode 0 = mean, 1 = add) ----
  * out[g] = w_g * sum_{n in graph g, node order} [relu](z[n]*scale + shift) */
 int molclr_pool_fwd(const float* z, const float* bn_coef, int relu, const int32_t* gptr, const int32_t* gperm,
-                    int pool_mode, int64_t G, int D, float* out, int round_tf32_out, cudaStream_t stream);
+                    int pool_mode, int64_t G, int D, float* out, int round_tf32_out, float* out_lo /* optional */,
+                    cudaStream_t stream);
 int molclr_pool_bwd_stats(const float* gp, const int32_t* node2graph, const int32_t* gptr, int pool_mode, const float* z,
                           const float* bn_coef, int64_t N, int D, float* partials, int* num_partials, cudaStream_t stream);
 
@@ -125,14 +129,20 @@ int molclr_pool_bwd_stats(const float* gp, const int32_t* node2graph, const int3
  * Epilogue, in this order: + bias[n]; + addend[m][n]; relu; * (mask[m][n] > 0); column statistics of the
  * result per 128-row tile (colstat_mode 1: sums -> colstat[tile][N]; 2: mean and M2 -> colstat[tile][2][N]);
  * out = (round_out ? tf32-rounded : exact); out2 = tf32-rounded copy.
+ * A_lo/B_lo (both or neither; same shape and ld as A/B): the tf32-rounded residuals x - tf32(x) of the true
+ * fp32 operands whose tf32-rounded values are in A/B.  When given, the product is error-compensated,
+ * A*B + A_lo*B + A*B_lo (three tensor-core passes, fp32 accumulate, ~fp32 accuracy) -- used by the forward
+ * pass so that ReLU masks match the fp32 reference.  out_lo receives the residual of the result.
  * split_k > 1 or transpose_out: raw products accumulated atomically into out (zeroed here first);
  * transpose_out stores C^T (out[n][m]).  No other epilogue option is allowed in that mode. */
 typedef struct {
   const float* A; int64_t lda; int32_t a_mn;
   const float* B; int64_t ldb; int32_t b_mn;
+  const float* A_lo; const float* B_lo;
   int64_t M, N, K;
   float* out; int64_t ldo; int32_t transpose_out;
   float* out2; int64_t ldo2;
+  float* out_lo; int64_t ldo_lo;
   const float* bias;
   const float* addend; int64_t ldadd;
   const float* mask; int64_t ldmask;
@@ -144,7 +154,8 @@ int molclr_gemm_colstat_tiles(int64_t M);
 int molclr_gemm_tf32(const molclr_gemm_args* args /* host */, cudaStream_t stream);
 
 /* ---- small elementwise ops ---------------------------------------------------------------------- */
-int molclr_round_tf32(const float* src, float* dst, int64_t n, cudaStream_t stream);
+/* hi = tf32(src); lo (optional) = tf32(src - hi) */
+int molclr_round_tf32(const float* src, float* hi, float* lo, int64_t n, cudaStream_t stream);
 /* F.normalize(z, dim=1), molclr.py:63-64 (eps 1e-12) and its backward */
 int molclr_l2_normalize_fwd(const float* z, int64_t R, int C, float eps, float* y, float* inv_norm, cudaStream_t stream);
 int molclr_l2_normalize_bwd(const float* gy, const float* y, const float* inv_norm, int64_t R, int C, float eps, float* gz,

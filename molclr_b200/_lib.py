@@ -19,9 +19,11 @@ class GemmArgs(C.Structure):
     _fields_ = [
         ("A", vp), ("lda", i64), ("a_mn", C.c_int32),
         ("B", vp), ("ldb", i64), ("b_mn", C.c_int32),
+        ("A_lo", vp), ("B_lo", vp),
         ("M", i64), ("N", i64), ("K", i64),
         ("out", vp), ("ldo", i64), ("transpose_out", C.c_int32),
         ("out2", vp), ("ldo2", i64),
+        ("out_lo", vp), ("ldo_lo", i64),
         ("bias", vp),
         ("addend", vp), ("ldadd", i64),
         ("mask", vp), ("ldmask", i64),
@@ -35,13 +37,14 @@ class GemmArgs(C.Structure):
 SIGNATURES = {
     "molclr_abi_version": (i32, []),
     "molclr_last_error": (C.c_char_p, []),
+    "molclr_launch_count": (C.c_uint64, []),
     "molclr_device_info": (i32, [C.POINTER(i32), C.POINTER(i32)]),
     "molclr_plan_workspace_bytes": (sz, [i64, i64, i64]),
     "molclr_plan_build": (i32, [vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp]),
     "molclr_embed_nodes_fwd": (i32, [vp, vp, vp, i64, i32, vp, vp]),
     "molclr_embed_nodes_bwd_blocks": (i32, [i32]),
     "molclr_embed_nodes_bwd": (i32, [vp, vp, i64, i32, vp, vp, vp]),
-    "molclr_gine_aggregate_fwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, i64, i32, vp, i32, vp]),
+    "molclr_gine_aggregate_fwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, i64, i32, vp, i32, vp, vp]),
     "molclr_rowwise_max_blocks": (i32, []),
     "molclr_gine_aggregate_bwd": (i32, [vp, vp, vp, vp, vp, i32, i64, i32, vp, vp, C.POINTER(i32), vp]),
     "molclr_edge_table_grad": (i32, [vp, vp, i64, i32, vp, vp, vp]),
@@ -50,11 +53,11 @@ SIGNATURES = {
     "molclr_bn_eval_coef": (i32, [vp, vp, vp, vp, f32, i32, vp, vp]),
     "molclr_bn_bwd_finalize": (i32, [vp, i32, i64, i32, vp, vp, i32, vp, vp, vp, vp]),
     "molclr_bn_bwd_apply": (i32, [vp, vp, vp, vp, i32, vp, vp, i64, i32, vp, vp, vp, vp]),
-    "molclr_pool_fwd": (i32, [vp, vp, i32, vp, vp, i32, i64, i32, vp, i32, vp]),
+    "molclr_pool_fwd": (i32, [vp, vp, i32, vp, vp, i32, i64, i32, vp, i32, vp, vp]),
     "molclr_pool_bwd_stats": (i32, [vp, vp, vp, i32, vp, vp, i64, i32, vp, C.POINTER(i32), vp]),
     "molclr_gemm_colstat_tiles": (i32, [i64]),
     "molclr_gemm_tf32": (i32, [C.POINTER(GemmArgs), vp]),
-    "molclr_round_tf32": (i32, [vp, vp, i64, vp]),
+    "molclr_round_tf32": (i32, [vp, vp, vp, i64, vp]),
     "molclr_l2_normalize_fwd": (i32, [vp, i64, i32, f32, vp, vp, vp]),
     "molclr_l2_normalize_bwd": (i32, [vp, vp, vp, i64, i32, f32, vp, vp]),
     "molclr_ntxent_workspace_bytes": (sz, [i64, i64, i32]),

@@ -14,8 +14,11 @@ namespace molclr {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 
+extern unsigned long long g_launches;   // kernels launched by this library (diagnostics: molclr_launch_count)
+
 #define MOLCLR_CHECK_LAUNCH(what)                                  \
   do {                                                             \
+    ++::molclr::g_launches;                                        \
     cudaError_t _e = cudaGetLastError();                           \
     if (_e != cudaSuccess) return ::molclr::cuda_fail(_e, what);   \
   } while (0)
@@ -49,6 +52,15 @@ __device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<fl
 
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+__device__ __forceinline__ float4 f4_tf32(float4 v) {
+  return make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+}
+// tf32( v - tf32(v) ): the "lo" half of the 2-term TF32 split used by the error-compensated GEMM
+__device__ __forceinline__ float4 f4_tf32_residual(float4 v) {
+  return make_float4(round_tf32(v.x - round_tf32(v.x)), round_tf32(v.y - round_tf32(v.y)), round_tf32(v.z - round_tf32(v.z)),
+                     round_tf32(v.w - round_tf32(v.w)));
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

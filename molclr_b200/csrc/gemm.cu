@@ -78,6 +78,10 @@ __device__ __forceinline__ float4 epilogue_apply(float4 v, const GemmParams& p, 
 __device__ __forceinline__ float4 f4_round(float4 v) {
   return make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
 }
+__device__ __forceinline__ float4 f4_residual(float4 v) {   // tf32( v - tf32(v) ): the "lo" half of a 2-term TF32 split
+  return make_float4(round_tf32(v.x - round_tf32(v.x)), round_tf32(v.y - round_tf32(v.y)), round_tf32(v.z - round_tf32(v.z)),
+                     round_tf32(v.w - round_tf32(v.w)));
+}
 
 // Column statistics of the finished tile held in `stage` (rows_valid x BN): mode 1 = sums,
 // mode 2 = (mean, M2) for the BatchNorm merge.  `tid` in [0, nthreads).
@@ -102,7 +106,8 @@ __device__ __forceinline__ void tile_colstat(const float* stage, int lds, int bn
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, (BN <= 160) ? 2 : 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -114,7 +119,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m_tile = blockIdx.y, m0 = m_tile * GEMM_BM;
   const int kb0 = blockIdx.z * p.kb_per_split;
-  const int nkb = min(p.num_kb, kb0 + p.kb_per_split) - kb0;
+  const int nkb_seg = min(p.num_kb, kb0 + p.kb_per_split) - kb0;
+  const int nkb = nkb_seg * p.segments;      // compensated mode walks K three times: (A,B) (A_lo,B) (A,B_lo)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1); }
@@ -122,6 +128,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
+    if (p.segments > 1) { ptx::prefetch_tensormap(&tmA2); ptx::prefetch_tensormap(&tmB2); }
   }
   if (warp == 1) { ptx::tmem_alloc(tmem_slot, GEMM_TMEM_COLS); ptx::tmem_relinquish(); }
   ptx::tc_fence_before();
@@ -138,13 +145,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::mbar_arrive_expect_tx(full_bar + s, Cfg::STAGE_BYTES);
         uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
         uint8_t* b_dst = a_dst + Cfg::A_BYTES;
-        const int kc = (kb0 + i) * GEMM_BK;
-        if (!p.a_mn) ptx::tma_load_2d(a_dst, &tmA, full_bar + s, kc, m0);
+        const int seg = i / nkb_seg;
+        const int kc = (kb0 + (i - seg * nkb_seg)) * GEMM_BK;
+        const CUtensorMap* ma = (seg == 1) ? &tmA2 : &tmA;
+        const CUtensorMap* mb = (seg == 2) ? &tmB2 : &tmB;
+        if (!p.a_mn) ptx::tma_load_2d(a_dst, ma, full_bar + s, kc, m0);
         else
-          for (int j = 0; j < GEMM_BM / 32; ++j) ptx::tma_load_2d(a_dst + j * 4096, &tmA, full_bar + s, m0 + 32 * j, kc);
-        if (!p.b_mn) ptx::tma_load_2d(b_dst, &tmB, full_bar + s, kc, n0);
+          for (int j = 0; j < GEMM_BM / 32; ++j) ptx::tma_load_2d(a_dst + j * 4096, ma, full_bar + s, m0 + 32 * j, kc);
+        if (!p.b_mn) ptx::tma_load_2d(b_dst, mb, full_bar + s, kc, n0);
         else
-          for (int j = 0; j < BN / 32; ++j) ptx::tma_load_2d(b_dst + j * 4096, &tmB, full_bar + s, n0 + 32 * j, kc);
+          for (int j = 0; j < BN / 32; ++j) ptx::tma_load_2d(b_dst + j * 4096, mb, full_bar + s, n0 + 32 * j, kc);
       }
     }
     __syncwarp();
@@ -161,8 +171,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t a_base = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES), b_base = a_base + Cfg::A_BYTES;
 #pragma unroll
         for (int k = 0; k < GEMM_BK / 8; ++k) {
-          const uint64_t ad = ptx::make_smem_desc(a_base + k * a_kstep, a_lbo, 1024u);
-          const uint64_t bd = ptx::make_smem_desc(b_base + k * b_kstep, b_lbo, 1024u);
+          const uint64_t ad = ptx::make_smem_desc(a_base + k * a_kstep, a_lbo, p.a_mn ? 512u : 1024u,
+                                                  p.a_mn ? ptx::kLayoutSw128Base32 : ptx::kLayoutSw128);
+          const uint64_t bd = ptx::make_smem_desc(b_base + k * b_kstep, b_lbo, p.b_mn ? 512u : 1024u,
+                                                  p.b_mn ? ptx::kLayoutSw128Base32 : ptx::kLayoutSw128);
           ptx::mma_tf32_ss(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
         }
         ptx::mma_commit(empty_bar + s);          // frees the smem slot once these MMAs have read it
@@ -241,6 +253,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (p.colstat) st_f4(stage + r * Cfg::LDS + 4 * c4, v);
           if (p.out) st_f4(p.out + (size_t)gr * p.ldo + col, p.round_out ? f4_round(v) : v);
           if (p.out2) st_f4(p.out2 + (size_t)gr * p.ldo2 + col, f4_round(v));
+          if (p.out_lo) st_f4(p.out_lo + (size_t)gr * p.ldo_lo + col, f4_residual(v));
         }
       }
       if (p.colstat) {
@@ -258,7 +271,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // Debug implementation: plain fp32 FMA, one thread per output row, 32 columns per block.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) gemm_simt_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B,
-                                                        long long ldb, const GemmParams p) {
+                                                        long long ldb, const float* __restrict__ A_lo, const float* __restrict__ B_lo,
+                                                        const GemmParams p) {
   __shared__ float stage[GEMM_BM * 33];
   const int n0 = blockIdx.x * 32, m_tile = blockIdx.y, m0 = m_tile * GEMM_BM;
   const int row = threadIdx.x, grow = m0 + row;
@@ -268,11 +282,15 @@ __global__ void __launch_bounds__(128) gemm_simt_kernel(const float* __restrict_
   for (int j = 0; j < 32; ++j) acc[j] = 0.f;
   if (grow < p.M) {
     for (int k = 0; k < p.K; ++k) {
-      const float a = p.a_mn ? A[(size_t)k * lda + grow] : A[(size_t)grow * lda + k];
+      const size_t ai = p.a_mn ? (size_t)k * lda + grow : (size_t)grow * lda + k;
+      const float a = A[ai] + (p.segments > 1 ? A_lo[ai] : 0.f);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int col = n0 + j;
-        if (col < p.N) acc[j] = fmaf(a, p.b_mn ? B[(size_t)k * ldb + col] : B[(size_t)col * ldb + k], acc[j]);
+        if (col < p.N) {
+          const size_t bi = p.b_mn ? (size_t)k * ldb + col : (size_t)col * ldb + k;
+          acc[j] = fmaf(a, B[bi] + (p.segments > 1 ? B_lo[bi] : 0.f), acc[j]);
+        }
       }
     }
   }
@@ -309,6 +327,7 @@ __global__ void __launch_bounds__(128) gemm_simt_kernel(const float* __restrict_
         v = epilogue_apply(v, p, grow, col);
         if (p.out) st_f4(p.out + (size_t)grow * p.ldo + col, p.round_out ? f4_round(v) : v);
         if (p.out2) st_f4(p.out2 + (size_t)grow * p.ldo2 + col, f4_round(v));
+        if (p.out_lo) st_f4(p.out_lo + (size_t)grow * p.ldo_lo + col, f4_residual(v));
       }
     }
     stage[row * 33 + j] = v.x; stage[row * 33 + j + 1] = v.y; stage[row * 33 + j + 2] = v.z; stage[row * 33 + j + 3] = v.w;
@@ -340,7 +359,11 @@ static EncodeTiledFn encode_tiled_fn() {
 
 // Tensor map over a row-major fp32 matrix [outer][inner] with leading dimension ld (elements),
 // box = [box_outer][32 inner elements], 128-byte swizzle, zero fill out of bounds.
-static int make_tmap(CUtensorMap* m, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_outer) {
+static int make_tmap(CUtensorMap* m, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_outer, bool mn_major) {
+  // cuTensorMapEncodeTiled is a driver-API call: make sure this thread (e.g. the autograd engine's) has the
+  // primary context bound before the first one.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
   EncodeTiledFn enc = encode_tiled_fn();
   MOLCLR_REQUIRE(enc != nullptr, "gemm: cuTensorMapEncodeTiled not available from the driver");
   MOLCLR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "gemm: operand base pointer must be 16-byte aligned");
@@ -350,7 +373,8 @@ static int make_tmap(CUtensorMap* m, const float* base, int64_t inner, int64_t o
   cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MOLCLR_REQUIRE(r == CUDA_SUCCESS, "gemm: cuTensorMapEncodeTiled failed with CUresult %d (inner=%lld outer=%lld ld=%lld)", (int)r,
                  (long long)inner, (long long)outer, (long long)ld);
@@ -360,20 +384,27 @@ static int make_tmap(CUtensorMap* m, const float* base, int64_t inner, int64_t o
 template <int BN>
 static int launch_tc(const GemmJob& j, const GemmParams& p, int n_tiles, int m_tiles, int splits, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmA2, tmB2;
   int rc;
   // K-major operand [rows][K]: inner = K, outer = rows, box = rows-per-tile x 32.  MN-major [K][rows]: inner = rows, outer = K, box 32 x 32.
-  rc = p.a_mn ? make_tmap(&tmA, j.A, p.M, p.K, j.lda, 32) : make_tmap(&tmA, j.A, p.K, p.M, j.lda, GEMM_BM);
+  rc = p.a_mn ? make_tmap(&tmA, j.A, p.M, p.K, j.lda, 32, true) : make_tmap(&tmA, j.A, p.K, p.M, j.lda, GEMM_BM, false);
   if (rc) return rc;
-  rc = p.b_mn ? make_tmap(&tmB, j.B, p.N, p.K, j.ldb, 32) : make_tmap(&tmB, j.B, p.K, p.N, j.ldb, BN);
+  rc = p.b_mn ? make_tmap(&tmB, j.B, p.N, p.K, j.ldb, 32, true) : make_tmap(&tmB, j.B, p.K, p.N, j.ldb, BN, false);
   if (rc) return rc;
+  tmA2 = tmA; tmB2 = tmB;
+  if (p.segments > 1) {
+    rc = p.a_mn ? make_tmap(&tmA2, j.A_lo, p.M, p.K, j.lda, 32, true) : make_tmap(&tmA2, j.A_lo, p.K, p.M, j.lda, GEMM_BM, false);
+    if (rc) return rc;
+    rc = p.b_mn ? make_tmap(&tmB2, j.B_lo, p.N, p.K, j.ldb, 32, true) : make_tmap(&tmB2, j.B_lo, p.K, p.N, j.ldb, BN, false);
+    if (rc) return rc;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "gemm: cudaFuncSetAttribute");
     attr_set = true;
   }
-  gemm_tf32_kernel<BN><<<dim3(n_tiles, m_tiles, splits), GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  gemm_tf32_kernel<BN><<<dim3(n_tiles, m_tiles, splits), GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
   MOLCLR_CHECK_LAUNCH("gemm_tf32");
   return 0;
 }
@@ -397,8 +428,10 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   MOLCLR_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
   MOLCLR_REQUIRE(p.N % 4 == 0, "gemm: N=%d must be a multiple of 4", p.N);
   const bool atomic = job.split_k > 1 || p.transpose_out;
+  MOLCLR_REQUIRE((job.A_lo == nullptr) == (job.B_lo == nullptr), "gemm: A_lo and B_lo must be given together");
+  p.segments = job.A_lo ? 3 : 1;
   if (atomic)
-    MOLCLR_REQUIRE(p.epi == EPI_GENERIC && !p.bias && !p.addend && !p.mask && !p.relu && !p.round_out && !p.out2 && !p.colstat && p.out &&
+    MOLCLR_REQUIRE(p.segments == 1 && !p.out_lo && p.epi == EPI_GENERIC && !p.bias && !p.addend && !p.mask && !p.relu && !p.round_out && !p.out2 && !p.colstat && p.out &&
                        p.alpha == 1.f,
                    "gemm: split-K / transposed output supports no fused epilogue");
   else if (p.epi != EPI_NTX_FWD) {
@@ -420,7 +453,7 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   }
   if (gemm_impl_simt()) {
     p.kb_per_split = p.num_kb;
-    gemm_simt_kernel<<<dim3((unsigned)((p.N + 31) / 32), m_tiles, 1), 128, 0, stream>>>(job.A, job.lda, job.B, job.ldb, p);
+    gemm_simt_kernel<<<dim3((unsigned)((p.N + 31) / 32), m_tiles, 1), 128, 0, stream>>>(job.A, job.lda, job.B, job.ldb, job.A_lo, job.B_lo, p);
     MOLCLR_CHECK_LAUNCH("gemm_simt");
     return 0;
   }
@@ -440,9 +473,11 @@ extern "C" int molclr_gemm_tf32(const molclr_gemm_args* args, cudaStream_t strea
   GemmJob j;
   memset(&j, 0, sizeof(j));
   j.A = a.A; j.lda = a.lda; j.B = a.B; j.ldb = a.ldb; j.split_k = a.split_k;
+  j.A_lo = a.A_lo; j.B_lo = a.B_lo;
   GemmParams& p = j.p;
   p.M = (int)a.M; p.N = (int)a.N; p.K = (int)a.K; p.a_mn = a.a_mn; p.b_mn = a.b_mn;
   p.out = a.out; p.ldo = a.ldo; p.transpose_out = a.transpose_out; p.out2 = a.out2; p.ldo2 = a.ldo2;
+  p.out_lo = a.out_lo; p.ldo_lo = a.ldo_lo;
   p.bias = a.bias; p.addend = a.addend; p.ldadd = a.ldadd; p.mask = a.mask; p.ldmask = a.ldmask;
   p.relu = a.relu; p.round_out = a.round_out; p.colstat = a.colstat; p.colstat_mode = a.colstat_mode;
   p.alpha = 1.f; p.epi = EPI_GENERIC;

@@ -11,8 +11,10 @@ struct GemmParams {
   int M, N, K;
   int a_mn, b_mn;
   int num_kb, kb_per_split;
+  int segments;                // 1: plain TF32.  3: error-compensated  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (~fp32 accuracy)
   float* out; long long ldo; int transpose_out;
   float* out2; long long ldo2;
+  float* out_lo; long long ldo_lo;   // tf32-rounded residual  v - round_tf32(v)  (compensated-precision consumers)
   const float* bias;
   const float* addend; long long ldadd;
   const float* mask; long long ldmask;
@@ -34,6 +36,7 @@ struct GemmParams {
 
 struct GemmJob {
   const float* A; long long lda; const float* B; long long ldb;
+  const float* A_lo; const float* B_lo;   // both non-null selects the 3-segment compensated product (same layout/ld as A, B)
   int split_k;
   GemmParams p;                // M,N,K,a_mn,b_mn and the epilogue fields filled by the caller
 };

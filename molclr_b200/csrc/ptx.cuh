@@ -89,16 +89,18 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// Shared-memory matrix descriptor, 128-byte swizzle, fp32/tf32 elements (32 per swizzle row).
-//  K-major  tile [rows][32 k]:  8-row groups 1024 B apart (SBO); LBO unused.
-//  MN-major tile [32 k][32 mn] blocks: blocks along MN `lbo_bytes` apart (LBO), 8-k groups 1024 B apart (SBO).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptor for fp32/tf32 tiles whose rows are 128 bytes (32 elements).
+//  K-major  tile [rows][32 k], SWIZZLE_128B (layout 2): 8-row groups 1024 B apart (SBO); LBO unused.
+//  MN-major tile [32 k][32 mn] blocks, SWIZZLE_128B_BASE32B (layout 1) -- the only swizzle the tensor core accepts
+//  for MN-major 32-bit operands: blocks along MN `lbo_bytes` apart (LBO), 4-k-row groups 512 B apart (SBO).
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;      // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;      // SWIZZLE_128B
+  d |= (uint64_t)layout << 61;
   return d;
 }
 

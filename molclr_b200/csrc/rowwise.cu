@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_fwd_kernel(
     const float* __restrict__ src, const float* __restrict__ coef, int relu,
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const uint8_t* __restrict__ eattr,
     const float* __restrict__ B1, const float* __restrict__ B2, int N, int D, float* __restrict__ out,
-    int round_out) {
+    int round_out, float* __restrict__ out_lo) {
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* ee = sm4;                       // [15][D4]
@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_fwd_kernel(
       const int q = lane + 32 * j;
       if (q < D4) {
         float4 r = f4_add(acc[j], f4_add(act(self[j], q), ee[kSelfLoopAttr * D4 + q]));   // self loop LAST
-        if (round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
+        if (out_lo) st_f4(out_lo + (size_t)i * D + 4 * q, f4_tf32_residual(r));
+        if (round_out) r = f4_tf32(r);
         st_f4(out + (size_t)i * D + 4 * q, r);
       }
     }
@@ -465,7 +466,8 @@ __global__ void __launch_bounds__(kRowThreads) bn_bwd_apply_kernel(
 template <int NCH>
 __global__ void __launch_bounds__(kRowThreads) pool_fwd_kernel(
     const float* __restrict__ z, const float* __restrict__ coef, int relu, const int32_t* __restrict__ gptr,
-    const int32_t* __restrict__ gperm, int pool_mean, int G, int D, float* __restrict__ out, int round_out) {
+    const int32_t* __restrict__ gperm, int pool_mean, int G, int D, float* __restrict__ out, int round_out,
+    float* __restrict__ out_lo) {
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* sc = sm4; float4* sh = sm4 + D4;
@@ -499,7 +501,8 @@ __global__ void __launch_bounds__(kRowThreads) pool_fwd_kernel(
       if (q < D4) {
         float4 r = acc[j];
         if (pool_mean) { r.x /= cntf; r.y /= cntf; r.z /= cntf; r.w /= cntf; }
-        if (round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
+        if (out_lo) st_f4(out_lo + (size_t)g * D + 4 * q, f4_tf32_residual(r));
+        if (round_out) r = f4_tf32(r);
         st_f4(out + (size_t)g * D + 4 * q, r);
       }
     }
@@ -546,10 +549,14 @@ __global__ void __launch_bounds__(kRowThreads) pool_bwd_stats_kernel(
 // ------------------------------------------------------------------------------------------------
 // Small elementwise helpers
 // ------------------------------------------------------------------------------------------------
-__global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
+__global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) dst[i] = round_tf32(src[i]);
+  for (; i < n; i += stride) {
+    const float v = src[i], h = round_tf32(v);
+    hi[i] = h;
+    if (lo) lo[i] = round_tf32(v - h);
+  }
 }
 
 // F.normalize(z, dim=1) (molclr.py:63-64; eps = 1e-12): y = z / max(||z||, eps).  One warp per row.
@@ -632,7 +639,7 @@ extern "C" int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, in
 
 extern "C" int molclr_gine_aggregate_fwd(const float* src, const float* bn_coef, int relu, const int32_t* rowptr,
                                          const int32_t* col, const uint8_t* eattr, const float* B1, const float* B2,
-                                         int64_t N, int D, float* out, int round_tf32_out, cudaStream_t stream) {
+                                         int64_t N, int D, float* out, int round_tf32_out, float* out_lo, cudaStream_t stream) {
   REQUIRE_D(D);
   if (N == 0) return 0;
   const size_t smem = (size_t)(kNumEdgeClass + 2) * D * sizeof(float);
@@ -640,11 +647,11 @@ extern "C" int molclr_gine_aggregate_fwd(const float* src, const float* bn_coef,
     if (bn_coef) {
       auto k = gine_aggregate_fwd_kernel<NCH, true>;
       k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
-          src, bn_coef, relu, rowptr, col, eattr, B1, B2, (int)N, D, out, round_tf32_out);
+          src, bn_coef, relu, rowptr, col, eattr, B1, B2, (int)N, D, out, round_tf32_out, out_lo);
     } else {
       auto k = gine_aggregate_fwd_kernel<NCH, false>;
       k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
-          src, nullptr, 0, rowptr, col, eattr, B1, B2, (int)N, D, out, round_tf32_out);
+          src, nullptr, 0, rowptr, col, eattr, B1, B2, (int)N, D, out, round_tf32_out, out_lo);
     }
   });
   MOLCLR_CHECK_LAUNCH("gine_aggregate_fwd");
@@ -745,7 +752,7 @@ extern "C" int molclr_bn_bwd_apply(const float* gy, const float* gp, const int32
 }
 
 extern "C" int molclr_pool_fwd(const float* z, const float* bn_coef, int relu, const int32_t* gptr, const int32_t* gperm,
-                               int pool_mode, int64_t G, int D, float* out, int round_tf32_out, cudaStream_t stream) {
+                               int pool_mode, int64_t G, int D, float* out, int round_tf32_out, float* out_lo, cudaStream_t stream) {
   REQUIRE_D(D);
   MOLCLR_REQUIRE(pool_mode == 0 || pool_mode == 1, "pool mode %d not supported (0 = mean, 1 = add)", pool_mode);
   if (G == 0) return 0;
@@ -753,7 +760,7 @@ extern "C" int molclr_pool_fwd(const float* z, const float* bn_coef, int relu, c
   NCH_DISPATCH(D / 4, {
     auto k = pool_fwd_kernel<NCH>;
     k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, G), kRowThreads, smem, stream>>>(z, bn_coef, relu, gptr, gperm,
-                                                                                          pool_mode == 0, (int)G, D, out, round_tf32_out);
+                                                                                          pool_mode == 0, (int)G, D, out, round_tf32_out, out_lo);
   });
   MOLCLR_CHECK_LAUNCH("pool_fwd");
   return 0;
@@ -775,11 +782,11 @@ extern "C" int molclr_pool_bwd_stats(const float* gp, const int32_t* node2graph,
   return 0;
 }
 
-extern "C" int molclr_round_tf32(const float* src, float* dst, int64_t n, cudaStream_t stream) {
+extern "C" int molclr_round_tf32(const float* src, float* dst, float* lo, int64_t n, cudaStream_t stream) {
   if (n == 0) return 0;
   int64_t blocks = (n + 1023) / 1024;
   if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
-  round_tf32_kernel<<<(int)blocks, 256, 0, stream>>>(src, dst, n);
+  round_tf32_kernel<<<(int)blocks, 256, 0, stream>>>(src, dst, lo, n);
   MOLCLR_CHECK_LAUNCH("round_tf32");
   return 0;
 }

@@ -41,8 +41,8 @@ class GINEConv(nn.Module):
 
 
 class _RoundedWeights:
-    """TF32-rounded shadow copies of the GEMM weights, refreshed only when a parameter changed
-    (tracked through the tensor version counter the optimizer bumps)."""
+    """TF32 (hi, lo) shadow copies of the GEMM weights -- hi = tf32(w), lo = tf32(w - hi) -- refreshed only
+    when a parameter changed (tracked through the tensor version counter the optimizer bumps)."""
 
     def __init__(self):
         self._cache = {}
@@ -50,15 +50,27 @@ class _RoundedWeights:
     def get(self, p):
         key = id(p)
         hit = self._cache.get(key)
-        if hit is not None and hit[0] == p._version and hit[1].data_ptr() != 0 and hit[2] == p.data_ptr():
+        if hit is not None and hit[0] == p._version and hit[2] == p.data_ptr():
             return hit[1]
-        r = ops.round_tf32(p.detach())
+        r = ops.split_tf32(p.detach())
         self._cache[key] = (p._version, r, p.data_ptr())
         return r
 
 
+PRECISIONS = ("tf32x3", "tf32")
+
+
 class _EncoderBase(nn.Module):
-    """Shared plumbing of the GINet / GCN drop-ins."""
+    """Shared plumbing of the GINet / GCN drop-ins.
+
+    ``precision`` (attribute, not a constructor argument -- the constructor is the reference's):
+      * ``"tf32x3"`` (default): every FORWARD contraction is the error-compensated 3-pass TF32 product
+        (~fp32 accuracy), so pre-activations -- and with them the ReLU masks the backward pass depends on --
+        match the fp32 reference; BACKWARD contractions are single-pass TF32.
+      * ``"tf32"``: single-pass TF32 everywhere (fastest; activations carry ~1e-3 relative error and the
+        resulting ReLU mask flips show up as percent-level noise in gradients).
+    """
+    precision = "tf32x3"
 
     def _check_input(self, data):
         if self.training and self.drop_ratio > 0:
@@ -113,18 +125,25 @@ class GINet(_EncoderBase):
         return h, out
 
 
-def _head_forward(m, p, rw):
+def _lo(x, comp):
+    return x if comp else None
+
+
+def _head_forward(m, p, p_lo, rw, comp):
     """h = feat_lin(p); out = out_lin(h)   (ginet_molclr.py:114-115).  Returns h, out and what backward needs."""
     G, D, Fd = p.shape[0], m.emb_dim, m.feat_dim
     dev = p.device
-    Wf, W0, W2 = rw.get(m.feat_lin.weight), rw.get(m.out_lin[0].weight), rw.get(m.out_lin[2].weight)
+    (Wf, Wf_lo), (W0, W0_lo), (W2, W2_lo) = rw.get(m.feat_lin.weight), rw.get(m.out_lin[0].weight), rw.get(m.out_lin[2].weight)
     h = torch.empty(G, Fd, device=dev)
     h_r = torch.empty(G, Fd, device=dev)
-    ops.gemm(p, Wf, G, Fd, D, out=h, out2=h_r, bias=m.feat_lin.bias.detach())
+    h_lo = torch.empty(G, Fd, device=dev) if comp else None
+    ops.gemm(p, Wf, G, Fd, D, A_lo=p_lo, B_lo=_lo(Wf_lo, comp), out=h, out2=h_r, out_lo=h_lo, bias=m.feat_lin.bias.detach())
     r = torch.empty(G, Fd, device=dev)
-    ops.gemm(h_r, W0, G, Fd, Fd, out=r, bias=m.out_lin[0].bias.detach(), relu=True, round_out=True)
+    r_lo = torch.empty(G, Fd, device=dev) if comp else None
+    ops.gemm(h_r, W0, G, Fd, Fd, A_lo=h_lo, B_lo=_lo(W0_lo, comp), out=r, out_lo=r_lo, bias=m.out_lin[0].bias.detach(),
+             relu=True, round_out=True)
     out = torch.empty(G, Fd // 2, device=dev)
-    ops.gemm(r, W2, G, Fd // 2, Fd, out=out, bias=m.out_lin[2].bias.detach())
+    ops.gemm(r, W2, G, Fd // 2, Fd, A_lo=r_lo, B_lo=_lo(W2_lo, comp), out=out, bias=m.out_lin[2].bias.detach())
     return h, out, (h_r, r, Wf, W0, W2)
 
 
@@ -163,6 +182,9 @@ class _GINetFunction(torch.autograd.Function):
         L, D, H, N = m.num_layer, m.emb_dim, 2 * m.emb_dim, plan.N
         dev = params[0].device
         rw = m._rounded
+        if m.precision not in PRECISIONS:
+            raise ValueError(f"molclr_b200: precision must be one of {PRECISIONS}, got {m.precision!r}")
+        comp = m.precision == "tf32x3"
         training = m.training
         pool_mode = ops.POOL_MODES[m.pool_name]
         h0 = ops.embed_nodes_fwd(plan, m.x_embedding1.weight.detach(), m.x_embedding2.weight.detach())
@@ -171,25 +193,32 @@ class _GINetFunction(torch.autograd.Function):
         T = ops.colstat_tiles(N)
         for l in range(L):
             g, bn = m.gnns[l], m.batch_norms[l]
-            a = ops.gine_aggregate_fwd(plan, src, g.edge_embedding1.weight.detach(), g.edge_embedding2.weight.detach(),
-                                       bn_coef=coef_prev, relu=True, round_out=True)
-            W1, W2 = rw.get(g.mlp[0].weight), rw.get(g.mlp[2].weight)
+            a, a_lo = ops.gine_aggregate_fwd(plan, src, g.edge_embedding1.weight.detach(), g.edge_embedding2.weight.detach(),
+                                             bn_coef=coef_prev, relu=True, round_out=True, want_lo=True) if comp else \
+                (ops.gine_aggregate_fwd(plan, src, g.edge_embedding1.weight.detach(), g.edge_embedding2.weight.detach(),
+                                        bn_coef=coef_prev, relu=True, round_out=True), None)
+            (W1, W1_lo), (W2, W2_lo) = rw.get(g.mlp[0].weight), rw.get(g.mlp[2].weight)
             u = torch.empty(N, H, device=dev)
-            ops.gemm(a, W1, N, H, D, out=u, bias=g.mlp[0].bias.detach(), relu=True, round_out=True)
+            u_lo = torch.empty(N, H, device=dev) if comp else None
+            ops.gemm(a, W1, N, H, D, A_lo=a_lo, B_lo=_lo(W1_lo, comp), out=u, out_lo=u_lo, bias=g.mlp[0].bias.detach(),
+                     relu=True, round_out=True)
             z = torch.empty(N, D, device=dev)
             if training:
                 stats = torch.empty(T, 2, D, device=dev)
-                ops.gemm(u, W2, N, D, H, out=z, bias=g.mlp[2].bias.detach(), colstat=stats, colstat_mode=2)
+                ops.gemm(u, W2, N, D, H, A_lo=u_lo, B_lo=_lo(W2_lo, comp), out=z, bias=g.mlp[2].bias.detach(), colstat=stats,
+                         colstat_mode=2)
                 momentum = 0.1 if bn.momentum is None else bn.momentum
                 coef = ops.bn_fwd_finalize(stats, T, N, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
                                            bn.num_batches_tracked, momentum, bn.eps)
             else:
-                ops.gemm(u, W2, N, D, H, out=z, bias=g.mlp[2].bias.detach())
+                ops.gemm(u, W2, N, D, H, A_lo=u_lo, B_lo=_lo(W2_lo, comp), out=z, bias=g.mlp[2].bias.detach())
                 coef = ops.bn_eval_coef(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
             layers.append((a, u, z, coef, W1, W2))
             src, coef_prev = z, coef
-        p = ops.pool_fwd(plan, src, coef_prev, pool_mode, relu=False, round_out=True)
-        h, out, head_saved = _head_forward(m, p, rw)
+            del a_lo, u_lo
+        p, p_lo = ops.pool_fwd(plan, src, coef_prev, pool_mode, relu=False, round_out=True, want_lo=True) if comp else \
+            (ops.pool_fwd(plan, src, coef_prev, pool_mode, relu=False, round_out=True), None)
+        h, out, head_saved = _head_forward(m, p, p_lo, rw, comp)
         ctx.m, ctx.plan, ctx.layers, ctx.p, ctx.head_saved = m, plan, layers, p, head_saved
         ctx.training, ctx.pool_mode = training, pool_mode
         return h, out

@@ -22,18 +22,20 @@ def max_blocks():
 
 
 # ------------------------------------------------------------------------------------------- GEMM
-def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, out=None, out2=None, bias=None, addend=None, mask=None,
-         relu=False, round_out=False, colstat=None, colstat_mode=0, transpose_out=False, split_k=1,
-         lda=None, ldb=None):
+def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=None, out2=None, out_lo=None, bias=None,
+         addend=None, mask=None, relu=False, round_out=False, colstat=None, colstat_mode=0, transpose_out=False,
+         split_k=1, lda=None, ldb=None):
     """C[M,N] = sum_k A(m,k) B(n,k) on tcgen05 (TF32 in, FP32 accumulate) with the fused epilogue of
     ``molclr_gemm_tf32`` (see include/molclr_b200.h)."""
     lib = _lib.load()
     a = GemmArgs()
     a.A, a.lda, a.a_mn = ptr(A), (A.stride(0) if lda is None else lda), int(a_mn)
     a.B, a.ldb, a.b_mn = ptr(B), (B.stride(0) if ldb is None else ldb), int(b_mn)
+    a.A_lo, a.B_lo = ptr(A_lo), ptr(B_lo)
     a.M, a.N, a.K = M, N, K
     a.out, a.ldo, a.transpose_out = ptr(out), (out.stride(0) if out is not None else 0), int(transpose_out)
     a.out2, a.ldo2 = ptr(out2), (out2.stride(0) if out2 is not None else 0)
+    a.out_lo, a.ldo_lo = ptr(out_lo), (out_lo.stride(0) if out_lo is not None else 0)
     a.bias = ptr(bias)
     a.addend, a.ldadd = ptr(addend), (addend.stride(0) if addend is not None else 0)
     a.mask, a.ldmask = ptr(mask), (mask.stride(0) if mask is not None else 0)
@@ -93,8 +95,15 @@ def reduce_partials(partials, P, length, out):
 
 def round_tf32(x):
     out = torch.empty_like(x)
-    check(_lib.load().molclr_round_tf32(ptr(x), ptr(out), x.numel(), stream()), "round_tf32")
+    check(_lib.load().molclr_round_tf32(ptr(x), ptr(out), None, x.numel(), stream()), "round_tf32")
     return out
+
+
+def split_tf32(x):
+    """(hi, lo) with hi = tf32(x), lo = tf32(x - hi): operands of the error-compensated product."""
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    check(_lib.load().molclr_round_tf32(ptr(x), ptr(hi), ptr(lo), x.numel(), stream()), "round_tf32")
+    return hi, lo
 
 
 # ------------------------------------------------------------------------------------------- row-wise
@@ -116,13 +125,15 @@ def embed_nodes_bwd(plan, g):
     return dE[:119], dE[119:]
 
 
-def gine_aggregate_fwd(plan, src, B1, B2, bn_coef=None, relu=True, round_out=True):
+def gine_aggregate_fwd(plan, src, B1, B2, bn_coef=None, relu=True, round_out=True, want_lo=False):
+    """Returns the aggregate (tf32-rounded if round_out), plus its tf32 residual when want_lo."""
     D = src.shape[1]
     out = torch.empty_like(src)
+    lo = torch.empty_like(src) if want_lo else None
     check(_lib.load().molclr_gine_aggregate_fwd(ptr(src), ptr(bn_coef), int(relu), ptr(plan.rowptr, torch.int32),
                                                 ptr(plan.col, torch.int32), ptr(plan.eattr, torch.uint8), ptr(B1), ptr(B2),
-                                                plan.N, D, ptr(out), int(round_out), stream()), "gine_aggregate_fwd")
-    return out
+                                                plan.N, D, ptr(out), int(round_out), ptr(lo), stream()), "gine_aggregate_fwd")
+    return (out, lo) if want_lo else out
 
 
 def gine_aggregate_bwd(plan, ga, z_prev=None, bn_coef=None, relu=True):
@@ -186,12 +197,13 @@ def bn_bwd_apply(z, bcoef, gy=None, gp=None, plan=None, pool_mean=True):
 POOL_MODES = {"mean": 0, "add": 1}
 
 
-def pool_fwd(plan, z, bn_coef, pool_mode, relu=False, round_out=True):
+def pool_fwd(plan, z, bn_coef, pool_mode, relu=False, round_out=True, want_lo=False):
     D = z.shape[1]
     out = _empty(plan.G, D, device=z.device)
+    lo = _empty(plan.G, D, device=z.device) if want_lo else None
     check(_lib.load().molclr_pool_fwd(ptr(z), ptr(bn_coef), int(relu), ptr(plan.gptr, torch.int32), ptr(plan.gperm, torch.int32),
-                                      pool_mode, plan.G, D, ptr(out), int(round_out), stream()), "pool_fwd")
-    return out
+                                      pool_mode, plan.G, D, ptr(out), int(round_out), ptr(lo), stream()), "pool_fwd")
+    return (out, lo) if want_lo else out
 
 
 def pool_bwd_stats(plan, gp, z, bn_coef, pool_mode):

