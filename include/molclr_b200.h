@@ -127,7 +127,7 @@ int molclr_pool_bwd_stats(const float* gp, const int32_t* node2graph, const int3
  * C[M][N] = sum_k A(m,k) * B(n,k).
  *   a_mn = 0: A is row-major [M][K] (ld = lda);  a_mn = 1: A is row-major [K][M].   Same for B with N.
  * Epilogue, in this order: + bias[n]; + addend[m][n]; relu; * (mask[m][n] > 0); column statistics of the
- * result per 128-row tile (colstat_mode 1: sums -> colstat[tile][N]; 2: mean and M2 -> colstat[tile][2][N]);
+ * result per 32-row group (colstat_mode 1: sums -> colstat[group][N]; 2: mean and M2 -> colstat[group][2][N]);
  * out = (round_out ? tf32-rounded : exact); out2 = tf32-rounded copy.
  * A_lo/B_lo (both or neither; same shape and ld as A/B): the tf32-rounded residuals x - tf32(x) of the true
  * fp32 operands whose tf32-rounded values are in A/B.  When given, the product is error-compensated,
@@ -150,7 +150,10 @@ typedef struct {
   float* colstat; int32_t colstat_mode;
   int32_t split_k;
 } molclr_gemm_args;
+/* column statistics are emitted per group of molclr_gemm_colstat_tile_rows() (= 32) consecutive rows;
+ * molclr_gemm_colstat_tiles(M) groups are written (a multiple of 4; trailing groups may be empty). */
 int molclr_gemm_colstat_tiles(int64_t M);
+int molclr_gemm_colstat_tile_rows(void);
 int molclr_gemm_tf32(const molclr_gemm_args* args /* host */, cudaStream_t stream);
 
 /* ---- small elementwise ops ---------------------------------------------------------------------- */

@@ -56,6 +56,7 @@ SIGNATURES = {
     "molclr_pool_fwd": (i32, [vp, vp, i32, vp, vp, i32, i64, i32, vp, i32, vp, vp]),
     "molclr_pool_bwd_stats": (i32, [vp, vp, vp, i32, vp, vp, i64, i32, vp, C.POINTER(i32), vp]),
     "molclr_gemm_colstat_tiles": (i32, [i64]),
+    "molclr_gemm_colstat_tile_rows": (i32, []),
     "molclr_gemm_tf32": (i32, [C.POINTER(GemmArgs), vp]),
     "molclr_round_tf32": (i32, [vp, vp, vp, i64, vp]),
     "molclr_l2_normalize_fwd": (i32, [vp, i64, i32, f32, vp, vp, vp]),

@@ -25,23 +25,29 @@ namespace molclr {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 32;          // 32 tf32 = one 128-byte swizzle row
 constexpr int GEMM_THREADS = 192;    // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
-constexpr int GEMM_TMEM_COLS = 256;
+constexpr int GEMM_TMEM_COLS = 512;  // two accumulator buffers of up to 256 columns
+constexpr int GEMM_STAT_ROWS = 32;   // column statistics are emitted per 32-row group (one epilogue warp)
+constexpr int GEMM_CHUNK = 16;       // epilogue column chunk staged per warp
+constexpr int GEMM_CHUNK_LD = 20;    // staging pitch (floats): conflict-free float4 rows
+constexpr int GEMM_SMEM_LIMIT = 232448;
 
-template <int BN>
+// FOUR = compensated product with all four operand tiles (A_hi, A_lo, B_hi, B_lo) in one stage and three
+// MMAs per K-slice; otherwise one (A, B) pair per stage.
+template <int BN, bool FOUR>
 struct GemmCfg {
-  static constexpr int STAGES = 3;
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 4;
   static constexpr int B_BYTES = BN * GEMM_BK * 4;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = (FOUR ? 2 : 1) * (A_BYTES + B_BYTES);
+  static constexpr int STAGING_BYTES = 4 * 32 * GEMM_CHUNK_LD * 4;     // 4 epilogue warps x 32 rows x chunk
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int STAGES_RAW = (GEMM_SMEM_LIMIT - STAGING_BYTES - BAR_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int LDS = BN + 4;                         // staging pitch (floats): conflict-free float4 rows
-  static constexpr int STAGING_BYTES = GEMM_BM * LDS * 4;
-  static constexpr int MAIN_BYTES = PIPE_BYTES > STAGING_BYTES ? PIPE_BYTES : STAGING_BYTES;
-  static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /* alignment slack */ + 128 /* barriers + tmem ptr */;
+  static constexpr int SMEM_BYTES = PIPE_BYTES + STAGING_BYTES + BAR_BYTES;
   static_assert(BN % 32 == 0 && BN <= 256, "BN must be a multiple of 32 (MN-major B blocks) and <= 256");
-  static_assert(STAGE_BYTES % 1024 == 0, "stage bases must stay 1024B aligned for SWIZZLE_128B");
+  static_assert(STAGE_BYTES % 1024 == 0, "stage bases must stay 1024B aligned for the 128B swizzles");
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
 };
-
 
 __device__ __forceinline__ float ntx_w_elem(float acc, const GemmParams& p, float lse_r, long long grow_g, long long gcol) {
   // W[r][k] = P[r][k] + P[k][r] - 2*[k == pos(r)],  P[i][k] = exp(l - lse_i) for k != i   (nt_xent.py:53-65 differentiated)
@@ -75,56 +81,53 @@ __device__ __forceinline__ float4 epilogue_apply(float4 v, const GemmParams& p, 
   }
   return v;
 }
-__device__ __forceinline__ float4 f4_round(float4 v) {
-  return make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
-}
-__device__ __forceinline__ float4 f4_residual(float4 v) {   // tf32( v - tf32(v) ): the "lo" half of a 2-term TF32 split
-  return make_float4(round_tf32(v.x - round_tf32(v.x)), round_tf32(v.y - round_tf32(v.y)), round_tf32(v.z - round_tf32(v.z)),
-                     round_tf32(v.w - round_tf32(v.w)));
-}
 
-// Column statistics of the finished tile held in `stage` (rows_valid x BN): mode 1 = sums,
-// mode 2 = (mean, M2) for the BatchNorm merge.  `tid` in [0, nthreads).
-__device__ __forceinline__ void tile_colstat(const float* stage, int lds, int bn, int rows_valid, int n0, int m_tile,
-                                             const GemmParams& p, int tid, int nthreads) {
-  for (int c = tid; c < bn; c += nthreads) {
-    const int col = n0 + c;
+// Column statistics over rows [0, rows) of a staged sub-tile (`ncols` columns, pitch `lds`): mode 1 = sums,
+// mode 2 = (mean, M2) for the BatchNorm merge.  Written as partial row `group` of the colstat buffer.
+__device__ __forceinline__ void colstat_group(const float* stage, int lds, int ncols, int rows, int col0, int group,
+                                              const GemmParams& p, int tid, int nthreads) {
+  for (int c = tid; c < ncols; c += nthreads) {
+    const int col = col0 + c;
     if (col >= p.N) continue;
     float s = 0.f;
-    for (int r = 0; r < rows_valid; ++r) s += stage[r * lds + c];
+    for (int r = 0; r < rows; ++r) s += stage[r * lds + c];
     if (p.colstat_mode == 1) {
-      p.colstat[(size_t)m_tile * p.N + col] = s;
+      p.colstat[(size_t)group * p.N + col] = s;
     } else {
-      const float mean = s / (float)rows_valid;
+      const float mean = rows > 0 ? s / (float)rows : 0.f;
       float m2 = 0.f;
-      for (int r = 0; r < rows_valid; ++r) { const float d = stage[r * lds + c] - mean; m2 = fmaf(d, d, m2); }
-      p.colstat[((size_t)m_tile * 2) * p.N + col] = mean;
-      p.colstat[((size_t)m_tile * 2 + 1) * p.N + col] = m2;
+      for (int r = 0; r < rows; ++r) { const float d = stage[r * lds + c] - mean; m2 = fmaf(d, d, m2); }
+      p.colstat[((size_t)group * 2) * p.N + col] = mean;
+      p.colstat[((size_t)group * 2 + 1) * p.N + col] = m2;
     }
   }
 }
 
-template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, (BN <= 160) ? 2 : 1)
+// Persistent, warp-specialised tcgen05 GEMM.  Each CTA (one per SM) walks tiles t = blockIdx.x + i*gridDim.x of the
+// (n_tile fastest, m_tile, k_split) grid.  The TMA producer and the MMA issuer run ahead across tiles through a
+// STAGES-deep smem ring; accumulators are double-buffered in TMEM so the 4 epilogue warps drain tile i while the
+// tensor core works on tile i+1.
+template <int BN, bool FOUR>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::MAIN_BYTES);
+  using Cfg = GemmCfg<BN, FOUR>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* staging = reinterpret_cast<float*>(smem + Cfg::PIPE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::PIPE_BYTES + Cfg::STAGING_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;     // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;              // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m_tile = blockIdx.y, m0 = m_tile * GEMM_BM;
-  const int kb0 = blockIdx.z * p.kb_per_split;
-  const int nkb_seg = min(p.num_kb, kb0 + p.kb_per_split) - kb0;
-  const int nkb = nkb_seg * p.segments;      // compensated mode walks K three times: (A,B) (A_lo,B) (A,B_lo)
+  const int n_tiles = p.n_tiles, m_tiles = p.m_tiles;
+  const int total = n_tiles * m_tiles * p.splits;
 
   if (threadIdx.x == 0) {
+    if ((ptx::smem_u32(smem) & 1023u) != 0) { printf("molclr gemm: dynamic smem base not 1024B aligned\n"); __trap(); }
     for (int s = 0; s < Cfg::STAGES; ++s) { ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1); }
-    ptx::mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(tfull_bar + b, 1); ptx::mbar_init(tempty_bar + b, 4); }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
@@ -139,22 +142,34 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % Cfg::STAGES;
-        ptx::mbar_wait(empty_bar + s, ((i / Cfg::STAGES) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(full_bar + s, Cfg::STAGE_BYTES);
-        uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
-        uint8_t* b_dst = a_dst + Cfg::A_BYTES;
-        const int seg = i / nkb_seg;
-        const int kc = (kb0 + (i - seg * nkb_seg)) * GEMM_BK;
-        const CUtensorMap* ma = (seg == 1) ? &tmA2 : &tmA;
-        const CUtensorMap* mb = (seg == 2) ? &tmB2 : &tmB;
-        if (!p.a_mn) ptx::tma_load_2d(a_dst, ma, full_bar + s, kc, m0);
-        else
-          for (int j = 0; j < GEMM_BM / 32; ++j) ptx::tma_load_2d(a_dst + j * 4096, ma, full_bar + s, m0 + 32 * j, kc);
-        if (!p.b_mn) ptx::tma_load_2d(b_dst, mb, full_bar + s, kc, n0);
-        else
-          for (int j = 0; j < BN / 32; ++j) ptx::tma_load_2d(b_dst + j * 4096, mb, full_bar + s, n0 + 32 * j, kc);
+      uint32_t it = 0;                                  // global k-block counter -> ring slot / phase
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int n0 = (t % n_tiles) * BN, m0 = ((t / n_tiles) % m_tiles) * GEMM_BM;
+        const int kb0 = (t / (n_tiles * m_tiles)) * p.kb_per_split;
+        const int nkb_seg = min(p.num_kb, kb0 + p.kb_per_split) - kb0;
+        const int nkb = FOUR ? nkb_seg : nkb_seg * p.segments;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % Cfg::STAGES;
+          ptx::mbar_wait(empty_bar + s, ((it / Cfg::STAGES) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(full_bar + s, Cfg::STAGE_BYTES);
+          uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + (FOUR ? 2 : 1) * Cfg::A_BYTES;
+          const int seg = FOUR ? 0 : i / nkb_seg;
+          const int kc = (kb0 + (i - seg * nkb_seg)) * GEMM_BK;
+#pragma unroll
+          for (int h = 0; h < (FOUR ? 2 : 1); ++h) {
+            const CUtensorMap* ma = (FOUR ? h == 1 : seg == 1) ? &tmA2 : &tmA;
+            const CUtensorMap* mb = (FOUR ? h == 1 : seg == 2) ? &tmB2 : &tmB;
+            uint8_t* ad = a_dst + h * Cfg::A_BYTES;
+            uint8_t* bd = b_dst + h * Cfg::B_BYTES;
+            if (!p.a_mn) ptx::tma_load_2d(ad, ma, full_bar + s, kc, m0);
+            else
+              for (int j = 0; j < GEMM_BM / 32; ++j) ptx::tma_load_2d(ad + j * 4096, ma, full_bar + s, m0 + 32 * j, kc);
+            if (!p.b_mn) ptx::tma_load_2d(bd, mb, full_bar + s, kc, n0);
+            else
+              for (int j = 0; j < BN / 32; ++j) ptx::tma_load_2d(bd + j * 4096, mb, full_bar + s, n0 + 32 * j, kc);
+          }
+        }
       }
     }
     __syncwarp();
@@ -163,106 +178,135 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       const uint32_t idesc = ptx::make_idesc_tf32(BN, p.a_mn != 0, p.b_mn != 0);
       const uint32_t a_lbo = p.a_mn ? 4096u : 16u, b_lbo = p.b_mn ? 4096u : 16u;
+      const uint32_t a_sbo = p.a_mn ? 512u : 1024u, b_sbo = p.b_mn ? 512u : 1024u;
+      const uint32_t a_lay = p.a_mn ? ptx::kLayoutSw128Base32 : ptx::kLayoutSw128, b_lay = p.b_mn ? ptx::kLayoutSw128Base32 : ptx::kLayoutSw128;
       const uint32_t a_kstep = p.a_mn ? 1024u : 32u, b_kstep = p.b_mn ? 1024u : 32u;   // bytes per K=8 slice
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % Cfg::STAGES;
-        ptx::mbar_wait(full_bar + s, (i / Cfg::STAGES) & 1);
+      uint32_t it = 0, tl = 0;                          // tl = local tile counter -> accumulator buffer / phase
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
+        const int kb0 = (t / (n_tiles * m_tiles)) * p.kb_per_split;
+        const int nkb_seg = min(p.num_kb, kb0 + p.kb_per_split) - kb0;
+        const int nkb = FOUR ? nkb_seg : nkb_seg * p.segments;
+        const uint32_t buf = tl & 1;
+        ptx::mbar_wait(tempty_bar + buf, ((tl >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
         ptx::tc_fence_after();
-        const uint32_t a_base = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES), b_base = a_base + Cfg::A_BYTES;
+        const uint32_t d_tmem = tmem_base + buf * 256u;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % Cfg::STAGES;
+          ptx::mbar_wait(full_bar + s, (it / Cfg::STAGES) & 1);
+          ptx::tc_fence_after();
+          const uint32_t a_base = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint32_t b_base = a_base + (FOUR ? 2 : 1) * Cfg::A_BYTES;
 #pragma unroll
-        for (int k = 0; k < GEMM_BK / 8; ++k) {
-          const uint64_t ad = ptx::make_smem_desc(a_base + k * a_kstep, a_lbo, p.a_mn ? 512u : 1024u,
-                                                  p.a_mn ? ptx::kLayoutSw128Base32 : ptx::kLayoutSw128);
-          const uint64_t bd = ptx::make_smem_desc(b_base + k * b_kstep, b_lbo, p.b_mn ? 512u : 1024u,
-                                                  p.b_mn ? ptx::kLayoutSw128Base32 : ptx::kLayoutSw128);
-          ptx::mma_tf32_ss(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < GEMM_BK / 8; ++k) {
+            const uint64_t ad = ptx::make_smem_desc(a_base + k * a_kstep, a_lbo, a_sbo, a_lay);
+            const uint64_t bd = ptx::make_smem_desc(b_base + k * b_kstep, b_lbo, b_sbo, b_lay);
+            ptx::mma_tf32_ss(d_tmem, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+            if (FOUR) {
+              const uint64_t ad2 = ptx::make_smem_desc(a_base + Cfg::A_BYTES + k * a_kstep, a_lbo, a_sbo, a_lay);
+              const uint64_t bd2 = ptx::make_smem_desc(b_base + Cfg::B_BYTES + k * b_kstep, b_lbo, b_sbo, b_lay);
+              ptx::mma_tf32_ss(d_tmem, ad2, bd, idesc, 1u);          // A_lo * B_hi
+              ptx::mma_tf32_ss(d_tmem, ad, bd2, idesc, 1u);          // A_hi * B_lo
+            }
+          }
+          ptx::mma_commit(empty_bar + s);          // frees the smem slot once these MMAs have read it
         }
-        ptx::mma_commit(empty_bar + s);          // frees the smem slot once these MMAs have read it
+        ptx::mma_commit(tfull_bar + buf);          // accumulator complete
       }
-      ptx::mma_commit(tmem_full_bar);            // accumulator complete
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------ epilogue (128 threads, thread <-> accumulator row)
-    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
-    const int row = q * 32 + lane, grow = m0 + row;
-    const int rows_valid = min(GEMM_BM, p.M - m0);
-    const int et = threadIdx.x - 64;              // 0..127
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    if (p.epi == EPI_NTX_FWD) {
-      // per-row (max, sum exp) of this column tile, own column masked; thread <-> row straight from TMEM
-      const long long gr = grow + p.row_offset;
-      long long pos = gr + p.num_cand / 2;
-      if (pos >= p.num_cand) pos -= p.num_cand;
-      float mx = -INFINITY;
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        float v[16];
-        ptx::tmem_ld_x16(taddr + c0, v);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const long long gc = n0 + c0 + j + p.col_offset;
-          if (n0 + c0 + j < p.N && gc != gr) mx = fmaxf(mx, v[j] * p.inv_tau);
-          if (gc == pos && n0 + c0 + j < p.N && grow < p.M) p.row_pos[grow] = v[j] * p.inv_tau;
-        }
-      }
-      float sum = 0.f;
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        float v[16];
-        ptx::tmem_ld_x16(taddr + c0, v);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const long long gc = n0 + c0 + j + p.col_offset;
-          if (n0 + c0 + j < p.N && gc != gr) sum += __expf(v[j] * p.inv_tau - mx);
-        }
-      }
-      if (grow < p.M) {
-        p.part_max[(size_t)blockIdx.x * p.M + grow] = mx;
-        p.part_sum[(size_t)blockIdx.x * p.M + grow] = sum;
-      }
-    } else if (p.atomic_out) {
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        float v[16];
-        ptx::tmem_ld_x16(taddr + c0, v);
-        if (grow < p.M) {
+    // ------------------------------------------------------------ epilogue: warp q owns accumulator rows 32q..32q+31
+    const int q = warp & 3;
+    float* stg = staging + q * 32 * GEMM_CHUNK_LD;
+    uint32_t tl = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
+      const int n_tile = t % n_tiles, m_tile = (t / n_tiles) % m_tiles;
+      const int n0 = n_tile * BN, m0 = m_tile * GEMM_BM;
+      const int row = q * 32 + lane, grow = m0 + row;
+      const int rows_w = max(0, min(32, p.M - m0 - q * 32));          // valid rows of this warp's group
+      const uint32_t buf = tl & 1;
+      ptx::mbar_wait(tfull_bar + buf, (tl >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
+      if (p.epi == EPI_NTX_FWD) {
+        // per-row (max, sum exp) of this column tile, own column masked; thread <-> row straight from TMEM
+        const long long gr = grow + p.row_offset;
+        long long pos = gr + p.num_cand / 2;
+        if (pos >= p.num_cand) pos -= p.num_cand;
+        float mx = -INFINITY;
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          float v[16];
+          ptx::tmem_ld_x16(taddr + c0, v);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int col = n0 + c0 + j;
-            if (col < p.N)
-              atomicAdd(p.transpose_out ? p.out + (size_t)col * p.ldo + grow : p.out + (size_t)grow * p.ldo + col, v[j]);
+            const long long gc = n0 + c0 + j + p.col_offset;
+            if (n0 + c0 + j < p.N && gc != gr) mx = fmaxf(mx, v[j] * p.inv_tau);
+            if (gc == pos && n0 + c0 + j < p.N && grow < p.M) p.row_pos[grow] = v[j] * p.inv_tau;
           }
         }
-      }
-    } else {
-      float* stage = reinterpret_cast<float*>(smem);   // pipeline buffers are idle once tmem_full fired
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        float v[16];
-        ptx::tmem_ld_x16(taddr + c0, v);
+        float sum = 0.f;
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          float v[16];
+          ptx::tmem_ld_x16(taddr + c0, v);
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) st_f4(stage + row * Cfg::LDS + c0 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-      }
-      ptx::named_bar_sync(1, 128);
-      for (int r = warp - 2; r < rows_valid; r += 4) {
-        const int gr = m0 + r;
-        for (int c4 = lane; c4 < BN / 4; c4 += 32) {
-          const int col = n0 + 4 * c4;
-          if (col >= p.N) continue;
-          float4 v = *reinterpret_cast<const float4*>(stage + r * Cfg::LDS + 4 * c4);
-          v = epilogue_apply(v, p, gr, col);
-          if (p.colstat) st_f4(stage + r * Cfg::LDS + 4 * c4, v);
-          if (p.out) st_f4(p.out + (size_t)gr * p.ldo + col, p.round_out ? f4_round(v) : v);
-          if (p.out2) st_f4(p.out2 + (size_t)gr * p.ldo2 + col, f4_round(v));
-          if (p.out_lo) st_f4(p.out_lo + (size_t)gr * p.ldo_lo + col, f4_residual(v));
+          for (int j = 0; j < 16; ++j) {
+            const long long gc = n0 + c0 + j + p.col_offset;
+            if (n0 + c0 + j < p.N && gc != gr) sum += __expf(v[j] * p.inv_tau - mx);
+          }
+        }
+        if (grow < p.M) {
+          p.part_max[(size_t)n_tile * p.M + grow] = mx;
+          p.part_sum[(size_t)n_tile * p.M + grow] = sum;
+        }
+      } else if (p.atomic_out) {
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          float v[16];
+          ptx::tmem_ld_x16(taddr + c0, v);
+          if (grow < p.M) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int col = n0 + c0 + j;
+              if (col < p.N)
+                atomicAdd(p.transpose_out ? p.out + (size_t)col * p.ldo + grow : p.out + (size_t)grow * p.ldo + col, v[j]);
+            }
+          }
+        }
+      } else {
+        const int group = m_tile * 4 + q;
+        for (int c0 = 0; c0 < BN && n0 + c0 < p.N; c0 += GEMM_CHUNK) {
+          float v[16];
+          ptx::tmem_ld_x16(taddr + c0, v);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) st_f4(stg + lane * GEMM_CHUNK_LD + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+          __syncwarp();
+          // read back row-wise: 4 lanes cover one row's 16 columns (64 B), 8 rows per pass -> coalesced row segments
+          const int col = n0 + c0 + 4 * (lane & 3);
+#pragma unroll
+          for (int pass = 0; pass < 4; ++pass) {
+            const int r = pass * 8 + (lane >> 2);
+            if (r < rows_w && col < p.N) {
+              const int gr = m0 + q * 32 + r;
+              float4 x = *reinterpret_cast<const float4*>(stg + r * GEMM_CHUNK_LD + 4 * (lane & 3));
+              x = epilogue_apply(x, p, gr, col);
+              if (p.colstat) st_f4(stg + r * GEMM_CHUNK_LD + 4 * (lane & 3), x);
+              if (p.out) st_f4(p.out + (size_t)gr * p.ldo + col, p.round_out ? f4_tf32(x) : x);
+              if (p.out2) st_f4(p.out2 + (size_t)gr * p.ldo2 + col, f4_tf32(x));
+              if (p.out_lo) st_f4(p.out_lo + (size_t)gr * p.ldo_lo + col, f4_tf32_residual(x));
+            }
+          }
+          if (p.colstat) {
+            __syncwarp();
+            colstat_group(stg, GEMM_CHUNK_LD, GEMM_CHUNK, rows_w, n0 + c0, group, p, lane, 32);
+          }
+          __syncwarp();
         }
       }
-      if (p.colstat) {
-        ptx::named_bar_sync(1, 128);
-        tile_colstat(stage, Cfg::LDS, BN, rows_valid, n0, m_tile, p, et, 128);
-      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar + buf);
     }
-    ptx::tc_fence_before();
   }
+  ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, GEMM_TMEM_COLS); }
 }
@@ -325,16 +369,17 @@ __global__ void __launch_bounds__(128) gemm_simt_kernel(const float* __restrict_
           atomicAdd(p.transpose_out ? p.out + (size_t)(col + t) * p.ldo + grow : p.out + (size_t)grow * p.ldo + col + t, vv[t]);
       } else {
         v = epilogue_apply(v, p, grow, col);
-        if (p.out) st_f4(p.out + (size_t)grow * p.ldo + col, p.round_out ? f4_round(v) : v);
-        if (p.out2) st_f4(p.out2 + (size_t)grow * p.ldo2 + col, f4_round(v));
-        if (p.out_lo) st_f4(p.out_lo + (size_t)grow * p.ldo_lo + col, f4_residual(v));
+        if (p.out) st_f4(p.out + (size_t)grow * p.ldo + col, p.round_out ? f4_tf32(v) : v);
+        if (p.out2) st_f4(p.out2 + (size_t)grow * p.ldo2 + col, f4_tf32(v));
+        if (p.out_lo) st_f4(p.out_lo + (size_t)grow * p.ldo_lo + col, f4_tf32_residual(v));
       }
     }
     stage[row * 33 + j] = v.x; stage[row * 33 + j + 1] = v.y; stage[row * 33 + j + 2] = v.z; stage[row * 33 + j + 3] = v.w;
   }
   if (p.colstat && !p.atomic_out) {
     __syncthreads();
-    tile_colstat(stage, 33, 32, rows_valid, n0, m_tile, p, threadIdx.x, 128);
+    for (int g = 0; g < 4; ++g)
+      colstat_group(stage + g * 32 * 33, 33, 32, max(0, min(32, rows_valid - 32 * g)), n0, m_tile * 4 + g, p, threadIdx.x, 128);
   }
 }
 
@@ -381,9 +426,10 @@ static int make_tmap(CUtensorMap* m, const float* base, int64_t inner, int64_t o
   return 0;
 }
 
-template <int BN>
-static int launch_tc(const GemmJob& j, const GemmParams& p, int n_tiles, int m_tiles, int splits, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+template <int BN, bool FOUR>
+static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, int splits, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, FOUR>;
+  p.n_tiles = n_tiles; p.m_tiles = m_tiles; p.splits = splits;
   CUtensorMap tmA, tmB, tmA2, tmB2;
   int rc;
   // K-major operand [rows][K]: inner = K, outer = rows, box = rows-per-tile x 32.  MN-major [K][rows]: inner = rows, outer = K, box 32 x 32.
@@ -400,11 +446,13 @@ static int launch_tc(const GemmJob& j, const GemmParams& p, int n_tiles, int m_t
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, FOUR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "gemm: cudaFuncSetAttribute");
     attr_set = true;
   }
-  gemm_tf32_kernel<BN><<<dim3(n_tiles, m_tiles, splits), GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
+  const long long total = (long long)n_tiles * m_tiles * splits;
+  const int grid = (int)(total < sm_count() ? total : sm_count());
+  gemm_tf32_kernel<BN, FOUR><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
   MOLCLR_CHECK_LAUNCH("gemm_tf32");
   return 0;
 }
@@ -457,15 +505,19 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
     MOLCLR_CHECK_LAUNCH("gemm_simt");
     return 0;
   }
-  if (gemm_bn(p.N) == 256) return launch_tc<256>(job, p, (p.N + 255) / 256, m_tiles, splits, stream);
-  return launch_tc<160>(job, p, (p.N + 159) / 160, m_tiles, splits, stream);
+  if (gemm_bn(p.N) == 256)
+    return p.segments > 1 ? launch_tc<256, true>(job, p, (p.N + 255) / 256, m_tiles, splits, stream)
+                          : launch_tc<256, false>(job, p, (p.N + 255) / 256, m_tiles, splits, stream);
+  return p.segments > 1 ? launch_tc<160, true>(job, p, (p.N + 159) / 160, m_tiles, splits, stream)
+                        : launch_tc<160, false>(job, p, (p.N + 159) / 160, m_tiles, splits, stream);
 }
 
 }  // namespace molclr
 
 using namespace molclr;
 
-extern "C" int molclr_gemm_colstat_tiles(int64_t M) { return (int)((M + GEMM_BM - 1) / GEMM_BM); }
+extern "C" int molclr_gemm_colstat_tiles(int64_t M) { return 4 * (int)((M + GEMM_BM - 1) / GEMM_BM); }
+extern "C" int molclr_gemm_colstat_tile_rows(void) { return GEMM_STAT_ROWS; }
 
 extern "C" int molclr_gemm_tf32(const molclr_gemm_args* args, cudaStream_t stream) {
   const molclr_gemm_args& a = *args;

@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(512) bn_fwd_finalize_kernel(
   if (c < D) {
     for (int t = threadIdx.y; t < T; t += 16) {
       const int rows = min(tile_rows, N - t * tile_rows);
+      if (rows <= 0) continue;                       // padding groups of the last 128-row GEMM tile
       const double nb = rows, mb = tile_stats[((size_t)t * 2) * D + c], qb = tile_stats[((size_t)t * 2 + 1) * D + c];
       const double tot = n + nb, delta = mb - mean;
       mean += delta * (nb / tot);

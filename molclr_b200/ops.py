@@ -50,6 +50,10 @@ def colstat_tiles(M):
     return _lib.load().molclr_gemm_colstat_tiles(M)
 
 
+def colstat_tile_rows():
+    return _lib.load().molclr_gemm_colstat_tile_rows()
+
+
 def _sm_count():
     if not hasattr(_sm_count, "v"):
         _sm_count.v = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
@@ -160,7 +164,7 @@ def edge_table_grad(plan, ga):
 def bn_fwd_finalize(tile_stats, T, N, gamma, beta, running_mean, running_var, nbt, momentum, eps):
     D = gamma.shape[0]
     coef = _empty(4, D, device=gamma.device)
-    check(_lib.load().molclr_bn_fwd_finalize(ptr(tile_stats), T, 128, N, D, ptr(gamma), ptr(beta), ptr(running_mean),
+    check(_lib.load().molclr_bn_fwd_finalize(ptr(tile_stats), T, colstat_tile_rows(), N, D, ptr(gamma), ptr(beta), ptr(running_mean),
                                              ptr(running_var), ptr(nbt, torch.int64), momentum, eps, ptr(coef), stream()),
           "bn_fwd_finalize")
     return coef

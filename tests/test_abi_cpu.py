@@ -32,7 +32,7 @@ def test_library_loads_and_reports_version(lib_path):
     lib = _lib.load()
     assert lib.molclr_abi_version() == 1
     assert lib.molclr_plan_workspace_bytes(10, 20, 3) >= 4 * 23
-    assert lib.molclr_gemm_colstat_tiles(129) == 2
+    assert lib.molclr_gemm_colstat_tiles(129) == 8 and lib.molclr_gemm_colstat_tile_rows() == 32
 
 
 def test_gemm_args_struct_matches_header_layout():

@@ -171,8 +171,9 @@ def test_gemm_epilogues():
     out, st = torch.empty(M, N, device=DEV), torch.empty(T, 2, N, device=DEV)
     ops.gemm(A, B, M, N, K, out=out, bias=bias, colstat=st, colstat_mode=2)
     want = ref + bias.double().cpu()
-    for t in range(T):
-        blk = want[t * 128:(t + 1) * 128]
+    R = ops.colstat_tile_rows()
+    for t in range(-(-M // R)):
+        blk = want[t * R:(t + 1) * R]
         assert rel_err(st[t, 0], blk.mean(0)) < 1e-4
         assert rel_err(st[t, 1], ((blk - blk.mean(0)) ** 2).sum(0)) < 1e-4
 
@@ -212,9 +213,10 @@ def test_bn_finalize_and_pool():
     N = plan.N
     z = (torch.randn(N, D) * 2 + 0.7)
     T = ops.colstat_tiles(N)
-    stats = torch.empty(T, 2, D)
-    for t in range(T):
-        blk = z[t * 128:(t + 1) * 128].double()
+    stats = torch.zeros(T, 2, D)
+    R = ops.colstat_tile_rows()
+    for t in range(-(-N // R)):
+        blk = z[t * R:(t + 1) * R].double()
         stats[t, 0], stats[t, 1] = blk.mean(0), ((blk - blk.mean(0)) ** 2).sum(0)
     bn = torch.nn.BatchNorm1d(D)
     bn.weight.data.normal_(); bn.bias.data.normal_()
