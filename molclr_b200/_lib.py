@@ -107,3 +107,12 @@ def ptr(t, dtype=torch.float32):
     if not t.is_contiguous():
         raise RuntimeError("molclr_b200: expected a contiguous tensor")
     return t.data_ptr()
+
+
+def ptr2d(t):
+    """Device pointer of a 2-D fp32 CUDA matrix whose rows are contiguous (row stride = leading dimension)."""
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype != torch.float32 or t.dim() != 2 or (t.size(1) > 1 and t.stride(1) != 1):
+        raise RuntimeError("molclr_b200: expected a 2-D fp32 CUDA matrix with contiguous rows")
+    return t.data_ptr()

@@ -27,8 +27,6 @@ constexpr int GEMM_BK = 32;          // 32 tf32 = one 128-byte swizzle row
 constexpr int GEMM_THREADS = 192;    // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int GEMM_TMEM_COLS = 512;  // two accumulator buffers of up to 256 columns
 constexpr int GEMM_STAT_ROWS = 32;   // column statistics are emitted per 32-row group (one epilogue warp)
-constexpr int GEMM_CHUNK = 16;       // epilogue column chunk staged per warp
-constexpr int GEMM_CHUNK_LD = 20;    // staging pitch (floats): conflict-free float4 rows
 constexpr int GEMM_SMEM_LIMIT = 232448;
 
 // FOUR = compensated product with all four operand tiles (A_hi, A_lo, B_hi, B_lo) in one stage and three
@@ -38,7 +36,11 @@ struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 4;
   static constexpr int B_BYTES = BN * GEMM_BK * 4;
   static constexpr int STAGE_BYTES = (FOUR ? 2 : 1) * (A_BYTES + B_BYTES);
-  static constexpr int STAGING_BYTES = 4 * 32 * GEMM_CHUNK_LD * 4;     // 4 epilogue warps x 32 rows x chunk
+  // epilogue column chunk staged per warp, and its pitch in floats (conflict-free float4 rows); the 4-tile stages
+  // leave room for a 16-column chunk only
+  static constexpr int CHUNK = FOUR ? 16 : 32;
+  static constexpr int CHUNK_LD = CHUNK + 4;
+  static constexpr int STAGING_BYTES = 4 * 32 * CHUNK_LD * 4;     // 4 epilogue warps x 32 rows x chunk
   static constexpr int BAR_BYTES = 256;
   static constexpr int STAGES_RAW = (GEMM_SMEM_LIMIT - STAGING_BYTES - BAR_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -107,7 +109,10 @@ __device__ __forceinline__ void colstat_group(const float* stage, int lds, int n
 // (n_tile fastest, m_tile, k_split) grid.  The TMA producer and the MMA issuer run ahead across tiles through a
 // STAGES-deep smem ring; accumulators are double-buffered in TMEM so the 4 epilogue warps drain tile i while the
 // tensor core works on tile i+1.
-template <int BN, bool FOUR>
+// KIND selects the epilogue at compile time so that each variant is a short, branch-free loop:
+enum : int { K_PLAIN = 0, K_LATE = 1, K_NTX_W = 2, K_NTX_FWD = 3, K_ATOMIC = 4 };
+
+template <int BN, bool FOUR, int KIND>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
@@ -217,7 +222,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ------------------------------------------------------------ epilogue: warp q owns accumulator rows 32q..32q+31
     const int q = warp & 3;
-    float* stg = staging + q * 32 * GEMM_CHUNK_LD;
+    float* stg = staging + q * 32 * Cfg::CHUNK_LD;
     uint32_t tl = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
       const int n_tile = t % n_tiles, m_tile = (t / n_tiles) % m_tiles;
@@ -228,7 +233,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::mbar_wait(tfull_bar + buf, (tl >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
-      if (p.epi == EPI_NTX_FWD) {
+      if (KIND == K_NTX_FWD) {
         // per-row (max, sum exp) of this column tile, own column masked; thread <-> row straight from TMEM
         const long long gr = grow + p.row_offset;
         long long pos = gr + p.num_cand / 2;
@@ -258,7 +263,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           p.part_max[(size_t)n_tile * p.M + grow] = mx;
           p.part_sum[(size_t)n_tile * p.M + grow] = sum;
         }
-      } else if (p.atomic_out) {
+      } else if (KIND == K_ATOMIC) {
         for (int c0 = 0; c0 < BN; c0 += 16) {
           float v[16];
           ptx::tmem_ld_x16(taddr + c0, v);
@@ -272,31 +277,51 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       } else {
+        // TMEM -> registers (thread = row) -> per-warp staging chunk -> coalesced row segments.  All elementwise
+        // terms are applied in the copy-out pass, where a lane owns one fixed float4 column group of the chunk.
         const int group = m_tile * 4 + q;
-        for (int c0 = 0; c0 < BN && n0 + c0 < p.N; c0 += GEMM_CHUNK) {
-          float v[16];
-          ptx::tmem_ld_x16(taddr + c0, v);
+        constexpr int CH = Cfg::CHUNK, LD = Cfg::CHUNK_LD;
+        constexpr int LPR = CH / 4;            // lanes covering one row of the chunk (float4 each)
+        constexpr int RPP = 32 / LPR;          // rows per copy-out pass
+        const float alpha = p.alpha, floor_v = p.relu ? 0.f : -INFINITY;
+        const bool has_bias = p.bias != nullptr, do_round = p.round_out != 0, has_out = p.out != nullptr,
+                   has_out2 = p.out2 != nullptr, has_lo = p.out_lo != nullptr, has_stat = p.colstat != nullptr;
+        const int cq = 4 * (lane % LPR), r_in = lane / LPR;
+        for (int c0 = 0; c0 < BN && n0 + c0 < p.N; c0 += CH) {
+          if (p.debug & 1) break;                     // timing experiment: no epilogue work at all
+          float v[CH];
+          ptx::tmem_ld_x16_nowait(taddr + c0, v);
+          if (CH == 32) ptx::tmem_ld_x16_nowait(taddr + c0 + 16, v + (CH == 32 ? 16 : 0));
+          ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) st_f4(stg + lane * GEMM_CHUNK_LD + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+          for (int j = 0; j < CH; j += 4) st_f4(stg + lane * LD + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
           __syncwarp();
-          // read back row-wise: 4 lanes cover one row's 16 columns (64 B), 8 rows per pass -> coalesced row segments
-          const int col = n0 + c0 + 4 * (lane & 3);
+          const int col = n0 + c0 + cq;
+          const bool col_ok = col < p.N;
+          float4 b4 = f4_zero();
+          if (KIND == K_PLAIN && has_bias && col_ok) b4 = ldg_f4(p.bias + col);
 #pragma unroll
-          for (int pass = 0; pass < 4; ++pass) {
-            const int r = pass * 8 + (lane >> 2);
-            if (r < rows_w && col < p.N) {
+          for (int pass = 0; pass < 32 / RPP; ++pass) {
+            const int r = pass * RPP + r_in;
+            if (r < rows_w && col_ok) {
               const int gr = m0 + q * 32 + r;
-              float4 x = *reinterpret_cast<const float4*>(stg + r * GEMM_CHUNK_LD + 4 * (lane & 3));
-              x = epilogue_apply(x, p, gr, col);
-              if (p.colstat) st_f4(stg + r * GEMM_CHUNK_LD + 4 * (lane & 3), x);
-              if (p.out) st_f4(p.out + (size_t)gr * p.ldo + col, p.round_out ? f4_tf32(x) : x);
-              if (p.out2) st_f4(p.out2 + (size_t)gr * p.ldo2 + col, f4_tf32(x));
-              if (p.out_lo) st_f4(p.out_lo + (size_t)gr * p.ldo_lo + col, f4_tf32_residual(x));
+              float4 x = *reinterpret_cast<const float4*>(stg + r * LD + cq);
+              if (KIND == K_PLAIN) {
+                x.x = fmaxf(fmaf(x.x, alpha, b4.x), floor_v); x.y = fmaxf(fmaf(x.y, alpha, b4.y), floor_v);
+                x.z = fmaxf(fmaf(x.z, alpha, b4.z), floor_v); x.w = fmaxf(fmaf(x.w, alpha, b4.w), floor_v);
+              } else {
+                x = epilogue_apply(x, p, gr, col);
+              }
+              if (has_stat) st_f4(stg + r * LD + cq, x);
+              const float4 xr = f4_tf32(x);
+              if (has_out) st_f4(p.out + (size_t)gr * p.ldo + col, do_round ? xr : x);
+              if (has_out2) st_f4(p.out2 + (size_t)gr * p.ldo2 + col, xr);
+              if (has_lo) st_f4(p.out_lo + (size_t)gr * p.ldo_lo + col, f4_tf32_residual(x));
             }
           }
-          if (p.colstat) {
+          if (has_stat) {
             __syncwarp();
-            colstat_group(stg, GEMM_CHUNK_LD, GEMM_CHUNK, rows_w, n0 + c0, group, p, lane, 32);
+            colstat_group(stg, LD, CH, rows_w, n0 + c0, group, p, lane, 32);
           }
           __syncwarp();
         }
@@ -426,7 +451,7 @@ static int make_tmap(CUtensorMap* m, const float* base, int64_t inner, int64_t o
   return 0;
 }
 
-template <int BN, bool FOUR>
+template <int BN, bool FOUR, int KIND>
 static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, int splits, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, FOUR>;
   p.n_tiles = n_tiles; p.m_tiles = m_tiles; p.splits = splits;
@@ -446,15 +471,21 @@ static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, i
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, FOUR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, FOUR, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "gemm: cudaFuncSetAttribute");
     attr_set = true;
   }
   const long long total = (long long)n_tiles * m_tiles * splits;
   const int grid = (int)(total < sm_count() ? total : sm_count());
-  gemm_tf32_kernel<BN, FOUR><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
+  gemm_tf32_kernel<BN, FOUR, KIND><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
   MOLCLR_CHECK_LAUNCH("gemm_tf32");
   return 0;
+}
+
+static int gemm_debug_flags() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MOLCLR_GEMM_DEBUG"); v = e ? atoi(e) : 0; }
+  return v;
 }
 
 static int gemm_impl_simt() {
@@ -493,6 +524,7 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   p.kb_per_split = (p.num_kb + splits - 1) / splits;
   splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;          // no empty split
   p.atomic_out = atomic ? 1 : 0;
+  p.debug = gemm_debug_flags();
   const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
   if (atomic) {
     const size_t w = (size_t)(p.transpose_out ? p.M : p.N) * sizeof(float), h = (size_t)(p.transpose_out ? p.N : p.M);
@@ -505,11 +537,19 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
     MOLCLR_CHECK_LAUNCH("gemm_simt");
     return 0;
   }
-  if (gemm_bn(p.N) == 256)
-    return p.segments > 1 ? launch_tc<256, true>(job, p, (p.N + 255) / 256, m_tiles, splits, stream)
-                          : launch_tc<256, false>(job, p, (p.N + 255) / 256, m_tiles, splits, stream);
-  return p.segments > 1 ? launch_tc<160, true>(job, p, (p.N + 159) / 160, m_tiles, splits, stream)
-                        : launch_tc<160, false>(job, p, (p.N + 159) / 160, m_tiles, splits, stream);
+  const int kind = p.epi == EPI_NTX_FWD ? K_NTX_FWD : atomic ? K_ATOMIC : p.epi == EPI_NTX_W ? K_NTX_W
+                   : (p.mask || p.addend) ? K_LATE : K_PLAIN;
+  MOLCLR_REQUIRE(p.segments == 1 || kind == K_PLAIN, "gemm: the compensated product supports the plain epilogue only");
+  const int bn = gemm_bn(p.N), nt = (p.N + bn - 1) / bn;
+#define MOLCLR_GEMM_CASE(BN_, FOUR_, KIND_) \
+  if (bn == BN_ && (p.segments > 1) == FOUR_ && kind == KIND_) return launch_tc<BN_, FOUR_, KIND_>(job, p, nt, m_tiles, splits, stream);
+  MOLCLR_GEMM_CASE(160, false, K_PLAIN) MOLCLR_GEMM_CASE(160, true, K_PLAIN) MOLCLR_GEMM_CASE(160, false, K_LATE)
+  MOLCLR_GEMM_CASE(160, false, K_NTX_W) MOLCLR_GEMM_CASE(160, false, K_NTX_FWD) MOLCLR_GEMM_CASE(160, false, K_ATOMIC)
+  MOLCLR_GEMM_CASE(256, false, K_PLAIN) MOLCLR_GEMM_CASE(256, true, K_PLAIN) MOLCLR_GEMM_CASE(256, false, K_LATE)
+  MOLCLR_GEMM_CASE(256, false, K_NTX_W) MOLCLR_GEMM_CASE(256, false, K_NTX_FWD) MOLCLR_GEMM_CASE(256, false, K_ATOMIC)
+#undef MOLCLR_GEMM_CASE
+  set_error("gemm: no kernel instance for bn=%d segments=%d kind=%d", bn, p.segments, kind);
+  return -2;
 }
 
 }  // namespace molclr

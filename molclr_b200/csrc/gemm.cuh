@@ -22,6 +22,7 @@ struct GemmParams {
   int relu, round_out;
   float* colstat; int colstat_mode;
   int atomic_out;
+  int debug;                   // MOLCLR_GEMM_DEBUG bit 0: skip the generic epilogue (timing experiments only)
   float alpha;                 // out = alpha * acc (+ bias + addend ...)
   // ---- NT-Xent epilogues (nt_xent.py:47-65); logits l = acc * inv_tau
   int epi;

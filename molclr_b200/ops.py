@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import GemmArgs, check, ptr, stream
+from ._lib import GemmArgs, check, ptr, ptr2d, stream
 
 F32 = torch.float32
 
@@ -29,9 +29,9 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=Non
     ``molclr_gemm_tf32`` (see include/molclr_b200.h)."""
     lib = _lib.load()
     a = GemmArgs()
-    a.A, a.lda, a.a_mn = ptr(A), (A.stride(0) if lda is None else lda), int(a_mn)
-    a.B, a.ldb, a.b_mn = ptr(B), (B.stride(0) if ldb is None else ldb), int(b_mn)
-    a.A_lo, a.B_lo = ptr(A_lo), ptr(B_lo)
+    a.A, a.lda, a.a_mn = ptr2d(A), (A.stride(0) if lda is None else lda), int(a_mn)
+    a.B, a.ldb, a.b_mn = ptr2d(B), (B.stride(0) if ldb is None else ldb), int(b_mn)
+    a.A_lo, a.B_lo = ptr2d(A_lo), ptr2d(B_lo)
     a.M, a.N, a.K = M, N, K
     a.out, a.ldo, a.transpose_out = ptr(out), (out.stride(0) if out is not None else 0), int(transpose_out)
     a.out2, a.ldo2 = ptr(out2), (out2.stride(0) if out2 is not None else 0)
@@ -76,7 +76,8 @@ def gemm_dw(dY, X):
     swap = area_b < area_a
     tiles = tiles_b if swap else tiles_a
     num_kb = -(-R // 32)
-    split = max(1, min(-(-2 * _sm_count() // tiles), max(1, num_kb // 8)))
+    # one wave of work items: tiles * split <= #SM (each CTA then streams a long K range)
+    split = max(1, min(_sm_count() // tiles, max(1, num_kb // 8)))
     if swap:    # compute dW^T = X^T dY with the wider operand on M, store transposed
         gemm(X, dY, I, O, R, a_mn=True, b_mn=True, out=dW, transpose_out=True, split_k=split)
     else:

@@ -1,0 +1,64 @@
+"""Times the tensor-core GEMM on the hot-path shapes (CUDA events), prints TFLOP/s and operand bytes/s."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from molclr_b200 import ops
+
+dev = "cuda:0"
+M = int(os.environ.get("M", 102400))
+
+
+def timeit(fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters * 1e3   # us
+
+
+def case(name, M, N, K, comp=False, b_mn=False, relu=False, pad_k=0, dw=False):
+    g = torch.Generator().manual_seed(0)
+    if dw:
+        dY, X = torch.randn(M, N, generator=g).to(dev), torch.randn(M, K, generator=g).to(dev)
+        us = timeit(lambda: ops.gemm_dw(dY, X))
+        flops = 2.0 * M * N * K
+        print(f"{name:34s} {us:9.1f} us  {flops / us / 1e6:8.1f} TFLOP/s")
+        return
+    A = torch.randn(M, K + pad_k, generator=g).to(dev)[:, :K]
+    B = (torch.randn(K, N, generator=g) if b_mn else torch.randn(N, K + pad_k, generator=g)).to(dev)
+    if not b_mn:
+        B = B[:, :K]
+    out = torch.empty(M, N, device=dev)
+    lo = torch.empty(M, N, device=dev) if comp else None
+    A_lo = torch.randn(M, K + pad_k, generator=g).to(dev)[:, :K] if comp else None
+    B_lo = (torch.randn_like(B) if comp else None)
+    bias = torch.randn(N, device=dev)
+    fn = lambda: ops.gemm(A, B, M, N, K, b_mn=b_mn, A_lo=A_lo, B_lo=B_lo, out=out, out_lo=lo, bias=bias, relu=relu, round_out=True,
+                          lda=K + pad_k, ldb=(N if b_mn else K + pad_k))
+    us = timeit(fn)
+    flops = 2.0 * M * N * K * (3 if comp else 1)
+    print(f"{name:34s} {us:9.1f} us  {flops / us / 1e6:8.1f} TFLOP/s (tensor work)  out {M * N * 4 * (2 if comp else 1) / us / 1e3:7.1f} GB/s")
+
+
+print("MOLCLR_GEMM_DEBUG =", os.environ.get("MOLCLR_GEMM_DEBUG"))
+if os.environ.get("QUICK"):
+    case("fwd1 x1   [M,300]x[600,300]", M, 600, 300)
+    case("tinyK x1  [M,32]x[600,32]", M, 600, 32)
+    case("sq   x1   [M,512]x[512,512]", M, 512, 512)
+    sys.exit(0)
+case("fwd1 x1   [M,300]x[600,300]", M, 600, 300)
+case("fwd1 x3   [M,300]x[600,300]", M, 600, 300, comp=True)
+case("fwd2 x1   [M,600]x[300,600]", M, 300, 600)
+case("fwd2 x3   [M,600]x[300,600]", M, 300, 600, comp=True)
+case("fwd1 x1 K=320 aligned pitch", M, 600, 320)
+case("fwd1 x1 pitch 304->320", M, 600, 300, pad_k=20)
+case("dX   x1   [M,300]x[300,600]mn", M, 600, 300, b_mn=True)
+case("dX   x1   [M,600]x[600,300]mn", M, 300, 600, b_mn=True)
+case("sq   x1   [M,512]x[512,512]", M, 512, 512)
+case("dW   [M,300]^T[M,600]", M, 300, 600, dw=True)
+case("dW   [M,600]^T[M,300]", M, 600, 300, dw=True)
