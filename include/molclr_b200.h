@@ -76,8 +76,8 @@ int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, int64_t N, in
  * (the previous layer's BatchNorm + ReLU, ginet_molclr.py:107-111, applied on the fly). */
 int molclr_gine_aggregate_fwd(const float* src, const float* bn_coef, int relu, const int32_t* rowptr, const int32_t* col,
                               const uint8_t* eattr, const float* B1, const float* B2, int64_t N, int D, float* out,
-                              int round_tf32_out, float* out_lo /* optional: tf32 residual of the exact sum */,
-                              cudaStream_t stream);
+                              int64_t ld_out /* row stride of out / out_lo in floats */, int round_tf32_out,
+                              float* out_lo /* optional: tf32 residual of the exact sum */, cudaStream_t stream);
 /* Backward (autograd of index_select/scatter_add_): gy[j] = sum_{out-edges e of j} ga[col_t[e]] + ga[j].
  * If z_prev != NULL additionally fuses the previous layer's ReLU backward and BatchNorm statistics:
  *   gy[j] *= [z_prev[j]*scale+shift > 0] (if relu);  partials[b][0] += gy, partials[b][1] += gy * (z_prev-mean)*invstd
@@ -111,14 +111,14 @@ int molclr_bn_bwd_finalize(const float* partials, int P, int64_t N, int D, const
 /* gz (tf32-rounded) = k1*gy + A + B*z.  gy from memory, or (gp != NULL) gy[n] = gp[node2graph[n]] * w_graph
  * (backward of global_mean/add_pool).  dbias (optional) = column sums of gz.  partials [max_blocks][D]. */
 int molclr_bn_bwd_apply(const float* gy, const float* gp, const int32_t* node2graph, const int32_t* gptr, int pool_mean,
-                        const float* z, const float* bcoef, int64_t N, int D, float* gz, float* dbias, float* partials,
-                        cudaStream_t stream);
+                        const float* z, const float* bcoef, int64_t N, int D, float* gz, int64_t ld_gz, float* dbias,
+                        float* partials, cudaStream_t stream);
 
 /* ---- global_mean_pool / global_add_pool: ginet_molclr.py:83-88,113 (pool_mode 0 = mean, 1 = add) ----
  * out[g] = w_g * sum_{n in graph g, node order} [relu](z[n]*scale + shift) */
 int molclr_pool_fwd(const float* z, const float* bn_coef, int relu, const int32_t* gptr, const int32_t* gperm,
-                    int pool_mode, int64_t G, int D, float* out, int round_tf32_out, float* out_lo /* optional */,
-                    cudaStream_t stream);
+                    int pool_mode, int64_t G, int D, float* out, int64_t ld_out, int round_tf32_out,
+                    float* out_lo /* optional */, cudaStream_t stream);
 int molclr_pool_bwd_stats(const float* gp, const int32_t* node2graph, const int32_t* gptr, int pool_mode, const float* z,
                           const float* bn_coef, int64_t N, int D, float* partials, int* num_partials, cudaStream_t stream);
 
@@ -159,6 +159,10 @@ int molclr_gemm_tf32(const molclr_gemm_args* args /* host */, cudaStream_t strea
 /* ---- small elementwise ops ---------------------------------------------------------------------- */
 /* hi = tf32(src); lo (optional) = tf32(src - hi) */
 int molclr_round_tf32(const float* src, float* hi, float* lo, int64_t n, cudaStream_t stream);
+/* same for a [rows][cols] matrix with row strides ld_src / ld_dst (hi and lo share ld_dst): lets tensor-core
+ * operands be stored with 128-byte aligned rows, which TMA streams markedly faster */
+int molclr_round_tf32_2d(const float* src, int64_t ld_src, float* hi, float* lo, int64_t ld_dst, int64_t rows, int64_t cols,
+                         cudaStream_t stream);
 /* F.normalize(z, dim=1), molclr.py:63-64 (eps 1e-12) and its backward */
 int molclr_l2_normalize_fwd(const float* z, int64_t R, int C, float eps, float* y, float* inv_norm, cudaStream_t stream);
 int molclr_l2_normalize_bwd(const float* gy, const float* y, const float* inv_norm, int64_t R, int C, float eps, float* gz,

@@ -24,7 +24,7 @@ namespace molclr {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 32;          // 32 tf32 = one 128-byte swizzle row
-constexpr int GEMM_THREADS = 192;    // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int GEMM_MAX_THREADS = 320; // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..: epilogue (4 or 8)
 constexpr int GEMM_TMEM_COLS = 512;  // two accumulator buffers of up to 256 columns
 constexpr int GEMM_STAT_ROWS = 32;   // column statistics are emitted per 32-row group (one epilogue warp)
 constexpr int GEMM_SMEM_LIMIT = 232448;
@@ -40,7 +40,10 @@ struct GemmCfg {
   // leave room for a 16-column chunk only
   static constexpr int CHUNK = FOUR ? 16 : 32;
   static constexpr int CHUNK_LD = CHUNK + 4;
-  static constexpr int STAGING_BYTES = 4 * 32 * CHUNK_LD * 4;     // 4 epilogue warps x 32 rows x chunk
+  // epilogue warps: two per TMEM lane quadrant (splitting the column chunks) where shared memory allows
+  static constexpr int EPI_WARPS = FOUR ? 4 : 8;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int STAGING_BYTES = EPI_WARPS * 32 * CHUNK_LD * 4;     // per epilogue warp: 32 rows x chunk
   static constexpr int BAR_BYTES = 256;
   static constexpr int STAGES_RAW = (GEMM_SMEM_LIMIT - STAGING_BYTES - BAR_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -113,7 +116,7 @@ __device__ __forceinline__ void colstat_group(const float* stage, int lds, int n
 enum : int { K_PLAIN = 0, K_LATE = 1, K_NTX_W = 2, K_NTX_FWD = 3, K_ATOMIC = 4 };
 
 template <int BN, bool FOUR, int KIND>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GemmCfg<BN, FOUR>::THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
   using Cfg = GemmCfg<BN, FOUR>;
@@ -132,7 +135,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (threadIdx.x == 0) {
     if ((ptx::smem_u32(smem) & 1023u) != 0) { printf("molclr gemm: dynamic smem base not 1024B aligned\n"); __trap(); }
     for (int s = 0; s < Cfg::STAGES; ++s) { ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(tfull_bar + b, 1); ptx::mbar_init(tempty_bar + b, 4); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(tfull_bar + b, 1); ptx::mbar_init(tempty_bar + b, Cfg::EPI_WARPS); }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
@@ -221,8 +224,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue: warp q owns accumulator rows 32q..32q+31
-    const int q = warp & 3;
-    float* stg = staging + q * 32 * Cfg::CHUNK_LD;
+    const int q = warp & 3;                          // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;                // 0/1: which share of the column chunks (8-warp configs)
+    constexpr int NSHARE = Cfg::EPI_WARPS / 4;
+    float* stg = staging + (warp - 2) * 32 * Cfg::CHUNK_LD;
     uint32_t tl = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
       const int n_tile = t % n_tiles, m_tile = (t / n_tiles) % m_tiles;
@@ -239,6 +244,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         long long pos = gr + p.num_cand / 2;
         if (pos >= p.num_cand) pos -= p.num_cand;
         float mx = -INFINITY;
+        if (half == 0)
         for (int c0 = 0; c0 < BN; c0 += 16) {
           float v[16];
           ptx::tmem_ld_x16(taddr + c0, v);
@@ -250,6 +256,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         float sum = 0.f;
+        if (half == 0)
         for (int c0 = 0; c0 < BN; c0 += 16) {
           float v[16];
           ptx::tmem_ld_x16(taddr + c0, v);
@@ -259,12 +266,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (n0 + c0 + j < p.N && gc != gr) sum += __expf(v[j] * p.inv_tau - mx);
           }
         }
-        if (grow < p.M) {
+        if (grow < p.M && half == 0) {
           p.part_max[(size_t)n_tile * p.M + grow] = mx;
           p.part_sum[(size_t)n_tile * p.M + grow] = sum;
         }
       } else if (KIND == K_ATOMIC) {
-        for (int c0 = 0; c0 < BN; c0 += 16) {
+        for (int c0 = 16 * half; c0 < BN; c0 += 16 * NSHARE) {
           float v[16];
           ptx::tmem_ld_x16(taddr + c0, v);
           if (grow < p.M) {
@@ -287,7 +294,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool has_bias = p.bias != nullptr, do_round = p.round_out != 0, has_out = p.out != nullptr,
                    has_out2 = p.out2 != nullptr, has_lo = p.out_lo != nullptr, has_stat = p.colstat != nullptr;
         const int cq = 4 * (lane % LPR), r_in = lane / LPR;
-        for (int c0 = 0; c0 < BN && n0 + c0 < p.N; c0 += CH) {
+        for (int c0 = CH * half; c0 < BN && n0 + c0 < p.N; c0 += CH * NSHARE) {
           if (p.debug & 1) break;                     // timing experiment: no epilogue work at all
           float v[CH];
           ptx::tmem_ld_x16_nowait(taddr + c0, v);
@@ -477,7 +484,7 @@ static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, i
   }
   const long long total = (long long)n_tiles * m_tiles * splits;
   const int grid = (int)(total < sm_count() ? total : sm_count());
-  gemm_tf32_kernel<BN, FOUR, KIND><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
+  gemm_tf32_kernel<BN, FOUR, KIND><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
   MOLCLR_CHECK_LAUNCH("gemm_tf32");
   return 0;
 }

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_fwd_kernel(
     const float* __restrict__ src, const float* __restrict__ coef, int relu,
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const uint8_t* __restrict__ eattr,
     const float* __restrict__ B1, const float* __restrict__ B2, int N, int D, float* __restrict__ out,
-    int round_out, float* __restrict__ out_lo) {
+    long long ld_out, int round_out, float* __restrict__ out_lo) {
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* ee = sm4;                       // [15][D4]
@@ -154,9 +154,9 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_fwd_kernel(
       const int q = lane + 32 * j;
       if (q < D4) {
         float4 r = f4_add(acc[j], f4_add(act(self[j], q), ee[kSelfLoopAttr * D4 + q]));   // self loop LAST
-        if (out_lo) st_f4(out_lo + (size_t)i * D + 4 * q, f4_tf32_residual(r));
+        if (out_lo) st_f4(out_lo + (size_t)i * ld_out + 4 * q, f4_tf32_residual(r));
         if (round_out) r = f4_tf32(r);
-        st_f4(out + (size_t)i * D + 4 * q, r);
+        st_f4(out + (size_t)i * ld_out + 4 * q, r);
       }
     }
   }
@@ -418,7 +418,7 @@ template <int NCH, int SRC>
 __global__ void __launch_bounds__(kRowThreads) bn_bwd_apply_kernel(
     const float* __restrict__ gy, const float* __restrict__ gp, const int32_t* __restrict__ node2graph,
     const int32_t* __restrict__ gptr, int pool_mean, const float* __restrict__ z, const float* __restrict__ bcoef,
-    int N, int D, float* __restrict__ gz, float* __restrict__ partials) {
+    int N, int D, float* __restrict__ gz, long long ld_gz, float* __restrict__ partials) {
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* cf = sm4;                 // [3][D4]
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(kRowThreads) bn_bwd_apply_kernel(
         r.z = fmaf(k1.z, g.z, fmaf(B.z, zv.z, A.z)); r.w = fmaf(k1.w, g.w, fmaf(B.w, zv.w, A.w));
         st[0][j] = f4_add(st[0][j], r);
         r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w);
-        st_f4(gz + (size_t)i * D + 4 * q, r);
+        st_f4(gz + (size_t)i * ld_gz + 4 * q, r);
       }
     }
   }
@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(kRowThreads) bn_bwd_apply_kernel(
 template <int NCH>
 __global__ void __launch_bounds__(kRowThreads) pool_fwd_kernel(
     const float* __restrict__ z, const float* __restrict__ coef, int relu, const int32_t* __restrict__ gptr,
-    const int32_t* __restrict__ gperm, int pool_mean, int G, int D, float* __restrict__ out, int round_out,
+    const int32_t* __restrict__ gperm, int pool_mean, int G, int D, float* __restrict__ out, long long ld_out, int round_out,
     float* __restrict__ out_lo) {
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
@@ -502,9 +502,9 @@ __global__ void __launch_bounds__(kRowThreads) pool_fwd_kernel(
       if (q < D4) {
         float4 r = acc[j];
         if (pool_mean) { r.x /= cntf; r.y /= cntf; r.z /= cntf; r.w /= cntf; }
-        if (out_lo) st_f4(out_lo + (size_t)g * D + 4 * q, f4_tf32_residual(r));
+        if (out_lo) st_f4(out_lo + (size_t)g * ld_out + 4 * q, f4_tf32_residual(r));
         if (round_out) r = f4_tf32(r);
-        st_f4(out + (size_t)g * D + 4 * q, r);
+        st_f4(out + (size_t)g * ld_out + 4 * q, r);
       }
     }
   }
@@ -557,6 +557,17 @@ __global__ void round_tf32_kernel(const float* __restrict__ src, float* __restri
     const float v = src[i], h = round_tf32(v);
     hi[i] = h;
     if (lo) lo[i] = round_tf32(v - h);
+  }
+}
+
+__global__ void round_tf32_2d_kernel(const float* __restrict__ src, long long ld_src, float* __restrict__ hi, float* __restrict__ lo,
+                                     long long ld_dst, int rows, int cols) {
+  const long long n = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
+    const float v = src[r * ld_src + c], h = round_tf32(v);
+    hi[r * ld_dst + c] = h;
+    if (lo) lo[r * ld_dst + c] = round_tf32(v - h);
   }
 }
 
@@ -640,19 +651,21 @@ extern "C" int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, in
 
 extern "C" int molclr_gine_aggregate_fwd(const float* src, const float* bn_coef, int relu, const int32_t* rowptr,
                                          const int32_t* col, const uint8_t* eattr, const float* B1, const float* B2,
-                                         int64_t N, int D, float* out, int round_tf32_out, float* out_lo, cudaStream_t stream) {
+                                         int64_t N, int D, float* out, int64_t ld_out, int round_tf32_out, float* out_lo,
+                                         cudaStream_t stream) {
   REQUIRE_D(D);
+  MOLCLR_REQUIRE(ld_out >= D && ld_out % 4 == 0, "gine_aggregate_fwd: ld_out must be >= D and a multiple of 4");
   if (N == 0) return 0;
   const size_t smem = (size_t)(kNumEdgeClass + 2) * D * sizeof(float);
   NCH_DISPATCH(D / 4, {
     if (bn_coef) {
       auto k = gine_aggregate_fwd_kernel<NCH, true>;
       k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
-          src, bn_coef, relu, rowptr, col, eattr, B1, B2, (int)N, D, out, round_tf32_out, out_lo);
+          src, bn_coef, relu, rowptr, col, eattr, B1, B2, (int)N, D, out, ld_out, round_tf32_out, out_lo);
     } else {
       auto k = gine_aggregate_fwd_kernel<NCH, false>;
       k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
-          src, nullptr, 0, rowptr, col, eattr, B1, B2, (int)N, D, out, round_tf32_out, out_lo);
+          src, nullptr, 0, rowptr, col, eattr, B1, B2, (int)N, D, out, ld_out, round_tf32_out, out_lo);
     }
   });
   MOLCLR_CHECK_LAUNCH("gine_aggregate_fwd");
@@ -730,9 +743,10 @@ extern "C" int molclr_bn_bwd_finalize(const float* partials, int P, int64_t N, i
 }
 
 extern "C" int molclr_bn_bwd_apply(const float* gy, const float* gp, const int32_t* node2graph, const int32_t* gptr, int pool_mean,
-                                   const float* z, const float* bcoef, int64_t N, int D, float* gz, float* dbias,
+                                   const float* z, const float* bcoef, int64_t N, int D, float* gz, int64_t ld_gz, float* dbias,
                                    float* partials, cudaStream_t stream) {
   REQUIRE_D(D);
+  MOLCLR_REQUIRE(ld_gz >= D && ld_gz % 4 == 0, "bn_bwd_apply: ld_gz must be >= D and a multiple of 4");
   if (N == 0) return 0;
   const size_t smem = (size_t)(3 + kRowWarps) * D * sizeof(float);
   int grid = 1;
@@ -740,11 +754,11 @@ extern "C" int molclr_bn_bwd_apply(const float* gy, const float* gp, const int32
     if (gp) {
       auto k = bn_bwd_apply_kernel<NCH, 1>;
       grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
-      k<<<grid, kRowThreads, smem, stream>>>(nullptr, gp, node2graph, gptr, pool_mean, z, bcoef, (int)N, D, gz, partials);
+      k<<<grid, kRowThreads, smem, stream>>>(nullptr, gp, node2graph, gptr, pool_mean, z, bcoef, (int)N, D, gz, ld_gz, partials);
     } else {
       auto k = bn_bwd_apply_kernel<NCH, 0>;
       grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
-      k<<<grid, kRowThreads, smem, stream>>>(gy, nullptr, nullptr, nullptr, 0, z, bcoef, (int)N, D, gz, partials);
+      k<<<grid, kRowThreads, smem, stream>>>(gy, nullptr, nullptr, nullptr, 0, z, bcoef, (int)N, D, gz, ld_gz, partials);
     }
   });
   MOLCLR_CHECK_LAUNCH("bn_bwd_apply");
@@ -753,7 +767,8 @@ extern "C" int molclr_bn_bwd_apply(const float* gy, const float* gp, const int32
 }
 
 extern "C" int molclr_pool_fwd(const float* z, const float* bn_coef, int relu, const int32_t* gptr, const int32_t* gperm,
-                               int pool_mode, int64_t G, int D, float* out, int round_tf32_out, float* out_lo, cudaStream_t stream) {
+                               int pool_mode, int64_t G, int D, float* out, int64_t ld_out, int round_tf32_out, float* out_lo,
+                               cudaStream_t stream) {
   REQUIRE_D(D);
   MOLCLR_REQUIRE(pool_mode == 0 || pool_mode == 1, "pool mode %d not supported (0 = mean, 1 = add)", pool_mode);
   if (G == 0) return 0;
@@ -761,7 +776,7 @@ extern "C" int molclr_pool_fwd(const float* z, const float* bn_coef, int relu, c
   NCH_DISPATCH(D / 4, {
     auto k = pool_fwd_kernel<NCH>;
     k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, G), kRowThreads, smem, stream>>>(z, bn_coef, relu, gptr, gperm,
-                                                                                          pool_mode == 0, (int)G, D, out, round_tf32_out, out_lo);
+                                                                                          pool_mode == 0, (int)G, D, out, ld_out, round_tf32_out, out_lo);
   });
   MOLCLR_CHECK_LAUNCH("pool_fwd");
   return 0;
@@ -789,6 +804,16 @@ extern "C" int molclr_round_tf32(const float* src, float* dst, float* lo, int64_
   if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
   round_tf32_kernel<<<(int)blocks, 256, 0, stream>>>(src, dst, lo, n);
   MOLCLR_CHECK_LAUNCH("round_tf32");
+  return 0;
+}
+
+extern "C" int molclr_round_tf32_2d(const float* src, int64_t ld_src, float* hi, float* lo, int64_t ld_dst, int64_t rows, int64_t cols,
+                                    cudaStream_t stream) {
+  if (rows * cols == 0) return 0;
+  int64_t blocks = (rows * cols + 1023) / 1024;
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  round_tf32_2d_kernel<<<(int)blocks, 256, 0, stream>>>(src, ld_src, hi, lo, ld_dst, (int)rows, (int)cols);
+  MOLCLR_CHECK_LAUNCH("round_tf32_2d");
   return 0;
 }
 

@@ -198,8 +198,8 @@ class _GINetFunction(torch.autograd.Function):
                 (ops.gine_aggregate_fwd(plan, src, g.edge_embedding1.weight.detach(), g.edge_embedding2.weight.detach(),
                                         bn_coef=coef_prev, relu=True, round_out=True), None)
             (W1, W1_lo), (W2, W2_lo) = rw.get(g.mlp[0].weight), rw.get(g.mlp[2].weight)
-            u = torch.empty(N, H, device=dev)
-            u_lo = torch.empty(N, H, device=dev) if comp else None
+            u = ops.padded(N, H, dev)
+            u_lo = ops.padded(N, H, dev) if comp else None
             ops.gemm(a, W1, N, H, D, A_lo=a_lo, B_lo=_lo(W1_lo, comp), out=u, out_lo=u_lo, bias=g.mlp[0].bias.detach(),
                      relu=True, round_out=True)
             z = torch.empty(N, D, device=dev)
@@ -245,7 +245,7 @@ class _GINetFunction(torch.autograd.Function):
             base = 2 + 8 * l
             grads[base + 6], grads[base + 7], grads[base + 3] = dgamma, dbeta, db2
             # g_u = (g_z W2) * [u > 0];  db1 = colsum(g_u)
-            g_u = torch.empty(N, H, device=dev)
+            g_u = ops.padded(N, H, dev)
             part = torch.empty(T, H, device=dev)
             ops.gemm(g_z, W2, N, H, D, b_mn=True, out=g_u, mask=u, round_out=True, colstat=part, colstat_mode=1)
             grads[base + 1] = ops.reduce_partials(part, T, H, torch.empty(H, device=dev))

@@ -17,6 +17,12 @@ def _empty(*shape, device):
     return torch.empty(*shape, dtype=F32, device=device)
 
 
+def padded(rows, cols, device):
+    """[rows, cols] fp32 view whose row stride is a multiple of 32 floats (128-byte aligned rows for TMA)."""
+    ld = (cols + 31) // 32 * 32
+    return torch.empty(rows, ld, dtype=F32, device=device)[:, :cols]
+
+
 def max_blocks():
     return _lib.load().molclr_rowwise_max_blocks()
 
@@ -33,12 +39,12 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=Non
     a.B, a.ldb, a.b_mn = ptr2d(B), (B.stride(0) if ldb is None else ldb), int(b_mn)
     a.A_lo, a.B_lo = ptr2d(A_lo), ptr2d(B_lo)
     a.M, a.N, a.K = M, N, K
-    a.out, a.ldo, a.transpose_out = ptr(out), (out.stride(0) if out is not None else 0), int(transpose_out)
-    a.out2, a.ldo2 = ptr(out2), (out2.stride(0) if out2 is not None else 0)
-    a.out_lo, a.ldo_lo = ptr(out_lo), (out_lo.stride(0) if out_lo is not None else 0)
+    a.out, a.ldo, a.transpose_out = ptr2d(out), (out.stride(0) if out is not None else 0), int(transpose_out)
+    a.out2, a.ldo2 = ptr2d(out2), (out2.stride(0) if out2 is not None else 0)
+    a.out_lo, a.ldo_lo = ptr2d(out_lo), (out_lo.stride(0) if out_lo is not None else 0)
     a.bias = ptr(bias)
-    a.addend, a.ldadd = ptr(addend), (addend.stride(0) if addend is not None else 0)
-    a.mask, a.ldmask = ptr(mask), (mask.stride(0) if mask is not None else 0)
+    a.addend, a.ldadd = ptr2d(addend), (addend.stride(0) if addend is not None else 0)
+    a.mask, a.ldmask = ptr2d(mask), (mask.stride(0) if mask is not None else 0)
     a.relu, a.round_out = int(relu), int(round_out)
     a.colstat, a.colstat_mode = ptr(colstat), int(colstat_mode)
     a.split_k = int(split_k)
@@ -105,7 +111,13 @@ def round_tf32(x):
 
 
 def split_tf32(x):
-    """(hi, lo) with hi = tf32(x), lo = tf32(x - hi): operands of the error-compensated product."""
+    """(hi, lo) with hi = tf32(x), lo = tf32(x - hi): operands of the error-compensated product.  2-D inputs
+    get 128-byte aligned rows."""
+    if x.dim() == 2:
+        hi, lo = padded(x.shape[0], x.shape[1], x.device), padded(x.shape[0], x.shape[1], x.device)
+        check(_lib.load().molclr_round_tf32_2d(ptr2d(x), x.stride(0), ptr2d(hi), ptr2d(lo), hi.stride(0), x.shape[0], x.shape[1],
+                                               stream()), "round_tf32_2d")
+        return hi, lo
     hi, lo = torch.empty_like(x), torch.empty_like(x)
     check(_lib.load().molclr_round_tf32(ptr(x), ptr(hi), ptr(lo), x.numel(), stream()), "round_tf32")
     return hi, lo
@@ -133,11 +145,12 @@ def embed_nodes_bwd(plan, g):
 def gine_aggregate_fwd(plan, src, B1, B2, bn_coef=None, relu=True, round_out=True, want_lo=False):
     """Returns the aggregate (tf32-rounded if round_out), plus its tf32 residual when want_lo."""
     D = src.shape[1]
-    out = torch.empty_like(src)
-    lo = torch.empty_like(src) if want_lo else None
+    out = padded(plan.N, D, src.device)          # a GEMM operand: 128-byte aligned rows
+    lo = padded(plan.N, D, src.device) if want_lo else None
     check(_lib.load().molclr_gine_aggregate_fwd(ptr(src), ptr(bn_coef), int(relu), ptr(plan.rowptr, torch.int32),
                                                 ptr(plan.col, torch.int32), ptr(plan.eattr, torch.uint8), ptr(B1), ptr(B2),
-                                                plan.N, D, ptr(out), int(round_out), ptr(lo), stream()), "gine_aggregate_fwd")
+                                                plan.N, D, ptr2d(out), out.stride(0), int(round_out), ptr2d(lo), stream()),
+          "gine_aggregate_fwd")
     return (out, lo) if want_lo else out
 
 
@@ -189,13 +202,13 @@ def bn_bwd_finalize(partials, P, N, gamma, coef, use_batch_stats):
 
 def bn_bwd_apply(z, bcoef, gy=None, gp=None, plan=None, pool_mean=True):
     N, D = z.shape
-    gz = torch.empty_like(z)
+    gz = padded(N, D, z.device)                  # a GEMM operand: 128-byte aligned rows
     dbias = _empty(D, device=z.device)
     partials = _empty(max_blocks(), D, device=z.device)
     n2g = ptr(plan.node2graph, torch.int32) if gp is not None else None
     gptr = ptr(plan.gptr, torch.int32) if gp is not None else None
-    check(_lib.load().molclr_bn_bwd_apply(ptr(gy), ptr(gp), n2g, gptr, int(pool_mean), ptr(z), ptr(bcoef), N, D, ptr(gz),
-                                          ptr(dbias), ptr(partials), stream()), "bn_bwd_apply")
+    check(_lib.load().molclr_bn_bwd_apply(ptr(gy), ptr(gp), n2g, gptr, int(pool_mean), ptr(z), ptr(bcoef), N, D, ptr2d(gz),
+                                          gz.stride(0), ptr(dbias), ptr(partials), stream()), "bn_bwd_apply")
     return gz, dbias
 
 
@@ -204,10 +217,10 @@ POOL_MODES = {"mean": 0, "add": 1}
 
 def pool_fwd(plan, z, bn_coef, pool_mode, relu=False, round_out=True, want_lo=False):
     D = z.shape[1]
-    out = _empty(plan.G, D, device=z.device)
-    lo = _empty(plan.G, D, device=z.device) if want_lo else None
+    out = padded(plan.G, D, z.device)
+    lo = padded(plan.G, D, z.device) if want_lo else None
     check(_lib.load().molclr_pool_fwd(ptr(z), ptr(bn_coef), int(relu), ptr(plan.gptr, torch.int32), ptr(plan.gperm, torch.int32),
-                                      pool_mode, plan.G, D, ptr(out), int(round_out), ptr(lo), stream()), "pool_fwd")
+                                      pool_mode, plan.G, D, ptr2d(out), out.stride(0), int(round_out), ptr2d(lo), stream()), "pool_fwd")
     return (out, lo) if want_lo else out
 
 
