@@ -206,7 +206,7 @@ def run_ours(args):
     launches = (lib.molclr_launch_count() - l0) // max(args.steps, 1)
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     value = world * B / (ms_step * 1e-3)
-    last_loss = float(loss.item())
+    last_loss = float((stepper.global_loss(loss) if stepper is not None else loss).item())
 
     # ---------------- e2e: pinned host batches, H2D + loss D2H inside the timed region
     def e2e_step(pair):
