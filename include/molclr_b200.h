@@ -98,10 +98,12 @@ int molclr_reduce_partials(const float* partials, int P, int len, float scale, i
 
 /* ---- BatchNorm1d: ginet_molclr.py:79-81,107 (torch defaults eps 1e-5, momentum 0.1) ----------------
  * tile_stats [T][2][D]: per tile of `tile_rows` rows, column mean and M2 (from the GEMM epilogue).
- * coef [4][D] = scale, shift, mean, invstd.  Updates running stats (unbiased var) and num_batches_tracked. */
+ * coef [4][D] = scale, shift, mean, invstd.  Updates running stats (unbiased var) and num_batches_tracked.
+ * Two-level deterministic merge (Chan et al.) through `workspace` (molclr_bn_finalize_workspace_bytes(D) bytes). */
+size_t molclr_bn_finalize_workspace_bytes(int D);
 int molclr_bn_fwd_finalize(const float* tile_stats, int T, int tile_rows, int64_t N, int D, const float* gamma,
                            const float* beta, float* running_mean, float* running_var, int64_t* num_batches_tracked,
-                           float momentum, float eps, float* coef, cudaStream_t stream);
+                           float momentum, float eps, float* coef, void* workspace /* 8-byte aligned */, cudaStream_t stream);
 int molclr_bn_eval_coef(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                         float eps, int D, float* coef, cudaStream_t stream);
 /* partials [P][2][D] = (sum gy, sum gy*xhat).  Writes dgamma, dbeta and bcoef [3][D] = (k1, A, B) with
@@ -126,7 +128,7 @@ int molclr_pool_bwd_stats(const float* gp, const int32_t* node2graph, const int3
  * gcn_molclr.py:76 and their autograd backward, on tcgen05 tensor cores (TF32 in, FP32 accumulate) ----
  * C[M][N] = sum_k A(m,k) * B(n,k).
  *   a_mn = 0: A is row-major [M][K] (ld = lda);  a_mn = 1: A is row-major [K][M].   Same for B with N.
- * Epilogue, in this order: + bias[n]; + addend[m][n]; relu; * (mask[m][n] > 0); column statistics of the
+ * Epilogue, in this order: + bias[n]; + addend[m][n]; relu; * (mask[m][n] > 0) or the mask_bits bit; column statistics of the
  * result per 32-row group (colstat_mode 1: sums -> colstat[group][N]; 2: mean and M2 -> colstat[group][2][N]);
  * out = (round_out ? tf32-rounded : exact); out2 = tf32-rounded copy.
  * A_lo/B_lo (both or neither; same shape and ld as A/B): the tf32-rounded residuals x - tf32(x) of the true
@@ -149,11 +151,15 @@ typedef struct {
   int32_t relu, round_out;
   float* colstat; int32_t colstat_mode;
   int32_t split_k;
+  uint32_t* relu_bits;        /* out: bit (n % 32) of word [m][n / 32] = (result[m][n] > 0)               */
+  const uint32_t* mask_bits;  /* in : result[m][n] = 0 where the bit is clear (ReLU backward), after bias/relu */
+  int64_t ld_bits;            /* words per row of either, >= molclr_gemm_mask_words(N)                    */
 } molclr_gemm_args;
 /* column statistics are emitted per group of molclr_gemm_colstat_tile_rows() (= 32) consecutive rows;
  * molclr_gemm_colstat_tiles(M) groups are written (a multiple of 4; trailing groups may be empty). */
 int molclr_gemm_colstat_tiles(int64_t M);
 int molclr_gemm_colstat_tile_rows(void);
+int molclr_gemm_mask_words(int64_t N);
 int molclr_gemm_tf32(const molclr_gemm_args* args /* host */, cudaStream_t stream);
 
 /* ---- small elementwise ops ---------------------------------------------------------------------- */

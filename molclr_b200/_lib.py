@@ -30,6 +30,7 @@ class GemmArgs(C.Structure):
         ("relu", C.c_int32), ("round_out", C.c_int32),
         ("colstat", vp), ("colstat_mode", C.c_int32),
         ("split_k", C.c_int32),
+        ("relu_bits", vp), ("mask_bits", vp), ("ld_bits", i64),
     ]
 
 
@@ -49,7 +50,8 @@ SIGNATURES = {
     "molclr_gine_aggregate_bwd": (i32, [vp, vp, vp, vp, vp, i32, i64, i32, vp, vp, C.POINTER(i32), vp]),
     "molclr_edge_table_grad": (i32, [vp, vp, i64, i32, vp, vp, vp]),
     "molclr_reduce_partials": (i32, [vp, i32, i32, f32, i32, vp, vp]),
-    "molclr_bn_fwd_finalize": (i32, [vp, i32, i32, i64, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp]),
+    "molclr_bn_finalize_workspace_bytes": (sz, [i32]),
+    "molclr_bn_fwd_finalize": (i32, [vp, i32, i32, i64, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp]),
     "molclr_bn_eval_coef": (i32, [vp, vp, vp, vp, f32, i32, vp, vp]),
     "molclr_bn_bwd_finalize": (i32, [vp, i32, i64, i32, vp, vp, i32, vp, vp, vp, vp]),
     "molclr_bn_bwd_apply": (i32, [vp, vp, vp, vp, i32, vp, vp, i64, i32, vp, i64, vp, vp, vp]),
@@ -57,6 +59,7 @@ SIGNATURES = {
     "molclr_pool_bwd_stats": (i32, [vp, vp, vp, i32, vp, vp, i64, i32, vp, C.POINTER(i32), vp]),
     "molclr_gemm_colstat_tiles": (i32, [i64]),
     "molclr_gemm_colstat_tile_rows": (i32, []),
+    "molclr_gemm_mask_words": (i32, [i64]),
     "molclr_gemm_tf32": (i32, [C.POINTER(GemmArgs), vp]),
     "molclr_round_tf32": (i32, [vp, vp, vp, i64, vp]),
     "molclr_round_tf32_2d": (i32, [vp, i64, vp, vp, i64, i64, i64, vp]),

@@ -235,6 +235,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row = q * 32 + lane, grow = m0 + row;
       const int rows_w = max(0, min(32, p.M - m0 - q * 32));          // valid rows of this warp's group
       const uint32_t buf = tl & 1;
+      constexpr int CH = Cfg::CHUNK, LD = Cfg::CHUNK_LD;
+      constexpr int STEP = CH * NSHARE;                  // column distance between consecutive chunks of this warp
+      constexpr int NCHUNK = (BN + STEP - 1) / STEP;
+      // ReLU-mask words of this thread's row (K_PLAIN backward GEMMs): fetched BEFORE waiting for the accumulator so
+      // that their latency hides behind the MMAs of this tile.
+      uint32_t mb[NCHUNK];
+      if (KIND == K_PLAIN && !FOUR) {
+#pragma unroll
+        for (int k = 0; k < NCHUNK; ++k) {
+          const int c0 = CH * (half + k * NSHARE);
+          mb[k] = (p.bits_in && c0 < BN && n0 + c0 < p.N && grow < p.M) ? __ldg(p.bits_in + (size_t)grow * p.ld_bits + ((n0 + c0) >> 5)) : 0u;
+        }
+      }
       ptx::mbar_wait(tfull_bar + buf, (tl >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
@@ -284,42 +297,66 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       } else {
-        // TMEM -> registers (thread = row) -> per-warp staging chunk -> coalesced row segments.  All elementwise
-        // terms are applied in the copy-out pass, where a lane owns one fixed float4 column group of the chunk.
+        // TMEM -> registers (thread = row) -> per-warp staging chunk -> coalesced row segments.  K_PLAIN applies
+        // alpha / bias / ReLU / the ReLU bit mask in the register stage (and emits the ReLU bits of the result);
+        // the other kinds apply their terms in the copy-out pass, where a lane owns one float4 column group.
         const int group = m_tile * 4 + q;
-        constexpr int CH = Cfg::CHUNK, LD = Cfg::CHUNK_LD;
         constexpr int LPR = CH / 4;            // lanes covering one row of the chunk (float4 each)
         constexpr int RPP = 32 / LPR;          // rows per copy-out pass
         const float alpha = p.alpha, floor_v = p.relu ? 0.f : -INFINITY;
         const bool has_bias = p.bias != nullptr, do_round = p.round_out != 0, has_out = p.out != nullptr,
-                   has_out2 = p.out2 != nullptr, has_lo = p.out_lo != nullptr, has_stat = p.colstat != nullptr;
+                   has_out2 = p.out2 != nullptr, has_lo = p.out_lo != nullptr, has_stat = p.colstat != nullptr,
+                   has_bits_in = p.bits_in != nullptr, has_bits_out = p.bits_out != nullptr;
         const int cq = 4 * (lane % LPR), r_in = lane / LPR;
-        for (int c0 = CH * half; c0 < BN && n0 + c0 < p.N; c0 += CH * NSHARE) {
+#pragma unroll(FOUR ? 1 : NCHUNK)
+        for (int k = 0; k < NCHUNK; ++k) {
+          const int c0 = CH * (half + k * NSHARE);
+          if (c0 >= BN || n0 + c0 >= p.N) break;
           if (p.debug & 1) break;                     // timing experiment: no epilogue work at all
           float v[CH];
           ptx::tmem_ld_x16_nowait(taddr + c0, v);
           if (CH == 32) ptx::tmem_ld_x16_nowait(taddr + c0 + 16, v + (CH == 32 ? 16 : 0));
           ptx::tmem_ld_wait();
+          if (KIND == K_PLAIN) {
+#pragma unroll
+            for (int j = 0; j < CH; j += 4) {
+              const int colj = n0 + c0 + j;
+              float4 b4 = f4_zero();
+              if (has_bias && colj < p.N) b4 = ldg_f4(p.bias + colj);     // warp-uniform address
+              v[j] = fmaxf(fmaf(v[j], alpha, b4.x), floor_v); v[j + 1] = fmaxf(fmaf(v[j + 1], alpha, b4.y), floor_v);
+              v[j + 2] = fmaxf(fmaf(v[j + 2], alpha, b4.z), floor_v); v[j + 3] = fmaxf(fmaf(v[j + 3], alpha, b4.w), floor_v);
+            }
+            if (!FOUR && has_bits_in) {
+              const uint32_t w = mb[k];
+#pragma unroll
+              for (int j = 0; j < CH; ++j) if (!((w >> j) & 1u)) v[j] = 0.f;
+            }
+            if (has_bits_out) {
+              uint32_t ob = 0;
+#pragma unroll
+              for (int j = 0; j < CH; ++j) ob |= (v[j] > 0.f ? 1u : 0u) << j;
+              if (grow < p.M) {
+                const size_t w = (size_t)grow * p.ld_bits + ((n0 + c0) >> 5);
+                if (CH == 32) p.bits_out[w] = ob;
+                else reinterpret_cast<uint16_t*>(p.bits_out)[2 * w + (((n0 + c0) >> 4) & 1)] = (uint16_t)ob;
+              }
+            }
+          }
 #pragma unroll
           for (int j = 0; j < CH; j += 4) st_f4(stg + lane * LD + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
           __syncwarp();
           const int col = n0 + c0 + cq;
           const bool col_ok = col < p.N;
-          float4 b4 = f4_zero();
-          if (KIND == K_PLAIN && has_bias && col_ok) b4 = ldg_f4(p.bias + col);
 #pragma unroll
           for (int pass = 0; pass < 32 / RPP; ++pass) {
             const int r = pass * RPP + r_in;
             if (r < rows_w && col_ok) {
               const int gr = m0 + q * 32 + r;
               float4 x = *reinterpret_cast<const float4*>(stg + r * LD + cq);
-              if (KIND == K_PLAIN) {
-                x.x = fmaxf(fmaf(x.x, alpha, b4.x), floor_v); x.y = fmaxf(fmaf(x.y, alpha, b4.y), floor_v);
-                x.z = fmaxf(fmaf(x.z, alpha, b4.z), floor_v); x.w = fmaxf(fmaf(x.w, alpha, b4.w), floor_v);
-              } else {
+              if (KIND != K_PLAIN) {
                 x = epilogue_apply(x, p, gr, col);
+                if (has_stat) st_f4(stg + r * LD + cq, x);
               }
-              if (has_stat) st_f4(stg + r * LD + cq, x);
               const float4 xr = f4_tf32(x);
               if (has_out) st_f4(p.out + (size_t)gr * p.ldo + col, do_round ? xr : x);
               if (has_out2) st_f4(p.out2 + (size_t)gr * p.ldo2 + col, xr);
@@ -516,6 +553,12 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   const bool atomic = job.split_k > 1 || p.transpose_out;
   MOLCLR_REQUIRE((job.A_lo == nullptr) == (job.B_lo == nullptr), "gemm: A_lo and B_lo must be given together");
   p.segments = job.A_lo ? 3 : 1;
+  MOLCLR_REQUIRE((!p.bits_in && !p.bits_out) || (p.epi == EPI_GENERIC && !atomic && !p.mask && !p.addend),
+                 "gemm: ReLU bit masks need the plain epilogue (no float mask / addend / split-K)");
+  MOLCLR_REQUIRE(!p.bits_in || p.segments == 1, "gemm: mask_bits is not supported by the compensated product");
+  if (p.bits_in || p.bits_out)
+    MOLCLR_REQUIRE(p.ld_bits >= molclr_gemm_mask_words(p.N), "gemm: ld_bits=%lld < molclr_gemm_mask_words(N)=%d", (long long)p.ld_bits,
+                   molclr_gemm_mask_words(p.N));
   if (atomic)
     MOLCLR_REQUIRE(p.segments == 1 && !p.out_lo && p.epi == EPI_GENERIC && !p.bias && !p.addend && !p.mask && !p.relu && !p.round_out && !p.out2 && !p.colstat && p.out &&
                        p.alpha == 1.f,
@@ -565,6 +608,11 @@ using namespace molclr;
 
 extern "C" int molclr_gemm_colstat_tiles(int64_t M) { return 4 * (int)((M + GEMM_BM - 1) / GEMM_BM); }
 extern "C" int molclr_gemm_colstat_tile_rows(void) { return GEMM_STAT_ROWS; }
+// 32-bit words per row of a ReLU bit mask over N columns (covers the column tiles the kernel will use)
+extern "C" int molclr_gemm_mask_words(int64_t N) {
+  const int bn = (N % 256 == 0 || N > 640) ? 256 : 160;
+  return (int)((N + bn - 1) / bn) * (bn / 32);
+}
 
 extern "C" int molclr_gemm_tf32(const molclr_gemm_args* args, cudaStream_t stream) {
   const molclr_gemm_args& a = *args;
@@ -579,6 +627,7 @@ extern "C" int molclr_gemm_tf32(const molclr_gemm_args* args, cudaStream_t strea
   p.out_lo = a.out_lo; p.ldo_lo = a.ldo_lo;
   p.bias = a.bias; p.addend = a.addend; p.ldadd = a.ldadd; p.mask = a.mask; p.ldmask = a.ldmask;
   p.relu = a.relu; p.round_out = a.round_out; p.colstat = a.colstat; p.colstat_mode = a.colstat_mode;
+  p.bits_out = a.relu_bits; p.bits_in = a.mask_bits; p.ld_bits = a.ld_bits;
   p.alpha = 1.f; p.epi = EPI_GENERIC;
   return gemm_run(j, stream);
 }

@@ -19,6 +19,7 @@ struct GemmParams {
   const float* bias;
   const float* addend; long long ldadd;
   const float* mask; long long ldmask;
+  uint32_t* bits_out; const uint32_t* bits_in; long long ld_bits;   // ReLU bit masks [M][ld_bits] (bit c%32 of word c/32)
   int relu, round_out;
   float* colstat; int colstat_mode;
   int atomic_out;

@@ -320,15 +320,19 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __re
 // coefficients the consumers use, and updates the running statistics exactly once.
 //   coef[0]=scale=gamma*invstd  coef[1]=shift=beta-mean*scale  coef[2]=mean  coef[3]=invstd
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) bn_fwd_finalize_kernel(
-    const float* __restrict__ tile_stats /* [T][2][D] */, int T, int tile_rows, int N, int D,
-    const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean, float* running_var,
-    long long* num_batches_tracked, float momentum, float eps, float* __restrict__ coef) {
+constexpr int kBnSplits = 32;   // first-level partial merges (one block row each)
+
+// Level 1: block (x = 32 columns, y = 16) of split s merges the tiles [s*per, (s+1)*per) into one (n, mean, M2)
+// per column, kept in double: ws[s][3][D].
+__global__ void __launch_bounds__(512) bn_merge_tiles_kernel(
+    const float* __restrict__ tile_stats /* [T][2][D] */, int T, int tile_rows, int N, int D, int per,
+    double* __restrict__ ws) {
   __shared__ double s_n[16][33], s_mean[16][33], s_m2[16][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
+  const int t0 = blockIdx.y * per, t1 = min(T, t0 + per);
   double n = 0.0, mean = 0.0, m2 = 0.0;
   if (c < D) {
-    for (int t = threadIdx.y; t < T; t += 16) {
+    for (int t = t0 + threadIdx.y; t < t1; t += 16) {
       const int rows = min(tile_rows, N - t * tile_rows);
       if (rows <= 0) continue;                       // padding groups of the last 128-row GEMM tile
       const double nb = rows, mb = tile_stats[((size_t)t * 2) * D + c], qb = tile_stats[((size_t)t * 2 + 1) * D + c];
@@ -349,6 +353,27 @@ __global__ void __launch_bounds__(512) bn_fwd_finalize_kernel(
       m2 += s_m2[k][threadIdx.x] + delta * delta * (n * nb / tot);
       n = tot;
     }
+    double* w = ws + (size_t)blockIdx.y * 3 * D;
+    w[c] = n; w[D + c] = mean; w[2 * D + c] = m2;
+  }
+}
+
+// Level 2: merges the S partials of each column, writes the coefficients and updates the running statistics.
+__global__ void __launch_bounds__(128) bn_fwd_finalize_kernel(
+    const double* __restrict__ ws /* [S][3][D] */, int S, int D,
+    const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean, float* running_var,
+    long long* num_batches_tracked, float momentum, float eps, float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < D) {
+    double n = 0.0, mean = 0.0, m2 = 0.0;
+    for (int k = 0; k < S; ++k) {
+      const double nb = ws[(size_t)k * 3 * D + c];
+      if (nb == 0.0) continue;
+      const double tot = n + nb, delta = ws[(size_t)k * 3 * D + D + c] - mean;
+      mean += delta * (nb / tot);
+      m2 += ws[(size_t)k * 3 * D + 2 * D + c] + delta * delta * (n * nb / tot);
+      n = tot;
+    }
     const double var = (n > 0.0) ? m2 / n : 0.0;
     const float invstd = (float)(1.0 / sqrt(var + (double)eps));
     const float scale = gamma[c] * invstd;
@@ -362,7 +387,7 @@ __global__ void __launch_bounds__(512) bn_fwd_finalize_kernel(
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
     }
   }
-  if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0) *num_batches_tracked += 1;
+  if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;
 }
 
 // Eval mode (molclr.py:163): coefficients from the running statistics.
@@ -717,12 +742,22 @@ extern "C" int molclr_edge_table_grad(const float* ga, const uint16_t* cnt, int6
   return molclr_reduce_partials(partials, grid, 8 * D, 1.f, 0, dB, stream);
 }
 
+extern "C" size_t molclr_bn_finalize_workspace_bytes(int D) { return (size_t)kBnSplits * 3 * D * sizeof(double); }
+
 extern "C" int molclr_bn_fwd_finalize(const float* tile_stats, int T, int tile_rows, int64_t N, int D, const float* gamma,
                                       const float* beta, float* running_mean, float* running_var, int64_t* num_batches_tracked,
-                                      float momentum, float eps, float* coef, cudaStream_t stream) {
-  bn_fwd_finalize_kernel<<<(D + 31) / 32, dim3(32, 16), 0, stream>>>(tile_stats, T, tile_rows, (int)N, D, gamma, beta, running_mean,
-                                                                       running_var, reinterpret_cast<long long*>(num_batches_tracked),
-                                                                       momentum, eps, coef);
+                                      float momentum, float eps, float* coef, void* workspace, cudaStream_t stream) {
+  MOLCLR_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 7) == 0, "bn_fwd_finalize: workspace must be 8-byte aligned");
+  MOLCLR_REQUIRE(T > 0 && D > 0, "bn_fwd_finalize: empty statistics");
+  int S = (T + 15) / 16;
+  if (S > kBnSplits) S = kBnSplits;
+  const int per = (T + S - 1) / S;
+  S = (T + per - 1) / per;
+  double* ws = reinterpret_cast<double*>(workspace);
+  bn_merge_tiles_kernel<<<dim3((D + 31) / 32, S), dim3(32, 16), 0, stream>>>(tile_stats, T, tile_rows, (int)N, D, per, ws);
+  MOLCLR_CHECK_LAUNCH("bn_merge_tiles");
+  bn_fwd_finalize_kernel<<<(D + 127) / 128, 128, 0, stream>>>(ws, S, D, gamma, beta, running_mean, running_var,
+                                                              reinterpret_cast<long long*>(num_batches_tracked), momentum, eps, coef);
   MOLCLR_CHECK_LAUNCH("bn_fwd_finalize");
   return 0;
 }

@@ -200,8 +200,9 @@ class _GINetFunction(torch.autograd.Function):
             (W1, W1_lo), (W2, W2_lo) = rw.get(g.mlp[0].weight), rw.get(g.mlp[2].weight)
             u = ops.padded(N, H, dev)
             u_lo = ops.padded(N, H, dev) if comp else None
+            ubits = ops.relu_bits_buffer(N, H, dev)       # [u > 0] as bits: the backward GEMM's mask (8 MB instead of 246)
             ops.gemm(a, W1, N, H, D, A_lo=a_lo, B_lo=_lo(W1_lo, comp), out=u, out_lo=u_lo, bias=g.mlp[0].bias.detach(),
-                     relu=True, round_out=True)
+                     relu=True, round_out=True, relu_bits=ubits)
             z = torch.empty(N, D, device=dev)
             if training:
                 stats = torch.empty(T, 2, D, device=dev)
@@ -213,7 +214,7 @@ class _GINetFunction(torch.autograd.Function):
             else:
                 ops.gemm(u, W2, N, D, H, A_lo=u_lo, B_lo=_lo(W2_lo, comp), out=z, bias=g.mlp[2].bias.detach())
                 coef = ops.bn_eval_coef(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
-            layers.append((a, u, z, coef, W1, W2))
+            layers.append((a, u, z, coef, W1, W2, ubits))
             src, coef_prev = z, coef
             del a_lo, u_lo
         p, p_lo = ops.pool_fwd(plan, src, coef_prev, pool_mode, relu=False, round_out=True, want_lo=True) if comp else \
@@ -234,20 +235,20 @@ class _GINetFunction(torch.autograd.Function):
         pool_mean = ctx.pool_mode == 0
         grads = [None] * (2 + 8 * L)
         # last layer: BatchNorm backward fed by the pool backward (g_y is never materialised)
-        a, u, z, coef, W1, W2 = layers[L - 1]
+        a, u, z, coef, W1, W2, ubits = layers[L - 1]
         bn = m.batch_norms[L - 1]
         partials, P = ops.pool_bwd_stats(plan, g_p, z, coef, ctx.pool_mode)
         dgamma, dbeta, bcoef = ops.bn_bwd_finalize(partials, P, N, bn.weight.detach(), coef, ctx.training)
         g_z, db2 = ops.bn_bwd_apply(z, bcoef, gp=g_p, plan=plan, pool_mean=pool_mean)
         T = ops.colstat_tiles(N)
         for l in range(L - 1, -1, -1):
-            a, u, z, coef, W1, W2 = layers[l]
+            a, u, z, coef, W1, W2, ubits = layers[l]
             base = 2 + 8 * l
             grads[base + 6], grads[base + 7], grads[base + 3] = dgamma, dbeta, db2
             # g_u = (g_z W2) * [u > 0];  db1 = colsum(g_u)
             g_u = ops.padded(N, H, dev)
             part = torch.empty(T, H, device=dev)
-            ops.gemm(g_z, W2, N, H, D, b_mn=True, out=g_u, mask=u, round_out=True, colstat=part, colstat_mode=1)
+            ops.gemm(g_z, W2, N, H, D, b_mn=True, out=g_u, mask_bits=ubits, round_out=True, colstat=part, colstat_mode=1)
             grads[base + 1] = ops.reduce_partials(part, T, H, torch.empty(H, device=dev))
             grads[base + 2] = ops.gemm_dw(g_z, u)                 # dW2 [D, H]
             g_a = torch.empty(N, D, device=dev)
@@ -255,7 +256,7 @@ class _GINetFunction(torch.autograd.Function):
             grads[base + 0] = ops.gemm_dw(g_u, a)                 # dW1 [H, D]
             grads[base + 4], grads[base + 5] = ops.edge_table_grad(plan, g_a)
             if l > 0:
-                _, _, zp, coefp, _, _ = layers[l - 1]
+                _, _, zp, coefp, _, _, _ = layers[l - 1]
                 bnp = m.batch_norms[l - 1]
                 g_y, partials, P = ops.gine_aggregate_bwd(plan, g_a, z_prev=zp, bn_coef=coefp, relu=True)
                 dgamma, dbeta, bcoef = ops.bn_bwd_finalize(partials, P, N, bnp.weight.detach(), coefp, ctx.training)

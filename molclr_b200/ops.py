@@ -30,7 +30,7 @@ def max_blocks():
 # ------------------------------------------------------------------------------------------- GEMM
 def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=None, out2=None, out_lo=None, bias=None,
          addend=None, mask=None, relu=False, round_out=False, colstat=None, colstat_mode=0, transpose_out=False,
-         split_k=1, lda=None, ldb=None):
+         split_k=1, lda=None, ldb=None, relu_bits=None, mask_bits=None):
     """C[M,N] = sum_k A(m,k) B(n,k) on tcgen05 (TF32 in, FP32 accumulate) with the fused epilogue of
     ``molclr_gemm_tf32`` (see include/molclr_b200.h)."""
     lib = _lib.load()
@@ -48,8 +48,16 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=Non
     a.relu, a.round_out = int(relu), int(round_out)
     a.colstat, a.colstat_mode = ptr(colstat), int(colstat_mode)
     a.split_k = int(split_k)
+    bits = relu_bits if relu_bits is not None else mask_bits
+    a.relu_bits, a.mask_bits = ptr(relu_bits, torch.int32), ptr(mask_bits, torch.int32)
+    a.ld_bits = bits.stride(0) if bits is not None else 0
     check(lib.molclr_gemm_tf32(C.byref(a), stream()), "gemm_tf32")
     return out
+
+
+def relu_bits_buffer(M, N, device):
+    """[M, words] int32 buffer for the ReLU bit mask of an [M, N] GEMM result."""
+    return torch.empty(M, _lib.load().molclr_gemm_mask_words(N), dtype=torch.int32, device=device)
 
 
 def colstat_tiles(M):
@@ -178,8 +186,10 @@ def edge_table_grad(plan, ga):
 def bn_fwd_finalize(tile_stats, T, N, gamma, beta, running_mean, running_var, nbt, momentum, eps):
     D = gamma.shape[0]
     coef = _empty(4, D, device=gamma.device)
-    check(_lib.load().molclr_bn_fwd_finalize(ptr(tile_stats), T, colstat_tile_rows(), N, D, ptr(gamma), ptr(beta), ptr(running_mean),
-                                             ptr(running_var), ptr(nbt, torch.int64), momentum, eps, ptr(coef), stream()),
+    lib = _lib.load()
+    ws = torch.empty(lib.molclr_bn_finalize_workspace_bytes(D) // 8, dtype=torch.float64, device=gamma.device)
+    check(lib.molclr_bn_fwd_finalize(ptr(tile_stats), T, colstat_tile_rows(), N, D, ptr(gamma), ptr(beta), ptr(running_mean),
+                                     ptr(running_var), ptr(nbt, torch.int64), momentum, eps, ptr(coef), ptr(ws, torch.float64), stream()),
           "bn_fwd_finalize")
     return coef
 

@@ -178,6 +178,37 @@ def test_gemm_epilogues():
         assert rel_err(st[t, 1], ((blk - blk.mean(0)) ** 2).sum(0)) < 1e-4
 
 
+def _unpack_bits(bits, N):
+    """[M, W] int32 words -> bool [M, N] (bit c % 32 of word c // 32)."""
+    w = bits.cpu().numpy().view(np.uint32)
+    cols = np.arange(N)
+    return torch.from_numpy(((w[:, cols // 32] >> (cols % 32).astype(np.uint32)) & 1).astype(bool))
+
+
+@pytest.mark.parametrize("M,N,K,comp", [(1000, 600, 300, False), (1000, 600, 300, True), (333, 512, 300, False), (200, 300, 64, True)])
+def test_gemm_relu_bit_mask_roundtrip(M, N, K, comp):
+    """Forward GEMM emits [result > 0] as bits (bit-exact against its own fp32 output); the backward GEMM applies them."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A, B = torch.randn(M, K, generator=g).to(DEV), torch.randn(N, K, generator=g).to(DEV)
+    (A_hi, A_lo), (B_hi, B_lo) = ops.split_tf32(A), ops.split_tf32(B)
+    bias = torch.randn(N, generator=g).to(DEV)
+    bits = ops.relu_bits_buffer(M, N, DEV)
+    bits.fill_(-1)
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm(A_hi, B_hi, M, N, K, A_lo=A_lo if comp else None, B_lo=B_lo if comp else None, out=out, bias=bias, relu=True,
+             relu_bits=bits)
+    assert torch.equal(_unpack_bits(bits, N), out.cpu() > 0)
+    # backward-style product masked by the bits, with column sums
+    G_, W_ = tf32_round(torch.randn(M, K, generator=g)).to(DEV), tf32_round(torch.randn(N, K, generator=g)).to(DEV)
+    T = ops.colstat_tiles(M)
+    gu, part = torch.empty(M, N, device=DEV), torch.empty(T, N, device=DEV)
+    ops.gemm(G_, W_, M, N, K, out=gu, mask_bits=bits, round_out=True, colstat=part, colstat_mode=1)
+    want = _gemm_ref(G_, W_, False, False) * (out.cpu() > 0)
+    assert max_rel(gu, want) < 1e-3 and torch.equal(gu == 0, (want == 0).to(DEV) | (gu == 0))
+    assert torch.equal((gu != 0).cpu() & ~(out.cpu() > 0), torch.zeros(M, N, dtype=torch.bool))
+    assert rel_err(part.double().sum(0), gu.double().sum(0)) < 1e-5
+
+
 @pytest.mark.parametrize("M,N,K,b_mn", [(1000, 600, 300, False), (333, 300, 600, False), (512, 512, 300, True)])
 def test_gemm_compensated_three_pass_is_fp32_accurate(M, N, K, b_mn):
     """A_hi*B_hi + A_lo*B_hi + A_hi*B_lo on unrounded fp32 inputs: ~fp32 accuracy (used by the forward pass)."""
