@@ -206,7 +206,7 @@ def test_gemm_relu_bit_mask_roundtrip(M, N, K, comp):
     want = _gemm_ref(G_, W_, False, False) * (out.cpu() > 0)
     assert max_rel(gu, want) < 1e-3 and torch.equal(gu == 0, (want == 0).to(DEV) | (gu == 0))
     assert torch.equal((gu != 0).cpu() & ~(out.cpu() > 0), torch.zeros(M, N, dtype=torch.bool))
-    assert rel_err(part.double().sum(0), gu.double().sum(0)) < 1e-5
+    assert rel_err(part.double().sum(0), want.sum(0)) < 1e-4          # sums of the exact (unrounded) masked product
 
 
 @pytest.mark.parametrize("M,N,K,b_mn", [(1000, 600, 300, False), (333, 300, 600, False), (512, 512, 300, True)])

@@ -21,8 +21,21 @@ def timeit(fn, iters=10):
     return a.elapsed_time(b) / iters * 1e3   # us
 
 
-def case(name, M, N, K, comp=False, b_mn=False, relu=False, pad_k=0, dw=False):
+def case(name, M, N, K, comp=False, b_mn=False, relu=False, pad_k=0, dw=False, masked=False, stat=0):
     g = torch.Generator().manual_seed(0)
+    if masked or stat:
+        A = ops.round_tf32(torch.randn(M, K, generator=g).to(dev))
+        B = ops.round_tf32((torch.randn(K, N, generator=g) if b_mn else torch.randn(N, K, generator=g)).to(dev))
+        out = ops.padded(M, N, dev)
+        bits = ops.relu_bits_buffer(M, N, dev)
+        bits.random_(-2**31, 2**31 - 1)
+        T = ops.colstat_tiles(M)
+        part = torch.empty(T, (2 if stat == 2 else 1) * N, device=dev) if stat else None
+        fn = lambda: ops.gemm(A, B, M, N, K, b_mn=b_mn, out=out, mask_bits=bits if masked else None, round_out=True, colstat=part,
+                              colstat_mode=stat)
+        us = timeit(fn)
+        print(f"{name:34s} {us:9.1f} us  {2.0 * M * N * K / us / 1e6:8.1f} TFLOP/s  out {M * N * 4 / us / 1e3:7.1f} GB/s")
+        return
     if dw:
         dY, X = torch.randn(M, N, generator=g).to(dev), torch.randn(M, K, generator=g).to(dev)
         us = timeit(lambda: ops.gemm_dw(dY, X))
@@ -60,5 +73,9 @@ case("fwd1 x1 pitch 304->320", M, 600, 300, pad_k=20)
 case("dX   x1   [M,300]x[300,600]mn", M, 600, 300, b_mn=True)
 case("dX   x1   [M,600]x[600,300]mn", M, 300, 600, b_mn=True)
 case("sq   x1   [M,512]x[512,512]", M, 512, 512)
+case("dU masked+colsum [M,300]x[300,600]mn", M, 600, 300, b_mn=True, masked=True, stat=1)
+case("dU masked        [M,300]x[300,600]mn", M, 600, 300, b_mn=True, masked=True)
+case("dU colsum        [M,300]x[300,600]mn", M, 600, 300, b_mn=True, stat=1)
+case("fwd2 x1 bn-stats [M,600]x[300,600]", M, 300, 600, stat=2)
 case("dW   [M,300]^T[M,600]", M, 300, 600, dw=True)
 case("dW   [M,600]^T[M,300]", M, 600, 300, dw=True)
