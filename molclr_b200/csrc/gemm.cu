@@ -108,6 +108,31 @@ __device__ __forceinline__ void colstat_group(const float* stage, int lds, int n
   }
 }
 
+// Warp version for the tensor-core epilogue: lane c owns column c of a 32-row staged chunk; the 32 row reads are
+// independent (fully unrolled), so their latency overlaps.
+template <int NCOLS>
+__device__ __forceinline__ void colstat_warp(const float* stage, int lds, int rows, int col0, int group, const GemmParams& p, int lane) {
+  const int c = lane, col = col0 + c;
+  if (NCOLS < 32 && c >= NCOLS) return;
+  float x[32];
+#pragma unroll
+  for (int r = 0; r < 32; ++r) x[r] = stage[r * lds + c];
+  float s = 0.f;
+#pragma unroll
+  for (int r = 0; r < 32; ++r) s += (r < rows) ? x[r] : 0.f;
+  if (col >= p.N) return;
+  if (p.colstat_mode == 1) {
+    p.colstat[(size_t)group * p.N + col] = s;
+  } else {
+    const float mean = rows > 0 ? s / (float)rows : 0.f;
+    float m2 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) { const float d = x[r] - mean; m2 = (r < rows) ? fmaf(d, d, m2) : m2; }
+    p.colstat[((size_t)group * 2) * p.N + col] = mean;
+    p.colstat[((size_t)group * 2 + 1) * p.N + col] = m2;
+  }
+}
+
 // Persistent, warp-specialised tcgen05 GEMM.  Each CTA (one per SM) walks tiles t = blockIdx.x + i*gridDim.x of the
 // (n_tile fastest, m_tile, k_split) grid.  The TMA producer and the MMA issuer run ahead across tiles through a
 // STAGES-deep smem ring; accumulators are double-buffered in TMEM so the 4 epilogue warps drain tile i while the
@@ -238,16 +263,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr int CH = Cfg::CHUNK, LD = Cfg::CHUNK_LD;
       constexpr int STEP = CH * NSHARE;                  // column distance between consecutive chunks of this warp
       constexpr int NCHUNK = (BN + STEP - 1) / STEP;
-      // ReLU-mask words of this thread's row (K_PLAIN backward GEMMs): fetched BEFORE waiting for the accumulator so
-      // that their latency hides behind the MMAs of this tile.
-      uint32_t mb[NCHUNK];
-      if (KIND == K_PLAIN && !FOUR) {
-#pragma unroll
-        for (int k = 0; k < NCHUNK; ++k) {
-          const int c0 = CH * (half + k * NSHARE);
-          mb[k] = (p.bits_in && c0 < BN && n0 + c0 < p.N && grow < p.M) ? __ldg(p.bits_in + (size_t)grow * p.ld_bits + ((n0 + c0) >> 5)) : 0u;
-        }
-      }
+      // ReLU-mask word of this thread's row for its first chunk (K_PLAIN backward GEMMs): fetched BEFORE waiting for
+      // the accumulator, the following ones one chunk ahead, so that their latency hides behind other work.
+      auto mask_word = [&](int k) -> uint32_t {
+        const int c0 = CH * (half + k * NSHARE);
+        return (c0 < BN && n0 + c0 < p.N && grow < p.M) ? __ldg(p.bits_in + (size_t)grow * p.ld_bits + ((n0 + c0) >> 5)) : 0u;
+      };
+      uint32_t mw_next = 0u;
+      if (KIND == K_PLAIN && !FOUR && p.bits_in) mw_next = mask_word(0);
       ptx::mbar_wait(tfull_bar + buf, (tl >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
@@ -308,7 +331,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                    has_out2 = p.out2 != nullptr, has_lo = p.out_lo != nullptr, has_stat = p.colstat != nullptr,
                    has_bits_in = p.bits_in != nullptr, has_bits_out = p.bits_out != nullptr;
         const int cq = 4 * (lane % LPR), r_in = lane / LPR;
-#pragma unroll(FOUR ? 1 : NCHUNK)
+#pragma unroll 1
         for (int k = 0; k < NCHUNK; ++k) {
           const int c0 = CH * (half + k * NSHARE);
           if (c0 >= BN || n0 + c0 >= p.N) break;
@@ -316,20 +339,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float v[CH];
           ptx::tmem_ld_x16_nowait(taddr + c0, v);
           if (CH == 32) ptx::tmem_ld_x16_nowait(taddr + c0 + 16, v + (CH == 32 ? 16 : 0));
+          uint32_t mw = mw_next;
+          if (KIND == K_PLAIN && !FOUR && has_bits_in && k + 1 < NCHUNK) mw_next = mask_word(k + 1);
           ptx::tmem_ld_wait();
           if (KIND == K_PLAIN) {
+            if (has_bias || alpha != 1.f || p.relu) {
 #pragma unroll
-            for (int j = 0; j < CH; j += 4) {
-              const int colj = n0 + c0 + j;
-              float4 b4 = f4_zero();
-              if (has_bias && colj < p.N) b4 = ldg_f4(p.bias + colj);     // warp-uniform address
-              v[j] = fmaxf(fmaf(v[j], alpha, b4.x), floor_v); v[j + 1] = fmaxf(fmaf(v[j + 1], alpha, b4.y), floor_v);
-              v[j + 2] = fmaxf(fmaf(v[j + 2], alpha, b4.z), floor_v); v[j + 3] = fmaxf(fmaf(v[j + 3], alpha, b4.w), floor_v);
+              for (int j = 0; j < CH; j += 4) {
+                const int colj = n0 + c0 + j;
+                float4 b4 = f4_zero();
+                if (has_bias && colj < p.N) b4 = ldg_f4(p.bias + colj);     // warp-uniform address
+                v[j] = fmaxf(fmaf(v[j], alpha, b4.x), floor_v); v[j + 1] = fmaxf(fmaf(v[j + 1], alpha, b4.y), floor_v);
+                v[j + 2] = fmaxf(fmaf(v[j + 2], alpha, b4.z), floor_v); v[j + 3] = fmaxf(fmaf(v[j + 3], alpha, b4.w), floor_v);
+              }
             }
             if (!FOUR && has_bits_in) {
-              const uint32_t w = mb[k];
 #pragma unroll
-              for (int j = 0; j < CH; ++j) if (!((w >> j) & 1u)) v[j] = 0.f;
+              for (int j = 0; j < CH; ++j) v[j] = ((mw >> j) & 1u) ? v[j] : 0.f;
             }
             if (has_bits_out) {
               uint32_t ob = 0;
@@ -346,26 +372,42 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < CH; j += 4) st_f4(stg + lane * LD + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
           __syncwarp();
           const int col = n0 + c0 + cq;
-          const bool col_ok = col < p.N;
+          if (KIND == K_PLAIN && rows_w == 32 && n0 + c0 + CH <= p.N) {
+            // full chunk: straight-line copy-out (predicated stores only)
+            const size_t gr0 = (size_t)(m0 + q * 32 + r_in);
+            float* po = p.out + gr0 * p.ldo + col;
+            float* po2 = p.out2 + gr0 * p.ldo2 + col;
+            float* pl = p.out_lo + gr0 * p.ldo_lo + col;
 #pragma unroll
-          for (int pass = 0; pass < 32 / RPP; ++pass) {
-            const int r = pass * RPP + r_in;
-            if (r < rows_w && col_ok) {
-              const int gr = m0 + q * 32 + r;
-              float4 x = *reinterpret_cast<const float4*>(stg + r * LD + cq);
-              if (KIND != K_PLAIN) {
-                x = epilogue_apply(x, p, gr, col);
-                if (has_stat) st_f4(stg + r * LD + cq, x);
-              }
+            for (int pass = 0; pass < 32 / RPP; ++pass) {
+              const float4 x = *reinterpret_cast<const float4*>(stg + (pass * RPP + r_in) * LD + cq);
               const float4 xr = f4_tf32(x);
-              if (has_out) st_f4(p.out + (size_t)gr * p.ldo + col, do_round ? xr : x);
-              if (has_out2) st_f4(p.out2 + (size_t)gr * p.ldo2 + col, xr);
-              if (has_lo) st_f4(p.out_lo + (size_t)gr * p.ldo_lo + col, f4_tf32_residual(x));
+              if (has_out) st_f4(po + (size_t)pass * RPP * p.ldo, do_round ? xr : x);
+              if (has_out2) st_f4(po2 + (size_t)pass * RPP * p.ldo2, xr);
+              if (has_lo) st_f4(pl + (size_t)pass * RPP * p.ldo_lo, f4_tf32_residual(x));
+            }
+          } else {
+            const bool col_ok = col < p.N;
+#pragma unroll 1
+            for (int pass = 0; pass < 32 / RPP; ++pass) {
+              const int r = pass * RPP + r_in;
+              if (r < rows_w && col_ok) {
+                const int gr = m0 + q * 32 + r;
+                float4 x = *reinterpret_cast<const float4*>(stg + r * LD + cq);
+                if (KIND != K_PLAIN) {
+                  x = epilogue_apply(x, p, gr, col);
+                  if (has_stat) st_f4(stg + r * LD + cq, x);
+                }
+                const float4 xr = f4_tf32(x);
+                if (has_out) st_f4(p.out + (size_t)gr * p.ldo + col, do_round ? xr : x);
+                if (has_out2) st_f4(p.out2 + (size_t)gr * p.ldo2 + col, xr);
+                if (has_lo) st_f4(p.out_lo + (size_t)gr * p.ldo_lo + col, f4_tf32_residual(x));
+              }
             }
           }
           if (has_stat) {
             __syncwarp();
-            colstat_group(stg, LD, CH, rows_w, n0 + c0, group, p, lane, 32);
+            colstat_warp<CH>(stg, LD, rows_w, n0 + c0, group, p, lane);
           }
           __syncwarp();
         }

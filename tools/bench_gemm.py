@@ -8,7 +8,7 @@ dev = "cuda:0"
 M = int(os.environ.get("M", 102400))
 
 
-def timeit(fn, iters=10):
+def timeit(fn, iters=int(os.environ.get('ITERS', 10))):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -21,7 +21,12 @@ def timeit(fn, iters=10):
     return a.elapsed_time(b) / iters * 1e3   # us
 
 
+ONLY = os.environ.get("CASE")
+
+
 def case(name, M, N, K, comp=False, b_mn=False, relu=False, pad_k=0, dw=False, masked=False, stat=0):
+    if ONLY and not name.startswith(ONLY):
+        return
     g = torch.Generator().manual_seed(0)
     if masked or stat:
         A = ops.round_tf32(torch.randn(M, K, generator=g).to(dev))

@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+TAG=${1:-x}
+for c in "dU masked " "fwd1 x3" "dW   [M,300]"; do
+  n=$(echo "$c" | tr -d ' [],' )
+  CASE="$c" ITERS=2 python tools/bench_gemm.py > gpurun_out/pp_$n.log 2>&1 &&
+  CASE="$c" ITERS=2 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32 -s 3 -c 1 -f -o gpurun_out/g_${n}_$TAG python tools/bench_gemm.py > gpurun_out/ncu_$n.log 2>&1
+  echo "$c rc=$?"
+done
