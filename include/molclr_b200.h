@@ -85,8 +85,28 @@ int molclr_gine_aggregate_fwd(const float* src, const float* bn_coef, int relu, 
  * (host) receives the number of partial rows written. */
 int molclr_rowwise_max_blocks(void);
 int molclr_gine_aggregate_bwd(const float* ga, const int32_t* rowptr_t, const int32_t* col_t, const float* z_prev,
-                              const float* bn_coef, int relu, int64_t N, int D, float* gy, float* partials,
+                              const float* bn_coef, int relu, int64_t N, int D, float* gy, int round_tf32_out, float* partials,
                               int* num_partials, cudaStream_t stream);
+/* The ReLU-backward / BatchNorm-statistics stage alone (no neighbour gather): gy = g * [relu mask of z_prev], partials as
+ * above.  Used by the GCN backward, where the gradient of a layer input arrives from a GEMM (gcn_molclr.py:76). */
+int molclr_relu_bn_bwd_stats(const float* g, const float* z_prev, const float* bn_coef, int relu, int64_t N, int D, float* gy,
+                             float* partials, int* num_partials, cudaStream_t stream);
+
+/* ---- GCNConv aggregation: gcn_molclr.py:72-88 (scalar bond embeddings [5][1], [3][1] broadcast over the features; the
+ * degree normalisation of gcn_molclr.py:27-36,74 is computed and DISCARDED by the reference, so none is applied) ----
+ * out[i] = sum_{in-edges e, input order}( src[col[e]] + (b1[t_e] + b2[d_e]) ) + ( src[i] + (b1[4] + b2[0]) ) + bias
+ * (src = x @ weight; `out += bias` comes last, gcn_molclr.py:81-82).  bias may be NULL. */
+int molclr_gcn_aggregate_fwd(const float* src, const int32_t* rowptr, const int32_t* col, const uint8_t* eattr, const float* b1,
+                             const float* b2, const float* bias, int64_t N, int D, float* out, int64_t ld_out, cudaStream_t stream);
+/* out[r] = sum_c in[r][c]: collapses the [8][D] result of molclr_edge_table_grad to the GCN's [5][1] + [3][1] gradients */
+int molclr_row_sum(const float* in, int R, int C, float* out, cudaStream_t stream);
+/* x = [relu](z*scale + shift) (bn_coef NULL: x = z) materialised as a tensor-core operand: hi = tf32(x), lo (optional) =
+ * tf32(x - hi); rows `ld` floats apart.  The GCN's GEMM input (gcn_molclr.py:146-152 then :76). */
+int molclr_bn_apply_fwd(const float* z, const float* bn_coef, int relu, int64_t N, int D, float* hi, float* lo, int64_t ld,
+                        cudaStream_t stream);
+/* tile_stats [T][2][D]: column mean and M2 of every 32-row group of z (T = molclr_gemm_colstat_tiles(N)): what the GEMM
+ * epilogue emits for the GIN path, for outputs that do not come from a GEMM. */
+int molclr_bn_tile_stats(const float* z, int64_t N, int D, int T, float* tile_stats, cudaStream_t stream);
 /* Gradients of edge_embedding1/2 (embedding_dense_backward over E' rows in the reference):
  * dB [8][D]: rows 0..4 = d edge_embedding1, rows 5..7 = d edge_embedding2.  partials: [max_blocks][8][D]. */
 int molclr_edge_table_grad(const float* ga, const uint16_t* cnt, int64_t N, int D, float* dB, float* partials,
@@ -110,11 +130,11 @@ int molclr_bn_eval_coef(const float* gamma, const float* beta, const float* runn
  * gz = k1*gy + A + B*z. */
 int molclr_bn_bwd_finalize(const float* partials, int P, int64_t N, int D, const float* gamma, const float* coef,
                            int use_batch_stats, float* dgamma, float* dbeta, float* bcoef, cudaStream_t stream);
-/* gz (tf32-rounded) = k1*gy + A + B*z.  gy from memory, or (gp != NULL) gy[n] = gp[node2graph[n]] * w_graph
+/* gz (tf32-rounded if round_tf32_out: it then feeds a GEMM) = k1*gy + A + B*z.  gy from memory, or (gp != NULL) gy[n] = gp[node2graph[n]] * w_graph
  * (backward of global_mean/add_pool).  dbias (optional) = column sums of gz.  partials [max_blocks][D]. */
 int molclr_bn_bwd_apply(const float* gy, const float* gp, const int32_t* node2graph, const int32_t* gptr, int pool_mean,
-                        const float* z, const float* bcoef, int64_t N, int D, float* gz, int64_t ld_gz, float* dbias,
-                        float* partials, cudaStream_t stream);
+                        const float* z, const float* bcoef, int64_t N, int D, float* gz, int64_t ld_gz, int round_tf32_out,
+                        float* dbias, float* partials, cudaStream_t stream);
 
 /* ---- global_mean_pool / global_add_pool: ginet_molclr.py:83-88,113 (pool_mode 0 = mean, 1 = add) ----
  * out[g] = w_g * sum_{n in graph g, node order} [relu](z[n]*scale + shift) */

@@ -5,6 +5,7 @@ hand-written sm_100a CUDA kernels behind the C ABI in ``include/molclr_b200.h``.
 """
 from .batch import Batch  # noqa: F401
 from .ginet import GINet, GINEConv  # noqa: F401
+from .gcn import GCN, GCNConv  # noqa: F401
 from .nt_xent import NTXentLoss  # noqa: F401
 from .graph import GraphPlan, get_plan  # noqa: F401
 from .functional import normalize, pretrain_loss  # noqa: F401

@@ -47,14 +47,19 @@ SIGNATURES = {
     "molclr_embed_nodes_bwd": (i32, [vp, vp, i64, i32, vp, vp, vp]),
     "molclr_gine_aggregate_fwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, i64, i32, vp, i64, i32, vp, vp]),
     "molclr_rowwise_max_blocks": (i32, []),
-    "molclr_gine_aggregate_bwd": (i32, [vp, vp, vp, vp, vp, i32, i64, i32, vp, vp, C.POINTER(i32), vp]),
+    "molclr_gine_aggregate_bwd": (i32, [vp, vp, vp, vp, vp, i32, i64, i32, vp, i32, vp, C.POINTER(i32), vp]),
+    "molclr_relu_bn_bwd_stats": (i32, [vp, vp, vp, i32, i64, i32, vp, vp, C.POINTER(i32), vp]),
+    "molclr_gcn_aggregate_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, i64, vp]),
+    "molclr_row_sum": (i32, [vp, i32, i32, vp, vp]),
+    "molclr_bn_apply_fwd": (i32, [vp, vp, i32, i64, i32, vp, vp, i64, vp]),
+    "molclr_bn_tile_stats": (i32, [vp, i64, i32, i32, vp, vp]),
     "molclr_edge_table_grad": (i32, [vp, vp, i64, i32, vp, vp, vp]),
     "molclr_reduce_partials": (i32, [vp, i32, i32, f32, i32, vp, vp]),
     "molclr_bn_finalize_workspace_bytes": (sz, [i32]),
     "molclr_bn_fwd_finalize": (i32, [vp, i32, i32, i64, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp]),
     "molclr_bn_eval_coef": (i32, [vp, vp, vp, vp, f32, i32, vp, vp]),
     "molclr_bn_bwd_finalize": (i32, [vp, i32, i64, i32, vp, vp, i32, vp, vp, vp, vp]),
-    "molclr_bn_bwd_apply": (i32, [vp, vp, vp, vp, i32, vp, vp, i64, i32, vp, i64, vp, vp, vp]),
+    "molclr_bn_bwd_apply": (i32, [vp, vp, vp, vp, i32, vp, vp, i64, i32, vp, i64, i32, vp, vp, vp]),
     "molclr_pool_fwd": (i32, [vp, vp, i32, vp, vp, i32, i64, i32, vp, i64, i32, vp, vp]),
     "molclr_pool_bwd_stats": (i32, [vp, vp, vp, i32, vp, vp, i64, i32, vp, C.POINTER(i32), vp]),
     "molclr_gemm_colstat_tiles": (i32, [i64]),

@@ -23,7 +23,9 @@
 namespace molclr {
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_BK = 32;          // 32 tf32 = one 128-byte swizzle row
+constexpr int GEMM_BK = 32;          // single-pass K block: 32 tf32 = one 128-byte swizzle row
+constexpr int GEMM_BK4 = 32;         // compensated (4-tile) K block.  16 (64-byte swizzle rows, 5 stages, 8 epilogue warps) also works
+                                     // but measured 20% slower: the 64-byte TMA boxes double the L2 request count of an L2-bound loop
 constexpr int GEMM_MAX_THREADS = 320; // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..: epilogue (4 or 8)
 constexpr int GEMM_TMEM_COLS = 512;  // two accumulator buffers of up to 256 columns
 constexpr int GEMM_STAT_ROWS = 32;   // column statistics are emitted per 32-row group (one epilogue warp)
@@ -33,15 +35,18 @@ constexpr int GEMM_SMEM_LIMIT = 232448;
 // MMAs per K-slice; otherwise one (A, B) pair per stage.
 template <int BN, bool FOUR>
 struct GemmCfg {
-  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 4;
-  static constexpr int B_BYTES = BN * GEMM_BK * 4;
+  static constexpr int BK = FOUR ? GEMM_BK4 : GEMM_BK;
+  static constexpr int A_BYTES = GEMM_BM * BK * 4;
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int MN_BLOCK_BYTES = 32 * BK * 4;      // one [BK k][32 mn] block of an MN-major operand
   static constexpr int STAGE_BYTES = (FOUR ? 2 : 1) * (A_BYTES + B_BYTES);
-  // epilogue column chunk staged per warp, and its pitch in floats (conflict-free float4 rows); the 4-tile stages
-  // leave room for a 16-column chunk only
-  static constexpr int CHUNK = FOUR ? 16 : 32;
+  // epilogue column chunk staged per warp, and its pitch in floats (conflict-free float4 rows); the 72 KB stages of
+  // the compensated product leave room for four warps with 16-column chunks only
+  static constexpr bool SMALL_EPI = FOUR && BK == 32;
+  static constexpr int CHUNK = SMALL_EPI ? 16 : 32;
   static constexpr int CHUNK_LD = CHUNK + 4;
   // epilogue warps: two per TMEM lane quadrant (splitting the column chunks) where shared memory allows
-  static constexpr int EPI_WARPS = FOUR ? 4 : 8;
+  static constexpr int EPI_WARPS = SMALL_EPI ? 4 : 8;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int STAGING_BYTES = EPI_WARPS * 32 * CHUNK_LD * 4;     // per epilogue warp: 32 rows x chunk
   static constexpr int BAR_BYTES = 256;
@@ -188,7 +193,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
           uint8_t* b_dst = a_dst + (FOUR ? 2 : 1) * Cfg::A_BYTES;
           const int seg = FOUR ? 0 : i / nkb_seg;
-          const int kc = (kb0 + (i - seg * nkb_seg)) * GEMM_BK;
+          const int kc = (kb0 + (i - seg * nkb_seg)) * Cfg::BK;
 #pragma unroll
           for (int h = 0; h < (FOUR ? 2 : 1); ++h) {
             const CUtensorMap* ma = (FOUR ? h == 1 : seg == 1) ? &tmA2 : &tmA;
@@ -197,10 +202,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint8_t* bd = b_dst + h * Cfg::B_BYTES;
             if (!p.a_mn) ptx::tma_load_2d(ad, ma, full_bar + s, kc, m0);
             else
-              for (int j = 0; j < GEMM_BM / 32; ++j) ptx::tma_load_2d(ad + j * 4096, ma, full_bar + s, m0 + 32 * j, kc);
+              for (int j = 0; j < GEMM_BM / 32; ++j) ptx::tma_load_2d(ad + j * Cfg::MN_BLOCK_BYTES, ma, full_bar + s, m0 + 32 * j, kc);
             if (!p.b_mn) ptx::tma_load_2d(bd, mb, full_bar + s, kc, n0);
             else
-              for (int j = 0; j < BN / 32; ++j) ptx::tma_load_2d(bd + j * 4096, mb, full_bar + s, n0 + 32 * j, kc);
+              for (int j = 0; j < BN / 32; ++j) ptx::tma_load_2d(bd + j * Cfg::MN_BLOCK_BYTES, mb, full_bar + s, n0 + 32 * j, kc);
           }
         }
       }
@@ -210,9 +215,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = ptx::make_idesc_tf32(BN, p.a_mn != 0, p.b_mn != 0);
-      const uint32_t a_lbo = p.a_mn ? 4096u : 16u, b_lbo = p.b_mn ? 4096u : 16u;
-      const uint32_t a_sbo = p.a_mn ? 512u : 1024u, b_sbo = p.b_mn ? 512u : 1024u;
-      const uint32_t a_lay = p.a_mn ? ptx::kLayoutSw128Base32 : ptx::kLayoutSw128, b_lay = p.b_mn ? ptx::kLayoutSw128Base32 : ptx::kLayoutSw128;
+      // K-major tiles: rows of BK*4 bytes (128B or 64B swizzle), 8-row groups SBO apart.  MN-major: [BK k][32 mn] blocks
+      // LBO apart, 4-k-row groups 512 B apart.
+      constexpr uint32_t kmaj_sbo = 8u * Cfg::BK * 4u, kmaj_lay = Cfg::BK == 16 ? ptx::kLayoutSw64 : ptx::kLayoutSw128;
+      const uint32_t a_lbo = p.a_mn ? (uint32_t)Cfg::MN_BLOCK_BYTES : 16u, b_lbo = p.b_mn ? (uint32_t)Cfg::MN_BLOCK_BYTES : 16u;
+      const uint32_t a_sbo = p.a_mn ? 512u : kmaj_sbo, b_sbo = p.b_mn ? 512u : kmaj_sbo;
+      const uint32_t a_lay = p.a_mn ? ptx::kLayoutSw128Base32 : kmaj_lay, b_lay = p.b_mn ? ptx::kLayoutSw128Base32 : kmaj_lay;
       const uint32_t a_kstep = p.a_mn ? 1024u : 32u, b_kstep = p.b_mn ? 1024u : 32u;   // bytes per K=8 slice
       uint32_t it = 0, tl = 0;                          // tl = local tile counter -> accumulator buffer / phase
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
@@ -230,7 +238,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t a_base = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES);
           const uint32_t b_base = a_base + (FOUR ? 2 : 1) * Cfg::A_BYTES;
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 8; ++k) {
+          for (int k = 0; k < Cfg::BK / 8; ++k) {
             const uint64_t ad = ptx::make_smem_desc(a_base + k * a_kstep, a_lbo, a_sbo, a_lay);
             const uint64_t bd = ptx::make_smem_desc(b_base + k * b_kstep, b_lbo, b_sbo, b_lay);
             ptx::mma_tf32_ss(d_tmem, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
@@ -515,7 +523,7 @@ static EncodeTiledFn encode_tiled_fn() {
 
 // Tensor map over a row-major fp32 matrix [outer][inner] with leading dimension ld (elements),
 // box = [box_outer][32 inner elements], 128-byte swizzle, zero fill out of bounds.
-static int make_tmap(CUtensorMap* m, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_outer, bool mn_major) {
+static int make_tmap(CUtensorMap* m, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_outer, bool mn_major, int bk) {
   // cuTensorMapEncodeTiled is a driver-API call: make sure this thread (e.g. the autograd engine's) has the
   // primary context bound before the first one.
   static thread_local bool ctx_bound = false;
@@ -526,10 +534,12 @@ static int make_tmap(CUtensorMap* m, const float* base, int64_t inner, int64_t o
   MOLCLR_REQUIRE(ld % 4 == 0, "gemm: leading dimension %lld must be a multiple of 4 floats (TMA 16-byte stride)", (long long)ld);
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
+  // K-major: box = [box_outer rows][bk k];  MN-major: box = [bk k rows][32 mn]
+  cuuint32_t box[2] = {mn_major ? 32u : (cuuint32_t)bk, (cuuint32_t)(mn_major ? bk : box_outer)};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : (bk == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MOLCLR_REQUIRE(r == CUDA_SUCCESS, "gemm: cuTensorMapEncodeTiled failed with CUresult %d (inner=%lld outer=%lld ld=%lld)", (int)r,
@@ -544,15 +554,15 @@ static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, i
   CUtensorMap tmA, tmB, tmA2, tmB2;
   int rc;
   // K-major operand [rows][K]: inner = K, outer = rows, box = rows-per-tile x 32.  MN-major [K][rows]: inner = rows, outer = K, box 32 x 32.
-  rc = p.a_mn ? make_tmap(&tmA, j.A, p.M, p.K, j.lda, 32, true) : make_tmap(&tmA, j.A, p.K, p.M, j.lda, GEMM_BM, false);
+  rc = p.a_mn ? make_tmap(&tmA, j.A, p.M, p.K, j.lda, 32, true, Cfg::BK) : make_tmap(&tmA, j.A, p.K, p.M, j.lda, GEMM_BM, false, Cfg::BK);
   if (rc) return rc;
-  rc = p.b_mn ? make_tmap(&tmB, j.B, p.N, p.K, j.ldb, 32, true) : make_tmap(&tmB, j.B, p.K, p.N, j.ldb, BN, false);
+  rc = p.b_mn ? make_tmap(&tmB, j.B, p.N, p.K, j.ldb, 32, true, Cfg::BK) : make_tmap(&tmB, j.B, p.K, p.N, j.ldb, BN, false, Cfg::BK);
   if (rc) return rc;
   tmA2 = tmA; tmB2 = tmB;
   if (p.segments > 1) {
-    rc = p.a_mn ? make_tmap(&tmA2, j.A_lo, p.M, p.K, j.lda, 32, true) : make_tmap(&tmA2, j.A_lo, p.K, p.M, j.lda, GEMM_BM, false);
+    rc = p.a_mn ? make_tmap(&tmA2, j.A_lo, p.M, p.K, j.lda, 32, true, Cfg::BK) : make_tmap(&tmA2, j.A_lo, p.K, p.M, j.lda, GEMM_BM, false, Cfg::BK);
     if (rc) return rc;
-    rc = p.b_mn ? make_tmap(&tmB2, j.B_lo, p.N, p.K, j.ldb, 32, true) : make_tmap(&tmB2, j.B_lo, p.K, p.N, j.ldb, BN, false);
+    rc = p.b_mn ? make_tmap(&tmB2, j.B_lo, p.N, p.K, j.ldb, 32, true, Cfg::BK) : make_tmap(&tmB2, j.B_lo, p.K, p.N, j.ldb, BN, false, Cfg::BK);
     if (rc) return rc;
   }
   static bool attr_set = false;
@@ -610,7 +620,8 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
     MOLCLR_REQUIRE((!p.out || p.ldo % 4 == 0) && (!p.out2 || p.ldo2 % 4 == 0), "gemm: output leading dimensions must be multiples of 4");
     MOLCLR_REQUIRE((!p.addend || p.ldadd % 4 == 0) && (!p.mask || p.ldmask % 4 == 0), "gemm: addend/mask leading dimensions must be multiples of 4");
   }
-  p.num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int bk = p.segments > 1 ? GEMM_BK4 : GEMM_BK;
+  p.num_kb = (p.K + bk - 1) / bk;
   int splits = job.split_k > 1 ? job.split_k : 1;
   if (splits > p.num_kb) splits = p.num_kb;
   p.kb_per_split = (p.num_kb + splits - 1) / splits;

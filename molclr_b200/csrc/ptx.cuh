@@ -108,7 +108,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //  K-major  tile [rows][32 k], SWIZZLE_128B (layout 2): 8-row groups 1024 B apart (SBO); LBO unused.
 //  MN-major tile [32 k][32 mn] blocks, SWIZZLE_128B_BASE32B (layout 1) -- the only swizzle the tensor core accepts
 //  for MN-major 32-bit operands: blocks along MN `lbo_bytes` apart (LBO), 4-k-row groups 512 B apart (SBO).
-constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1, kLayoutSw64 = 4;
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);

@@ -91,23 +91,32 @@ __global__ void __launch_bounds__(512) embed_nodes_bwd_kernel(
 // per-feature (scale, shift) so the normalised activations never round-trip through HBM.
 // Both bond tables are folded into one 15-row table staged in shared memory.
 // ------------------------------------------------------------------------------------------------
-template <int NCH, bool HAS_BN>
+// SCALAR (GCNConv, gcn_molclr.py:72-88): the bond tables are [5][1] / [3][1] scalars broadcast over the D features and a
+// bias row is added after the sum (`out += bias`, gcn_molclr.py:81-82); the staged table then holds splatted scalars.
+template <int NCH, bool HAS_BN, bool SCALAR>
 __global__ void __launch_bounds__(kRowThreads) gine_aggregate_fwd_kernel(
     const float* __restrict__ src, const float* __restrict__ coef, int relu,
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const uint8_t* __restrict__ eattr,
-    const float* __restrict__ B1, const float* __restrict__ B2, int N, int D, float* __restrict__ out,
-    long long ld_out, int round_out, float* __restrict__ out_lo) {
+    const float* __restrict__ B1, const float* __restrict__ B2, const float* __restrict__ bias, int N, int D,
+    float* __restrict__ out, long long ld_out, int round_out, float* __restrict__ out_lo) {
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* ee = sm4;                       // [15][D4]
-  float4* sc = ee + kNumEdgeClass * D4;   // [D4] scale
+  float4* sc = ee + kNumEdgeClass * D4;   // [D4] scale  (SCALAR: the bias row)
   float4* sh = sc + D4;                   // [D4] shift
   for (int i = threadIdx.x; i < kNumEdgeClass * D4; i += blockDim.x) {
     const int cls = i / D4, q = i - cls * D4;
-    ee[i] = f4_add(ldg_f4(B1 + (size_t)(cls / 3) * D + 4 * q), ldg_f4(B2 + (size_t)(cls % 3) * D + 4 * q));
+    if (SCALAR) {
+      const float sv = __ldg(B1 + cls / 3) + __ldg(B2 + cls % 3);
+      ee[i] = make_float4(sv, sv, sv, sv);
+    } else {
+      ee[i] = f4_add(ldg_f4(B1 + (size_t)(cls / 3) * D + 4 * q), ldg_f4(B2 + (size_t)(cls % 3) * D + 4 * q));
+    }
   }
   if (HAS_BN)
     for (int i = threadIdx.x; i < D4; i += blockDim.x) { sc[i] = ldg_f4(coef + 4 * i); sh[i] = ldg_f4(coef + D + 4 * i); }
+  if (SCALAR)
+    for (int i = threadIdx.x; i < D4; i += blockDim.x) sc[i] = bias ? ldg_f4(bias + 4 * i) : f4_zero();
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -154,6 +163,7 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_fwd_kernel(
       const int q = lane + 32 * j;
       if (q < D4) {
         float4 r = f4_add(acc[j], f4_add(act(self[j], q), ee[kSelfLoopAttr * D4 + q]));   // self loop LAST
+        if (SCALAR) r = f4_add(r, sc[q]);                                                  // then the bias row
         if (out_lo) st_f4(out_lo + (size_t)i * ld_out + 4 * q, f4_tf32_residual(r));
         if (round_out) r = f4_tf32(r);
         st_f4(out + (size_t)i * ld_out + 4 * q, r);
@@ -191,11 +201,13 @@ __device__ __forceinline__ void block_reduce_rows(float4 (&acc)[NV][NCH], float4
 //   g_y[j] = g_h[j] * [z[j]*scale + shift > 0];  s1 += g_y;  s2 += g_y * xhat,  xhat = (z - mean) * invstd
 // MODE 0: plain (layer 0: g_h feeds the node-embedding backward).  MODE 1: fused as above.
 // ------------------------------------------------------------------------------------------------
-template <int NCH, int MODE>
+// GATHER = false: no neighbour terms (g_h = g_a): the ReLU / BatchNorm-statistics stage alone, used by the GCN backward
+// where the gradient arrives from a GEMM instead of an aggregation.
+template <int NCH, int MODE, bool GATHER>
 __global__ void __launch_bounds__(kRowThreads) gine_aggregate_bwd_kernel(
     const float* __restrict__ ga, const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ col_t,
     const float* __restrict__ z, const float* __restrict__ coef, int relu, int N, int D,
-    float* __restrict__ gy, float* __restrict__ partials) {
+    float* __restrict__ gy, float* __restrict__ partials, int round_out) {
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* cf = sm4;                          // [4][D4] scale, shift, mean, invstd
@@ -210,7 +222,7 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_bwd_kernel(
 #pragma unroll
   for (int j = 0; j < NCH; ++j) { st[0][j] = f4_zero(); st[1][j] = f4_zero(); }
   for (int i = warp; i < N; i += nwarps) {
-    const int beg = __ldg(rowptr_t + i), end = __ldg(rowptr_t + i + 1);
+    const int beg = GATHER ? __ldg(rowptr_t + i) : 0, end = GATHER ? __ldg(rowptr_t + i + 1) : 0;
     float4 acc[NCH], zz[NCH];
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
@@ -250,7 +262,7 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_bwd_kernel(
           st[1][j].z = fmaf(r.z, (zv.z - m.z) * is.z, st[1][j].z);
           st[1][j].w = fmaf(r.w, (zv.w - m.w) * is.w, st[1][j].w);
         }
-        st_f4(gy + (size_t)i * D + 4 * q, r);
+        st_f4(gy + (size_t)i * D + 4 * q, round_out ? f4_tf32(r) : r);
       }
     }
   }
@@ -443,7 +455,7 @@ template <int NCH, int SRC>
 __global__ void __launch_bounds__(kRowThreads) bn_bwd_apply_kernel(
     const float* __restrict__ gy, const float* __restrict__ gp, const int32_t* __restrict__ node2graph,
     const int32_t* __restrict__ gptr, int pool_mean, const float* __restrict__ z, const float* __restrict__ bcoef,
-    int N, int D, float* __restrict__ gz, long long ld_gz, float* __restrict__ partials) {
+    int N, int D, float* __restrict__ gz, long long ld_gz, float* __restrict__ partials, int round_out) {
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* cf = sm4;                 // [3][D4]
@@ -477,8 +489,7 @@ __global__ void __launch_bounds__(kRowThreads) bn_bwd_apply_kernel(
         r.x = fmaf(k1.x, g.x, fmaf(B.x, zv.x, A.x)); r.y = fmaf(k1.y, g.y, fmaf(B.y, zv.y, A.y));
         r.z = fmaf(k1.z, g.z, fmaf(B.z, zv.z, A.z)); r.w = fmaf(k1.w, g.w, fmaf(B.w, zv.w, A.w));
         st[0][j] = f4_add(st[0][j], r);
-        r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w);
-        st_f4(gz + (size_t)i * ld_gz + 4 * q, r);
+        st_f4(gz + (size_t)i * ld_gz + 4 * q, round_out ? f4_tf32(r) : r);
       }
     }
   }
@@ -570,6 +581,95 @@ __global__ void __launch_bounds__(kRowThreads) pool_bwd_stats_kernel(
     }
   }
   block_reduce_rows<NCH, 2>(st, red, D4, partials);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GCN path helpers (gcn_molclr.py:62-84: the GEMM comes BEFORE the aggregation, so its A operand -- the previous
+// layer's BatchNorm + ReLU output, gcn_molclr.py:146-152 -- has to exist in memory, and the BatchNorm statistics of
+// the aggregated output cannot come from a GEMM epilogue).
+// ------------------------------------------------------------------------------------------------
+// x = [relu](z*scale + shift) (coef == NULL: x = z), written as a tensor-core operand: hi = tf32(x), lo = tf32(x - hi).
+template <int NCH>
+__global__ void __launch_bounds__(kRowThreads) bn_apply_fwd_kernel(
+    const float* __restrict__ z, const float* __restrict__ coef, int relu, int N, int D, float* __restrict__ hi,
+    float* __restrict__ lo, long long ld) {
+  extern __shared__ float4 sm4[];
+  const int D4 = D >> 2;
+  float4* sc = sm4; float4* sh = sm4 + D4;
+  if (coef) {
+    for (int i = threadIdx.x; i < D4; i += blockDim.x) { sc[i] = ldg_f4(coef + 4 * i); sh[i] = ldg_f4(coef + D + 4 * i); }
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * kRowWarps + (threadIdx.x >> 5), nwarps = gridDim.x * kRowWarps;
+  for (int i = warp; i < N; i += nwarps) {
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int q = lane + 32 * j;
+      if (q < D4) {
+        float4 v = ld_stream_f4(z + (size_t)i * D + 4 * q);
+        if (coef) {
+          const float4 s = sc[q], b = sh[q];
+          v.x = fmaf(v.x, s.x, b.x); v.y = fmaf(v.y, s.y, b.y); v.z = fmaf(v.z, s.z, b.z); v.w = fmaf(v.w, s.w, b.w);
+          if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        }
+        st_f4(hi + (size_t)i * ld + 4 * q, f4_tf32(v));
+        if (lo) st_f4(lo + (size_t)i * ld + 4 * q, f4_tf32_residual(v));
+      }
+    }
+  }
+}
+
+// Column (mean, M2) of every 32-row group of z: the same [T][2][D] tile statistics the GEMM epilogue emits, so that
+// molclr_bn_fwd_finalize serves both encoders.  One warp per group; the second pass re-reads the group from L1/L2.
+template <int NCH>
+__global__ void __launch_bounds__(kRowThreads) bn_tile_stats_kernel(const float* __restrict__ z, int N, int D, int T,
+                                                                    float* __restrict__ tile_stats) {
+  const int D4 = D >> 2, lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * kRowWarps + (threadIdx.x >> 5), nwarps = gridDim.x * kRowWarps;
+  for (int t = warp; t < T; t += nwarps) {
+    const int r0 = t * 32, rows = max(0, min(32, N - r0));
+    float4 sum[NCH], m2[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) { sum[j] = f4_zero(); m2[j] = f4_zero(); }
+    for (int r = 0; r < rows; ++r)
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const int q = lane + 32 * j;
+        if (q < D4) sum[j] = f4_add(sum[j], ldg_f4(z + (size_t)(r0 + r) * D + 4 * q));
+      }
+    const float inv = rows > 0 ? 1.f / (float)rows : 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) { sum[j].x *= inv; sum[j].y *= inv; sum[j].z *= inv; sum[j].w *= inv; }
+    for (int r = 0; r < rows; ++r)
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const int q = lane + 32 * j;
+        if (q < D4) {
+          const float4 v = ldg_f4(z + (size_t)(r0 + r) * D + 4 * q);
+          const float dx = v.x - sum[j].x, dy = v.y - sum[j].y, dz = v.z - sum[j].z, dw = v.w - sum[j].w;
+          m2[j].x = fmaf(dx, dx, m2[j].x); m2[j].y = fmaf(dy, dy, m2[j].y); m2[j].z = fmaf(dz, dz, m2[j].z); m2[j].w = fmaf(dw, dw, m2[j].w);
+        }
+      }
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int q = lane + 32 * j;
+      if (q < D4) {
+        st_f4(tile_stats + ((size_t)t * 2) * D + 4 * q, sum[j]);
+        st_f4(tile_stats + ((size_t)t * 2 + 1) * D + 4 * q, m2[j]);
+      }
+    }
+  }
+}
+
+// out[r] = sum_c in[r][c] (one warp per row, fixed order): collapses the [8][D] bond-table gradient to the GCN's [8][1].
+__global__ void row_sum_kernel(const float* __restrict__ in, int R, int C, float* __restrict__ out) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= R) return;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += in[(size_t)r * C + c];
+  s = warp_sum(s);
+  if (lane == 0) out[r] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -674,36 +774,53 @@ extern "C" int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, in
   return molclr_reduce_partials(partials, blocks, rows * D, 1.f, 0, dE, stream);
 }
 
+static int aggregate_fwd_launch(const float* src, const float* bn_coef, int relu, const int32_t* rowptr, const int32_t* col,
+                                const uint8_t* eattr, const float* B1, const float* B2, const float* bias, bool scalar, int64_t N,
+                                int D, float* out, int64_t ld_out, int round_tf32_out, float* out_lo, cudaStream_t stream) {
+  REQUIRE_D(D);
+  MOLCLR_REQUIRE(ld_out >= D && ld_out % 4 == 0, "aggregate_fwd: ld_out must be >= D and a multiple of 4");
+  if (N == 0) return 0;
+  const size_t smem = (size_t)(kNumEdgeClass + 2) * D * sizeof(float);
+  NCH_DISPATCH(D / 4, {
+    if (scalar) {
+      auto k = gine_aggregate_fwd_kernel<NCH, false, true>;
+      k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
+          src, nullptr, 0, rowptr, col, eattr, B1, B2, bias, (int)N, D, out, ld_out, round_tf32_out, out_lo);
+    } else if (bn_coef) {
+      auto k = gine_aggregate_fwd_kernel<NCH, true, false>;
+      k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
+          src, bn_coef, relu, rowptr, col, eattr, B1, B2, nullptr, (int)N, D, out, ld_out, round_tf32_out, out_lo);
+    } else {
+      auto k = gine_aggregate_fwd_kernel<NCH, false, false>;
+      k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
+          src, nullptr, 0, rowptr, col, eattr, B1, B2, nullptr, (int)N, D, out, ld_out, round_tf32_out, out_lo);
+    }
+  });
+  MOLCLR_CHECK_LAUNCH("aggregate_fwd");
+  return 0;
+}
+
 extern "C" int molclr_gine_aggregate_fwd(const float* src, const float* bn_coef, int relu, const int32_t* rowptr,
                                          const int32_t* col, const uint8_t* eattr, const float* B1, const float* B2,
                                          int64_t N, int D, float* out, int64_t ld_out, int round_tf32_out, float* out_lo,
                                          cudaStream_t stream) {
-  REQUIRE_D(D);
-  MOLCLR_REQUIRE(ld_out >= D && ld_out % 4 == 0, "gine_aggregate_fwd: ld_out must be >= D and a multiple of 4");
-  if (N == 0) return 0;
-  const size_t smem = (size_t)(kNumEdgeClass + 2) * D * sizeof(float);
-  NCH_DISPATCH(D / 4, {
-    if (bn_coef) {
-      auto k = gine_aggregate_fwd_kernel<NCH, true>;
-      k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
-          src, bn_coef, relu, rowptr, col, eattr, B1, B2, (int)N, D, out, ld_out, round_tf32_out, out_lo);
-    } else {
-      auto k = gine_aggregate_fwd_kernel<NCH, false>;
-      k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
-          src, nullptr, 0, rowptr, col, eattr, B1, B2, (int)N, D, out, ld_out, round_tf32_out, out_lo);
-    }
-  });
-  MOLCLR_CHECK_LAUNCH("gine_aggregate_fwd");
-  return 0;
+  return aggregate_fwd_launch(src, bn_coef, relu, rowptr, col, eattr, B1, B2, nullptr, false, N, D, out, ld_out, round_tf32_out,
+                              out_lo, stream);
+}
+
+extern "C" int molclr_gcn_aggregate_fwd(const float* src, const int32_t* rowptr, const int32_t* col, const uint8_t* eattr,
+                                        const float* b1, const float* b2, const float* bias, int64_t N, int D, float* out,
+                                        int64_t ld_out, cudaStream_t stream) {
+  return aggregate_fwd_launch(src, nullptr, 0, rowptr, col, eattr, b1, b2, bias, true, N, D, out, ld_out, 0, nullptr, stream);
 }
 
 // Number of partial rows the persistent row-wise kernels with block partials emit (upper bound on
 // their grid): callers size `partials` as [molclr_rowwise_max_blocks()][NV][D].
 extern "C" int molclr_rowwise_max_blocks(void) { return 8 * sm_count(); }
 
-extern "C" int molclr_gine_aggregate_bwd(const float* ga, const int32_t* rowptr_t, const int32_t* col_t, const float* z_prev,
-                                         const float* bn_coef, int relu, int64_t N, int D, float* gy, float* partials,
-                                         int* num_partials, cudaStream_t stream) {
+static int aggregate_bwd_launch(const float* ga, const int32_t* rowptr_t, const int32_t* col_t, bool gather, const float* z_prev,
+                                const float* bn_coef, int relu, int64_t N, int D, float* gy, int round_out, float* partials,
+                                int* num_partials, cudaStream_t stream) {
   REQUIRE_D(D);
   if (num_partials) *num_partials = 0;
   if (N == 0) return 0;
@@ -711,18 +828,37 @@ extern "C" int molclr_gine_aggregate_bwd(const float* ga, const int32_t* rowptr_
   NCH_DISPATCH(D4, {
     if (z_prev) {
       const size_t smem = (size_t)(4 + 2 * kRowWarps) * D * sizeof(float);
-      auto k = gine_aggregate_bwd_kernel<NCH, 1>;
-      const int grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
-      k<<<grid, kRowThreads, smem, stream>>>(ga, rowptr_t, col_t, z_prev, bn_coef, relu, (int)N, D, gy, partials);
+      int grid;
+      if (gather) {
+        auto k = gine_aggregate_bwd_kernel<NCH, 1, true>;
+        grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
+        k<<<grid, kRowThreads, smem, stream>>>(ga, rowptr_t, col_t, z_prev, bn_coef, relu, (int)N, D, gy, partials, round_out);
+      } else {
+        auto k = gine_aggregate_bwd_kernel<NCH, 1, false>;
+        grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
+        k<<<grid, kRowThreads, smem, stream>>>(ga, nullptr, nullptr, z_prev, bn_coef, relu, (int)N, D, gy, partials, round_out);
+      }
       if (num_partials) *num_partials = grid;
     } else {
-      auto k = gine_aggregate_bwd_kernel<NCH, 0>;
+      MOLCLR_REQUIRE(gather, "relu_bn_bwd_stats: z_prev is required");
+      auto k = gine_aggregate_bwd_kernel<NCH, 0, true>;
       k<<<persistent_grid(k, kRowThreads, 0, kRowWarps, N), kRowThreads, 0, stream>>>(ga, rowptr_t, col_t, nullptr, nullptr, 0,
-                                                                                        (int)N, D, gy, nullptr);
+                                                                                        (int)N, D, gy, nullptr, round_out);
     }
   });
-  MOLCLR_CHECK_LAUNCH("gine_aggregate_bwd");
+  MOLCLR_CHECK_LAUNCH("aggregate_bwd");
   return 0;
+}
+
+extern "C" int molclr_gine_aggregate_bwd(const float* ga, const int32_t* rowptr_t, const int32_t* col_t, const float* z_prev,
+                                         const float* bn_coef, int relu, int64_t N, int D, float* gy, int round_tf32_out,
+                                         float* partials, int* num_partials, cudaStream_t stream) {
+  return aggregate_bwd_launch(ga, rowptr_t, col_t, true, z_prev, bn_coef, relu, N, D, gy, round_tf32_out, partials, num_partials, stream);
+}
+
+extern "C" int molclr_relu_bn_bwd_stats(const float* g, const float* z_prev, const float* bn_coef, int relu, int64_t N, int D,
+                                        float* gy, float* partials, int* num_partials, cudaStream_t stream) {
+  return aggregate_bwd_launch(g, nullptr, nullptr, false, z_prev, bn_coef, relu, N, D, gy, 0, partials, num_partials, stream);
 }
 
 extern "C" int molclr_edge_table_grad(const float* ga, const uint16_t* cnt, int64_t N, int D, float* dB /* [8][D]: 5 type rows then 3 direction rows */,
@@ -778,8 +914,8 @@ extern "C" int molclr_bn_bwd_finalize(const float* partials, int P, int64_t N, i
 }
 
 extern "C" int molclr_bn_bwd_apply(const float* gy, const float* gp, const int32_t* node2graph, const int32_t* gptr, int pool_mean,
-                                   const float* z, const float* bcoef, int64_t N, int D, float* gz, int64_t ld_gz, float* dbias,
-                                   float* partials, cudaStream_t stream) {
+                                   const float* z, const float* bcoef, int64_t N, int D, float* gz, int64_t ld_gz, int round_tf32_out,
+                                   float* dbias, float* partials, cudaStream_t stream) {
   REQUIRE_D(D);
   MOLCLR_REQUIRE(ld_gz >= D && ld_gz % 4 == 0, "bn_bwd_apply: ld_gz must be >= D and a multiple of 4");
   if (N == 0) return 0;
@@ -789,11 +925,11 @@ extern "C" int molclr_bn_bwd_apply(const float* gy, const float* gp, const int32
     if (gp) {
       auto k = bn_bwd_apply_kernel<NCH, 1>;
       grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
-      k<<<grid, kRowThreads, smem, stream>>>(nullptr, gp, node2graph, gptr, pool_mean, z, bcoef, (int)N, D, gz, ld_gz, partials);
+      k<<<grid, kRowThreads, smem, stream>>>(nullptr, gp, node2graph, gptr, pool_mean, z, bcoef, (int)N, D, gz, ld_gz, partials, round_tf32_out);
     } else {
       auto k = bn_bwd_apply_kernel<NCH, 0>;
       grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
-      k<<<grid, kRowThreads, smem, stream>>>(gy, nullptr, nullptr, nullptr, 0, z, bcoef, (int)N, D, gz, ld_gz, partials);
+      k<<<grid, kRowThreads, smem, stream>>>(gy, nullptr, nullptr, nullptr, 0, z, bcoef, (int)N, D, gz, ld_gz, partials, round_tf32_out);
     }
   });
   MOLCLR_CHECK_LAUNCH("bn_bwd_apply");
@@ -830,6 +966,39 @@ extern "C" int molclr_pool_bwd_stats(const float* gp, const int32_t* node2graph,
     if (num_partials) *num_partials = grid;
   });
   MOLCLR_CHECK_LAUNCH("pool_bwd_stats");
+  return 0;
+}
+
+extern "C" int molclr_bn_apply_fwd(const float* z, const float* bn_coef, int relu, int64_t N, int D, float* hi, float* lo,
+                                   int64_t ld, cudaStream_t stream) {
+  REQUIRE_D(D);
+  MOLCLR_REQUIRE(ld >= D && ld % 4 == 0, "bn_apply_fwd: ld must be >= D and a multiple of 4");
+  if (N == 0) return 0;
+  const size_t smem = (size_t)2 * D * sizeof(float);
+  NCH_DISPATCH(D / 4, {
+    auto k = bn_apply_fwd_kernel<NCH>;
+    k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(z, bn_coef, relu, (int)N, D, hi, lo, ld);
+  });
+  MOLCLR_CHECK_LAUNCH("bn_apply_fwd");
+  return 0;
+}
+
+extern "C" int molclr_bn_tile_stats(const float* z, int64_t N, int D, int T, float* tile_stats, cudaStream_t stream) {
+  REQUIRE_D(D);
+  MOLCLR_REQUIRE((int64_t)T * 32 >= N, "bn_tile_stats: T=%d groups of 32 rows do not cover N=%lld", T, (long long)N);
+  if (T == 0) return 0;
+  NCH_DISPATCH(D / 4, {
+    auto k = bn_tile_stats_kernel<NCH>;
+    k<<<persistent_grid(k, kRowThreads, 0, kRowWarps, T), kRowThreads, 0, stream>>>(z, (int)N, D, T, tile_stats);
+  });
+  MOLCLR_CHECK_LAUNCH("bn_tile_stats");
+  return 0;
+}
+
+extern "C" int molclr_row_sum(const float* in, int R, int C, float* out, cudaStream_t stream) {
+  if (R == 0) return 0;
+  row_sum_kernel<<<(R + 7) / 8, 256, 0, stream>>>(in, R, C, out);
+  MOLCLR_CHECK_LAUNCH("row_sum");
   return 0;
 }
 

@@ -1,0 +1,164 @@
+"""GCN: drop-in for ``models/gcn_molclr.py`` (same constructor, ``forward(data) -> (h, out)``, ``state_dict`` keys --
+checked against the reference's shipped checkpoint) on the hand-written sm_100a kernels.
+
+What the reference's ``GCNConv`` actually computes (gcn_molclr.py:62-88): the symmetric degree
+normalisation of ``gcn_norm`` is computed and then DISCARDED (``edge_index, __ = gcn_norm(edge_index)``, line 74), so a layer
+is the UN-normalised ``out = (A + I)(x W) + s 1^T + b`` with ``s_i`` the sum of the scalar bond embeddings of node i's
+in-edges (self loop = type 4, direction 0).  That is what runs here.
+
+Per view (N nodes, D = emb_dim):
+
+    plan (once per batch)        CSR + transpose + bond-class counts + graph segments
+    embed_nodes_fwd              h0 = E1[x0] + E2[x1]                                  gcn_molclr.py:144
+    per layer l:
+      bn_apply_fwd               x_l = relu(BN_{l-1}(z_{l-1})) as a tf32 (hi, lo) GEMM operand (x_0 = h0)     :146-152
+      gemm                       y_l = x_l W_l          (W stored [in, out]: consumed MN-major in place)      :76
+      gcn_aggregate_fwd          z_l = sum_j (y_l[j] + s_e) + (y_l[i] + s_self) + b_l                          :79-88
+      bn_tile_stats + finalize   batch statistics -> (scale, shift, mean, invstd); running stats              :147
+    pool_fwd, head               as GINet                                                                     :154-156
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import ops
+from .ginet import (PRECISIONS, _EncoderBase, _RoundedWeights, _head_backward, _head_forward, _lo, num_atom_type, num_bond_direction,
+                    num_bond_type, num_chirality_tag)
+from .graph import get_plan
+
+
+class GCNConv(nn.Module):
+    """Parameter container with the reference's names and initialisation (gcn_molclr.py:39-60)."""
+
+    def __init__(self, emb_dim, aggr="add"):
+        super().__init__()
+        self.emb_dim, self.aggr = emb_dim, aggr
+        self.weight = nn.Parameter(torch.empty(emb_dim, emb_dim))          # stored [in, out]
+        self.bias = nn.Parameter(torch.empty(emb_dim))
+        stdv = math.sqrt(6.0 / (emb_dim + emb_dim))                        # glorot, gcn_molclr.py:55-60
+        self.weight.data.uniform_(-stdv, stdv)
+        self.bias.data.fill_(0)
+        self.edge_embedding1 = nn.Embedding(num_bond_type, 1)
+        self.edge_embedding2 = nn.Embedding(num_bond_direction, 1)
+        nn.init.xavier_uniform_(self.edge_embedding1.weight.data)
+        nn.init.xavier_uniform_(self.edge_embedding2.weight.data)
+
+
+class GCN(_EncoderBase):
+    """gcn_molclr.py:94-158.
+
+    Args:
+        num_layer (int): the number of GNN layers (>= 2)
+        emb_dim (int): dimensionality of embeddings
+        feat_dim (int): dimensionality of the returned representation ``h``
+        drop_ratio (float): dropout rate
+        pool (str): 'mean' | 'add' | 'max'
+    """
+
+    def __init__(self, num_layer=5, emb_dim=300, feat_dim=256, drop_ratio=0, pool="mean"):
+        super().__init__()
+        self.num_layer, self.emb_dim, self.feat_dim, self.drop_ratio = num_layer, emb_dim, feat_dim, drop_ratio
+        if self.num_layer < 2:
+            raise ValueError("Number of GNN layers must be greater than 1.")          # gcn_molclr.py:102-103
+        if pool not in ("mean", "add", "max"):
+            raise ValueError("Not defined pooling!")                                  # gcn_molclr.py:127-128
+        self.pool_name = pool
+        self.x_embedding1 = nn.Embedding(num_atom_type, emb_dim)
+        self.x_embedding2 = nn.Embedding(num_chirality_tag, emb_dim)
+        nn.init.xavier_uniform_(self.x_embedding1.weight.data)
+        nn.init.xavier_uniform_(self.x_embedding2.weight.data)
+        self.gnns = nn.ModuleList([GCNConv(emb_dim, aggr="add") for _ in range(num_layer)])
+        self.batch_norms = nn.ModuleList([nn.BatchNorm1d(emb_dim) for _ in range(num_layer)])
+        self.feat_lin = nn.Linear(emb_dim, feat_dim)
+        self.out_lin = nn.Sequential(nn.Linear(feat_dim, feat_dim), nn.ReLU(inplace=True), nn.Linear(feat_dim, feat_dim // 2))
+        self._rounded = _RoundedWeights()
+
+    def _params(self):
+        ps = [self.x_embedding1.weight, self.x_embedding2.weight]
+        for g, bn in zip(self.gnns, self.batch_norms):
+            ps += [g.weight, g.bias, g.edge_embedding1.weight, g.edge_embedding2.weight, bn.weight, bn.bias]
+        ps += [self.feat_lin.weight, self.feat_lin.bias, self.out_lin[0].weight, self.out_lin[0].bias,
+               self.out_lin[2].weight, self.out_lin[2].bias]
+        return ps
+
+    def forward(self, data):
+        self._check_input(data)
+        plan = get_plan(data)
+        h, out = _GCNFunction.apply(self, plan, *self._params())
+        return h, out
+
+
+class _GCNFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, m, plan, *params):
+        L, D, N = m.num_layer, m.emb_dim, plan.N
+        dev = params[0].device
+        rw = m._rounded
+        if m.precision not in PRECISIONS:
+            raise ValueError(f"molclr_b200: precision must be one of {PRECISIONS}, got {m.precision!r}")
+        comp = m.precision == "tf32x3"
+        training = m.training
+        pool_mode = ops.POOL_MODES[m.pool_name]
+        h0 = ops.embed_nodes_fwd(plan, m.x_embedding1.weight.detach(), m.x_embedding2.weight.detach())
+        x_hi, x_lo = ops.bn_apply_fwd(h0, None, False, comp)
+        layers = []
+        z = coef = None
+        for l in range(L):
+            g, bn = m.gnns[l], m.batch_norms[l]
+            W_hi, W_lo = rw.get(g.weight)
+            y = torch.empty(N, D, device=dev)
+            ops.gemm(x_hi, W_hi, N, D, D, b_mn=True, A_lo=x_lo, B_lo=_lo(W_lo, comp), out=y)            # x @ weight
+            z = ops.gcn_aggregate_fwd(plan, y, g.edge_embedding1.weight.detach(), g.edge_embedding2.weight.detach(), g.bias.detach())
+            if training:
+                stats, T = ops.bn_tile_stats(z)
+                momentum = 0.1 if bn.momentum is None else bn.momentum
+                coef = ops.bn_fwd_finalize(stats, T, N, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
+                                           bn.num_batches_tracked, momentum, bn.eps)
+            else:
+                coef = ops.bn_eval_coef(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
+            layers.append((x_hi, z, coef, W_hi))
+            if l < L - 1:
+                x_hi, x_lo = ops.bn_apply_fwd(z, coef, True, comp)
+        p, p_lo = ops.pool_fwd(plan, z, coef, pool_mode, relu=False, round_out=True, want_lo=True) if comp else \
+            (ops.pool_fwd(plan, z, coef, pool_mode, relu=False, round_out=True), None)
+        h, out, head_saved = _head_forward(m, p, p_lo, rw, comp)
+        ctx.m, ctx.plan, ctx.layers, ctx.p, ctx.head_saved = m, plan, layers, p, head_saved
+        ctx.training, ctx.pool_mode = training, pool_mode
+        return h, out
+
+    @staticmethod
+    def backward(ctx, g_h, g_out):
+        m, plan, layers, p = ctx.m, ctx.plan, ctx.layers, ctx.p
+        L, D, N = m.num_layer, m.emb_dim, plan.N
+        dev = p.device
+        if g_out is None:
+            g_out = torch.zeros(p.shape[0], m.feat_dim // 2, device=dev)
+        g_p, head_grads = _head_backward(m, p, ctx.head_saved, g_h, g_out)
+        grads = [None] * (2 + 6 * L)
+        x_hi, z, coef, W_hi = layers[L - 1]
+        bn = m.batch_norms[L - 1]
+        partials, P = ops.pool_bwd_stats(plan, g_p, z, coef, ctx.pool_mode)
+        dgamma, dbeta, bcoef = ops.bn_bwd_finalize(partials, P, N, bn.weight.detach(), coef, ctx.training)
+        g_z, db = ops.bn_bwd_apply(z, bcoef, gp=g_p, plan=plan, pool_mean=ctx.pool_mode == 0, round_out=False)
+        for l in range(L - 1, -1, -1):
+            x_hi, z, coef, W_hi = layers[l]
+            base = 2 + 6 * l
+            grads[base + 4], grads[base + 5], grads[base + 1] = dgamma, dbeta, db          # BN weight/bias, conv bias
+            ds = ops.row_sum(ops.edge_table_grad_raw(plan, g_z))                          # scalar bond tables: [8]
+            grads[base + 2], grads[base + 3] = ds[:5].reshape(5, 1), ds[5:].reshape(3, 1)
+            g_y, _, _ = ops.gine_aggregate_bwd(plan, g_z, round_out=True)                 # (A + I)^T g_z, tf32 for the GEMMs
+            grads[base + 0] = ops.gemm_dw(x_hi, g_y)                                      # dW [in, out] = x^T g_y
+            g_x = torch.empty(N, D, device=dev)
+            ops.gemm(g_y, W_hi, N, D, D, out=g_x)                                         # g_x = g_y W^T
+            if l > 0:
+                _, zp, coefp, _ = layers[l - 1]
+                bnp = m.batch_norms[l - 1]
+                g_r, partials, P = ops.relu_bn_bwd_stats(g_x, zp, coefp, relu=True)
+                dgamma, dbeta, bcoef = ops.bn_bwd_finalize(partials, P, N, bnp.weight.detach(), coefp, ctx.training)
+                g_z, db = ops.bn_bwd_apply(zp, bcoef, gy=g_r, round_out=False)
+            else:
+                grads[0], grads[1] = ops.embed_nodes_bwd(plan, g_x)
+        ctx.layers = None
+        return (None, None, *grads, *head_grads)

@@ -162,24 +162,76 @@ def gine_aggregate_fwd(plan, src, B1, B2, bn_coef=None, relu=True, round_out=Tru
     return (out, lo) if want_lo else out
 
 
-def gine_aggregate_bwd(plan, ga, z_prev=None, bn_coef=None, relu=True):
+def gine_aggregate_bwd(plan, ga, z_prev=None, bn_coef=None, relu=True, round_out=False):
     """Returns (gy, partials, P): partials/P are None/0 when z_prev is None."""
     D = ga.shape[1]
     gy = torch.empty_like(ga)
     partials = _empty(max_blocks(), 2, D, device=ga.device) if z_prev is not None else None
     n = C.c_int(0)
     check(_lib.load().molclr_gine_aggregate_bwd(ptr(ga), ptr(plan.rowptr_t, torch.int32), ptr(plan.col_t, torch.int32),
-                                                ptr(z_prev), ptr(bn_coef), int(relu), plan.N, D, ptr(gy), ptr(partials),
-                                                C.byref(n), stream()), "gine_aggregate_bwd")
+                                                ptr(z_prev), ptr(bn_coef), int(relu), plan.N, D, ptr(gy), int(round_out),
+                                                ptr(partials), C.byref(n), stream()), "gine_aggregate_bwd")
     return gy, partials, n.value
 
 
-def edge_table_grad(plan, ga):
+def relu_bn_bwd_stats(g, z_prev, bn_coef, relu=True):
+    """gy = g * [relu(BN(z_prev)) > 0] and the (sum gy, sum gy*xhat) partials.  Returns (gy, partials, P)."""
+    N, D = g.shape
+    gy = torch.empty_like(g)
+    partials = _empty(max_blocks(), 2, D, device=g.device)
+    n = C.c_int(0)
+    check(_lib.load().molclr_relu_bn_bwd_stats(ptr(g), ptr(z_prev), ptr(bn_coef), int(relu), N, D, ptr(gy), ptr(partials),
+                                               C.byref(n), stream()), "relu_bn_bwd_stats")
+    return gy, partials, n.value
+
+
+def gcn_aggregate_fwd(plan, src, b1, b2, bias):
+    """GCNConv propagate + bias (gcn_molclr.py:79-82) on y = x @ weight; exact fp32 output."""
+    D = src.shape[1]
+    out = _empty(plan.N, D, device=src.device)
+    check(_lib.load().molclr_gcn_aggregate_fwd(ptr2d(src), ptr(plan.rowptr, torch.int32), ptr(plan.col, torch.int32),
+                                               ptr(plan.eattr, torch.uint8), ptr(b1.reshape(-1)), ptr(b2.reshape(-1)), ptr(bias),
+                                               plan.N, D, ptr(out), D, stream()), "gcn_aggregate_fwd")
+    return out
+
+
+def row_sum(x):
+    R, Cc = x.shape
+    out = _empty(R, device=x.device)
+    check(_lib.load().molclr_row_sum(ptr(x), R, Cc, ptr(out), stream()), "row_sum")
+    return out
+
+
+def bn_apply_fwd(z, bn_coef, relu, want_lo):
+    """(hi, lo) tensor-core operand pair of relu(BN(z)) (bn_coef None: of z itself), 128-byte aligned rows."""
+    N, D = z.shape
+    hi = padded(N, D, z.device)
+    lo = padded(N, D, z.device) if want_lo else None
+    check(_lib.load().molclr_bn_apply_fwd(ptr(z), ptr(bn_coef), int(relu), N, D, ptr2d(hi), ptr2d(lo), hi.stride(0), stream()),
+          "bn_apply_fwd")
+    return hi, lo
+
+
+def bn_tile_stats(z):
+    N, D = z.shape
+    T = colstat_tiles(N)
+    st = _empty(T, 2, D, device=z.device)
+    check(_lib.load().molclr_bn_tile_stats(ptr(z), N, D, T, ptr(st), stream()), "bn_tile_stats")
+    return st, T
+
+
+def edge_table_grad_raw(plan, ga):
+    """dB [8, D]: rows 0..4 = gradient of the bond-type table, rows 5..7 = of the bond-direction table."""
     D = ga.shape[1]
     dB = _empty(8, D, device=ga.device)
     partials = _empty(max_blocks(), 8 * D, device=ga.device)
     check(_lib.load().molclr_edge_table_grad(ptr(ga), ptr(plan.cnt, torch.uint16), plan.N, D, ptr(dB), ptr(partials), stream()),
           "edge_table_grad")
+    return dB
+
+
+def edge_table_grad(plan, ga):
+    dB = edge_table_grad_raw(plan, ga)
     return dB[:5], dB[5:]
 
 
@@ -210,15 +262,15 @@ def bn_bwd_finalize(partials, P, N, gamma, coef, use_batch_stats):
     return dgamma, dbeta, bcoef
 
 
-def bn_bwd_apply(z, bcoef, gy=None, gp=None, plan=None, pool_mean=True):
+def bn_bwd_apply(z, bcoef, gy=None, gp=None, plan=None, pool_mean=True, round_out=True):
     N, D = z.shape
-    gz = padded(N, D, z.device)                  # a GEMM operand: 128-byte aligned rows
+    gz = padded(N, D, z.device) if round_out else _empty(N, D, device=z.device)   # GEMM operand: 128-byte aligned rows
     dbias = _empty(D, device=z.device)
     partials = _empty(max_blocks(), D, device=z.device)
     n2g = ptr(plan.node2graph, torch.int32) if gp is not None else None
     gptr = ptr(plan.gptr, torch.int32) if gp is not None else None
     check(_lib.load().molclr_bn_bwd_apply(ptr(gy), ptr(gp), n2g, gptr, int(pool_mean), ptr(z), ptr(bcoef), N, D, ptr2d(gz),
-                                          gz.stride(0), ptr(dbias), ptr(partials), stream()), "bn_bwd_apply")
+                                          gz.stride(0), int(round_out), ptr(dbias), ptr(partials), stream()), "bn_bwd_apply")
     return gz, dbias
 
 

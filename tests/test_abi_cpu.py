@@ -66,3 +66,21 @@ def test_drop_in_constructor_signatures():
     assert [p.default for p in list(sig.parameters.values())[1:]] == [5, 300, 256, 0, "mean"]
     sig = inspect.signature(molclr_b200.NTXentLoss.__init__)
     assert list(sig.parameters)[1:] == ["device", "batch_size", "temperature", "use_cosine_similarity"]
+
+
+def test_gcn_drop_in_layout_and_errors():
+    """GCN state_dict keys/shapes/dtypes == the reference's shipped checkpoint (tests/golden/gcn_ckpt_manifest.json)."""
+    import json
+    import molclr_b200
+    man = json.load(open(os.path.join(ROOT, "tests", "golden", "gcn_ckpt_manifest.json")))["entries"]
+    sd = molclr_b200.GCN(5, 300, 512, 0, "mean").state_dict()
+    assert set(sd.keys()) == set(man.keys())
+    for k, v in sd.items():
+        assert list(v.shape) == man[k]["shape"] and str(v.dtype).replace("torch.", "") == man[k]["dtype"], k
+    with pytest.raises(ValueError):
+        molclr_b200.GCN(1, 32, 16)
+    with pytest.raises(ValueError):
+        molclr_b200.GCN(3, 32, 16, 0, "bogus")
+    import inspect
+    sig = inspect.signature(molclr_b200.GCN.__init__)
+    assert list(sig.parameters)[1:] == ["num_layer", "emb_dim", "feat_dim", "drop_ratio", "pool"]
