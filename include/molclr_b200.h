@@ -180,6 +180,9 @@ typedef struct {
 int molclr_gemm_colstat_tiles(int64_t M);
 int molclr_gemm_colstat_tile_rows(void);
 int molclr_gemm_mask_words(int64_t N);
+/* work decomposition of a split-K launch, for callers that size split_k: output tiles of an [M][N] product, concurrent CTAs */
+int molclr_gemm_tile_count(int64_t M, int64_t N, int b_mn);
+int molclr_gemm_workers(void);
 int molclr_gemm_tf32(const molclr_gemm_args* args /* host */, cudaStream_t stream);
 
 /* ---- small elementwise ops ---------------------------------------------------------------------- */

@@ -65,6 +65,8 @@ SIGNATURES = {
     "molclr_gemm_colstat_tiles": (i32, [i64]),
     "molclr_gemm_colstat_tile_rows": (i32, []),
     "molclr_gemm_mask_words": (i32, [i64]),
+    "molclr_gemm_tile_count": (i32, [i64, i64, i32]),
+    "molclr_gemm_workers": (i32, []),
     "molclr_gemm_tf32": (i32, [C.POINTER(GemmArgs), vp]),
     "molclr_round_tf32": (i32, [vp, vp, vp, i64, vp]),
     "molclr_round_tf32_2d": (i32, [vp, i64, vp, vp, i64, i64, i64, vp]),

@@ -31,30 +31,40 @@ constexpr int GEMM_TMEM_COLS = 512;  // two accumulator buffers of up to 256 col
 constexpr int GEMM_STAT_ROWS = 32;   // column statistics are emitted per 32-row group (one epilogue warp)
 constexpr int GEMM_SMEM_LIMIT = 232448;
 
+static int gemm_workers(bool pair) { return pair ? sm_count() / 2 : sm_count(); }
+
 // FOUR = compensated product with all four operand tiles (A_hi, A_lo, B_hi, B_lo) in one stage and three
 // MMAs per K-slice; otherwise one (A, B) pair per stage.
-template <int BN, bool FOUR>
+// TWO = CTA pair (cluster of 2, tcgen05 cta_group::2): the pair computes a 256 x BN tile; each CTA stages its own 128 rows
+// of A and HALF of the B tile, which cuts the L2 -> shared-memory traffic that bounds these loops (the weights are
+// re-read per row tile) by 28..45%.
+template <int BN, bool FOUR, bool TWO>
 struct GemmCfg {
   static constexpr int BK = FOUR ? GEMM_BK4 : GEMM_BK;
+  static constexpr int BN_CTA = TWO ? BN / 2 : BN;        // B rows staged by one CTA
   static constexpr int A_BYTES = GEMM_BM * BK * 4;
-  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int B_BYTES = BN_CTA * BK * 4;
   static constexpr int MN_BLOCK_BYTES = 32 * BK * 4;      // one [BK k][32 mn] block of an MN-major operand
   static constexpr int STAGE_BYTES = (FOUR ? 2 : 1) * (A_BYTES + B_BYTES);
   // epilogue column chunk staged per warp, and its pitch in floats (conflict-free float4 rows); the 72 KB stages of
   // the compensated product leave room for four warps with 16-column chunks only
-  static constexpr bool SMALL_EPI = FOUR && BK == 32;
+  static constexpr bool SMALL_EPI = FOUR && (GEMM_SMEM_LIMIT - 8 * 32 * 32 * 4 - 256 - 2048) / STAGE_BYTES < 3;
   static constexpr int CHUNK = SMALL_EPI ? 16 : 32;
-  static constexpr int CHUNK_LD = CHUNK + 4;
+  // 32-column chunks are staged unpadded with an XOR swizzle of the 16-byte column groups (stg_off); 16-column ones padded
+  static constexpr int CHUNK_LD = CHUNK == 32 ? 32 : CHUNK + 4;
   // epilogue warps: two per TMEM lane quadrant (splitting the column chunks) where shared memory allows
   static constexpr int EPI_WARPS = SMALL_EPI ? 4 : 8;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int STAGING_BYTES = EPI_WARPS * 32 * CHUNK_LD * 4;     // per epilogue warp: 32 rows x chunk
-  static constexpr int BAR_BYTES = 256;
+  static constexpr bool BIAS_SMEM = !(FOUR && !TWO);       // (the single-CTA compensated config has no room left)
+  static constexpr int BAR_BYTES = 256 + (BIAS_SMEM ? 2 * 256 * 4 : 0);   // mbarriers + TMEM slot, then two bias tiles (double-buffered)
   static constexpr int STAGES_RAW = (GEMM_SMEM_LIMIT - STAGING_BYTES - BAR_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int SMEM_BYTES = PIPE_BYTES + STAGING_BYTES + BAR_BYTES;
+  static constexpr int TX_BYTES = (TWO ? 2 : 1) * STAGE_BYTES;   // bytes arriving on the (leader's) full barrier per stage
   static_assert(BN % 32 == 0 && BN <= 256, "BN must be a multiple of 32 (MN-major B blocks) and <= 256");
+  static_assert(!TWO || BN_CTA % 16 == 0, "a CTA pair splits B in halves of whole 8-row groups");
   static_assert(STAGE_BYTES % 1024 == 0, "stage bases must stay 1024B aligned for the 128B swizzles");
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
 };
@@ -113,15 +123,21 @@ __device__ __forceinline__ void colstat_group(const float* stage, int lds, int n
   }
 }
 
+// Float offset of element (row r, column c) of a staged epilogue chunk with pitch LD: LD == 32 -> rows unpadded, the eight
+// 16-byte column groups of a row XOR-swizzled with r & 7 (conflict-free for row-wise float4 writes, row-segment float4 reads
+// and column reads alike); otherwise plain padded rows.
+template <int LD>
+__device__ __forceinline__ int stg_off(int r, int c) { return LD == 32 ? r * 32 + ((((c >> 2) ^ (r & 7)) << 2) | (c & 3)) : r * LD + c; }
+
 // Warp version for the tensor-core epilogue: lane c owns column c of a 32-row staged chunk; the 32 row reads are
 // independent (fully unrolled), so their latency overlaps.
-template <int NCOLS>
-__device__ __forceinline__ void colstat_warp(const float* stage, int lds, int rows, int col0, int group, const GemmParams& p, int lane) {
+template <int NCOLS, int LD>
+__device__ __forceinline__ void colstat_warp(const float* stage, int rows, int col0, int group, const GemmParams& p, int lane) {
   const int c = lane, col = col0 + c;
-  if (NCOLS < 32 && c >= NCOLS) return;
+  if ((NCOLS < 32 && c >= NCOLS) || group >= p.stat_groups) return;
   float x[32];
 #pragma unroll
-  for (int r = 0; r < 32; ++r) x[r] = stage[r * lds + c];
+  for (int r = 0; r < 32; ++r) x[r] = stage[stg_off<LD>(r, c)];
   float s = 0.f;
 #pragma unroll
   for (int r = 0; r < 32; ++r) s += (r < rows) ? x[r] : 0.f;
@@ -145,11 +161,11 @@ __device__ __forceinline__ void colstat_warp(const float* stage, int lds, int ro
 // KIND selects the epilogue at compile time so that each variant is a short, branch-free loop:
 enum : int { K_PLAIN = 0, K_LATE = 1, K_NTX_W = 2, K_NTX_FWD = 3, K_ATOMIC = 4 };
 
-template <int BN, bool FOUR, int KIND>
-__global__ void __launch_bounds__(GemmCfg<BN, FOUR>::THREADS, 1)
+template <int BN, bool FOUR, int KIND, bool TWO>
+__global__ void __launch_bounds__(GemmCfg<BN, FOUR, TWO>::THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
-  using Cfg = GemmCfg<BN, FOUR>;
+  using Cfg = GemmCfg<BN, FOUR, TWO>;
   extern __shared__ __align__(1024) uint8_t smem[];
   float* staging = reinterpret_cast<float*>(smem + Cfg::PIPE_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::PIPE_BYTES + Cfg::STAGING_BYTES);
@@ -157,23 +173,32 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;     // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;              // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* bias_s = reinterpret_cast<float*>(smem + Cfg::PIPE_BYTES + Cfg::STAGING_BYTES + 256);   // [2][256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = p.n_tiles, m_tiles = p.m_tiles;
   const int total = n_tiles * m_tiles * p.splits;
+  // a CTA pair is one worker: both CTAs walk the same tile sequence, rank r owns rows [128 r, 128 r + 128) of the 256-row
+  // tile and stages rows [r BN/2, (r+1) BN/2) of the B tile; only the leader (rank 0) issues MMAs.
+  const uint32_t rank = TWO ? ptx::cluster_ctarank() : 0u;
+  const int worker = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, num_workers = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int TILE_M = TWO ? 2 * GEMM_BM : GEMM_BM;
 
   if (threadIdx.x == 0) {
     if ((ptx::smem_u32(smem) & 1023u) != 0) { printf("molclr gemm: dynamic smem base not 1024B aligned\n"); __trap(); }
     for (int s = 0; s < Cfg::STAGES; ++s) { ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(tfull_bar + b, 1); ptx::mbar_init(tempty_bar + b, Cfg::EPI_WARPS); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(tfull_bar + b, 1); ptx::mbar_init(tempty_bar + b, (TWO ? 2 : 1) * Cfg::EPI_WARPS); }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
     if (p.segments > 1) { ptx::prefetch_tensormap(&tmA2); ptx::prefetch_tensormap(&tmB2); }
   }
-  if (warp == 1) { ptx::tmem_alloc(tmem_slot, GEMM_TMEM_COLS); ptx::tmem_relinquish(); }
+  if (warp == 1) {
+    if (TWO) { ptx::tmem_alloc_2cta(tmem_slot, GEMM_TMEM_COLS); ptx::tmem_relinquish_2cta(); }
+    else { ptx::tmem_alloc(tmem_slot, GEMM_TMEM_COLS); ptx::tmem_relinquish(); }
+  }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (TWO) ptx::cluster_sync(); else __syncthreads();     // barriers initialised and TMEM allocated in BOTH CTAs
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -181,15 +206,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0;                                  // global k-block counter -> ring slot / phase
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int n0 = (t % n_tiles) * BN, m0 = ((t / n_tiles) % m_tiles) * GEMM_BM;
+      for (int t = worker; t < total; t += num_workers) {
+        const int n0 = (t % n_tiles) * BN + (int)rank * Cfg::BN_CTA, m0 = ((t / n_tiles) % m_tiles) * TILE_M + (int)rank * GEMM_BM;
         const int kb0 = (t / (n_tiles * m_tiles)) * p.kb_per_split;
         const int nkb_seg = min(p.num_kb, kb0 + p.kb_per_split) - kb0;
         const int nkb = FOUR ? nkb_seg : nkb_seg * p.segments;
         for (int i = 0; i < nkb; ++i, ++it) {
           const int s = it % Cfg::STAGES;
           ptx::mbar_wait(empty_bar + s, ((it / Cfg::STAGES) & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(full_bar + s, Cfg::STAGE_BYTES);
+          if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar + s, Cfg::TX_BYTES);
+          const uint32_t fb = TWO ? ptx::mapa(ptx::smem_u32(full_bar + s), 0u) : 0u;     // the leader's barrier
+          auto load = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
+            if (TWO) ptx::tma_load_2d_2cta(dst, m, fb, c0, c1); else ptx::tma_load_2d(dst, m, full_bar + s, c0, c1);
+          };
           uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
           uint8_t* b_dst = a_dst + (FOUR ? 2 : 1) * Cfg::A_BYTES;
           const int seg = FOUR ? 0 : i / nkb_seg;
@@ -200,12 +229,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const CUtensorMap* mb = (FOUR ? h == 1 : seg == 2) ? &tmB2 : &tmB;
             uint8_t* ad = a_dst + h * Cfg::A_BYTES;
             uint8_t* bd = b_dst + h * Cfg::B_BYTES;
-            if (!p.a_mn) ptx::tma_load_2d(ad, ma, full_bar + s, kc, m0);
+            if (!p.a_mn) load(ad, ma, kc, m0);
             else
-              for (int j = 0; j < GEMM_BM / 32; ++j) ptx::tma_load_2d(ad + j * Cfg::MN_BLOCK_BYTES, ma, full_bar + s, m0 + 32 * j, kc);
-            if (!p.b_mn) ptx::tma_load_2d(bd, mb, full_bar + s, kc, n0);
+              for (int j = 0; j < GEMM_BM / 32; ++j) load(ad + j * Cfg::MN_BLOCK_BYTES, ma, m0 + 32 * j, kc);
+            if (!p.b_mn) load(bd, mb, kc, n0);
             else
-              for (int j = 0; j < BN / 32; ++j) ptx::tma_load_2d(bd + j * Cfg::MN_BLOCK_BYTES, mb, full_bar + s, n0 + 32 * j, kc);
+              for (int j = 0; j < Cfg::BN_CTA / 32; ++j) load(bd + j * Cfg::MN_BLOCK_BYTES, mb, n0 + 32 * j, kc);
           }
         }
       }
@@ -213,8 +242,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_tf32(BN, p.a_mn != 0, p.b_mn != 0);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = ptx::make_idesc_tf32(BN, p.a_mn != 0, p.b_mn != 0, TILE_M);
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+        if (TWO) ptx::mma_tf32_ss_2cta(d, a, b, idesc, acc); else ptx::mma_tf32_ss(d, a, b, idesc, acc);
+      };
+      auto commit = [&](uint64_t* bar) { if (TWO) ptx::mma_commit_2cta(bar); else ptx::mma_commit(bar); };
       // K-major tiles: rows of BK*4 bytes (128B or 64B swizzle), 8-row groups SBO apart.  MN-major: [BK k][32 mn] blocks
       // LBO apart, 4-k-row groups 512 B apart.
       constexpr uint32_t kmaj_sbo = 8u * Cfg::BK * 4u, kmaj_lay = Cfg::BK == 16 ? ptx::kLayoutSw64 : ptx::kLayoutSw128;
@@ -223,7 +256,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t a_lay = p.a_mn ? ptx::kLayoutSw128Base32 : kmaj_lay, b_lay = p.b_mn ? ptx::kLayoutSw128Base32 : kmaj_lay;
       const uint32_t a_kstep = p.a_mn ? 1024u : 32u, b_kstep = p.b_mn ? 1024u : 32u;   // bytes per K=8 slice
       uint32_t it = 0, tl = 0;                          // tl = local tile counter -> accumulator buffer / phase
-      for (int t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
+      for (int t = worker; t < total; t += num_workers, ++tl) {
         const int kb0 = (t / (n_tiles * m_tiles)) * p.kb_per_split;
         const int nkb_seg = min(p.num_kb, kb0 + p.kb_per_split) - kb0;
         const int nkb = FOUR ? nkb_seg : nkb_seg * p.segments;
@@ -241,17 +274,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int k = 0; k < Cfg::BK / 8; ++k) {
             const uint64_t ad = ptx::make_smem_desc(a_base + k * a_kstep, a_lbo, a_sbo, a_lay);
             const uint64_t bd = ptx::make_smem_desc(b_base + k * b_kstep, b_lbo, b_sbo, b_lay);
-            ptx::mma_tf32_ss(d_tmem, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+            mma(d_tmem, ad, bd, (i | k) != 0 ? 1u : 0u);
             if (FOUR) {
               const uint64_t ad2 = ptx::make_smem_desc(a_base + Cfg::A_BYTES + k * a_kstep, a_lbo, a_sbo, a_lay);
               const uint64_t bd2 = ptx::make_smem_desc(b_base + Cfg::B_BYTES + k * b_kstep, b_lbo, b_sbo, b_lay);
-              ptx::mma_tf32_ss(d_tmem, ad2, bd, idesc, 1u);          // A_lo * B_hi
-              ptx::mma_tf32_ss(d_tmem, ad, bd2, idesc, 1u);          // A_hi * B_lo
+              mma(d_tmem, ad2, bd, 1u);          // A_lo * B_hi
+              mma(d_tmem, ad, bd2, 1u);          // A_hi * B_lo
             }
           }
-          ptx::mma_commit(empty_bar + s);          // frees the smem slot once these MMAs have read it
+          commit(empty_bar + s);          // frees the smem slot (of both CTAs) once these MMAs have read it
         }
-        ptx::mma_commit(tfull_bar + buf);          // accumulator complete
+        commit(tfull_bar + buf);          // accumulator complete
       }
     }
     __syncwarp();
@@ -262,9 +295,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int NSHARE = Cfg::EPI_WARPS / 4;
     float* stg = staging + (warp - 2) * 32 * Cfg::CHUNK_LD;
     uint32_t tl = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++tl) {
+    const uint32_t tempty_leader = TWO ? ptx::mapa(ptx::smem_u32(tempty_bar), 0u) : 0u;
+    for (int t = worker; t < total; t += num_workers, ++tl) {
       const int n_tile = t % n_tiles, m_tile = (t / n_tiles) % m_tiles;
-      const int n0 = n_tile * BN, m0 = m_tile * GEMM_BM;
+      const int n0 = n_tile * BN, m0 = m_tile * TILE_M + (int)rank * GEMM_BM;
       const int row = q * 32 + lane, grow = m0 + row;
       const int rows_w = max(0, min(32, p.M - m0 - q * 32));          // valid rows of this warp's group
       const uint32_t buf = tl & 1;
@@ -279,6 +313,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       };
       uint32_t mw_next = 0u;
       if (KIND == K_PLAIN && !FOUR && p.bits_in) mw_next = mask_word(0);
+      // this tile's bias slice goes to shared memory once (double-buffered across tiles; one named barrier per tile
+      // among the epilogue warps), so that the register stage reads it with broadcast LDS instead of dependent LDGs
+      const float* bias_t = bias_s + (tl & 1) * 256;
+      if (KIND == K_PLAIN && Cfg::BIAS_SMEM && p.bias) {
+        for (int e = threadIdx.x - 64; e < BN; e += Cfg::EPI_WARPS * 32)
+          bias_s[(tl & 1) * 256 + e] = (n0 + e < p.N) ? __ldg(p.bias + n0 + e) : 0.f;
+        ptx::named_bar_sync(1, Cfg::EPI_WARPS * 32);
+      }
       ptx::mbar_wait(tfull_bar + buf, (tl >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
@@ -331,7 +373,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // TMEM -> registers (thread = row) -> per-warp staging chunk -> coalesced row segments.  K_PLAIN applies
         // alpha / bias / ReLU / the ReLU bit mask in the register stage (and emits the ReLU bits of the result);
         // the other kinds apply their terms in the copy-out pass, where a lane owns one float4 column group.
-        const int group = m_tile * 4 + q;
+        const int group = (m0 >> 5) + q;
         constexpr int LPR = CH / 4;            // lanes covering one row of the chunk (float4 each)
         constexpr int RPP = 32 / LPR;          // rows per copy-out pass
         const float alpha = p.alpha, floor_v = p.relu ? 0.f : -INFINITY;
@@ -354,9 +396,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (has_bias || alpha != 1.f || p.relu) {
 #pragma unroll
               for (int j = 0; j < CH; j += 4) {
-                const int colj = n0 + c0 + j;
                 float4 b4 = f4_zero();
-                if (has_bias && colj < p.N) b4 = ldg_f4(p.bias + colj);     // warp-uniform address
+                if (has_bias) {
+                  if (Cfg::BIAS_SMEM) b4 = *reinterpret_cast<const float4*>(bias_t + c0 + j);     // broadcast
+                  else if (n0 + c0 + j < p.N) b4 = ldg_f4(p.bias + n0 + c0 + j);
+                }
                 v[j] = fmaxf(fmaf(v[j], alpha, b4.x), floor_v); v[j + 1] = fmaxf(fmaf(v[j + 1], alpha, b4.y), floor_v);
                 v[j + 2] = fmaxf(fmaf(v[j + 2], alpha, b4.z), floor_v); v[j + 3] = fmaxf(fmaf(v[j + 3], alpha, b4.w), floor_v);
               }
@@ -377,7 +421,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
 #pragma unroll
-          for (int j = 0; j < CH; j += 4) st_f4(stg + lane * LD + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+          for (int j = 0; j < CH; j += 4) st_f4(stg + stg_off<LD>(lane, j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
           __syncwarp();
           const int col = n0 + c0 + cq;
           if (KIND == K_PLAIN && rows_w == 32 && n0 + c0 + CH <= p.N) {
@@ -388,7 +432,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float* pl = p.out_lo + gr0 * p.ldo_lo + col;
 #pragma unroll
             for (int pass = 0; pass < 32 / RPP; ++pass) {
-              const float4 x = *reinterpret_cast<const float4*>(stg + (pass * RPP + r_in) * LD + cq);
+              const float4 x = *reinterpret_cast<const float4*>(stg + stg_off<LD>(pass * RPP + r_in, cq));
               const float4 xr = f4_tf32(x);
               if (has_out) st_f4(po + (size_t)pass * RPP * p.ldo, do_round ? xr : x);
               if (has_out2) st_f4(po2 + (size_t)pass * RPP * p.ldo2, xr);
@@ -401,10 +445,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const int r = pass * RPP + r_in;
               if (r < rows_w && col_ok) {
                 const int gr = m0 + q * 32 + r;
-                float4 x = *reinterpret_cast<const float4*>(stg + r * LD + cq);
+                float4 x = *reinterpret_cast<const float4*>(stg + stg_off<LD>(r, cq));
                 if (KIND != K_PLAIN) {
                   x = epilogue_apply(x, p, gr, col);
-                  if (has_stat) st_f4(stg + r * LD + cq, x);
+                  if (has_stat) st_f4(stg + stg_off<LD>(r, cq), x);
                 }
                 const float4 xr = f4_tf32(x);
                 if (has_out) st_f4(p.out + (size_t)gr * p.ldo + col, do_round ? xr : x);
@@ -415,19 +459,24 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (has_stat) {
             __syncwarp();
-            colstat_warp<CH>(stg, LD, rows_w, n0 + c0, group, p, lane);
+            colstat_warp<CH, LD>(stg, rows_w, n0 + c0, group, p, lane);
           }
           __syncwarp();
         }
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tempty_bar + buf);
+      if (lane == 0) {
+        if (TWO) ptx::mbar_arrive_cluster(tempty_leader + buf * 8u); else ptx::mbar_arrive(tempty_bar + buf);
+      }
     }
   }
   ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, GEMM_TMEM_COLS); }
+  if (TWO) ptx::cluster_sync(); else __syncthreads();     // nobody leaves (or frees TMEM) while the peer may still signal / be read
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    if (TWO) ptx::tmem_dealloc_2cta(tmem_base, GEMM_TMEM_COLS); else ptx::tmem_dealloc(tmem_base, GEMM_TMEM_COLS);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -547,34 +596,48 @@ static int make_tmap(CUtensorMap* m, const float* base, int64_t inner, int64_t o
   return 0;
 }
 
-template <int BN, bool FOUR, int KIND>
+template <int BN, bool FOUR, int KIND, bool TWO>
 static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, int splits, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, FOUR>;
+  using Cfg = GemmCfg<BN, FOUR, TWO>;
   p.n_tiles = n_tiles; p.m_tiles = m_tiles; p.splits = splits;
+  MOLCLR_REQUIRE(!p.b_mn || Cfg::BN_CTA % 32 == 0, "gemm: internal: MN-major B needs whole 32-column blocks per CTA (BN=%d)", BN);
   CUtensorMap tmA, tmB, tmA2, tmB2;
   int rc;
-  // K-major operand [rows][K]: inner = K, outer = rows, box = rows-per-tile x 32.  MN-major [K][rows]: inner = rows, outer = K, box 32 x 32.
+  // K-major operand [rows][K]: inner = K, outer = rows, box = rows-per-CTA x BK.  MN-major [K][rows]: inner = rows, outer = K, box BK x 32.
   rc = p.a_mn ? make_tmap(&tmA, j.A, p.M, p.K, j.lda, 32, true, Cfg::BK) : make_tmap(&tmA, j.A, p.K, p.M, j.lda, GEMM_BM, false, Cfg::BK);
   if (rc) return rc;
-  rc = p.b_mn ? make_tmap(&tmB, j.B, p.N, p.K, j.ldb, 32, true, Cfg::BK) : make_tmap(&tmB, j.B, p.K, p.N, j.ldb, BN, false, Cfg::BK);
+  rc = p.b_mn ? make_tmap(&tmB, j.B, p.N, p.K, j.ldb, 32, true, Cfg::BK) : make_tmap(&tmB, j.B, p.K, p.N, j.ldb, Cfg::BN_CTA, false, Cfg::BK);
   if (rc) return rc;
   tmA2 = tmA; tmB2 = tmB;
   if (p.segments > 1) {
     rc = p.a_mn ? make_tmap(&tmA2, j.A_lo, p.M, p.K, j.lda, 32, true, Cfg::BK) : make_tmap(&tmA2, j.A_lo, p.K, p.M, j.lda, GEMM_BM, false, Cfg::BK);
     if (rc) return rc;
-    rc = p.b_mn ? make_tmap(&tmB2, j.B_lo, p.N, p.K, j.ldb, 32, true, Cfg::BK) : make_tmap(&tmB2, j.B_lo, p.K, p.N, j.ldb, BN, false, Cfg::BK);
+    rc = p.b_mn ? make_tmap(&tmB2, j.B_lo, p.N, p.K, j.ldb, 32, true, Cfg::BK) : make_tmap(&tmB2, j.B_lo, p.K, p.N, j.ldb, Cfg::BN_CTA, false, Cfg::BK);
     if (rc) return rc;
   }
+  auto kernel = gemm_tf32_kernel<BN, FOUR, KIND, TWO>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, FOUR, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "gemm: cudaFuncSetAttribute");
     attr_set = true;
   }
   const long long total = (long long)n_tiles * m_tiles * splits;
-  const int grid = (int)(total < sm_count() ? total : sm_count());
-  gemm_tf32_kernel<BN, FOUR, KIND><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
-  MOLCLR_CHECK_LAUNCH("gemm_tf32");
+  const int workers = gemm_workers(TWO);
+  const int active = (int)(total < workers ? total : workers);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(TWO ? 2 * active : active), 1, 1);
+  cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = TWO ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmA2, tmB2, p);
+  ++g_launches;
+  if (e != cudaSuccess) return cuda_fail(e, "gemm_tf32 launch");
   return 0;
 }
 
@@ -590,11 +653,23 @@ static int gemm_impl_simt() {
   return v;
 }
 
-static int gemm_bn(long long N) { return (N % 256 == 0 || N > 640) ? 256 : 160; }
+// CTA pairs (cluster of 2, 256-row tiles) unless MOLCLR_GEMM_PAIR=0
+static bool gemm_pair() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MOLCLR_GEMM_PAIR"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  return v != 0;
+}
+
+// Column-tile width.  Pairs: each CTA stages BN/2 rows of B; an MN-major B needs BN/2 to be whole 32-column blocks.
+static int gemm_bn(long long N, bool b_mn, bool pair) {
+  if (!pair) return (N % 256 == 0 || N > 640) ? 256 : 160;
+  if (N % 256 == 0 || N > 320) return 256;
+  return b_mn ? 192 : 160;
+}
 
 int gemm_n_tiles(long long N) {
   if (gemm_impl_simt()) return (int)((N + 31) / 32);
-  const int bn = gemm_bn(N);
+  const int bn = gemm_bn(N, false, gemm_pair());
   return (int)((N + bn - 1) / bn);
 }
 
@@ -628,7 +703,11 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;          // no empty split
   p.atomic_out = atomic ? 1 : 0;
   p.debug = gemm_debug_flags();
-  const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+  // split-K weight gradients stay on single CTAs: their 300/600-wide outputs pad badly to 256-row pair tiles (MMA-bound)
+  const bool pair = gemm_pair() && !gemm_impl_simt() && !atomic;
+  const int tile_m = pair ? 2 * GEMM_BM : GEMM_BM;
+  const int m_tiles = (p.M + tile_m - 1) / tile_m;
+  p.stat_groups = molclr_gemm_colstat_tiles(p.M);
   if (atomic) {
     const size_t w = (size_t)(p.transpose_out ? p.M : p.N) * sizeof(float), h = (size_t)(p.transpose_out ? p.N : p.M);
     cudaError_t e = cudaMemset2DAsync(p.out, (size_t)p.ldo * sizeof(float), 0, w, h, stream);
@@ -636,20 +715,22 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   }
   if (gemm_impl_simt()) {
     p.kb_per_split = p.num_kb;
-    gemm_simt_kernel<<<dim3((unsigned)((p.N + 31) / 32), m_tiles, 1), 128, 0, stream>>>(job.A, job.lda, job.B, job.ldb, job.A_lo, job.B_lo, p);
+    gemm_simt_kernel<<<dim3((unsigned)((p.N + 31) / 32), (p.M + GEMM_BM - 1) / GEMM_BM, 1), 128, 0, stream>>>(job.A, job.lda, job.B, job.ldb, job.A_lo, job.B_lo, p);
     MOLCLR_CHECK_LAUNCH("gemm_simt");
     return 0;
   }
   const int kind = p.epi == EPI_NTX_FWD ? K_NTX_FWD : atomic ? K_ATOMIC : p.epi == EPI_NTX_W ? K_NTX_W
                    : (p.mask || p.addend) ? K_LATE : K_PLAIN;
   MOLCLR_REQUIRE(p.segments == 1 || kind == K_PLAIN, "gemm: the compensated product supports the plain epilogue only");
-  const int bn = gemm_bn(p.N), nt = (p.N + bn - 1) / bn;
-#define MOLCLR_GEMM_CASE(BN_, FOUR_, KIND_) \
-  if (bn == BN_ && (p.segments > 1) == FOUR_ && kind == KIND_) return launch_tc<BN_, FOUR_, KIND_>(job, p, nt, m_tiles, splits, stream);
-  MOLCLR_GEMM_CASE(160, false, K_PLAIN) MOLCLR_GEMM_CASE(160, true, K_PLAIN) MOLCLR_GEMM_CASE(160, false, K_LATE)
-  MOLCLR_GEMM_CASE(160, false, K_NTX_W) MOLCLR_GEMM_CASE(160, false, K_NTX_FWD) MOLCLR_GEMM_CASE(160, false, K_ATOMIC)
-  MOLCLR_GEMM_CASE(256, false, K_PLAIN) MOLCLR_GEMM_CASE(256, true, K_PLAIN) MOLCLR_GEMM_CASE(256, false, K_LATE)
-  MOLCLR_GEMM_CASE(256, false, K_NTX_W) MOLCLR_GEMM_CASE(256, false, K_NTX_FWD) MOLCLR_GEMM_CASE(256, false, K_ATOMIC)
+  const int bn = gemm_bn(p.N, p.b_mn != 0, pair), nt = (p.N + bn - 1) / bn;
+#define MOLCLR_GEMM_CASE(BN_, FOUR_, KIND_, TWO_) \
+  if (bn == BN_ && (p.segments > 1) == FOUR_ && kind == KIND_ && pair == TWO_) return launch_tc<BN_, FOUR_, KIND_, TWO_>(job, p, nt, m_tiles, splits, stream);
+#define MOLCLR_GEMM_KINDS(BN_, TWO_) \
+  MOLCLR_GEMM_CASE(BN_, false, K_PLAIN, TWO_) MOLCLR_GEMM_CASE(BN_, true, K_PLAIN, TWO_) MOLCLR_GEMM_CASE(BN_, false, K_LATE, TWO_) \
+  MOLCLR_GEMM_CASE(BN_, false, K_NTX_W, TWO_) MOLCLR_GEMM_CASE(BN_, false, K_NTX_FWD, TWO_) MOLCLR_GEMM_CASE(BN_, false, K_ATOMIC, TWO_)
+  MOLCLR_GEMM_KINDS(160, false) MOLCLR_GEMM_KINDS(256, false)
+  MOLCLR_GEMM_KINDS(160, true) MOLCLR_GEMM_KINDS(192, true) MOLCLR_GEMM_KINDS(256, true)
+#undef MOLCLR_GEMM_KINDS
 #undef MOLCLR_GEMM_CASE
   set_error("gemm: no kernel instance for bn=%d segments=%d kind=%d", bn, p.segments, kind);
   return -2;
@@ -663,9 +744,17 @@ extern "C" int molclr_gemm_colstat_tiles(int64_t M) { return 4 * (int)((M + GEMM
 extern "C" int molclr_gemm_colstat_tile_rows(void) { return GEMM_STAT_ROWS; }
 // 32-bit words per row of a ReLU bit mask over N columns (covers the column tiles the kernel will use)
 extern "C" int molclr_gemm_mask_words(int64_t N) {
-  const int bn = (N % 256 == 0 || N > 640) ? 256 : 160;
-  return (int)((N + bn - 1) / bn) * (bn / 32);
+  int words = 0;
+  for (int bn : {160, 192, 256}) { const int w = (int)((N + bn - 1) / bn) * (bn / 32); if (w > words) words = w; }
+  return words;
 }
+// Work decomposition the launcher will use (for callers that size a split-K): number of output tiles of an [M][N] product
+// and the number of concurrent workers (CTAs, or CTA pairs).
+extern "C" int molclr_gemm_tile_count(int64_t M, int64_t N, int b_mn) {
+  const int bn = gemm_bn(N, b_mn != 0, false);
+  return (int)(((M + GEMM_BM - 1) / GEMM_BM) * ((N + bn - 1) / bn));
+}
+extern "C" int molclr_gemm_workers(void) { return gemm_workers(false); }
 
 extern "C" int molclr_gemm_tf32(const molclr_gemm_args* args, cudaStream_t stream) {
   const molclr_gemm_args& a = *args;

@@ -22,6 +22,7 @@ struct GemmParams {
   uint32_t* bits_out; const uint32_t* bits_in; long long ld_bits;   // ReLU bit masks [M][ld_bits] (bit c%32 of word c/32)
   int relu, round_out;
   float* colstat; int colstat_mode;
+  int stat_groups;             // number of 32-row groups the colstat buffer holds (filled by the launcher)
   int atomic_out;
   int debug;                   // MOLCLR_GEMM_DEBUG bit 0: skip the generic epilogue (timing experiments only)
   float alpha;                 // out = alpha * acc (+ bias + addend ...)

@@ -82,16 +82,13 @@ def gemm_dw(dY, X):
     I = X.shape[1]
     dW = _empty(O, I, device=dY.device)
 
-    def padded(m, n):
-        bn = 256 if (n % 256 == 0 or n > 640) else 160
-        return (-(-m // 128) * 128) * (-(-n // bn) * bn), (-(-m // 128)) * (-(-n // bn))
-
-    (area_a, tiles_a), (area_b, tiles_b) = padded(O, I), padded(I, O)
-    swap = area_b < area_a
+    lib = _lib.load()
+    tiles_a, tiles_b = lib.molclr_gemm_tile_count(O, I, 1), lib.molclr_gemm_tile_count(I, O, 1)
+    swap = tiles_b < tiles_a
     tiles = tiles_b if swap else tiles_a
     num_kb = -(-R // 32)
-    # one wave of work items: tiles * split <= #SM (each CTA then streams a long K range)
-    split = max(1, min(_sm_count() // tiles, max(1, num_kb // 8)))
+    # one wave of work items: tiles * split <= #workers (each worker then streams a long K range)
+    split = max(1, min(lib.molclr_gemm_workers() // tiles, max(1, num_kb // 8)))
     if swap:    # compute dW^T = X^T dY with the wider operand on M, store transposed
         gemm(X, dY, I, O, R, a_mn=True, b_mn=True, out=dW, transpose_out=True, split_k=split)
     else:
