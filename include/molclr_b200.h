@@ -201,21 +201,22 @@ int molclr_l2_normalize_bwd(const float* gy, const float* y, const float* inv_no
  * rep [R][C] fp32, R = 2N rows ordered [zjs; zis] (nt_xent.py:48), already L2-normalised when
  * use_cosine (the cosine similarity's own normalisation is applied by the caller-side kernels
  * molclr_l2_normalize_*).  `cols` [Rc][C] are the candidate rows (== rep for one GPU; the all-gathered
- * projections of every rank for global negatives), row r of rep is row r + row_offset of cols and its
- * positive is column (r + row_offset + Rc/2) mod Rc.
+ * projections of every rank for global negatives).  rep is this rank's [zjs_local; zis_local]: its first R/2 rows are
+ * candidates row_offset + r, the other R/2 rows candidates row_offset2 + (r - R/2) (one GPU: 0 and R/2); the positive of
+ * global row g is column (g + Rc/2) mod Rc.
  *   forward : row_lse[r] = log sum_{k != self} exp(S[r][k]/tau),  row_pos[r] = S[r][pos(r)]/tau,
  *             loss[0] = sum_r (row_lse[r] - row_pos[r]) / Rc  (this rank's share of the mean over Rc anchors).
  *   backward: g_rep[r] = (gscale/tau) * sum_k (P[r][k] + P[k][r] - 2*[k = pos(r)]) * cols[k],
  *             P[i][k] = exp(S[i][k]/tau - lse[i]) for k != i; col_lse[Rc] holds the log-sum-exp of every
  *             candidate row (== row_lse on one GPU, all-gathered for global negatives); gscale = 1/Rc.
  * The Rc x Rc similarity matrix is never written to memory: backward works in L2-resident stripes of
- * 1024 candidate columns.  Requires Rc % 4 == 0 and C % 4 == 0. */
+ * 2048 candidate columns; per-stripe partial gradients are summed in stripe order.  Requires R even, Rc % 4 == 0, C % 4 == 0. */
 size_t molclr_ntxent_workspace_bytes(int64_t R, int64_t Rc, int C);
 int molclr_ntxent_fwd(const float* rep, const float* cols, int64_t R, int64_t Rc, int C, int64_t row_offset,
-                      float inv_temperature, float* row_lse, float* row_pos, float* loss /* [1], optional */,
+                      int64_t row_offset2, float inv_temperature, float* row_lse, float* row_pos, float* loss /* [1], optional */,
                       void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int molclr_ntxent_bwd(const float* rep, const float* cols, int64_t R, int64_t Rc, int C, int64_t row_offset,
-                      float inv_temperature, const float* row_lse, const float* col_lse, float gscale, float* g_rep,
+                      int64_t row_offset2, float inv_temperature, const float* row_lse, const float* col_lse, float gscale, float* g_rep,
                       void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 #ifdef __cplusplus

@@ -83,7 +83,7 @@ __device__ __forceinline__ float ntx_w_elem(float acc, const GemmParams& p, floa
 __device__ __forceinline__ float4 epilogue_apply(float4 v, const GemmParams& p, int grow, int col) {
   if (p.epi == EPI_NTX_W) {
     const float lse_r = __ldg(p.row_lse + grow);
-    const long long gr = grow + p.row_offset, gc = col + p.col_offset;
+    const long long gr = grow < p.row_split ? grow + p.row_offset : grow - p.row_split + p.row_offset2, gc = col + p.col_offset;
     v.x = ntx_w_elem(v.x, p, lse_r, gr, gc); v.y = ntx_w_elem(v.y, p, lse_r, gr, gc + 1);
     v.z = ntx_w_elem(v.z, p, lse_r, gr, gc + 2); v.w = ntx_w_elem(v.w, p, lse_r, gr, gc + 3);
     return v;
@@ -321,40 +321,49 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           bias_s[(tl & 1) * 256 + e] = (n0 + e < p.N) ? __ldg(p.bias + n0 + e) : 0.f;
         ptx::named_bar_sync(1, Cfg::EPI_WARPS * 32);
       }
+      if (KIND == K_NTX_W) {            // the candidates' log-sum-exps of this column tile, pre-scaled for ex2
+        for (int e = threadIdx.x - 64; e < BN; e += Cfg::EPI_WARPS * 32)
+          bias_s[(tl & 1) * 256 + e] = (n0 + e < p.N) ? __ldg(p.col_lse + p.col_offset + n0 + e) * 1.4426950408889634f : 0.f;
+        ptx::named_bar_sync(1, Cfg::EPI_WARPS * 32);
+      }
       ptx::mbar_wait(tfull_bar + buf, (tl >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
       if (KIND == K_NTX_FWD) {
-        // per-row (max, sum exp) of this column tile, own column masked; thread <-> row straight from TMEM
-        const long long gr = grow + p.row_offset;
+        // per-row (max, sum exp) of this warp's share of the column tile, own column masked; thread <-> row straight
+        // from TMEM, one pass with a running maximum.  Partials are indexed [n_tile * NSHARE + half][row].
+        const long long gr = grow < p.row_split ? grow + p.row_offset : grow - p.row_split + p.row_offset2;
         long long pos = gr + p.num_cand / 2;
         if (pos >= p.num_cand) pos -= p.num_cand;
-        float mx = -INFINITY;
-        if (half == 0)
-        for (int c0 = 0; c0 < BN; c0 += 16) {
+        const float k2 = p.inv_tau * 1.4426950408889634f;            // logits in base-2 units
+        float mx = -INFINITY, sum = 0.f;
+        for (int c0 = 16 * half; c0 < BN && n0 + c0 < p.N; c0 += 16 * NSHARE) {
           float v[16];
           ptx::tmem_ld_x16(taddr + c0, v);
+          const long long gc0 = n0 + c0 + p.col_offset;
+          float cm = -INFINITY;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const long long gc = n0 + c0 + j + p.col_offset;
-            if (n0 + c0 + j < p.N && gc != gr) mx = fmaxf(mx, v[j] * p.inv_tau);
-            if (gc == pos && n0 + c0 + j < p.N && grow < p.M) p.row_pos[grow] = v[j] * p.inv_tau;
+            const bool ok = (n0 + c0 + j < p.N) && (gc0 + j != gr);
+            v[j] = ok ? v[j] * k2 : -INFINITY;
+            cm = fmaxf(cm, v[j]);
           }
-        }
-        float sum = 0.f;
-        if (half == 0)
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-          float v[16];
-          ptx::tmem_ld_x16(taddr + c0, v);
+          if (pos >= gc0 && pos < gc0 + 16 && grow < p.M) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const long long gc = n0 + c0 + j + p.col_offset;
-            if (n0 + c0 + j < p.N && gc != gr) sum += __expf(v[j] * p.inv_tau - mx);
+            for (int j = 0; j < 16; ++j) if (gc0 + j == pos) p.row_pos[grow] = v[j] * 0.6931471805599453f;
+          }
+          const float nm = fmaxf(mx, cm);
+          if (nm > -INFINITY) {
+            float cs = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) cs += exp2f(v[j] - nm);
+            sum = sum * exp2f(mx - nm) + cs;
+            mx = nm;
           }
         }
-        if (grow < p.M && half == 0) {
-          p.part_max[(size_t)n_tile * p.M + grow] = mx;
-          p.part_sum[(size_t)n_tile * p.M + grow] = sum;
+        if (grow < p.M) {                                           // natural-log units for the merge kernel
+          p.part_max[((size_t)n_tile * NSHARE + half) * p.M + grow] = mx * 0.6931471805599453f;
+          p.part_sum[((size_t)n_tile * NSHARE + half) * p.M + grow] = sum;
         }
       } else if (KIND == K_ATOMIC) {
         for (int c0 = 16 * half; c0 < BN; c0 += 16 * NSHARE) {
@@ -392,6 +401,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t mw = mw_next;
           if (KIND == K_PLAIN && !FOUR && has_bits_in && k + 1 < NCHUNK) mw_next = mask_word(k + 1);
           ptx::tmem_ld_wait();
+          if (KIND == K_NTX_W) {
+            // W[r][k] = P[r][k] + P[k][r] - 2 [k == pos(r)],  P[i][k] = exp(l - lse_i) for k != i (nt_xent.py:53-65 differentiated)
+            const long long gr = grow < p.row_split ? grow + p.row_offset : grow - p.row_split + p.row_offset2;
+            long long pos = gr + p.num_cand / 2;
+            if (pos >= p.num_cand) pos -= p.num_cand;
+            const float k2 = p.inv_tau * 1.4426950408889634f;
+            const float lr2 = (grow < p.M ? __ldg(p.row_lse + grow) : 0.f) * 1.4426950408889634f;
+            const long long gc0 = n0 + c0 + p.col_offset;
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+              const float l2 = v[j] * k2;
+              float w = exp2f(l2 - lr2) + exp2f(l2 - bias_t[c0 + j]);
+              w = (gc0 + j == gr) ? 0.f : w;
+              v[j] = (gc0 + j == pos) ? w - 2.f : w;
+            }
+          }
           if (KIND == K_PLAIN) {
             if (has_bias || alpha != 1.f || p.relu) {
 #pragma unroll
@@ -424,7 +449,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < CH; j += 4) st_f4(stg + stg_off<LD>(lane, j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
           __syncwarp();
           const int col = n0 + c0 + cq;
-          if (KIND == K_PLAIN && rows_w == 32 && n0 + c0 + CH <= p.N) {
+          if ((KIND == K_PLAIN || KIND == K_NTX_W) && rows_w == 32 && n0 + c0 + CH <= p.N) {
             // full chunk: straight-line copy-out (predicated stores only)
             const size_t gr0 = (size_t)(m0 + q * 32 + r_in);
             float* po = p.out + gr0 * p.ldo + col;
@@ -446,7 +471,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (r < rows_w && col_ok) {
                 const int gr = m0 + q * 32 + r;
                 float4 x = *reinterpret_cast<const float4*>(stg + stg_off<LD>(r, cq));
-                if (KIND != K_PLAIN) {
+                if (KIND != K_PLAIN && KIND != K_NTX_W) {
                   x = epilogue_apply(x, p, gr, col);
                   if (has_stat) st_f4(stg + stg_off<LD>(r, cq), x);
                 }
@@ -508,7 +533,7 @@ __global__ void __launch_bounds__(128) gemm_simt_kernel(const float* __restrict_
   }
   if (p.epi == EPI_NTX_FWD) {
     if (grow < p.M) {
-      const long long gr = grow + p.row_offset;
+      const long long gr = grow < p.row_split ? grow + p.row_offset : grow - p.row_split + p.row_offset2;
       long long pos = gr + p.num_cand / 2;
       if (pos >= p.num_cand) pos -= p.num_cand;
       float mx = -INFINITY, sum = 0.f;
@@ -667,10 +692,10 @@ static int gemm_bn(long long N, bool b_mn, bool pair) {
   return b_mn ? 192 : 160;
 }
 
-int gemm_n_tiles(long long N) {
+int gemm_n_tiles(long long N) {     // number of NT-Xent forward partials per row
   if (gemm_impl_simt()) return (int)((N + 31) / 32);
   const int bn = gemm_bn(N, false, gemm_pair());
-  return (int)((N + bn - 1) / bn);
+  return 2 * (int)((N + bn - 1) / bn);          // two epilogue warps share the columns of a tile
 }
 
 int gemm_run(const GemmJob& job, cudaStream_t stream) {
@@ -722,7 +747,7 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   const int kind = p.epi == EPI_NTX_FWD ? K_NTX_FWD : atomic ? K_ATOMIC : p.epi == EPI_NTX_W ? K_NTX_W
                    : (p.mask || p.addend) ? K_LATE : K_PLAIN;
   MOLCLR_REQUIRE(p.segments == 1 || kind == K_PLAIN, "gemm: the compensated product supports the plain epilogue only");
-  const int bn = gemm_bn(p.N, p.b_mn != 0, pair), nt = (p.N + bn - 1) / bn;
+  const int bn = (job.bn_hint && pair) ? job.bn_hint : gemm_bn(p.N, p.b_mn != 0, pair), nt = (p.N + bn - 1) / bn;
 #define MOLCLR_GEMM_CASE(BN_, FOUR_, KIND_, TWO_) \
   if (bn == BN_ && (p.segments > 1) == FOUR_ && kind == KIND_ && pair == TWO_) return launch_tc<BN_, FOUR_, KIND_, TWO_>(job, p, nt, m_tiles, splits, stream);
 #define MOLCLR_GEMM_KINDS(BN_, TWO_) \
@@ -730,6 +755,7 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   MOLCLR_GEMM_CASE(BN_, false, K_NTX_W, TWO_) MOLCLR_GEMM_CASE(BN_, false, K_NTX_FWD, TWO_) MOLCLR_GEMM_CASE(BN_, false, K_ATOMIC, TWO_)
   MOLCLR_GEMM_KINDS(160, false) MOLCLR_GEMM_KINDS(256, false)
   MOLCLR_GEMM_KINDS(160, true) MOLCLR_GEMM_KINDS(192, true) MOLCLR_GEMM_KINDS(256, true)
+  MOLCLR_GEMM_CASE(128, false, K_PLAIN, true)
 #undef MOLCLR_GEMM_KINDS
 #undef MOLCLR_GEMM_CASE
   set_error("gemm: no kernel instance for bn=%d segments=%d kind=%d", bn, p.segments, kind);

@@ -29,7 +29,8 @@ struct GemmParams {
   // ---- NT-Xent epilogues (nt_xent.py:47-65); logits l = acc * inv_tau
   int epi;
   float inv_tau;
-  long long row_offset;        // global candidate index of A row r is r + row_offset (its own column: masked out)
+  long long row_offset;        // global candidate index of A row r is r + row_offset (its own column: masked out) ...
+  long long row_split, row_offset2;   // ... for r < row_split, and r - row_split + row_offset2 for the remaining rows
   long long col_offset;        // global candidate index of B row n is n + col_offset
   long long num_cand;          // Rc; positive of global row g is (g + Rc/2) mod Rc
   const float* row_lse;        // [M]   (EPI_NTX_W)
@@ -42,6 +43,7 @@ struct GemmJob {
   const float* A; long long lda; const float* B; long long ldb;
   const float* A_lo; const float* B_lo;   // both non-null selects the 3-segment compensated product (same layout/ld as A, B)
   int split_k;
+  int bn_hint;                 // 0, or a column-tile width to use instead of the default (more tiles for narrow outputs)
   GemmParams p;                // M,N,K,a_mn,b_mn and the epilogue fields filled by the caller
 };
 

@@ -63,15 +63,11 @@ class _GlobalNTXentFunction(torch.autograd.Function):
         cols = torch.empty(2 * Bg, C, dtype=local_r.dtype, device=local_r.device)
         _gather_rows(cols[:Bg], local_r[:B], group)                          # all zjs
         _gather_rows(cols[Bg:], local_r[B:], group)                          # all zis
-        lse = torch.empty(2, B, dtype=local_r.dtype, device=local_r.device)
-        share = None
-        for v in range(2):
-            loss_v, lse_v, _pos = kern.ntxent_fwd(local_r[v * B:(v + 1) * B], cols, v * Bg + r * B, 1.0 / temperature)
-            lse[v].copy_(lse_v)
-            share = loss_v if share is None else share + loss_v
+        # local rows [zjs; zis] are candidates r*B.. and Bg + r*B.. of the global ordering
+        share, lse, _pos = kern.ntxent_fwd(local_r, cols, r * B, 1.0 / temperature, Bg + r * B)
         col_lse = torch.empty(2 * Bg, dtype=lse.dtype, device=lse.device)
-        _gather_rows(col_lse[:Bg], lse[0], group)
-        _gather_rows(col_lse[Bg:], lse[1], group)
+        _gather_rows(col_lse[:Bg], lse[:B], group)
+        _gather_rows(col_lse[Bg:], lse[B:], group)
         ctx.save_for_backward(local_n, inv, local_r, cols, lse, col_lse)
         ctx.meta = (B, Bg, r, temperature, use_cosine, kern)
         return share[0]
@@ -80,9 +76,7 @@ class _GlobalNTXentFunction(torch.autograd.Function):
     def backward(ctx, g_loss):
         local_n, inv, local_r, cols, lse, col_lse = ctx.saved_tensors
         B, Bg, r, temperature, use_cosine, kern = ctx.meta
-        parts = [kern.ntxent_bwd(local_r[v * B:(v + 1) * B], cols, v * Bg + r * B, 1.0 / temperature, lse[v], col_lse)
-                 for v in range(2)]
-        g = torch.cat(parts, dim=0) * g_loss
+        g = kern.ntxent_bwd(local_r, cols, r * B, 1.0 / temperature, lse, col_lse, Bg + r * B) * g_loss
         if use_cosine:
             g = kern.l2_normalize_bwd(g.contiguous(), local_n, inv, 1e-8)
         return g[B:], g[:B], None, None, None, None

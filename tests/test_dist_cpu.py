@@ -40,25 +40,26 @@ class TorchKernels:
         return x.clone()
 
     @staticmethod
-    def _logits(rep, cols, row_offset, inv_t):
+    def _logits(rep, cols, row_offset, inv_t, row_offset2=None):
         R, Rc = rep.shape[0], cols.shape[0]
         lg = (rep.double() @ cols.double().T) * inv_t
-        rows = torch.arange(R) + row_offset
+        row_offset2 = row_offset + R // 2 if row_offset2 is None else row_offset2
+        rows = torch.cat([torch.arange(R // 2) + row_offset, torch.arange(R - R // 2) + row_offset2])
         self_mask = torch.arange(Rc)[None, :] == rows[:, None]
         pos = (rows + Rc // 2) % Rc
         return lg, self_mask, pos
 
     @classmethod
-    def ntxent_fwd(cls, rep, cols, row_offset, inv_t):
-        lg, self_mask, pos = cls._logits(rep, cols, row_offset, inv_t)
+    def ntxent_fwd(cls, rep, cols, row_offset, inv_t, row_offset2=None):
+        lg, self_mask, pos = cls._logits(rep, cols, row_offset, inv_t, row_offset2)
         row_pos = lg[torch.arange(rep.shape[0]), pos]
         row_lse = torch.logsumexp(lg.masked_fill(self_mask, float("-inf")), dim=1)
         loss = ((row_lse - row_pos).sum() / cols.shape[0]).reshape(1)
         return loss.to(rep.dtype), row_lse.to(rep.dtype), row_pos.to(rep.dtype)
 
     @classmethod
-    def ntxent_bwd(cls, rep, cols, row_offset, inv_t, row_lse, col_lse):
-        lg, self_mask, pos = cls._logits(rep, cols, row_offset, inv_t)
+    def ntxent_bwd(cls, rep, cols, row_offset, inv_t, row_lse, col_lse, row_offset2=None):
+        lg, self_mask, pos = cls._logits(rep, cols, row_offset, inv_t, row_offset2)
         Rc = cols.shape[0]
         w = torch.exp(lg - row_lse.double()[:, None]) + torch.exp(lg - col_lse.double()[None, :])
         w = w.masked_fill(self_mask, 0.0)

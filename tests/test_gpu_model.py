@@ -164,3 +164,37 @@ def test_unknown_pool_and_cpu_input_fail_loudly():
     m = GINet(2, 32, 16).to(DEV)
     with pytest.raises(RuntimeError):
         m(bi)                     # CPU tensors: there is no CPU path
+
+
+def test_ntxent_global_negatives_two_rank_emulation():
+    """The multi-GPU NT-Xent kernels (rows = this rank's [zjs; zis] halves inside the all-gathered candidates) run rank by
+    rank on ONE GPU against the fp64 closed form over the concatenated batch (dist.py drives the same calls)."""
+    from molclr_b200 import ops
+    W, B, C, tau = 2, 384, 256, 0.1
+    torch.manual_seed(7)
+    a = torch.nn.functional.normalize(torch.randn(W * B, C), dim=1)
+    b = torch.nn.functional.normalize(0.7 * a + 0.7 * torch.randn(W * B, C), dim=1)
+    zis64, zjs64 = a.double().requires_grad_(True), b.double().requires_grad_(True)
+    ref = ntxent_closed_form(zis64, zjs64, tau, True)
+    ref.backward()
+    Bg = W * B
+    cols = ops.round_tf32(torch.cat([b, a]).to(DEV))                       # [all zjs; all zis]
+    shares, lses = [], []
+    for r in range(W):
+        local = torch.cat([cols[r * B:(r + 1) * B], cols[Bg + r * B:Bg + (r + 1) * B]]).contiguous()
+        loss, lse, _ = ops.ntxent_fwd(local, cols, r * B, 1.0 / tau, Bg + r * B)
+        shares.append(loss)
+        lses.append(lse)
+    total = sum(float(s) for s in shares)
+    assert abs(total - float(ref)) < RTOL_LOSS * abs(float(ref)), (total, float(ref))
+    col_lse = torch.cat([torch.cat([l[:B] for l in lses]), torch.cat([l[B:] for l in lses])])
+    for r in range(W):
+        local = torch.cat([cols[r * B:(r + 1) * B], cols[Bg + r * B:Bg + (r + 1) * B]]).contiguous()
+        g = ops.ntxent_bwd(local, cols, r * B, 1.0 / tau, lses[r], col_lse, Bg + r * B)
+        # gradient w.r.t. the (already unit-norm) candidates: compare with the closed form's gradient projected likewise
+        # through the cosine normalisation, which is the identity on the tangent space here
+        gj, gi = zjs64.grad[r * B:(r + 1) * B], zis64.grad[r * B:(r + 1) * B]
+        n_j, n_i = b[r * B:(r + 1) * B].double(), a[r * B:(r + 1) * B].double()
+        proj = lambda gg, n: gg - n * (gg * n).sum(1, keepdim=True)
+        assert rel_err(proj(g[:B].double().cpu(), n_j), gj) < RTOL_GRAD
+        assert rel_err(proj(g[B:].double().cpu(), n_i), gi) < RTOL_GRAD
