@@ -50,24 +50,26 @@ int molclr_device_info(int* sm_count, int* cc);
  *   rowptr[N+1], col[E] (source of each in-edge), eattr[E] uint8 = type*3+dir: destination-sorted,
  *     in-edges in INPUT order; the self loop is implicit (summed last by the aggregation kernel);
  *   rowptr_t[N+1], col_t[E] (destination of each out-edge): source-sorted transpose for backward;
- *   cnt[N][8] uint16: in-edge counts per bond type (0..4, self loop = type 4) and direction (5..7);
+ *   cnt[N][8] float: in-edge counts per bond type (0..4, self loop = type 4) and direction (5..7), clamped to 2048
+ *     (exact in TF32: they are an operand of the table-gradient contraction);
  *   gptr[G+1], gperm[N]: nodes grouped by graph (identity permutation for sorted `batch`).
  *   status[4]: [0] = error bits (1 node feature, 2 edge endpoint, 4 edge attr, 8 batch id out of
- *              range, 16 degree overflow); [1] = 1 if `batch` was not sorted.
+ *              range, 16 a per-class in-degree above 2048); [1] = 1 if `batch` was not sorted.
  */
 size_t molclr_plan_workspace_bytes(int64_t N, int64_t E, int64_t G);
 int molclr_plan_build(const int64_t* x, const int64_t* edge_index, const int64_t* edge_attr, const int64_t* batch,
                       int64_t N, int64_t E, int64_t G, int32_t* xpacked, int32_t* node2graph, int32_t* rowptr,
-                      int32_t* col, uint8_t* eattr, int32_t* rowptr_t, int32_t* col_t, uint16_t* cnt, int32_t* gptr,
+                      int32_t* col, uint8_t* eattr, int32_t* rowptr_t, int32_t* col_t, float* cnt, int32_t* gptr,
                       int32_t* gperm, void* workspace, size_t workspace_bytes, int32_t* status, cudaStream_t stream);
 
 /* ---- node embedding: ginet_molclr.py:103 / gcn_molclr.py:144 ------------------------------------- */
 int molclr_embed_nodes_fwd(const int32_t* xpacked, const float* E1, const float* E2, int64_t N, int D, float* out,
                            cudaStream_t stream);
-/* dE is ONE buffer [(119+3)][D]: rows 0..118 = grad of x_embedding1, 119..121 = grad of x_embedding2.
- * partials: [molclr_embed_nodes_bwd_blocks(D)][(119+3)*D] floats. */
-int molclr_embed_nodes_bwd_blocks(int D);
-int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, int64_t N, int D, float* dE, float* partials,
+/* dE is ONE buffer [(119+3)][D]: rows 0..118 = grad of x_embedding1, 119..121 = grad of x_embedding2
+ * (= onehot^T . g, a split-K tensor-core contraction; g rows ld_g floats apart).
+ * workspace: molclr_embed_nodes_bwd_workspace_bytes(N) bytes, 16-byte aligned (holds the [N][128] one-hot matrix). */
+size_t molclr_embed_nodes_bwd_workspace_bytes(int64_t N);
+int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, int64_t ld_g, int64_t N, int D, float* dE, void* workspace,
                            cudaStream_t stream);
 
 /* ---- GINE neighbour aggregation: ginet_molclr.py:39-44 + PyG propagate (index_select, add, scatter_add_) ----
@@ -108,9 +110,9 @@ int molclr_bn_apply_fwd(const float* z, const float* bn_coef, int relu, int64_t 
  * epilogue emits for the GIN path, for outputs that do not come from a GEMM. */
 int molclr_bn_tile_stats(const float* z, int64_t N, int D, int T, float* tile_stats, cudaStream_t stream);
 /* Gradients of edge_embedding1/2 (embedding_dense_backward over E' rows in the reference):
- * dB [8][D]: rows 0..4 = d edge_embedding1, rows 5..7 = d edge_embedding2.  partials: [max_blocks][8][D]. */
-int molclr_edge_table_grad(const float* ga, const uint16_t* cnt, int64_t N, int D, float* dB, float* partials,
-                           cudaStream_t stream);
+ * dB [8][D] = cnt^T . ga: rows 0..4 = d edge_embedding1, rows 5..7 = d edge_embedding2 (a split-K tensor-core contraction;
+ * ga rows ld_ga floats apart). */
+int molclr_edge_table_grad(const float* ga, int64_t ld_ga, const float* cnt, int64_t N, int D, float* dB, cudaStream_t stream);
 
 /* out[c] (+)= scale * sum_p partials[p][c], p in increasing order (deterministic). */
 int molclr_reduce_partials(const float* partials, int P, int len, float scale, int accumulate, float* out,

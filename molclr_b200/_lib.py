@@ -43,8 +43,8 @@ SIGNATURES = {
     "molclr_plan_workspace_bytes": (sz, [i64, i64, i64]),
     "molclr_plan_build": (i32, [vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp]),
     "molclr_embed_nodes_fwd": (i32, [vp, vp, vp, i64, i32, vp, vp]),
-    "molclr_embed_nodes_bwd_blocks": (i32, [i32]),
-    "molclr_embed_nodes_bwd": (i32, [vp, vp, i64, i32, vp, vp, vp]),
+    "molclr_embed_nodes_bwd_workspace_bytes": (sz, [i64]),
+    "molclr_embed_nodes_bwd": (i32, [vp, vp, i64, i64, i32, vp, vp, vp]),
     "molclr_gine_aggregate_fwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, i64, i32, vp, i64, i32, vp, vp]),
     "molclr_rowwise_max_blocks": (i32, []),
     "molclr_gine_aggregate_bwd": (i32, [vp, vp, vp, vp, vp, i32, i64, i32, vp, i32, vp, C.POINTER(i32), vp]),
@@ -53,7 +53,7 @@ SIGNATURES = {
     "molclr_row_sum": (i32, [vp, i32, i32, vp, vp]),
     "molclr_bn_apply_fwd": (i32, [vp, vp, i32, i64, i32, vp, vp, i64, vp]),
     "molclr_bn_tile_stats": (i32, [vp, i64, i32, i32, vp, vp]),
-    "molclr_edge_table_grad": (i32, [vp, vp, i64, i32, vp, vp, vp]),
+    "molclr_edge_table_grad": (i32, [vp, i64, vp, i64, i32, vp, vp]),
     "molclr_reduce_partials": (i32, [vp, i32, i32, f32, i32, vp, vp]),
     "molclr_bn_finalize_workspace_bytes": (sz, [i32]),
     "molclr_bn_fwd_finalize": (i32, [vp, i32, i32, i64, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp]),

@@ -100,7 +100,7 @@ __global__ void plan_rows_kernel(const int64_t* __restrict__ ei, const int64_t* 
                                  int64_t N, int64_t E, int64_t G, const int32_t* __restrict__ rowptr,
                                  const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ gptr,
                                  int32_t* col, uint8_t* __restrict__ eattr, int32_t* col_t,
-                                 uint16_t* __restrict__ cnt, int32_t* gperm, int32_t* status) {
+                                 float* __restrict__ cnt, int32_t* gperm, int32_t* status) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t n = i; n < N; n += stride) {
@@ -118,7 +118,7 @@ __global__ void plan_rows_kernel(const int64_t* __restrict__ ei, const int64_t* 
     }
     bool over = false;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { over |= c[k] > 65535; cnt[n * 8 + k] = (uint16_t)min(c[k], 65535); }
+    for (int k = 0; k < 8; ++k) { over |= c[k] > 2048; cnt[n * 8 + k] = (float)min(c[k], 2048); }   // exact in TF32
     if (over) atomicOr(&status[0], ERR_DEGREE);
     b = rowptr_t[n]; e = rowptr_t[n + 1];
     insertion_sort(col_t + b, e - b);
@@ -144,7 +144,7 @@ extern "C" size_t molclr_plan_workspace_bytes(int64_t N, int64_t E, int64_t G) {
 extern "C" int molclr_plan_build(const int64_t* x, const int64_t* edge_index, const int64_t* edge_attr,
                                  const int64_t* batch, int64_t N, int64_t E, int64_t G, int32_t* xpacked,
                                  int32_t* node2graph, int32_t* rowptr, int32_t* col, uint8_t* eattr,
-                                 int32_t* rowptr_t, int32_t* col_t, uint16_t* cnt, int32_t* gptr,
+                                 int32_t* rowptr_t, int32_t* col_t, float* cnt, int32_t* gptr,
                                  int32_t* gperm, void* workspace, size_t workspace_bytes, int32_t* status,
                                  cudaStream_t stream) {
   MOLCLR_REQUIRE(N >= 0 && E >= 0 && G >= 0, "plan_build: negative size");

@@ -6,7 +6,10 @@
 // a row is summed in a fixed order without atomics (deterministic, and bit-exact against the CPU
 // reference order where that matters).  Grids are persistent: (#SM x resident CTAs) blocks that
 // grid-stride over rows.
+#include <cstring>
+
 #include "common.cuh"
+#include "gemm.cuh"
 #include "molclr_b200.h"
 
 namespace molclr {
@@ -55,32 +58,20 @@ __global__ void __launch_bounds__(kRowThreads) embed_nodes_fwd_kernel(
   }
 }
 
-// Backward of the node embedding: dE1[t] = sum_{n: x[n,0]=t} g[n], dE2[c] likewise.  Each block
-// accumulates a private (119+3) x D table in shared memory (spread-address shared atomics), then
-// writes it as one partial; partials are summed in block order by reduce_partials.
-__global__ void __launch_bounds__(512) embed_nodes_bwd_kernel(
-    const int32_t* __restrict__ xpacked, const float* __restrict__ g, int N, int D,
-    float* __restrict__ partials) {
-  extern __shared__ float tab[];                     // [(119+3) * D]
-  const int rows = kNumAtomType + kNumChirality;
-  for (int i = threadIdx.x; i < rows * D; i += blockDim.x) tab[i] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  const int warp = blockIdx.x * wpb + (threadIdx.x >> 5), nwarps = gridDim.x * wpb;
+// Backward of the node embedding: dE1[t] = sum_{n: x[n,0]=t} g[n], dE2[c] likewise, i.e. dE [122][D] = onehot^T [122][N] . g
+// (embedding_dense_backward in the reference).  The one-hot matrix (two ones per row: atom type, 119 + chirality) is
+// written once to a [N][128] fp32 workspace and the contraction runs as a split-K tensor-core GEMM.
+__global__ void __launch_bounds__(256) embed_onehot_kernel(const int32_t* __restrict__ xpacked, int N, float* __restrict__ onehot) {
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
   for (int n = warp; n < N; n += nwarps) {
-    const int xp = xpacked[n];
-    float* t1 = tab + (xp & 0xff) * D;
-    float* t2 = tab + (kNumAtomType + (xp >> 8)) * D;
-    const float* gr = g + (size_t)n * D;
-    for (int f = lane; f < D; f += 32) {
-      const float v = __ldg(gr + f);
-      atomicAdd(t1 + f, v);
-      atomicAdd(t2 + f, v);
-    }
+    const int xp = __ldg(xpacked + n), a = xp & 0xff, c = kNumAtomType + (xp >> 8);
+    const int c0 = 4 * lane;
+    float4 v;
+    v.x = (c0 == a || c0 == c) ? 1.f : 0.f; v.y = (c0 + 1 == a || c0 + 1 == c) ? 1.f : 0.f;
+    v.z = (c0 + 2 == a || c0 + 2 == c) ? 1.f : 0.f; v.w = (c0 + 3 == a || c0 + 3 == c) ? 1.f : 0.f;
+    st_f4(onehot + (size_t)n * 128 + c0, v);
   }
-  __syncthreads();
-  float* dst = partials + (size_t)blockIdx.x * rows * D;
-  for (int i = threadIdx.x; i < rows * D; i += blockDim.x) dst[i] = tab[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -270,42 +261,6 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_bwd_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
-// Bond-embedding table gradients.  dB1[t] = sum_i cnt[i][t] * g_a[i], dB2[d] = sum_i cnt[i][5+d] * g_a[i]
-// where cnt[i][.] counts node i's in-edges per bond type / direction (self loop included), i.e. the
-// E' x D embedding_dense_backward of the reference collapsed to one pass over g_a.
-// ------------------------------------------------------------------------------------------------
-template <int NCH>
-__global__ void __launch_bounds__(kRowThreads) edge_table_grad_kernel(
-    const float* __restrict__ ga, const uint16_t* __restrict__ cnt, int N, int D, float* __restrict__ partials) {
-  extern __shared__ float4 sm4[];            // [kRowWarps][8][D4]
-  const int D4 = D >> 2, lane = threadIdx.x & 31;
-  const int warp = blockIdx.x * kRowWarps + (threadIdx.x >> 5), nwarps = gridDim.x * kRowWarps;
-  float4 acc[8][NCH];
-#pragma unroll
-  for (int k = 0; k < 8; ++k)
-#pragma unroll
-    for (int j = 0; j < NCH; ++j) acc[k][j] = f4_zero();
-  for (int i = warp; i < N; i += nwarps) {
-    const uint4 c = __ldg(reinterpret_cast<const uint4*>(cnt) + i);
-    const float w[8] = {(float)(c.x & 0xffff), (float)(c.x >> 16), (float)(c.y & 0xffff), (float)(c.y >> 16),
-                        (float)(c.z & 0xffff), (float)(c.z >> 16), (float)(c.w & 0xffff), (float)(c.w >> 16)};
-#pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-      const int q = lane + 32 * j;
-      if (q < D4) {
-        const float4 g = ld_stream_f4(ga + (size_t)i * D + 4 * q);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          acc[k][j].x = fmaf(w[k], g.x, acc[k][j].x); acc[k][j].y = fmaf(w[k], g.y, acc[k][j].y);
-          acc[k][j].z = fmaf(w[k], g.z, acc[k][j].z); acc[k][j].w = fmaf(w[k], g.w, acc[k][j].w);
-        }
-      }
-    }
-  }
-  block_reduce_rows<NCH, 8>(acc, sm4, D4, partials);
-}
-
-// ------------------------------------------------------------------------------------------------
 // Deterministic reduction of partial rows:  out[c] (+)= scale * sum_p partials[p][c], p in order.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ partials, int P, int len,
@@ -332,7 +287,19 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __re
 // coefficients the consumers use, and updates the running statistics exactly once.
 //   coef[0]=scale=gamma*invstd  coef[1]=shift=beta-mean*scale  coef[2]=mean  coef[3]=invstd
 // ------------------------------------------------------------------------------------------------
-constexpr int kBnSplits = 32;   // first-level partial merges (one block row each)
+constexpr int kBnSplits = 32;   // first-level partial merges (one block row each) == lanes of the second-level warp
+
+// Chan et al. merge of (n, mean, M2) pairs.  Counts are small exact integers, so the ratio nb/tot is formed in fp32 (the
+// double-precision divide is by far the slowest instruction here); everything else stays in double.
+struct BnAcc { double n, mean, m2; };
+__device__ __forceinline__ void bn_merge(BnAcc& a, double nb, double mb, double qb) {
+  if (nb == 0.0) return;
+  const double tot = a.n + nb, delta = mb - a.mean;
+  const double w = (double)((float)nb / (float)tot);
+  a.mean += delta * w;
+  a.m2 += qb + delta * delta * (a.n * w);
+  a.n = tot;
+}
 
 // Level 1: block (x = 32 columns, y = 16) of split s merges the tiles [s*per, (s+1)*per) into one (n, mean, M2)
 // per column, kept in double: ws[s][3][D].
@@ -342,61 +309,52 @@ __global__ void __launch_bounds__(512) bn_merge_tiles_kernel(
   __shared__ double s_n[16][33], s_mean[16][33], s_m2[16][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int t0 = blockIdx.y * per, t1 = min(T, t0 + per);
-  double n = 0.0, mean = 0.0, m2 = 0.0;
+  BnAcc a = {0.0, 0.0, 0.0};
   if (c < D) {
     for (int t = t0 + threadIdx.y; t < t1; t += 16) {
       const int rows = min(tile_rows, N - t * tile_rows);
       if (rows <= 0) continue;                       // padding groups of the last 128-row GEMM tile
-      const double nb = rows, mb = tile_stats[((size_t)t * 2) * D + c], qb = tile_stats[((size_t)t * 2 + 1) * D + c];
-      const double tot = n + nb, delta = mb - mean;
-      mean += delta * (nb / tot);
-      m2 += qb + delta * delta * (n * nb / tot);
-      n = tot;
+      bn_merge(a, rows, tile_stats[((size_t)t * 2) * D + c], tile_stats[((size_t)t * 2 + 1) * D + c]);
     }
   }
-  s_n[threadIdx.y][threadIdx.x] = n; s_mean[threadIdx.y][threadIdx.x] = mean; s_m2[threadIdx.y][threadIdx.x] = m2;
+  s_n[threadIdx.y][threadIdx.x] = a.n; s_mean[threadIdx.y][threadIdx.x] = a.mean; s_m2[threadIdx.y][threadIdx.x] = a.m2;
   __syncthreads();
   if (threadIdx.y == 0 && c < D) {
-    for (int k = 1; k < 16; ++k) {
-      const double nb = s_n[k][threadIdx.x];
-      if (nb == 0.0) continue;
-      const double tot = n + nb, delta = s_mean[k][threadIdx.x] - mean;
-      mean += delta * (nb / tot);
-      m2 += s_m2[k][threadIdx.x] + delta * delta * (n * nb / tot);
-      n = tot;
-    }
+    for (int k = 1; k < 16; ++k) bn_merge(a, s_n[k][threadIdx.x], s_mean[k][threadIdx.x], s_m2[k][threadIdx.x]);
     double* w = ws + (size_t)blockIdx.y * 3 * D;
-    w[c] = n; w[D + c] = mean; w[2 * D + c] = m2;
+    w[c] = a.n; w[D + c] = a.mean; w[2 * D + c] = a.m2;
   }
 }
 
-// Level 2: merges the S partials of each column, writes the coefficients and updates the running statistics.
-__global__ void __launch_bounds__(128) bn_fwd_finalize_kernel(
+// Level 2: one warp per column; lane s holds partial s, merged by a fixed shuffle tree (deterministic); lane 0 writes the
+// coefficients and updates the running statistics.
+__global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(
     const double* __restrict__ ws /* [S][3][D] */, int S, int D,
     const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean, float* running_var,
     long long* num_batches_tracked, float momentum, float eps, float* __restrict__ coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c < D) {
-    double n = 0.0, mean = 0.0, m2 = 0.0;
-    for (int k = 0; k < S; ++k) {
-      const double nb = ws[(size_t)k * 3 * D + c];
-      if (nb == 0.0) continue;
-      const double tot = n + nb, delta = ws[(size_t)k * 3 * D + D + c] - mean;
-      mean += delta * (nb / tot);
-      m2 += ws[(size_t)k * 3 * D + 2 * D + c] + delta * delta * (n * nb / tot);
-      n = tot;
+    BnAcc a = {0.0, 0.0, 0.0};
+    if (lane < S) { a.n = ws[(size_t)lane * 3 * D + c]; a.mean = ws[(size_t)lane * 3 * D + D + c]; a.m2 = ws[(size_t)lane * 3 * D + 2 * D + c]; }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double nb = __shfl_down_sync(0xffffffffu, a.n, o), mb = __shfl_down_sync(0xffffffffu, a.mean, o),
+                   qb = __shfl_down_sync(0xffffffffu, a.m2, o);
+      if ((lane & (2 * o - 1)) == 0) bn_merge(a, nb, mb, qb);
     }
-    const double var = (n > 0.0) ? m2 / n : 0.0;
-    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float scale = gamma[c] * invstd;
-    coef[c] = scale;
-    coef[D + c] = beta[c] - (float)mean * scale;
-    coef[2 * D + c] = (float)mean;
-    coef[3 * D + c] = invstd;
-    if (running_mean) {
-      const double unbiased = (n > 1.0) ? m2 / (n - 1.0) : var;
-      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    if (lane == 0) {
+      const double var = (a.n > 0.0) ? a.m2 / a.n : 0.0;
+      const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+      const float scale = gamma[c] * invstd;
+      coef[c] = scale;
+      coef[D + c] = beta[c] - (float)a.mean * scale;
+      coef[2 * D + c] = (float)a.mean;
+      coef[3 * D + c] = invstd;
+      if (running_mean) {
+        const double unbiased = (a.n > 1.0) ? a.m2 / (a.n - 1.0) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)a.mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+      }
     }
   }
   if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;
@@ -752,26 +710,29 @@ extern "C" int molclr_reduce_partials(const float* partials, int P, int len, flo
   return 0;
 }
 
-extern "C" int molclr_embed_nodes_bwd_blocks(int D) {
-  (void)D;
-  return sm_count();
-}
+extern "C" size_t molclr_embed_nodes_bwd_workspace_bytes(int64_t N) { return (size_t)N * 128 * sizeof(float); }
 
-extern "C" int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, int64_t N, int D, float* dE, float* partials,
-                                      cudaStream_t stream) {
+extern "C" int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, int64_t ld_g, int64_t N, int D, float* dE,
+                                      void* workspace, cudaStream_t stream) {
   REQUIRE_D(D);
+  MOLCLR_REQUIRE(N > 0 && N < (1ll << 31), "embed_nodes_bwd: N out of range");
+  MOLCLR_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "embed_nodes_bwd: workspace must be 16-byte aligned");
+  float* onehot = reinterpret_cast<float*>(workspace);
+  int blocks = (int)((N + 7) / 8);
+  if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+  embed_onehot_kernel<<<blocks, 256, 0, stream>>>(xpacked, (int)N, onehot);
+  MOLCLR_CHECK_LAUNCH("embed_onehot");
   const int rows = kNumAtomType + kNumChirality;
-  const size_t smem = (size_t)rows * D * sizeof(float);
-  MOLCLR_REQUIRE(smem <= 200 * 1024, "embed_nodes_bwd: D=%d too wide for the shared-memory table", D);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(embed_nodes_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
-  }
-  const int blocks = molclr_embed_nodes_bwd_blocks(D);
-  embed_nodes_bwd_kernel<<<blocks, 512, smem, stream>>>(xpacked, g, (int)N, D, partials);
-  MOLCLR_CHECK_LAUNCH("embed_nodes_bwd");
-  return molclr_reduce_partials(partials, blocks, rows * D, 1.f, 0, dE, stream);
+  GemmJob j;
+  memset(&j, 0, sizeof(j));
+  j.A = onehot; j.lda = 128; j.B = g; j.ldb = ld_g;
+  j.p.M = rows; j.p.N = D; j.p.K = (int)N; j.p.a_mn = 1; j.p.b_mn = 1;
+  j.p.out = dE; j.p.ldo = D; j.p.alpha = 1.f; j.p.epi = EPI_GENERIC;
+  const int tiles = molclr_gemm_tile_count(rows, D, 1), num_kb = (int)((N + 31) / 32);
+  int split = molclr_gemm_workers() / (tiles > 0 ? tiles : 1);
+  if (split > num_kb / 8) split = num_kb / 8;
+  j.split_k = split < 2 ? 2 : split;
+  return gemm_run(j, stream);
 }
 
 static int aggregate_fwd_launch(const float* src, const float* bn_coef, int relu, const int32_t* rowptr, const int32_t* col,
@@ -861,21 +822,23 @@ extern "C" int molclr_relu_bn_bwd_stats(const float* g, const float* z_prev, con
   return aggregate_bwd_launch(g, nullptr, nullptr, false, z_prev, bn_coef, relu, N, D, gy, 0, partials, num_partials, stream);
 }
 
-extern "C" int molclr_edge_table_grad(const float* ga, const uint16_t* cnt, int64_t N, int D, float* dB /* [8][D]: 5 type rows then 3 direction rows */,
-                                      float* partials, cudaStream_t stream) {
+// Bond-embedding table gradients: dB1[t] = sum_i cnt[i][t] * g_a[i], dB2[d] = sum_i cnt[i][5+d] * g_a[i], where cnt[i][.]
+// counts node i's in-edges per bond type / direction (self loop included) -- the E' x D embedding_dense_backward of the
+// reference collapsed to dB [8][D] = cnt^T [8][N] . g_a [N][D], which is a skinny split-K contraction: it runs
+// on the tensor-core GEMM (both operands consumed MN-major in place; counts <= 2048 are exact in TF32).
+extern "C" int molclr_edge_table_grad(const float* ga, int64_t ld_ga, const float* cnt, int64_t N, int D, float* dB, cudaStream_t stream) {
   REQUIRE_D(D);
-  const size_t smem = (size_t)kRowWarps * 8 * D * sizeof(float);
-  int grid = 1;
-  NCH_DISPATCH(D / 4, {
-    auto k = edge_table_grad_kernel<NCH>;
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_set = true; }
-    MOLCLR_REQUIRE(smem <= 160 * 1024, "edge_table_grad: D too wide");
-    grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N > 0 ? N : 1);
-    k<<<grid, kRowThreads, smem, stream>>>(ga, cnt, (int)N, D, partials);
-  });
-  MOLCLR_CHECK_LAUNCH("edge_table_grad");
-  return molclr_reduce_partials(partials, grid, 8 * D, 1.f, 0, dB, stream);
+  MOLCLR_REQUIRE(N > 0 && N < (1ll << 31), "edge_table_grad: N out of range");
+  GemmJob j;
+  memset(&j, 0, sizeof(j));
+  j.A = cnt; j.lda = 8; j.B = ga; j.ldb = ld_ga;
+  j.p.M = 8; j.p.N = D; j.p.K = (int)N; j.p.a_mn = 1; j.p.b_mn = 1;
+  j.p.out = dB; j.p.ldo = D; j.p.alpha = 1.f; j.p.epi = EPI_GENERIC;
+  const int tiles = molclr_gemm_tile_count(8, D, 1), num_kb = (int)((N + 31) / 32);
+  int split = molclr_gemm_workers() / (tiles > 0 ? tiles : 1);
+  if (split > num_kb / 8) split = num_kb / 8;
+  j.split_k = split < 2 ? 2 : split;          // >= 2 selects the zero-initialised atomic accumulation path
+  return gemm_run(j, stream);
 }
 
 extern "C" size_t molclr_bn_finalize_workspace_bytes(int D) { return (size_t)kBnSplits * 3 * D * sizeof(double); }
@@ -892,7 +855,7 @@ extern "C" int molclr_bn_fwd_finalize(const float* tile_stats, int T, int tile_r
   double* ws = reinterpret_cast<double*>(workspace);
   bn_merge_tiles_kernel<<<dim3((D + 31) / 32, S), dim3(32, 16), 0, stream>>>(tile_stats, T, tile_rows, (int)N, D, per, ws);
   MOLCLR_CHECK_LAUNCH("bn_merge_tiles");
-  bn_fwd_finalize_kernel<<<(D + 127) / 128, 128, 0, stream>>>(ws, S, D, gamma, beta, running_mean, running_var,
+  bn_fwd_finalize_kernel<<<(D + 7) / 8, 256, 0, stream>>>(ws, S, D, gamma, beta, running_mean, running_var,
                                                               reinterpret_cast<long long*>(num_batches_tracked), momentum, eps, coef);
   MOLCLR_CHECK_LAUNCH("bn_fwd_finalize");
   return 0;

@@ -12,7 +12,7 @@ from ._lib import check, ptr, stream
 
 _ERR_BITS = {1: "node feature out of range (atom type must be < 119, chirality < 3; ginet_molclr.py:9-10)",
              2: "edge_index endpoint out of range", 4: "edge_attr out of range (bond type < 5, direction < 3)",
-             8: "batch id out of range", 16: "node in-degree above 65535"}
+             8: "batch id out of range", 16: "a per-class node in-degree above 2048"}
 
 
 def _al(n, a=4):
@@ -41,7 +41,7 @@ class GraphPlan:
         lib = _lib.load()
         ws_bytes = lib.molclr_plan_workspace_bytes(N, E, G)
         # one allocation, carved into 16-byte aligned int32 views
-        sizes = [_al(N), _al(N), _al(N + 1), _al(E), _al((E + 3) // 4), _al(N + 1), _al(E), _al(4 * N), _al(G + 1), _al(N),
+        sizes = [_al(N), _al(N), _al(N + 1), _al(E), _al((E + 3) // 4), _al(N + 1), _al(E), _al(8 * N), _al(G + 1), _al(N),
                  _al((ws_bytes + 3) // 4), 4]
         buf = torch.empty(sum(sizes), dtype=torch.int32, device=x.device)
         views, off = [], 0
@@ -50,13 +50,13 @@ class GraphPlan:
         (self.xpacked, self.node2graph, self.rowptr, self.col, eattr32, self.rowptr_t, self.col_t, cnt32, self.gptr,
          self.gperm, ws, self.status) = views
         self.eattr = eattr32.view(torch.uint8)
-        self.cnt = cnt32.view(torch.uint16)
+        self.cnt = cnt32.view(torch.float32)
         self._buf = buf
         x, ei, ea, batch = x.contiguous(), ei.contiguous(), ea.contiguous(), batch.contiguous()
         check(lib.molclr_plan_build(ptr(x, torch.int64), ptr(ei, torch.int64), ptr(ea, torch.int64), ptr(batch, torch.int64),
                                     N, E, G, ptr(self.xpacked, torch.int32), ptr(self.node2graph, torch.int32),
                                     ptr(self.rowptr, torch.int32), ptr(self.col, torch.int32), ptr(self.eattr, torch.uint8),
-                                    ptr(self.rowptr_t, torch.int32), ptr(self.col_t, torch.int32), ptr(self.cnt, torch.uint16),
+                                    ptr(self.rowptr_t, torch.int32), ptr(self.col_t, torch.int32), ptr(self.cnt),
                                     ptr(self.gptr, torch.int32), ptr(self.gperm, torch.int32), ptr(ws, torch.int32), ws_bytes,
                                     ptr(self.status, torch.int32), stream()), "plan_build")
         self._checked = False

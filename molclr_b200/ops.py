@@ -141,8 +141,8 @@ def embed_nodes_bwd(plan, g):
     lib = _lib.load()
     D = g.shape[1]
     dE = _empty(119 + 3, D, device=g.device)
-    partials = _empty(lib.molclr_embed_nodes_bwd_blocks(D), (119 + 3) * D, device=g.device)
-    check(lib.molclr_embed_nodes_bwd(ptr(plan.xpacked, torch.int32), ptr(g), plan.N, D, ptr(dE), ptr(partials), stream()),
+    ws = torch.empty(lib.molclr_embed_nodes_bwd_workspace_bytes(plan.N) // 4, dtype=F32, device=g.device)
+    check(lib.molclr_embed_nodes_bwd(ptr(plan.xpacked, torch.int32), ptr2d(g), g.stride(0), plan.N, D, ptr(dE), ptr(ws), stream()),
           "embed_nodes_bwd")
     return dE[:119], dE[119:]
 
@@ -221,9 +221,7 @@ def edge_table_grad_raw(plan, ga):
     """dB [8, D]: rows 0..4 = gradient of the bond-type table, rows 5..7 = of the bond-direction table."""
     D = ga.shape[1]
     dB = _empty(8, D, device=ga.device)
-    partials = _empty(max_blocks(), 8 * D, device=ga.device)
-    check(_lib.load().molclr_edge_table_grad(ptr(ga), ptr(plan.cnt, torch.uint16), plan.N, D, ptr(dB), ptr(partials), stream()),
-          "edge_table_grad")
+    check(_lib.load().molclr_edge_table_grad(ptr2d(ga), ga.stride(0), ptr(plan.cnt), plan.N, D, ptr(dB), stream()), "edge_table_grad")
     return dB
 
 
