@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmolclr_b200.so")
+LIB_PATH = os.environ.get("MOLCLR_B200_LIB") or os.path.join(_HERE, "libmolclr_b200.so")   # (override: A/B timing of builds)
 
 vp, i64, i32, f32, sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
 
