@@ -194,6 +194,12 @@ int molclr_round_tf32(const float* src, float* hi, float* lo, int64_t n, cudaStr
  * operands be stored with 128-byte aligned rows, which TMA streams markedly faster */
 int molclr_round_tf32_2d(const float* src, int64_t ld_src, float* hi, float* lo, int64_t ld_dst, int64_t rows, int64_t cols,
                          cudaStream_t stream);
+/* device-to-device 2-D copy (byte pitches / width): pads the 2- or 1-row output layer of the fine-tune head to 4 rows */
+int molclr_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t height, cudaStream_t stream);
+/* activations of the fine-tune prediction head (ginet_finetune.py:96-127): mode 0 = Softplus (beta 1, threshold 20), 1 = ReLU.
+ * forward: hi = tf32(act(x)), lo (optional) = tf32 residual; backward: gx = tf32(gy * act'(x)). */
+int molclr_act_fwd(const float* x, int mode, int64_t n, float* hi, float* lo, cudaStream_t stream);
+int molclr_act_bwd(const float* gy, const float* x, int mode, int64_t n, float* gx, cudaStream_t stream);
 /* F.normalize(z, dim=1), molclr.py:63-64 (eps 1e-12) and its backward */
 int molclr_l2_normalize_fwd(const float* z, int64_t R, int C, float eps, float* y, float* inv_norm, cudaStream_t stream);
 int molclr_l2_normalize_bwd(const float* gy, const float* y, const float* inv_norm, int64_t R, int C, float eps, float* gz,

@@ -70,6 +70,9 @@ SIGNATURES = {
     "molclr_gemm_tf32": (i32, [C.POINTER(GemmArgs), vp]),
     "molclr_round_tf32": (i32, [vp, vp, vp, i64, vp]),
     "molclr_round_tf32_2d": (i32, [vp, i64, vp, vp, i64, i64, i64, vp]),
+    "molclr_copy_2d": (i32, [vp, sz, vp, sz, sz, sz, vp]),
+    "molclr_act_fwd": (i32, [vp, i32, i64, vp, vp, vp]),
+    "molclr_act_bwd": (i32, [vp, vp, i32, i64, vp, vp]),
     "molclr_l2_normalize_fwd": (i32, [vp, i64, i32, f32, vp, vp, vp]),
     "molclr_l2_normalize_bwd": (i32, [vp, vp, vp, i64, i32, f32, vp, vp]),
     "molclr_ntxent_workspace_bytes": (sz, [i64, i64, i32]),

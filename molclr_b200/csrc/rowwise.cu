@@ -677,6 +677,28 @@ __global__ void row_sum_kernel(const float* __restrict__ in, int R, int C, float
 }
 
 // ------------------------------------------------------------------------------------------------
+// Activations of the fine-tune prediction head (ginet_finetune.py:96-127): mode 0 = Softplus (torch defaults beta 1,
+// threshold 20), mode 1 = ReLU.  Forward writes the result as a tensor-core operand pair; backward writes the rounded
+// gradient (it only ever feeds GEMMs).
+// ------------------------------------------------------------------------------------------------
+__global__ void act_fwd_kernel(const float* __restrict__ x, int mode, int64_t n, float* __restrict__ hi, float* __restrict__ lo) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const float y = mode == 0 ? (v > 20.f ? v : log1pf(expf(v))) : fmaxf(v, 0.f);
+    const float h = round_tf32(y);
+    hi[i] = h;
+    if (lo) lo[i] = round_tf32(y - h);
+  }
+}
+__global__ void act_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, int mode, int64_t n, float* __restrict__ gx) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const float d = mode == 0 ? (v > 20.f ? 1.f : 1.f / (1.f + expf(-v))) : (v > 0.f ? 1.f : 0.f);
+    gx[i] = round_tf32(gy[i] * d);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Small elementwise helpers
 // ------------------------------------------------------------------------------------------------
 __global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
@@ -1008,6 +1030,34 @@ extern "C" int molclr_row_sum(const float* in, int R, int C, float* out, cudaStr
   if (R == 0) return 0;
   row_sum_kernel<<<(R + 7) / 8, 256, 0, stream>>>(in, R, C, out);
   MOLCLR_CHECK_LAUNCH("row_sum");
+  return 0;
+}
+
+extern "C" int molclr_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t height,
+                              cudaStream_t stream) {
+  if (width_bytes == 0 || height == 0) return 0;
+  cudaError_t e = cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, height, cudaMemcpyDeviceToDevice, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "copy_2d");
+  return 0;
+}
+
+extern "C" int molclr_act_fwd(const float* x, int mode, int64_t n, float* hi, float* lo, cudaStream_t stream) {
+  MOLCLR_REQUIRE(mode == 0 || mode == 1, "act_fwd: mode %d (0 = softplus, 1 = relu)", mode);
+  if (n == 0) return 0;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  act_fwd_kernel<<<(int)blocks, 256, 0, stream>>>(x, mode, n, hi, lo);
+  MOLCLR_CHECK_LAUNCH("act_fwd");
+  return 0;
+}
+
+extern "C" int molclr_act_bwd(const float* gy, const float* x, int mode, int64_t n, float* gx, cudaStream_t stream) {
+  MOLCLR_REQUIRE(mode == 0 || mode == 1, "act_bwd: mode %d (0 = softplus, 1 = relu)", mode);
+  if (n == 0) return 0;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  act_bwd_kernel<<<(int)blocks, 256, 0, stream>>>(gy, x, mode, n, gx);
+  MOLCLR_CHECK_LAUNCH("act_bwd");
   return 0;
 }
 

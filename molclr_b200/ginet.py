@@ -175,51 +175,101 @@ def _head_backward(m, p, saved, g_h, g_out):
     return g_p, (dWf, dbf, dW0, db0, dW2, db2)
 
 
+def _encoder_forward(m, plan, comp, training, pool_mode):
+    """Node embedding -> L x (aggregate, MLP, BatchNorm statistics) -> pooled graph vectors (ginet_molclr.py:103-113).
+    Returns (p, p_lo, layers): the pooled operand pair and the per-layer tensors the backward needs."""
+    L, D, H, N = m.num_layer, m.emb_dim, 2 * m.emb_dim, plan.N
+    dev = m.x_embedding1.weight.device
+    rw = m._rounded
+    h0 = ops.embed_nodes_fwd(plan, m.x_embedding1.weight.detach(), m.x_embedding2.weight.detach())
+    src, coef_prev = h0, None
+    layers = []
+    T = ops.colstat_tiles(N)
+    for l in range(L):
+        g, bn = m.gnns[l], m.batch_norms[l]
+        a, a_lo = ops.gine_aggregate_fwd(plan, src, g.edge_embedding1.weight.detach(), g.edge_embedding2.weight.detach(),
+                                         bn_coef=coef_prev, relu=True, round_out=True, want_lo=True) if comp else \
+            (ops.gine_aggregate_fwd(plan, src, g.edge_embedding1.weight.detach(), g.edge_embedding2.weight.detach(),
+                                    bn_coef=coef_prev, relu=True, round_out=True), None)
+        (W1, W1_lo), (W2, W2_lo) = rw.get(g.mlp[0].weight), rw.get(g.mlp[2].weight)
+        u = ops.padded(N, H, dev)
+        u_lo = ops.padded(N, H, dev) if comp else None
+        ubits = ops.relu_bits_buffer(N, H, dev)       # [u > 0] as bits: the backward GEMM's mask (8 MB instead of 246)
+        ops.gemm(a, W1, N, H, D, A_lo=a_lo, B_lo=_lo(W1_lo, comp), out=u, out_lo=u_lo, bias=g.mlp[0].bias.detach(),
+                 relu=True, round_out=True, relu_bits=ubits)
+        z = torch.empty(N, D, device=dev)
+        if training:
+            stats = torch.empty(T, 2, D, device=dev)
+            ops.gemm(u, W2, N, D, H, A_lo=u_lo, B_lo=_lo(W2_lo, comp), out=z, bias=g.mlp[2].bias.detach(), colstat=stats,
+                     colstat_mode=2)
+            momentum = 0.1 if bn.momentum is None else bn.momentum
+            coef = ops.bn_fwd_finalize(stats, T, N, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
+                                       bn.num_batches_tracked, momentum, bn.eps)
+        else:
+            ops.gemm(u, W2, N, D, H, A_lo=u_lo, B_lo=_lo(W2_lo, comp), out=z, bias=g.mlp[2].bias.detach())
+            coef = ops.bn_eval_coef(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
+        layers.append((a, u, z, coef, W1, W2, ubits))
+        src, coef_prev = z, coef
+        del a_lo, u_lo
+    p, p_lo = ops.pool_fwd(plan, src, coef_prev, pool_mode, relu=False, round_out=True, want_lo=True) if comp else \
+        (ops.pool_fwd(plan, src, coef_prev, pool_mode, relu=False, round_out=True), None)
+    return p, p_lo, layers
+
+
+def _encoder_backward(m, plan, layers, g_p, training, pool_mode):
+    """Backward of ``_encoder_forward`` given the gradient of the pooled vectors.  Returns the gradients of
+    [x_embedding1, x_embedding2] + per layer [mlp0.w, mlp0.b, mlp2.w, mlp2.b, edge_emb1, edge_emb2, bn.w, bn.b]."""
+    L, D, H, N = m.num_layer, m.emb_dim, 2 * m.emb_dim, plan.N
+    dev = g_p.device
+    grads = [None] * (2 + 8 * L)
+    # last layer: BatchNorm backward fed by the pool backward (g_y is never materialised)
+    a, u, z, coef, W1, W2, ubits = layers[L - 1]
+    bn = m.batch_norms[L - 1]
+    partials, P = ops.pool_bwd_stats(plan, g_p, z, coef, pool_mode)
+    dgamma, dbeta, bcoef = ops.bn_bwd_finalize(partials, P, N, bn.weight.detach(), coef, training)
+    g_z, db2 = ops.bn_bwd_apply(z, bcoef, gp=g_p, plan=plan, pool_mean=pool_mode == 0)
+    T = ops.colstat_tiles(N)
+    for l in range(L - 1, -1, -1):
+        a, u, z, coef, W1, W2, ubits = layers[l]
+        base = 2 + 8 * l
+        grads[base + 6], grads[base + 7], grads[base + 3] = dgamma, dbeta, db2
+        # g_u = (g_z W2) * [u > 0];  db1 = colsum(g_u)
+        g_u = ops.padded(N, H, dev)
+        part = torch.empty(T, H, device=dev)
+        ops.gemm(g_z, W2, N, H, D, b_mn=True, out=g_u, mask_bits=ubits, round_out=True, colstat=part, colstat_mode=1)
+        grads[base + 1] = ops.reduce_partials(part, T, H, torch.empty(H, device=dev))
+        grads[base + 2] = ops.gemm_dw(g_z, u)                 # dW2 [D, H]
+        g_a = torch.empty(N, D, device=dev)
+        ops.gemm(g_u, W1, N, D, H, b_mn=True, out=g_a)
+        grads[base + 0] = ops.gemm_dw(g_u, a)                 # dW1 [H, D]
+        grads[base + 4], grads[base + 5] = ops.edge_table_grad(plan, g_a)
+        if l > 0:
+            _, _, zp, coefp, _, _, _ = layers[l - 1]
+            bnp = m.batch_norms[l - 1]
+            g_y, partials, P = ops.gine_aggregate_bwd(plan, g_a, z_prev=zp, bn_coef=coefp, relu=True)
+            dgamma, dbeta, bcoef = ops.bn_bwd_finalize(partials, P, N, bnp.weight.detach(), coefp, training)
+            g_z, db2 = ops.bn_bwd_apply(zp, bcoef, gy=g_y)
+        else:
+            g_h0, _, _ = ops.gine_aggregate_bwd(plan, g_a)
+            grads[0], grads[1] = ops.embed_nodes_bwd(plan, g_h0)
+    return grads
+
+
+def _check_precision(m):
+    if m.precision not in PRECISIONS:
+        raise ValueError(f"molclr_b200: precision must be one of {PRECISIONS}, got {m.precision!r}")
+    return m.precision == "tf32x3"
+
+
 class _GINetFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, m, plan, *params):
-        L, D, H, N = m.num_layer, m.emb_dim, 2 * m.emb_dim, plan.N
-        dev = params[0].device
-        rw = m._rounded
-        if m.precision not in PRECISIONS:
-            raise ValueError(f"molclr_b200: precision must be one of {PRECISIONS}, got {m.precision!r}")
-        comp = m.precision == "tf32x3"
+        comp = _check_precision(m)
         training = m.training
         pool_mode = ops.POOL_MODES[m.pool_name]
-        h0 = ops.embed_nodes_fwd(plan, m.x_embedding1.weight.detach(), m.x_embedding2.weight.detach())
-        src, coef_prev = h0, None
-        layers = []
-        T = ops.colstat_tiles(N)
-        for l in range(L):
-            g, bn = m.gnns[l], m.batch_norms[l]
-            a, a_lo = ops.gine_aggregate_fwd(plan, src, g.edge_embedding1.weight.detach(), g.edge_embedding2.weight.detach(),
-                                             bn_coef=coef_prev, relu=True, round_out=True, want_lo=True) if comp else \
-                (ops.gine_aggregate_fwd(plan, src, g.edge_embedding1.weight.detach(), g.edge_embedding2.weight.detach(),
-                                        bn_coef=coef_prev, relu=True, round_out=True), None)
-            (W1, W1_lo), (W2, W2_lo) = rw.get(g.mlp[0].weight), rw.get(g.mlp[2].weight)
-            u = ops.padded(N, H, dev)
-            u_lo = ops.padded(N, H, dev) if comp else None
-            ubits = ops.relu_bits_buffer(N, H, dev)       # [u > 0] as bits: the backward GEMM's mask (8 MB instead of 246)
-            ops.gemm(a, W1, N, H, D, A_lo=a_lo, B_lo=_lo(W1_lo, comp), out=u, out_lo=u_lo, bias=g.mlp[0].bias.detach(),
-                     relu=True, round_out=True, relu_bits=ubits)
-            z = torch.empty(N, D, device=dev)
-            if training:
-                stats = torch.empty(T, 2, D, device=dev)
-                ops.gemm(u, W2, N, D, H, A_lo=u_lo, B_lo=_lo(W2_lo, comp), out=z, bias=g.mlp[2].bias.detach(), colstat=stats,
-                         colstat_mode=2)
-                momentum = 0.1 if bn.momentum is None else bn.momentum
-                coef = ops.bn_fwd_finalize(stats, T, N, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
-                                           bn.num_batches_tracked, momentum, bn.eps)
-            else:
-                ops.gemm(u, W2, N, D, H, A_lo=u_lo, B_lo=_lo(W2_lo, comp), out=z, bias=g.mlp[2].bias.detach())
-                coef = ops.bn_eval_coef(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
-            layers.append((a, u, z, coef, W1, W2, ubits))
-            src, coef_prev = z, coef
-            del a_lo, u_lo
-        p, p_lo = ops.pool_fwd(plan, src, coef_prev, pool_mode, relu=False, round_out=True, want_lo=True) if comp else \
-            (ops.pool_fwd(plan, src, coef_prev, pool_mode, relu=False, round_out=True), None)
-        h, out, head_saved = _head_forward(m, p, p_lo, rw, comp)
+        p, p_lo, layers = _encoder_forward(m, plan, comp, training, pool_mode)
+        h, out, head_saved = _head_forward(m, p, p_lo, m._rounded, comp)
         ctx.m, ctx.plan, ctx.layers, ctx.p, ctx.head_saved = m, plan, layers, p, head_saved
         ctx.training, ctx.pool_mode = training, pool_mode
         return h, out
@@ -227,42 +277,9 @@ class _GINetFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_h, g_out):
         m, plan, layers, p = ctx.m, ctx.plan, ctx.layers, ctx.p
-        L, D, H, N = m.num_layer, m.emb_dim, 2 * m.emb_dim, plan.N
-        dev = p.device
         if g_out is None:
-            g_out = torch.zeros(p.shape[0], m.feat_dim // 2, device=dev)
+            g_out = torch.zeros(p.shape[0], m.feat_dim // 2, device=p.device)
         g_p, head_grads = _head_backward(m, p, ctx.head_saved, g_h, g_out)
-        pool_mean = ctx.pool_mode == 0
-        grads = [None] * (2 + 8 * L)
-        # last layer: BatchNorm backward fed by the pool backward (g_y is never materialised)
-        a, u, z, coef, W1, W2, ubits = layers[L - 1]
-        bn = m.batch_norms[L - 1]
-        partials, P = ops.pool_bwd_stats(plan, g_p, z, coef, ctx.pool_mode)
-        dgamma, dbeta, bcoef = ops.bn_bwd_finalize(partials, P, N, bn.weight.detach(), coef, ctx.training)
-        g_z, db2 = ops.bn_bwd_apply(z, bcoef, gp=g_p, plan=plan, pool_mean=pool_mean)
-        T = ops.colstat_tiles(N)
-        for l in range(L - 1, -1, -1):
-            a, u, z, coef, W1, W2, ubits = layers[l]
-            base = 2 + 8 * l
-            grads[base + 6], grads[base + 7], grads[base + 3] = dgamma, dbeta, db2
-            # g_u = (g_z W2) * [u > 0];  db1 = colsum(g_u)
-            g_u = ops.padded(N, H, dev)
-            part = torch.empty(T, H, device=dev)
-            ops.gemm(g_z, W2, N, H, D, b_mn=True, out=g_u, mask_bits=ubits, round_out=True, colstat=part, colstat_mode=1)
-            grads[base + 1] = ops.reduce_partials(part, T, H, torch.empty(H, device=dev))
-            grads[base + 2] = ops.gemm_dw(g_z, u)                 # dW2 [D, H]
-            g_a = torch.empty(N, D, device=dev)
-            ops.gemm(g_u, W1, N, D, H, b_mn=True, out=g_a)
-            grads[base + 0] = ops.gemm_dw(g_u, a)                 # dW1 [H, D]
-            grads[base + 4], grads[base + 5] = ops.edge_table_grad(plan, g_a)
-            if l > 0:
-                _, _, zp, coefp, _, _, _ = layers[l - 1]
-                bnp = m.batch_norms[l - 1]
-                g_y, partials, P = ops.gine_aggregate_bwd(plan, g_a, z_prev=zp, bn_coef=coefp, relu=True)
-                dgamma, dbeta, bcoef = ops.bn_bwd_finalize(partials, P, N, bnp.weight.detach(), coefp, ctx.training)
-                g_z, db2 = ops.bn_bwd_apply(zp, bcoef, gy=g_y)
-            else:
-                g_h0, _, _ = ops.gine_aggregate_bwd(plan, g_a)
-                grads[0], grads[1] = ops.embed_nodes_bwd(plan, g_h0)
+        grads = _encoder_backward(m, plan, layers, g_p, ctx.training, ctx.pool_mode)
         ctx.layers = None
         return (None, None, *grads, *head_grads)

@@ -290,6 +290,39 @@ def pool_bwd_stats(plan, gp, z, bn_coef, pool_mode):
     return partials, n.value
 
 
+def copy_rows(src, dst, rows):
+    """dst[:rows, :cols] = src[:rows, :cols] (2-D fp32, contiguous rows): tiny pad/unpad copies via cudaMemcpy2DAsync."""
+    import ctypes as _C
+    cols = src.shape[1]
+    _cudart_memcpy2d(dst.data_ptr(), dst.stride(0) * 4, src.data_ptr(), src.stride(0) * 4, cols * 4, rows)
+
+
+def copy_cols(src, dst, cols):
+    """dst[:, :cols] = src[:, :cols]."""
+    _cudart_memcpy2d(dst.data_ptr(), dst.stride(0) * 4, src.data_ptr(), src.stride(0) * 4, cols * 4, src.shape[0])
+
+
+def _cudart_memcpy2d(dst, dpitch, src, spitch, width, height):
+    check(_lib.load().molclr_copy_2d(dst, dpitch, src, spitch, width, height, stream()), "copy_2d")
+
+
+ACT_MODES = {"softplus": 0, "relu": 1}
+
+
+def act_fwd(x, mode, want_lo):
+    """(hi, lo) tensor-core operand pair of act(x) for a contiguous 2-D x whose width is a multiple of 32."""
+    hi = torch.empty_like(x)
+    lo = torch.empty_like(x) if want_lo else None
+    check(_lib.load().molclr_act_fwd(ptr(x), mode, x.numel(), ptr(hi), ptr(lo), stream()), "act_fwd")
+    return hi, lo
+
+
+def act_bwd(gy, x, mode):
+    gx = torch.empty_like(x)
+    check(_lib.load().molclr_act_bwd(ptr(gy), ptr(x), mode, x.numel(), ptr(gx), stream()), "act_bwd")
+    return gx
+
+
 # ------------------------------------------------------------------------------------------- normalize / NT-Xent
 def l2_normalize_fwd(z, eps):
     R, Cc = z.shape

@@ -222,3 +222,44 @@ class GCN(nn.Module):
         h = self.feat_lin(h)
         out = self.out_lin(h)
         return h, out
+
+
+# ----------------------------------------------------------------------------- fine-tune GINet
+class GINetFinetune(nn.Module):
+    """models/ginet_finetune.py:52-147: the same GIN-E encoder, ``feat_lin`` and the ``pred_head`` MLP; returns
+    ``(h, pred_head(h))``."""
+
+    def __init__(self, task="classification", num_layer=5, emb_dim=300, feat_dim=512, drop_ratio=0, pool="mean",
+                 pred_n_layer=2, pred_act="softplus"):
+        super().__init__()
+        self.num_layer, self.emb_dim, self.feat_dim, self.drop_ratio, self.task = num_layer, emb_dim, feat_dim, drop_ratio, task
+        self.x_embedding1 = nn.Embedding(num_atom_type, emb_dim)
+        self.x_embedding2 = nn.Embedding(num_chirality_tag, emb_dim)
+        nn.init.xavier_uniform_(self.x_embedding1.weight.data)
+        nn.init.xavier_uniform_(self.x_embedding2.weight.data)
+        self.gnns = nn.ModuleList([GINEConv(emb_dim) for _ in range(num_layer)])
+        self.batch_norms = nn.ModuleList([nn.BatchNorm1d(emb_dim) for _ in range(num_layer)])
+        if pool in _POOLS:
+            self.pool = _POOLS[pool]
+        self.feat_lin = nn.Linear(emb_dim, feat_dim)
+        out_dim = {"classification": 2, "regression": 1}[task]                      # ginet_finetune.py:96-99
+        self.pred_n_layer = max(1, pred_n_layer)
+        act = {"relu": lambda: nn.ReLU(inplace=True), "softplus": nn.Softplus}[pred_act]   # ginet_finetune.py:103-124
+        head = [nn.Linear(feat_dim, feat_dim // 2), act()]
+        for _ in range(self.pred_n_layer - 1):
+            head.extend([nn.Linear(feat_dim // 2, feat_dim // 2), act()])
+        head.append(nn.Linear(feat_dim // 2, out_dim))
+        self.pred_head = nn.Sequential(*head)
+
+    def forward(self, data):
+        h = self.x_embedding1(data.x[:, 0]) + self.x_embedding2(data.x[:, 1])
+        for layer in range(self.num_layer):                                         # ginet_finetune.py:136-142
+            h = self.gnns[layer](h, data.edge_index, data.edge_attr)
+            h = self.batch_norms[layer](h)
+            if layer == self.num_layer - 1:
+                h = F.dropout(h, self.drop_ratio, training=self.training)
+            else:
+                h = F.dropout(F.relu(h), self.drop_ratio, training=self.training)
+        h = self.pool(h, data.batch)
+        h = self.feat_lin(h)
+        return h, self.pred_head(h)
