@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--local-negatives", action="store_true", help="N>1: NT-Xent over the local batch only")
+    ap.add_argument("--model", default="gin", choices=["gin", "gcn"], help="gin = BASELINE configs 1/2/5 (headline), gcn = config 3")
     return ap.parse_args()
 
 
@@ -133,7 +134,7 @@ def batch_bytes(b):
 
 def run_ours(args):
     import torch.distributed as dist
-    from molclr_b200 import Batch, GINet, NTXentLoss, _lib, ops, pretrain_loss
+    from molclr_b200 import Batch, GCN, GINet, NTXentLoss, _lib, ops, pretrain_loss
     from molclr_b200.synth import make_pair_batch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -147,7 +148,7 @@ def run_ours(args):
     B = args.batch
 
     torch.manual_seed(0)
-    model = GINet(5, 300, 512, 0, "mean").to(dev)
+    model = (GINet if args.model == "gin" else GCN)(5, 300, 512, 0, "mean").to(dev)
     model.precision = args.precision
     if world > 1:
         from molclr_b200.dist import DataParallelStep
@@ -236,8 +237,7 @@ def run_ours(args):
         times.append((a, b, plan.N, plan.E))
         return out
     ops.gine_aggregate_fwd = timed_aggregate
-    import molclr_b200.ginet as _g
-    for i in range(3):
+    for i in range(3 if args.model == "gin" else 0):
         step(*resident[i % NB])
     torch.cuda.synchronize()
     ops.gine_aggregate_fwd = orig
@@ -247,15 +247,18 @@ def run_ours(args):
     # CSR rowptr/col/eattr, BN coefficients and bond tables
     def alg_bytes(N, E):
         return 4 * D * N + (2 if comp else 1) * 4 * D * N + 4 * (N + 1) + 5 * E + 4 * D * (2 + 8)
-    agg_ms = sum(a.elapsed_time(b) for a, b, _, _ in times) / len(times)
-    agg_bytes = sum(alg_bytes(N, E) for _, _, N, E in times) / len(times)
     peak, peak_src = peaks()
-    achieved = agg_bytes / (agg_ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "gine_aggregate_fwd_kernel<3,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "us_per_launch": agg_ms * 1e3,
-            "algorithmic_bytes_per_launch": agg_bytes, "launches_timed": len(times)}
+    if times:
+        agg_ms = sum(a.elapsed_time(b) for a, b, _, _ in times) / len(times)
+        agg_bytes = sum(alg_bytes(N, E) for _, _, N, E in times) / len(times)
+        achieved = agg_bytes / (agg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "gine_aggregate_fwd_kernel<3,true,false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "us_per_launch": agg_ms * 1e3,
+                "algorithmic_bytes_per_launch": agg_bytes, "launches_timed": len(times)}
+    else:
+        roof = None
     ncu_traffic = os.path.join(ROOT, "profiles", "aggregate_traffic.json")
-    if os.path.exists(ncu_traffic):
+    if roof is not None and os.path.exists(ncu_traffic):
         try:
             roof["traffic"] = json.load(open(ncu_traffic))["dram_bytes_per_launch"]
         except Exception:
@@ -265,9 +268,10 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    line = {"metric": METRIC, "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": METRIC if args.model == "gin" else METRIC.replace("GIN", "GCN"), "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "precision": args.precision,
+            "config": {"workload": WORKLOAD if args.model == "gin" else WORKLOAD.replace("GIN-5", "GCN-5 (un-normalised GCNConv as the reference computes it)"),
+                       "batch_per_gpu": B, "global_batch": B * world, "precision": args.precision,
                        "parallelism": f"dp{world}" + ("" if world == 1 else ("-localneg" if args.local_negatives else "-globalneg")),
                        "l2": "no flush: per-step working set (~5 GB of activations) >> 126 MB L2", "loss": last_loss,
                        "nodes_per_view": int(resident[0][0].x.size(0)), "edges_per_view": int(resident[0][0].edge_index.size(1))},

@@ -79,7 +79,8 @@ int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, int64_t ld_g,
 int molclr_gine_aggregate_fwd(const float* src, const float* bn_coef, int relu, const int32_t* rowptr, const int32_t* col,
                               const uint8_t* eattr, const float* B1, const float* B2, int64_t N, int D, float* out,
                               int64_t ld_out /* row stride of out / out_lo in floats */, int round_tf32_out,
-                              float* out_lo /* optional: tf32 residual of the exact sum */, cudaStream_t stream);
+                              float* out_lo /* optional: tf32 residual of the exact sum */,
+                              uint32_t drop_seed, float drop_p /* dropout of f (see "Dropout" below); 0 = none */, cudaStream_t stream);
 /* Backward (autograd of index_select/scatter_add_): gy[j] = sum_{out-edges e of j} ga[col_t[e]] + ga[j].
  * If z_prev != NULL additionally fuses the previous layer's ReLU backward and BatchNorm statistics:
  *   gy[j] *= [z_prev[j]*scale+shift > 0] (if relu);  partials[b][0] += gy, partials[b][1] += gy * (z_prev-mean)*invstd
@@ -88,11 +89,11 @@ int molclr_gine_aggregate_fwd(const float* src, const float* bn_coef, int relu, 
 int molclr_rowwise_max_blocks(void);
 int molclr_gine_aggregate_bwd(const float* ga, const int32_t* rowptr_t, const int32_t* col_t, const float* z_prev,
                               const float* bn_coef, int relu, int64_t N, int D, float* gy, int round_tf32_out, float* partials,
-                              int* num_partials, cudaStream_t stream);
+                              int* num_partials, uint32_t drop_seed, float drop_p, cudaStream_t stream);
 /* The ReLU-backward / BatchNorm-statistics stage alone (no neighbour gather): gy = g * [relu mask of z_prev], partials as
  * above.  Used by the GCN backward, where the gradient of a layer input arrives from a GEMM (gcn_molclr.py:76). */
 int molclr_relu_bn_bwd_stats(const float* g, const float* z_prev, const float* bn_coef, int relu, int64_t N, int D, float* gy,
-                             float* partials, int* num_partials, cudaStream_t stream);
+                             float* partials, int* num_partials, uint32_t drop_seed, float drop_p, cudaStream_t stream);
 
 /* ---- GCNConv aggregation: gcn_molclr.py:72-88 (scalar bond embeddings [5][1], [3][1] broadcast over the features; the
  * degree normalisation of gcn_molclr.py:27-36,74 is computed and DISCARDED by the reference, so none is applied) ----
@@ -105,7 +106,7 @@ int molclr_row_sum(const float* in, int R, int C, float* out, cudaStream_t strea
 /* x = [relu](z*scale + shift) (bn_coef NULL: x = z) materialised as a tensor-core operand: hi = tf32(x), lo (optional) =
  * tf32(x - hi); rows `ld` floats apart.  The GCN's GEMM input (gcn_molclr.py:146-152 then :76). */
 int molclr_bn_apply_fwd(const float* z, const float* bn_coef, int relu, int64_t N, int D, float* hi, float* lo, int64_t ld,
-                        cudaStream_t stream);
+                        uint32_t drop_seed, float drop_p, cudaStream_t stream);
 /* tile_stats [T][2][D]: column mean and M2 of every 32-row group of z (T = molclr_gemm_colstat_tiles(N)): what the GEMM
  * epilogue emits for the GIN path, for outputs that do not come from a GEMM. */
 int molclr_bn_tile_stats(const float* z, int64_t N, int D, int T, float* tile_stats, cudaStream_t stream);
@@ -133,18 +134,28 @@ int molclr_bn_eval_coef(const float* gamma, const float* beta, const float* runn
 int molclr_bn_bwd_finalize(const float* partials, int P, int64_t N, int D, const float* gamma, const float* coef,
                            int use_batch_stats, float* dgamma, float* dbeta, float* bcoef, cudaStream_t stream);
 /* gz (tf32-rounded if round_tf32_out: it then feeds a GEMM) = k1*gy + A + B*z.  gy from memory, or (gp != NULL) gy[n] = gp[node2graph[n]] * w_graph
- * (backward of global_mean/add_pool).  dbias (optional) = column sums of gz.  partials [max_blocks][D]. */
-int molclr_bn_bwd_apply(const float* gy, const float* gp, const int32_t* node2graph, const int32_t* gptr, int pool_mean,
-                        const float* z, const float* bcoef, int64_t N, int D, float* gz, int64_t ld_gz, int round_tf32_out,
-                        float* dbias, float* partials, cudaStream_t stream);
+ * (backward of global_mean/add/max_pool, times the last layer's dropout mask).  dbias (optional) = column sums of gz.  partials [max_blocks][D]. */
+int molclr_bn_bwd_apply(const float* gy, const float* gp, const int32_t* node2graph, const int32_t* gptr, int pool_mode,
+                        const int32_t* argmax, const float* z, const float* bcoef, int64_t N, int D, float* gz, int64_t ld_gz,
+                        int round_tf32_out, float* dbias, float* partials, uint32_t drop_seed, float drop_p, cudaStream_t stream);
 
-/* ---- global_mean_pool / global_add_pool: ginet_molclr.py:83-88,113 (pool_mode 0 = mean, 1 = add) ----
- * out[g] = w_g * sum_{n in graph g, node order} [relu](z[n]*scale + shift) */
+/* ---- global_mean_pool / global_add_pool / global_max_pool: ginet_molclr.py:83-88,113 (pool_mode 0 = mean, 1 = add, 2 = max) ----
+ * out[g] = w_g * sum (or max) over n in graph g, node order, of dropout([relu](z[n]*scale + shift)).
+ * max: argmax [G][D] int32 receives the node that attains the maximum (first one wins); the backward kernels route the
+ * gradient to it. */
 int molclr_pool_fwd(const float* z, const float* bn_coef, int relu, const int32_t* gptr, const int32_t* gperm,
                     int pool_mode, int64_t G, int D, float* out, int64_t ld_out, int round_tf32_out,
-                    float* out_lo /* optional */, cudaStream_t stream);
-int molclr_pool_bwd_stats(const float* gp, const int32_t* node2graph, const int32_t* gptr, int pool_mode, const float* z,
-                          const float* bn_coef, int64_t N, int D, float* partials, int* num_partials, cudaStream_t stream);
+                    float* out_lo /* optional */, int32_t* argmax /* mode 2 */, uint32_t drop_seed, float drop_p, cudaStream_t stream);
+int molclr_pool_bwd_stats(const float* gp, const int32_t* node2graph, const int32_t* gptr, int pool_mode, const int32_t* argmax,
+                          const float* z, const float* bn_coef, int64_t N, int D, float* partials, int* num_partials,
+                          uint32_t drop_seed, float drop_p, cudaStream_t stream);
+
+/* ---- Dropout: ginet_molclr.py:108-111 (F.dropout(relu(BN(z))) per layer, F.dropout(BN(z)) after the last) ----
+ * The normalised activations are never stored, so the mask is a counter-based hash of (drop_seed, node, feature): every
+ * consumer above that takes (drop_seed, drop_p) recomputes it; kept values are scaled by 1/(1-p).  Use one seed per layer
+ * and forward call, and the same seed in the matching backward call.  molclr_dropout_mask writes the mask itself
+ * (0 or 1/(1-p)) -- the test oracle applies it explicitly. */
+int molclr_dropout_mask(uint32_t drop_seed, float drop_p, int64_t N, int D, float* out, cudaStream_t stream);
 
 /* ---- dense contractions: the nn.Linear / matmul calls of ginet_molclr.py:19-23,46-47,90-96,114-115,
  * gcn_molclr.py:76 and their autograd backward, on tcgen05 tensor cores (TF32 in, FP32 accumulate) ----

@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MOLCLR_B200_LIB") or os.path.join(_HERE, "libmolclr_b200.so")   # (override: A/B timing of builds)
 
-vp, i64, i32, f32, sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
+vp, i64, i32, f32, sz, u32 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t, C.c_uint32
 
 
 class GemmArgs(C.Structure):
@@ -45,13 +45,13 @@ SIGNATURES = {
     "molclr_embed_nodes_fwd": (i32, [vp, vp, vp, i64, i32, vp, vp]),
     "molclr_embed_nodes_bwd_workspace_bytes": (sz, [i64]),
     "molclr_embed_nodes_bwd": (i32, [vp, vp, i64, i64, i32, vp, vp, vp]),
-    "molclr_gine_aggregate_fwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, i64, i32, vp, i64, i32, vp, vp]),
+    "molclr_gine_aggregate_fwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, i64, i32, vp, i64, i32, vp, u32, f32, vp]),
     "molclr_rowwise_max_blocks": (i32, []),
-    "molclr_gine_aggregate_bwd": (i32, [vp, vp, vp, vp, vp, i32, i64, i32, vp, i32, vp, C.POINTER(i32), vp]),
-    "molclr_relu_bn_bwd_stats": (i32, [vp, vp, vp, i32, i64, i32, vp, vp, C.POINTER(i32), vp]),
+    "molclr_gine_aggregate_bwd": (i32, [vp, vp, vp, vp, vp, i32, i64, i32, vp, i32, vp, C.POINTER(i32), u32, f32, vp]),
+    "molclr_relu_bn_bwd_stats": (i32, [vp, vp, vp, i32, i64, i32, vp, vp, C.POINTER(i32), u32, f32, vp]),
     "molclr_gcn_aggregate_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, i64, vp]),
     "molclr_row_sum": (i32, [vp, i32, i32, vp, vp]),
-    "molclr_bn_apply_fwd": (i32, [vp, vp, i32, i64, i32, vp, vp, i64, vp]),
+    "molclr_bn_apply_fwd": (i32, [vp, vp, i32, i64, i32, vp, vp, i64, u32, f32, vp]),
     "molclr_bn_tile_stats": (i32, [vp, i64, i32, i32, vp, vp]),
     "molclr_edge_table_grad": (i32, [vp, i64, vp, i64, i32, vp, vp]),
     "molclr_reduce_partials": (i32, [vp, i32, i32, f32, i32, vp, vp]),
@@ -59,9 +59,10 @@ SIGNATURES = {
     "molclr_bn_fwd_finalize": (i32, [vp, i32, i32, i64, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp]),
     "molclr_bn_eval_coef": (i32, [vp, vp, vp, vp, f32, i32, vp, vp]),
     "molclr_bn_bwd_finalize": (i32, [vp, i32, i64, i32, vp, vp, i32, vp, vp, vp, vp]),
-    "molclr_bn_bwd_apply": (i32, [vp, vp, vp, vp, i32, vp, vp, i64, i32, vp, i64, i32, vp, vp, vp]),
-    "molclr_pool_fwd": (i32, [vp, vp, i32, vp, vp, i32, i64, i32, vp, i64, i32, vp, vp]),
-    "molclr_pool_bwd_stats": (i32, [vp, vp, vp, i32, vp, vp, i64, i32, vp, C.POINTER(i32), vp]),
+    "molclr_bn_bwd_apply": (i32, [vp, vp, vp, vp, i32, vp, vp, vp, i64, i32, vp, i64, i32, vp, vp, u32, f32, vp]),
+    "molclr_pool_fwd": (i32, [vp, vp, i32, vp, vp, i32, i64, i32, vp, i64, i32, vp, vp, u32, f32, vp]),
+    "molclr_dropout_mask": (i32, [u32, f32, i64, i32, vp, vp]),
+    "molclr_pool_bwd_stats": (i32, [vp, vp, vp, i32, vp, vp, vp, i64, i32, vp, C.POINTER(i32), u32, f32, vp]),
     "molclr_gemm_colstat_tiles": (i32, [i64]),
     "molclr_gemm_colstat_tile_rows": (i32, []),
     "molclr_gemm_mask_words": (i32, [i64]),

@@ -28,6 +28,34 @@ static int persistent_grid(K kernel, int threads, size_t smem, int64_t rows_per_
   return (int)(g < 1 ? 1 : g);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Dropout (ginet_molclr.py:108-111: h = dropout(relu(BN(z))), last layer dropout(BN(z))).  The normalised activations are
+// never stored, so the Bernoulli mask is a pure function of (seed, node, feature) -- a counter-based hash -- that every
+// consumer (the next layer's gather, the pooling, and their backward kernels) recomputes.  One 64-bit draw per float4:
+// four 16-bit lanes, keep iff draw >= thr (thr = round(p * 65536)); kept values are scaled by 1/(1-p).
+// ------------------------------------------------------------------------------------------------
+struct DropCfg { uint32_t seed, thr; float scale; };
+static DropCfg make_drop(uint32_t seed, float p) {
+  DropCfg d;
+  d.seed = seed;
+  d.thr = p > 0.f ? (uint32_t)(p * 65536.f + 0.5f) : 0u;
+  d.scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  return d;
+}
+__device__ __forceinline__ uint32_t fmix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ float4 drop_mask4(const DropCfg& d, int row, int q, int D4) {
+  const uint32_t idx = (uint32_t)row * (uint32_t)D4 + (uint32_t)q;
+  const uint32_t h0 = fmix32(idx ^ fmix32(d.seed ^ 0x9E3779B9u)), h1 = fmix32(h0 + 0x6A09E667u + d.seed);
+  float4 m;
+  m.x = (h0 & 0xffffu) >= d.thr ? d.scale : 0.f; m.y = (h0 >> 16) >= d.thr ? d.scale : 0.f;
+  m.z = (h1 & 0xffffu) >= d.thr ? d.scale : 0.f; m.w = (h1 >> 16) >= d.thr ? d.scale : 0.f;
+  return m;
+}
+__device__ __forceinline__ float4 f4_mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+
 #define NCH_DISPATCH(D4, ...)                                                    \
   do {                                                                           \
     if ((D4) <= 32) { constexpr int NCH = 1; __VA_ARGS__; }                             \
@@ -130,7 +158,7 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_fwd_kernel(
     const float* __restrict__ src, const float* __restrict__ coef, int relu,
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const uint8_t* __restrict__ eattr,
     const float* __restrict__ B1, const float* __restrict__ B2, const float* __restrict__ bias, int N, int D,
-    float* __restrict__ out, long long ld_out, int round_out, float* __restrict__ out_lo) {
+    float* __restrict__ out, long long ld_out, int round_out, float* __restrict__ out_lo, const DropCfg drop) {
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* ee = sm4;                       // [15][D4]
@@ -153,11 +181,12 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_fwd_kernel(
 
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * kRowWarps + (threadIdx.x >> 5), nwarps = gridDim.x * kRowWarps;
-  auto act = [&](float4 v, int q) -> float4 {
+  auto act = [&](float4 v, int q, int row) -> float4 {
     if (HAS_BN) {
       const float4 s = sc[q], b = sh[q];
       v.x = fmaf(v.x, s.x, b.x); v.y = fmaf(v.y, s.y, b.y); v.z = fmaf(v.z, s.z, b.z); v.w = fmaf(v.w, s.w, b.w);
       if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      if (drop.thr) v = f4_mul(v, drop_mask4(drop, row, q, D4));
     }
     return v;
   };
@@ -185,8 +214,8 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_fwd_kernel(
       for (int j = 0; j < NCH; ++j) {
         const int q = lane + 32 * j;
         if (q < D4) {
-          acc[j] = f4_add(acc[j], f4_add(act(v0[j], q), ee[a0 * D4 + q]));
-          if (two) acc[j] = f4_add(acc[j], f4_add(act(v1[j], q), ee[a1 * D4 + q]));
+          acc[j] = f4_add(acc[j], f4_add(act(v0[j], q, s0), ee[a0 * D4 + q]));
+          if (two) acc[j] = f4_add(acc[j], f4_add(act(v1[j], q, s1), ee[a1 * D4 + q]));
         }
       }
     }
@@ -194,7 +223,7 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_fwd_kernel(
     for (int j = 0; j < NCH; ++j) {
       const int q = lane + 32 * j;
       if (q < D4) {
-        float4 r = f4_add(acc[j], f4_add(act(self[j], q), ee[kSelfLoopAttr * D4 + q]));   // self loop LAST
+        float4 r = f4_add(acc[j], f4_add(act(self[j], q, i), ee[kSelfLoopAttr * D4 + q]));   // self loop LAST
         if (SCALAR) r = f4_add(r, sc[q]);                                                  // then the bias row
         if (out_lo) st_f4(out_lo + (size_t)i * ld_out + 4 * q, f4_tf32_residual(r));
         if (round_out) r = f4_tf32(r);
@@ -239,7 +268,7 @@ template <int NCH, int MODE, bool GATHER>
 __global__ void __launch_bounds__(kRowThreads) gine_aggregate_bwd_kernel(
     const float* __restrict__ ga, const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ col_t,
     const float* __restrict__ z, const float* __restrict__ coef, int relu, int N, int D,
-    float* __restrict__ gy, float* __restrict__ partials, int round_out) {
+    float* __restrict__ gy, float* __restrict__ partials, int round_out, const DropCfg drop) {
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* cf = sm4;                          // [4][D4] scale, shift, mean, invstd
@@ -293,6 +322,7 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_bwd_kernel(
             if (!(fmaf(zv.z, s.z, b.z) > 0.f)) r.z = 0.f;
             if (!(fmaf(zv.w, s.w, b.w) > 0.f)) r.w = 0.f;
           }
+          if (drop.thr) r = f4_mul(r, drop_mask4(drop, i, q, D4));
           st[0][j] = f4_add(st[0][j], r);
           st[1][j].x = fmaf(r.x, (zv.x - m.x) * is.x, st[1][j].x);
           st[1][j].y = fmaf(r.y, (zv.y - m.y) * is.y, st[1][j].y);
@@ -458,8 +488,9 @@ __global__ void __launch_bounds__(512) bn_bwd_finalize_kernel(
 template <int NCH, int SRC>
 __global__ void __launch_bounds__(kRowThreads) bn_bwd_apply_kernel(
     const float* __restrict__ gy, const float* __restrict__ gp, const int32_t* __restrict__ node2graph,
-    const int32_t* __restrict__ gptr, int pool_mean, const float* __restrict__ z, const float* __restrict__ bcoef,
-    int N, int D, float* __restrict__ gz, long long ld_gz, float* __restrict__ partials, int round_out) {
+    const int32_t* __restrict__ gptr, int pool_mode, const int32_t* __restrict__ arg, const float* __restrict__ z,
+    const float* __restrict__ bcoef, int N, int D, float* __restrict__ gz, long long ld_gz, float* __restrict__ partials,
+    int round_out, const DropCfg drop) {
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* cf = sm4;                 // [3][D4]
@@ -474,10 +505,12 @@ __global__ void __launch_bounds__(kRowThreads) bn_bwd_apply_kernel(
   for (int i = warp; i < N; i += nwarps) {
     float w = 1.f;
     const float* grow;
+    const int32_t* arow = nullptr;
     if (SRC == 1) {
       const int g = __ldg(node2graph + i);
-      if (pool_mean) w = 1.f / (float)max(__ldg(gptr + g + 1) - __ldg(gptr + g), 1);
+      if (pool_mode == 0) w = 1.f / (float)max(__ldg(gptr + g + 1) - __ldg(gptr + g), 1);
       grow = gp + (size_t)g * D;
+      if (pool_mode == 2) arow = arg + (size_t)g * D;
     } else {
       grow = gy + (size_t)i * D;
     }
@@ -488,7 +521,14 @@ __global__ void __launch_bounds__(kRowThreads) bn_bwd_apply_kernel(
         float4 g = (SRC == 1) ? ldg_f4(grow + 4 * q) : ld_stream_f4(grow + 4 * q);
         const float4 zv = ld_stream_f4(z + (size_t)i * D + 4 * q);
         const float4 k1 = cf[q], A = cf[D4 + q], B = cf[2 * D4 + q];
-        if (SRC == 1) { g.x *= w; g.y *= w; g.z *= w; g.w *= w; }
+        if (SRC == 1) {
+          g.x *= w; g.y *= w; g.z *= w; g.w *= w;
+          if (arow) {                                  // max pooling: the gradient goes to the arg-max node only
+            const int4 am = __ldg(reinterpret_cast<const int4*>(arow + 4 * q));
+            g.x = am.x == i ? g.x : 0.f; g.y = am.y == i ? g.y : 0.f; g.z = am.z == i ? g.z : 0.f; g.w = am.w == i ? g.w : 0.f;
+          }
+          if (drop.thr) g = f4_mul(g, drop_mask4(drop, i, q, D4));
+        }
         float4 r;
         r.x = fmaf(k1.x, g.x, fmaf(B.x, zv.x, A.x)); r.y = fmaf(k1.y, g.y, fmaf(B.y, zv.y, A.y));
         r.z = fmaf(k1.z, g.z, fmaf(B.z, zv.z, A.z)); r.w = fmaf(k1.w, g.w, fmaf(B.w, zv.w, A.w));
@@ -507,8 +547,8 @@ __global__ void __launch_bounds__(kRowThreads) bn_bwd_apply_kernel(
 template <int NCH>
 __global__ void __launch_bounds__(kRowThreads) pool_fwd_kernel(
     const float* __restrict__ z, const float* __restrict__ coef, int relu, const int32_t* __restrict__ gptr,
-    const int32_t* __restrict__ gperm, int pool_mean, int G, int D, float* __restrict__ out, long long ld_out, int round_out,
-    float* __restrict__ out_lo) {
+    const int32_t* __restrict__ gperm, int pool_mode, int G, int D, float* __restrict__ out, long long ld_out, int round_out,
+    float* __restrict__ out_lo, int32_t* __restrict__ arg, const DropCfg drop) {
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* sc = sm4; float4* sh = sm4 + D4;
@@ -519,8 +559,10 @@ __global__ void __launch_bounds__(kRowThreads) pool_fwd_kernel(
   for (int g = warp; g < G; g += nwarps) {
     const int beg = __ldg(gptr + g), end = __ldg(gptr + g + 1);
     float4 acc[NCH];
+    int4 am[NCH];
+    const float init = (pool_mode == 2 && end > beg) ? -INFINITY : 0.f;
 #pragma unroll
-    for (int j = 0; j < NCH; ++j) acc[j] = f4_zero();
+    for (int j = 0; j < NCH; ++j) { acc[j] = make_float4(init, init, init, init); am[j] = make_int4(-1, -1, -1, -1); }
     for (int p = beg; p < end; ++p) {
       const int n = __ldg(gperm + p);
 #pragma unroll
@@ -531,10 +573,19 @@ __global__ void __launch_bounds__(kRowThreads) pool_fwd_kernel(
           const float4 s = sc[q], b = sh[q];
           v.x = fmaf(v.x, s.x, b.x); v.y = fmaf(v.y, s.y, b.y); v.z = fmaf(v.z, s.z, b.z); v.w = fmaf(v.w, s.w, b.w);
           if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-          acc[j] = f4_add(acc[j], v);
+          if (drop.thr) v = f4_mul(v, drop_mask4(drop, n, q, D4));
+          if (pool_mode == 2) {                             // global_max_pool: first maximum wins
+            if (v.x > acc[j].x) { acc[j].x = v.x; am[j].x = n; }
+            if (v.y > acc[j].y) { acc[j].y = v.y; am[j].y = n; }
+            if (v.z > acc[j].z) { acc[j].z = v.z; am[j].z = n; }
+            if (v.w > acc[j].w) { acc[j].w = v.w; am[j].w = n; }
+          } else {
+            acc[j] = f4_add(acc[j], v);
+          }
         }
       }
     }
+    const bool pool_mean = pool_mode == 0;
     const float cntf = (float)max(end - beg, 1);             // count.clamp(min=1)
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
@@ -542,6 +593,7 @@ __global__ void __launch_bounds__(kRowThreads) pool_fwd_kernel(
       if (q < D4) {
         float4 r = acc[j];
         if (pool_mean) { r.x /= cntf; r.y /= cntf; r.z /= cntf; r.w /= cntf; }
+        if (pool_mode == 2 && arg) *reinterpret_cast<int4*>(arg + (size_t)g * D + 4 * q) = am[j];
         if (out_lo) st_f4(out_lo + (size_t)g * ld_out + 4 * q, f4_tf32_residual(r));
         if (round_out) r = f4_tf32(r);
         st_f4(out + (size_t)g * ld_out + 4 * q, r);
@@ -555,8 +607,8 @@ __global__ void __launch_bounds__(kRowThreads) pool_fwd_kernel(
 template <int NCH>
 __global__ void __launch_bounds__(kRowThreads) pool_bwd_stats_kernel(
     const float* __restrict__ gp, const int32_t* __restrict__ node2graph, const int32_t* __restrict__ gptr,
-    int pool_mean, const float* __restrict__ z, const float* __restrict__ coef, int N, int D,
-    float* __restrict__ partials) {
+    int pool_mode, const int32_t* __restrict__ arg, const float* __restrict__ z, const float* __restrict__ coef, int N, int D,
+    float* __restrict__ partials, const DropCfg drop) {
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* cf = sm4;                 // mean, invstd
@@ -570,7 +622,7 @@ __global__ void __launch_bounds__(kRowThreads) pool_bwd_stats_kernel(
   for (int j = 0; j < NCH; ++j) { st[0][j] = f4_zero(); st[1][j] = f4_zero(); }
   for (int i = warp; i < N; i += nwarps) {
     const int g = __ldg(node2graph + i);
-    const float w = pool_mean ? 1.f / (float)max(__ldg(gptr + g + 1) - __ldg(gptr + g), 1) : 1.f;
+    const float w = pool_mode == 0 ? 1.f / (float)max(__ldg(gptr + g + 1) - __ldg(gptr + g), 1) : 1.f;
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
       const int q = lane + 32 * j;
@@ -578,6 +630,11 @@ __global__ void __launch_bounds__(kRowThreads) pool_bwd_stats_kernel(
         float4 r = ldg_f4(gp + (size_t)g * D + 4 * q);
         const float4 zv = ld_stream_f4(z + (size_t)i * D + 4 * q), m = cf[q], is = cf[D4 + q];
         r.x *= w; r.y *= w; r.z *= w; r.w *= w;
+        if (pool_mode == 2) {
+          const int4 am = __ldg(reinterpret_cast<const int4*>(arg + (size_t)g * D + 4 * q));
+          r.x = am.x == i ? r.x : 0.f; r.y = am.y == i ? r.y : 0.f; r.z = am.z == i ? r.z : 0.f; r.w = am.w == i ? r.w : 0.f;
+        }
+        if (drop.thr) r = f4_mul(r, drop_mask4(drop, i, q, D4));
         st[0][j] = f4_add(st[0][j], r);
         st[1][j].x = fmaf(r.x, (zv.x - m.x) * is.x, st[1][j].x); st[1][j].y = fmaf(r.y, (zv.y - m.y) * is.y, st[1][j].y);
         st[1][j].z = fmaf(r.z, (zv.z - m.z) * is.z, st[1][j].z); st[1][j].w = fmaf(r.w, (zv.w - m.w) * is.w, st[1][j].w);
@@ -596,7 +653,7 @@ __global__ void __launch_bounds__(kRowThreads) pool_bwd_stats_kernel(
 template <int NCH>
 __global__ void __launch_bounds__(kRowThreads) bn_apply_fwd_kernel(
     const float* __restrict__ z, const float* __restrict__ coef, int relu, int N, int D, float* __restrict__ hi,
-    float* __restrict__ lo, long long ld) {
+    float* __restrict__ lo, long long ld, const DropCfg drop) {
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* sc = sm4; float4* sh = sm4 + D4;
@@ -616,6 +673,7 @@ __global__ void __launch_bounds__(kRowThreads) bn_apply_fwd_kernel(
           const float4 s = sc[q], b = sh[q];
           v.x = fmaf(v.x, s.x, b.x); v.y = fmaf(v.y, s.y, b.y); v.z = fmaf(v.z, s.z, b.z); v.w = fmaf(v.w, s.w, b.w);
           if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          if (drop.thr) v = f4_mul(v, drop_mask4(drop, i, q, D4));
         }
         st_f4(hi + (size_t)i * ld + 4 * q, f4_tf32(v));
         if (lo) st_f4(lo + (size_t)i * ld + 4 * q, f4_tf32_residual(v));
@@ -695,6 +753,15 @@ __global__ void act_bwd_kernel(const float* __restrict__ gy, const float* __rest
     const float v = x[i];
     const float d = mode == 0 ? (v > 20.f ? 1.f : 1.f / (1.f + expf(-v))) : (v > 0.f ? 1.f : 0.f);
     gx[i] = round_tf32(gy[i] * d);
+  }
+}
+
+// The dropout mask itself (0 or 1/(1-p)) as a matrix: what the fused consumers apply.  Test / diagnostics hook.
+__global__ void dropout_mask_kernel(int N, int D, float* __restrict__ out, const DropCfg drop) {
+  const int D4 = D >> 2;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)N * D4; t += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(t / D4), q = (int)(t - (long long)row * D4);
+    st_f4(out + (size_t)row * D + 4 * q, drop.thr ? drop_mask4(drop, row, q, D4) : make_float4(1.f, 1.f, 1.f, 1.f));
   }
 }
 
@@ -805,7 +872,7 @@ extern "C" int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, in
 
 static int aggregate_fwd_launch(const float* src, const float* bn_coef, int relu, const int32_t* rowptr, const int32_t* col,
                                 const uint8_t* eattr, const float* B1, const float* B2, const float* bias, bool scalar, int64_t N,
-                                int D, float* out, int64_t ld_out, int round_tf32_out, float* out_lo, cudaStream_t stream) {
+                                int D, float* out, int64_t ld_out, int round_tf32_out, float* out_lo, const DropCfg drop, cudaStream_t stream) {
   REQUIRE_D(D);
   MOLCLR_REQUIRE(ld_out >= D && ld_out % 4 == 0, "aggregate_fwd: ld_out must be >= D and a multiple of 4");
   if (N == 0) return 0;
@@ -814,15 +881,15 @@ static int aggregate_fwd_launch(const float* src, const float* bn_coef, int relu
     if (scalar) {
       auto k = gine_aggregate_fwd_kernel<NCH, false, true>;
       k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
-          src, nullptr, 0, rowptr, col, eattr, B1, B2, bias, (int)N, D, out, ld_out, round_tf32_out, out_lo);
+          src, nullptr, 0, rowptr, col, eattr, B1, B2, bias, (int)N, D, out, ld_out, round_tf32_out, out_lo, drop);
     } else if (bn_coef) {
       auto k = gine_aggregate_fwd_kernel<NCH, true, false>;
       k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
-          src, bn_coef, relu, rowptr, col, eattr, B1, B2, nullptr, (int)N, D, out, ld_out, round_tf32_out, out_lo);
+          src, bn_coef, relu, rowptr, col, eattr, B1, B2, nullptr, (int)N, D, out, ld_out, round_tf32_out, out_lo, drop);
     } else {
       auto k = gine_aggregate_fwd_kernel<NCH, false, false>;
       k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
-          src, nullptr, 0, rowptr, col, eattr, B1, B2, nullptr, (int)N, D, out, ld_out, round_tf32_out, out_lo);
+          src, nullptr, 0, rowptr, col, eattr, B1, B2, nullptr, (int)N, D, out, ld_out, round_tf32_out, out_lo, drop);
     }
   });
   MOLCLR_CHECK_LAUNCH("aggregate_fwd");
@@ -832,15 +899,16 @@ static int aggregate_fwd_launch(const float* src, const float* bn_coef, int relu
 extern "C" int molclr_gine_aggregate_fwd(const float* src, const float* bn_coef, int relu, const int32_t* rowptr,
                                          const int32_t* col, const uint8_t* eattr, const float* B1, const float* B2,
                                          int64_t N, int D, float* out, int64_t ld_out, int round_tf32_out, float* out_lo,
-                                         cudaStream_t stream) {
+                                         uint32_t drop_seed, float drop_p, cudaStream_t stream) {
+  MOLCLR_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "dropout probability %f not in [0, 1)", drop_p);
   return aggregate_fwd_launch(src, bn_coef, relu, rowptr, col, eattr, B1, B2, nullptr, false, N, D, out, ld_out, round_tf32_out,
-                              out_lo, stream);
+                              out_lo, make_drop(drop_seed, bn_coef ? drop_p : 0.f), stream);
 }
 
 extern "C" int molclr_gcn_aggregate_fwd(const float* src, const int32_t* rowptr, const int32_t* col, const uint8_t* eattr,
                                         const float* b1, const float* b2, const float* bias, int64_t N, int D, float* out,
                                         int64_t ld_out, cudaStream_t stream) {
-  return aggregate_fwd_launch(src, nullptr, 0, rowptr, col, eattr, b1, b2, bias, true, N, D, out, ld_out, 0, nullptr, stream);
+  return aggregate_fwd_launch(src, nullptr, 0, rowptr, col, eattr, b1, b2, bias, true, N, D, out, ld_out, 0, nullptr, make_drop(0, 0.f), stream);
 }
 
 // Number of partial rows the persistent row-wise kernels with block partials emit (upper bound on
@@ -849,7 +917,7 @@ extern "C" int molclr_rowwise_max_blocks(void) { return 8 * sm_count(); }
 
 static int aggregate_bwd_launch(const float* ga, const int32_t* rowptr_t, const int32_t* col_t, bool gather, const float* z_prev,
                                 const float* bn_coef, int relu, int64_t N, int D, float* gy, int round_out, float* partials,
-                                int* num_partials, cudaStream_t stream) {
+                                int* num_partials, const DropCfg drop, cudaStream_t stream) {
   REQUIRE_D(D);
   if (num_partials) *num_partials = 0;
   if (N == 0) return 0;
@@ -861,18 +929,18 @@ static int aggregate_bwd_launch(const float* ga, const int32_t* rowptr_t, const 
       if (gather) {
         auto k = gine_aggregate_bwd_kernel<NCH, 1, true>;
         grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
-        k<<<grid, kRowThreads, smem, stream>>>(ga, rowptr_t, col_t, z_prev, bn_coef, relu, (int)N, D, gy, partials, round_out);
+        k<<<grid, kRowThreads, smem, stream>>>(ga, rowptr_t, col_t, z_prev, bn_coef, relu, (int)N, D, gy, partials, round_out, drop);
       } else {
         auto k = gine_aggregate_bwd_kernel<NCH, 1, false>;
         grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
-        k<<<grid, kRowThreads, smem, stream>>>(ga, nullptr, nullptr, z_prev, bn_coef, relu, (int)N, D, gy, partials, round_out);
+        k<<<grid, kRowThreads, smem, stream>>>(ga, nullptr, nullptr, z_prev, bn_coef, relu, (int)N, D, gy, partials, round_out, drop);
       }
       if (num_partials) *num_partials = grid;
     } else {
       MOLCLR_REQUIRE(gather, "relu_bn_bwd_stats: z_prev is required");
       auto k = gine_aggregate_bwd_kernel<NCH, 0, true>;
       k<<<persistent_grid(k, kRowThreads, 0, kRowWarps, N), kRowThreads, 0, stream>>>(ga, rowptr_t, col_t, nullptr, nullptr, 0,
-                                                                                        (int)N, D, gy, nullptr, round_out);
+                                                                                        (int)N, D, gy, nullptr, round_out, drop);
     }
   });
   MOLCLR_CHECK_LAUNCH("aggregate_bwd");
@@ -881,13 +949,18 @@ static int aggregate_bwd_launch(const float* ga, const int32_t* rowptr_t, const 
 
 extern "C" int molclr_gine_aggregate_bwd(const float* ga, const int32_t* rowptr_t, const int32_t* col_t, const float* z_prev,
                                          const float* bn_coef, int relu, int64_t N, int D, float* gy, int round_tf32_out,
-                                         float* partials, int* num_partials, cudaStream_t stream) {
-  return aggregate_bwd_launch(ga, rowptr_t, col_t, true, z_prev, bn_coef, relu, N, D, gy, round_tf32_out, partials, num_partials, stream);
+                                         float* partials, int* num_partials, uint32_t drop_seed, float drop_p, cudaStream_t stream) {
+  MOLCLR_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "dropout probability %f not in [0, 1)", drop_p);
+  return aggregate_bwd_launch(ga, rowptr_t, col_t, true, z_prev, bn_coef, relu, N, D, gy, round_tf32_out, partials, num_partials,
+                              make_drop(drop_seed, z_prev ? drop_p : 0.f), stream);
 }
 
 extern "C" int molclr_relu_bn_bwd_stats(const float* g, const float* z_prev, const float* bn_coef, int relu, int64_t N, int D,
-                                        float* gy, float* partials, int* num_partials, cudaStream_t stream) {
-  return aggregate_bwd_launch(g, nullptr, nullptr, false, z_prev, bn_coef, relu, N, D, gy, 0, partials, num_partials, stream);
+                                        float* gy, float* partials, int* num_partials, uint32_t drop_seed, float drop_p,
+                                        cudaStream_t stream) {
+  MOLCLR_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "dropout probability %f not in [0, 1)", drop_p);
+  return aggregate_bwd_launch(g, nullptr, nullptr, false, z_prev, bn_coef, relu, N, D, gy, 0, partials, num_partials,
+                              make_drop(drop_seed, drop_p), stream);
 }
 
 // Bond-embedding table gradients: dB1[t] = sum_i cnt[i][t] * g_a[i], dB2[d] = sum_i cnt[i][5+d] * g_a[i], where cnt[i][.]
@@ -944,10 +1017,18 @@ extern "C" int molclr_bn_bwd_finalize(const float* partials, int P, int64_t N, i
   return 0;
 }
 
-extern "C" int molclr_bn_bwd_apply(const float* gy, const float* gp, const int32_t* node2graph, const int32_t* gptr, int pool_mean,
-                                   const float* z, const float* bcoef, int64_t N, int D, float* gz, int64_t ld_gz, int round_tf32_out,
-                                   float* dbias, float* partials, cudaStream_t stream) {
+#define REQUIRE_POOL(mode, arg) \
+  MOLCLR_REQUIRE((mode) >= 0 && (mode) <= 2 && ((mode) != 2 || (arg) != nullptr), "pool mode %d (0 = mean, 1 = add, 2 = max; max needs the arg-max buffer)", (int)(mode))
+#define REQUIRE_DROP(p) MOLCLR_REQUIRE((p) >= 0.f && (p) < 1.f, "dropout probability %f not in [0, 1)", (double)(p))
+
+extern "C" int molclr_bn_bwd_apply(const float* gy, const float* gp, const int32_t* node2graph, const int32_t* gptr, int pool_mode,
+                                   const int32_t* argmax, const float* z, const float* bcoef, int64_t N, int D, float* gz, int64_t ld_gz,
+                                   int round_tf32_out, float* dbias, float* partials, uint32_t drop_seed, float drop_p,
+                                   cudaStream_t stream) {
   REQUIRE_D(D);
+  REQUIRE_DROP(drop_p);
+  if (gp) REQUIRE_POOL(pool_mode, argmax);
+  const DropCfg drop = make_drop(drop_seed, gp ? drop_p : 0.f);
   MOLCLR_REQUIRE(ld_gz >= D && ld_gz % 4 == 0, "bn_bwd_apply: ld_gz must be >= D and a multiple of 4");
   if (N == 0) return 0;
   const size_t smem = (size_t)(3 + kRowWarps) * D * sizeof(float);
@@ -956,11 +1037,13 @@ extern "C" int molclr_bn_bwd_apply(const float* gy, const float* gp, const int32
     if (gp) {
       auto k = bn_bwd_apply_kernel<NCH, 1>;
       grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
-      k<<<grid, kRowThreads, smem, stream>>>(nullptr, gp, node2graph, gptr, pool_mean, z, bcoef, (int)N, D, gz, ld_gz, partials, round_tf32_out);
+      k<<<grid, kRowThreads, smem, stream>>>(nullptr, gp, node2graph, gptr, pool_mode, argmax, z, bcoef, (int)N, D, gz, ld_gz, partials,
+                                             round_tf32_out, drop);
     } else {
       auto k = bn_bwd_apply_kernel<NCH, 0>;
       grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
-      k<<<grid, kRowThreads, smem, stream>>>(gy, nullptr, nullptr, nullptr, 0, z, bcoef, (int)N, D, gz, ld_gz, partials, round_tf32_out);
+      k<<<grid, kRowThreads, smem, stream>>>(gy, nullptr, nullptr, nullptr, 0, nullptr, z, bcoef, (int)N, D, gz, ld_gz, partials,
+                                             round_tf32_out, drop);
     }
   });
   MOLCLR_CHECK_LAUNCH("bn_bwd_apply");
@@ -970,30 +1053,35 @@ extern "C" int molclr_bn_bwd_apply(const float* gy, const float* gp, const int32
 
 extern "C" int molclr_pool_fwd(const float* z, const float* bn_coef, int relu, const int32_t* gptr, const int32_t* gperm,
                                int pool_mode, int64_t G, int D, float* out, int64_t ld_out, int round_tf32_out, float* out_lo,
-                               cudaStream_t stream) {
+                               int32_t* argmax, uint32_t drop_seed, float drop_p, cudaStream_t stream) {
   REQUIRE_D(D);
-  MOLCLR_REQUIRE(pool_mode == 0 || pool_mode == 1, "pool mode %d not supported (0 = mean, 1 = add)", pool_mode);
+  REQUIRE_DROP(drop_p);
+  REQUIRE_POOL(pool_mode, argmax);
   if (G == 0) return 0;
   const size_t smem = (size_t)2 * D * sizeof(float);
   NCH_DISPATCH(D / 4, {
     auto k = pool_fwd_kernel<NCH>;
     k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, G), kRowThreads, smem, stream>>>(z, bn_coef, relu, gptr, gperm,
-                                                                                          pool_mode == 0, (int)G, D, out, ld_out, round_tf32_out, out_lo);
+                                                                                          pool_mode, (int)G, D, out, ld_out, round_tf32_out, out_lo, argmax,
+                                                                                          make_drop(drop_seed, drop_p));
   });
   MOLCLR_CHECK_LAUNCH("pool_fwd");
   return 0;
 }
 
-extern "C" int molclr_pool_bwd_stats(const float* gp, const int32_t* node2graph, const int32_t* gptr, int pool_mode, const float* z,
-                                     const float* bn_coef, int64_t N, int D, float* partials, int* num_partials, cudaStream_t stream) {
+extern "C" int molclr_pool_bwd_stats(const float* gp, const int32_t* node2graph, const int32_t* gptr, int pool_mode,
+                                     const int32_t* argmax, const float* z, const float* bn_coef, int64_t N, int D, float* partials,
+                                     int* num_partials, uint32_t drop_seed, float drop_p, cudaStream_t stream) {
   REQUIRE_D(D);
+  REQUIRE_DROP(drop_p);
+  REQUIRE_POOL(pool_mode, argmax);
   if (num_partials) *num_partials = 0;
   if (N == 0) return 0;
   const size_t smem = (size_t)(2 + 2 * kRowWarps) * D * sizeof(float);
   NCH_DISPATCH(D / 4, {
     auto k = pool_bwd_stats_kernel<NCH>;
     const int grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
-    k<<<grid, kRowThreads, smem, stream>>>(gp, node2graph, gptr, pool_mode == 0, z, bn_coef, (int)N, D, partials);
+    k<<<grid, kRowThreads, smem, stream>>>(gp, node2graph, gptr, pool_mode, argmax, z, bn_coef, (int)N, D, partials, make_drop(drop_seed, drop_p));
     if (num_partials) *num_partials = grid;
   });
   MOLCLR_CHECK_LAUNCH("pool_bwd_stats");
@@ -1001,14 +1089,16 @@ extern "C" int molclr_pool_bwd_stats(const float* gp, const int32_t* node2graph,
 }
 
 extern "C" int molclr_bn_apply_fwd(const float* z, const float* bn_coef, int relu, int64_t N, int D, float* hi, float* lo,
-                                   int64_t ld, cudaStream_t stream) {
+                                   int64_t ld, uint32_t drop_seed, float drop_p, cudaStream_t stream) {
   REQUIRE_D(D);
+  REQUIRE_DROP(drop_p);
   MOLCLR_REQUIRE(ld >= D && ld % 4 == 0, "bn_apply_fwd: ld must be >= D and a multiple of 4");
   if (N == 0) return 0;
   const size_t smem = (size_t)2 * D * sizeof(float);
   NCH_DISPATCH(D / 4, {
     auto k = bn_apply_fwd_kernel<NCH>;
-    k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(z, bn_coef, relu, (int)N, D, hi, lo, ld);
+    k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(z, bn_coef, relu, (int)N, D, hi, lo, ld,
+                                                                                          make_drop(drop_seed, bn_coef ? drop_p : 0.f));
   });
   MOLCLR_CHECK_LAUNCH("bn_apply_fwd");
   return 0;
@@ -1023,6 +1113,17 @@ extern "C" int molclr_bn_tile_stats(const float* z, int64_t N, int D, int T, flo
     k<<<persistent_grid(k, kRowThreads, 0, kRowWarps, T), kRowThreads, 0, stream>>>(z, (int)N, D, T, tile_stats);
   });
   MOLCLR_CHECK_LAUNCH("bn_tile_stats");
+  return 0;
+}
+
+extern "C" int molclr_dropout_mask(uint32_t drop_seed, float drop_p, int64_t N, int D, float* out, cudaStream_t stream) {
+  REQUIRE_D(D);
+  REQUIRE_DROP(drop_p);
+  if (N == 0) return 0;
+  int64_t blocks = (N * (D / 4) + 255) / 256;
+  if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+  dropout_mask_kernel<<<(int)blocks, 256, 0, stream>>>((int)N, D, out, make_drop(drop_seed, drop_p));
+  MOLCLR_CHECK_LAUNCH("dropout_mask");
   return 0;
 }
 

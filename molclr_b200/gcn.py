@@ -104,6 +104,7 @@ class _GCNFunction(torch.autograd.Function):
         h0 = ops.embed_nodes_fwd(plan, m.x_embedding1.weight.detach(), m.x_embedding2.weight.detach())
         x_hi, x_lo = ops.bn_apply_fwd(h0, None, False, comp)
         layers = []
+        drops = m._dropout_seeds()
         z = coef = None
         for l in range(L):
             g, bn = m.gnns[l], m.batch_norms[l]
@@ -120,12 +121,13 @@ class _GCNFunction(torch.autograd.Function):
                 coef = ops.bn_eval_coef(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
             layers.append((x_hi, z, coef, W_hi))
             if l < L - 1:
-                x_hi, x_lo = ops.bn_apply_fwd(z, coef, True, comp)
-        p, p_lo = ops.pool_fwd(plan, z, coef, pool_mode, relu=False, round_out=True, want_lo=True) if comp else \
-            (ops.pool_fwd(plan, z, coef, pool_mode, relu=False, round_out=True), None)
+                x_hi, x_lo = ops.bn_apply_fwd(z, coef, True, comp, drop=drops[l])
+        argmax = torch.empty(plan.G, D, dtype=torch.int32, device=dev) if pool_mode == 2 else None
+        p, p_lo = ops.pool_fwd(plan, z, coef, pool_mode, relu=False, round_out=True, want_lo=True, argmax=argmax, drop=drops[L - 1]) \
+            if comp else (ops.pool_fwd(plan, z, coef, pool_mode, relu=False, round_out=True, argmax=argmax, drop=drops[L - 1]), None)
         h, out, head_saved = _head_forward(m, p, p_lo, rw, comp)
         ctx.m, ctx.plan, ctx.layers, ctx.p, ctx.head_saved = m, plan, layers, p, head_saved
-        ctx.training, ctx.pool_mode = training, pool_mode
+        ctx.training, ctx.pool_mode, ctx.drops, ctx.argmax = training, pool_mode, drops, argmax
         return h, out
 
     @staticmethod
@@ -139,9 +141,10 @@ class _GCNFunction(torch.autograd.Function):
         grads = [None] * (2 + 6 * L)
         x_hi, z, coef, W_hi = layers[L - 1]
         bn = m.batch_norms[L - 1]
-        partials, P = ops.pool_bwd_stats(plan, g_p, z, coef, ctx.pool_mode)
+        drops, argmax = ctx.drops, ctx.argmax
+        partials, P = ops.pool_bwd_stats(plan, g_p, z, coef, ctx.pool_mode, argmax=argmax, drop=drops[L - 1])
         dgamma, dbeta, bcoef = ops.bn_bwd_finalize(partials, P, N, bn.weight.detach(), coef, ctx.training)
-        g_z, db = ops.bn_bwd_apply(z, bcoef, gp=g_p, plan=plan, pool_mean=ctx.pool_mode == 0, round_out=False)
+        g_z, db = ops.bn_bwd_apply(z, bcoef, gp=g_p, plan=plan, pool_mode=ctx.pool_mode, round_out=False, argmax=argmax, drop=drops[L - 1])
         for l in range(L - 1, -1, -1):
             x_hi, z, coef, W_hi = layers[l]
             base = 2 + 6 * l
@@ -155,7 +158,7 @@ class _GCNFunction(torch.autograd.Function):
             if l > 0:
                 _, zp, coefp, _ = layers[l - 1]
                 bnp = m.batch_norms[l - 1]
-                g_r, partials, P = ops.relu_bn_bwd_stats(g_x, zp, coefp, relu=True)
+                g_r, partials, P = ops.relu_bn_bwd_stats(g_x, zp, coefp, relu=True, drop=drops[l - 1])
                 dgamma, dbeta, bcoef = ops.bn_bwd_finalize(partials, P, N, bnp.weight.detach(), coefp, ctx.training)
                 g_z, db = ops.bn_bwd_apply(zp, bcoef, gy=g_r, round_out=False)
             else:

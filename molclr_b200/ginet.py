@@ -73,14 +73,19 @@ class _EncoderBase(nn.Module):
     precision = "tf32x3"
 
     def _check_input(self, data):
-        if self.training and self.drop_ratio > 0:
-            raise NotImplementedError("molclr_b200: drop_ratio > 0 in training mode is not implemented yet "
-                                      "(pre-training uses drop_ratio 0, config.yaml:20)")
+        if not 0 <= self.drop_ratio < 1:
+            raise ValueError(f"dropout probability has to be between 0 and 1, but got {self.drop_ratio}")
         if self.pool_name not in ops.POOL_MODES:
-            if self.pool_name == "max":
-                raise NotImplementedError("molclr_b200: pool='max' is not implemented yet")
             # the reference leaves self.pool unset for unknown names and fails at forward (ginet_molclr.py:83-88,113)
             raise AttributeError(f"'{type(self).__name__}' object has no attribute 'pool'")
+
+    def _dropout_seeds(self):
+        """One counter-hash seed per layer and forward call (drawn from torch's CPU generator, so torch.manual_seed makes
+        a run reproducible); (0, 0.0) entries when dropout is inactive (eval mode or drop_ratio 0)."""
+        if not self.training or self.drop_ratio <= 0:
+            return [(0, 0.0)] * self.num_layer
+        base = torch.randint(0, 2 ** 31 - 1, (self.num_layer,))
+        return [(int(b), float(self.drop_ratio)) for b in base]
 
 
 class GINet(_EncoderBase):
@@ -185,12 +190,14 @@ def _encoder_forward(m, plan, comp, training, pool_mode):
     src, coef_prev = h0, None
     layers = []
     T = ops.colstat_tiles(N)
+    drops = m._dropout_seeds()                # drops[l]: dropout applied to layer l's output (ginet_molclr.py:108-111)
     for l in range(L):
         g, bn = m.gnns[l], m.batch_norms[l]
+        dp = drops[l - 1] if l > 0 else (0, 0.0)
         a, a_lo = ops.gine_aggregate_fwd(plan, src, g.edge_embedding1.weight.detach(), g.edge_embedding2.weight.detach(),
-                                         bn_coef=coef_prev, relu=True, round_out=True, want_lo=True) if comp else \
+                                         bn_coef=coef_prev, relu=True, round_out=True, want_lo=True, drop=dp) if comp else \
             (ops.gine_aggregate_fwd(plan, src, g.edge_embedding1.weight.detach(), g.edge_embedding2.weight.detach(),
-                                    bn_coef=coef_prev, relu=True, round_out=True), None)
+                                    bn_coef=coef_prev, relu=True, round_out=True, drop=dp), None)
         (W1, W1_lo), (W2, W2_lo) = rw.get(g.mlp[0].weight), rw.get(g.mlp[2].weight)
         u = ops.padded(N, H, dev)
         u_lo = ops.padded(N, H, dev) if comp else None
@@ -211,8 +218,10 @@ def _encoder_forward(m, plan, comp, training, pool_mode):
         layers.append((a, u, z, coef, W1, W2, ubits))
         src, coef_prev = z, coef
         del a_lo, u_lo
-    p, p_lo = ops.pool_fwd(plan, src, coef_prev, pool_mode, relu=False, round_out=True, want_lo=True) if comp else \
-        (ops.pool_fwd(plan, src, coef_prev, pool_mode, relu=False, round_out=True), None)
+    argmax = torch.empty(plan.G, D, dtype=torch.int32, device=dev) if pool_mode == 2 else None
+    p, p_lo = ops.pool_fwd(plan, src, coef_prev, pool_mode, relu=False, round_out=True, want_lo=True, argmax=argmax, drop=drops[L - 1]) \
+        if comp else (ops.pool_fwd(plan, src, coef_prev, pool_mode, relu=False, round_out=True, argmax=argmax, drop=drops[L - 1]), None)
+    layers.append((drops, argmax))            # trailing entry: what the backward needs besides the per-layer tensors
     return p, p_lo, layers
 
 
@@ -222,12 +231,13 @@ def _encoder_backward(m, plan, layers, g_p, training, pool_mode):
     L, D, H, N = m.num_layer, m.emb_dim, 2 * m.emb_dim, plan.N
     dev = g_p.device
     grads = [None] * (2 + 8 * L)
+    drops, argmax = layers[L]
     # last layer: BatchNorm backward fed by the pool backward (g_y is never materialised)
     a, u, z, coef, W1, W2, ubits = layers[L - 1]
     bn = m.batch_norms[L - 1]
-    partials, P = ops.pool_bwd_stats(plan, g_p, z, coef, pool_mode)
+    partials, P = ops.pool_bwd_stats(plan, g_p, z, coef, pool_mode, argmax=argmax, drop=drops[L - 1])
     dgamma, dbeta, bcoef = ops.bn_bwd_finalize(partials, P, N, bn.weight.detach(), coef, training)
-    g_z, db2 = ops.bn_bwd_apply(z, bcoef, gp=g_p, plan=plan, pool_mean=pool_mode == 0)
+    g_z, db2 = ops.bn_bwd_apply(z, bcoef, gp=g_p, plan=plan, pool_mode=pool_mode, argmax=argmax, drop=drops[L - 1])
     T = ops.colstat_tiles(N)
     for l in range(L - 1, -1, -1):
         a, u, z, coef, W1, W2, ubits = layers[l]
@@ -246,7 +256,7 @@ def _encoder_backward(m, plan, layers, g_p, training, pool_mode):
         if l > 0:
             _, _, zp, coefp, _, _, _ = layers[l - 1]
             bnp = m.batch_norms[l - 1]
-            g_y, partials, P = ops.gine_aggregate_bwd(plan, g_a, z_prev=zp, bn_coef=coefp, relu=True)
+            g_y, partials, P = ops.gine_aggregate_bwd(plan, g_a, z_prev=zp, bn_coef=coefp, relu=True, drop=drops[l - 1])
             dgamma, dbeta, bcoef = ops.bn_bwd_finalize(partials, P, N, bnp.weight.detach(), coefp, training)
             g_z, db2 = ops.bn_bwd_apply(zp, bcoef, gy=g_y)
         else:

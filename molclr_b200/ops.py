@@ -147,19 +147,19 @@ def embed_nodes_bwd(plan, g):
     return dE[:119], dE[119:]
 
 
-def gine_aggregate_fwd(plan, src, B1, B2, bn_coef=None, relu=True, round_out=True, want_lo=False):
+def gine_aggregate_fwd(plan, src, B1, B2, bn_coef=None, relu=True, round_out=True, want_lo=False, drop=(0, 0.0)):
     """Returns the aggregate (tf32-rounded if round_out), plus its tf32 residual when want_lo."""
     D = src.shape[1]
     out = padded(plan.N, D, src.device)          # a GEMM operand: 128-byte aligned rows
     lo = padded(plan.N, D, src.device) if want_lo else None
     check(_lib.load().molclr_gine_aggregate_fwd(ptr(src), ptr(bn_coef), int(relu), ptr(plan.rowptr, torch.int32),
                                                 ptr(plan.col, torch.int32), ptr(plan.eattr, torch.uint8), ptr(B1), ptr(B2),
-                                                plan.N, D, ptr2d(out), out.stride(0), int(round_out), ptr2d(lo), stream()),
-          "gine_aggregate_fwd")
+                                                plan.N, D, ptr2d(out), out.stride(0), int(round_out), ptr2d(lo), drop[0], drop[1],
+                                                stream()), "gine_aggregate_fwd")
     return (out, lo) if want_lo else out
 
 
-def gine_aggregate_bwd(plan, ga, z_prev=None, bn_coef=None, relu=True, round_out=False):
+def gine_aggregate_bwd(plan, ga, z_prev=None, bn_coef=None, relu=True, round_out=False, drop=(0, 0.0)):
     """Returns (gy, partials, P): partials/P are None/0 when z_prev is None."""
     D = ga.shape[1]
     gy = torch.empty_like(ga)
@@ -167,18 +167,18 @@ def gine_aggregate_bwd(plan, ga, z_prev=None, bn_coef=None, relu=True, round_out
     n = C.c_int(0)
     check(_lib.load().molclr_gine_aggregate_bwd(ptr(ga), ptr(plan.rowptr_t, torch.int32), ptr(plan.col_t, torch.int32),
                                                 ptr(z_prev), ptr(bn_coef), int(relu), plan.N, D, ptr(gy), int(round_out),
-                                                ptr(partials), C.byref(n), stream()), "gine_aggregate_bwd")
+                                                ptr(partials), C.byref(n), drop[0], drop[1], stream()), "gine_aggregate_bwd")
     return gy, partials, n.value
 
 
-def relu_bn_bwd_stats(g, z_prev, bn_coef, relu=True):
+def relu_bn_bwd_stats(g, z_prev, bn_coef, relu=True, drop=(0, 0.0)):
     """gy = g * [relu(BN(z_prev)) > 0] and the (sum gy, sum gy*xhat) partials.  Returns (gy, partials, P)."""
     N, D = g.shape
     gy = torch.empty_like(g)
     partials = _empty(max_blocks(), 2, D, device=g.device)
     n = C.c_int(0)
     check(_lib.load().molclr_relu_bn_bwd_stats(ptr(g), ptr(z_prev), ptr(bn_coef), int(relu), N, D, ptr(gy), ptr(partials),
-                                               C.byref(n), stream()), "relu_bn_bwd_stats")
+                                               C.byref(n), drop[0], drop[1], stream()), "relu_bn_bwd_stats")
     return gy, partials, n.value
 
 
@@ -199,13 +199,13 @@ def row_sum(x):
     return out
 
 
-def bn_apply_fwd(z, bn_coef, relu, want_lo):
+def bn_apply_fwd(z, bn_coef, relu, want_lo, drop=(0, 0.0)):
     """(hi, lo) tensor-core operand pair of relu(BN(z)) (bn_coef None: of z itself), 128-byte aligned rows."""
     N, D = z.shape
     hi = padded(N, D, z.device)
     lo = padded(N, D, z.device) if want_lo else None
-    check(_lib.load().molclr_bn_apply_fwd(ptr(z), ptr(bn_coef), int(relu), N, D, ptr2d(hi), ptr2d(lo), hi.stride(0), stream()),
-          "bn_apply_fwd")
+    check(_lib.load().molclr_bn_apply_fwd(ptr(z), ptr(bn_coef), int(relu), N, D, ptr2d(hi), ptr2d(lo), hi.stride(0), drop[0], drop[1],
+                                          stream()), "bn_apply_fwd")
     return hi, lo
 
 
@@ -257,36 +257,39 @@ def bn_bwd_finalize(partials, P, N, gamma, coef, use_batch_stats):
     return dgamma, dbeta, bcoef
 
 
-def bn_bwd_apply(z, bcoef, gy=None, gp=None, plan=None, pool_mean=True, round_out=True):
+def bn_bwd_apply(z, bcoef, gy=None, gp=None, plan=None, pool_mode=0, round_out=True, argmax=None, drop=(0, 0.0)):
     N, D = z.shape
     gz = padded(N, D, z.device) if round_out else _empty(N, D, device=z.device)   # GEMM operand: 128-byte aligned rows
     dbias = _empty(D, device=z.device)
     partials = _empty(max_blocks(), D, device=z.device)
     n2g = ptr(plan.node2graph, torch.int32) if gp is not None else None
     gptr = ptr(plan.gptr, torch.int32) if gp is not None else None
-    check(_lib.load().molclr_bn_bwd_apply(ptr(gy), ptr(gp), n2g, gptr, int(pool_mean), ptr(z), ptr(bcoef), N, D, ptr2d(gz),
-                                          gz.stride(0), int(round_out), ptr(dbias), ptr(partials), stream()), "bn_bwd_apply")
+    check(_lib.load().molclr_bn_bwd_apply(ptr(gy), ptr(gp), n2g, gptr, int(pool_mode), ptr(argmax, torch.int32), ptr(z), ptr(bcoef), N, D,
+                                          ptr2d(gz), gz.stride(0), int(round_out), ptr(dbias), ptr(partials), drop[0], drop[1], stream()),
+          "bn_bwd_apply")
     return gz, dbias
 
 
-POOL_MODES = {"mean": 0, "add": 1}
+POOL_MODES = {"mean": 0, "add": 1, "max": 2}
 
 
-def pool_fwd(plan, z, bn_coef, pool_mode, relu=False, round_out=True, want_lo=False):
+def pool_fwd(plan, z, bn_coef, pool_mode, relu=False, round_out=True, want_lo=False, argmax=None, drop=(0, 0.0)):
     D = z.shape[1]
     out = padded(plan.G, D, z.device)
     lo = padded(plan.G, D, z.device) if want_lo else None
     check(_lib.load().molclr_pool_fwd(ptr(z), ptr(bn_coef), int(relu), ptr(plan.gptr, torch.int32), ptr(plan.gperm, torch.int32),
-                                      pool_mode, plan.G, D, ptr2d(out), out.stride(0), int(round_out), ptr2d(lo), stream()), "pool_fwd")
+                                      pool_mode, plan.G, D, ptr2d(out), out.stride(0), int(round_out), ptr2d(lo),
+                                      ptr(argmax, torch.int32), drop[0], drop[1], stream()), "pool_fwd")
     return (out, lo) if want_lo else out
 
 
-def pool_bwd_stats(plan, gp, z, bn_coef, pool_mode):
+def pool_bwd_stats(plan, gp, z, bn_coef, pool_mode, argmax=None, drop=(0, 0.0)):
     D = z.shape[1]
     partials = _empty(max_blocks(), 2, D, device=z.device)
     n = C.c_int(0)
     check(_lib.load().molclr_pool_bwd_stats(ptr(gp), ptr(plan.node2graph, torch.int32), ptr(plan.gptr, torch.int32), pool_mode,
-                                            ptr(z), ptr(bn_coef), plan.N, D, ptr(partials), C.byref(n), stream()), "pool_bwd_stats")
+                                            ptr(argmax, torch.int32), ptr(z), ptr(bn_coef), plan.N, D, ptr(partials), C.byref(n),
+                                            drop[0], drop[1], stream()), "pool_bwd_stats")
     return partials, n.value
 
 
@@ -304,6 +307,13 @@ def copy_cols(src, dst, cols):
 
 def _cudart_memcpy2d(dst, dpitch, src, spitch, width, height):
     check(_lib.load().molclr_copy_2d(dst, dpitch, src, spitch, width, height, stream()), "copy_2d")
+
+
+def dropout_mask(seed, p, N, D, device):
+    """The mask (0 or 1/(1-p)) the fused kernels apply for (seed, p): test / diagnostics hook."""
+    out = _empty(N, D, device=device)
+    check(_lib.load().molclr_dropout_mask(seed, p, N, D, ptr(out), stream()), "dropout_mask")
+    return out
 
 
 ACT_MODES = {"softplus": 0, "relu": 1}

@@ -77,6 +77,16 @@ def global_max_pool(x, batch, size=None):
 _POOLS = {"mean": global_mean_pool, "max": global_max_pool, "add": global_add_pool}
 
 
+def _dropout(model, layer, h):
+    """F.dropout(h, drop_ratio, training) -- or, when the test sets ``model.dropout_masks`` (a list of per-layer
+    [N, D] tensors holding 0 or 1/(1-p)), multiplication by that explicit mask, so that the CUDA kernels' counter-based
+    masks can be checked value by value."""
+    masks = getattr(model, "dropout_masks", None)
+    if masks is not None and model.training:
+        return h * masks[layer].to(h.dtype)
+    return F.dropout(h, model.drop_ratio, training=model.training)
+
+
 def _self_loop_attr(edge_attr, num_nodes):
     # ginet_molclr.py:34-37 / gcn_molclr.py:67-70: rows [4, 0] appended after the real edges
     sl = torch.zeros(num_nodes, 2)
@@ -136,9 +146,9 @@ class GINet(nn.Module):
             h = self.gnns[layer](h, data.edge_index, data.edge_attr)
             h = self.batch_norms[layer](h)
             if layer == self.num_layer - 1:
-                h = F.dropout(h, self.drop_ratio, training=self.training)
+                h = _dropout(self, layer, h)
             else:
-                h = F.dropout(F.relu(h), self.drop_ratio, training=self.training)
+                h = _dropout(self, layer, F.relu(h))
             layers.append(h)
         return (h, layers) if return_layers else h
 
@@ -215,9 +225,9 @@ class GCN(nn.Module):
             h = self.gnns[layer](h, data.edge_index, data.edge_attr)
             h = self.batch_norms[layer](h)
             if layer == self.num_layer - 1:
-                h = F.dropout(h, self.drop_ratio, training=self.training)
+                h = _dropout(self, layer, h)
             else:
-                h = F.dropout(F.relu(h), self.drop_ratio, training=self.training)
+                h = _dropout(self, layer, F.relu(h))
         h = self.pool(h, data.batch)
         h = self.feat_lin(h)
         out = self.out_lin(h)
@@ -257,9 +267,9 @@ class GINetFinetune(nn.Module):
             h = self.gnns[layer](h, data.edge_index, data.edge_attr)
             h = self.batch_norms[layer](h)
             if layer == self.num_layer - 1:
-                h = F.dropout(h, self.drop_ratio, training=self.training)
+                h = _dropout(self, layer, h)
             else:
-                h = F.dropout(F.relu(h), self.drop_ratio, training=self.training)
+                h = _dropout(self, layer, F.relu(h))
         h = self.pool(h, data.batch)
         h = self.feat_lin(h)
         return h, self.pred_head(h)
