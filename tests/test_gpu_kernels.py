@@ -273,7 +273,7 @@ def test_bn_finalize_and_pool():
     ognn.global_mean_pool(bn64(zz), bi.batch).backward(gp.double())
     partials, P = ops.pool_bwd_stats(plan, gp.to(DEV), z.to(DEV), coef, 0)
     dgamma, dbeta, bcoef = ops.bn_bwd_finalize(partials, P, N, bn.weight.detach().to(DEV), coef, True)
-    gz, dbias = ops.bn_bwd_apply(z.to(DEV), bcoef, gp=gp.to(DEV), plan=plan, pool_mean=True)
+    gz, dbias = ops.bn_bwd_apply(z.to(DEV), bcoef, gp=gp.to(DEV), plan=plan, pool_mode=0)
     assert rel_err(dgamma, bn64.weight.grad) < 1e-4 and rel_err(dbeta, bn64.bias.grad) < 1e-4
     assert rel_err(gz, zz.grad) < 2e-3          # gz is stored tf32-rounded
     assert float(dbias.abs().max()) < 1e-2 * float(gz.abs().max()) * N ** 0.5
