@@ -197,6 +197,10 @@ int molclr_gemm_mask_words(int64_t N);
 int molclr_gemm_tile_count(int64_t M, int64_t N, int b_mn);
 int molclr_gemm_workers(void);
 int molclr_gemm_tf32(const molclr_gemm_args* args /* host */, cudaStream_t stream);
+/* dW [O][I] (rows ldw apart) = dY^T X for row-major dY [R][O], X [R][I] (tf32-rounded): the weight gradient of a Linear
+ * (autograd of ginet_molclr.py:19-23,90-96; gcn_molclr.py:76).  Split-K over R, one wave, atomic accumulation. */
+int molclr_gemm_dw(const float* dY, int64_t ldy, const float* X, int64_t ldx, int64_t R, int64_t O, int64_t I, float* dW,
+                   int64_t ldw, cudaStream_t stream);
 
 /* ---- small elementwise ops ---------------------------------------------------------------------- */
 /* hi = tf32(src); lo (optional) = tf32(src - hi) */

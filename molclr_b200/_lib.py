@@ -69,6 +69,7 @@ SIGNATURES = {
     "molclr_gemm_tile_count": (i32, [i64, i64, i32]),
     "molclr_gemm_workers": (i32, []),
     "molclr_gemm_tf32": (i32, [C.POINTER(GemmArgs), vp]),
+    "molclr_gemm_dw": (i32, [vp, i64, vp, i64, i64, i64, i64, vp, i64, vp]),
     "molclr_round_tf32": (i32, [vp, vp, vp, i64, vp]),
     "molclr_round_tf32_2d": (i32, [vp, i64, vp, vp, i64, i64, i64, vp]),
     "molclr_copy_2d": (i32, [vp, sz, vp, sz, sz, sz, vp]),

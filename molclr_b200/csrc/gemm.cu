@@ -41,6 +41,9 @@ static int gemm_workers(bool pair) { return pair ? sm_count() / 2 : sm_count(); 
 template <int BN, bool FOUR, bool TWO>
 struct GemmCfg {
   static constexpr int BK = FOUR ? GEMM_BK4 : GEMM_BK;
+  // BN = 320 ("wide", split-K weight gradients on CTA pairs only): the tile is covered by two MMAs per K slice, N1 = 256
+  // and N2 = 64 columns, into adjacent TMEM columns (one accumulator buffer: such a launch gives every worker one tile).
+  static constexpr int N1 = BN > 256 ? 256 : BN, N2 = BN - N1;
   static constexpr int BN_CTA = TWO ? BN / 2 : BN;        // B rows staged by one CTA
   static constexpr int A_BYTES = GEMM_BM * BK * 4;
   static constexpr int B_BYTES = BN_CTA * BK * 4;
@@ -63,7 +66,7 @@ struct GemmCfg {
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int SMEM_BYTES = PIPE_BYTES + STAGING_BYTES + BAR_BYTES;
   static constexpr int TX_BYTES = (TWO ? 2 : 1) * STAGE_BYTES;   // bytes arriving on the (leader's) full barrier per stage
-  static_assert(BN % 32 == 0 && BN <= 256, "BN must be a multiple of 32 (MN-major B blocks) and <= 256");
+  static_assert(BN % 32 == 0 && (BN <= 256 || (BN == 320 && TWO && !FOUR)), "BN: multiple of 32, <= 256 (or the wide 320 on pairs)");
   static_assert(!TWO || BN_CTA % 16 == 0, "a CTA pair splits B in halves of whole 8-row groups");
   static_assert(STAGE_BYTES % 1024 == 0, "stage bases must stay 1024B aligned for the 128B swizzles");
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
@@ -207,7 +210,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       uint32_t it = 0;                                  // global k-block counter -> ring slot / phase
       for (int t = worker; t < total; t += num_workers) {
-        const int n0 = (t % n_tiles) * BN + (int)rank * Cfg::BN_CTA, m0 = ((t / n_tiles) % m_tiles) * TILE_M + (int)rank * GEMM_BM;
+        const int nb0 = (t % n_tiles) * BN;                                  // first column of the tile
+        const int n0 = nb0 + (int)rank * Cfg::BN_CTA, m0 = ((t / n_tiles) % m_tiles) * TILE_M + (int)rank * GEMM_BM;
         const int kb0 = (t / (n_tiles * m_tiles)) * p.kb_per_split;
         const int nkb_seg = min(p.num_kb, kb0 + p.kb_per_split) - kb0;
         const int nkb = FOUR ? nkb_seg : nkb_seg * p.segments;
@@ -234,7 +238,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int j = 0; j < GEMM_BM / 32; ++j) load(ad + j * Cfg::MN_BLOCK_BYTES, ma, m0 + 32 * j, kc);
             if (!p.b_mn) load(bd, mb, kc, n0);
             else
-              for (int j = 0; j < Cfg::BN_CTA / 32; ++j) load(bd + j * Cfg::MN_BLOCK_BYTES, mb, n0 + 32 * j, kc);
+              for (int j = 0; j < Cfg::BN_CTA / 32; ++j) {
+                // blocks of the first MMA (N1) first, then those of the second (N2); each CTA of a pair stages its half of both
+                constexpr int J1 = (TWO ? Cfg::N1 / 2 : Cfg::N1) / 32;
+                const int colb = j < J1 ? nb0 + (int)rank * (TWO ? Cfg::N1 / 2 : 0) + 32 * j
+                                        : nb0 + Cfg::N1 + (int)rank * (Cfg::N2 / 2) + 32 * (j - J1);
+                load(bd + j * Cfg::MN_BLOCK_BYTES, mb, colb, kc);
+              }
           }
         }
       }
@@ -243,10 +253,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0 && rank == 0) {
-      const uint32_t idesc = ptx::make_idesc_tf32(BN, p.a_mn != 0, p.b_mn != 0, TILE_M);
-      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
-        if (TWO) ptx::mma_tf32_ss_2cta(d, a, b, idesc, acc); else ptx::mma_tf32_ss(d, a, b, idesc, acc);
+      const uint32_t idesc = ptx::make_idesc_tf32(Cfg::N1, p.a_mn != 0, p.b_mn != 0, TILE_M);
+      const uint32_t idesc2 = ptx::make_idesc_tf32(Cfg::N2 > 0 ? Cfg::N2 : 16, p.a_mn != 0, p.b_mn != 0, TILE_M);
+      auto mma_i = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+        if (TWO) ptx::mma_tf32_ss_2cta(d, a, b, id, acc); else ptx::mma_tf32_ss(d, a, b, id, acc);
       };
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) { mma_i(d, a, b, idesc, acc); };
       auto commit = [&](uint64_t* bar) { if (TWO) ptx::mma_commit_2cta(bar); else ptx::mma_commit(bar); };
       // K-major tiles: rows of BK*4 bytes (128B or 64B swizzle), 8-row groups SBO apart.  MN-major: [BK k][32 mn] blocks
       // LBO apart, 4-k-row groups 512 B apart.
@@ -275,6 +287,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint64_t ad = ptx::make_smem_desc(a_base + k * a_kstep, a_lbo, a_sbo, a_lay);
             const uint64_t bd = ptx::make_smem_desc(b_base + k * b_kstep, b_lbo, b_sbo, b_lay);
             mma(d_tmem, ad, bd, (i | k) != 0 ? 1u : 0u);
+            if (Cfg::N2 > 0) {     // wide tile: the remaining N2 columns (MN-major B: its blocks follow those of the first MMA)
+              constexpr uint32_t b2_off = (uint32_t)((TWO ? Cfg::N1 / 2 : Cfg::N1) / 32) * Cfg::MN_BLOCK_BYTES;
+              const uint64_t bdw = ptx::make_smem_desc(b_base + b2_off + k * b_kstep, b_lbo, b_sbo, b_lay);
+              mma_i(d_tmem + Cfg::N1, ad, bdw, idesc2, (i | k) != 0 ? 1u : 0u);
+            }
             if (FOUR) {
               const uint64_t ad2 = ptx::make_smem_desc(a_base + Cfg::A_BYTES + k * a_kstep, a_lbo, a_sbo, a_lay);
               const uint64_t bd2 = ptx::make_smem_desc(b_base + Cfg::B_BYTES + k * b_kstep, b_lbo, b_sbo, b_lay);
@@ -729,7 +746,9 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   p.atomic_out = atomic ? 1 : 0;
   p.debug = gemm_debug_flags();
   // split-K weight gradients stay on single CTAs: their 300/600-wide outputs pad badly to 256-row pair tiles (MMA-bound)
-  const bool pair = gemm_pair() && !gemm_impl_simt() && !atomic;
+  const bool wide = atomic && job.wide && gemm_pair() && !gemm_impl_simt();
+  if (wide) MOLCLR_REQUIRE(p.a_mn && p.b_mn, "gemm: wide split-K tiles need both operands MN-major");
+  const bool pair = gemm_pair() && !gemm_impl_simt() && (!atomic || wide);
   const int tile_m = pair ? 2 * GEMM_BM : GEMM_BM;
   const int m_tiles = (p.M + tile_m - 1) / tile_m;
   p.stat_groups = molclr_gemm_colstat_tiles(p.M);
@@ -747,7 +766,8 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   const int kind = p.epi == EPI_NTX_FWD ? K_NTX_FWD : atomic ? K_ATOMIC : p.epi == EPI_NTX_W ? K_NTX_W
                    : (p.mask || p.addend) ? K_LATE : K_PLAIN;
   MOLCLR_REQUIRE(p.segments == 1 || kind == K_PLAIN, "gemm: the compensated product supports the plain epilogue only");
-  const int bn = (job.bn_hint && pair) ? job.bn_hint : gemm_bn(p.N, p.b_mn != 0, pair), nt = (p.N + bn - 1) / bn;
+  const int bn = wide ? 320 : (job.bn_hint && pair) ? job.bn_hint : gemm_bn(p.N, p.b_mn != 0, pair), nt = (p.N + bn - 1) / bn;
+  if (wide) MOLCLR_REQUIRE((long long)nt * m_tiles * splits <= gemm_workers(true), "gemm: a wide split-K launch must be one wave");
 #define MOLCLR_GEMM_CASE(BN_, FOUR_, KIND_, TWO_) \
   if (bn == BN_ && (p.segments > 1) == FOUR_ && kind == KIND_ && pair == TWO_) return launch_tc<BN_, FOUR_, KIND_, TWO_>(job, p, nt, m_tiles, splits, stream);
 #define MOLCLR_GEMM_KINDS(BN_, TWO_) \
@@ -755,7 +775,7 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   MOLCLR_GEMM_CASE(BN_, false, K_NTX_W, TWO_) MOLCLR_GEMM_CASE(BN_, false, K_NTX_FWD, TWO_) MOLCLR_GEMM_CASE(BN_, false, K_ATOMIC, TWO_)
   MOLCLR_GEMM_KINDS(160, false) MOLCLR_GEMM_KINDS(256, false)
   MOLCLR_GEMM_KINDS(160, true) MOLCLR_GEMM_KINDS(192, true) MOLCLR_GEMM_KINDS(256, true)
-  MOLCLR_GEMM_CASE(128, false, K_PLAIN, true)
+  MOLCLR_GEMM_CASE(128, false, K_PLAIN, true) MOLCLR_GEMM_CASE(320, false, K_ATOMIC, true)
 #undef MOLCLR_GEMM_KINDS
 #undef MOLCLR_GEMM_CASE
   set_error("gemm: no kernel instance for bn=%d segments=%d kind=%d", bn, p.segments, kind);
@@ -781,6 +801,39 @@ extern "C" int molclr_gemm_tile_count(int64_t M, int64_t N, int b_mn) {
   return (int)(((M + GEMM_BM - 1) / GEMM_BM) * ((N + bn - 1) / bn));
 }
 extern "C" int molclr_gemm_workers(void) { return gemm_workers(false); }
+
+// dW [O][I] = dY^T X for row-major dY [R][O], X [R][I]: the weight gradient of a Linear.  Both operands are consumed MN-major
+// in place; the reduction over R is split across one wave of workers and accumulated atomically.  Orientation (which operand
+// is "M") and tile shape (128 x 160/256 on single CTAs, or 256 x 320 on CTA pairs) are chosen to minimise the operand bytes
+// every K row costs on the L2 -> shared-memory path, n_tiles * M + m_tiles * N, which is what bounds this kernel.
+extern "C" int molclr_gemm_dw(const float* dY, int64_t ldy, const float* X, int64_t ldx, int64_t R, int64_t O, int64_t I, float* dW,
+                              int64_t ldw, cudaStream_t stream) {
+  MOLCLR_REQUIRE(R > 0 && O > 0 && I > 0 && R < (1ll << 31) && O < (1ll << 31) && I < (1ll << 31), "gemm_dw: bad extents");
+  long long best = -1;
+  int best_swap = 0, best_wide = 0, best_tiles = 1;
+  for (int swap = 0; swap < 2; ++swap)
+    for (int wide = 0; wide < 2; ++wide) {
+      const long long M = swap ? I : O, N = swap ? O : I;
+      if (wide && (!gemm_pair() || gemm_impl_simt() || M <= GEMM_BM)) continue;
+      const int bn = wide ? 320 : gemm_bn(N, true, false), tm = wide ? 2 * GEMM_BM : GEMM_BM;
+      const long long mt = (M + tm - 1) / tm, nt = (N + bn - 1) / bn, cost = nt * M + mt * N;
+      if (mt * nt > gemm_workers(wide != 0)) continue;
+      if (best < 0 || cost < best) { best = cost; best_swap = swap; best_wide = wide; best_tiles = (int)(mt * nt); }
+    }
+  MOLCLR_REQUIRE(best >= 0, "gemm_dw: output [%lld x %lld] has more tiles than the GPU has workers", (long long)O, (long long)I);
+  const int num_kb = (int)((R + GEMM_BK - 1) / GEMM_BK);
+  int split = gemm_workers(best_wide != 0) / best_tiles;
+  if (split > num_kb / 8) split = num_kb / 8;
+  if (split < 1) split = 1;
+  GemmJob j;
+  memset(&j, 0, sizeof(j));
+  j.A = best_swap ? X : dY; j.lda = best_swap ? ldx : ldy;
+  j.B = best_swap ? dY : X; j.ldb = best_swap ? ldy : ldx;
+  j.p.M = (int)(best_swap ? I : O); j.p.N = (int)(best_swap ? O : I); j.p.K = (int)R; j.p.a_mn = 1; j.p.b_mn = 1;
+  j.p.out = dW; j.p.ldo = ldw; j.p.transpose_out = best_swap; j.p.alpha = 1.f; j.p.epi = EPI_GENERIC;
+  j.split_k = split; j.wide = best_wide;
+  return gemm_run(j, stream);
+}
 
 extern "C" int molclr_gemm_tf32(const molclr_gemm_args* args, cudaStream_t stream) {
   const molclr_gemm_args& a = *args;

@@ -43,6 +43,7 @@ struct GemmJob {
   const float* A; long long lda; const float* B; long long ldb;
   const float* A_lo; const float* B_lo;   // both non-null selects the 3-segment compensated product (same layout/ld as A, B)
   int split_k;
+  int wide;                    // split-K only: 256 x 320 tiles on CTA pairs (both operands MN-major)
   int bn_hint;                 // 0, or a column-tile width to use instead of the default (more tiles for narrow outputs)
   GemmParams p;                // M,N,K,a_mn,b_mn and the epilogue fields filled by the caller
 };

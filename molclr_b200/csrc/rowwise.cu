@@ -153,7 +153,7 @@ struct CsrRowPrefetch {
 
 // SCALAR (GCNConv, gcn_molclr.py:72-88): the bond tables are [5][1] / [3][1] scalars broadcast over the D features and a
 // bias row is added after the sum (`out += bias`, gcn_molclr.py:81-82); the staged table then holds splatted scalars.
-template <int NCH, bool HAS_BN, bool SCALAR>
+template <int NCH, bool HAS_BN, bool SCALAR, bool DROP>
 __global__ void __launch_bounds__(kRowThreads) gine_aggregate_fwd_kernel(
     const float* __restrict__ src, const float* __restrict__ coef, int relu,
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const uint8_t* __restrict__ eattr,
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_fwd_kernel(
       const float4 s = sc[q], b = sh[q];
       v.x = fmaf(v.x, s.x, b.x); v.y = fmaf(v.y, s.y, b.y); v.z = fmaf(v.z, s.z, b.z); v.w = fmaf(v.w, s.w, b.w);
       if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-      if (drop.thr) v = f4_mul(v, drop_mask4(drop, row, q, D4));
+      if (DROP) v = f4_mul(v, drop_mask4(drop, row, q, D4));
     }
     return v;
   };
@@ -264,7 +264,7 @@ __device__ __forceinline__ void block_reduce_rows(float4 (&acc)[NV][NCH], float4
 // ------------------------------------------------------------------------------------------------
 // GATHER = false: no neighbour terms (g_h = g_a): the ReLU / BatchNorm-statistics stage alone, used by the GCN backward
 // where the gradient arrives from a GEMM instead of an aggregation.
-template <int NCH, int MODE, bool GATHER>
+template <int NCH, int MODE, bool GATHER, bool DROP>
 __global__ void __launch_bounds__(kRowThreads) gine_aggregate_bwd_kernel(
     const float* __restrict__ ga, const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ col_t,
     const float* __restrict__ z, const float* __restrict__ coef, int relu, int N, int D,
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_bwd_kernel(
             if (!(fmaf(zv.z, s.z, b.z) > 0.f)) r.z = 0.f;
             if (!(fmaf(zv.w, s.w, b.w) > 0.f)) r.w = 0.f;
           }
-          if (drop.thr) r = f4_mul(r, drop_mask4(drop, i, q, D4));
+          if (DROP) r = f4_mul(r, drop_mask4(drop, i, q, D4));
           st[0][j] = f4_add(st[0][j], r);
           st[1][j].x = fmaf(r.x, (zv.x - m.x) * is.x, st[1][j].x);
           st[1][j].y = fmaf(r.y, (zv.y - m.y) * is.y, st[1][j].y);
@@ -563,27 +563,41 @@ __global__ void __launch_bounds__(kRowThreads) pool_fwd_kernel(
     const float init = (pool_mode == 2 && end > beg) ? -INFINITY : 0.f;
 #pragma unroll
     for (int j = 0; j < NCH; ++j) { acc[j] = make_float4(init, init, init, init); am[j] = make_int4(-1, -1, -1, -1); }
-    for (int p = beg; p < end; ++p) {
-      const int n = __ldg(gperm + p);
+    auto consume = [&](float4 v, int n, int q, int j) {
+      const float4 s = sc[q], b = sh[q];
+      v.x = fmaf(v.x, s.x, b.x); v.y = fmaf(v.y, s.y, b.y); v.z = fmaf(v.z, s.z, b.z); v.w = fmaf(v.w, s.w, b.w);
+      if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      if (drop.thr) v = f4_mul(v, drop_mask4(drop, n, q, D4));
+      if (pool_mode == 2) {                             // global_max_pool: first maximum wins
+        if (v.x > acc[j].x) { acc[j].x = v.x; am[j].x = n; }
+        if (v.y > acc[j].y) { acc[j].y = v.y; am[j].y = n; }
+        if (v.z > acc[j].z) { acc[j].z = v.z; am[j].z = n; }
+        if (v.w > acc[j].w) { acc[j].w = v.w; am[j].w = n; }
+      } else {
+        acc[j] = f4_add(acc[j], v);
+      }
+    };
+    for (int p = beg; p < end; p += 4) {                  // four node rows in flight; consumed in node order
+      int n[4];
+      float4 v[4][NCH];
 #pragma unroll
-      for (int j = 0; j < NCH; ++j) {
-        const int q = lane + 32 * j;
-        if (q < D4) {
-          float4 v = ld_stream_f4(z + (size_t)n * D + 4 * q);
-          const float4 s = sc[q], b = sh[q];
-          v.x = fmaf(v.x, s.x, b.x); v.y = fmaf(v.y, s.y, b.y); v.z = fmaf(v.z, s.z, b.z); v.w = fmaf(v.w, s.w, b.w);
-          if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-          if (drop.thr) v = f4_mul(v, drop_mask4(drop, n, q, D4));
-          if (pool_mode == 2) {                             // global_max_pool: first maximum wins
-            if (v.x > acc[j].x) { acc[j].x = v.x; am[j].x = n; }
-            if (v.y > acc[j].y) { acc[j].y = v.y; am[j].y = n; }
-            if (v.z > acc[j].z) { acc[j].z = v.z; am[j].z = n; }
-            if (v.w > acc[j].w) { acc[j].w = v.w; am[j].w = n; }
-          } else {
-            acc[j] = f4_add(acc[j], v);
-          }
+      for (int u = 0; u < 4; ++u) {
+        n[u] = (p + u < end) ? __ldg(gperm + p + u) : -1;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+          const int q = lane + 32 * j;
+          v[u][j] = (q < D4 && n[u] >= 0) ? ld_stream_f4(z + (size_t)n[u] * D + 4 * q) : f4_zero();
         }
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (n[u] >= 0) {
+#pragma unroll
+          for (int j = 0; j < NCH; ++j) {
+            const int q = lane + 32 * j;
+            if (q < D4) consume(v[u][j], n[u], q, j);
+          }
+        }
     }
     const bool pool_mean = pool_mode == 0;
     const float cntf = (float)max(end - beg, 1);             // count.clamp(min=1)
@@ -879,15 +893,19 @@ static int aggregate_fwd_launch(const float* src, const float* bn_coef, int relu
   const size_t smem = (size_t)(kNumEdgeClass + 2) * D * sizeof(float);
   NCH_DISPATCH(D / 4, {
     if (scalar) {
-      auto k = gine_aggregate_fwd_kernel<NCH, false, true>;
+      auto k = gine_aggregate_fwd_kernel<NCH, false, true, false>;
       k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
           src, nullptr, 0, rowptr, col, eattr, B1, B2, bias, (int)N, D, out, ld_out, round_tf32_out, out_lo, drop);
+    } else if (bn_coef && drop.thr) {
+      auto k = gine_aggregate_fwd_kernel<NCH, true, false, true>;
+      k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
+          src, bn_coef, relu, rowptr, col, eattr, B1, B2, nullptr, (int)N, D, out, ld_out, round_tf32_out, out_lo, drop);
     } else if (bn_coef) {
-      auto k = gine_aggregate_fwd_kernel<NCH, true, false>;
+      auto k = gine_aggregate_fwd_kernel<NCH, true, false, false>;
       k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
           src, bn_coef, relu, rowptr, col, eattr, B1, B2, nullptr, (int)N, D, out, ld_out, round_tf32_out, out_lo, drop);
     } else {
-      auto k = gine_aggregate_fwd_kernel<NCH, false, false>;
+      auto k = gine_aggregate_fwd_kernel<NCH, false, false, false>;
       k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
           src, nullptr, 0, rowptr, col, eattr, B1, B2, nullptr, (int)N, D, out, ld_out, round_tf32_out, out_lo, drop);
     }
@@ -915,6 +933,16 @@ extern "C" int molclr_gcn_aggregate_fwd(const float* src, const int32_t* rowptr,
 // their grid): callers size `partials` as [molclr_rowwise_max_blocks()][NV][D].
 extern "C" int molclr_rowwise_max_blocks(void) { return 8 * sm_count(); }
 
+template <int NCH, bool GATHER, bool DROP>
+static int launch_bwd_fused(const float* ga, const int32_t* rowptr_t, const int32_t* col_t, const float* z_prev, const float* bn_coef,
+                            int relu, int64_t N, int D, float* gy, float* partials, int round_out, const DropCfg& drop, size_t smem,
+                            cudaStream_t stream) {
+  auto k = gine_aggregate_bwd_kernel<NCH, 1, GATHER, DROP>;
+  const int grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
+  k<<<grid, kRowThreads, smem, stream>>>(ga, rowptr_t, col_t, z_prev, bn_coef, relu, (int)N, D, gy, partials, round_out, drop);
+  return grid;
+}
+
 static int aggregate_bwd_launch(const float* ga, const int32_t* rowptr_t, const int32_t* col_t, bool gather, const float* z_prev,
                                 const float* bn_coef, int relu, int64_t N, int D, float* gy, int round_out, float* partials,
                                 int* num_partials, const DropCfg drop, cudaStream_t stream) {
@@ -926,19 +954,14 @@ static int aggregate_bwd_launch(const float* ga, const int32_t* rowptr_t, const 
     if (z_prev) {
       const size_t smem = (size_t)(4 + 2 * kRowWarps) * D * sizeof(float);
       int grid;
-      if (gather) {
-        auto k = gine_aggregate_bwd_kernel<NCH, 1, true>;
-        grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
-        k<<<grid, kRowThreads, smem, stream>>>(ga, rowptr_t, col_t, z_prev, bn_coef, relu, (int)N, D, gy, partials, round_out, drop);
-      } else {
-        auto k = gine_aggregate_bwd_kernel<NCH, 1, false>;
-        grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
-        k<<<grid, kRowThreads, smem, stream>>>(ga, nullptr, nullptr, z_prev, bn_coef, relu, (int)N, D, gy, partials, round_out, drop);
-      }
+if (gather && drop.thr) grid = launch_bwd_fused<NCH, true, true>(ga, rowptr_t, col_t, z_prev, bn_coef, relu, N, D, gy, partials, round_out, drop, smem, stream);
+      else if (gather) grid = launch_bwd_fused<NCH, true, false>(ga, rowptr_t, col_t, z_prev, bn_coef, relu, N, D, gy, partials, round_out, drop, smem, stream);
+      else if (drop.thr) grid = launch_bwd_fused<NCH, false, true>(ga, nullptr, nullptr, z_prev, bn_coef, relu, N, D, gy, partials, round_out, drop, smem, stream);
+      else grid = launch_bwd_fused<NCH, false, false>(ga, nullptr, nullptr, z_prev, bn_coef, relu, N, D, gy, partials, round_out, drop, smem, stream);
       if (num_partials) *num_partials = grid;
     } else {
       MOLCLR_REQUIRE(gather, "relu_bn_bwd_stats: z_prev is required");
-      auto k = gine_aggregate_bwd_kernel<NCH, 0, true>;
+      auto k = gine_aggregate_bwd_kernel<NCH, 0, true, false>;
       k<<<persistent_grid(k, kRowThreads, 0, kRowWarps, N), kRowThreads, 0, stream>>>(ga, rowptr_t, col_t, nullptr, nullptr, 0,
                                                                                         (int)N, D, gy, nullptr, round_out, drop);
     }

@@ -82,17 +82,7 @@ def gemm_dw(dY, X):
     I = X.shape[1]
     dW = _empty(O, I, device=dY.device)
 
-    lib = _lib.load()
-    tiles_a, tiles_b = lib.molclr_gemm_tile_count(O, I, 1), lib.molclr_gemm_tile_count(I, O, 1)
-    swap = tiles_b < tiles_a
-    tiles = tiles_b if swap else tiles_a
-    num_kb = -(-R // 32)
-    # one wave of work items: tiles * split <= #workers (each worker then streams a long K range)
-    split = max(1, min(lib.molclr_gemm_workers() // tiles, max(1, num_kb // 8)))
-    if swap:    # compute dW^T = X^T dY with the wider operand on M, store transposed
-        gemm(X, dY, I, O, R, a_mn=True, b_mn=True, out=dW, transpose_out=True, split_k=split)
-    else:
-        gemm(dY, X, O, I, R, a_mn=True, b_mn=True, out=dW, split_k=split)
+    check(_lib.load().molclr_gemm_dw(ptr2d(dY), dY.stride(0), ptr2d(X), X.stride(0), R, O, I, ptr(dW), dW.stride(0), stream()), "gemm_dw")
     return dW
 
 
