@@ -42,29 +42,70 @@ __global__ void plan_count_kernel(const int64_t* __restrict__ x, const int64_t* 
   if (err) atomicOr(&status[0], err);
 }
 
-// Exclusive scan of `cnt[0..n)` into `ptr[0..n]`, one block per array (blockIdx.x selects).
+// Exclusive scan of `cnt[0..n)` into `ptr[0..n]` for three arrays at once (blockIdx.y selects the array), in three
+// phases over kScanChunk-element chunks: chunk sums -> scan of the chunk sums (one block per array) -> in-chunk scan
+// plus the chunk offset.  (The first version scanned each array with ONE block: 108 us for N = 102k nodes.)
 struct ScanJob { const int32_t* cnt; int32_t* ptr; int64_t n; };
-struct ScanJobs { ScanJob j[3]; };
+struct ScanJobs { ScanJob j[3]; int32_t* bsum; int64_t nb_max; };      // bsum: [3][nb_max] chunk sums, then chunk offsets
+constexpr int kScanThreads = 256, kScanPerThread = 8, kScanChunk = kScanThreads * kScanPerThread;
 
-__global__ void plan_scan_kernel(ScanJobs jobs) {
-  const ScanJob job = jobs.j[blockIdx.x];
-  __shared__ int32_t part[1024];
-  const int t = threadIdx.x;
-  const int64_t chunk = (job.n + blockDim.x - 1) / blockDim.x;
-  const int64_t b = t * chunk, e = min(job.n, b + chunk);
-  int32_t s = 0;
-  for (int64_t k = b; k < e; ++k) s += job.cnt[k];
-  part[t] = s;
+__device__ __forceinline__ int32_t block_exclusive_scan(int32_t v, int32_t* warp_sums, int32_t& total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) warp_sums[w] = inc;
   __syncthreads();
-  for (int off = 1; off < (int)blockDim.x; off <<= 1) {       // Hillis-Steele inclusive scan
-    int32_t v = (t >= off) ? part[t - off] : 0;
-    __syncthreads();
-    part[t] += v;
-    __syncthreads();
+  int32_t base = 0, tot = 0;
+  for (int k = 0; k < nw; ++k) { const int32_t sv = warp_sums[k]; if (k < w) base += sv; tot += sv; }
+  total = tot;
+  __syncthreads();
+  return base + inc - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) plan_scan_sums_kernel(ScanJobs jobs) {
+  const ScanJob job = jobs.j[blockIdx.y];
+  const int64_t c0 = (int64_t)blockIdx.x * kScanChunk;
+  if (c0 >= job.n) return;
+  __shared__ int32_t ws[kScanThreads / 32];
+  int32_t s = 0;
+  for (int i = 0; i < kScanPerThread; ++i) {
+    const int64_t k = c0 + (int64_t)i * kScanThreads + threadIdx.x;
+    if (k < job.n) s += job.cnt[k];
   }
-  int32_t run = part[t] - s;                                    // exclusive prefix of this chunk
-  for (int64_t k = b; k < e; ++k) { job.ptr[k] = run; run += job.cnt[k]; }
-  if (t == (int)blockDim.x - 1) job.ptr[job.n] = part[t];
+  int32_t total;
+  block_exclusive_scan(s, ws, total);
+  if (threadIdx.x == 0) jobs.bsum[blockIdx.y * jobs.nb_max + blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) plan_scan_offsets_kernel(ScanJobs jobs) {
+  const ScanJob job = jobs.j[blockIdx.x];
+  int32_t* bs = jobs.bsum + blockIdx.x * jobs.nb_max;
+  const int64_t nb = (job.n + kScanChunk - 1) / kScanChunk;
+  __shared__ int32_t ws[32];
+  const int64_t per = (nb + blockDim.x - 1) / blockDim.x, b = threadIdx.x * per, e = min(nb, b + per);
+  int32_t s = 0;
+  for (int64_t k = b; k < e; ++k) s += bs[k];
+  int32_t total;
+  int32_t run = block_exclusive_scan(s, ws, total);
+  for (int64_t k = b; k < e; ++k) { const int32_t v = bs[k]; bs[k] = run; run += v; }
+  if (threadIdx.x == 0) job.ptr[job.n] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) plan_scan_apply_kernel(ScanJobs jobs) {
+  const ScanJob job = jobs.j[blockIdx.y];
+  const int64_t c0 = (int64_t)blockIdx.x * kScanChunk;
+  if (c0 >= job.n) return;
+  __shared__ int32_t ws[kScanThreads / 32];
+  // thread t owns kScanPerThread CONSECUTIVE elements of the chunk
+  const int64_t k0 = c0 + (int64_t)threadIdx.x * kScanPerThread;
+  int32_t v[kScanPerThread], s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanPerThread; ++i) { v[i] = (k0 + i < job.n) ? job.cnt[k0 + i] : 0; s += v[i]; }
+  int32_t total;
+  int32_t run = block_exclusive_scan(s, ws, total) + jobs.bsum[blockIdx.y * jobs.nb_max + blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < kScanPerThread; ++i) { if (k0 + i < job.n) job.ptr[k0 + i] = run; run += v[i]; }
 }
 
 __global__ void plan_fill_kernel(const int64_t* __restrict__ ei, int64_t N, int64_t E,
@@ -136,9 +177,11 @@ __global__ void plan_rows_kernel(const int64_t* __restrict__ ei, const int64_t* 
 
 using namespace molclr;
 
+static int64_t scan_chunks(int64_t n) { return (n + kScanChunk - 1) / kScanChunk + 1; }
+
 extern "C" size_t molclr_plan_workspace_bytes(int64_t N, int64_t E, int64_t G) {
   (void)E;
-  return sizeof(int32_t) * (size_t)(2 * N + G + 16);
+  return sizeof(int32_t) * (size_t)(2 * N + G + 16 + 3 * scan_chunks(N > G ? N : G));
 }
 
 extern "C" int molclr_plan_build(const int64_t* x, const int64_t* edge_index, const int64_t* edge_attr,
@@ -168,8 +211,15 @@ extern "C" int molclr_plan_build(const int64_t* x, const int64_t* edge_index, co
   jobs.j[0] = {deg_in, rowptr, N};
   jobs.j[1] = {deg_out, rowptr_t, N};
   jobs.j[2] = {gcount, gptr, G};
-  plan_scan_kernel<<<3, 1024, 0, stream>>>(jobs);
-  MOLCLR_CHECK_LAUNCH("plan_scan");
+  jobs.nb_max = scan_chunks(N > G ? N : G);
+  jobs.bsum = gcount + G + 16;
+  const dim3 sgrid((unsigned)jobs.nb_max, 3);
+  plan_scan_sums_kernel<<<sgrid, kScanThreads, 0, stream>>>(jobs);
+  MOLCLR_CHECK_LAUNCH("plan_scan_sums");
+  plan_scan_offsets_kernel<<<3, 1024, 0, stream>>>(jobs);
+  MOLCLR_CHECK_LAUNCH("plan_scan_offsets");
+  plan_scan_apply_kernel<<<sgrid, kScanThreads, 0, stream>>>(jobs);
+  MOLCLR_CHECK_LAUNCH("plan_scan_apply");
   plan_fill_kernel<<<blocks, threads, 0, stream>>>(edge_index, N, E, node2graph, rowptr, rowptr_t, gptr,
                                                    deg_in, deg_out, gcount, col, col_t, gperm);
   MOLCLR_CHECK_LAUNCH("plan_fill");
