@@ -16,18 +16,35 @@ namespace molclr {
 
 constexpr int kStripe = 2048;     // W stripe [R][2048] fp32: 64 MB at R = 8192, L2-resident between the two GEMMs
 
-__global__ void ntx_merge_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum, int tiles, int R,
-                                 float* __restrict__ row_lse) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= R) return;
-  float m = -INFINITY;
-  for (int t = 0; t < tiles; ++t) m = fmaxf(m, part_max[(size_t)t * R + r]);
-  float s = 0.f;
-  for (int t = 0; t < tiles; ++t) {
-    const float pm = part_max[(size_t)t * R + r];
-    if (pm > -INFINITY) s += part_sum[(size_t)t * R + r] * __expf(pm - m);
+// One block handles 32 rows: threadIdx.x = row (coalesced partial reads), threadIdx.y strides over the column-tile partials;
+// the 8 y-partials of a row are merged through shared memory in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) ntx_merge_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum, int tiles, int R,
+                                                        float* __restrict__ row_lse) {
+  __shared__ float s_m[8][33], s_s[8][33];
+  const int r = blockIdx.x * 32 + threadIdx.x;
+  float m = -INFINITY, s = 0.f;
+  if (r < R)
+    for (int t = threadIdx.y; t < tiles; t += 8) {
+      const float pm = part_max[(size_t)t * R + r];
+      if (pm > -INFINITY) {
+        const float nm = fmaxf(m, pm);
+        s = s * __expf(m - nm) + part_sum[(size_t)t * R + r] * __expf(pm - nm);
+        m = nm;
+      }
+    }
+  s_m[threadIdx.y][threadIdx.x] = m; s_s[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && r < R) {
+    for (int k = 1; k < 8; ++k) {
+      const float pm = s_m[k][threadIdx.x];
+      if (pm > -INFINITY) {
+        const float nm = fmaxf(m, pm);
+        s = s * __expf(m - nm) + s_s[k][threadIdx.x] * __expf(pm - nm);
+        m = nm;
+      }
+    }
+    row_lse[r] = m + logf(s);
   }
-  row_lse[r] = m + logf(s);
 }
 
 // loss = (1/Rc) * sum_r (row_lse[r] - row_pos[r]); single block, fixed order -> deterministic.
@@ -85,7 +102,7 @@ extern "C" int molclr_ntxent_fwd(const float* rep, const float* cols, int64_t R,
   p.part_max = part_max; p.part_sum = part_sum; p.row_pos = row_pos;
   int rc = gemm_run(j, stream);
   if (rc) return rc;
-  ntx_merge_kernel<<<(int)((R + 255) / 256), 256, 0, stream>>>(part_max, part_sum, tiles, (int)R, row_lse);
+  ntx_merge_kernel<<<(int)((R + 31) / 32), dim3(32, 8), 0, stream>>>(part_max, part_sum, tiles, (int)R, row_lse);
   MOLCLR_CHECK_LAUNCH("ntx_merge");
   if (loss) {
     ntx_loss_kernel<<<1, 1024, 0, stream>>>(row_lse, row_pos, (int)R, 1.0f / (float)Rc, loss);
