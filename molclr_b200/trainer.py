@@ -1,0 +1,187 @@
+"""Trainer shell for MolCLR pre-training on the molclr_b200 kernels.
+
+Mirrors what ``molclr.py`` does around the hot path -- same ``config.yaml`` keys, same optimiser / schedule / checkpoint
+behaviour -- as thin PyTorch host code:
+
+* ``MolCLR(dataset, config).train()``: Adam(init_lr, weight_decay) (molclr.py:84-87), cosine annealing after ``warm_up``
+  epochs (88-91,146-147), validation in eval mode every ``eval_every_n_epochs`` with best-model checkpointing (131-140),
+  periodic ``model_{epoch}.pth`` (142-143), ``load_model`` resume from ``./ckpt/<name>/checkpoints/model.pth`` (149-158),
+  TensorBoard scalars when tensorboard is importable (116-118,139).
+* ``SyntheticMoleculeDatasetWrapper(batch_size, num_workers, valid_size, data_path)``: stands in for
+  ``dataset.MoleculeDatasetWrapper`` (RDKit is not a dependency): deterministic synthetic molecules with the reference's
+  node-mask / bond-delete augmentation (dataset.py:112-145), ``drop_last`` batches of (xis, xjs).
+
+    python -m molclr_b200.trainer [config.yaml] [--epochs N] [--steps-per-epoch K]
+"""
+import math
+import os
+import shutil
+import sys
+import time
+
+import torch
+
+from . import GCN, GINet, NTXentLoss, normalize
+from .synth import make_pair_batch
+
+DEFAULT_CONFIG = {
+    "batch_size": 512, "warm_up": 10, "epochs": 100, "load_model": "None", "eval_every_n_epochs": 1, "save_every_n_epochs": 5,
+    "log_every_n_steps": 50, "fp16_precision": False, "init_lr": 0.0005, "weight_decay": "1e-5", "gpu": "cuda:0", "model_type": "gin",
+    "model": {"num_layer": 5, "emb_dim": 300, "feat_dim": 512, "drop_ratio": 0, "pool": "mean"},
+    "aug": "node", "dataset": {"num_workers": 12, "valid_size": 0.05, "data_path": "synthetic:20000"},
+    "loss": {"temperature": 0.1, "use_cosine_similarity": True},
+}
+
+
+class _Loader:
+    """Iterable of (xis, xjs) pinned host batches; batch k of epoch e is a pure function of (seed, e, k)."""
+
+    def __init__(self, batch_size, num_batches, seed, reshuffle):
+        self.batch_size, self.num_batches, self.seed, self.reshuffle, self.epoch = batch_size, num_batches, seed, reshuffle, 0
+
+    def __len__(self):
+        return self.num_batches
+
+    def __iter__(self):
+        base = self.seed + (self.epoch * 1_000_003 if self.reshuffle else 0)
+        self.epoch += 1
+        for k in range(self.num_batches):
+            xis, xjs = make_pair_batch(self.batch_size, seed=base + k)
+            yield xis.pin_memory(), xjs.pin_memory()
+
+
+class SyntheticMoleculeDatasetWrapper:
+    """Same constructor as dataset.MoleculeDatasetWrapper (dataset.py:153-159).  ``data_path = "synthetic:<count>"`` sets the
+    number of molecules; the train / validation split follows ``valid_size`` and both loaders drop the last ragged batch
+    (dataset.py:176-184)."""
+
+    def __init__(self, batch_size, num_workers, valid_size, data_path):
+        self.batch_size, self.num_workers, self.valid_size = batch_size, num_workers, valid_size
+        self.num_molecules = int(str(data_path).split(":", 1)[1]) if str(data_path).startswith("synthetic:") else 20000
+
+    def get_data_loaders(self):
+        n_valid = int(math.floor(self.valid_size * self.num_molecules))
+        n_train = self.num_molecules - n_valid
+        return (_Loader(self.batch_size, n_train // self.batch_size, seed=1, reshuffle=True),
+                _Loader(self.batch_size, max(n_valid // self.batch_size, 1), seed=900_000_007, reshuffle=False))
+
+
+class MolCLR:
+    def __init__(self, dataset, config, log_root="ckpt"):
+        self.config, self.dataset = config, dataset
+        if not torch.cuda.is_available() or config["gpu"] == "cpu":
+            raise RuntimeError("molclr_b200.trainer needs a CUDA device (the kernels have no CPU path)")
+        self.device = torch.device(config["gpu"])
+        torch.cuda.set_device(self.device)
+        self.log_dir = os.path.join(log_root, time.strftime("%b%d_%H-%M-%S"))
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+            self.writer = SummaryWriter(log_dir=self.log_dir)
+        except Exception:                                   # tensorboard is optional here
+            self.writer = None
+        self.nt_xent_criterion = NTXentLoss(self.device, config["batch_size"], **config["loss"])
+
+    # the hot path: molclr.py:55-67
+    def _step(self, model, xis, xjs, n_iter=None):
+        _ris, zis = model(xis)
+        _rjs, zjs = model(xjs)
+        return self.nt_xent_criterion(normalize(zis, dim=1), normalize(zjs, dim=1))
+
+    def _scalar(self, tag, value, step):
+        if self.writer is not None:
+            self.writer.add_scalar(tag, value, global_step=step)
+
+    def _build_model(self):
+        kind = self.config["model_type"]
+        if kind not in ("gin", "gcn"):
+            raise ValueError("Undefined GNN model.")
+        model = (GINet if kind == "gin" else GCN)(**self.config["model"]).to(self.device)
+        return self._load_pre_trained_weights(model)
+
+    def train(self, max_steps_per_epoch=None):
+        cfg = self.config
+        train_loader, valid_loader = self.dataset.get_data_loaders()
+        model = self._build_model()
+        weight_decay = cfg["weight_decay"]
+        weight_decay = float(eval(weight_decay)) if isinstance(weight_decay, str) else float(weight_decay)   # molclr.py:86
+        optimizer = torch.optim.Adam(model.parameters(), cfg["init_lr"], weight_decay=weight_decay, fused=True)
+        scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=max(cfg["epochs"] - cfg["warm_up"], 1), eta_min=0)
+        ckpt_dir = os.path.join(self.log_dir, "checkpoints")
+        os.makedirs(ckpt_dir, exist_ok=True)
+        if os.path.exists("./config.yaml"):
+            shutil.copy("./config.yaml", os.path.join(ckpt_dir, "config.yaml"))
+        n_iter, valid_n_iter, best_valid, history = 0, 0, float("inf"), []
+        for epoch in range(cfg["epochs"]):
+            for bn, (xis, xjs) in enumerate(train_loader):
+                if max_steps_per_epoch is not None and bn >= max_steps_per_epoch:
+                    break
+                optimizer.zero_grad(set_to_none=True)
+                loss = self._step(model, xis.to(self.device, non_blocking=True), xjs.to(self.device, non_blocking=True), n_iter)
+                if n_iter % cfg["log_every_n_steps"] == 0:
+                    self._scalar("train_loss", loss.item(), n_iter)
+                    self._scalar("cosine_lr_decay", scheduler.get_last_lr()[0], n_iter)
+                    print(epoch, bn, loss.item())
+                loss.backward()
+                optimizer.step()
+                n_iter += 1
+            if epoch % cfg["eval_every_n_epochs"] == 0:
+                valid_loss = self._validate(model, valid_loader)
+                print(epoch, valid_loss, "(validation)")
+                history.append(valid_loss)
+                if valid_loss < best_valid:
+                    best_valid = valid_loss
+                    torch.save(model.state_dict(), os.path.join(ckpt_dir, "model.pth"))
+                self._scalar("validation_loss", valid_loss, valid_n_iter)
+                valid_n_iter += 1
+            if (epoch + 1) % cfg["save_every_n_epochs"] == 0:
+                torch.save(model.state_dict(), os.path.join(ckpt_dir, f"model_{epoch}.pth"))
+            if epoch >= cfg["warm_up"]:
+                scheduler.step()
+        return model, history
+
+    def _load_pre_trained_weights(self, model):
+        path = os.path.join("./ckpt", str(self.config["load_model"]), "checkpoints", "model.pth")
+        if os.path.exists(path):
+            model.load_state_dict(torch.load(path, map_location=self.device))
+            print("Loaded pre-trained model with success.")
+        else:
+            print("Pre-trained weights not found. Training from scratch.")
+        return model
+
+    def _validate(self, model, valid_loader):
+        model.eval()
+        total, count = 0.0, 0
+        with torch.no_grad():
+            for xis, xjs in valid_loader:
+                total += self._step(model, xis.to(self.device), xjs.to(self.device)).item()
+                count += 1
+        model.train()
+        return total / max(count, 1)
+
+
+def main(argv=None):
+    import argparse
+    import copy
+    ap = argparse.ArgumentParser()
+    ap.add_argument("config", nargs="?", default=None)
+    ap.add_argument("--epochs", type=int, default=None)
+    ap.add_argument("--steps-per-epoch", type=int, default=None)
+    args = ap.parse_args(argv)
+    config = copy.deepcopy(DEFAULT_CONFIG)
+    if args.config:
+        import yaml
+        config.update(yaml.load(open(args.config), Loader=yaml.FullLoader))
+    if args.epochs is not None:
+        config["epochs"] = args.epochs
+    if config["aug"] != "node":
+        raise ValueError("Not defined molecule augmentation!" if config["aug"] not in ("subgraph", "mix") else
+                         "molclr_b200.trainer: only the 'node' augmentation (dataset.py) has a synthetic stand-in")
+    data_path = config["dataset"]["data_path"]
+    if not str(data_path).startswith("synthetic:"):
+        config["dataset"]["data_path"] = "synthetic:20000"            # SMILES parsing needs RDKit (out of scope)
+    dataset = SyntheticMoleculeDatasetWrapper(config["batch_size"], **config["dataset"])
+    MolCLR(dataset, config).train(max_steps_per_epoch=args.steps_per_epoch)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

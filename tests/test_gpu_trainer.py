@@ -1,0 +1,35 @@
+"""Trainer shell: a few epochs on synthetic molecules -- the loss goes down, checkpoints are written in the
+reference's layout and load back into a fresh model, eval-mode validation leaves the BatchNorm buffers alone."""
+import copy
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_trainer_runs_checkpoints_and_resumes(tmp_path, monkeypatch):
+    from molclr_b200 import GINet
+    from molclr_b200.trainer import DEFAULT_CONFIG, MolCLR, SyntheticMoleculeDatasetWrapper
+    monkeypatch.chdir(tmp_path)
+    cfg = copy.deepcopy(DEFAULT_CONFIG)
+    cfg.update(batch_size=64, epochs=3, warm_up=1, save_every_n_epochs=2, log_every_n_steps=4)
+    cfg["model"].update(num_layer=3, emb_dim=64, feat_dim=64)
+    cfg["dataset"].update(data_path="synthetic:700", valid_size=0.1)
+    torch.manual_seed(0)
+    trainer = MolCLR(SyntheticMoleculeDatasetWrapper(cfg["batch_size"], **cfg["dataset"]), cfg, log_root=str(tmp_path / "ckpt"))
+    model, history = trainer.train()
+    assert len(history) == 3 and all(h == h for h in history) and history[-1] < history[0]      # finite and decreasing
+    ckpt = os.path.join(trainer.log_dir, "checkpoints")
+    assert sorted(os.listdir(ckpt)) == ["model.pth", "model_1.pth"]
+    sd = torch.load(os.path.join(ckpt, "model.pth"))
+    fresh = GINet(**cfg["model"])
+    fresh.load_state_dict(sd)                                   # strict: same keys / shapes as the reference layout
+    assert int(sd["batch_norms.0.num_batches_tracked"]) > 0
+    # validation runs in eval mode: running statistics and counters untouched
+    before = {k: v.clone() for k, v in model.state_dict().items() if "running" in k or "tracked" in k}
+    trainer._validate(model, trainer.dataset.get_data_loaders()[1])
+    for k, v in model.state_dict().items():
+        if k in before:
+            assert torch.equal(v, before[k]), k
