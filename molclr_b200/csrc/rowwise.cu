@@ -190,8 +190,13 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_fwd_kernel(
     }
     return v;
   };
+  const int row_lines = (D * 4 + 127) / 128;                 // 128-byte lines per feature row
   for (int i = warp; i < N; i += nwarps) {
     const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
+    // the next row this warp will own: pull its feature row (first touch: HBM latency) and its CSR entries into L2 now
+    // (measured: 86 -> 79 us for the BatchNorm-fused variant; the leaner layer-0 variant gets slower, so it is left alone)
+    if (HAS_BN && i + nwarps < N && lane < row_lines) prefetch_l2(src + (size_t)(i + nwarps) * D + 32 * lane);
+    if (HAS_BN && i + nwarps < N && lane == 31) prefetch_l2(rowptr + i + nwarps);
     float4 acc[NCH], self[NCH];
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
