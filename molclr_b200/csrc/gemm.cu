@@ -4,11 +4,13 @@
 //   * operands are the fp32 tensors themselves (pre-rounded to TF32 by their producers), staged by
 //     TMA into 128B-swizzled shared-memory tiles; out-of-range rows/columns are zero-filled by TMA so
 //     the awkward extents (300, 600, ragged node counts) need no padding in HBM;
-//   * one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) into a TMEM accumulator;
+//   * one elected thread issues tcgen05.mma.kind::tf32 (K=8 per instruction) into a TMEM accumulator: M=128 on one CTA, or
+//     M=256 on a CTA pair (cta_group::2: each CTA stages its own 128 rows of A and half of the B tile);
 //   * both operands may be K-major ([rows][K]) or MN-major ([K][rows]) so that Y = X W^T, dX = dY W
 //     and dW = dY^T X all read the row-major activations/weights in place (no transposed copies);
-//   * the epilogue (4 warps) drains TMEM through a shared staging tile and fuses bias, addend, ReLU,
-//     ReLU-mask, TF32 rounding, BatchNorm tile statistics / column sums and coalesced stores.
+//   * the epilogue warps (two per TMEM lane quadrant) drain TMEM through per-warp staging chunks and fuse bias, ReLU,
+//     ReLU bit masks, addend, TF32 rounding / hi+lo residual outputs, BatchNorm tile statistics / column sums, the NT-Xent
+//     log-sum-exp and softmax-weight transforms, and coalesced stores.
 //
 // A scalar-FMA kernel with the same argument struct (MOLCLR_GEMM_IMPL=simt) exists for debugging
 // the tensor-core path on the GPU; it is never selected implicitly.
@@ -26,7 +28,6 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 32;          // single-pass K block: 32 tf32 = one 128-byte swizzle row
 constexpr int GEMM_BK4 = 32;         // compensated (4-tile) K block.  16 (64-byte swizzle rows, 5 stages, 8 epilogue warps) also works
                                      // but measured 20% slower: the 64-byte TMA boxes double the L2 request count of an L2-bound loop
-constexpr int GEMM_MAX_THREADS = 320; // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..: epilogue (4 or 8)
 constexpr int GEMM_TMEM_COLS = 512;  // two accumulator buffers of up to 256 columns
 constexpr int GEMM_STAT_ROWS = 32;   // column statistics are emitted per 32-row group (one epilogue warp)
 constexpr int GEMM_SMEM_LIMIT = 232448;
@@ -159,7 +160,7 @@ __device__ __forceinline__ void colstat_warp(const float* stage, int rows, int c
 
 // Persistent, warp-specialised tcgen05 GEMM.  Each CTA (one per SM) walks tiles t = blockIdx.x + i*gridDim.x of the
 // (n_tile fastest, m_tile, k_split) grid.  The TMA producer and the MMA issuer run ahead across tiles through a
-// STAGES-deep smem ring; accumulators are double-buffered in TMEM so the 4 epilogue warps drain tile i while the
+// STAGES-deep smem ring; accumulators are double-buffered in TMEM so the epilogue warps drain tile i while the
 // tensor core works on tile i+1.
 // KIND selects the epilogue at compile time so that each variant is a short, branch-free loop:
 enum : int { K_PLAIN = 0, K_LATE = 1, K_NTX_W = 2, K_NTX_FWD = 3, K_ATOMIC = 4 };

@@ -68,12 +68,6 @@ def colstat_tile_rows():
     return _lib.load().molclr_gemm_colstat_tile_rows()
 
 
-def _sm_count():
-    if not hasattr(_sm_count, "v"):
-        _sm_count.v = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
-    return _sm_count.v
-
-
 def gemm_dw(dY, X):
     """dW[O,I] = dY^T X for row-major dY [R,O], X [R,I] (both tf32-rounded): the weight gradient of a
     Linear (autograd of ginet_molclr.py:19-23,90-96).  Both operands are consumed MN-major in place;

@@ -3,13 +3,13 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from molclr_b200 import Batch, GINet, NTXentLoss, pretrain_loss
+from molclr_b200 import Batch, GCN, GINet, NTXentLoss, pretrain_loss
 from molclr_b200.synth import make_pair_batch
 
 B = int(os.environ.get("BATCH", 4096))
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-model = GINet(5, 300, 512).to(dev)
+model = (GCN if os.environ.get("MODEL") == "gcn" else GINet)(5, 300, 512).to(dev)
 model.precision = os.environ.get("PREC", "tf32x3")
 crit = NTXentLoss(dev, B, 0.1, True)
 opt = torch.optim.Adam(model.parameters(), 5e-4, weight_decay=1e-5, fused=True)
