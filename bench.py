@@ -252,25 +252,24 @@ def run_ours(args):
         a.record()
         out = orig(plan, src, B1, B2, bn_coef=bn_coef, **kw)
         b.record()
-        times.append((a, b, plan.N, plan.E))
+        times.append((a, b, plan.N, plan.E, bool(kw.get("want_lo"))))
         return out
     ops.gine_aggregate_fwd = timed_aggregate
     for i in range(3 if args.model == "gin" else 0):
         step(*resident[i % NB])
     torch.cuda.synchronize()
     ops.gine_aggregate_fwd = orig
-    comp = args.precision == "tf32x3"
     D = 300
-    # algorithmic bytes per launch: read src rows once, write the aggregate (hi [+ lo residual in tf32x3]),
-    # CSR rowptr/col/eattr, BN coefficients and bond tables
-    def alg_bytes(N, E):
-        return 4 * D * N + (2 if comp else 1) * 4 * D * N + 4 * (N + 1) + 5 * E + 4 * D * (2 + 8)
+    # algorithmic bytes per launch (DESIGN.md / SURVEY 8d): read src rows once, write the aggregate (one tensor; plus the tf32
+    # residual when the caller asks for it), CSR rowptr/col/eattr, BN coefficients and bond tables
+    def alg_bytes(N, E, lo):
+        return 4 * D * N + (2 if lo else 1) * 4 * D * N + 4 * (N + 1) + 5 * E + 4 * D * (2 + 8)
     peak, peak_src = peaks()
     if times:
-        agg_ms = sum(a.elapsed_time(b) for a, b, _, _ in times) / len(times)
-        agg_bytes = sum(alg_bytes(N, E) for _, _, N, E in times) / len(times)
+        agg_ms = sum(t[0].elapsed_time(t[1]) for t in times) / len(times)
+        agg_bytes = sum(alg_bytes(*t[2:]) for t in times) / len(times)
         achieved = agg_bytes / (agg_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "gine_aggregate_fwd_kernel<3,true,false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roof = {"bound": "hbm", "kernel": "gine_aggregate_fwd_tile_kernel<3,true,false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "us_per_launch": agg_ms * 1e3,
                 "algorithmic_bytes_per_launch": agg_bytes, "launches_timed": len(times)}
     else:

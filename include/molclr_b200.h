@@ -52,6 +52,9 @@ int molclr_device_info(int* sm_count, int* cc);
  *   rowptr_t[N+1], col_t[E] (destination of each out-edge): source-sorted transpose for backward;
  *   cnt[N][8] float: in-edge counts per bond type (0..4, self loop = type 4) and direction (5..7), clamped to 2048
  *     (exact in TF32: they are an operand of the table-gradient contraction);
+ *   nbr[N][8] uint32 (optional, 32-byte aligned): fixed-width copy of rows with <= 8 in-edges, entry = source << 4 | eattr,
+ *     0xFFFFFFFF = empty, [7] = 0xFFFFFFFE = "row too long, use the CSR": lets the aggregation kernel fetch a row's neighbour
+ *     list with ONE load (no rowptr -> col dependency);
  *   gptr[G+1], gperm[N]: nodes grouped by graph (identity permutation for sorted `batch`).
  *   status[4]: [0] = error bits (1 node feature, 2 edge endpoint, 4 edge attr, 8 batch id out of
  *              range, 16 a per-class in-degree above 2048); [1] = 1 if `batch` was not sorted.
@@ -59,7 +62,7 @@ int molclr_device_info(int* sm_count, int* cc);
 size_t molclr_plan_workspace_bytes(int64_t N, int64_t E, int64_t G);
 int molclr_plan_build(const int64_t* x, const int64_t* edge_index, const int64_t* edge_attr, const int64_t* batch,
                       int64_t N, int64_t E, int64_t G, int32_t* xpacked, int32_t* node2graph, int32_t* rowptr,
-                      int32_t* col, uint8_t* eattr, int32_t* rowptr_t, int32_t* col_t, float* cnt, int32_t* gptr,
+                      int32_t* col, uint8_t* eattr, int32_t* rowptr_t, int32_t* col_t, float* cnt, uint32_t* nbr, int32_t* gptr,
                       int32_t* gperm, void* workspace, size_t workspace_bytes, int32_t* status, cudaStream_t stream);
 
 /* ---- node embedding: ginet_molclr.py:103 / gcn_molclr.py:144 ------------------------------------- */
@@ -77,7 +80,8 @@ int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, int64_t ld_g,
  * f = identity if bn_coef == NULL, else f(v) = [relu](v*scale + shift) with scale = bn_coef[0..D), shift = bn_coef[D..2D)
  * (the previous layer's BatchNorm + ReLU, ginet_molclr.py:107-111, applied on the fly). */
 int molclr_gine_aggregate_fwd(const float* src, const float* bn_coef, int relu, const int32_t* rowptr, const int32_t* col,
-                              const uint8_t* eattr, const float* B1, const float* B2, int64_t N, int D, float* out,
+                              const uint8_t* eattr, const uint32_t* nbr /* optional, see molclr_plan_build */, const float* B1,
+                              const float* B2, int64_t N, int D, float* out,
                               int64_t ld_out /* row stride of out / out_lo in floats */, int round_tf32_out,
                               float* out_lo /* optional: tf32 residual of the exact sum */,
                               uint32_t drop_seed, float drop_p /* dropout of f (see "Dropout" below); 0 = none */, cudaStream_t stream);
@@ -164,10 +168,12 @@ int molclr_dropout_mask(uint32_t drop_seed, float drop_p, int64_t N, int D, floa
  * Epilogue, in this order: + bias[n]; + addend[m][n]; relu; * (mask[m][n] > 0) or the mask_bits bit; column statistics of the
  * result per 32-row group (colstat_mode 1: sums -> colstat[group][N]; 2: mean and M2 -> colstat[group][2][N]);
  * out = (round_out ? tf32-rounded : exact); out2 = tf32-rounded copy.
- * A_lo/B_lo (both or neither; same shape and ld as A/B): the tf32-rounded residuals x - tf32(x) of the true
+ * A_lo/B_lo (same shape and ld as A/B; B_lo alone is allowed, see below): the tf32-rounded residuals x - tf32(x) of the true
  * fp32 operands whose tf32-rounded values are in A/B.  When given, the product is error-compensated,
  * A*B + A_lo*B + A*B_lo (three tensor-core passes, fp32 accumulate, ~fp32 accuracy) -- used by the forward
  * pass so that ReLU masks match the fp32 reference.  out_lo receives the residual of the result.
+ * B_lo without A_lo: A holds UNROUNDED fp32 values; the kernel uses the raw tile as the (truncated) hi operand and derives
+ * A_lo = tf32(A - trunc_tf32(A)) in shared memory (converter warps), so the producer of A writes one tensor instead of two.
  * split_k > 1 or transpose_out: raw products accumulated atomically into out (zeroed here first);
  * transpose_out stores C^T (out[n][m]).  No other epilogue option is allowed in that mode. */
 typedef struct {

@@ -52,16 +52,18 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = (FOUR ? 2 : 1) * (A_BYTES + B_BYTES);
   // epilogue column chunk staged per warp, and its pitch in floats (conflict-free float4 rows); the 72 KB stages of
   // the compensated product leave room for four warps with 16-column chunks only
-  static constexpr bool SMALL_EPI = FOUR && (GEMM_SMEM_LIMIT - 8 * 32 * 32 * 4 - 256 - 2048) / STAGE_BYTES < 3;
+  static constexpr bool SMALL_EPI = FOUR && (GEMM_SMEM_LIMIT - 8 * 32 * 32 * 4 - 512 - 2048) / STAGE_BYTES < 3;
   static constexpr int CHUNK = SMALL_EPI ? 16 : 32;
   // 32-column chunks are staged unpadded with an XOR swizzle of the 16-byte column groups (stg_off); 16-column ones padded
   static constexpr int CHUNK_LD = CHUNK == 32 ? 32 : CHUNK + 4;
   // epilogue warps: two per TMEM lane quadrant (splitting the column chunks) where shared memory allows
   static constexpr int EPI_WARPS = SMALL_EPI ? 4 : 8;
-  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  // converter warps (compensated product with derive_lo): compute the A_lo tile from the fp32 A tile in shared memory
+  static constexpr int CONV_WARPS = FOUR ? 2 : 0;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * CONV_WARPS;
   static constexpr int STAGING_BYTES = EPI_WARPS * 32 * CHUNK_LD * 4;     // per epilogue warp: 32 rows x chunk
   static constexpr bool BIAS_SMEM = !(FOUR && !TWO);       // (the single-CTA compensated config has no room left)
-  static constexpr int BAR_BYTES = 256 + (BIAS_SMEM ? 2 * 256 * 4 : 0);   // mbarriers + TMEM slot, then two bias tiles (double-buffered)
+  static constexpr int BAR_BYTES = 512 + (BIAS_SMEM ? 2 * 256 * 4 : 0);   // mbarriers + TMEM slot, then two bias tiles (double-buffered)
   static constexpr int STAGES_RAW = (GEMM_SMEM_LIMIT - STAGING_BYTES - BAR_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
@@ -176,8 +178,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;     // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;              // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* bias_s = reinterpret_cast<float*>(smem + Cfg::PIPE_BYTES + Cfg::STAGING_BYTES + 256);   // [2][256]
+  uint64_t* afull_bar = tempty_bar + 2;              // [STAGES] derive_lo: this CTA's fp32 A tile has landed
+  uint64_t* conv_bar = afull_bar + Cfg::STAGES;      // [STAGES] derive_lo: A_lo tiles of the worker converted (leader's copy is used)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv_bar + Cfg::STAGES);
+  static_assert((4 * Cfg::STAGES + 4) * 8 + 4 <= 512, "barrier area");
+  float* bias_s = reinterpret_cast<float*>(smem + Cfg::PIPE_BYTES + Cfg::STAGING_BYTES + 512);   // [2][256]
+  const bool derive = FOUR && p.derive_lo != 0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = p.n_tiles, m_tiles = p.m_tiles;
@@ -190,7 +196,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (threadIdx.x == 0) {
     if ((ptx::smem_u32(smem) & 1023u) != 0) { printf("molclr gemm: dynamic smem base not 1024B aligned\n"); __trap(); }
-    for (int s = 0; s < Cfg::STAGES; ++s) { ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1);
+      ptx::mbar_init(afull_bar + s, 1); ptx::mbar_init(conv_bar + s, (TWO ? 2 : 1) * (Cfg::CONV_WARPS > 0 ? Cfg::CONV_WARPS : 1));
+    }
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(tfull_bar + b, 1); ptx::mbar_init(tempty_bar + b, (TWO ? 2 : 1) * Cfg::EPI_WARPS); }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmA);
@@ -219,7 +228,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = 0; i < nkb; ++i, ++it) {
           const int s = it % Cfg::STAGES;
           ptx::mbar_wait(empty_bar + s, ((it / Cfg::STAGES) & 1) ^ 1);
-          if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar + s, Cfg::TX_BYTES);
+          // derive_lo: the fp32 A tile goes to a CTA-local barrier (the converter warps of THIS CTA consume it) and no A_lo is loaded
+          if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar + s, derive ? (TWO ? 2 : 1) * 2 * Cfg::B_BYTES : Cfg::TX_BYTES);
+          if (derive) ptx::mbar_arrive_expect_tx(afull_bar + s, Cfg::A_BYTES);
           const uint32_t fb = TWO ? ptx::mapa(ptx::smem_u32(full_bar + s), 0u) : 0u;     // the leader's barrier
           auto load = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
             if (TWO) ptx::tma_load_2d_2cta(dst, m, fb, c0, c1); else ptx::tma_load_2d(dst, m, full_bar + s, c0, c1);
@@ -234,7 +245,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const CUtensorMap* mb = (FOUR ? h == 1 : seg == 2) ? &tmB2 : &tmB;
             uint8_t* ad = a_dst + h * Cfg::A_BYTES;
             uint8_t* bd = b_dst + h * Cfg::B_BYTES;
-            if (!p.a_mn) load(ad, ma, kc, m0);
+            if (derive) {
+              if (h == 0) {
+                if (!p.a_mn) ptx::tma_load_2d(ad, ma, afull_bar + s, kc, m0);
+                else
+                  for (int j = 0; j < GEMM_BM / 32; ++j) ptx::tma_load_2d(ad + j * Cfg::MN_BLOCK_BYTES, ma, afull_bar + s, m0 + 32 * j, kc);
+              }
+            } else if (!p.a_mn) load(ad, ma, kc, m0);
             else
               for (int j = 0; j < GEMM_BM / 32; ++j) load(ad + j * Cfg::MN_BLOCK_BYTES, ma, m0 + 32 * j, kc);
             if (!p.b_mn) load(bd, mb, kc, n0);
@@ -280,6 +297,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = 0; i < nkb; ++i, ++it) {
           const int s = it % Cfg::STAGES;
           ptx::mbar_wait(full_bar + s, (it / Cfg::STAGES) & 1);
+          if (derive) ptx::mbar_wait(conv_bar + s, (it / Cfg::STAGES) & 1);
           ptx::tc_fence_after();
           const uint32_t a_base = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES);
           const uint32_t b_base = a_base + (FOUR ? 2 : 1) * Cfg::A_BYTES;
@@ -306,6 +324,40 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     __syncwarp();
+  } else if (Cfg::CONV_WARPS > 0 && warp >= 2 + Cfg::EPI_WARPS) {
+    // ------------------------------------------------------------ converter (derive_lo): A_lo = tf32(A - trunc_tf32(A))
+    // The tensor core reads only the top 19 bits of an fp32 operand, so the raw tile IS the "hi" operand (truncated); the
+    // residual is formed element-wise at the same (swizzled) offset of the A_lo slot, whatever the tile layout.
+    if (derive) {
+      const int ct = threadIdx.x - 32 * (2 + Cfg::EPI_WARPS);
+      const uint32_t conv_leader = TWO ? ptx::mapa(ptx::smem_u32(conv_bar), 0u) : 0u;
+      uint32_t it = 0;
+      for (int t = worker; t < total; t += num_workers) {
+        const int kb0 = (t / (n_tiles * m_tiles)) * p.kb_per_split;
+        const int nkb = min(p.num_kb, kb0 + p.kb_per_split) - kb0;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % Cfg::STAGES;
+          ptx::mbar_wait(afull_bar + s, (it / Cfg::STAGES) & 1);
+          const float4* hi = reinterpret_cast<const float4*>(smem + s * Cfg::STAGE_BYTES);
+          float4* lo = reinterpret_cast<float4*>(smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES);
+#pragma unroll 4
+          for (int e = ct; e < Cfg::A_BYTES / 16; e += 32 * Cfg::CONV_WARPS) {
+            const float4 v = hi[e];
+            float4 r;
+            r.x = round_tf32(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+            r.y = round_tf32(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+            r.z = round_tf32(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+            r.w = round_tf32(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+            lo[e] = r;
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (TWO) ptx::mbar_arrive_cluster(conv_leader + s * 8u); else ptx::mbar_arrive(conv_bar + s);
+          }
+        }
+      }
+    }
   } else {
     // ------------------------------------------------------------ epilogue: warp q owns accumulator rows 32q..32q+31
     const int q = warp & 3;                          // TMEM lane quadrant this warp may access
@@ -538,7 +590,7 @@ __global__ void __launch_bounds__(128) gemm_simt_kernel(const float* __restrict_
   if (grow < p.M) {
     for (int k = 0; k < p.K; ++k) {
       const size_t ai = p.a_mn ? (size_t)k * lda + grow : (size_t)grow * lda + k;
-      const float a = A[ai] + (p.segments > 1 ? A_lo[ai] : 0.f);
+      const float a = A[ai] + ((p.segments > 1 && A_lo) ? A_lo[ai] : 0.f);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int col = n0 + j;
@@ -653,8 +705,10 @@ static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, i
   if (rc) return rc;
   tmA2 = tmA; tmB2 = tmB;
   if (p.segments > 1) {
-    rc = p.a_mn ? make_tmap(&tmA2, j.A_lo, p.M, p.K, j.lda, 32, true, Cfg::BK) : make_tmap(&tmA2, j.A_lo, p.K, p.M, j.lda, GEMM_BM, false, Cfg::BK);
-    if (rc) return rc;
+    if (j.A_lo) {
+      rc = p.a_mn ? make_tmap(&tmA2, j.A_lo, p.M, p.K, j.lda, 32, true, Cfg::BK) : make_tmap(&tmA2, j.A_lo, p.K, p.M, j.lda, GEMM_BM, false, Cfg::BK);
+      if (rc) return rc;
+    }
     rc = p.b_mn ? make_tmap(&tmB2, j.B_lo, p.N, p.K, j.ldb, 32, true, Cfg::BK) : make_tmap(&tmB2, j.B_lo, p.K, p.N, j.ldb, Cfg::BN_CTA, false, Cfg::BK);
     if (rc) return rc;
   }
@@ -725,8 +779,9 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   MOLCLR_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
   MOLCLR_REQUIRE(p.N % 4 == 0, "gemm: N=%d must be a multiple of 4", p.N);
   const bool atomic = job.split_k > 1 || p.transpose_out;
-  MOLCLR_REQUIRE((job.A_lo == nullptr) == (job.B_lo == nullptr), "gemm: A_lo and B_lo must be given together");
-  p.segments = job.A_lo ? 3 : 1;
+  MOLCLR_REQUIRE(job.A_lo == nullptr || job.B_lo != nullptr, "gemm: A_lo needs B_lo");
+  p.segments = job.B_lo ? 3 : 1;
+  p.derive_lo = (job.B_lo && !job.A_lo) ? 1 : 0;          // compensated product with A_lo derived on chip from an unrounded A
   MOLCLR_REQUIRE((!p.bits_in && !p.bits_out) || (p.epi == EPI_GENERIC && !atomic && !p.mask && !p.addend),
                  "gemm: ReLU bit masks need the plain epilogue (no float mask / addend / split-K)");
   MOLCLR_REQUIRE(!p.bits_in || p.segments == 1, "gemm: mask_bits is not supported by the compensated product");

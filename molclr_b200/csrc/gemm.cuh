@@ -12,6 +12,7 @@ struct GemmParams {
   int a_mn, b_mn;
   int num_kb, kb_per_split;
   int n_tiles, m_tiles, splits;   // tile grid walked by the persistent CTAs (filled by the launcher)
+  int derive_lo;               // compensated product: A holds unrounded fp32 and the kernel derives A_lo = A - trunc_tf32(A) on chip
   int segments;                // 1: plain TF32.  3: error-compensated  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (~fp32 accuracy)
   float* out; long long ldo; int transpose_out;
   float* out2; long long ldo2;

@@ -141,7 +141,7 @@ __global__ void plan_rows_kernel(const int64_t* __restrict__ ei, const int64_t* 
                                  int64_t N, int64_t E, int64_t G, const int32_t* __restrict__ rowptr,
                                  const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ gptr,
                                  int32_t* col, uint8_t* __restrict__ eattr, int32_t* col_t,
-                                 float* __restrict__ cnt, int32_t* gperm, int32_t* status) {
+                                 float* __restrict__ cnt, uint32_t* __restrict__ nbr, int32_t* gperm, int32_t* status) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t n = i; n < N; n += stride) {
@@ -156,6 +156,16 @@ __global__ void plan_rows_kernel(const int64_t* __restrict__ ei, const int64_t* 
       col[p] = (int32_t)ei[id];                           // source node of the in-edge
       eattr[p] = (uint8_t)(t * 3 + r);
       c[t]++; c[5 + r]++;
+    }
+    if (nbr) {     // fixed-width copy of short rows: (source << 4 | attr) x 8, 0xFFFFFFFF = empty, [7] = 0xFFFFFFFE = row too long
+      const bool fits = (e - b <= 8) && N < (1ll << 28);
+      uint32_t w[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) w[k] = (fits && b + k < e) ? ((uint32_t)col[b + k] << 4 | (uint32_t)eattr[b + k]) : 0xFFFFFFFFu;
+      if (!fits) w[7] = 0xFFFFFFFEu;
+      uint4* dst = reinterpret_cast<uint4*>(nbr + 8 * n);
+      dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
     bool over = false;
 #pragma unroll
@@ -187,7 +197,7 @@ extern "C" size_t molclr_plan_workspace_bytes(int64_t N, int64_t E, int64_t G) {
 extern "C" int molclr_plan_build(const int64_t* x, const int64_t* edge_index, const int64_t* edge_attr,
                                  const int64_t* batch, int64_t N, int64_t E, int64_t G, int32_t* xpacked,
                                  int32_t* node2graph, int32_t* rowptr, int32_t* col, uint8_t* eattr,
-                                 int32_t* rowptr_t, int32_t* col_t, float* cnt, int32_t* gptr,
+                                 int32_t* rowptr_t, int32_t* col_t, float* cnt, uint32_t* nbr, int32_t* gptr,
                                  int32_t* gperm, void* workspace, size_t workspace_bytes, int32_t* status,
                                  cudaStream_t stream) {
   MOLCLR_REQUIRE(N >= 0 && E >= 0 && G >= 0, "plan_build: negative size");
@@ -227,7 +237,7 @@ extern "C" int molclr_plan_build(const int64_t* x, const int64_t* edge_index, co
   int blocks2 = (int)((work2 + threads - 1) / threads);
   blocks2 = blocks2 < 1 ? 1 : blocks2;
   plan_rows_kernel<<<blocks2, threads, 0, stream>>>(edge_index, edge_attr, N, E, G, rowptr, rowptr_t, gptr,
-                                                    col, eattr, col_t, cnt, gperm, status);
+                                                    col, eattr, col_t, cnt, nbr, gperm, status);
   MOLCLR_CHECK_LAUNCH("plan_rows");
   return 0;
 }

@@ -6,11 +6,13 @@
 // a row is summed in a fixed order without atomics (deterministic, and bit-exact against the CPU
 // reference order where that matters).  Grids are persistent: (#SM x resident CTAs) blocks that
 // grid-stride over rows.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
 #include "gemm.cuh"
 #include "molclr_b200.h"
+#include "ptx.cuh"
 
 namespace molclr {
 
@@ -235,6 +237,152 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_fwd_kernel(
         st_f4(out + (size_t)i * ld_out + 4 * q, r);
       }
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GINE aggregation forward, shared-memory tile variant (the GINEConv product path; same sums in the same order).
+// The warp-per-row kernel above re-reads every neighbour row from L2 (1 + mean in-degree = 3.6 reads of each feature row),
+// which makes it L2 -> SM fabric bound well below the HBM roofline.  Molecules are small connected blocks of CONSECUTIVE
+// rows, so a tile of T consecutive rows holds almost all neighbours of its own rows: a producer warp streams tiles
+// [t*T, (t+1)*T) of `src` (one 1D bulk copy, T*D*4 bytes) and of the fixed-width neighbour table nbr[N][8] (see
+// molclr_plan_build) through a ring of shared-memory stages, and 15 consumer warps (warp = row, lanes = float4 chunks)
+// gather from the staged tile; a neighbour outside the tile (a molecule cut by the tile boundary) or a row with more than
+// 8 in-edges falls back to global loads.  Each feature row then crosses L2 -> SM once.  The previous layer's BatchNorm
+// coefficients live in registers (applied on use, as above), so the staged tile is read-only.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTileConsumerWarps = 15;       // + the producer warp = 512 threads: 128 registers each
+constexpr int kTileThreads = 32 * (kTileConsumerWarps + 1);
+constexpr int kTileStages = 4;
+constexpr uint32_t kNbrEmpty = 0xFFFFFFFFu, kNbrLong = 0xFFFFFFFEu;
+
+// A/B switch for measurements: MOLCLR_AGG_TILE=0 forces the warp-per-row kernel
+static const bool g_aggregate_tile = [] { const char* e = getenv("MOLCLR_AGG_TILE"); return !(e && e[0] == '0'); }();
+
+static size_t aggregate_tile_smem(int D, int T) {
+  return (size_t)kNumEdgeClass * D * 4 + (size_t)kTileStages * T * (D * 4 + 32) + 2 * kTileStages * sizeof(uint64_t);
+}
+
+template <int NCH, bool HAS_BN, bool DROP>
+__global__ void __launch_bounds__(kTileThreads, 1) gine_aggregate_fwd_tile_kernel(
+    const float* __restrict__ src, const float* __restrict__ coef, int relu,
+    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const uint8_t* __restrict__ eattr,
+    const uint32_t* __restrict__ nbr, const float* __restrict__ B1, const float* __restrict__ B2, int N, int D, int T,
+    float* __restrict__ out, long long ld_out, int round_out, float* __restrict__ out_lo, const DropCfg drop) {
+  extern __shared__ float4 sm4[];
+  const int D4 = D >> 2;
+  float4* ee = sm4;                                                  // [15][D4]
+  float4* feat = ee + kNumEdgeClass * D4;                            // [stages][T][D4]
+  uint32_t* nb = reinterpret_cast<uint32_t*>(feat + (size_t)kTileStages * T * D4);   // [stages][T][8]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(nb + (size_t)kTileStages * T * 8);
+  uint64_t* empty_bar = full_bar + kTileStages;
+  for (int i = threadIdx.x; i < kNumEdgeClass * D4; i += blockDim.x) {
+    const int cls = i / D4, q = i - cls * D4;
+    ee[i] = f4_add(ldg_f4(B1 + (size_t)(cls / 3) * D + 4 * q), ldg_f4(B2 + (size_t)(cls % 3) * D + 4 * q));
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTileStages; ++s) { ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, kTileConsumerWarps); }
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ntiles = (N + T - 1) / T;
+  if (warp == kTileConsumerWarps) {
+    // ---------------------------------------------------------------- producer
+    if (lane == 0) {
+      int k = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++k) {
+        const int s = k % kTileStages;
+        ptx::mbar_wait(empty_bar + s, ((k / kTileStages) & 1) ^ 1);
+        const int t0 = t * T, rows = min(T, N - t0);
+        ptx::mbar_arrive_expect_tx(full_bar + s, (uint32_t)rows * (uint32_t)(D * 4 + 32));
+        ptx::bulk_load_1d(feat + (size_t)s * T * D4, src + (size_t)t0 * D, (uint32_t)rows * (uint32_t)(D * 4), full_bar + s);
+        ptx::bulk_load_1d(nb + (size_t)s * T * 8, nbr + (size_t)t0 * 8, (uint32_t)rows * 32u, full_bar + s);
+      }
+    }
+    return;
+  }
+  // ------------------------------------------------------------------ consumers
+  float4 scr[NCH], shr[NCH];
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    const int q = lane + 32 * j;
+    scr[j] = (HAS_BN && q < D4) ? ldg_f4(coef + 4 * q) : f4_zero();
+    shr[j] = (HAS_BN && q < D4) ? ldg_f4(coef + D + 4 * q) : f4_zero();
+  }
+  auto act = [&](float4 v, int j, int row) -> float4 {
+    if (HAS_BN) {
+      const float4 s = scr[j], b = shr[j];
+      v.x = fmaf(v.x, s.x, b.x); v.y = fmaf(v.y, s.y, b.y); v.z = fmaf(v.z, s.z, b.z); v.w = fmaf(v.w, s.w, b.w);
+      if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      if (DROP) v = f4_mul(v, drop_mask4(drop, row, lane + 32 * j, D4));
+    }
+    return v;
+  };
+  int k = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++k) {
+    const int s = k % kTileStages;
+    const int t0 = t * T, rows = min(T, N - t0);
+    const float4* ft = feat + (size_t)s * T * D4;
+    const uint32_t* nt = nb + (size_t)s * T * 8;
+    ptx::mbar_wait(full_bar + s, (k / kTileStages) & 1);
+    // feature row `sidx`: from the staged tile when it is one of this tile's rows, else from global memory
+    auto fetch = [&](int sidx, float4 (&v)[NCH]) {
+      const unsigned rel = (unsigned)(sidx - t0);
+      if (rel < (unsigned)rows) {
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) { const int q = lane + 32 * j; v[j] = (q < D4) ? ft[rel * D4 + q] : f4_zero(); }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) { const int q = lane + 32 * j; v[j] = (q < D4) ? ldg_f4(src + (size_t)sidx * D + 4 * q) : f4_zero(); }
+      }
+    };
+    for (int r = warp; r < rows; r += kTileConsumerWarps) {
+      const int i = t0 + r;
+      float4 acc[NCH];
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) acc[j] = f4_zero();
+      auto add2 = [&](int s0, int a0, bool two, int s1, int a1) {      // same order as the row kernel: e, then e + 1
+        float4 v0[NCH], v1[NCH];
+        fetch(s0, v0);
+        if (two) fetch(s1, v1);
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+          const int q = lane + 32 * j;
+          if (q < D4) {
+            acc[j] = f4_add(acc[j], f4_add(act(v0[j], j, s0), ee[a0 * D4 + q]));
+            if (two) acc[j] = f4_add(acc[j], f4_add(act(v1[j], j, s1), ee[a1 * D4 + q]));
+          }
+        }
+      };
+      if (nt[r * 8 + 7] != kNbrLong) {
+        for (int kk = 0; kk < 8; kk += 2) {
+          const uint2 w = *reinterpret_cast<const uint2*>(nt + r * 8 + kk);      // (source << 4 | attr) of entries kk, kk + 1
+          if (w.x == kNbrEmpty) break;
+          add2((int)(w.x >> 4), (int)(w.x & 15u), w.y != kNbrEmpty, (int)(w.y >> 4), (int)(w.y & 15u));
+        }
+      } else {
+        const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
+        for (int e = beg; e < end; e += 2) {
+          const bool two = (e + 1 < end);
+          const int s0 = __ldg(col + e), a0 = __ldg(eattr + e);
+          add2(s0, a0, two, two ? __ldg(col + e + 1) : s0, two ? (int)__ldg(eattr + e + 1) : a0);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const int q = lane + 32 * j;
+        if (q < D4) {
+          float4 rr = f4_add(acc[j], f4_add(act(ft[r * D4 + q], j, i), ee[kSelfLoopAttr * D4 + q]));   // self loop LAST
+          if (out_lo) st_f4(out_lo + (size_t)i * ld_out + 4 * q, f4_tf32_residual(rr));
+          if (round_out) rr = f4_tf32(rr);
+          st_f4(out + (size_t)i * ld_out + 4 * q, rr);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(empty_bar + s);
   }
 }
 
@@ -889,12 +1037,43 @@ extern "C" int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, in
   return gemm_run(j, stream);
 }
 
+template <int NCH, bool HAS_BN, bool DROP>
+static void launch_fwd_tile(const float* src, const float* bn_coef, int relu, const int32_t* rowptr, const int32_t* col,
+                            const uint8_t* eattr, const uint32_t* nbr, const float* B1, const float* B2, int64_t N, int D, int T,
+                            float* out, int64_t ld_out, int round_out, float* out_lo, const DropCfg& drop, cudaStream_t stream) {
+  auto k = gine_aggregate_fwd_tile_kernel<NCH, HAS_BN, DROP>;
+  const size_t smem = aggregate_tile_smem(D, T);
+  static bool attr_set = false;                      // per instantiation
+  if (!attr_set) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+  const int64_t ntiles = (N + T - 1) / T;
+  const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+  k<<<grid, kTileThreads, smem, stream>>>(src, bn_coef, relu, rowptr, col, eattr, nbr, B1, B2, (int)N, D, T, out, ld_out, round_out,
+                                          out_lo, drop);
+}
+
 static int aggregate_fwd_launch(const float* src, const float* bn_coef, int relu, const int32_t* rowptr, const int32_t* col,
-                                const uint8_t* eattr, const float* B1, const float* B2, const float* bias, bool scalar, int64_t N,
-                                int D, float* out, int64_t ld_out, int round_tf32_out, float* out_lo, const DropCfg drop, cudaStream_t stream) {
+                                const uint8_t* eattr, const uint32_t* nbr, const float* B1, const float* B2, const float* bias, bool scalar,
+                                int64_t N, int D, float* out, int64_t ld_out, int round_tf32_out, float* out_lo, const DropCfg drop,
+                                cudaStream_t stream) {
   REQUIRE_D(D);
   MOLCLR_REQUIRE(ld_out >= D && ld_out % 4 == 0, "aggregate_fwd: ld_out must be >= D and a multiple of 4");
   if (N == 0) return 0;
+  if (nbr && !scalar && g_aggregate_tile) {
+    // shared-memory tile path (see gine_aggregate_fwd_tile_kernel): T rows per stage, as many as fit
+    MOLCLR_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(nbr) & 15) == 0,
+                   "aggregate_fwd: src and nbr must be 16-byte aligned");
+    const int T = aggregate_tile_smem(D, 2 * kTileConsumerWarps) <= 200 * 1024 ? 2 * kTileConsumerWarps : kTileConsumerWarps;
+    NCH_DISPATCH(D / 4, {
+      if (bn_coef && drop.thr)
+        launch_fwd_tile<NCH, true, true>(src, bn_coef, relu, rowptr, col, eattr, nbr, B1, B2, N, D, T, out, ld_out, round_tf32_out, out_lo, drop, stream);
+      else if (bn_coef)
+        launch_fwd_tile<NCH, true, false>(src, bn_coef, relu, rowptr, col, eattr, nbr, B1, B2, N, D, T, out, ld_out, round_tf32_out, out_lo, drop, stream);
+      else
+        launch_fwd_tile<NCH, false, false>(src, nullptr, 0, rowptr, col, eattr, nbr, B1, B2, N, D, T, out, ld_out, round_tf32_out, out_lo, drop, stream);
+    });
+    MOLCLR_CHECK_LAUNCH("aggregate_fwd_tile");
+    return 0;
+  }
   const size_t smem = (size_t)(kNumEdgeClass + 2) * D * sizeof(float);
   NCH_DISPATCH(D / 4, {
     if (scalar) {
@@ -920,18 +1099,18 @@ static int aggregate_fwd_launch(const float* src, const float* bn_coef, int relu
 }
 
 extern "C" int molclr_gine_aggregate_fwd(const float* src, const float* bn_coef, int relu, const int32_t* rowptr,
-                                         const int32_t* col, const uint8_t* eattr, const float* B1, const float* B2,
-                                         int64_t N, int D, float* out, int64_t ld_out, int round_tf32_out, float* out_lo,
-                                         uint32_t drop_seed, float drop_p, cudaStream_t stream) {
+                                         const int32_t* col, const uint8_t* eattr, const uint32_t* nbr, const float* B1,
+                                         const float* B2, int64_t N, int D, float* out, int64_t ld_out, int round_tf32_out,
+                                         float* out_lo, uint32_t drop_seed, float drop_p, cudaStream_t stream) {
   MOLCLR_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "dropout probability %f not in [0, 1)", drop_p);
-  return aggregate_fwd_launch(src, bn_coef, relu, rowptr, col, eattr, B1, B2, nullptr, false, N, D, out, ld_out, round_tf32_out,
+  return aggregate_fwd_launch(src, bn_coef, relu, rowptr, col, eattr, nbr, B1, B2, nullptr, false, N, D, out, ld_out, round_tf32_out,
                               out_lo, make_drop(drop_seed, bn_coef ? drop_p : 0.f), stream);
 }
 
 extern "C" int molclr_gcn_aggregate_fwd(const float* src, const int32_t* rowptr, const int32_t* col, const uint8_t* eattr,
                                         const float* b1, const float* b2, const float* bias, int64_t N, int D, float* out,
                                         int64_t ld_out, cudaStream_t stream) {
-  return aggregate_fwd_launch(src, nullptr, 0, rowptr, col, eattr, b1, b2, bias, true, N, D, out, ld_out, 0, nullptr, make_drop(0, 0.f), stream);
+  return aggregate_fwd_launch(src, nullptr, 0, rowptr, col, eattr, nullptr, b1, b2, bias, true, N, D, out, ld_out, 0, nullptr, make_drop(0, 0.f), stream);
 }
 
 // Number of partial rows the persistent row-wise kernels with block partials emit (upper bound on

@@ -194,30 +194,25 @@ def _encoder_forward(m, plan, comp, training, pool_mode):
     for l in range(L):
         g, bn = m.gnns[l], m.batch_norms[l]
         dp = drops[l - 1] if l > 0 else (0, 0.0)
-        a, a_lo = ops.gine_aggregate_fwd(plan, src, g.edge_embedding1.weight.detach(), g.edge_embedding2.weight.detach(),
-                                         bn_coef=coef_prev, relu=True, round_out=True, want_lo=True, drop=dp) if comp else \
-            (ops.gine_aggregate_fwd(plan, src, g.edge_embedding1.weight.detach(), g.edge_embedding2.weight.detach(),
-                                    bn_coef=coef_prev, relu=True, round_out=True, drop=dp), None)
+        # a and u stay UNROUNDED fp32 (one tensor each): the compensated GEMMs derive their low halves on chip
+        a = ops.gine_aggregate_fwd(plan, src, g.edge_embedding1.weight.detach(), g.edge_embedding2.weight.detach(),
+                                   bn_coef=coef_prev, relu=True, round_out=False, drop=dp)
         (W1, W1_lo), (W2, W2_lo) = rw.get(g.mlp[0].weight), rw.get(g.mlp[2].weight)
         u = ops.padded(N, H, dev)
-        u_lo = ops.padded(N, H, dev) if comp else None
         ubits = ops.relu_bits_buffer(N, H, dev)       # [u > 0] as bits: the backward GEMM's mask (8 MB instead of 246)
-        ops.gemm(a, W1, N, H, D, A_lo=a_lo, B_lo=_lo(W1_lo, comp), out=u, out_lo=u_lo, bias=g.mlp[0].bias.detach(),
-                 relu=True, round_out=True, relu_bits=ubits)
+        ops.gemm(a, W1, N, H, D, B_lo=_lo(W1_lo, comp), out=u, bias=g.mlp[0].bias.detach(), relu=True, relu_bits=ubits)
         z = torch.empty(N, D, device=dev)
         if training:
             stats = torch.empty(T, 2, D, device=dev)
-            ops.gemm(u, W2, N, D, H, A_lo=u_lo, B_lo=_lo(W2_lo, comp), out=z, bias=g.mlp[2].bias.detach(), colstat=stats,
-                     colstat_mode=2)
+            ops.gemm(u, W2, N, D, H, B_lo=_lo(W2_lo, comp), out=z, bias=g.mlp[2].bias.detach(), colstat=stats, colstat_mode=2)
             momentum = 0.1 if bn.momentum is None else bn.momentum
             coef = ops.bn_fwd_finalize(stats, T, N, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
                                        bn.num_batches_tracked, momentum, bn.eps)
         else:
-            ops.gemm(u, W2, N, D, H, A_lo=u_lo, B_lo=_lo(W2_lo, comp), out=z, bias=g.mlp[2].bias.detach())
+            ops.gemm(u, W2, N, D, H, B_lo=_lo(W2_lo, comp), out=z, bias=g.mlp[2].bias.detach())
             coef = ops.bn_eval_coef(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
         layers.append((a, u, z, coef, W1, W2, ubits))
         src, coef_prev = z, coef
-        del a_lo, u_lo
     argmax = torch.empty(plan.G, D, dtype=torch.int32, device=dev) if pool_mode == 2 else None
     p, p_lo = ops.pool_fwd(plan, src, coef_prev, pool_mode, relu=False, round_out=True, want_lo=True, argmax=argmax, drop=drops[L - 1]) \
         if comp else (ops.pool_fwd(plan, src, coef_prev, pool_mode, relu=False, round_out=True, argmax=argmax, drop=drops[L - 1]), None)

@@ -131,13 +131,15 @@ def embed_nodes_bwd(plan, g):
     return dE[:119], dE[119:]
 
 
-def gine_aggregate_fwd(plan, src, B1, B2, bn_coef=None, relu=True, round_out=True, want_lo=False, drop=(0, 0.0)):
-    """Returns the aggregate (tf32-rounded if round_out), plus its tf32 residual when want_lo."""
+def gine_aggregate_fwd(plan, src, B1, B2, bn_coef=None, relu=True, round_out=True, want_lo=False, drop=(0, 0.0), use_nbr=True):
+    """Returns the aggregate (tf32-rounded if round_out), plus its tf32 residual when want_lo.  use_nbr=False withholds the
+    fixed-width neighbour table, which selects the warp-per-row CSR kernel instead of the shared-memory tile kernel."""
     D = src.shape[1]
     out = padded(plan.N, D, src.device)          # a GEMM operand: 128-byte aligned rows
     lo = padded(plan.N, D, src.device) if want_lo else None
     check(_lib.load().molclr_gine_aggregate_fwd(ptr(src), ptr(bn_coef), int(relu), ptr(plan.rowptr, torch.int32),
-                                                ptr(plan.col, torch.int32), ptr(plan.eattr, torch.uint8), ptr(B1), ptr(B2),
+                                                ptr(plan.col, torch.int32), ptr(plan.eattr, torch.uint8),
+                                                ptr(plan.nbr if use_nbr else None, torch.int32), ptr(B1), ptr(B2),
                                                 plan.N, D, ptr2d(out), out.stride(0), int(round_out), ptr2d(lo), drop[0], drop[1],
                                                 stream()), "gine_aggregate_fwd")
     return (out, lo) if want_lo else out

@@ -39,6 +39,43 @@ def test_plan_bit_exact(bs, seed):
     assert np.array_equal(got["gptr"], gptr) and np.array_equal(got["gperm"], gperm)
     xp = plan.xpacked[:plan.N].cpu().numpy()
     assert np.array_equal(xp & 0xff, bi.x[:, 0].numpy()) and np.array_equal(xp >> 8, bi.x[:, 1].numpy())
+    assert np.array_equal(plan.nbr[:8 * plan.N].cpu().numpy().view(np.uint32).reshape(-1, 8), _nbr_table(want, plan.N))
+
+
+def _nbr_table(csr, N):
+    """Fixed-width neighbour table restated from the CSR (include/molclr_b200.h: molclr_plan_build, `nbr`)."""
+    t = np.full((N, 8), 0xFFFFFFFF, dtype=np.uint32)
+    rp, col, ea = csr["rowptr"], csr["col"], csr["eattr"]
+    for n in range(N):
+        b, e = int(rp[n]), int(rp[n + 1])
+        if e - b <= 8:
+            t[n, :e - b] = (col[b:e].astype(np.uint32) << 4) | ea[b:e].astype(np.uint32)
+        else:
+            t[n, 7] = 0xFFFFFFFE
+    return t
+
+
+@pytest.mark.parametrize("D,drop", [(300, 0.0), (300, 0.3), (512, 0.0), (64, 0.0)])
+def test_aggregate_tile_kernel_equals_row_kernel(D, drop):
+    """The shared-memory tile kernel (neighbour table given) and the warp-per-row CSR kernel compute the same sums in the same
+    order: bitwise equal outputs, with and without the fused BatchNorm/ReLU/dropout, on molecules and on irregular graphs
+    (rows longer than the table, neighbours outside the staged tile, a ragged last tile)."""
+    from tests.test_gpu_properties import _random_batch
+    g = torch.Generator().manual_seed(D)
+    B1, B2 = torch.randn(5, D, generator=g).to(DEV), torch.randn(3, D, generator=g).to(DEV)
+    coef = torch.randn(4, D, generator=g)
+    coef[0] = coef[0].abs() + 0.5
+    for b in (make_pair_batch(200, seed=5)[0], _random_batch(np.random.default_rng(3), 30, 70), make_plain_batch(1, seed=1)):
+        plan = GraphPlan(b.to(DEV))
+        h = torch.randn(plan.N, D, generator=g).to(DEV)
+        for bn in (None, coef.to(DEV)):
+            dp = (1234, drop) if bn is not None else (0, 0.0)
+            a = ops.gine_aggregate_fwd(plan, h, B1, B2, bn_coef=bn, round_out=False, drop=dp)
+            r = ops.gine_aggregate_fwd(plan, h, B1, B2, bn_coef=bn, round_out=False, drop=dp, use_nbr=False)
+            assert torch.equal(a[:, :D], r[:, :D])
+        a, lo = ops.gine_aggregate_fwd(plan, h, B1, B2, round_out=True, want_lo=True)
+        r, rlo = ops.gine_aggregate_fwd(plan, h, B1, B2, round_out=True, want_lo=True, use_nbr=False)
+        assert torch.equal(a[:, :D], r[:, :D]) and torch.equal(lo[:, :D], rlo[:, :D])
 
 
 def test_plan_edge_cases():
@@ -226,6 +263,26 @@ def test_gemm_compensated_three_pass_is_fp32_accurate(M, N, K, b_mn):
     e3, e1 = rel_err(out, ref), rel_err(single, ref)
     assert e3 < 1e-5 and e1 > 20 * e3, (e3, e1)     # floor: the tensor core's truncating fp32 accumulation
     assert torch.equal(out_lo.cpu(), tf32_round(out.cpu() - tf32_round(out.cpu())))
+
+
+@pytest.mark.parametrize("M,N,K,b_mn", [(1000, 600, 300, False), (5000, 300, 600, False), (333, 512, 300, True), (130, 160, 40, False)])
+def test_gemm_compensated_with_low_half_derived_on_chip(M, N, K, b_mn):
+    """B_lo without A_lo: A is UNROUNDED fp32 and the kernel's converter warps form A_lo = tf32(A - trunc_tf32(A)) in shared
+    memory -- same ~fp32 accuracy as the explicit (A_hi, A_lo) pair, with one A tensor instead of two."""
+    g = torch.Generator().manual_seed(M + N + 1)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    B = torch.randn((K, N) if b_mn else (N, K), generator=g).to(DEV)
+    A_pad = ops.padded(M, K, DEV)
+    A_pad.copy_(A)
+    B_hi, B_lo = ops.split_tf32(B)
+    bias = torch.randn(N, generator=g).to(DEV)
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm(A_pad, B_hi, M, N, K, b_mn=b_mn, B_lo=B_lo, out=out, bias=bias)
+    ref = _gemm_ref(A, B, False, b_mn) + bias.double().cpu()
+    single = torch.empty(M, N, device=DEV)
+    ops.gemm(A_pad, B_hi, M, N, K, b_mn=b_mn, out=single, bias=bias)
+    e3, e1 = rel_err(out, ref), rel_err(single, ref)
+    assert e3 < 1e-5 and e1 > 20 * e3, (e3, e1)
 
 
 @pytest.mark.parametrize("R,O,I", [(5000, 300, 600), (5000, 600, 300), (4096, 256, 512), (700, 512, 300)])

@@ -24,7 +24,7 @@ def timeit(fn, iters=int(os.environ.get('ITERS', 10))):
 ONLY = os.environ.get("CASE")
 
 
-def case(name, M, N, K, comp=False, b_mn=False, relu=False, pad_k=0, dw=False, masked=False, stat=0):
+def case(name, M, N, K, comp=False, b_mn=False, relu=False, pad_k=0, dw=False, masked=False, stat=0, derive=False):
     if ONLY and not name.startswith(ONLY):
         return
     g = torch.Generator().manual_seed(0)
@@ -53,7 +53,9 @@ def case(name, M, N, K, comp=False, b_mn=False, relu=False, pad_k=0, dw=False, m
         B = B[:, :K]
     out = torch.empty(M, N, device=dev)
     lo = torch.empty(M, N, device=dev) if comp else None
-    A_lo = torch.randn(M, K + pad_k, generator=g).to(dev)[:, :K] if comp else None
+    A_lo = torch.randn(M, K + pad_k, generator=g).to(dev)[:, :K] if (comp and not derive) else None
+    if derive:
+        lo = None
     B_lo = (torch.randn_like(B) if comp else None)
     bias = torch.randn(N, device=dev)
     fn = lambda: ops.gemm(A, B, M, N, K, b_mn=b_mn, A_lo=A_lo, B_lo=B_lo, out=out, out_lo=lo, bias=bias, relu=relu, round_out=True,
@@ -71,6 +73,10 @@ if os.environ.get("QUICK"):
     sys.exit(0)
 case("fwd1 x1   [M,300]x[600,300]", M, 600, 300)
 case("fwd1 x3   [M,300]x[600,300]", M, 600, 300, comp=True)
+case("fwd1 x3 derive, aligned", M, 600, 300, comp=True, derive=True, pad_k=20)
+case("fwd1 x3 explicit lo, aligned", M, 600, 300, comp=True, pad_k=20)
+case("fwd2 x3 derive, aligned", M, 300, 600, comp=True, derive=True, pad_k=8)
+case("fwd2 x3 explicit lo, aligned", M, 300, 600, comp=True, pad_k=8)
 case("fwd2 x1   [M,600]x[300,600]", M, 300, 600)
 case("fwd2 x3   [M,600]x[300,600]", M, 300, 600, comp=True)
 case("fwd1 x1 K=320 aligned pitch", M, 600, 320)

@@ -38,6 +38,13 @@ idx = 4 * (N + 1) + 5 * E
 report("aggregate fwd (BN+ReLU fused, hi+lo out)", timeit(lambda k: ops.gine_aggregate_fwd(plan, srcs[k % 3], B1, B2, bn_coef=coef, want_lo=True)),
        4 * D * N * 3 + idx)
 report("aggregate fwd (BN+ReLU fused, hi out)", timeit(lambda k: ops.gine_aggregate_fwd(plan, srcs[k % 3], B1, B2, bn_coef=coef)), 4 * D * N * 2 + idx)
+report("aggregate fwd (BN+ReLU, fp32 out, tile kernel)", timeit(lambda k: ops.gine_aggregate_fwd(plan, srcs[k % 3], B1, B2, bn_coef=coef, round_out=False)),
+       4 * D * N * 2 + idx)
+report("aggregate fwd (BN+ReLU, fp32 out, row kernel)",
+       timeit(lambda k: ops.gine_aggregate_fwd(plan, srcs[k % 3], B1, B2, bn_coef=coef, round_out=False, use_nbr=False)), 4 * D * N * 2 + idx)
+report("aggregate fwd (layer 0, fp32 out, tile kernel)", timeit(lambda k: ops.gine_aggregate_fwd(plan, srcs[k % 3], B1, B2, round_out=False)), 4 * D * N * 2 + idx)
+report("aggregate fwd (layer 0, fp32 out, row kernel)", timeit(lambda k: ops.gine_aggregate_fwd(plan, srcs[k % 3], B1, B2, round_out=False, use_nbr=False)),
+       4 * D * N * 2 + idx)
 report("aggregate fwd (layer 0, hi+lo out)", timeit(lambda k: ops.gine_aggregate_fwd(plan, srcs[k % 3], B1, B2, want_lo=True)), 4 * D * N * 3 + idx)
 report("aggregate bwd (ReLU/BN stats fused)", timeit(lambda k: ops.gine_aggregate_bwd(plan, srcs[k % 3], z_prev=srcs[(k + 1) % 3], bn_coef=coef)),
        4 * D * N * 3 + 4 * (N + 1) + 4 * E)
