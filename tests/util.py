@@ -25,3 +25,60 @@ def sync_oracle_from(model, oracle):
     """Copies the state_dict of the CUDA drop-in into the CPU oracle (shared weights)."""
     oracle.load_state_dict({k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
     return oracle
+
+
+def golden_weights(template, seed):
+    """Deterministic parameter values as a function of (key, shape, seed) only, so that the fixture generator (on the
+    reference model's state_dict) and the tests (on the oracle's / the CUDA drop-in's) build IDENTICAL weights without
+    storing them: xavier-like uniform for matrices, small biases, BatchNorm affine near (1, 0), fresh running statistics."""
+    import zlib
+    out = {}
+    for k in sorted(template.keys()):
+        t = template[k]
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(k.encode())) % (2 ** 31))
+        if k.endswith("running_mean"):
+            v = torch.zeros(t.shape)
+        elif k.endswith("running_var"):
+            v = torch.ones(t.shape)
+        elif k.endswith("num_batches_tracked"):
+            v = torch.zeros(t.shape, dtype=torch.int64)
+        else:
+            u = torch.rand(tuple(t.shape), generator=g) * 2 - 1
+            if "batch_norms" in k:
+                v = (1.0 + 0.2 * u) if k.endswith("weight") else 0.2 * u
+            elif t.dim() == 2:
+                v = u * float(np.sqrt(6.0 / (t.shape[0] + t.shape[1])))
+            else:
+                v = 0.05 * u
+        out[k] = v.to(t.dtype)
+    return out
+
+
+def golden_batch(g, tag):
+    """Rebuilds a molclr_b200.Batch from the arrays `make_encoder_golden.py` stored under `tag`."""
+    from molclr_b200 import Batch
+    t = lambda k: torch.from_numpy(np.ascontiguousarray(g[f"{tag}_{k}"]))
+    return Batch(t("x"), t("edge_index"), t("edge_attr"), t("batch"))
+
+
+def check_golden_grads(model, g, tol, skip=()):
+    """Compares every parameter gradient with the reference's: norm-relative error on tensors stored in full, the norm and
+    the strided sample otherwise.  Returns the list of (key, error) that exceed `tol`."""
+    bad = []
+    for k, p in model.named_parameters():
+        if f"gradnorm.{k}" not in g.files or any(k.endswith(s) for s in skip):
+            continue
+        assert p.grad is not None, k
+        gr = p.grad.detach().double().cpu()
+        want_norm = float(g[f"gradnorm.{k}"])
+        if f"grad.{k}" in g.files:
+            want = torch.from_numpy(g[f"grad.{k}"]).double()
+            e = float((gr - want).norm() / max(want_norm, 1e-30))
+        else:
+            want = torch.from_numpy(g[f"gradsample.{k}"]).double()
+            flat = gr.reshape(-1)
+            got = flat[::flat.numel() // want.numel()][:want.numel()]
+            e = max(float((got - want).norm() / want.norm().clamp_min(1e-30)), abs(float(gr.norm()) - want_norm) / max(want_norm, 1e-30))
+        if not e < tol:
+            bad.append((k, e))
+    return bad
