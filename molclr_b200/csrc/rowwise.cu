@@ -242,18 +242,20 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_fwd_kernel(
 
 // ------------------------------------------------------------------------------------------------
 // GINE aggregation forward, shared-memory tile variant (the GINEConv product path; same sums in the same order).
-// The warp-per-row kernel above re-reads every neighbour row from L2 (1 + mean in-degree = 3.6 reads of each feature row),
-// which makes it L2 -> SM fabric bound well below the HBM roofline.  Molecules are small connected blocks of CONSECUTIVE
-// rows, so a tile of T consecutive rows holds almost all neighbours of its own rows: a producer warp streams tiles
-// [t*T, (t+1)*T) of `src` (one 1D bulk copy, T*D*4 bytes) and of the fixed-width neighbour table nbr[N][8] (see
-// molclr_plan_build) through a ring of shared-memory stages, and 15 consumer warps (warp = row, lanes = float4 chunks)
-// gather from the staged tile; a neighbour outside the tile (a molecule cut by the tile boundary) or a row with more than
-// 8 in-edges falls back to global loads.  Each feature row then crosses L2 -> SM once.  The previous layer's BatchNorm
-// coefficients live in registers (applied on use, as above), so the staged tile is read-only.
+// The warp-per-row kernel above is bound by latency, not bandwidth: a row is one long dependent chain (rowptr -> col ->
+// feature rows from L2 -> adds) per warp, a quarter of the lane slots idle (75 float4 chunks on 3 x 32 lanes), and its
+// registers allow 24 warps per SM.  Here molecules being small connected blocks of CONSECUTIVE rows is used: a producer
+// thread streams tiles [t*T, (t+1)*T) of `src` (one 1D bulk copy of T*D*4 bytes) and of the fixed-width neighbour table
+// nbr[N][8] (see molclr_plan_build) through a ring of shared-memory stages; ~1000 consumer threads are laid out as
+// R rows x D/4 float4 chunks (thread = one chunk of one row: no idle lanes, ~45 registers, 32 warps per SM) and gather
+// from the staged tile.  A neighbour outside the tile (a molecule cut by the tile boundary) or a row with more than 8
+// in-edges falls back to global loads.  The previous layer's BatchNorm coefficients and the self-loop table row of the
+// thread's chunk live in registers, so the staged tile is read-only and every feature row crosses L2 -> SM once.
 // ------------------------------------------------------------------------------------------------
-constexpr int kTileConsumerWarps = 15;       // + the producer warp = 512 threads: 128 registers each
-constexpr int kTileThreads = 32 * (kTileConsumerWarps + 1);
+constexpr int kTileThreads = 1024;
+constexpr int kTileConsumers = kTileThreads - 32;      // the last warp hosts the producer thread
 constexpr int kTileStages = 4;
+constexpr int kTileRowsPerSlot = 3;                    // rows of a stage handled by one consumer thread
 constexpr uint32_t kNbrEmpty = 0xFFFFFFFFu, kNbrLong = 0xFFFFFFFEu;
 
 // A/B switch for measurements: MOLCLR_AGG_TILE=0 forces the warp-per-row kernel
@@ -262,8 +264,14 @@ static const bool g_aggregate_tile = [] { const char* e = getenv("MOLCLR_AGG_TIL
 static size_t aggregate_tile_smem(int D, int T) {
   return (size_t)kNumEdgeClass * D * 4 + (size_t)kTileStages * T * (D * 4 + 32) + 2 * kTileStages * sizeof(uint64_t);
 }
+static int aggregate_tile_rows(int D) {       // rows per stage: a whole number of row slots per consumer thread that fits
+  const int R = kTileConsumers / (D / 4);
+  int per_slot = kTileRowsPerSlot;
+  while (per_slot > 1 && aggregate_tile_smem(D, per_slot * R) > 220 * 1024) --per_slot;
+  return per_slot * R;
+}
 
-template <int NCH, bool HAS_BN, bool DROP>
+template <bool HAS_BN, bool DROP>
 __global__ void __launch_bounds__(kTileThreads, 1) gine_aggregate_fwd_tile_kernel(
     const float* __restrict__ src, const float* __restrict__ coef, int relu,
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const uint8_t* __restrict__ eattr,
@@ -276,19 +284,21 @@ __global__ void __launch_bounds__(kTileThreads, 1) gine_aggregate_fwd_tile_kerne
   uint32_t* nb = reinterpret_cast<uint32_t*>(feat + (size_t)kTileStages * T * D4);   // [stages][T][8]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(nb + (size_t)kTileStages * T * 8);
   uint64_t* empty_bar = full_bar + kTileStages;
+  const int R = kTileConsumers / D4;                                 // rows in flight: consumer thread = (row slot, chunk)
+  const int n_active = R * D4, n_active_warps = (n_active + 31) >> 5;
   for (int i = threadIdx.x; i < kNumEdgeClass * D4; i += blockDim.x) {
     const int cls = i / D4, q = i - cls * D4;
     ee[i] = f4_add(ldg_f4(B1 + (size_t)(cls / 3) * D + 4 * q), ldg_f4(B2 + (size_t)(cls % 3) * D + 4 * q));
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTileStages; ++s) { ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, kTileConsumerWarps); }
+    for (int s = 0; s < kTileStages; ++s) { ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, n_active_warps); }
     ptx::fence_barrier_init();
   }
   __syncthreads();
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int ntiles = (N + T - 1) / T;
-  if (warp == kTileConsumerWarps) {
+  if (tid >= kTileConsumers) {
     // ---------------------------------------------------------------- producer
     if (lane == 0) {
       int k = 0;
@@ -303,20 +313,17 @@ __global__ void __launch_bounds__(kTileThreads, 1) gine_aggregate_fwd_tile_kerne
     }
     return;
   }
+  if ((tid & ~31) >= n_active) return;                               // warps without any (row slot, chunk)
   // ------------------------------------------------------------------ consumers
-  float4 scr[NCH], shr[NCH];
-#pragma unroll
-  for (int j = 0; j < NCH; ++j) {
-    const int q = lane + 32 * j;
-    scr[j] = (HAS_BN && q < D4) ? ldg_f4(coef + 4 * q) : f4_zero();
-    shr[j] = (HAS_BN && q < D4) ? ldg_f4(coef + D + 4 * q) : f4_zero();
-  }
-  auto act = [&](float4 v, int j, int row) -> float4 {
+  const bool active = tid < n_active;
+  const int slot = active ? tid / D4 : 0, q = active ? tid - slot * D4 : 0;
+  const float4 sc = HAS_BN ? ldg_f4(coef + 4 * q) : f4_zero(), sh = HAS_BN ? ldg_f4(coef + D + 4 * q) : f4_zero();
+  const float4 ee_self = ee[kSelfLoopAttr * D4 + q];
+  auto act = [&](float4 v, int row) -> float4 {
     if (HAS_BN) {
-      const float4 s = scr[j], b = shr[j];
-      v.x = fmaf(v.x, s.x, b.x); v.y = fmaf(v.y, s.y, b.y); v.z = fmaf(v.z, s.z, b.z); v.w = fmaf(v.w, s.w, b.w);
+      v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
       if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-      if (DROP) v = f4_mul(v, drop_mask4(drop, row, lane + 32 * j, D4));
+      if (DROP) v = f4_mul(v, drop_mask4(drop, row, q, D4));
     }
     return v;
   };
@@ -327,58 +334,39 @@ __global__ void __launch_bounds__(kTileThreads, 1) gine_aggregate_fwd_tile_kerne
     const float4* ft = feat + (size_t)s * T * D4;
     const uint32_t* nt = nb + (size_t)s * T * 8;
     ptx::mbar_wait(full_bar + s, (k / kTileStages) & 1);
-    // feature row `sidx`: from the staged tile when it is one of this tile's rows, else from global memory
-    auto fetch = [&](int sidx, float4 (&v)[NCH]) {
+    // chunk q of feature row `sidx`: from the staged tile when it is one of this tile's rows, else from global memory
+    auto fetch = [&](int sidx) -> float4 {
       const unsigned rel = (unsigned)(sidx - t0);
-      if (rel < (unsigned)rows) {
-#pragma unroll
-        for (int j = 0; j < NCH; ++j) { const int q = lane + 32 * j; v[j] = (q < D4) ? ft[rel * D4 + q] : f4_zero(); }
-      } else {
-#pragma unroll
-        for (int j = 0; j < NCH; ++j) { const int q = lane + 32 * j; v[j] = (q < D4) ? ldg_f4(src + (size_t)sidx * D + 4 * q) : f4_zero(); }
-      }
+      return rel < (unsigned)rows ? ft[rel * D4 + q] : ldg_f4(src + (size_t)sidx * D + 4 * q);
     };
-    for (int r = warp; r < rows; r += kTileConsumerWarps) {
-      const int i = t0 + r;
-      float4 acc[NCH];
-#pragma unroll
-      for (int j = 0; j < NCH; ++j) acc[j] = f4_zero();
-      auto add2 = [&](int s0, int a0, bool two, int s1, int a1) {      // same order as the row kernel: e, then e + 1
-        float4 v0[NCH], v1[NCH];
-        fetch(s0, v0);
-        if (two) fetch(s1, v1);
-#pragma unroll
-        for (int j = 0; j < NCH; ++j) {
-          const int q = lane + 32 * j;
-          if (q < D4) {
-            acc[j] = f4_add(acc[j], f4_add(act(v0[j], j, s0), ee[a0 * D4 + q]));
-            if (two) acc[j] = f4_add(acc[j], f4_add(act(v1[j], j, s1), ee[a1 * D4 + q]));
+    if (active) {
+      for (int r = slot; r < rows; r += R) {
+        const int i = t0 + r;
+        const uint32_t* nr = nt + r * 8;
+        float4 acc = f4_zero();
+        if (nr[7] != kNbrLong) {
+          for (int kk = 0; kk < 8; kk += 2) {
+            const uint2 w = *reinterpret_cast<const uint2*>(nr + kk);      // (source << 4 | attr) of entries kk, kk + 1
+            if (w.x == kNbrEmpty) break;
+            const bool two = w.y != kNbrEmpty;
+            const int s0 = (int)(w.x >> 4), s1 = (int)(w.y >> 4);
+            const float4 v0 = fetch(s0), e0 = ee[(w.x & 15u) * D4 + q];
+            float4 v1 = f4_zero(), e1 = f4_zero();
+            if (two) { v1 = fetch(s1); e1 = ee[(w.y & 15u) * D4 + q]; }
+            acc = f4_add(acc, f4_add(act(v0, s0), e0));                    // same order as the row kernel: e, then e + 1
+            if (two) acc = f4_add(acc, f4_add(act(v1, s1), e1));
+          }
+        } else {
+          const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
+          for (int e = beg; e < end; ++e) {
+            const int s0 = __ldg(col + e);
+            acc = f4_add(acc, f4_add(act(fetch(s0), s0), ee[(int)__ldg(eattr + e) * D4 + q]));
           }
         }
-      };
-      if (nt[r * 8 + 7] != kNbrLong) {
-        for (int kk = 0; kk < 8; kk += 2) {
-          const uint2 w = *reinterpret_cast<const uint2*>(nt + r * 8 + kk);      // (source << 4 | attr) of entries kk, kk + 1
-          if (w.x == kNbrEmpty) break;
-          add2((int)(w.x >> 4), (int)(w.x & 15u), w.y != kNbrEmpty, (int)(w.y >> 4), (int)(w.y & 15u));
-        }
-      } else {
-        const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
-        for (int e = beg; e < end; e += 2) {
-          const bool two = (e + 1 < end);
-          const int s0 = __ldg(col + e), a0 = __ldg(eattr + e);
-          add2(s0, a0, two, two ? __ldg(col + e + 1) : s0, two ? (int)__ldg(eattr + e + 1) : a0);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < NCH; ++j) {
-        const int q = lane + 32 * j;
-        if (q < D4) {
-          float4 rr = f4_add(acc[j], f4_add(act(ft[r * D4 + q], j, i), ee[kSelfLoopAttr * D4 + q]));   // self loop LAST
-          if (out_lo) st_f4(out_lo + (size_t)i * ld_out + 4 * q, f4_tf32_residual(rr));
-          if (round_out) rr = f4_tf32(rr);
-          st_f4(out + (size_t)i * ld_out + 4 * q, rr);
-        }
+        float4 rr = f4_add(acc, f4_add(act(ft[r * D4 + q], i), ee_self));   // self loop LAST
+        if (out_lo) st_f4(out_lo + (size_t)i * ld_out + 4 * q, f4_tf32_residual(rr));
+        if (round_out) rr = f4_tf32(rr);
+        st_f4(out + (size_t)i * ld_out + 4 * q, rr);
       }
     }
     __syncwarp();
@@ -1037,14 +1025,14 @@ extern "C" int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, in
   return gemm_run(j, stream);
 }
 
-template <int NCH, bool HAS_BN, bool DROP>
+template <bool HAS_BN, bool DROP>
 static void launch_fwd_tile(const float* src, const float* bn_coef, int relu, const int32_t* rowptr, const int32_t* col,
                             const uint8_t* eattr, const uint32_t* nbr, const float* B1, const float* B2, int64_t N, int D, int T,
                             float* out, int64_t ld_out, int round_out, float* out_lo, const DropCfg& drop, cudaStream_t stream) {
-  auto k = gine_aggregate_fwd_tile_kernel<NCH, HAS_BN, DROP>;
+  auto k = gine_aggregate_fwd_tile_kernel<HAS_BN, DROP>;
   const size_t smem = aggregate_tile_smem(D, T);
   static bool attr_set = false;                      // per instantiation
-  if (!attr_set) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+  if (!attr_set) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
   const int64_t ntiles = (N + T - 1) / T;
   const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
   k<<<grid, kTileThreads, smem, stream>>>(src, bn_coef, relu, rowptr, col, eattr, nbr, B1, B2, (int)N, D, T, out, ld_out, round_out,
@@ -1059,18 +1047,17 @@ static int aggregate_fwd_launch(const float* src, const float* bn_coef, int relu
   MOLCLR_REQUIRE(ld_out >= D && ld_out % 4 == 0, "aggregate_fwd: ld_out must be >= D and a multiple of 4");
   if (N == 0) return 0;
   if (nbr && !scalar && g_aggregate_tile) {
-    // shared-memory tile path (see gine_aggregate_fwd_tile_kernel): T rows per stage, as many as fit
+    // shared-memory tile path (see gine_aggregate_fwd_tile_kernel)
     MOLCLR_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(nbr) & 15) == 0,
                    "aggregate_fwd: src and nbr must be 16-byte aligned");
-    const int T = aggregate_tile_smem(D, 2 * kTileConsumerWarps) <= 200 * 1024 ? 2 * kTileConsumerWarps : kTileConsumerWarps;
-    NCH_DISPATCH(D / 4, {
-      if (bn_coef && drop.thr)
-        launch_fwd_tile<NCH, true, true>(src, bn_coef, relu, rowptr, col, eattr, nbr, B1, B2, N, D, T, out, ld_out, round_tf32_out, out_lo, drop, stream);
-      else if (bn_coef)
-        launch_fwd_tile<NCH, true, false>(src, bn_coef, relu, rowptr, col, eattr, nbr, B1, B2, N, D, T, out, ld_out, round_tf32_out, out_lo, drop, stream);
-      else
-        launch_fwd_tile<NCH, false, false>(src, nullptr, 0, rowptr, col, eattr, nbr, B1, B2, N, D, T, out, ld_out, round_tf32_out, out_lo, drop, stream);
-    });
+    const int T = aggregate_tile_rows(D);
+    MOLCLR_REQUIRE(aggregate_tile_smem(D, T) <= 227 * 1024, "aggregate_fwd: tile of %d rows x %d features does not fit shared memory", T, D);
+    if (bn_coef && drop.thr)
+      launch_fwd_tile<true, true>(src, bn_coef, relu, rowptr, col, eattr, nbr, B1, B2, N, D, T, out, ld_out, round_tf32_out, out_lo, drop, stream);
+    else if (bn_coef)
+      launch_fwd_tile<true, false>(src, bn_coef, relu, rowptr, col, eattr, nbr, B1, B2, N, D, T, out, ld_out, round_tf32_out, out_lo, drop, stream);
+    else
+      launch_fwd_tile<false, false>(src, nullptr, 0, rowptr, col, eattr, nbr, B1, B2, N, D, T, out, ld_out, round_tf32_out, out_lo, drop, stream);
     MOLCLR_CHECK_LAUNCH("aggregate_fwd_tile");
     return 0;
   }
