@@ -53,7 +53,7 @@ int molclr_device_info(int* sm_count, int* cc);
  *   cnt[N][8] float: in-edge counts per bond type (0..4, self loop = type 4) and direction (5..7), clamped to 2048
  *     (exact in TF32: they are an operand of the table-gradient contraction);
  *   nbr[N][8] uint32 (optional, 32-byte aligned): fixed-width copy of rows with <= 8 in-edges, entry = source << 4 | eattr,
- *     0xFFFFFFFF = empty, [7] = 0xFFFFFFFE = "row too long, use the CSR": lets the aggregation kernel fetch a row's neighbour
+ *     0xFFFFFFFF = empty, [0] = 0xFFFFFFFE = "row too long, use the CSR": lets the aggregation kernel fetch a row's neighbour
  *     list with ONE load (no rowptr -> col dependency);
  *   gptr[G+1], gperm[N]: nodes grouped by graph (identity permutation for sorted `batch`).
  *   status[4]: [0] = error bits (1 node feature, 2 edge endpoint, 4 edge attr, 8 batch id out of

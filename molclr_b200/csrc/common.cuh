@@ -54,6 +54,28 @@ __device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<fl
 
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+// Packed fp32 pairs (FADD2 / FFMA2 on sm_100): the same IEEE round-to-nearest results as four scalar instructions in half
+// the issue slots -- for kernels that are bound by instruction issue rather than by the FP32 pipe.
+__device__ __forceinline__ float4 f4_add2(float4 a, float4 b) {
+  float4 r;
+  asm("{\n\t.reg .b64 a0, a1, b0, b1, r0, r1;\n\t"
+      "mov.b64 a0, {%4, %5}; mov.b64 a1, {%6, %7}; mov.b64 b0, {%8, %9}; mov.b64 b1, {%10, %11};\n\t"
+      "add.rn.f32x2 r0, a0, b0; add.rn.f32x2 r1, a1, b1;\n\t"
+      "mov.b64 {%0, %1}, r0; mov.b64 {%2, %3}, r1;\n\t}"
+      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+      : "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w));
+  return r;
+}
+__device__ __forceinline__ float4 f4_fma2(float4 a, float4 b, float4 c) {
+  float4 r;
+  asm("{\n\t.reg .b64 a0, a1, b0, b1, c0, c1, r0, r1;\n\t"
+      "mov.b64 a0, {%4, %5}; mov.b64 a1, {%6, %7}; mov.b64 b0, {%8, %9}; mov.b64 b1, {%10, %11}; mov.b64 c0, {%12, %13}; mov.b64 c1, {%14, %15};\n\t"
+      "fma.rn.f32x2 r0, a0, b0, c0; fma.rn.f32x2 r1, a1, b1, c1;\n\t"
+      "mov.b64 {%0, %1}, r0; mov.b64 {%2, %3}, r1;\n\t}"
+      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+      : "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w), "f"(c.x), "f"(c.y), "f"(c.z), "f"(c.w));
+  return r;
+}
 
 __device__ __forceinline__ float4 f4_tf32(float4 v) {
   return make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));

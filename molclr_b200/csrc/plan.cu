@@ -157,12 +157,12 @@ __global__ void plan_rows_kernel(const int64_t* __restrict__ ei, const int64_t* 
       eattr[p] = (uint8_t)(t * 3 + r);
       c[t]++; c[5 + r]++;
     }
-    if (nbr) {     // fixed-width copy of short rows: (source << 4 | attr) x 8, 0xFFFFFFFF = empty, [7] = 0xFFFFFFFE = row too long
+    if (nbr) {     // fixed-width copy of short rows: (source << 4 | attr) x 8, 0xFFFFFFFF = empty, [0] = 0xFFFFFFFE = row too long
       const bool fits = (e - b <= 8) && N < (1ll << 28);
       uint32_t w[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) w[k] = (fits && b + k < e) ? ((uint32_t)col[b + k] << 4 | (uint32_t)eattr[b + k]) : 0xFFFFFFFFu;
-      if (!fits) w[7] = 0xFFFFFFFEu;
+      if (!fits) w[0] = 0xFFFFFFFEu;
       uint4* dst = reinterpret_cast<uint4*>(nbr + 8 * n);
       dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
       dst[1] = make_uint4(w[4], w[5], w[6], w[7]);

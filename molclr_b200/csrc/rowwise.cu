@@ -56,7 +56,10 @@ __device__ __forceinline__ float4 drop_mask4(const DropCfg& d, int row, int q, i
   m.z = (h1 & 0xffffu) >= d.thr ? d.scale : 0.f; m.w = (h1 >> 16) >= d.thr ? d.scale : 0.f;
   return m;
 }
-__device__ __forceinline__ float4 f4_mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+// (a rounded product, never contracted into an FMA with a following add: dropout(h) is a tensor of its own in the reference)
+__device__ __forceinline__ float4 f4_mul(float4 a, float4 b) {
+  return make_float4(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y), __fmul_rn(a.z, b.z), __fmul_rn(a.w, b.w));
+}
 
 #define NCH_DISPATCH(D4, ...)                                                    \
   do {                                                                           \
@@ -254,20 +257,24 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_fwd_kernel(
 // ------------------------------------------------------------------------------------------------
 constexpr int kTileThreads = 1024;
 constexpr int kTileConsumers = kTileThreads - 32;      // the last warp hosts the producer thread
-constexpr int kTileStages = 4;
-constexpr int kTileRowsPerSlot = 3;                    // rows of a stage handled by one consumer thread
+constexpr int kTileMaxStages = 12;
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+// ring depth and rows of a stage handled by one consumer thread (overridable for measurements; sweep on B200 at the bench
+// shape, tools/sweep_aggregate.sh: 3 x 3 and 4 x 2 are best, deeper rings are SLOWER -- more reads in flight delay the writes)
+static const int g_tile_stages = env_int("MOLCLR_AGG_STAGES", 3), g_tile_rows_per_slot = env_int("MOLCLR_AGG_ROWS", 3);
+static const int g_tile_store_cs = env_int("MOLCLR_AGG_STORE_CS", 0), g_tile_blocked = env_int("MOLCLR_AGG_BLOCKED", 0);
 constexpr uint32_t kNbrEmpty = 0xFFFFFFFFu, kNbrLong = 0xFFFFFFFEu;
 
 // A/B switch for measurements: MOLCLR_AGG_TILE=0 forces the warp-per-row kernel
 static const bool g_aggregate_tile = [] { const char* e = getenv("MOLCLR_AGG_TILE"); return !(e && e[0] == '0'); }();
 
-static size_t aggregate_tile_smem(int D, int T) {
-  return (size_t)kNumEdgeClass * D * 4 + (size_t)kTileStages * T * (D * 4 + 32) + 2 * kTileStages * sizeof(uint64_t);
+static size_t aggregate_tile_smem(int D, int T, int stages) {
+  return (size_t)kNumEdgeClass * D * 4 + (size_t)stages * T * (D * 4 + 32) + 2 * kTileMaxStages * sizeof(uint64_t);
 }
-static int aggregate_tile_rows(int D) {       // rows per stage: a whole number of row slots per consumer thread that fits
+static int aggregate_tile_rows(int D, int stages) {       // rows per stage: a whole number of row slots per consumer thread that fits
   const int R = kTileConsumers / (D / 4);
-  int per_slot = kTileRowsPerSlot;
-  while (per_slot > 1 && aggregate_tile_smem(D, per_slot * R) > 220 * 1024) --per_slot;
+  int per_slot = g_tile_rows_per_slot;
+  while (per_slot > 1 && aggregate_tile_smem(D, per_slot * R, stages) > 220 * 1024) --per_slot;
   return per_slot * R;
 }
 
@@ -276,14 +283,15 @@ __global__ void __launch_bounds__(kTileThreads, 1) gine_aggregate_fwd_tile_kerne
     const float* __restrict__ src, const float* __restrict__ coef, int relu,
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const uint8_t* __restrict__ eattr,
     const uint32_t* __restrict__ nbr, const float* __restrict__ B1, const float* __restrict__ B2, int N, int D, int T,
-    float* __restrict__ out, long long ld_out, int round_out, float* __restrict__ out_lo, const DropCfg drop) {
+    int kTileStages, int store_cs, int blocked, float* __restrict__ out, long long ld_out, int round_out, float* __restrict__ out_lo,
+    const DropCfg drop) {
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* ee = sm4;                                                  // [15][D4]
   float4* feat = ee + kNumEdgeClass * D4;                            // [stages][T][D4]
   uint32_t* nb = reinterpret_cast<uint32_t*>(feat + (size_t)kTileStages * T * D4);   // [stages][T][8]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(nb + (size_t)kTileStages * T * 8);
-  uint64_t* empty_bar = full_bar + kTileStages;
+  uint64_t* empty_bar = full_bar + kTileMaxStages;
   const int R = kTileConsumers / D4;                                 // rows in flight: consumer thread = (row slot, chunk)
   const int n_active = R * D4, n_active_warps = (n_active + 31) >> 5;
   for (int i = threadIdx.x; i < kNumEdgeClass * D4; i += blockDim.x) {
@@ -298,11 +306,15 @@ __global__ void __launch_bounds__(kTileThreads, 1) gine_aggregate_fwd_tile_kerne
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int ntiles = (N + T - 1) / T;
+  // tiles of this CTA: round-robin over the grid, or (blocked) one contiguous range per CTA
+  const int per_cta = (ntiles + gridDim.x - 1) / gridDim.x;
+  const int t_first = blocked ? blockIdx.x * per_cta : blockIdx.x, t_step = blocked ? 1 : gridDim.x;
+  const int t_end = blocked ? min(ntiles, t_first + per_cta) : ntiles;
   if (tid >= kTileConsumers) {
     // ---------------------------------------------------------------- producer
     if (lane == 0) {
       int k = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++k) {
+      for (int t = t_first; t < t_end; t += t_step, ++k) {
         const int s = k % kTileStages;
         ptx::mbar_wait(empty_bar + s, ((k / kTileStages) & 1) ^ 1);
         const int t0 = t * T, rows = min(T, N - t0);
@@ -318,55 +330,65 @@ __global__ void __launch_bounds__(kTileThreads, 1) gine_aggregate_fwd_tile_kerne
   const bool active = tid < n_active;
   const int slot = active ? tid / D4 : 0, q = active ? tid - slot * D4 : 0;
   const float4 sc = HAS_BN ? ldg_f4(coef + 4 * q) : f4_zero(), sh = HAS_BN ? ldg_f4(coef + D + 4 * q) : f4_zero();
-  const float4 ee_self = ee[kSelfLoopAttr * D4 + q];
+  const float4* ee_q = ee + q;                                       // this thread's chunk of the 15 table rows
+  const float4 ee_self = ee_q[kSelfLoopAttr * D4];
   auto act = [&](float4 v, int row) -> float4 {
     if (HAS_BN) {
-      v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+      v = f4_fma2(v, sc, sh);
       if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
       if (DROP) v = f4_mul(v, drop_mask4(drop, row, q, D4));
     }
     return v;
   };
   int k = 0;
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++k) {
+  for (int t = t_first; t < t_end; t += t_step, ++k) {
     const int s = k % kTileStages;
     const int t0 = t * T, rows = min(T, N - t0);
-    const float4* ft = feat + (size_t)s * T * D4;
+    const float4* ft_q = feat + (size_t)s * T * D4 + q;              // this thread's chunk of the staged rows
     const uint32_t* nt = nb + (size_t)s * T * 8;
     ptx::mbar_wait(full_bar + s, (k / kTileStages) & 1);
-    // chunk q of feature row `sidx`: from the staged tile when it is one of this tile's rows, else from global memory
-    auto fetch = [&](int sidx) -> float4 {
-      const unsigned rel = (unsigned)(sidx - t0);
-      return rel < (unsigned)rows ? ft[rel * D4 + q] : ldg_f4(src + (size_t)sidx * D + 4 * q);
-    };
     if (active) {
       for (int r = slot; r < rows; r += R) {
         const int i = t0 + r;
-        const uint32_t* nr = nt + r * 8;
         float4 acc = f4_zero();
-        if (nr[7] != kNbrLong) {
-          for (int kk = 0; kk < 8; kk += 2) {
-            const uint2 w = *reinterpret_cast<const uint2*>(nr + kk);      // (source << 4 | attr) of entries kk, kk + 1
-            if (w.x == kNbrEmpty) break;
-            const bool two = w.y != kNbrEmpty;
-            const int s0 = (int)(w.x >> 4), s1 = (int)(w.y >> 4);
-            const float4 v0 = fetch(s0), e0 = ee[(w.x & 15u) * D4 + q];
-            float4 v1 = f4_zero(), e1 = f4_zero();
-            if (two) { v1 = fetch(s1); e1 = ee[(w.y & 15u) * D4 + q]; }
-            acc = f4_add(acc, f4_add(act(v0, s0), e0));                    // same order as the row kernel: e, then e + 1
-            if (two) acc = f4_add(acc, f4_add(act(v1, s1), e1));
+        // one in-edge, packed (source << 4 | attr): acc += f(src[source]) + table[attr]; the source row comes from the staged
+        // tile when it is one of this tile's rows, else (a molecule cut by the tile boundary) from global memory
+        auto edge = [&](uint32_t w) {
+          const int sidx = (int)(w >> 4);
+          const unsigned rel = (unsigned)(sidx - t0);
+          float4 v;
+          if (rel < (unsigned)rows) v = ft_q[rel * D4];
+          else v = ldg_f4(src + (size_t)sidx * D + 4 * q);
+          acc = f4_add2(acc, f4_add2(act(v, sidx), ee_q[(w & 15u) * D4]));
+        };
+        const uint4 wa = *reinterpret_cast<const uint4*>(nt + r * 8);
+        if (wa.x < kNbrLong) {                                       // entries in input order; kNbrEmpty ends the list
+          edge(wa.x);
+          if (wa.y < kNbrLong) {
+            edge(wa.y);
+            if (wa.z < kNbrLong) {
+              edge(wa.z);
+              if (wa.w < kNbrLong) {
+                edge(wa.w);
+                const uint4 wb = *reinterpret_cast<const uint4*>(nt + r * 8 + 4);
+                const uint32_t w4[4] = {wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  if (w4[kk] >= kNbrLong) break;
+                  edge(w4[kk]);
+                }
+              }
+            }
           }
-        } else {
+        } else if (wa.x == kNbrLong) {                               // more than 8 in-edges: walk the CSR row
           const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
-          for (int e = beg; e < end; ++e) {
-            const int s0 = __ldg(col + e);
-            acc = f4_add(acc, f4_add(act(fetch(s0), s0), ee[(int)__ldg(eattr + e) * D4 + q]));
-          }
+          for (int e = beg; e < end; ++e) edge(((uint32_t)__ldg(col + e) << 4) | (uint32_t)__ldg(eattr + e));
         }
-        float4 rr = f4_add(acc, f4_add(act(ft[r * D4 + q], i), ee_self));   // self loop LAST
+        float4 rr = f4_add2(acc, f4_add2(act(ft_q[r * D4], i), ee_self));   // self loop LAST
         if (out_lo) st_f4(out_lo + (size_t)i * ld_out + 4 * q, f4_tf32_residual(rr));
         if (round_out) rr = f4_tf32(rr);
-        st_f4(out + (size_t)i * ld_out + 4 * q, rr);
+        if (store_cs) __stcs(reinterpret_cast<float4*>(out + (size_t)i * ld_out + 4 * q), rr);
+        else st_f4(out + (size_t)i * ld_out + 4 * q, rr);
       }
     }
     __syncwarp();
@@ -1030,13 +1052,14 @@ static void launch_fwd_tile(const float* src, const float* bn_coef, int relu, co
                             const uint8_t* eattr, const uint32_t* nbr, const float* B1, const float* B2, int64_t N, int D, int T,
                             float* out, int64_t ld_out, int round_out, float* out_lo, const DropCfg& drop, cudaStream_t stream) {
   auto k = gine_aggregate_fwd_tile_kernel<HAS_BN, DROP>;
-  const size_t smem = aggregate_tile_smem(D, T);
+  const int stages = g_tile_stages < 2 ? 2 : (g_tile_stages > kTileMaxStages ? kTileMaxStages : g_tile_stages);
+  const size_t smem = aggregate_tile_smem(D, T, stages);
   static bool attr_set = false;                      // per instantiation
   if (!attr_set) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
   const int64_t ntiles = (N + T - 1) / T;
   const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
-  k<<<grid, kTileThreads, smem, stream>>>(src, bn_coef, relu, rowptr, col, eattr, nbr, B1, B2, (int)N, D, T, out, ld_out, round_out,
-                                          out_lo, drop);
+  k<<<grid, kTileThreads, smem, stream>>>(src, bn_coef, relu, rowptr, col, eattr, nbr, B1, B2, (int)N, D, T, stages, g_tile_store_cs, g_tile_blocked, out,
+                                          ld_out, round_out, out_lo, drop);
 }
 
 static int aggregate_fwd_launch(const float* src, const float* bn_coef, int relu, const int32_t* rowptr, const int32_t* col,
@@ -1050,8 +1073,9 @@ static int aggregate_fwd_launch(const float* src, const float* bn_coef, int relu
     // shared-memory tile path (see gine_aggregate_fwd_tile_kernel)
     MOLCLR_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(nbr) & 15) == 0,
                    "aggregate_fwd: src and nbr must be 16-byte aligned");
-    const int T = aggregate_tile_rows(D);
-    MOLCLR_REQUIRE(aggregate_tile_smem(D, T) <= 227 * 1024, "aggregate_fwd: tile of %d rows x %d features does not fit shared memory", T, D);
+    const int stages = g_tile_stages < 2 ? 2 : (g_tile_stages > kTileMaxStages ? kTileMaxStages : g_tile_stages);
+    const int T = aggregate_tile_rows(D, stages);
+    MOLCLR_REQUIRE(aggregate_tile_smem(D, T, stages) <= 227 * 1024, "aggregate_fwd: tile of %d rows x %d features does not fit shared memory", T, D);
     if (bn_coef && drop.thr)
       launch_fwd_tile<true, true>(src, bn_coef, relu, rowptr, col, eattr, nbr, B1, B2, N, D, T, out, ld_out, round_tf32_out, out_lo, drop, stream);
     else if (bn_coef)

@@ -51,7 +51,7 @@ def _nbr_table(csr, N):
         if e - b <= 8:
             t[n, :e - b] = (col[b:e].astype(np.uint32) << 4) | ea[b:e].astype(np.uint32)
         else:
-            t[n, 7] = 0xFFFFFFFE
+            t[n, 0] = 0xFFFFFFFE
     return t
 
 

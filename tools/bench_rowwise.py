@@ -35,6 +35,11 @@ def report(name, us, nbytes):
 
 
 idx = 4 * (N + 1) + 5 * E
+if os.environ.get("ONLY_AGG"):
+    report("aggregate fwd (BN+ReLU, fp32 out, tile kernel)", timeit(lambda k: ops.gine_aggregate_fwd(plan, srcs[k % 3], B1, B2, bn_coef=coef, round_out=False)),
+           4 * D * N * 2 + idx)
+    report("aggregate fwd (layer 0, fp32 out, tile kernel)", timeit(lambda k: ops.gine_aggregate_fwd(plan, srcs[k % 3], B1, B2, round_out=False)), 4 * D * N * 2 + idx)
+    sys.exit(0)
 report("aggregate fwd (BN+ReLU fused, hi+lo out)", timeit(lambda k: ops.gine_aggregate_fwd(plan, srcs[k % 3], B1, B2, bn_coef=coef, want_lo=True)),
        4 * D * N * 3 + idx)
 report("aggregate fwd (BN+ReLU fused, hi out)", timeit(lambda k: ops.gine_aggregate_fwd(plan, srcs[k % 3], B1, B2, bn_coef=coef)), 4 * D * N * 2 + idx)
