@@ -193,6 +193,10 @@ typedef struct {
   uint32_t* relu_bits;        /* out: bit (n % 32) of word [m][n / 32] = (result[m][n] > 0)               */
   const uint32_t* mask_bits;  /* in : result[m][n] = 0 where the bit is clear (ReLU backward), after bias/relu */
   int64_t ld_bits;            /* words per row of either, >= molclr_gemm_mask_words(N)                    */
+  int32_t compensate;         /* 1: A and B are UNROUNDED fp32, both K-major, A_lo = B_lo = NULL: ~fp32-accurate product with
+                                 every low half derived on chip -- pass 1 in TF32 on the raw tiles (the tensor core truncates),
+                                 the corrections (A - trunc A) * B and A * (B - trunc B) as kind::f16 MMAs on bf16 tiles the
+                                 kernel forms in shared memory (their 2^-9 rounding applies to terms 2^-10 of the product)    */
 } molclr_gemm_args;
 /* column statistics are emitted per group of molclr_gemm_colstat_tile_rows() (= 32) consecutive rows;
  * molclr_gemm_colstat_tiles(M) groups are written (a multiple of 4; trailing groups may be empty). */

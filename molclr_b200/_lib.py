@@ -31,6 +31,7 @@ class GemmArgs(C.Structure):
         ("colstat", vp), ("colstat_mode", C.c_int32),
         ("split_k", C.c_int32),
         ("relu_bits", vp), ("mask_bits", vp), ("ld_bits", i64),
+        ("compensate", C.c_int32),
     ]
 
 

@@ -14,6 +14,7 @@
 //
 // A scalar-FMA kernel with the same argument struct (MOLCLR_GEMM_IMPL=simt) exists for debugging
 // the tensor-core path on the GPU; it is never selected implicitly.
+#include <cuda_bf16.h>
 #include <cstdlib>
 #include <cstring>
 
@@ -59,7 +60,7 @@ struct GemmCfg {
   // epilogue warps: two per TMEM lane quadrant (splitting the column chunks) where shared memory allows
   static constexpr int EPI_WARPS = SMALL_EPI ? 4 : 8;
   // converter warps (compensated product with derive_lo): compute the A_lo tile from the fp32 A tile in shared memory
-  static constexpr int CONV_WARPS = FOUR ? 2 : 0;
+  static constexpr int CONV_WARPS = FOUR ? 8 : 0;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * CONV_WARPS;
   static constexpr int STAGING_BYTES = EPI_WARPS * 32 * CHUNK_LD * 4;     // per epilogue warp: 32 rows x chunk
   static constexpr bool BIAS_SMEM = !(FOUR && !TWO);       // (the single-CTA compensated config has no room left)
@@ -184,6 +185,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   static_assert((4 * Cfg::STAGES + 4) * 8 + 4 <= 512, "barrier area");
   float* bias_s = reinterpret_cast<float*>(smem + Cfg::PIPE_BYTES + Cfg::STAGING_BYTES + 512);   // [2][256]
   const bool derive = FOUR && p.derive_lo != 0;
+  // derive_lo == 2 ("mixed"): A and B are both UNROUNDED fp32, K-major; stage = [A][A_hi16|A_lo16][B][B_hi16|B_lo16]: the tensor core
+  // truncates the raw tiles for the TF32 pass, the converter warps form bf16(x) and bf16(x - trunc_tf32(x)) of both tiles for the
+  // two correction passes, which run as kind::f16 MMAs -- no rounded or split copy of either operand is ever read from HBM / L2
+  const bool mixed = FOUR && p.derive_lo == 2;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = p.n_tiles, m_tiles = p.m_tiles;
@@ -225,12 +230,27 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int kb0 = (t / (n_tiles * m_tiles)) * p.kb_per_split;
         const int nkb_seg = min(p.num_kb, kb0 + p.kb_per_split) - kb0;
         const int nkb = FOUR ? nkb_seg : nkb_seg * p.segments;
+        // L2 prefetch of the streamed operand (K-major A: first touched here, from HBM) `pf` K blocks ahead, running into the
+        // worker's next tile: with the 64-72 KB stages of the compensated product only three stages fit, and the HBM latency of
+        // each TMA load would otherwise sit on the critical path of a three-deep ring
+        const int pf = (!p.a_mn && !p.atomic_out) ? p.prefetch : 0;
+        const int tn = t + num_workers;
+        const int m0n = tn < total ? ((tn / n_tiles) % m_tiles) * TILE_M + (int)rank * GEMM_BM : -1;
+        const bool next_new_rows = m0n >= 0 && m0n != m0;       // (the other column tiles of the same rows hit L2 anyway)
+        if (pf && t == worker)
+          for (int i = 0; i < min(pf, nkb_seg); ++i) ptx::tma_prefetch_2d(&tmA, (kb0 + i) * Cfg::BK, m0);
         for (int i = 0; i < nkb; ++i, ++it) {
+          if (pf) {
+            const int ib = (FOUR ? i : i % nkb_seg) + pf;
+            if (ib < nkb_seg) ptx::tma_prefetch_2d(&tmA, (kb0 + ib) * Cfg::BK, m0);
+            else if (next_new_rows && ib - nkb_seg < min(pf, nkb_seg)) ptx::tma_prefetch_2d(&tmA, (ib - nkb_seg) * Cfg::BK, m0n);
+          }
           const int s = it % Cfg::STAGES;
           ptx::mbar_wait(empty_bar + s, ((it / Cfg::STAGES) & 1) ^ 1);
           // derive_lo: the fp32 A tile goes to a CTA-local barrier (the converter warps of THIS CTA consume it) and no A_lo is loaded
-          if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar + s, derive ? (TWO ? 2 : 1) * 2 * Cfg::B_BYTES : Cfg::TX_BYTES);
-          if (derive) ptx::mbar_arrive_expect_tx(afull_bar + s, Cfg::A_BYTES);
+          // mixed: both raw tiles go to the CTA-local barrier and the MMA issuer waits for the converters only
+          if (rank == 0 && !mixed) ptx::mbar_arrive_expect_tx(full_bar + s, derive ? (TWO ? 2 : 1) * 2 * Cfg::B_BYTES : Cfg::TX_BYTES);
+          if (derive) ptx::mbar_arrive_expect_tx(afull_bar + s, mixed ? Cfg::A_BYTES + Cfg::B_BYTES : Cfg::A_BYTES);
           const uint32_t fb = TWO ? ptx::mapa(ptx::smem_u32(full_bar + s), 0u) : 0u;     // the leader's barrier
           auto load = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
             if (TWO) ptx::tma_load_2d_2cta(dst, m, fb, c0, c1); else ptx::tma_load_2d(dst, m, full_bar + s, c0, c1);
@@ -254,7 +274,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             } else if (!p.a_mn) load(ad, ma, kc, m0);
             else
               for (int j = 0; j < GEMM_BM / 32; ++j) load(ad + j * Cfg::MN_BLOCK_BYTES, ma, m0 + 32 * j, kc);
-            if (!p.b_mn) load(bd, mb, kc, n0);
+            if (mixed) {
+              if (h == 0) ptx::tma_load_2d(bd, &tmB, afull_bar + s, kc, n0);
+            } else if (!p.b_mn) load(bd, mb, kc, n0);
             else
               for (int j = 0; j < Cfg::BN_CTA / 32; ++j) {
                 // blocks of the first MMA (N1) first, then those of the second (N2); each CTA of a pair stages its half of both
@@ -273,6 +295,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0 && rank == 0) {
       const uint32_t idesc = ptx::make_idesc_tf32(Cfg::N1, p.a_mn != 0, p.b_mn != 0, TILE_M);
       const uint32_t idesc2 = ptx::make_idesc_tf32(Cfg::N2 > 0 ? Cfg::N2 : 16, p.a_mn != 0, p.b_mn != 0, TILE_M);
+      const uint32_t idesc16 = ptx::make_idesc_bf16(Cfg::N1, TILE_M);
       auto mma_i = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
         if (TWO) ptx::mma_tf32_ss_2cta(d, a, b, id, acc); else ptx::mma_tf32_ss(d, a, b, id, acc);
       };
@@ -296,7 +319,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t d_tmem = tmem_base + buf * 256u;
         for (int i = 0; i < nkb; ++i, ++it) {
           const int s = it % Cfg::STAGES;
-          ptx::mbar_wait(full_bar + s, (it / Cfg::STAGES) & 1);
+          if (!mixed) ptx::mbar_wait(full_bar + s, (it / Cfg::STAGES) & 1);
           if (derive) ptx::mbar_wait(conv_bar + s, (it / Cfg::STAGES) & 1);
           ptx::tc_fence_after();
           const uint32_t a_base = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES);
@@ -311,11 +334,24 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const uint64_t bdw = ptx::make_smem_desc(b_base + b2_off + k * b_kstep, b_lbo, b_sbo, b_lay);
               mma_i(d_tmem + Cfg::N1, ad, bdw, idesc2, (i | k) != 0 ? 1u : 0u);
             }
-            if (FOUR) {
+            if (FOUR && !mixed) {
               const uint64_t ad2 = ptx::make_smem_desc(a_base + Cfg::A_BYTES + k * a_kstep, a_lbo, a_sbo, a_lay);
               const uint64_t bd2 = ptx::make_smem_desc(b_base + Cfg::B_BYTES + k * b_kstep, b_lbo, b_sbo, b_lay);
               mma(d_tmem, ad2, bd, 1u);          // A_lo * B_hi
               mma(d_tmem, ad, bd2, 1u);          // A_hi * B_lo
+            }
+          }
+          if (mixed && !(p.debug & 4)) {
+            // correction passes on the bf16 tiles: K-major rows of 32 bf16 = 64 bytes (64B swizzle, 8-row groups 512 B apart),
+            // K = 16 (32 bytes) per instruction
+#pragma unroll
+            for (int k = 0; k < Cfg::BK / 16; ++k) {
+              const uint64_t ah = ptx::make_smem_desc(a_base + Cfg::A_BYTES + k * 32u, 16u, 512u, ptx::kLayoutSw64);
+              const uint64_t al = ptx::make_smem_desc(a_base + Cfg::A_BYTES + Cfg::A_BYTES / 2 + k * 32u, 16u, 512u, ptx::kLayoutSw64);
+              const uint64_t bh = ptx::make_smem_desc(b_base + Cfg::B_BYTES + k * 32u, 16u, 512u, ptx::kLayoutSw64);
+              const uint64_t bl = ptx::make_smem_desc(b_base + Cfg::B_BYTES + Cfg::B_BYTES / 2 + k * 32u, 16u, 512u, ptx::kLayoutSw64);
+              if (TWO) { ptx::mma_f16_ss_2cta(d_tmem, al, bh, idesc16, 1u); ptx::mma_f16_ss_2cta(d_tmem, ah, bl, idesc16, 1u); }
+              else { ptx::mma_f16_ss(d_tmem, al, bh, idesc16, 1u); ptx::mma_f16_ss(d_tmem, ah, bl, idesc16, 1u); }
             }
           }
           commit(empty_bar + s);          // frees the smem slot (of both CTAs) once these MMAs have read it
@@ -340,6 +376,42 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::mbar_wait(afull_bar + s, (it / Cfg::STAGES) & 1);
           const float4* hi = reinterpret_cast<const float4*>(smem + s * Cfg::STAGE_BYTES);
           float4* lo = reinterpret_cast<float4*>(smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES);
+          if (mixed) {
+            // bf16 tiles for the correction passes: hi16 = bf16(x), lo16 = bf16(x - trunc_tf32(x)), of the A tile and of this CTA's
+            // B tile.  Source: K-major fp32 rows of 128 B, 16-byte chunk c of row r stored at chunk c ^ (r & 7); destination: rows
+            // of 64 B, chunk j at j ^ ((r >> 1) & 3).
+            // Thread ct owns chunks ct + NT*i (NT = converter threads, a multiple of 64 = 8 rows): the row's swizzle phases are the
+            // same for all of them, so source and destination offsets are per-thread constants plus a fixed stride.
+            constexpr int NT = 32 * Cfg::CONV_WARPS;
+            const int r0 = ct >> 3, c = (ct & 7) ^ (r0 & 7);                 // logical 16-byte chunk of the row: k = 4c .. 4c + 3
+            const int off0 = r0 * 64 + (((c >> 1) ^ ((r0 >> 1) & 3)) << 4) + ((c & 1) << 3);
+            auto convert = [&](const uint8_t* src, uint8_t* hi16, int chunks) {
+              uint8_t* lo16 = hi16 + chunks * 8;                             // the lo tile follows the hi tile (half the bytes each)
+              constexpr int U = 4;
+              for (int e0 = ct; e0 < chunks; e0 += U * NT) {
+                float4 v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) v[u] = (e0 + u * NT < chunks) ? reinterpret_cast<const float4*>(src)[e0 + u * NT] : f4_zero();
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                  if (e0 + u * NT >= chunks) break;
+                  const int off = off0 + ((e0 - ct) / NT + u) * (NT / 8) * 64;
+                  const float4 x = v[u];
+                  const float lx = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u), ly = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                  const float lz = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u), lw = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                  __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
+                  __nv_bfloat162 l0 = __floats2bfloat162_rn(lx, ly), l1 = __floats2bfloat162_rn(lz, lw);
+                  *reinterpret_cast<uint2*>(hi16 + off) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+                  *reinterpret_cast<uint2*>(lo16 + off) = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+                }
+              }
+            };
+            uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+            if (!(p.debug & 2)) {      // (timing experiments: skip the conversion)
+              convert(st, st + Cfg::A_BYTES, Cfg::A_BYTES / 16);
+              convert(st + 2 * Cfg::A_BYTES, st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, Cfg::B_BYTES / 16);
+            }
+          } else
 #pragma unroll 4
           for (int e = ct; e < Cfg::A_BYTES / 16; e += 32 * Cfg::CONV_WARPS) {
             const float4 v = hi[e];
@@ -590,13 +662,13 @@ __global__ void __launch_bounds__(128) gemm_simt_kernel(const float* __restrict_
   if (grow < p.M) {
     for (int k = 0; k < p.K; ++k) {
       const size_t ai = p.a_mn ? (size_t)k * lda + grow : (size_t)grow * lda + k;
-      const float a = A[ai] + ((p.segments > 1 && A_lo) ? A_lo[ai] : 0.f);
+      const float a = A[ai] + ((p.segments > 1 && A_lo) ? A_lo[ai] : 0.f);   // (compensate = 1: A and B are the full values already)
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int col = n0 + j;
         if (col < p.N) {
           const size_t bi = p.b_mn ? (size_t)k * ldb + col : (size_t)col * ldb + k;
-          acc[j] = fmaf(a, B[bi] + (p.segments > 1 ? B_lo[bi] : 0.f), acc[j]);
+          acc[j] = fmaf(a, B[bi] + ((p.segments > 1 && B_lo) ? B_lo[bi] : 0.f), acc[j]);
         }
       }
     }
@@ -709,7 +781,8 @@ static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, i
       rc = p.a_mn ? make_tmap(&tmA2, j.A_lo, p.M, p.K, j.lda, 32, true, Cfg::BK) : make_tmap(&tmA2, j.A_lo, p.K, p.M, j.lda, GEMM_BM, false, Cfg::BK);
       if (rc) return rc;
     }
-    rc = p.b_mn ? make_tmap(&tmB2, j.B_lo, p.N, p.K, j.ldb, 32, true, Cfg::BK) : make_tmap(&tmB2, j.B_lo, p.K, p.N, j.ldb, Cfg::BN_CTA, false, Cfg::BK);
+    if (p.derive_lo != 2)            // (mixed: no second B tensor at all)
+      rc = p.b_mn ? make_tmap(&tmB2, j.B_lo, p.N, p.K, j.ldb, 32, true, Cfg::BK) : make_tmap(&tmB2, j.B_lo, p.K, p.N, j.ldb, Cfg::BN_CTA, false, Cfg::BK);
     if (rc) return rc;
   }
   auto kernel = gemm_tf32_kernel<BN, FOUR, KIND, TWO>;
@@ -780,8 +853,11 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   MOLCLR_REQUIRE(p.N % 4 == 0, "gemm: N=%d must be a multiple of 4", p.N);
   const bool atomic = job.split_k > 1 || p.transpose_out;
   MOLCLR_REQUIRE(job.A_lo == nullptr || job.B_lo != nullptr, "gemm: A_lo needs B_lo");
-  p.segments = job.B_lo ? 3 : 1;
-  p.derive_lo = (job.B_lo && !job.A_lo) ? 1 : 0;          // compensated product with A_lo derived on chip from an unrounded A
+  MOLCLR_REQUIRE(!job.compensate || (!job.A_lo && !job.B_lo && !p.a_mn && !p.b_mn), "gemm: compensate = 1 takes unrounded K-major A and B and no lo tensors");
+  p.segments = (job.B_lo || job.compensate) ? 3 : 1;
+  // compensated product with the low halves derived on chip: 1 = A_lo (fp32 tile) from an unrounded A, B_hi/B_lo from the caller;
+  // 2 = "mixed": both operands unrounded, bf16 correction tiles of both formed on chip
+  p.derive_lo = job.compensate ? 2 : (job.B_lo && !job.A_lo) ? 1 : 0;
   MOLCLR_REQUIRE((!p.bits_in && !p.bits_out) || (p.epi == EPI_GENERIC && !atomic && !p.mask && !p.addend),
                  "gemm: ReLU bit masks need the plain epilogue (no float mask / addend / split-K)");
   MOLCLR_REQUIRE(!p.bits_in || p.segments == 1, "gemm: mask_bits is not supported by the compensated product");
@@ -805,6 +881,8 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;          // no empty split
   p.atomic_out = atomic ? 1 : 0;
   p.debug = gemm_debug_flags();
+  static const int prefetch_kb = [] { const char* e = getenv("MOLCLR_GEMM_PREFETCH"); return e ? atoi(e) : 0; }();
+  p.prefetch = prefetch_kb;
   // split-K weight gradients stay on single CTAs: their 300/600-wide outputs pad badly to 256-row pair tiles (MMA-bound)
   const bool wide = atomic && job.wide && gemm_pair() && !gemm_impl_simt();
   if (wide) MOLCLR_REQUIRE(p.a_mn && p.b_mn, "gemm: wide split-K tiles need both operands MN-major");
@@ -903,6 +981,7 @@ extern "C" int molclr_gemm_tf32(const molclr_gemm_args* args, cudaStream_t strea
   memset(&j, 0, sizeof(j));
   j.A = a.A; j.lda = a.lda; j.B = a.B; j.ldb = a.ldb; j.split_k = a.split_k;
   j.A_lo = a.A_lo; j.B_lo = a.B_lo;
+  j.compensate = a.compensate;
   GemmParams& p = j.p;
   p.M = (int)a.M; p.N = (int)a.N; p.K = (int)a.K; p.a_mn = a.a_mn; p.b_mn = a.b_mn;
   p.out = a.out; p.ldo = a.ldo; p.transpose_out = a.transpose_out; p.out2 = a.out2; p.ldo2 = a.ldo2;

@@ -12,7 +12,8 @@ struct GemmParams {
   int a_mn, b_mn;
   int num_kb, kb_per_split;
   int n_tiles, m_tiles, splits;   // tile grid walked by the persistent CTAs (filled by the launcher)
-  int derive_lo;               // compensated product: A holds unrounded fp32 and the kernel derives A_lo = A - trunc_tf32(A) on chip
+  int derive_lo;               // compensated product with low halves derived on chip: 1 = A_lo from an unrounded A; 2 = "mixed": A and B
+                               // both unrounded, bf16 correction tiles of both formed in shared memory (see gemm.cu)
   int segments;                // 1: plain TF32.  3: error-compensated  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (~fp32 accuracy)
   float* out; long long ldo; int transpose_out;
   float* out2; long long ldo2;
@@ -25,6 +26,7 @@ struct GemmParams {
   float* colstat; int colstat_mode;
   int stat_groups;             // number of 32-row groups the colstat buffer holds (filled by the launcher)
   int atomic_out;
+  int prefetch;                // K blocks of the (K-major) A operand to prefetch into L2 ahead of the TMA loads (0 = off)
   int debug;                   // MOLCLR_GEMM_DEBUG bit 0: skip the generic epilogue (timing experiments only)
   float alpha;                 // out = alpha * acc (+ bias + addend ...)
   // ---- NT-Xent epilogues (nt_xent.py:47-65); logits l = acc * inv_tau
@@ -43,6 +45,7 @@ struct GemmParams {
 struct GemmJob {
   const float* A; long long lda; const float* B; long long ldb;
   const float* A_lo; const float* B_lo;   // both non-null selects the 3-segment compensated product (same layout/ld as A, B)
+  int compensate;              // 1: A and B are unrounded K-major fp32; ~fp32-accurate product, everything derived on chip ("mixed")
   int split_k;
   int wide;                    // split-K only: 256 x 320 tiles on CTA pairs (both operands MN-major)
   int bn_hint;                 // 0, or a column-tile width to use instead of the default (more tiles for narrow outputs)

@@ -58,6 +58,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// L2 prefetch of one box of a tiled tensor map (no shared memory, no completion mechanism)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1) : "memory");
+}
+
 // 1D bulk copy global -> shared (bytes % 16 == 0, both addresses 16-byte aligned), completion on an mbarrier.
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -135,6 +141,28 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int n, bool a_mn_major, b
          | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16)
          | ((uint32_t)(n >> 3) << 17)            // N / 8
          | ((uint32_t)(m >> 4) << 24);           // M / 16
+}
+
+// kind::f16 with BF16 inputs, FP32 accumulate (K = 16 per instruction): the correction passes of the mixed compensated product
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int n, int m = 128) {
+  return (1u << 4)                               // D format: F32
+         | (1u << 7) | (1u << 10)                // A, B format: BF16
+         | ((uint32_t)(n >> 3) << 17)            // N / 8
+         | ((uint32_t)(m >> 4) << 24);           // M / 16   (both operands K-major)
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 // ------------------------------------------------------------------ CTA pairs (cluster of 2, tcgen05 cta_group::2)

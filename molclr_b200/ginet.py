@@ -56,6 +56,17 @@ class _RoundedWeights:
         self._cache[key] = (p._version, r, p.data_ptr())
         return r
 
+    def raw(self, p):
+        """Unrounded copy with 128-byte aligned rows: the B operand of the compensated GEMM that derives every low half on chip."""
+        key = ("raw", id(p))
+        hit = self._cache.get(key)
+        if hit is not None and hit[0] == p._version and hit[2] == p.data_ptr():
+            return hit[1]
+        r = ops.padded(p.shape[0], p.shape[1], p.device)
+        r.copy_(p.detach())
+        self._cache[key] = (p._version, r, p.data_ptr())
+        return r
+
 
 PRECISIONS = ("tf32x3", "tf32")
 
@@ -197,19 +208,22 @@ def _encoder_forward(m, plan, comp, training, pool_mode):
         # a and u stay UNROUNDED fp32 (one tensor each): the compensated GEMMs derive their low halves on chip
         a = ops.gine_aggregate_fwd(plan, src, g.edge_embedding1.weight.detach(), g.edge_embedding2.weight.detach(),
                                    bn_coef=coef_prev, relu=True, round_out=False, drop=dp)
-        (W1, W1_lo), (W2, W2_lo) = rw.get(g.mlp[0].weight), rw.get(g.mlp[2].weight)
+        # W1 / W2: tf32-rounded copies (single-pass forward, and the backward's dX GEMMs); tf32x3: the raw weights, the
+        # compensated GEMM derives the bf16 correction tiles of both operands on chip
+        (W1, _), (W2, _) = rw.get(g.mlp[0].weight), rw.get(g.mlp[2].weight)
+        B1, B2 = (rw.raw(g.mlp[0].weight), rw.raw(g.mlp[2].weight)) if comp else (W1, W2)
         u = ops.padded(N, H, dev)
         ubits = ops.relu_bits_buffer(N, H, dev)       # [u > 0] as bits: the backward GEMM's mask (8 MB instead of 246)
-        ops.gemm(a, W1, N, H, D, B_lo=_lo(W1_lo, comp), out=u, bias=g.mlp[0].bias.detach(), relu=True, relu_bits=ubits)
+        ops.gemm(a, B1, N, H, D, compensate=comp, out=u, bias=g.mlp[0].bias.detach(), relu=True, relu_bits=ubits)
         z = torch.empty(N, D, device=dev)
         if training:
             stats = torch.empty(T, 2, D, device=dev)
-            ops.gemm(u, W2, N, D, H, B_lo=_lo(W2_lo, comp), out=z, bias=g.mlp[2].bias.detach(), colstat=stats, colstat_mode=2)
+            ops.gemm(u, B2, N, D, H, compensate=comp, out=z, bias=g.mlp[2].bias.detach(), colstat=stats, colstat_mode=2)
             momentum = 0.1 if bn.momentum is None else bn.momentum
             coef = ops.bn_fwd_finalize(stats, T, N, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
                                        bn.num_batches_tracked, momentum, bn.eps)
         else:
-            ops.gemm(u, W2, N, D, H, B_lo=_lo(W2_lo, comp), out=z, bias=g.mlp[2].bias.detach())
+            ops.gemm(u, B2, N, D, H, compensate=comp, out=z, bias=g.mlp[2].bias.detach())
             coef = ops.bn_eval_coef(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
         layers.append((a, u, z, coef, W1, W2, ubits))
         src, coef_prev = z, coef

@@ -30,7 +30,7 @@ def max_blocks():
 # ------------------------------------------------------------------------------------------- GEMM
 def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=None, out2=None, out_lo=None, bias=None,
          addend=None, mask=None, relu=False, round_out=False, colstat=None, colstat_mode=0, transpose_out=False,
-         split_k=1, lda=None, ldb=None, relu_bits=None, mask_bits=None):
+         split_k=1, lda=None, ldb=None, relu_bits=None, mask_bits=None, compensate=False):
     """C[M,N] = sum_k A(m,k) B(n,k) on tcgen05 (TF32 in, FP32 accumulate) with the fused epilogue of
     ``molclr_gemm_tf32`` (see include/molclr_b200.h)."""
     lib = _lib.load()
@@ -51,6 +51,7 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=Non
     bits = relu_bits if relu_bits is not None else mask_bits
     a.relu_bits, a.mask_bits = ptr(relu_bits, torch.int32), ptr(mask_bits, torch.int32)
     a.ld_bits = bits.stride(0) if bits is not None else 0
+    a.compensate = int(compensate)      # A, B unrounded fp32 (K-major): ~fp32-accurate product, low halves derived on chip
     check(lib.molclr_gemm_tf32(C.byref(a), stream()), "gemm_tf32")
     return out
 

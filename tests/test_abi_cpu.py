@@ -40,7 +40,7 @@ def test_gemm_args_struct_matches_header_layout():
     # 8-byte aligned fields in header order; guards against silent drift between header and ctypes mirror
     assert GemmArgs.A.offset == 0 and GemmArgs.lda.offset == 8 and GemmArgs.a_mn.offset == 16
     assert GemmArgs.B.offset == 24 and GemmArgs.A_lo.offset == 48 and GemmArgs.M.offset == 64 and GemmArgs.out.offset == 88
-    assert GemmArgs.out_lo.offset == 128 and ctypes.sizeof(GemmArgs) == 232 and GemmArgs.relu_bits.offset == 208
+    assert GemmArgs.out_lo.offset == 128 and ctypes.sizeof(GemmArgs) == 240 and GemmArgs.relu_bits.offset == 208 and GemmArgs.compensate.offset == 232
 
 
 def test_product_has_no_cpu_fallback():

@@ -285,6 +285,29 @@ def test_gemm_compensated_with_low_half_derived_on_chip(M, N, K, b_mn):
     assert e3 < 1e-5 and e1 > 20 * e3, (e3, e1)
 
 
+@pytest.mark.parametrize("M,N,K", [(1000, 600, 300), (5000, 300, 600), (130, 160, 40), (4097, 512, 300), (50, 256, 512)])
+def test_gemm_compensated_on_chip_bf16_corrections(M, N, K):
+    """compensate=True: A and B are the UNROUNDED fp32 tensors.  Pass 1 runs in TF32 on the raw tiles (the tensor core
+    truncates), the corrections (A - trunc A) * B and A * (B - trunc B) as kind::f16 MMAs on bf16 tiles the converter warps form
+    in shared memory.  The corrections are 2^-10 of the product and their bf16 rounding 2^-9 of that: ~1e-6 relative."""
+    g = torch.Generator().manual_seed(M + N + 3)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    B = torch.randn(N, K, generator=g).to(DEV)
+    A_pad, B_pad = ops.padded(M, K, DEV), ops.padded(N, K, DEV)
+    A_pad.copy_(A); B_pad.copy_(B)
+    bias = torch.randn(N, generator=g).to(DEV)
+    out = torch.empty(M, N, device=DEV)
+    bits = ops.relu_bits_buffer(M, N, DEV)
+    ops.gemm(A_pad, B_pad, M, N, K, compensate=True, out=out, bias=bias, relu=True, relu_bits=bits)
+    ref = torch.relu(_gemm_ref(A, B, False, False) + bias.double().cpu())
+    single = torch.empty(M, N, device=DEV)
+    ops.gemm(ops.split_tf32(A)[0], ops.split_tf32(B)[0], M, N, K, out=single, bias=bias, relu=True)
+    e3, e1 = rel_err(out, ref), rel_err(single, ref)
+    assert e3 < 5e-6 and e1 > 20 * e3, (e3, e1)
+    with pytest.raises(RuntimeError):       # K-major operands only, no lo tensors
+        ops.gemm(A_pad, B_pad, M, N, K, compensate=True, b_mn=True, out=out)
+
+
 @pytest.mark.parametrize("R,O,I", [(5000, 300, 600), (5000, 600, 300), (4096, 256, 512), (700, 512, 300)])
 def test_gemm_weight_gradient_split_k(R, O, I):
     g = torch.Generator().manual_seed(R + O)

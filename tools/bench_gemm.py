@@ -24,7 +24,7 @@ def timeit(fn, iters=int(os.environ.get('ITERS', 10))):
 ONLY = os.environ.get("CASE")
 
 
-def case(name, M, N, K, comp=False, b_mn=False, relu=False, pad_k=0, dw=False, masked=False, stat=0, derive=False):
+def case(name, M, N, K, comp=False, b_mn=False, relu=False, pad_k=0, dw=False, masked=False, stat=0, derive=False, mixed=False):
     if ONLY and not name.startswith(ONLY):
         return
     g = torch.Generator().manual_seed(0)
@@ -53,13 +53,15 @@ def case(name, M, N, K, comp=False, b_mn=False, relu=False, pad_k=0, dw=False, m
         B = B[:, :K]
     out = torch.empty(M, N, device=dev)
     lo = torch.empty(M, N, device=dev) if comp else None
-    A_lo = torch.randn(M, K + pad_k, generator=g).to(dev)[:, :K] if (comp and not derive) else None
+    A_lo = torch.randn(M, K + pad_k, generator=g).to(dev)[:, :K] if (comp and not derive and not mixed) else None
     if derive:
         lo = None
-    B_lo = (torch.randn_like(B) if comp else None)
+    B_lo = (torch.randn_like(B) if (comp and not mixed) else None)
+    if mixed:
+        lo = None
     bias = torch.randn(N, device=dev)
     fn = lambda: ops.gemm(A, B, M, N, K, b_mn=b_mn, A_lo=A_lo, B_lo=B_lo, out=out, out_lo=lo, bias=bias, relu=relu, round_out=True,
-                          lda=K + pad_k, ldb=(N if b_mn else K + pad_k))
+                          lda=K + pad_k, ldb=(N if b_mn else K + pad_k), compensate=mixed)
     us = timeit(fn)
     flops = 2.0 * M * N * K * (3 if comp else 1)
     print(f"{name:34s} {us:9.1f} us  {flops / us / 1e6:8.1f} TFLOP/s (tensor work)  out {M * N * 4 * (2 if comp else 1) / us / 1e3:7.1f} GB/s")
@@ -74,6 +76,8 @@ if os.environ.get("QUICK"):
 case("fwd1 x1   [M,300]x[600,300]", M, 600, 300)
 case("fwd1 x3   [M,300]x[600,300]", M, 600, 300, comp=True)
 case("fwd1 x3 derive, aligned", M, 600, 300, comp=True, derive=True, pad_k=20)
+case("fwd1 mixed (on-chip bf16 corr.)", M, 600, 300, comp=True, mixed=True, pad_k=20)
+case("fwd2 mixed (on-chip bf16 corr.)", M, 300, 600, comp=True, mixed=True, pad_k=8)
 case("fwd1 x3 explicit lo, aligned", M, 600, 300, comp=True, pad_k=20)
 case("fwd2 x3 derive, aligned", M, 300, 600, comp=True, derive=True, pad_k=8)
 case("fwd2 x3 explicit lo, aligned", M, 300, 600, comp=True, pad_k=8)

@@ -1,0 +1,3 @@
+#!/bin/bash
+# timing experiments on the mixed compensated GEMM: debug bit 1 = no epilogue, 2 = no conversion, 4 = no correction MMAs
+for D in 0 1 2 4 6 7; do echo "== MOLCLR_GEMM_DEBUG=$D"; MOLCLR_GEMM_DEBUG=$D CASE=fwd timeout 120 python tools/bench_gemm.py 2>&1 | grep -E "mixed|fwd1 x1   "; done
