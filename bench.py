@@ -225,14 +225,27 @@ def run_ours(args):
                 t.record_stream(main)
         return dev_pair, ev
 
+    loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+
     def e2e_loop(n):
+        """Every step: H2D of its inputs (side stream, overlapping the previous step) and a D2H read of its loss into pinned
+        memory; the host consumes the loss of step k while step k+1 runs (a logger does not need to stall the GPU), the last one
+        after the final synchronize."""
         nxt = prefetch(host[0])
+        seen = []
         for i in range(n):
             (bi, bj), ev = nxt
             torch.cuda.current_stream().wait_event(ev)
             nxt = prefetch(host[(i + 1) % NB])
-            float(step(bi, bj).item())
+            loss_host[i % 2].copy_(step(bi, bj).detach(), non_blocking=True)
+            loss_ready[i % 2].record()
+            if i > 0:
+                loss_ready[(i - 1) % 2].synchronize()
+                seen.append(float(loss_host[(i - 1) % 2]))
         torch.cuda.synchronize()
+        seen.append(float(loss_host[(n - 1) % 2]))
+        assert len(seen) == n and all(v == v for v in seen)
 
     e2e_loop(2)
     barrier()

@@ -65,6 +65,22 @@ int molclr_plan_build(const int64_t* x, const int64_t* edge_index, const int64_t
                       int32_t* col, uint8_t* eattr, int32_t* rowptr_t, int32_t* col_t, float* cnt, uint32_t* nbr, int32_t* gptr,
                       int32_t* gperm, void* workspace, size_t workspace_bytes, int32_t* status, cudaStream_t stream);
 
+/* ---- on-device batch construction + augmentation: dataset/dataset.py:112-145 and the DataLoader collate
+ * (dataset.py:179-184) from a packed molecule store in HBM ("molclr-packed v1": atom_ptr[M+1], atoms = type | chirality << 8;
+ * bond_ptr[M+1], bonds = begin | end << 12 | type << 24 | dir << 27).  For batch slot s = molecule mol_ids[s], views i and j
+ * independently: max(1, floor(N/4)) atoms -> [118, 0], floor(M/4) bonds deleted (both directions), survivors in order, each as
+ * two consecutive directed edges.  node_off / edge_off / bond_off [B]: exclusive prefix sums of atoms, surviving directed
+ * edges 2 (M - floor(M/4)) and bonds M over the batch (host-computed from the pointer arrays).  Outputs are the int64
+ * tensors of a PyG Batch (edge_index row-major [2][E_total]).  The random k-subsets are the k smallest of counter-based
+ * keys of (seed, view, slot, item); node_masked [2][N_total] / bond_deleted [2][M_total] (optional) export the selection so
+ * that a CPU oracle can replay it.  status[0] bit 0: a molecule id out of range. */
+int molclr_augment_views(const int32_t* atom_ptr, const int32_t* atoms, const int32_t* bond_ptr, const int32_t* bonds,
+                         int64_t n_mols, const int64_t* mol_ids, int64_t B, const int32_t* node_off, const int32_t* edge_off,
+                         const int32_t* bond_off, uint64_t seed, int64_t N_total, int64_t E_total, int64_t M_total, int64_t* x_i,
+                         int64_t* edge_index_i, int64_t* edge_attr_i, int64_t* batch_i, int64_t* x_j, int64_t* edge_index_j,
+                         int64_t* edge_attr_j, int64_t* batch_j, uint8_t* node_masked, uint8_t* bond_deleted, int32_t* status,
+                         cudaStream_t stream);
+
 /* ---- node embedding: ginet_molclr.py:103 / gcn_molclr.py:144 ------------------------------------- */
 int molclr_embed_nodes_fwd(const int32_t* xpacked, const float* E1, const float* E2, int64_t N, int D, float* out,
                            cudaStream_t stream);

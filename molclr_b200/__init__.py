@@ -10,3 +10,4 @@ from . import ginet_finetune  # noqa: F401  (ginet_finetune.GINet: models/ginet_
 from .nt_xent import NTXentLoss  # noqa: F401
 from .graph import GraphPlan, get_plan  # noqa: F401
 from .functional import normalize, pretrain_loss  # noqa: F401
+from .dataset import PackedMolecules, augment_pair  # noqa: F401

@@ -43,6 +43,8 @@ SIGNATURES = {
     "molclr_device_info": (i32, [C.POINTER(i32), C.POINTER(i32)]),
     "molclr_plan_workspace_bytes": (sz, [i64, i64, i64]),
     "molclr_plan_build": (i32, [vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp]),
+    "molclr_augment_views": (i32, [vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, C.c_uint64, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                   vp, vp]),
     "molclr_embed_nodes_fwd": (i32, [vp, vp, vp, i64, i32, vp, vp]),
     "molclr_embed_nodes_bwd_workspace_bytes": (sz, [i64]),
     "molclr_embed_nodes_bwd": (i32, [vp, vp, i64, i64, i32, vp, vp, vp]),

@@ -382,7 +382,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // of 64 B, chunk j at j ^ ((r >> 1) & 3).
             // Thread ct owns chunks ct + NT*i (NT = converter threads, a multiple of 64 = 8 rows): the row's swizzle phases are the
             // same for all of them, so source and destination offsets are per-thread constants plus a fixed stride.
-            constexpr int NT = 32 * Cfg::CONV_WARPS;
+            constexpr int NT = Cfg::CONV_WARPS > 0 ? 32 * Cfg::CONV_WARPS : 32;   // (no converter warps: dead code in that instance)
             const int r0 = ct >> 3, c = (ct & 7) ^ (r0 & 7);                 // logical 16-byte chunk of the row: k = 4c .. 4c + 3
             const int off0 = r0 * 64 + (((c >> 1) ^ ((r0 >> 1) & 3)) << 4) + ((c & 1) << 3);
             auto convert = [&](const uint8_t* src, uint8_t* hi16, int chunks) {

@@ -263,7 +263,7 @@ static int env_int(const char* name, int dflt) { const char* e = getenv(name); r
 // shape, tools/sweep_aggregate.sh: 3 x 3 and 4 x 2 are best, deeper rings are SLOWER -- more reads in flight delay the writes)
 static const int g_tile_stages = env_int("MOLCLR_AGG_STAGES", 3), g_tile_rows_per_slot = env_int("MOLCLR_AGG_ROWS", 3);
 static const int g_tile_store_cs = env_int("MOLCLR_AGG_STORE_CS", 0), g_tile_blocked = env_int("MOLCLR_AGG_BLOCKED", 0);
-constexpr uint32_t kNbrEmpty = 0xFFFFFFFFu, kNbrLong = 0xFFFFFFFEu;
+constexpr uint32_t kNbrLong = 0xFFFFFFFEu;      // entries >= kNbrLong end a row's list: 0xFFFFFFFF = empty, kNbrLong in [0] = use the CSR
 
 // A/B switch for measurements: MOLCLR_AGG_TILE=0 forces the warp-per-row kernel
 static const bool g_aggregate_tile = [] { const char* e = getenv("MOLCLR_AGG_TILE"); return !(e && e[0] == '0'); }();
