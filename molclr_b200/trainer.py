@@ -66,6 +66,51 @@ class SyntheticMoleculeDatasetWrapper:
                 _Loader(self.batch_size, max(n_valid // self.batch_size, 1), seed=900_000_007, reshuffle=False))
 
 
+class _DeviceLoader:
+    """Iterable of (xis, xjs) built ON THE GPU from a packed store: ids = a fresh permutation of the subset every epoch
+    (SubsetRandomSampler, dataset.py:166-177), views from ``augment_pair`` (one kernel per batch, no host batch at all)."""
+
+    def __init__(self, store, ids, batch_size, seed, reshuffle):
+        self.store, self.ids, self.batch_size, self.seed, self.reshuffle, self.epoch = store, ids, batch_size, seed, reshuffle, 0
+
+    def __len__(self):
+        return len(self.ids) // self.batch_size                 # drop_last=True (dataset.py:179-184)
+
+    def __iter__(self):
+        import numpy as np
+        from .dataset import augment_pair
+        e = self.epoch if self.reshuffle else 0
+        self.epoch += 1
+        order = np.random.default_rng(self.seed + e).permutation(self.ids) if self.reshuffle else self.ids
+        for k in range(len(self)):
+            yield augment_pair(self.store, order[k * self.batch_size:(k + 1) * self.batch_size], seed=(self.seed + e) * 1_000_003 + k)
+
+
+class PackedMoleculeDatasetWrapper:
+    """``MoleculeDatasetWrapper`` (dataset.py:153-184) over a packed molecule store resident in HBM.  ``data_path`` is a
+    ``molclr-packed v1`` .npz file (``PackedMolecules.save``) or ``"synthetic:<count>"``; the train / validation split by
+    ``valid_size`` over a seeded shuffle of the indices follows dataset.py:166-175."""
+
+    def __init__(self, batch_size, num_workers, valid_size, data_path, device="cuda:0", seed=0):
+        import numpy as np
+        from .dataset import PackedMolecules
+        from .synth import random_molecule
+        self.batch_size, self.num_workers, self.valid_size = batch_size, num_workers, valid_size
+        if str(data_path).startswith("synthetic:"):
+            rng = np.random.default_rng(seed)
+            store = PackedMolecules.from_graphs(random_molecule(rng) for _ in range(int(str(data_path).split(":", 1)[1])))
+        else:
+            store = PackedMolecules.load(data_path)
+        self.store = store.to(device)
+        idx = np.random.default_rng(seed + 1).permutation(len(store))
+        split = int(math.floor(valid_size * len(store)))
+        self.valid_idx, self.train_idx = idx[:split], idx[split:]
+
+    def get_data_loaders(self):
+        return (_DeviceLoader(self.store, self.train_idx, self.batch_size, seed=1, reshuffle=True),
+                _DeviceLoader(self.store, self.valid_idx, self.batch_size, seed=900_000_007, reshuffle=False))
+
+
 class MolCLR:
     def __init__(self, dataset, config, log_root="ckpt"):
         self.config, self.dataset = config, dataset

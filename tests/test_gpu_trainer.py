@@ -33,3 +33,21 @@ def test_trainer_runs_checkpoints_and_resumes(tmp_path, monkeypatch):
     for k, v in model.state_dict().items():
         if k in before:
             assert torch.equal(v, before[k]), k
+
+
+def test_trainer_on_the_device_resident_packed_store(tmp_path, monkeypatch):
+    """Same loop fed by PackedMoleculeDatasetWrapper: batches are built and augmented on the GPU (no host batch, no H2D)."""
+    from molclr_b200.trainer import DEFAULT_CONFIG, MolCLR, PackedMoleculeDatasetWrapper
+    monkeypatch.chdir(tmp_path)
+    cfg = copy.deepcopy(DEFAULT_CONFIG)
+    cfg.update(batch_size=64, epochs=3, warm_up=1, save_every_n_epochs=5, log_every_n_steps=4)
+    cfg["model"].update(num_layer=3, emb_dim=64, feat_dim=64)
+    cfg["dataset"].update(data_path="synthetic:700", valid_size=0.1)
+    torch.manual_seed(0)
+    data = PackedMoleculeDatasetWrapper(cfg["batch_size"], **cfg["dataset"])
+    train, valid = data.get_data_loaders()
+    assert len(train) == 630 // 64 and len(valid) == 70 // 64
+    xis, xjs = next(iter(train))
+    assert xis.x.is_cuda and xis.num_graphs == 64 and xis.x.shape == xjs.x.shape and not torch.equal(xis.x, xjs.x)
+    model, history = MolCLR(data, cfg, log_root=str(tmp_path / "ckpt")).train()
+    assert len(history) == 3 and all(h == h for h in history) and history[-1] < history[0]
