@@ -89,79 +89,96 @@ class GCN(_EncoderBase):
         return h, out
 
 
+def _gcn_encoder_forward(m, plan, comp, training, pool_mode):
+    """Node embedding -> L x (x W, scalar-table aggregation + bias, BatchNorm statistics) -> pooled graph vectors
+    (gcn_molclr.py:144-154).  Returns (p, p_lo, saved) with saved = (layers, drops, argmax)."""
+    L, D, N = m.num_layer, m.emb_dim, plan.N
+    dev = m.x_embedding1.weight.device
+    rw = m._rounded
+    h0 = ops.embed_nodes_fwd(plan, m.x_embedding1.weight.detach(), m.x_embedding2.weight.detach())
+    x_hi, x_lo = ops.bn_apply_fwd(h0, None, False, comp)
+    layers = []
+    drops = m._dropout_seeds()
+    z = coef = None
+    for l in range(L):
+        g, bn = m.gnns[l], m.batch_norms[l]
+        W_hi, W_lo = rw.get(g.weight)
+        y = torch.empty(N, D, device=dev)
+        ops.gemm(x_hi, W_hi, N, D, D, b_mn=True, A_lo=x_lo, B_lo=_lo(W_lo, comp), out=y)            # x @ weight
+        z = ops.gcn_aggregate_fwd(plan, y, g.edge_embedding1.weight.detach(), g.edge_embedding2.weight.detach(), g.bias.detach())
+        if training:
+            stats, T = ops.bn_tile_stats(z)
+            momentum = 0.1 if bn.momentum is None else bn.momentum
+            coef = ops.bn_fwd_finalize(stats, T, N, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
+                                       bn.num_batches_tracked, momentum, bn.eps)
+        else:
+            coef = ops.bn_eval_coef(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
+        layers.append((x_hi, z, coef, W_hi))
+        if l < L - 1:
+            x_hi, x_lo = ops.bn_apply_fwd(z, coef, True, comp, drop=drops[l])
+    argmax = torch.empty(plan.G, D, dtype=torch.int32, device=dev) if pool_mode == 2 else None
+    p, p_lo = ops.pool_fwd(plan, z, coef, pool_mode, relu=False, round_out=True, want_lo=True, argmax=argmax, drop=drops[L - 1]) \
+        if comp else (ops.pool_fwd(plan, z, coef, pool_mode, relu=False, round_out=True, argmax=argmax, drop=drops[L - 1]), None)
+    return p, p_lo, (layers, drops, argmax)
+
+
+def _gcn_encoder_backward(m, plan, saved, g_p, training, pool_mode):
+    """Backward of ``_gcn_encoder_forward``: gradients of [x_embedding1, x_embedding2] + per layer
+    [weight, bias, edge_emb1, edge_emb2, bn.weight, bn.bias]."""
+    layers, drops, argmax = saved
+    L, D, N = m.num_layer, m.emb_dim, plan.N
+    dev = g_p.device
+    grads = [None] * (2 + 6 * L)
+    x_hi, z, coef, W_hi = layers[L - 1]
+    bn = m.batch_norms[L - 1]
+    partials, P = ops.pool_bwd_stats(plan, g_p, z, coef, pool_mode, argmax=argmax, drop=drops[L - 1])
+    dgamma, dbeta, bcoef = ops.bn_bwd_finalize(partials, P, N, bn.weight.detach(), coef, training)
+    g_z, db = ops.bn_bwd_apply(z, bcoef, gp=g_p, plan=plan, pool_mode=pool_mode, round_out=False, argmax=argmax, drop=drops[L - 1])
+    for l in range(L - 1, -1, -1):
+        x_hi, z, coef, W_hi = layers[l]
+        base = 2 + 6 * l
+        grads[base + 4], grads[base + 5], grads[base + 1] = dgamma, dbeta, db          # BN weight/bias, conv bias
+        ds = ops.row_sum(ops.edge_table_grad_raw(plan, g_z))                          # scalar bond tables: [8]
+        grads[base + 2], grads[base + 3] = ds[:5].reshape(5, 1), ds[5:].reshape(3, 1)
+        g_y, _, _ = ops.gine_aggregate_bwd(plan, g_z, round_out=True)                 # (A + I)^T g_z, tf32 for the GEMMs
+        grads[base + 0] = ops.gemm_dw(x_hi, g_y)                                      # dW [in, out] = x^T g_y
+        g_x = torch.empty(N, D, device=dev)
+        ops.gemm(g_y, W_hi, N, D, D, out=g_x)                                         # g_x = g_y W^T
+        if l > 0:
+            _, zp, coefp, _ = layers[l - 1]
+            bnp = m.batch_norms[l - 1]
+            g_r, partials, P = ops.relu_bn_bwd_stats(g_x, zp, coefp, relu=True, drop=drops[l - 1])
+            dgamma, dbeta, bcoef = ops.bn_bwd_finalize(partials, P, N, bnp.weight.detach(), coefp, training)
+            g_z, db = ops.bn_bwd_apply(zp, bcoef, gy=g_r, round_out=False)
+        else:
+            grads[0], grads[1] = ops.embed_nodes_bwd(plan, g_x)
+    return grads
+
+
+def _gcn_precision(m):
+    if m.precision not in PRECISIONS:
+        raise ValueError(f"molclr_b200: precision must be one of {PRECISIONS}, got {m.precision!r}")
+    return m.precision == "tf32x3"
+
+
 class _GCNFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, m, plan, *params):
-        L, D, N = m.num_layer, m.emb_dim, plan.N
-        dev = params[0].device
-        rw = m._rounded
-        if m.precision not in PRECISIONS:
-            raise ValueError(f"molclr_b200: precision must be one of {PRECISIONS}, got {m.precision!r}")
-        comp = m.precision == "tf32x3"
-        training = m.training
-        pool_mode = ops.POOL_MODES[m.pool_name]
-        h0 = ops.embed_nodes_fwd(plan, m.x_embedding1.weight.detach(), m.x_embedding2.weight.detach())
-        x_hi, x_lo = ops.bn_apply_fwd(h0, None, False, comp)
-        layers = []
-        drops = m._dropout_seeds()
-        z = coef = None
-        for l in range(L):
-            g, bn = m.gnns[l], m.batch_norms[l]
-            W_hi, W_lo = rw.get(g.weight)
-            y = torch.empty(N, D, device=dev)
-            ops.gemm(x_hi, W_hi, N, D, D, b_mn=True, A_lo=x_lo, B_lo=_lo(W_lo, comp), out=y)            # x @ weight
-            z = ops.gcn_aggregate_fwd(plan, y, g.edge_embedding1.weight.detach(), g.edge_embedding2.weight.detach(), g.bias.detach())
-            if training:
-                stats, T = ops.bn_tile_stats(z)
-                momentum = 0.1 if bn.momentum is None else bn.momentum
-                coef = ops.bn_fwd_finalize(stats, T, N, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
-                                           bn.num_batches_tracked, momentum, bn.eps)
-            else:
-                coef = ops.bn_eval_coef(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
-            layers.append((x_hi, z, coef, W_hi))
-            if l < L - 1:
-                x_hi, x_lo = ops.bn_apply_fwd(z, coef, True, comp, drop=drops[l])
-        argmax = torch.empty(plan.G, D, dtype=torch.int32, device=dev) if pool_mode == 2 else None
-        p, p_lo = ops.pool_fwd(plan, z, coef, pool_mode, relu=False, round_out=True, want_lo=True, argmax=argmax, drop=drops[L - 1]) \
-            if comp else (ops.pool_fwd(plan, z, coef, pool_mode, relu=False, round_out=True, argmax=argmax, drop=drops[L - 1]), None)
-        h, out, head_saved = _head_forward(m, p, p_lo, rw, comp)
-        ctx.m, ctx.plan, ctx.layers, ctx.p, ctx.head_saved = m, plan, layers, p, head_saved
-        ctx.training, ctx.pool_mode, ctx.drops, ctx.argmax = training, pool_mode, drops, argmax
+        comp = _gcn_precision(m)
+        training, pool_mode = m.training, ops.POOL_MODES[m.pool_name]
+        p, p_lo, saved = _gcn_encoder_forward(m, plan, comp, training, pool_mode)
+        h, out, head_saved = _head_forward(m, p, p_lo, m._rounded, comp)
+        ctx.m, ctx.plan, ctx.saved, ctx.p, ctx.head_saved = m, plan, saved, p, head_saved
+        ctx.training, ctx.pool_mode = training, pool_mode
         return h, out
 
     @staticmethod
     def backward(ctx, g_h, g_out):
-        m, plan, layers, p = ctx.m, ctx.plan, ctx.layers, ctx.p
-        L, D, N = m.num_layer, m.emb_dim, plan.N
-        dev = p.device
+        m, plan, p = ctx.m, ctx.plan, ctx.p
         if g_out is None:
-            g_out = torch.zeros(p.shape[0], m.feat_dim // 2, device=dev)
+            g_out = torch.zeros(p.shape[0], m.feat_dim // 2, device=p.device)
         g_p, head_grads = _head_backward(m, p, ctx.head_saved, g_h, g_out)
-        grads = [None] * (2 + 6 * L)
-        x_hi, z, coef, W_hi = layers[L - 1]
-        bn = m.batch_norms[L - 1]
-        drops, argmax = ctx.drops, ctx.argmax
-        partials, P = ops.pool_bwd_stats(plan, g_p, z, coef, ctx.pool_mode, argmax=argmax, drop=drops[L - 1])
-        dgamma, dbeta, bcoef = ops.bn_bwd_finalize(partials, P, N, bn.weight.detach(), coef, ctx.training)
-        g_z, db = ops.bn_bwd_apply(z, bcoef, gp=g_p, plan=plan, pool_mode=ctx.pool_mode, round_out=False, argmax=argmax, drop=drops[L - 1])
-        for l in range(L - 1, -1, -1):
-            x_hi, z, coef, W_hi = layers[l]
-            base = 2 + 6 * l
-            grads[base + 4], grads[base + 5], grads[base + 1] = dgamma, dbeta, db          # BN weight/bias, conv bias
-            ds = ops.row_sum(ops.edge_table_grad_raw(plan, g_z))                          # scalar bond tables: [8]
-            grads[base + 2], grads[base + 3] = ds[:5].reshape(5, 1), ds[5:].reshape(3, 1)
-            g_y, _, _ = ops.gine_aggregate_bwd(plan, g_z, round_out=True)                 # (A + I)^T g_z, tf32 for the GEMMs
-            grads[base + 0] = ops.gemm_dw(x_hi, g_y)                                      # dW [in, out] = x^T g_y
-            g_x = torch.empty(N, D, device=dev)
-            ops.gemm(g_y, W_hi, N, D, D, out=g_x)                                         # g_x = g_y W^T
-            if l > 0:
-                _, zp, coefp, _ = layers[l - 1]
-                bnp = m.batch_norms[l - 1]
-                g_r, partials, P = ops.relu_bn_bwd_stats(g_x, zp, coefp, relu=True, drop=drops[l - 1])
-                dgamma, dbeta, bcoef = ops.bn_bwd_finalize(partials, P, N, bnp.weight.detach(), coefp, ctx.training)
-                g_z, db = ops.bn_bwd_apply(zp, bcoef, gy=g_r, round_out=False)
-            else:
-                grads[0], grads[1] = ops.embed_nodes_bwd(plan, g_x)
-        ctx.layers = None
+        grads = _gcn_encoder_backward(m, plan, ctx.saved, g_p, ctx.training, ctx.pool_mode)
+        ctx.saved = None
         return (None, None, *grads, *head_grads)

@@ -98,6 +98,66 @@ def _pad4(w_hi, w_lo, rows, dev):
     return out
 
 
+def finetune_head_forward(m, p, p_lo, lins, mode, comp):
+    """feat_lin followed by the prediction MLP ``lins`` (activation ``mode`` between the Linears): ginet_finetune.py:144-147,
+    gcn_finetune.py:158-160.  Returns (h, pred, saved, Wf)."""
+    G, D, Fd = p.shape[0], m.emb_dim, m.feat_dim
+    dev, rw = p.device, m._rounded
+    Wf, Wf_lo = rw.get(m.feat_lin.weight)
+    h, h_r = torch.empty(G, Fd, device=dev), torch.empty(G, Fd, device=dev)
+    h_lo = torch.empty(G, Fd, device=dev) if comp else None
+    ops.gemm(p, Wf, G, Fd, D, A_lo=p_lo, B_lo=_lo(Wf_lo, comp), out=h, out2=h_r, out_lo=h_lo, bias=m.feat_lin.bias.detach())
+    x_hi, x_lo, saved = h_r, h_lo, []
+    for k, lin in enumerate(lins):
+        O, I = lin.weight.shape
+        W, W_lo = rw.get(lin.weight)
+        last = k == len(lins) - 1
+        O4 = (O + 3) // 4 * 4
+        bias = lin.bias.detach()
+        if O4 != O:
+            W, W_lo = _pad4(W, W_lo, O, dev)
+            bias4 = torch.zeros(O4, device=dev)
+            ops.copy_rows(bias.reshape(O, 1), bias4.reshape(O4, 1), O)
+            bias = bias4
+        t = torch.empty(G, O4, device=dev)
+        ops.gemm(x_hi, W, G, O4, I, A_lo=x_lo, B_lo=_lo(W_lo, comp), out=t, bias=bias)
+        saved.append((x_hi, t, W, O))
+        if not last:
+            x_hi, x_lo = ops.act_fwd(t, mode, comp)
+    return h, t[:, :lins[-1].weight.shape[0]], saved, Wf
+
+
+def finetune_head_backward(m, p, saved, Wf, g_h, g_pred, mode):
+    """Returns (g_p, dWf, dbf, head_grads) with head_grads = [dW, db] per Linear of the prediction MLP."""
+    G, D, Fd = p.shape[0], m.emb_dim, m.feat_dim
+    dev = p.device
+    head_grads = [None] * (2 * len(saved))
+    # gradient arriving on the (4-padded) head output
+    x_hi, t, W, O = saved[-1]
+    g_t = torch.zeros(G, t.shape[1], device=dev)
+    if g_pred is not None:
+        ops.copy_cols(g_pred.contiguous(), g_t, O)
+    g_t = ops.round_tf32(g_t)
+    g_x = None
+    for k in range(len(saved) - 1, -1, -1):
+        x_hi, t, W, O = saved[k]
+        I = x_hi.shape[1]
+        dW = ops.gemm_dw(g_t, x_hi)                          # [O4, I]
+        head_grads[2 * k], head_grads[2 * k + 1] = dW[:O], ops.colsum(g_t)[:O]
+        g_x = torch.empty(G, I, device=dev)
+        if k > 0:
+            ops.gemm(g_t, W, G, I, t.shape[1], b_mn=True, out=g_x)
+            g_t = ops.act_bwd(g_x, saved[k - 1][1], mode)    # through the activation in front of this Linear
+        else:                                                # reaches h: add the gradient arriving on the returned h
+            g_hh_r = torch.empty(G, I, device=dev)
+            ops.gemm(g_t, W, G, I, t.shape[1], b_mn=True, out=g_x, out2=g_hh_r, addend=None if g_h is None else g_h.contiguous())
+    dWf = ops.gemm_dw(g_hh_r, p)
+    dbf = ops.colsum(g_x)
+    g_p = torch.empty(G, D, device=dev)
+    ops.gemm(g_hh_r, Wf, G, D, Fd, b_mn=True, out=g_p)
+    return g_p, dWf, dbf, head_grads
+
+
 class _FinetuneFunction(torch.autograd.Function):
 
     @staticmethod
@@ -105,64 +165,16 @@ class _FinetuneFunction(torch.autograd.Function):
         comp = _check_precision(m)
         training, pool_mode = m.training, ops.POOL_MODES[m.pool_name]
         p, p_lo, layers = _encoder_forward(m, plan, comp, training, pool_mode)
-        G, D, Fd = p.shape[0], m.emb_dim, m.feat_dim
-        dev, rw, mode = p.device, m._rounded, ops.ACT_MODES[m.pred_act]
-        Wf, Wf_lo = rw.get(m.feat_lin.weight)
-        h, h_r = torch.empty(G, Fd, device=dev), torch.empty(G, Fd, device=dev)
-        h_lo = torch.empty(G, Fd, device=dev) if comp else None
-        ops.gemm(p, Wf, G, Fd, D, A_lo=p_lo, B_lo=_lo(Wf_lo, comp), out=h, out2=h_r, out_lo=h_lo, bias=m.feat_lin.bias.detach())
-        lins = m._head_linears()
-        x_hi, x_lo, saved = h_r, h_lo, []
-        for k, lin in enumerate(lins):
-            O, I = lin.weight.shape
-            W, W_lo = rw.get(lin.weight)
-            last = k == len(lins) - 1
-            O4 = (O + 3) // 4 * 4
-            bias = lin.bias.detach()
-            if O4 != O:
-                W, W_lo = _pad4(W, W_lo, O, dev)
-                bias4 = torch.zeros(O4, device=dev)
-                ops.copy_rows(bias.reshape(O, 1), bias4.reshape(O4, 1), O)
-                bias = bias4
-            t = torch.empty(G, O4, device=dev)
-            ops.gemm(x_hi, W, G, O4, I, A_lo=x_lo, B_lo=_lo(W_lo, comp), out=t, bias=bias)
-            saved.append((x_hi, t, W, O))
-            if not last:
-                x_hi, x_lo = ops.act_fwd(t, mode, comp)
-        pred = t[:, :lins[-1].weight.shape[0]]
+        mode = ops.ACT_MODES[m.pred_act]
+        h, pred, saved, Wf = finetune_head_forward(m, p, p_lo, m._head_linears(), mode, comp)
         ctx.m, ctx.plan, ctx.layers, ctx.p, ctx.saved, ctx.Wf = m, plan, layers, p, saved, Wf
         ctx.training, ctx.pool_mode, ctx.mode = training, pool_mode, mode
         return h, pred
 
     @staticmethod
     def backward(ctx, g_h, g_pred):
-        m, plan, p, saved, mode = ctx.m, ctx.plan, ctx.p, ctx.saved, ctx.mode
-        G, D, Fd = p.shape[0], m.emb_dim, m.feat_dim
-        dev = p.device
-        head_grads = [None] * (2 * len(saved))
-        # gradient arriving on the (4-padded) head output
-        x_hi, t, W, O = saved[-1]
-        g_t = torch.zeros(G, t.shape[1], device=dev)
-        if g_pred is not None:
-            ops.copy_cols(g_pred.contiguous(), g_t, O)
-        g_t = ops.round_tf32(g_t)
-        g_x = None
-        for k in range(len(saved) - 1, -1, -1):
-            x_hi, t, W, O = saved[k]
-            I = x_hi.shape[1]
-            dW = ops.gemm_dw(g_t, x_hi)                          # [O4, I]
-            head_grads[2 * k], head_grads[2 * k + 1] = dW[:O], ops.colsum(g_t)[:O]
-            g_x = torch.empty(G, I, device=dev)
-            if k > 0:
-                ops.gemm(g_t, W, G, I, t.shape[1], b_mn=True, out=g_x)
-                g_t = ops.act_bwd(g_x, saved[k - 1][1], mode)    # through the activation in front of this Linear
-            else:                                                # reaches h: add the gradient arriving on the returned h
-                g_hh_r = torch.empty(G, I, device=dev)
-                ops.gemm(g_t, W, G, I, t.shape[1], b_mn=True, out=g_x, out2=g_hh_r, addend=None if g_h is None else g_h.contiguous())
-        dWf = ops.gemm_dw(g_hh_r, p)
-        dbf = ops.colsum(g_x)
-        g_p = torch.empty(G, D, device=dev)
-        ops.gemm(g_hh_r, ctx.Wf, G, D, Fd, b_mn=True, out=g_p)
+        m, plan, p = ctx.m, ctx.plan, ctx.p
+        g_p, dWf, dbf, head_grads = finetune_head_backward(m, p, ctx.saved, ctx.Wf, g_h, g_pred, ctx.mode)
         grads = _encoder_backward(m, plan, ctx.layers, g_p, ctx.training, ctx.pool_mode)
         ctx.layers = None
         return (None, None, *grads, dWf, dbf, *head_grads)

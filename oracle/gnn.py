@@ -273,3 +273,40 @@ class GINetFinetune(nn.Module):
         h = self.pool(h, data.batch)
         h = self.feat_lin(h)
         return h, self.pred_head(h)
+
+
+# ----------------------------------------------------------------------------- fine-tune GCN
+class GCNFinetune(nn.Module):
+    """models/gcn_finetune.py:94-163: the GCN encoder, ``feat_lin`` and ``pred_lin`` = Linear -> Softplus -> Linear(., 2 | 1);
+    returns ``(h, pred_lin(h))``."""
+
+    def __init__(self, task="classification", num_layer=5, emb_dim=300, feat_dim=256, drop_ratio=0, pool="mean"):
+        super().__init__()
+        self.num_layer, self.emb_dim, self.feat_dim, self.drop_ratio, self.task = num_layer, emb_dim, feat_dim, drop_ratio, task
+        if num_layer < 2:
+            raise ValueError("Number of GNN layers must be greater than 1.")
+        self.x_embedding1 = nn.Embedding(num_atom_type, emb_dim)
+        self.x_embedding2 = nn.Embedding(num_chirality_tag, emb_dim)
+        nn.init.xavier_uniform_(self.x_embedding1.weight.data)
+        nn.init.xavier_uniform_(self.x_embedding2.weight.data)
+        self.gnns = nn.ModuleList([GCNConv(emb_dim) for _ in range(num_layer)])
+        self.batch_norms = nn.ModuleList([nn.BatchNorm1d(emb_dim) for _ in range(num_layer)])
+        if pool not in _POOLS:
+            raise ValueError("Not defined pooling!")
+        self.pool = _POOLS[pool]
+        self.feat_lin = nn.Linear(emb_dim, feat_dim)
+        out_dim = {"classification": 2, "regression": 1}[task]                      # gcn_finetune.py:133-144
+        self.pred_lin = nn.Sequential(nn.Linear(feat_dim, feat_dim // 2), nn.Softplus(), nn.Linear(feat_dim // 2, out_dim))
+
+    def forward(self, data):
+        h = self.x_embedding1(data.x[:, 0]) + self.x_embedding2(data.x[:, 1])
+        for layer in range(self.num_layer):                                         # gcn_finetune.py:152-158
+            h = self.gnns[layer](h, data.edge_index, data.edge_attr)
+            h = self.batch_norms[layer](h)
+            if layer == self.num_layer - 1:
+                h = _dropout(self, layer, h)
+            else:
+                h = _dropout(self, layer, F.relu(h))
+        h = self.pool(h, data.batch)
+        h = self.feat_lin(h)
+        return h, self.pred_lin(h)

@@ -2,7 +2,7 @@
 
 Run in the dev container only (needs /root/reference):  python tests/golden/make_encoder_golden.py
 
-`models/ginet_molclr.py`, `models/gcn_molclr.py` and `models/ginet_finetune.py` are imported from /root/reference as they
+`models/ginet_molclr.py`, `models/gcn_molclr.py`, `models/ginet_finetune.py` and `models/gcn_finetune.py` are imported from /root/reference as they
 are; their third-party base (torch-geometric 1.6.3 / torch-scatter 2.0.6, not vendored, not installable offline) is
 provided by the restatement in `pyg163_stub.py` (MessagePassing.propagate = index_select + scatter_add_, add_self_loops,
 global_*_pool).  Every line of the reference's GINEConv / GCNConv / GINet / GCN / fine-tune GINet -- self-loop attributes,
@@ -32,6 +32,7 @@ sys.path.insert(0, REF)
 from models.ginet_molclr import GINet as RefGINet            # noqa: E402  (the reference classes themselves)
 from models.gcn_molclr import GCN as RefGCN                  # noqa: E402
 from models.ginet_finetune import GINet as RefGINetFinetune  # noqa: E402
+from models.gcn_finetune import GCN as RefGCNFinetune        # noqa: E402
 from utils.nt_xent import NTXentLoss                         # noqa: E402
 
 from molclr_b200.synth import make_pair_batch, make_plain_batch   # noqa: E402
@@ -125,10 +126,10 @@ def small_case(name, cls, pool, graphs, seed, wseed, layers=3, emb=64, feat=64):
     print(name, float(loss))
 
 
-def finetune_case(name, task, graphs, seed, wseed):
-    """models/ginet_finetune.py GINet + the criteria of finetune.py:70-77 (classification: CrossEntropyLoss on
-    data.y.flatten(); regression: MSELoss), drop_ratio 0 (dropout is not reproducible bit for bit)."""
-    model = RefGINetFinetune(task, 5, 300, 512, 0, "mean")
+def finetune_case(name, task, graphs, seed, wseed, gcn=False):
+    """models/ginet_finetune.py GINet (or models/gcn_finetune.py GCN) + the criteria of finetune.py:70-77 (classification:
+    CrossEntropyLoss on data.y.flatten(); regression: MSELoss), drop_ratio 0 (dropout is not reproducible bit for bit)."""
+    model = RefGCNFinetune(task, 5, 300, 256, 0, "mean") if gcn else RefGINetFinetune(task, 5, 300, 512, 0, "mean")
     model.load_state_dict(golden_weights(model.state_dict(), wseed))
     model.train()
     b = make_plain_batch(graphs, seed=seed, mean_atoms=46.0 if task == "classification" else 26.0, std_atoms=18.0 if task == "classification" else 13.0)
@@ -159,3 +160,5 @@ if __name__ == "__main__":
     small_case("enc_gcn_small_mean", RefGCN, "mean", 14, seed=22, wseed=5)
     finetune_case("enc_finetune_cls", "classification", 12, seed=30, wseed=6)
     finetune_case("enc_finetune_reg", "regression", 12, seed=31, wseed=7)
+    finetune_case("enc_gcn_finetune_cls", "classification", 12, seed=32, wseed=8, gcn=True)
+    finetune_case("enc_gcn_finetune_reg", "regression", 12, seed=33, wseed=9, gcn=True)

@@ -59,10 +59,10 @@ def test_oracle_small_models_all_pools_match_reference_models(path):
     assert not check_golden_grads(m, g, TOL_GRAD)
 
 
-@pytest.mark.parametrize("task", ["cls", "reg"])
-def test_oracle_finetune_matches_reference_model(task):
-    g = np.load(os.path.join(GOLDEN, f"enc_finetune_{task}.npz"))
-    m = _load(ognn.GINetFinetune(str(g["task"]), 5, 300, 512, 0, "mean"), g)
+@pytest.mark.parametrize("task,gcn", [("cls", False), ("reg", False), ("cls", True), ("reg", True)])
+def test_oracle_finetune_matches_reference_model(task, gcn):
+    g = np.load(os.path.join(GOLDEN, f"enc_{'gcn_' if gcn else ''}finetune_{task}.npz"))
+    m = _load(ognn.GCNFinetune(str(g["task"]), 5, 300, 256, 0, "mean") if gcn else ognn.GINetFinetune(str(g["task"]), 5, 300, 512, 0, "mean"), g)
     h, pred = m(golden_batch(g, "b"))
     y = torch.from_numpy(g["y"])
     loss = torch.nn.CrossEntropyLoss()(pred, y.flatten()) if task == "cls" else torch.nn.MSELoss()(pred, y)

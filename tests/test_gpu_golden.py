@@ -13,7 +13,7 @@ from tests.util import golden_weights, golden_batch, check_golden_grads, max_rel
 pytestmark = pytest.mark.gpu
 
 if torch.cuda.is_available():
-    from molclr_b200 import GINet, GCN, NTXentLoss, pretrain_loss, ginet_finetune
+    from molclr_b200 import GINet, GCN, NTXentLoss, pretrain_loss, ginet_finetune, gcn_finetune
 
 DEV = "cuda:0"
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
@@ -72,10 +72,10 @@ def test_small_models_all_pools_match_reference_models(path):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("task", ["cls", "reg"])
-def test_finetune_matches_reference_model(task):
-    g = np.load(os.path.join(GOLDEN, f"enc_finetune_{task}.npz"))
-    m = _load(ginet_finetune.GINet(str(g["task"]), 5, 300, 512, 0, "mean"), g)
+@pytest.mark.parametrize("task,gcn", [("cls", False), ("reg", False), ("cls", True), ("reg", True)])
+def test_finetune_matches_reference_model(task, gcn):
+    g = np.load(os.path.join(GOLDEN, f"enc_{'gcn_' if gcn else ''}finetune_{task}.npz"))
+    m = _load(gcn_finetune.GCN(str(g["task"]), 5, 300, 256, 0, "mean") if gcn else ginet_finetune.GINet(str(g["task"]), 5, 300, 512, 0, "mean"), g)
     h, pred = m(golden_batch(g, "b").to(DEV))
     y = torch.from_numpy(g["y"]).to(DEV)
     loss = torch.nn.CrossEntropyLoss()(pred, y.flatten()) if task == "cls" else torch.nn.MSELoss()(pred, y)
