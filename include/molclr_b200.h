@@ -123,10 +123,11 @@ int molclr_gcn_aggregate_fwd(const float* src, const int32_t* rowptr, const int3
                              const float* b2, const float* bias, int64_t N, int D, float* out, int64_t ld_out, cudaStream_t stream);
 /* out[r] = sum_c in[r][c]: collapses the [8][D] result of molclr_edge_table_grad to the GCN's [5][1] + [3][1] gradients */
 int molclr_row_sum(const float* in, int R, int C, float* out, cudaStream_t stream);
-/* x = [relu](z*scale + shift) (bn_coef NULL: x = z) materialised as a tensor-core operand: hi = tf32(x), lo (optional) =
- * tf32(x - hi); rows `ld` floats apart.  The GCN's GEMM input (gcn_molclr.py:146-152 then :76). */
+/* x = [relu](z*scale + shift) (bn_coef NULL: x = z) materialised as a tensor-core operand: hi = tf32(x) (round_hi = 0: x itself,
+ * for the compensated GEMM that derives its low halves on chip), lo (optional) = tf32(x - tf32(x)); rows `ld` floats apart.
+ * The GCN's GEMM input (gcn_molclr.py:146-152 then :76). */
 int molclr_bn_apply_fwd(const float* z, const float* bn_coef, int relu, int64_t N, int D, float* hi, float* lo, int64_t ld,
-                        uint32_t drop_seed, float drop_p, cudaStream_t stream);
+                        int round_hi, uint32_t drop_seed, float drop_p, cudaStream_t stream);
 /* tile_stats [T][2][D]: column mean and M2 of every 32-row group of z (T = molclr_gemm_colstat_tiles(N)): what the GEMM
  * epilogue emits for the GIN path, for outputs that do not come from a GEMM. */
 int molclr_bn_tile_stats(const float* z, int64_t N, int D, int T, float* tile_stats, cudaStream_t stream);

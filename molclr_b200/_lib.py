@@ -54,7 +54,7 @@ SIGNATURES = {
     "molclr_relu_bn_bwd_stats": (i32, [vp, vp, vp, i32, i64, i32, vp, vp, C.POINTER(i32), u32, f32, vp]),
     "molclr_gcn_aggregate_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, i64, vp]),
     "molclr_row_sum": (i32, [vp, i32, i32, vp, vp]),
-    "molclr_bn_apply_fwd": (i32, [vp, vp, i32, i64, i32, vp, vp, i64, u32, f32, vp]),
+    "molclr_bn_apply_fwd": (i32, [vp, vp, i32, i64, i32, vp, vp, i64, i32, u32, f32, vp]),
     "molclr_bn_tile_stats": (i32, [vp, i64, i32, i32, vp, vp]),
     "molclr_edge_table_grad": (i32, [vp, i64, vp, i64, i32, vp, vp]),
     "molclr_reduce_partials": (i32, [vp, i32, i32, f32, i32, vp, vp]),

@@ -840,7 +840,7 @@ __global__ void __launch_bounds__(kRowThreads) pool_bwd_stats_kernel(
 template <int NCH>
 __global__ void __launch_bounds__(kRowThreads) bn_apply_fwd_kernel(
     const float* __restrict__ z, const float* __restrict__ coef, int relu, int N, int D, float* __restrict__ hi,
-    float* __restrict__ lo, long long ld, const DropCfg drop) {
+    float* __restrict__ lo, long long ld, int round_hi, const DropCfg drop) {
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* sc = sm4; float4* sh = sm4 + D4;
@@ -862,7 +862,7 @@ __global__ void __launch_bounds__(kRowThreads) bn_apply_fwd_kernel(
           if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
           if (drop.thr) v = f4_mul(v, drop_mask4(drop, i, q, D4));
         }
-        st_f4(hi + (size_t)i * ld + 4 * q, f4_tf32(v));
+        st_f4(hi + (size_t)i * ld + 4 * q, round_hi ? f4_tf32(v) : v);
         if (lo) st_f4(lo + (size_t)i * ld + 4 * q, f4_tf32_residual(v));
       }
     }
@@ -1317,7 +1317,7 @@ extern "C" int molclr_pool_bwd_stats(const float* gp, const int32_t* node2graph,
 }
 
 extern "C" int molclr_bn_apply_fwd(const float* z, const float* bn_coef, int relu, int64_t N, int D, float* hi, float* lo,
-                                   int64_t ld, uint32_t drop_seed, float drop_p, cudaStream_t stream) {
+                                   int64_t ld, int round_hi, uint32_t drop_seed, float drop_p, cudaStream_t stream) {
   REQUIRE_D(D);
   REQUIRE_DROP(drop_p);
   MOLCLR_REQUIRE(ld >= D && ld % 4 == 0, "bn_apply_fwd: ld must be >= D and a multiple of 4");
@@ -1325,7 +1325,7 @@ extern "C" int molclr_bn_apply_fwd(const float* z, const float* bn_coef, int rel
   const size_t smem = (size_t)2 * D * sizeof(float);
   NCH_DISPATCH(D / 4, {
     auto k = bn_apply_fwd_kernel<NCH>;
-    k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(z, bn_coef, relu, (int)N, D, hi, lo, ld,
+    k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(z, bn_coef, relu, (int)N, D, hi, lo, ld, round_hi,
                                                                                           make_drop(drop_seed, bn_coef ? drop_p : 0.f));
   });
   MOLCLR_CHECK_LAUNCH("bn_apply_fwd");

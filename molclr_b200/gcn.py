@@ -11,8 +11,9 @@ Per view (N nodes, D = emb_dim):
     plan (once per batch)        CSR + transpose + bond-class counts + graph segments
     embed_nodes_fwd              h0 = E1[x0] + E2[x1]                                  gcn_molclr.py:144
     per layer l:
-      bn_apply_fwd               x_l = relu(BN_{l-1}(z_{l-1})) as a tf32 (hi, lo) GEMM operand (x_0 = h0)     :146-152
-      gemm                       y_l = x_l W_l          (W stored [in, out]: consumed MN-major in place)      :76
+      bn_apply_fwd               x_l = relu(BN_{l-1}(z_{l-1})) as ONE unrounded fp32 GEMM operand (x_0 = h0)  :146-152
+      gemm (compensate)          y_l = x_l W_l   (~fp32: TF32 pass + bf16 corrections derived on chip, on a
+                                 K-major copy of W^T; "tf32" mode: W [in, out] consumed MN-major in place)      :76
       gcn_aggregate_fwd          z_l = sum_j (y_l[j] + s_e) + (y_l[i] + s_self) + b_l                          :79-88
       bn_tile_stats + finalize   batch statistics -> (scale, shift, mean, invstd); running stats              :147
     pool_fwd, head               as GINet                                                                     :154-156
@@ -23,7 +24,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .ginet import (PRECISIONS, _EncoderBase, _RoundedWeights, _head_backward, _head_forward, _lo, num_atom_type, num_bond_direction,
+from .ginet import (PRECISIONS, _EncoderBase, _RoundedWeights, _head_backward, _head_forward, num_atom_type, num_bond_direction,
                     num_bond_type, num_chirality_tag)
 from .graph import get_plan
 
@@ -96,15 +97,20 @@ def _gcn_encoder_forward(m, plan, comp, training, pool_mode):
     dev = m.x_embedding1.weight.device
     rw = m._rounded
     h0 = ops.embed_nodes_fwd(plan, m.x_embedding1.weight.detach(), m.x_embedding2.weight.detach())
-    x_hi, x_lo = ops.bn_apply_fwd(h0, None, False, comp)
+    # tf32x3: the GEMM input stays one unrounded fp32 tensor (h0 itself for layer 0) and x @ weight runs as the compensated
+    # product that derives its bf16 correction tiles on chip, on a K-major copy of weight^T; tf32: a tf32-rounded operand
+    x = h0 if comp else ops.bn_apply_fwd(h0, None, False, False)[0]
     layers = []
     drops = m._dropout_seeds()
     z = coef = None
     for l in range(L):
         g, bn = m.gnns[l], m.batch_norms[l]
-        W_hi, W_lo = rw.get(g.weight)
+        W_hi, _ = rw.get(g.weight)
         y = torch.empty(N, D, device=dev)
-        ops.gemm(x_hi, W_hi, N, D, D, b_mn=True, A_lo=x_lo, B_lo=_lo(W_lo, comp), out=y)            # x @ weight
+        if comp:
+            ops.gemm(x, rw.raw(g.weight, transpose=True), N, D, D, compensate=True, out=y)    # x @ weight
+        else:
+            ops.gemm(x, W_hi, N, D, D, b_mn=True, out=y)
         z = ops.gcn_aggregate_fwd(plan, y, g.edge_embedding1.weight.detach(), g.edge_embedding2.weight.detach(), g.bias.detach())
         if training:
             stats, T = ops.bn_tile_stats(z)
@@ -113,9 +119,9 @@ def _gcn_encoder_forward(m, plan, comp, training, pool_mode):
                                        bn.num_batches_tracked, momentum, bn.eps)
         else:
             coef = ops.bn_eval_coef(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
-        layers.append((x_hi, z, coef, W_hi))
+        layers.append((x, z, coef, W_hi))
         if l < L - 1:
-            x_hi, x_lo = ops.bn_apply_fwd(z, coef, True, comp, drop=drops[l])
+            x = ops.bn_apply_fwd(z, coef, True, False, drop=drops[l], round_hi=not comp)[0]
     argmax = torch.empty(plan.G, D, dtype=torch.int32, device=dev) if pool_mode == 2 else None
     p, p_lo = ops.pool_fwd(plan, z, coef, pool_mode, relu=False, round_out=True, want_lo=True, argmax=argmax, drop=drops[L - 1]) \
         if comp else (ops.pool_fwd(plan, z, coef, pool_mode, relu=False, round_out=True, argmax=argmax, drop=drops[L - 1]), None)

@@ -56,14 +56,16 @@ class _RoundedWeights:
         self._cache[key] = (p._version, r, p.data_ptr())
         return r
 
-    def raw(self, p):
-        """Unrounded copy with 128-byte aligned rows: the B operand of the compensated GEMM that derives every low half on chip."""
-        key = ("raw", id(p))
+    def raw(self, p, transpose=False):
+        """Unrounded copy (of the transpose, for weights stored [in, out]) with 128-byte aligned rows: the K-major B operand of
+        the compensated GEMM that derives every low half on chip."""
+        key = ("raw", id(p), transpose)
         hit = self._cache.get(key)
         if hit is not None and hit[0] == p._version and hit[2] == p.data_ptr():
             return hit[1]
-        r = ops.padded(p.shape[0], p.shape[1], p.device)
-        r.copy_(p.detach())
+        src = p.detach().t() if transpose else p.detach()
+        r = ops.padded(src.shape[0], src.shape[1], p.device)
+        r.copy_(src)
         self._cache[key] = (p._version, r, p.data_ptr())
         return r
 

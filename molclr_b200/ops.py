@@ -186,13 +186,14 @@ def row_sum(x):
     return out
 
 
-def bn_apply_fwd(z, bn_coef, relu, want_lo, drop=(0, 0.0)):
-    """(hi, lo) tensor-core operand pair of relu(BN(z)) (bn_coef None: of z itself), 128-byte aligned rows."""
+def bn_apply_fwd(z, bn_coef, relu, want_lo, drop=(0, 0.0), round_hi=True):
+    """(hi, lo) tensor-core operand pair of relu(BN(z)) (bn_coef None: of z itself), 128-byte aligned rows; round_hi=False
+    leaves hi unrounded (operand of the compensated GEMM that derives its low halves on chip)."""
     N, D = z.shape
     hi = padded(N, D, z.device)
     lo = padded(N, D, z.device) if want_lo else None
-    check(_lib.load().molclr_bn_apply_fwd(ptr(z), ptr(bn_coef), int(relu), N, D, ptr2d(hi), ptr2d(lo), hi.stride(0), drop[0], drop[1],
-                                          stream()), "bn_apply_fwd")
+    check(_lib.load().molclr_bn_apply_fwd(ptr(z), ptr(bn_coef), int(relu), N, D, ptr2d(hi), ptr2d(lo), hi.stride(0), int(round_hi),
+                                          drop[0], drop[1], stream()), "bn_apply_fwd")
     return hi, lo
 
 
