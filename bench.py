@@ -267,11 +267,26 @@ def run_ours(args):
         b.record()
         times.append((a, b, plan.N, plan.E, bool(kw.get("want_lo"))))
         return out
+    # ... and the row GEMMs of the GIN MLP (the largest share of the step), same in-situ timing: useful FLOPs 2 M N K per call
+    gemm_times = []
+    orig_gemm = ops.gemm
+
+    def timed_gemm(A, B, M, N, K, **kw):
+        if M < 50000:                               # head GEMMs: not the ones that matter
+            return orig_gemm(A, B, M, N, K, **kw)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = orig_gemm(A, B, M, N, K, **kw)
+        b.record()
+        gemm_times.append((a, b, 2.0 * M * N * K, bool(kw.get("compensate"))))
+        return out
     ops.gine_aggregate_fwd = timed_aggregate
+    ops.gemm = timed_gemm
     for i in range(3 if args.model == "gin" else 0):
         step(*resident[i % NB])
     torch.cuda.synchronize()
     ops.gine_aggregate_fwd = orig
+    ops.gemm = orig_gemm
     D = 300
     # algorithmic bytes per launch (DESIGN.md / SURVEY 8d): read src rows once, write the aggregate (one tensor; plus the tf32
     # residual when the caller asks for it), CSR rowptr/col/eattr, BN coefficients and bond tables
@@ -287,6 +302,25 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": agg_bytes, "launches_timed": len(times)}
     else:
         roof = None
+    roof_gemm = None
+    if gemm_times:
+        try:
+            tf32_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]) / 2
+            tf32_src = "measured sustained bf16 cuBLAS throughput / 2 (MEASURED_PEAKS.json; TF32 runs at half the bf16 rate)"
+        except Exception:
+            tf32_peak, tf32_src = 1100.0, "fallback: nominal dense TF32"
+        def tfl(sel):
+            ts = [t for t in gemm_times if sel(t)]
+            return (sum(t[2] for t in ts) / (sum(t[0].elapsed_time(t[1]) for t in ts) * 1e-3) / 1e12, len(ts)) if ts else (None, 0)
+        fwd, n_fwd = tfl(lambda t: t[3])
+        bwd, n_bwd = tfl(lambda t: not t[3])
+        roof_gemm = {"bound": "tensor", "kernel": "gemm_tf32_kernel, row GEMMs of the GIN MLP (M = nodes)", "unit": "TFLOP/s", "peak": tf32_peak,
+                     "peak_source": tf32_src, "achieved": fwd if fwd is not None else bwd,
+                     "frac": (fwd if fwd is not None else bwd) / tf32_peak,
+                     "forward_compensated_useful_tflops": fwd, "forward_calls_timed": n_fwd,
+                     "backward_single_pass_tflops": bwd, "backward_calls_timed": n_bwd,
+                     "note": "useful FLOPs 2MNK per product (the compensated forward issues 2x that in tensor work); these loops are "
+                             "bound by L2<->SM traffic (operand tiles in, output tiles out), see DESIGN.md section 6"}
     ncu_traffic = os.path.join(ROOT, "profiles", "aggregate_traffic.json")
     if roof is not None and os.path.exists(ncu_traffic):
         try:
@@ -308,7 +342,7 @@ def run_ours(args):
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "molecules/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms},
-            "roofline": roof}
+            "roofline": roof, "roofline_gemm": roof_gemm}
     if world == 1 and not args.no_cpu_baseline:
         mols, threads, dt = cpu_reference_run(args.cpu_batch, 2, 1)
         line["cpu_baseline"] = {"value": mols, "unit": "molecules/s", "cores": threads, "kind": "port",
