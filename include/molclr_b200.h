@@ -54,7 +54,8 @@ int molclr_device_info(int* sm_count, int* cc);
  *     (exact in TF32: they are an operand of the table-gradient contraction);
  *   nbr[N][8] uint32 (optional, 32-byte aligned): fixed-width copy of rows with <= 8 in-edges, entry = source << 4 | eattr,
  *     0xFFFFFFFF = empty, [0] = 0xFFFFFFFE = "row too long, use the CSR": lets the aggregation kernel fetch a row's neighbour
- *     list with ONE load (no rowptr -> col dependency);
+ *     list with ONE load (no rowptr -> col dependency); nbr_t[N][8] (optional): the same for the out-edges (destination << 4),
+ *     used by the backward aggregation;
  *   gptr[G+1], gperm[N]: nodes grouped by graph (identity permutation for sorted `batch`).
  *   status[4]: [0] = error bits (1 node feature, 2 edge endpoint, 4 edge attr, 8 batch id out of
  *              range, 16 a per-class in-degree above 2048); [1] = 1 if `batch` was not sorted.
@@ -62,8 +63,8 @@ int molclr_device_info(int* sm_count, int* cc);
 size_t molclr_plan_workspace_bytes(int64_t N, int64_t E, int64_t G);
 int molclr_plan_build(const int64_t* x, const int64_t* edge_index, const int64_t* edge_attr, const int64_t* batch,
                       int64_t N, int64_t E, int64_t G, int32_t* xpacked, int32_t* node2graph, int32_t* rowptr,
-                      int32_t* col, uint8_t* eattr, int32_t* rowptr_t, int32_t* col_t, float* cnt, uint32_t* nbr, int32_t* gptr,
-                      int32_t* gperm, void* workspace, size_t workspace_bytes, int32_t* status, cudaStream_t stream);
+                      int32_t* col, uint8_t* eattr, int32_t* rowptr_t, int32_t* col_t, float* cnt, uint32_t* nbr, uint32_t* nbr_t,
+                      int32_t* gptr, int32_t* gperm, void* workspace, size_t workspace_bytes, int32_t* status, cudaStream_t stream);
 
 /* ---- on-device batch construction + augmentation: dataset/dataset.py:112-145 and the DataLoader collate
  * (dataset.py:179-184) from a packed molecule store in HBM ("molclr-packed v1": atom_ptr[M+1], atoms = type | chirality << 8;
@@ -107,7 +108,8 @@ int molclr_gine_aggregate_fwd(const float* src, const float* bn_coef, int relu, 
  * with bn_coef = [scale, shift, mean, invstd][D].  partials: [molclr_rowwise_max_blocks()][2][D]; *num_partials
  * (host) receives the number of partial rows written. */
 int molclr_rowwise_max_blocks(void);
-int molclr_gine_aggregate_bwd(const float* ga, const int32_t* rowptr_t, const int32_t* col_t, const float* z_prev,
+int molclr_gine_aggregate_bwd(const float* ga, const int32_t* rowptr_t, const int32_t* col_t,
+                              const uint32_t* nbr_t /* optional: selects the shared-memory tile kernel */, const float* z_prev,
                               const float* bn_coef, int relu, int64_t N, int D, float* gy, int round_tf32_out, float* partials,
                               int* num_partials, uint32_t drop_seed, float drop_p, cudaStream_t stream);
 /* The ReLU-backward / BatchNorm-statistics stage alone (no neighbour gather): gy = g * [relu mask of z_prev], partials as

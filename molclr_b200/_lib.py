@@ -42,7 +42,7 @@ SIGNATURES = {
     "molclr_launch_count": (C.c_uint64, []),
     "molclr_device_info": (i32, [C.POINTER(i32), C.POINTER(i32)]),
     "molclr_plan_workspace_bytes": (sz, [i64, i64, i64]),
-    "molclr_plan_build": (i32, [vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp]),
+    "molclr_plan_build": (i32, [vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp]),
     "molclr_augment_views": (i32, [vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, C.c_uint64, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                    vp, vp]),
     "molclr_embed_nodes_fwd": (i32, [vp, vp, vp, i64, i32, vp, vp]),
@@ -50,7 +50,7 @@ SIGNATURES = {
     "molclr_embed_nodes_bwd": (i32, [vp, vp, i64, i64, i32, vp, vp, vp]),
     "molclr_gine_aggregate_fwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, vp, i64, i32, vp, u32, f32, vp]),
     "molclr_rowwise_max_blocks": (i32, []),
-    "molclr_gine_aggregate_bwd": (i32, [vp, vp, vp, vp, vp, i32, i64, i32, vp, i32, vp, C.POINTER(i32), u32, f32, vp]),
+    "molclr_gine_aggregate_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i64, i32, vp, i32, vp, C.POINTER(i32), u32, f32, vp]),
     "molclr_relu_bn_bwd_stats": (i32, [vp, vp, vp, i32, i64, i32, vp, vp, C.POINTER(i32), u32, f32, vp]),
     "molclr_gcn_aggregate_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, i64, vp]),
     "molclr_row_sum": (i32, [vp, i32, i32, vp, vp]),

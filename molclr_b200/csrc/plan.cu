@@ -141,7 +141,7 @@ __global__ void plan_rows_kernel(const int64_t* __restrict__ ei, const int64_t* 
                                  int64_t N, int64_t E, int64_t G, const int32_t* __restrict__ rowptr,
                                  const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ gptr,
                                  int32_t* col, uint8_t* __restrict__ eattr, int32_t* col_t,
-                                 float* __restrict__ cnt, uint32_t* __restrict__ nbr, int32_t* gperm, int32_t* status) {
+                                 float* __restrict__ cnt, uint32_t* __restrict__ nbr, uint32_t* __restrict__ nbr_t, int32_t* gperm, int32_t* status) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t n = i; n < N; n += stride) {
@@ -174,6 +174,16 @@ __global__ void plan_rows_kernel(const int64_t* __restrict__ ei, const int64_t* 
     b = rowptr_t[n]; e = rowptr_t[n + 1];
     insertion_sort(col_t + b, e - b);
     for (int p = b; p < e; ++p) col_t[p] = (int32_t)ei[E + col_t[p]];   // destination of the out-edge
+    if (nbr_t) {   // the same fixed-width table for the transposed (out-edge) rows: destination << 4, no attribute
+      const bool fits = (e - b <= 8) && N < (1ll << 28);
+      uint32_t w[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) w[k] = (fits && b + k < e) ? ((uint32_t)col_t[b + k] << 4) : 0xFFFFFFFFu;
+      if (!fits) w[0] = 0xFFFFFFFEu;
+      uint4* dst = reinterpret_cast<uint4*>(nbr_t + 8 * n);
+      dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
   }
   const bool sorted = (status[1] == 0);
   for (int64_t g = i; g < G; g += stride) {
@@ -197,7 +207,7 @@ extern "C" size_t molclr_plan_workspace_bytes(int64_t N, int64_t E, int64_t G) {
 extern "C" int molclr_plan_build(const int64_t* x, const int64_t* edge_index, const int64_t* edge_attr,
                                  const int64_t* batch, int64_t N, int64_t E, int64_t G, int32_t* xpacked,
                                  int32_t* node2graph, int32_t* rowptr, int32_t* col, uint8_t* eattr,
-                                 int32_t* rowptr_t, int32_t* col_t, float* cnt, uint32_t* nbr, int32_t* gptr,
+                                 int32_t* rowptr_t, int32_t* col_t, float* cnt, uint32_t* nbr, uint32_t* nbr_t, int32_t* gptr,
                                  int32_t* gperm, void* workspace, size_t workspace_bytes, int32_t* status,
                                  cudaStream_t stream) {
   MOLCLR_REQUIRE(N >= 0 && E >= 0 && G >= 0, "plan_build: negative size");
@@ -237,7 +247,7 @@ extern "C" int molclr_plan_build(const int64_t* x, const int64_t* edge_index, co
   int blocks2 = (int)((work2 + threads - 1) / threads);
   blocks2 = blocks2 < 1 ? 1 : blocks2;
   plan_rows_kernel<<<blocks2, threads, 0, stream>>>(edge_index, edge_attr, N, E, G, rowptr, rowptr_t, gptr,
-                                                    col, eattr, col_t, cnt, nbr, gperm, status);
+                                                    col, eattr, col_t, cnt, nbr, nbr_t, gperm, status);
   MOLCLR_CHECK_LAUNCH("plan_rows");
   return 0;
 }

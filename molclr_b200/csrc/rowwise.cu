@@ -500,6 +500,126 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_bwd_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
+// GINE aggregation backward, shared-memory tile variant: the transposed gather over the same ring of staged tiles as the
+// forward kernel (tiles of g_a rows + the fixed-width OUT-edge table nbr_t of the plan), thread = (row slot, float4 chunk).
+// Sums run in the order of the warp-per-row kernel (self first, then out-edges in pairs), so gy is bitwise identical to it;
+// the BatchNorm statistics partials are reduced over the row slots of a CTA in slot order (deterministic).
+// ------------------------------------------------------------------------------------------------
+template <int MODE, bool DROP>
+__global__ void __launch_bounds__(kTileThreads, 1) gine_aggregate_bwd_tile_kernel(
+    const float* __restrict__ ga, const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ col_t,
+    const uint32_t* __restrict__ nbr_t, const float* __restrict__ z, const float* __restrict__ coef, int relu, int N, int D, int T,
+    int n_stages, float* __restrict__ gy, float* __restrict__ partials, int round_out, const DropCfg drop) {
+  extern __shared__ float4 sm4[];
+  const int D4 = D >> 2;
+  float4* feat = sm4;                                                // [stages][T][D4]   (reused for the final reduction)
+  uint32_t* nb = reinterpret_cast<uint32_t*>(feat + (size_t)n_stages * T * D4);   // [stages][T][8]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(nb + (size_t)n_stages * T * 8);
+  uint64_t* empty_bar = full_bar + kTileMaxStages;
+  const int R = kTileConsumers / D4;
+  const int n_active = R * D4, n_active_warps = (n_active + 31) >> 5;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < n_stages; ++s) { ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, n_active_warps); }
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int ntiles = (N + T - 1) / T;
+  const bool active = tid < n_active;
+  const int slot = active ? tid / D4 : 0, q = active ? tid - slot * D4 : 0;
+  float4 s1 = f4_zero(), s2 = f4_zero();
+  if (tid >= kTileConsumers) {
+    // ---------------------------------------------------------------- producer
+    if (lane == 0) {
+      int k = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++k) {
+        const int s = k % n_stages;
+        ptx::mbar_wait(empty_bar + s, ((k / n_stages) & 1) ^ 1);
+        const int t0 = t * T, rows = min(T, N - t0);
+        ptx::mbar_arrive_expect_tx(full_bar + s, (uint32_t)rows * (uint32_t)(D * 4 + 32));
+        ptx::bulk_load_1d(feat + (size_t)s * T * D4, ga + (size_t)t0 * D, (uint32_t)rows * (uint32_t)(D * 4), full_bar + s);
+        ptx::bulk_load_1d(nb + (size_t)s * T * 8, nbr_t + (size_t)t0 * 8, (uint32_t)rows * 32u, full_bar + s);
+      }
+    }
+  } else if ((tid & ~31) < n_active) {
+    // ------------------------------------------------------------------ consumers
+    float4 sc = f4_zero(), sh = f4_zero(), mean = f4_zero(), istd = f4_zero();
+    if (MODE == 1) { sc = ldg_f4(coef + 4 * q); sh = ldg_f4(coef + D + 4 * q); mean = ldg_f4(coef + 2 * D + 4 * q); istd = ldg_f4(coef + 3 * D + 4 * q); }
+    int k = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++k) {
+      const int s = k % n_stages;
+      const int t0 = t * T, rows = min(T, N - t0);
+      const float4* ft_q = feat + (size_t)s * T * D4 + q;
+      const uint32_t* nt = nb + (size_t)s * T * 8;
+      ptx::mbar_wait(full_bar + s, (k / n_stages) & 1);
+      if (active) {
+        for (int r = slot; r < rows; r += R) {
+          const int i = t0 + r;
+          float4 zv = f4_zero();
+          if (MODE == 1) zv = ld_stream_f4(z + (size_t)i * D + 4 * q);
+          auto fetch = [&](uint32_t w) -> float4 {
+            const int didx = (int)(w >> 4);
+            const unsigned rel = (unsigned)(didx - t0);
+            return rel < (unsigned)rows ? ft_q[rel * D4] : ldg_f4(ga + (size_t)didx * D + 4 * q);
+          };
+          float4 acc = ft_q[r * D4];                                     // self loop first (as the warp-per-row kernel)
+          const uint4 wa = *reinterpret_cast<const uint4*>(nt + r * 8);
+          if (wa.x < kNbrLong) {
+            acc = f4_add2(acc, f4_add2(fetch(wa.x), wa.y < kNbrLong ? fetch(wa.y) : f4_zero()));
+            if (wa.y < kNbrLong && wa.z < kNbrLong) {
+              acc = f4_add2(acc, f4_add2(fetch(wa.z), wa.w < kNbrLong ? fetch(wa.w) : f4_zero()));
+              if (wa.w < kNbrLong) {
+                const uint4 wb = *reinterpret_cast<const uint4*>(nt + r * 8 + 4);
+                if (wb.x < kNbrLong) {
+                  acc = f4_add2(acc, f4_add2(fetch(wb.x), wb.y < kNbrLong ? fetch(wb.y) : f4_zero()));
+                  if (wb.y < kNbrLong && wb.z < kNbrLong)
+                    acc = f4_add2(acc, f4_add2(fetch(wb.z), wb.w < kNbrLong ? fetch(wb.w) : f4_zero()));
+                }
+              }
+            }
+          } else if (wa.x == kNbrLong) {                                 // more than 8 out-edges: walk the CSR row, in pairs
+            const int beg = __ldg(rowptr_t + i), end = __ldg(rowptr_t + i + 1);
+            for (int e = beg; e < end; e += 2) {
+              const float4 v0 = fetch((uint32_t)__ldg(col_t + e) << 4);
+              const float4 v1 = (e + 1 < end) ? fetch((uint32_t)__ldg(col_t + e + 1) << 4) : f4_zero();
+              acc = f4_add2(acc, f4_add2(v0, v1));
+            }
+          }
+          float4 rr = acc;
+          if (MODE == 1) {
+            if (relu) {
+              if (!(fmaf(zv.x, sc.x, sh.x) > 0.f)) rr.x = 0.f;
+              if (!(fmaf(zv.y, sc.y, sh.y) > 0.f)) rr.y = 0.f;
+              if (!(fmaf(zv.z, sc.z, sh.z) > 0.f)) rr.z = 0.f;
+              if (!(fmaf(zv.w, sc.w, sh.w) > 0.f)) rr.w = 0.f;
+            }
+            if (DROP) rr = f4_mul(rr, drop_mask4(drop, i, q, D4));
+            s1 = f4_add(s1, rr);
+            s2.x = fmaf(rr.x, (zv.x - mean.x) * istd.x, s2.x); s2.y = fmaf(rr.y, (zv.y - mean.y) * istd.y, s2.y);
+            s2.z = fmaf(rr.z, (zv.z - mean.z) * istd.z, s2.z); s2.w = fmaf(rr.w, (zv.w - mean.w) * istd.w, s2.w);
+          }
+          st_f4(gy + (size_t)i * D + 4 * q, round_out ? f4_tf32(rr) : rr);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(empty_bar + s);
+    }
+  }
+  if (MODE == 1) {
+    // block partial of the BatchNorm statistics: row slots summed in slot order, through the (now idle) ring memory
+    __syncthreads();
+    float4* red = feat;                                               // [R][2][D4]
+    if (active) { red[(slot * 2 + 0) * D4 + q] = s1; red[(slot * 2 + 1) * D4 + q] = s2; }
+    __syncthreads();
+    for (int e = tid; e < 2 * D4; e += blockDim.x) {
+      float4 a = red[e];
+      for (int sl = 1; sl < R; ++sl) a = f4_add(a, red[sl * 2 * D4 + e]);
+      st_f4(partials + (size_t)blockIdx.x * 2 * D + 4 * e, a);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Deterministic reduction of partial rows:  out[c] (+)= scale * sum_p partials[p][c], p in order.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ partials, int P, int len,
@@ -1148,13 +1268,40 @@ static int launch_bwd_fused(const float* ga, const int32_t* rowptr_t, const int3
   return grid;
 }
 
-static int aggregate_bwd_launch(const float* ga, const int32_t* rowptr_t, const int32_t* col_t, bool gather, const float* z_prev,
-                                const float* bn_coef, int relu, int64_t N, int D, float* gy, int round_out, float* partials,
-                                int* num_partials, const DropCfg drop, cudaStream_t stream) {
+template <int MODE, bool DROP>
+static int launch_bwd_tile(const float* ga, const int32_t* rowptr_t, const int32_t* col_t, const uint32_t* nbr_t, const float* z_prev,
+                           const float* bn_coef, int relu, int64_t N, int D, float* gy, float* partials, int round_out,
+                           const DropCfg& drop, cudaStream_t stream) {
+  auto k = gine_aggregate_bwd_tile_kernel<MODE, DROP>;
+  const int stages = g_tile_stages < 2 ? 2 : (g_tile_stages > kTileMaxStages ? kTileMaxStages : g_tile_stages);
+  const int T = aggregate_tile_rows(D, stages);
+  const size_t smem = aggregate_tile_smem(D, T, stages);        // (sized with the forward kernel's table; only more than needed)
+  static bool attr_set = false;                      // per instantiation
+  if (!attr_set) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
+  const int64_t ntiles = (N + T - 1) / T;
+  const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+  k<<<grid, kTileThreads, smem, stream>>>(ga, rowptr_t, col_t, nbr_t, z_prev, bn_coef, relu, (int)N, D, T, stages, gy, partials, round_out, drop);
+  return grid;
+}
+
+static int aggregate_bwd_launch(const float* ga, const int32_t* rowptr_t, const int32_t* col_t, const uint32_t* nbr_t, bool gather,
+                                const float* z_prev, const float* bn_coef, int relu, int64_t N, int D, float* gy, int round_out,
+                                float* partials, int* num_partials, const DropCfg drop, cudaStream_t stream) {
   REQUIRE_D(D);
   if (num_partials) *num_partials = 0;
   if (N == 0) return 0;
   const int D4 = D / 4;
+  if (gather && nbr_t && g_aggregate_tile) {
+    MOLCLR_REQUIRE((reinterpret_cast<uintptr_t>(ga) & 15) == 0 && (reinterpret_cast<uintptr_t>(nbr_t) & 15) == 0,
+                   "aggregate_bwd: ga and nbr_t must be 16-byte aligned");
+    int grid;
+    if (z_prev && drop.thr) grid = launch_bwd_tile<1, true>(ga, rowptr_t, col_t, nbr_t, z_prev, bn_coef, relu, N, D, gy, partials, round_out, drop, stream);
+    else if (z_prev) grid = launch_bwd_tile<1, false>(ga, rowptr_t, col_t, nbr_t, z_prev, bn_coef, relu, N, D, gy, partials, round_out, drop, stream);
+    else grid = launch_bwd_tile<0, false>(ga, rowptr_t, col_t, nbr_t, nullptr, nullptr, 0, N, D, gy, nullptr, round_out, drop, stream);
+    if (num_partials && z_prev) *num_partials = grid;
+    MOLCLR_CHECK_LAUNCH("aggregate_bwd_tile");
+    return 0;
+  }
   NCH_DISPATCH(D4, {
     if (z_prev) {
       const size_t smem = (size_t)(4 + 2 * kRowWarps) * D * sizeof(float);
@@ -1175,11 +1322,12 @@ if (gather && drop.thr) grid = launch_bwd_fused<NCH, true, true>(ga, rowptr_t, c
   return 0;
 }
 
-extern "C" int molclr_gine_aggregate_bwd(const float* ga, const int32_t* rowptr_t, const int32_t* col_t, const float* z_prev,
-                                         const float* bn_coef, int relu, int64_t N, int D, float* gy, int round_tf32_out,
-                                         float* partials, int* num_partials, uint32_t drop_seed, float drop_p, cudaStream_t stream) {
+extern "C" int molclr_gine_aggregate_bwd(const float* ga, const int32_t* rowptr_t, const int32_t* col_t, const uint32_t* nbr_t,
+                                         const float* z_prev, const float* bn_coef, int relu, int64_t N, int D, float* gy,
+                                         int round_tf32_out, float* partials, int* num_partials, uint32_t drop_seed, float drop_p,
+                                         cudaStream_t stream) {
   MOLCLR_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "dropout probability %f not in [0, 1)", drop_p);
-  return aggregate_bwd_launch(ga, rowptr_t, col_t, true, z_prev, bn_coef, relu, N, D, gy, round_tf32_out, partials, num_partials,
+  return aggregate_bwd_launch(ga, rowptr_t, col_t, nbr_t, true, z_prev, bn_coef, relu, N, D, gy, round_tf32_out, partials, num_partials,
                               make_drop(drop_seed, z_prev ? drop_p : 0.f), stream);
 }
 
@@ -1187,7 +1335,7 @@ extern "C" int molclr_relu_bn_bwd_stats(const float* g, const float* z_prev, con
                                         float* gy, float* partials, int* num_partials, uint32_t drop_seed, float drop_p,
                                         cudaStream_t stream) {
   MOLCLR_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "dropout probability %f not in [0, 1)", drop_p);
-  return aggregate_bwd_launch(g, nullptr, nullptr, false, z_prev, bn_coef, relu, N, D, gy, 0, partials, num_partials,
+  return aggregate_bwd_launch(g, nullptr, nullptr, nullptr, false, z_prev, bn_coef, relu, N, D, gy, 0, partials, num_partials,
                               make_drop(drop_seed, drop_p), stream);
 }
 

@@ -22,7 +22,7 @@ def _al(n, a=4):
 class GraphPlan:
     """Device-resident int32 index structures for one batch (see include/molclr_b200.h: molclr_plan_build)."""
 
-    __slots__ = ("N", "E", "G", "xpacked", "node2graph", "rowptr", "col", "eattr", "rowptr_t", "col_t", "cnt", "nbr",
+    __slots__ = ("N", "E", "G", "xpacked", "node2graph", "rowptr", "col", "eattr", "rowptr_t", "col_t", "cnt", "nbr", "nbr_t",
                  "gptr", "gperm", "status", "_buf", "_checked")
 
     def __init__(self, data, validate=True):
@@ -41,14 +41,14 @@ class GraphPlan:
         lib = _lib.load()
         ws_bytes = lib.molclr_plan_workspace_bytes(N, E, G)
         # one allocation, carved into 16-byte aligned int32 views
-        sizes = [_al(N, 8), _al(N, 8), _al(N + 1, 8), _al(E, 8), _al((E + 3) // 4, 8), _al(N + 1, 8), _al(E, 8), _al(8 * N, 8), _al(G + 1, 8), _al(N, 8), _al(8 * N, 8),
+        sizes = [_al(N, 8), _al(N, 8), _al(N + 1, 8), _al(E, 8), _al((E + 3) // 4, 8), _al(N + 1, 8), _al(E, 8), _al(8 * N, 8), _al(G + 1, 8), _al(N, 8), _al(8 * N, 8), _al(8 * N, 8),
                  _al((ws_bytes + 3) // 4), 4]
         buf = torch.empty(sum(sizes), dtype=torch.int32, device=x.device)
         views, off = [], 0
         for s in sizes:
             views.append(buf[off:off + s]); off += s
         (self.xpacked, self.node2graph, self.rowptr, self.col, eattr32, self.rowptr_t, self.col_t, cnt32, self.gptr,
-         self.gperm, self.nbr, ws, self.status) = views
+         self.gperm, self.nbr, self.nbr_t, ws, self.status) = views
         self.eattr = eattr32.view(torch.uint8)
         self.cnt = cnt32.view(torch.float32)
         self._buf = buf
@@ -56,7 +56,7 @@ class GraphPlan:
         check(lib.molclr_plan_build(ptr(x, torch.int64), ptr(ei, torch.int64), ptr(ea, torch.int64), ptr(batch, torch.int64),
                                     N, E, G, ptr(self.xpacked, torch.int32), ptr(self.node2graph, torch.int32),
                                     ptr(self.rowptr, torch.int32), ptr(self.col, torch.int32), ptr(self.eattr, torch.uint8),
-                                    ptr(self.rowptr_t, torch.int32), ptr(self.col_t, torch.int32), ptr(self.cnt), ptr(self.nbr, torch.int32),
+                                    ptr(self.rowptr_t, torch.int32), ptr(self.col_t, torch.int32), ptr(self.cnt), ptr(self.nbr, torch.int32), ptr(self.nbr_t, torch.int32),
                                     ptr(self.gptr, torch.int32), ptr(self.gperm, torch.int32), ptr(ws, torch.int32), ws_bytes,
                                     ptr(self.status, torch.int32), stream()), "plan_build")
         self._checked = False

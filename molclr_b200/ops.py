@@ -146,14 +146,15 @@ def gine_aggregate_fwd(plan, src, B1, B2, bn_coef=None, relu=True, round_out=Tru
     return (out, lo) if want_lo else out
 
 
-def gine_aggregate_bwd(plan, ga, z_prev=None, bn_coef=None, relu=True, round_out=False, drop=(0, 0.0)):
-    """Returns (gy, partials, P): partials/P are None/0 when z_prev is None."""
+def gine_aggregate_bwd(plan, ga, z_prev=None, bn_coef=None, relu=True, round_out=False, drop=(0, 0.0), use_nbr=True):
+    """Returns (gy, partials, P): partials/P are None/0 when z_prev is None.  use_nbr=False withholds the out-edge table, which
+    selects the warp-per-row CSR kernel instead of the shared-memory tile kernel."""
     D = ga.shape[1]
     gy = torch.empty_like(ga)
     partials = _empty(max_blocks(), 2, D, device=ga.device) if z_prev is not None else None
     n = C.c_int(0)
     check(_lib.load().molclr_gine_aggregate_bwd(ptr(ga), ptr(plan.rowptr_t, torch.int32), ptr(plan.col_t, torch.int32),
-                                                ptr(z_prev), ptr(bn_coef), int(relu), plan.N, D, ptr(gy), int(round_out),
+                                                ptr(plan.nbr_t if use_nbr else None, torch.int32), ptr(z_prev), ptr(bn_coef), int(relu), plan.N, D, ptr(gy), int(round_out),
                                                 ptr(partials), C.byref(n), drop[0], drop[1], stream()), "gine_aggregate_bwd")
     return gy, partials, n.value
 

@@ -56,6 +56,31 @@ def _nbr_table(csr, N):
 
 
 @pytest.mark.parametrize("D,drop", [(300, 0.0), (300, 0.3), (512, 0.0), (64, 0.0)])
+def test_aggregate_bwd_tile_kernel_equals_row_kernel(D, drop):
+    """Backward: gy of the tile kernel (out-edge table given) is bitwise the warp-per-row kernel's; the BatchNorm statistics
+    partials are summed in a different (fixed) order, so their totals agree to fp32 rounding."""
+    from tests.test_gpu_properties import _random_batch
+    g = torch.Generator().manual_seed(D + 7)
+    coef = torch.randn(4, D, generator=g)
+    coef[0] = coef[0].abs() + 0.5; coef[3] = coef[3].abs() + 0.5
+    for b in (make_pair_batch(200, seed=6)[0], _random_batch(np.random.default_rng(4), 30, 70), make_plain_batch(1, seed=2)):
+        plan = GraphPlan(b.to(DEV))
+        want = build_csr(b.edge_index.numpy(), b.edge_attr.numpy(), b.num_nodes)
+        nt = plan.nbr_t[:8 * plan.N].cpu().numpy().view(np.uint32).reshape(-1, 8)
+        assert np.array_equal(nt, _nbr_table({"rowptr": want["rowptr_t"], "col": want["col_t"], "eattr": np.zeros_like(want["col_t"])}, plan.N))
+        ga, z = torch.randn(plan.N, D, generator=g).to(DEV), torch.randn(plan.N, D, generator=g).to(DEV)
+        a, _, _ = ops.gine_aggregate_bwd(plan, ga)
+        r, _, _ = ops.gine_aggregate_bwd(plan, ga, use_nbr=False)
+        assert torch.equal(a, r)
+        dp = (77, drop)
+        a, pa, na = ops.gine_aggregate_bwd(plan, ga, z_prev=z, bn_coef=coef.to(DEV), drop=dp, round_out=True)
+        r, pr, nr = ops.gine_aggregate_bwd(plan, ga, z_prev=z, bn_coef=coef.to(DEV), drop=dp, round_out=True, use_nbr=False)
+        assert torch.equal(a, r)
+        sa, sr = pa[:na].double().sum(0), pr[:nr].double().sum(0)
+        assert rel_err(sa, sr) < 1e-5, rel_err(sa, sr)
+
+
+@pytest.mark.parametrize("D,drop", [(300, 0.0), (300, 0.3), (512, 0.0), (64, 0.0)])
 def test_aggregate_tile_kernel_equals_row_kernel(D, drop):
     """The shared-memory tile kernel (neighbour table given) and the warp-per-row CSR kernel compute the same sums in the same
     order: bitwise equal outputs, with and without the fused BatchNorm/ReLU/dropout, on molecules and on irregular graphs

@@ -53,6 +53,9 @@ report("aggregate fwd (layer 0, fp32 out, row kernel)", timeit(lambda k: ops.gin
 report("aggregate fwd (layer 0, hi+lo out)", timeit(lambda k: ops.gine_aggregate_fwd(plan, srcs[k % 3], B1, B2, want_lo=True)), 4 * D * N * 3 + idx)
 report("aggregate bwd (ReLU/BN stats fused)", timeit(lambda k: ops.gine_aggregate_bwd(plan, srcs[k % 3], z_prev=srcs[(k + 1) % 3], bn_coef=coef)),
        4 * D * N * 3 + 4 * (N + 1) + 4 * E)
+report("aggregate bwd (ReLU/BN stats fused, row kernel)", timeit(lambda k: ops.gine_aggregate_bwd(plan, srcs[k % 3], z_prev=srcs[(k + 1) % 3], bn_coef=coef, use_nbr=False)),
+       4 * D * N * 3 + 4 * (N + 1) + 4 * E)
+report("aggregate bwd (plain, row kernel)", timeit(lambda k: ops.gine_aggregate_bwd(plan, srcs[k % 3], use_nbr=False)), 4 * D * N * 2 + 4 * (N + 1) + 4 * E)
 report("aggregate bwd (plain)", timeit(lambda k: ops.gine_aggregate_bwd(plan, srcs[k % 3])), 4 * D * N * 2 + 4 * (N + 1) + 4 * E)
 bc = torch.randn(3, D).to(dev)
 report("bn_bwd_apply", timeit(lambda k: ops.bn_bwd_apply(srcs[k % 3], bc, gy=srcs[(k + 1) % 3])), 4 * D * N * 3)
