@@ -627,18 +627,8 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __re
   __shared__ float red[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  if (c < len) {
-    // four independent partial sums (rows p, p + 32, p + 64, p + 96 of this thread's stride) keep four loads in flight;
-    // the order is fixed, so the result is deterministic
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int p = threadIdx.y;
-    for (; p + 96 < P; p += 128) {
-      s0 += partials[(size_t)p * len + c]; s1 += partials[(size_t)(p + 32) * len + c];
-      s2 += partials[(size_t)(p + 64) * len + c]; s3 += partials[(size_t)(p + 96) * len + c];
-    }
-    for (; p < P; p += 32) s0 += partials[(size_t)p * len + c];
-    s = (s0 + s1) + (s2 + s3);
-  }
+  if (c < len)
+    for (int p = threadIdx.y; p < P; p += 32) s += partials[(size_t)p * len + c];
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && c < len) {
