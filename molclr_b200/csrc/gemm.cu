@@ -230,21 +230,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int kb0 = (t / (n_tiles * m_tiles)) * p.kb_per_split;
         const int nkb_seg = min(p.num_kb, kb0 + p.kb_per_split) - kb0;
         const int nkb = FOUR ? nkb_seg : nkb_seg * p.segments;
-        // L2 prefetch of the streamed operand (K-major A: first touched here, from HBM) `pf` K blocks ahead, running into the
-        // worker's next tile: with the 64-72 KB stages of the compensated product only three stages fit, and the HBM latency of
-        // each TMA load would otherwise sit on the critical path of a three-deep ring
-        const int pf = (!p.a_mn && !p.atomic_out) ? p.prefetch : 0;
-        const int tn = t + num_workers;
-        const int m0n = tn < total ? ((tn / n_tiles) % m_tiles) * TILE_M + (int)rank * GEMM_BM : -1;
-        const bool next_new_rows = m0n >= 0 && m0n != m0;       // (the other column tiles of the same rows hit L2 anyway)
-        if (pf && t == worker)
-          for (int i = 0; i < min(pf, nkb_seg); ++i) ptx::tma_prefetch_2d(&tmA, (kb0 + i) * Cfg::BK, m0);
         for (int i = 0; i < nkb; ++i, ++it) {
-          if (pf) {
-            const int ib = (FOUR ? i : i % nkb_seg) + pf;
-            if (ib < nkb_seg) ptx::tma_prefetch_2d(&tmA, (kb0 + ib) * Cfg::BK, m0);
-            else if (next_new_rows && ib - nkb_seg < min(pf, nkb_seg)) ptx::tma_prefetch_2d(&tmA, (ib - nkb_seg) * Cfg::BK, m0n);
-          }
           const int s = it % Cfg::STAGES;
           ptx::mbar_wait(empty_bar + s, ((it / Cfg::STAGES) & 1) ^ 1);
           // derive_lo: the fp32 A tile goes to a CTA-local barrier (the converter warps of THIS CTA consume it) and no A_lo is loaded
@@ -881,8 +867,6 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;          // no empty split
   p.atomic_out = atomic ? 1 : 0;
   p.debug = gemm_debug_flags();
-  static const int prefetch_kb = [] { const char* e = getenv("MOLCLR_GEMM_PREFETCH"); return e ? atoi(e) : 0; }();
-  p.prefetch = prefetch_kb;
   // split-K weight gradients stay on single CTAs: their 300/600-wide outputs pad badly to 256-row pair tiles (MMA-bound)
   const bool wide = atomic && job.wide && gemm_pair() && !gemm_impl_simt();
   if (wide) MOLCLR_REQUIRE(p.a_mn && p.b_mn, "gemm: wide split-K tiles need both operands MN-major");

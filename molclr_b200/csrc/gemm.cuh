@@ -26,7 +26,6 @@ struct GemmParams {
   float* colstat; int colstat_mode;
   int stat_groups;             // number of 32-row groups the colstat buffer holds (filled by the launcher)
   int atomic_out;
-  int prefetch;                // K blocks of the (K-major) A operand to prefetch into L2 ahead of the TMA loads (0 = off)
   int debug;                   // MOLCLR_GEMM_DEBUG bit 0: skip the generic epilogue (timing experiments only)
   float alpha;                 // out = alpha * acc (+ bias + addend ...)
   // ---- NT-Xent epilogues (nt_xent.py:47-65); logits l = acc * inv_tau
