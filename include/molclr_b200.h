@@ -261,15 +261,19 @@ int molclr_l2_normalize_bwd(const float* gy, const float* y, const float* inv_no
  *   backward: g_rep[r] = (gscale/tau) * sum_k (P[r][k] + P[k][r] - 2*[k = pos(r)]) * cols[k],
  *             P[i][k] = exp(S[i][k]/tau - lse[i]) for k != i; col_lse[Rc] holds the log-sum-exp of every
  *             candidate row (== row_lse on one GPU, all-gathered for global negatives); gscale = 1/Rc.
- * The Rc x Rc similarity matrix is never written to memory: backward works in L2-resident stripes of
- * 2048 candidate columns; per-stripe partial gradients are summed in stripe order.  Requires R even, Rc % 4 == 0, C % 4 == 0. */
+ * The Rc x Rc similarity matrix is never written to memory: backward works in L2-resident stripes of candidate columns
+ * (64 MB at R = 8192); per-stripe partial gradients are summed in stripe order.  Requires R even, Rc % 4 == 0, C % 4 == 0.
+ * unit_rows != 0 promises that every row of rep and cols has norm <= 1 (the cosine similarity of nt_xent.py:40-45, rows
+ * normalised by the caller): the tensor-core passes then run on FP16 copies of the rows (the 11-bit significand of TF32,
+ * fp32 accumulation, twice the tensor rate; the softmax weights are staged as fp16 x 2^10).  unit_rows == 0 (dot similarity, nt_xent.py:32-38, rows of
+ * any magnitude): TF32 operands, fp32 weights. */
 size_t molclr_ntxent_workspace_bytes(int64_t R, int64_t Rc, int C);
 int molclr_ntxent_fwd(const float* rep, const float* cols, int64_t R, int64_t Rc, int C, int64_t row_offset,
-                      int64_t row_offset2, float inv_temperature, float* row_lse, float* row_pos, float* loss /* [1], optional */,
-                      void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                      int64_t row_offset2, float inv_temperature, int unit_rows, float* row_lse, float* row_pos,
+                      float* loss /* [1], optional */, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int molclr_ntxent_bwd(const float* rep, const float* cols, int64_t R, int64_t Rc, int C, int64_t row_offset,
-                      int64_t row_offset2, float inv_temperature, const float* row_lse, const float* col_lse, float gscale, float* g_rep,
-                      void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                      int64_t row_offset2, float inv_temperature, int unit_rows, const float* row_lse, const float* col_lse, float gscale,
+                      float* g_rep, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -81,8 +81,8 @@ SIGNATURES = {
     "molclr_l2_normalize_fwd": (i32, [vp, i64, i32, f32, vp, vp, vp]),
     "molclr_l2_normalize_bwd": (i32, [vp, vp, vp, i64, i32, f32, vp, vp]),
     "molclr_ntxent_workspace_bytes": (sz, [i64, i64, i32]),
-    "molclr_ntxent_fwd": (i32, [vp, vp, i64, i64, i32, i64, i64, f32, vp, vp, vp, vp, sz, vp]),
-    "molclr_ntxent_bwd": (i32, [vp, vp, i64, i64, i32, i64, i64, f32, vp, vp, f32, vp, vp, sz, vp]),
+    "molclr_ntxent_fwd": (i32, [vp, vp, i64, i64, i32, i64, i64, f32, i32, vp, vp, vp, vp, sz, vp]),
+    "molclr_ntxent_bwd": (i32, [vp, vp, i64, i64, i32, i64, i64, f32, i32, vp, vp, f32, vp, vp, sz, vp]),
 }
 
 _lib = None

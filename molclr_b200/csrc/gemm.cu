@@ -15,6 +15,7 @@
 // A scalar-FMA kernel with the same argument struct (MOLCLR_GEMM_IMPL=simt) exists for debugging
 // the tensor-core path on the GPU; it is never selected implicitly.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdlib>
 #include <cstring>
 
@@ -244,7 +245,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
           uint8_t* b_dst = a_dst + (FOUR ? 2 : 1) * Cfg::A_BYTES;
           const int seg = FOUR ? 0 : i / nkb_seg;
-          const int kc = (kb0 + (i - seg * nkb_seg)) * Cfg::BK;
+          const int kc = (kb0 + (i - seg * nkb_seg)) * (p.half16 ? 2 * Cfg::BK : Cfg::BK);   // fp16: 64 elements per 128-byte tile row
 #pragma unroll
           for (int h = 0; h < (FOUR ? 2 : 1); ++h) {
             const CUtensorMap* ma = (FOUR ? h == 1 : seg == 1) ? &tmA2 : &tmA;
@@ -279,11 +280,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0 && rank == 0) {
-      const uint32_t idesc = ptx::make_idesc_tf32(Cfg::N1, p.a_mn != 0, p.b_mn != 0, TILE_M);
+      // fp16 operands (K-major): the same 128-byte-row tiles and descriptors, K = 16 (32 bytes) per kind::f16 instruction
+      const bool h16 = !FOUR && p.half16 != 0;
+      const uint32_t idesc = h16 ? ptx::make_idesc_f16(Cfg::N1, TILE_M) : ptx::make_idesc_tf32(Cfg::N1, p.a_mn != 0, p.b_mn != 0, TILE_M);
       const uint32_t idesc2 = ptx::make_idesc_tf32(Cfg::N2 > 0 ? Cfg::N2 : 16, p.a_mn != 0, p.b_mn != 0, TILE_M);
       const uint32_t idesc16 = ptx::make_idesc_bf16(Cfg::N1, TILE_M);
       auto mma_i = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
-        if (TWO) ptx::mma_tf32_ss_2cta(d, a, b, id, acc); else ptx::mma_tf32_ss(d, a, b, id, acc);
+        if (h16) { if (TWO) ptx::mma_f16_ss_2cta(d, a, b, id, acc); else ptx::mma_f16_ss(d, a, b, id, acc); }
+        else if (TWO) ptx::mma_tf32_ss_2cta(d, a, b, id, acc); else ptx::mma_tf32_ss(d, a, b, id, acc);
       };
       auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) { mma_i(d, a, b, idesc, acc); };
       auto commit = [&](uint64_t* bar) { if (TWO) ptx::mma_commit_2cta(bar); else ptx::mma_commit(bar); };
@@ -449,9 +453,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           bias_s[(tl & 1) * 256 + e] = (n0 + e < p.N) ? __ldg(p.bias + n0 + e) : 0.f;
         ptx::named_bar_sync(1, Cfg::EPI_WARPS * 32);
       }
+      float nlr = 0.f;                  // K_NTX_W, fp16 output: 10 - log2e * (log-sum-exp of this thread's row)
       if (KIND == K_NTX_W) {            // the candidates' log-sum-exps of this column tile, pre-scaled for ex2
-        for (int e = threadIdx.x - 64; e < BN; e += Cfg::EPI_WARPS * 32)
-          bias_s[(tl & 1) * 256 + e] = (n0 + e < p.N) ? __ldg(p.col_lse + p.col_offset + n0 + e) * 1.4426950408889634f : 0.f;
+        // (fp16 output: negated and shifted by 10, so that ex2(fma(s, k2, .)) is the softmax weight times 2^10)
+        const bool w16 = p.out16 != nullptr;
+        for (int e = threadIdx.x - 64; e < BN; e += Cfg::EPI_WARPS * 32) {
+          const float l2 = (n0 + e < p.N) ? __ldg(p.col_lse + p.col_offset + n0 + e) * 1.4426950408889634f : 0.f;
+          bias_s[(tl & 1) * 256 + e] = w16 ? 10.f - l2 : l2;
+        }
+        if (w16) nlr = 10.f - (grow < p.M ? __ldg(p.row_lse + grow) : 0.f) * 1.4426950408889634f;
         ptx::named_bar_sync(1, Cfg::EPI_WARPS * 32);
       }
       ptx::mbar_wait(tfull_bar + buf, (tl >> 1) & 1);
@@ -460,38 +470,139 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (KIND == K_NTX_FWD) {
         // per-row (max, sum exp) of this warp's share of the column tile, own column masked; thread <-> row straight
         // from TMEM, one pass with a running maximum.  Partials are indexed [n_tile * NSHARE + half][row].
+        // 32 columns per step, the next step's TMEM loads in flight while this one is reduced; per element the loop costs
+        // FMNMX + FFMA + EX2 + FADD: the self column and the positive are looked for only in the blocks that hold them.
         const long long gr = grow < p.row_split ? grow + p.row_offset : grow - p.row_split + p.row_offset2;
         long long pos = gr + p.num_cand / 2;
         if (pos >= p.num_cand) pos -= p.num_cand;
         const float k2 = p.inv_tau * 1.4426950408889634f;            // logits in base-2 units
         float mx = -INFINITY, sum = 0.f;
-        for (int c0 = 16 * half; c0 < BN && n0 + c0 < p.N; c0 += 16 * NSHARE) {
-          float v[16];
-          ptx::tmem_ld_x16(taddr + c0, v);
-          const long long gc0 = n0 + c0 + p.col_offset;
-          float cm = -INFINITY;
+        constexpr int NBLK = (BN / 32 + NSHARE - 1) / NSHARE;        // 32-column blocks of this warp: c0 = 32 (half + b NSHARE)
+        auto blk_c0 = [&](int b) { return 32 * (half + b * NSHARE); };
+        auto blk_ok = [&](int b) { return blk_c0(b) < BN && n0 + blk_c0(b) < p.N; };
+        auto blk_load = [&](int b, float (&v)[32]) {
+          ptx::tmem_ld_x16_nowait(taddr + blk_c0(b), v);
+          ptx::tmem_ld_x16_nowait(taddr + blk_c0(b) + 16, v + 16);
+        };
+        auto blk_reduce = [&](int b, float (&v)[32]) {
+          const int c0 = blk_c0(b), nvalid = p.N - n0 - c0;           // > 0
+          const long long gc0 = (long long)n0 + c0 + p.col_offset;
+          const unsigned long long d_self = (unsigned long long)(gr - gc0), d_pos = (unsigned long long)(pos - gc0);
+          if (nvalid < 32) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const bool ok = (n0 + c0 + j < p.N) && (gc0 + j != gr);
-            v[j] = ok ? v[j] * k2 : -INFINITY;
-            cm = fmaxf(cm, v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = j < nvalid ? v[j] : -INFINITY;
           }
-          if (pos >= gc0 && pos < gc0 + 16 && grow < p.M) {
+          if (d_pos < 32ull && grow < p.M) {
+            const int dp = (int)d_pos;
+            float pv = 0.f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) if (gc0 + j == pos) p.row_pos[grow] = v[j] * 0.6931471805599453f;
+            for (int j = 0; j < 32; ++j) pv = j == dp ? v[j] : pv;
+            p.row_pos[grow] = pv * p.inv_tau;
           }
-          const float nm = fmaxf(mx, cm);
+          if (d_self < 32ull) {
+            const int ds = (int)d_self;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = j == ds ? -INFINITY : v[j];
+          }
+          float cm0 = fmaxf(v[0], v[1]), cm1 = fmaxf(v[2], v[3]);
+#pragma unroll
+          for (int j = 4; j < 32; j += 2) { cm0 = fmaxf(cm0, v[j]); cm1 = fmaxf(cm1, v[j + 1]); }
+          const float nm = fmaxf(mx, fmaxf(cm0, cm1) * k2);
           if (nm > -INFINITY) {
-            float cs = 0.f;
+            float cs0 = 0.f, cs1 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) cs += exp2f(v[j] - nm);
-            sum = sum * exp2f(mx - nm) + cs;
+            for (int j = 0; j < 32; j += 2) { cs0 += ptx::ex2_approx(fmaf(v[j], k2, -nm)); cs1 += ptx::ex2_approx(fmaf(v[j + 1], k2, -nm)); }
+            sum = fmaf(sum, ptx::ex2_approx(mx - nm), cs0 + cs1);
             mx = nm;
           }
+        };
+        float va[32], vb[32];
+        if (blk_ok(0)) blk_load(0, va);
+#pragma unroll
+        for (int b = 0; b < NBLK; b += 2) {
+          if (!blk_ok(b)) break;
+          ptx::tmem_ld_wait_dep(va);
+          if (b + 1 < NBLK && blk_ok(b + 1)) blk_load(b + 1, vb);
+          blk_reduce(b, va);
+          if (b + 1 >= NBLK || !blk_ok(b + 1)) break;
+          ptx::tmem_ld_wait_dep(vb);
+          if (b + 2 < NBLK && blk_ok(b + 2)) blk_load(b + 2, va);
+          blk_reduce(b + 1, vb);
         }
         if (grow < p.M) {                                           // natural-log units for the merge kernel
           p.part_max[((size_t)n_tile * NSHARE + half) * p.M + grow] = mx * 0.6931471805599453f;
           p.part_sum[((size_t)n_tile * NSHARE + half) * p.M + grow] = sum;
+        }
+      } else if (KIND == K_NTX_W && p.out16 != nullptr) {
+        // Softmax-weight tile W[r][k] = P[r][k] + P[k][r] - 2 [k == pos(r)]  (nt_xent.py:53-65 differentiated) written as fp16,
+        // scaled by 2^10 (weights are <= 2; the scale keeps the ~1/Rc entries out of the fp16 subnormals), for the fp16 dZ GEMM.
+        // 32 columns per step (next step's TMEM loads in flight), thread = row; per element 2 FFMA + 2 EX2 + FADD + half a CVT.
+        const long long gr = grow < p.row_split ? grow + p.row_offset : grow - p.row_split + p.row_offset2;
+        long long pos = gr + p.num_cand / 2;
+        if (pos >= p.num_cand) pos -= p.num_cand;
+        const float k2 = p.inv_tau * 1.4426950408889634f;
+        constexpr int NBLK = (BN / 32 + NSHARE - 1) / NSHARE;
+        uint8_t* stg8 = reinterpret_cast<uint8_t*>(stg);             // 32 rows x 64 bytes, 16-byte chunk j of row r at j ^ ((r >> 1) & 3)
+        __half* out16 = reinterpret_cast<__half*>(p.out16);
+        auto blk_c0 = [&](int b) { return 32 * (half + b * NSHARE); };
+        auto blk_ok = [&](int b) { return blk_c0(b) < BN && n0 + blk_c0(b) < p.N; };
+        auto blk_load = [&](int b, float (&v)[32]) {
+          ptx::tmem_ld_x16_nowait(taddr + blk_c0(b), v);
+          ptx::tmem_ld_x16_nowait(taddr + blk_c0(b) + 16, v + 16);
+        };
+        auto blk_emit = [&](int b, float (&v)[32]) {
+          const int c0 = blk_c0(b);
+          const long long gc0 = (long long)n0 + c0 + p.col_offset;
+          const unsigned long long d_self = (unsigned long long)(gr - gc0), d_pos = (unsigned long long)(pos - gc0);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 nlc = *reinterpret_cast<const float4*>(bias_t + c0 + j);     // broadcast
+            v[j] = ptx::ex2_approx(fmaf(v[j], k2, nlr)) + ptx::ex2_approx(fmaf(v[j], k2, nlc.x));
+            v[j + 1] = ptx::ex2_approx(fmaf(v[j + 1], k2, nlr)) + ptx::ex2_approx(fmaf(v[j + 1], k2, nlc.y));
+            v[j + 2] = ptx::ex2_approx(fmaf(v[j + 2], k2, nlr)) + ptx::ex2_approx(fmaf(v[j + 2], k2, nlc.z));
+            v[j + 3] = ptx::ex2_approx(fmaf(v[j + 3], k2, nlr)) + ptx::ex2_approx(fmaf(v[j + 3], k2, nlc.w));
+          }
+          if (d_self < 32ull) {
+            const int ds = (int)d_self;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = j == ds ? 0.f : v[j];
+          }
+          if (d_pos < 32ull) {
+            const int dp = (int)d_pos;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = j == dp ? v[j] - 2048.f : v[j];
+          }
+          uint32_t h[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const __half2 hh = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+            h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+          }
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            *reinterpret_cast<uint4*>(stg8 + lane * 64 + ((jj ^ ((lane >> 1) & 3)) << 4)) = make_uint4(h[4 * jj], h[4 * jj + 1], h[4 * jj + 2], h[4 * jj + 3]);
+          __syncwarp();
+          const int r_in = lane >> 2, ch = lane & 3, col = n0 + c0 + 8 * ch;
+#pragma unroll
+          for (int pass = 0; pass < 4; ++pass) {
+            const int r = pass * 8 + r_in;
+            const uint4 x = *reinterpret_cast<const uint4*>(stg8 + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4));
+            if (r < rows_w && col < p.N) *reinterpret_cast<uint4*>(out16 + (size_t)(m0 + q * 32 + r) * p.ldo16 + col) = x;
+          }
+          __syncwarp();
+        };
+        float va[32], vb[32];
+        if (blk_ok(0)) blk_load(0, va);
+#pragma unroll
+        for (int b = 0; b < NBLK; b += 2) {
+          if (!blk_ok(b)) break;
+          ptx::tmem_ld_wait_dep(va);
+          if (b + 1 < NBLK && blk_ok(b + 1)) blk_load(b + 1, vb);
+          blk_emit(b, va);
+          if (b + 1 >= NBLK || !blk_ok(b + 1)) break;
+          ptx::tmem_ld_wait_dep(vb);
+          if (b + 2 < NBLK && blk_ok(b + 2)) blk_load(b + 2, va);
+          blk_emit(b + 1, vb);
         }
       } else if (KIND == K_ATOMIC) {
         for (int c0 = 16 * half; c0 < BN; c0 += 16 * NSHARE) {
@@ -723,25 +834,29 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// Tensor map over a row-major fp32 matrix [outer][inner] with leading dimension ld (elements),
-// box = [box_outer][32 inner elements], 128-byte swizzle, zero fill out of bounds.
-static int make_tmap(CUtensorMap* m, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_outer, bool mn_major, int bk) {
+// Tensor map over a row-major matrix [outer][inner] of fp32 (or fp16: `half16`, K-major only) with leading dimension ld
+// (elements), box = [box_outer][bk inner elements] = rows of 128 bytes (bk = 32 fp32 / 64 fp16), 128-byte swizzle, zero fill
+// out of bounds.
+static int make_tmap(CUtensorMap* m, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_outer, bool mn_major, int bk,
+                     bool half16 = false) {
   // cuTensorMapEncodeTiled is a driver-API call: make sure this thread (e.g. the autograd engine's) has the
   // primary context bound before the first one.
   static thread_local bool ctx_bound = false;
   if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
   EncodeTiledFn enc = encode_tiled_fn();
   MOLCLR_REQUIRE(enc != nullptr, "gemm: cuTensorMapEncodeTiled not available from the driver");
+  const int esize = half16 ? 2 : 4;
   MOLCLR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "gemm: operand base pointer must be 16-byte aligned");
-  MOLCLR_REQUIRE(ld % 4 == 0, "gemm: leading dimension %lld must be a multiple of 4 floats (TMA 16-byte stride)", (long long)ld);
+  MOLCLR_REQUIRE(ld % (16 / esize) == 0, "gemm: leading dimension %lld must be a multiple of %d elements (TMA 16-byte stride)", (long long)ld, 16 / esize);
+  MOLCLR_REQUIRE(!half16 || !mn_major, "gemm: fp16 operands are K-major only");
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esize};
   // K-major: box = [box_outer rows][bk k];  MN-major: box = [bk k rows][32 mn]
   cuuint32_t box[2] = {mn_major ? 32u : (cuuint32_t)bk, (cuuint32_t)(mn_major ? bk : box_outer)};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+  CUresult r = enc(m, half16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : (bk == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : (bk * esize == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MOLCLR_REQUIRE(r == CUDA_SUCCESS, "gemm: cuTensorMapEncodeTiled failed with CUresult %d (inner=%lld outer=%lld ld=%lld)", (int)r,
@@ -757,9 +872,11 @@ static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, i
   CUtensorMap tmA, tmB, tmA2, tmB2;
   int rc;
   // K-major operand [rows][K]: inner = K, outer = rows, box = rows-per-CTA x BK.  MN-major [K][rows]: inner = rows, outer = K, box BK x 32.
-  rc = p.a_mn ? make_tmap(&tmA, j.A, p.M, p.K, j.lda, 32, true, Cfg::BK) : make_tmap(&tmA, j.A, p.K, p.M, j.lda, GEMM_BM, false, Cfg::BK);
+  const bool h16 = p.half16 != 0;
+  const int bk_el = h16 ? 2 * Cfg::BK : Cfg::BK;          // elements per 128-byte tile row
+  rc = p.a_mn ? make_tmap(&tmA, j.A, p.M, p.K, j.lda, 32, true, Cfg::BK) : make_tmap(&tmA, j.A, p.K, p.M, j.lda, GEMM_BM, false, bk_el, h16);
   if (rc) return rc;
-  rc = p.b_mn ? make_tmap(&tmB, j.B, p.N, p.K, j.ldb, 32, true, Cfg::BK) : make_tmap(&tmB, j.B, p.K, p.N, j.ldb, Cfg::BN_CTA, false, Cfg::BK);
+  rc = p.b_mn ? make_tmap(&tmB, j.B, p.N, p.K, j.ldb, 32, true, Cfg::BK) : make_tmap(&tmB, j.B, p.K, p.N, j.ldb, Cfg::BN_CTA, false, bk_el, h16);
   if (rc) return rc;
   tmA2 = tmA; tmB2 = tmB;
   if (p.segments > 1) {
@@ -827,6 +944,8 @@ static int gemm_bn(long long N, bool b_mn, bool pair, bool allow224 = false) {
   return 256;
 }
 
+bool gemm_f16_ok() { return !gemm_impl_simt(); }
+
 int gemm_n_tiles(long long N) {     // number of NT-Xent forward partials per row
   if (gemm_impl_simt()) return (int)((N + 31) / 32);
   const int bn = gemm_bn(N, false, gemm_pair());
@@ -855,11 +974,14 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
                        p.alpha == 1.f,
                    "gemm: split-K / transposed output supports no fused epilogue");
   else if (p.epi != EPI_NTX_FWD) {
-    MOLCLR_REQUIRE(p.out != nullptr || p.out2 != nullptr || p.colstat != nullptr, "gemm: no output requested");
+    MOLCLR_REQUIRE(p.out != nullptr || p.out2 != nullptr || p.colstat != nullptr || p.out16 != nullptr, "gemm: no output requested");
     MOLCLR_REQUIRE((!p.out || p.ldo % 4 == 0) && (!p.out2 || p.ldo2 % 4 == 0), "gemm: output leading dimensions must be multiples of 4");
     MOLCLR_REQUIRE((!p.addend || p.ldadd % 4 == 0) && (!p.mask || p.ldmask % 4 == 0), "gemm: addend/mask leading dimensions must be multiples of 4");
   }
-  const int bk = p.segments > 1 ? GEMM_BK4 : GEMM_BK;
+  if (p.half16)
+    MOLCLR_REQUIRE(p.segments == 1 && !p.a_mn && !p.b_mn && !atomic && !gemm_impl_simt(), "gemm: fp16 operands: single pass, K-major, no split-K");
+  MOLCLR_REQUIRE(!p.out16 || (p.epi == EPI_NTX_W && p.ldo16 % 8 == 0 && !p.out), "gemm: out16 is the fp16 output of the NT-Xent weight epilogue");
+  const int bk = p.half16 ? 2 * GEMM_BK : p.segments > 1 ? GEMM_BK4 : GEMM_BK;
   p.num_kb = (p.K + bk - 1) / bk;
   int splits = job.split_k > 1 ? job.split_k : 1;
   if (splits > p.num_kb) splits = p.num_kb;

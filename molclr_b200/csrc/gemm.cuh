@@ -10,6 +10,7 @@ enum GemmEpilogue : int { EPI_GENERIC = 0, EPI_NTX_FWD = 1, EPI_NTX_W = 2 };
 struct GemmParams {
   int M, N, K;
   int a_mn, b_mn;
+  int half16;                  // operands are fp16 (K-major only, 64 elements per 128-byte tile row): tcgen05 kind::f16, fp32 accumulation
   int num_kb, kb_per_split;
   int n_tiles, m_tiles, splits;   // tile grid walked by the persistent CTAs (filled by the launcher)
   int derive_lo;               // compensated product with low halves derived on chip: 1 = A_lo from an unrounded A; 2 = "mixed": A and B
@@ -18,6 +19,7 @@ struct GemmParams {
   float* out; long long ldo; int transpose_out;
   float* out2; long long ldo2;
   float* out_lo; long long ldo_lo;   // tf32-rounded residual  v - round_tf32(v)  (compensated-precision consumers)
+  void* out16; long long ldo16;      // EPI_NTX_W only: the softmax-weight tile as fp16, scaled by 2^10 (ldo16 in halves, % 8 == 0)
   const float* bias;
   const float* addend; long long ldadd;
   const float* mask; long long ldmask;
@@ -42,7 +44,7 @@ struct GemmParams {
 };
 
 struct GemmJob {
-  const float* A; long long lda; const float* B; long long ldb;
+  const float* A; long long lda; const float* B; long long ldb;   // p.half16: __half tensors, leading dimensions in halves (% 8 == 0)
   const float* A_lo; const float* B_lo;   // both non-null selects the 3-segment compensated product (same layout/ld as A, B)
   int compensate;              // 1: A and B are unrounded K-major fp32; ~fp32-accurate product, everything derived on chip ("mixed")
   int split_k;
@@ -53,6 +55,7 @@ struct GemmJob {
 
 // Validates, builds the tensor maps and launches.  Returns 0 or a negative error code.
 int gemm_run(const GemmJob& job, cudaStream_t stream);
+bool gemm_f16_ok();               // false only under the scalar debug implementation (MOLCLR_GEMM_IMPL=simt)
 int gemm_n_tiles(long long N);   // number of column tiles the launcher will use for this N
 
 }  // namespace molclr

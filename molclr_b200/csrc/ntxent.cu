@@ -8,6 +8,15 @@
 //           row's log-sum-exp).  W is produced and consumed in L2-resident column stripes of
 //           kStripe candidates: a stripe GEMM with the W epilogue followed by a stripe GEMM into that stripe's partial
 //           gradient; the partials are summed in stripe order at the end (deterministic).
+//
+// unit_rows != 0 (cosine similarity: every operand row has norm <= 1): the three tensor-core passes run on FP16 copies of the
+// rows (kind::f16, fp32 accumulation) -- the same 11-bit significand as TF32, so results are those of the TF32 passes, at
+// twice the tensor rate and half the shared-memory bytes -- and W is staged as fp16 scaled by 2^10 (stripes of 4096
+// candidates, the same 64 MB).  Otherwise
+// (dot-product similarity on rows of unknown magnitude) everything stays TF32 / fp32.
+#include <cuda_fp16.h>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "gemm.cuh"
 #include "molclr_b200.h"
@@ -15,6 +24,51 @@
 namespace molclr {
 
 constexpr int kStripe = 2048;     // W stripe [R][2048] fp32: 64 MB at R = 8192, L2-resident between the two GEMMs
+constexpr int kStripe16Max = 4096;   // fp16 W stripe [R][4096]: the same bytes
+
+static int stripe16() {              // MOLCLR_NTX_STRIPE16 = 1024 | 2048 | 4096 (tuning)
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("MOLCLR_NTX_STRIPE16");
+    const int x = e ? atoi(e) : 0;
+    v = (x == 1024 || x == 2048 || x == 4096) ? x : kStripe16Max;
+  }
+  return v;
+}
+
+// dst[r][0..C) = fp16(src[r][0..C)), row pitch ld16 halves (a multiple of 8); one thread per 4 elements
+__global__ void __launch_bounds__(256) ntx_to_half_kernel(const float* __restrict__ src, long long rows, int C, int ld16, __half* __restrict__ dst) {
+  const int c4 = C / 4;
+  const long long total = rows * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / c4;
+    const int c = (int)(i - r * c4) * 4;
+    const float4 v = ld_stream_f4(src + r * C + c);
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(dst + r * ld16 + c) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+  }
+}
+
+// dstT[c][r] = fp16(src[r][c]), row pitch ldT halves: the K-major "B" operand of the dZ contraction over candidates
+__global__ void __launch_bounds__(256) ntx_to_half_t_kernel(const float* __restrict__ src, long long rows, int C, long long ldT, __half* __restrict__ dstT) {
+  __shared__ float tile[64][33];
+  const long long r0 = (long long)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 32;
+  for (int k = threadIdx.y; k < 64; k += 8) {
+    const long long r = r0 + k;
+    const int c = c0 + threadIdx.x;
+    tile[k][threadIdx.x] = (r < rows && c < C) ? src[r * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int k = threadIdx.y; k < 32; k += 8) {
+    const int c = c0 + k;
+    const long long r = r0 + 2 * threadIdx.x;
+    if (c < C && r < rows) {       // rows is even: r + 1 < rows too
+      const __half2 h = __floats2half2_rn(tile[2 * threadIdx.x][k], tile[2 * threadIdx.x + 1][k]);
+      *reinterpret_cast<__half2*>(dstT + (size_t)c * ldT + r) = h;
+    }
+  }
+}
 
 // One block handles 32 rows: threadIdx.x = row (coalesced partial reads), threadIdx.y strides over the column-tile partials;
 // the 8 y-partials of a row are merged through shared memory in a fixed order (deterministic).
@@ -76,26 +130,82 @@ __global__ void __launch_bounds__(256) ntx_sum_partials_kernel(const float* __re
 
 using namespace molclr;
 
-static int64_t num_stripes(int64_t Rc) { return (Rc + kStripe - 1) / kStripe; }
+static int64_t num_stripes(int64_t Rc, int w = kStripe) { return (Rc + w - 1) / w; }
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// Workspace layout (one buffer serves either call and either operand mode)
+struct NtxLayout {
+  int ld16; long long ldT;
+  size_t part, f_rep16, f_cols16, fwd_total;                          // forward
+  size_t stripe, partials, b_rep16, b_cols16, b_colsT16, bwd_total;   // backward
+};
+static NtxLayout ntx_layout(int64_t R, int64_t Rc, int C) {
+  NtxLayout l;
+  l.ld16 = (C + 7) & ~7; l.ldT = (Rc + 7) & ~(long long)7;
+  const size_t rep16 = align256((size_t)R * l.ld16 * 2), cols16 = align256((size_t)Rc * l.ld16 * 2), colsT16 = align256((size_t)C * l.ldT * 2);
+  l.part = 0;
+  l.f_rep16 = align256((size_t)2 * gemm_n_tiles(Rc) * R * sizeof(float));
+  l.f_cols16 = l.f_rep16 + rep16;
+  l.fwd_total = l.f_cols16 + cols16;
+  l.stripe = 0;                                                       // [R][2048] fp32 or [R][4096] fp16
+  l.partials = align256((size_t)R * kStripe * sizeof(float));
+  l.b_rep16 = l.partials + align256((size_t)num_stripes(Rc) * R * C * sizeof(float));
+  l.b_cols16 = l.b_rep16 + rep16;
+  l.b_colsT16 = l.b_cols16 + cols16;
+  l.bwd_total = l.b_colsT16 + colsT16;
+  return l;
+}
 
 extern "C" size_t molclr_ntxent_workspace_bytes(int64_t R, int64_t Rc, int C) {
-  const size_t fwd = (size_t)2 * gemm_n_tiles(Rc) * R * sizeof(float);
-  const size_t bwd = (size_t)R * kStripe * sizeof(float) + (size_t)num_stripes(Rc) * R * C * sizeof(float);
-  return (fwd > bwd ? fwd : bwd) + 256;
+  const NtxLayout l = ntx_layout(R, Rc, C);
+  return (l.fwd_total > l.bwd_total ? l.fwd_total : l.bwd_total) + 256;
+}
+
+static int to_half(const float* src, int64_t rows, int C, int ld16, __half* dst, cudaStream_t stream) {
+  const long long total = rows * (C / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 16 * sm_count()) blocks = 16 * sm_count();
+  ntx_to_half_kernel<<<(int)blocks, 256, 0, stream>>>(src, rows, C, ld16, dst);
+  MOLCLR_CHECK_LAUNCH("ntx_to_half");
+  return 0;
+}
+
+// fp16 copies of rep and cols; rep rows that ARE rows of cols (one GPU: rep == cols) are not converted twice
+static int ntx_operands16(const float* rep, const float* cols, int64_t R, int64_t Rc, int C, int ld16, __half* rep16_buf, __half* cols16,
+                          const __half** rep16, cudaStream_t stream) {
+  int rc = to_half(cols, Rc, C, ld16, cols16, stream);
+  if (rc) return rc;
+  if (rep >= cols && rep + (size_t)R * C <= cols + (size_t)Rc * C && (rep - cols) % C == 0) {
+    *rep16 = cols16 + (size_t)((rep - cols) / C) * ld16;
+    return 0;
+  }
+  *rep16 = rep16_buf;
+  return to_half(rep, R, C, ld16, rep16_buf, stream);
 }
 
 extern "C" int molclr_ntxent_fwd(const float* rep, const float* cols, int64_t R, int64_t Rc, int C, int64_t row_offset,
-                                 int64_t row_offset2, float inv_temperature, float* row_lse, float* row_pos, float* loss, void* workspace,
-                                 size_t workspace_bytes, cudaStream_t stream) {
+                                 int64_t row_offset2, float inv_temperature, int unit_rows, float* row_lse, float* row_pos, float* loss,
+                                 void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   MOLCLR_REQUIRE(R > 0 && R % 2 == 0 && Rc >= R && Rc % 4 == 0 && C % 4 == 0, "ntxent: need R > 0 and even, Rc >= R, Rc %% 4 == 0, C %% 4 == 0 (R=%lld Rc=%lld C=%d)",
                  (long long)R, (long long)Rc, C);
   MOLCLR_REQUIRE(workspace_bytes >= molclr_ntxent_workspace_bytes(R, Rc, C), "ntxent_fwd: workspace too small");
+  const NtxLayout l = ntx_layout(R, Rc, C);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   const int tiles = gemm_n_tiles(Rc);
-  float* part_max = reinterpret_cast<float*>(workspace);
+  float* part_max = reinterpret_cast<float*>(ws + l.part);
   float* part_sum = part_max + (size_t)tiles * R;
+  const bool f16 = unit_rows != 0 && gemm_f16_ok();
   GemmJob j;
   memset(&j, 0, sizeof(j));
   j.A = rep; j.lda = C; j.B = cols; j.ldb = C; j.split_k = 1;
+  if (f16) {
+    const __half* rep16;
+    int rc = ntx_operands16(rep, cols, R, Rc, C, l.ld16, reinterpret_cast<__half*>(ws + l.f_rep16), reinterpret_cast<__half*>(ws + l.f_cols16), &rep16, stream);
+    if (rc) return rc;
+    j.A = reinterpret_cast<const float*>(rep16); j.lda = l.ld16;
+    j.B = reinterpret_cast<const float*>(ws + l.f_cols16); j.ldb = l.ld16;
+    j.p.half16 = 1;
+  }
   GemmParams& p = j.p;
   p.M = (int)R; p.N = (int)Rc; p.K = C; p.alpha = 1.f;
   p.epi = EPI_NTX_FWD; p.inv_tau = inv_temperature; p.row_offset = row_offset; p.row_split = R / 2; p.row_offset2 = row_offset2; p.col_offset = 0; p.num_cand = Rc;
@@ -112,30 +222,55 @@ extern "C" int molclr_ntxent_fwd(const float* rep, const float* cols, int64_t R,
 }
 
 extern "C" int molclr_ntxent_bwd(const float* rep, const float* cols, int64_t R, int64_t Rc, int C, int64_t row_offset,
-                                 int64_t row_offset2, float inv_temperature, const float* row_lse, const float* col_lse, float gscale, float* g_rep,
-                                 void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                                 int64_t row_offset2, float inv_temperature, int unit_rows, const float* row_lse, const float* col_lse, float gscale,
+                                 float* g_rep, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   MOLCLR_REQUIRE(R > 0 && R % 2 == 0 && Rc >= R && Rc % 4 == 0 && C % 4 == 0, "ntxent: need R > 0 and even, Rc >= R, Rc %% 4 == 0, C %% 4 == 0");
   MOLCLR_REQUIRE(workspace_bytes >= molclr_ntxent_workspace_bytes(R, Rc, C), "ntxent_bwd: workspace too small");
-  float* stripe = reinterpret_cast<float*>(workspace);
-  float* partials = stripe + (size_t)R * kStripe;                 // [stripes][R][C]
-  const int64_t ns = num_stripes(Rc);
+  const NtxLayout l = ntx_layout(R, Rc, C);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  float* stripe = reinterpret_cast<float*>(ws + l.stripe);
+  float* partials = reinterpret_cast<float*>(ws + l.partials);    // [stripes][R][C]
+  const bool f16 = unit_rows != 0 && gemm_f16_ok();
+  const int sw = f16 ? stripe16() : kStripe;
+  const int64_t ns = num_stripes(Rc, sw);
+  const __half* rep16 = nullptr;
+  const __half* cols16 = reinterpret_cast<const __half*>(ws + l.b_cols16);
+  __half* colsT16 = reinterpret_cast<__half*>(ws + l.b_colsT16);
+  if (f16) {
+    int rc = ntx_operands16(rep, cols, R, Rc, C, l.ld16, reinterpret_cast<__half*>(ws + l.b_rep16), reinterpret_cast<__half*>(ws + l.b_cols16), &rep16, stream);
+    if (rc) return rc;
+    ntx_to_half_t_kernel<<<dim3((unsigned)((Rc + 63) / 64), (unsigned)((C + 31) / 32)), dim3(32, 8), 0, stream>>>(cols, Rc, C, l.ldT, colsT16);
+    MOLCLR_CHECK_LAUNCH("ntx_to_half_t");
+  }
   for (int64_t si = 0; si < ns; ++si) {
-    const int64_t c0 = si * kStripe;
-    const int kc = (int)((Rc - c0) < kStripe ? (Rc - c0) : kStripe);
+    const int64_t c0 = si * sw;
+    const int kc = (int)((Rc - c0) < sw ? (Rc - c0) : sw);
     GemmJob w;
     memset(&w, 0, sizeof(w));
     w.A = rep; w.lda = C; w.B = cols + (size_t)c0 * C; w.ldb = C; w.split_k = 1;
     w.p.M = (int)R; w.p.N = kc; w.p.K = C; w.p.alpha = 1.f;
     w.p.epi = EPI_NTX_W; w.p.inv_tau = inv_temperature; w.p.row_offset = row_offset; w.p.row_split = R / 2; w.p.row_offset2 = row_offset2; w.p.col_offset = c0; w.p.num_cand = Rc;
     w.p.row_lse = row_lse; w.p.col_lse = col_lse;
-    w.p.out = stripe; w.p.ldo = kStripe; w.p.round_out = 1;
+    if (f16) {
+      w.A = reinterpret_cast<const float*>(rep16); w.lda = l.ld16;
+      w.B = reinterpret_cast<const float*>(cols16 + (size_t)c0 * l.ld16); w.ldb = l.ld16;
+      w.p.half16 = 1; w.p.out16 = stripe; w.p.ldo16 = sw;
+    } else {
+      w.p.out = stripe; w.p.ldo = kStripe; w.p.round_out = 1;
+    }
     int rc = gemm_run(w, stream);
     if (rc) return rc;
     GemmJob g;
     memset(&g, 0, sizeof(g));
-    g.A = stripe; g.lda = kStripe; g.B = cols + (size_t)c0 * C; g.ldb = C; g.split_k = 1;
-    g.p.M = (int)R; g.p.N = C; g.p.K = kc; g.p.a_mn = 0; g.p.b_mn = 1;
-    g.p.alpha = inv_temperature * gscale; g.p.epi = EPI_GENERIC;
+    g.split_k = 1;
+    g.p.M = (int)R; g.p.N = C; g.p.K = kc; g.p.epi = EPI_GENERIC;
+    if (f16) {     // both operands K-major over the candidates: W stripe [R][sw] and cols^T [C][ldT]; W carries a factor 2^10
+      g.A = stripe; g.lda = sw; g.B = reinterpret_cast<const float*>(colsT16 + c0); g.ldb = l.ldT;
+      g.p.half16 = 1; g.p.alpha = inv_temperature * gscale * (1.f / 1024.f);
+    } else {
+      g.A = stripe; g.lda = kStripe; g.B = cols + (size_t)c0 * C; g.ldb = C;
+      g.p.a_mn = 0; g.p.b_mn = 1; g.p.alpha = inv_temperature * gscale;
+    }
     g.p.out = partials + (size_t)si * R * C; g.p.ldo = C;
     g.bn_hint = 128;             // C = 256 is one 256-wide tile per row tile: halve it so that the stripe fills the GPU
     rc = gemm_run(g, stream);
@@ -148,4 +283,3 @@ extern "C" int molclr_ntxent_bwd(const float* rep, const float* cols, int64_t R,
   MOLCLR_CHECK_LAUNCH("ntx_sum_partials");
   return 0;
 }
-

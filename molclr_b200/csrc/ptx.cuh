@@ -112,6 +112,18 @@ __device__ __forceinline__ void tmem_ld_x16_nowait(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The same wait, carrying the 32 destination registers of two x16 loads through the asm statement, so that no use of them can
+// be scheduled above the wait while ANOTHER block of loads stays in flight (software-pipelined epilogues).
+__device__ __forceinline__ void tmem_ld_wait_dep(float (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                 "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]),
+                 "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]),
+                 "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
+               :: "memory");
+}
+// 2^x on the SFU (ex2.approx: 2 ulp, -inf -> +0), without the denormal-range fix-ups of exp2f()
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // Shared-memory matrix descriptor for fp32/tf32 tiles whose rows are 128 bytes (32 elements).
 //  K-major  tile [rows][32 k], SWIZZLE_128B (layout 2): 8-row groups 1024 B apart (SBO); LBO unused.
@@ -143,6 +155,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int n, int m = 128) {
          | (1u << 7) | (1u << 10)                // A, B format: BF16
          | ((uint32_t)(n >> 3) << 17)            // N / 8
          | ((uint32_t)(m >> 4) << 24);           // M / 16   (both operands K-major)
+}
+// kind::f16 with FP16 inputs (11-bit significand like TF32; for operands of magnitude <= 1), both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n, int m = 128) {
+  return (1u << 4)                               // D format: F32;  A, B format 0: F16
+         | ((uint32_t)(n >> 3) << 17)            // N / 8
+         | ((uint32_t)(m >> 4) << 24);           // M / 16
 }
 __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(

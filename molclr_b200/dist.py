@@ -64,7 +64,7 @@ class _GlobalNTXentFunction(torch.autograd.Function):
         _gather_rows(cols[:Bg], local_r[:B], group)                          # all zjs
         _gather_rows(cols[Bg:], local_r[B:], group)                          # all zis
         # local rows [zjs; zis] are candidates r*B.. and Bg + r*B.. of the global ordering
-        share, lse, _pos = kern.ntxent_fwd(local_r, cols, r * B, 1.0 / temperature, Bg + r * B)
+        share, lse, _pos = kern.ntxent_fwd(local_r, cols, r * B, 1.0 / temperature, Bg + r * B, unit_rows=use_cosine)
         col_lse = torch.empty(2 * Bg, dtype=lse.dtype, device=lse.device)
         _gather_rows(col_lse[:Bg], lse[:B], group)
         _gather_rows(col_lse[Bg:], lse[B:], group)
@@ -76,7 +76,7 @@ class _GlobalNTXentFunction(torch.autograd.Function):
     def backward(ctx, g_loss):
         local_n, inv, local_r, cols, lse, col_lse = ctx.saved_tensors
         B, Bg, r, temperature, use_cosine, kern = ctx.meta
-        g = kern.ntxent_bwd(local_r, cols, r * B, 1.0 / temperature, lse, col_lse, Bg + r * B) * g_loss
+        g = kern.ntxent_bwd(local_r, cols, r * B, 1.0 / temperature, lse, col_lse, Bg + r * B, unit_rows=use_cosine) * g_loss
         if use_cosine:
             g = kern.l2_normalize_bwd(g.contiguous(), local_n, inv, 1e-8)
         return g[B:], g[:B], None, None, None, None

@@ -22,7 +22,7 @@ class _NTXentFunction(torch.autograd.Function):
             rep_n, inv = rep, None
         rep_r = ops.round_tf32(rep_n)
         cols, row_offset = rep_r, 0
-        loss, row_lse, _row_pos = ops.ntxent_fwd(rep_r, cols, row_offset, 1.0 / temperature)
+        loss, row_lse, _row_pos = ops.ntxent_fwd(rep_r, cols, row_offset, 1.0 / temperature, unit_rows=use_cosine)
         ctx.save_for_backward(rep_n, inv, rep_r, row_lse)
         ctx.n, ctx.temperature, ctx.use_cosine = n, temperature, use_cosine
         return loss[0]
@@ -30,7 +30,7 @@ class _NTXentFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss):
         rep_n, inv, rep_r, row_lse = ctx.saved_tensors
-        g = ops.ntxent_bwd(rep_r, rep_r, 0, 1.0 / ctx.temperature, row_lse, row_lse)
+        g = ops.ntxent_bwd(rep_r, rep_r, 0, 1.0 / ctx.temperature, row_lse, row_lse, unit_rows=ctx.use_cosine)
         g = g * g_loss
         if ctx.use_cosine:
             g = ops.l2_normalize_bwd(g.contiguous(), rep_n, inv, 1e-8)

@@ -337,9 +337,9 @@ def l2_normalize_bwd(gy, y, inv, eps):
     return gz
 
 
-def ntxent_fwd(rep, cols, row_offset, inv_temperature, row_offset2=None):
+def ntxent_fwd(rep, cols, row_offset, inv_temperature, row_offset2=None, unit_rows=False):
     """Returns (loss[1], row_lse[R], row_pos[R]) for local rows `rep` ([zjs; zis] halves at candidate rows row_offset /
-    row_offset2) against candidates `cols`."""
+    row_offset2) against candidates `cols`.  unit_rows: all rows have norm <= 1 (cosine similarity) -> fp16 tensor-core operands."""
     lib = _lib.load()
     R, Cc = rep.shape
     Rc = cols.shape[0]
@@ -347,12 +347,12 @@ def ntxent_fwd(rep, cols, row_offset, inv_temperature, row_offset2=None):
     ws = torch.empty(nbytes, dtype=torch.uint8, device=rep.device)
     row_lse, row_pos, loss = _empty(R, device=rep.device), _empty(R, device=rep.device), _empty(1, device=rep.device)
     row_offset2 = row_offset + R // 2 if row_offset2 is None else row_offset2
-    check(lib.molclr_ntxent_fwd(ptr(rep), ptr(cols), R, Rc, Cc, row_offset, row_offset2, inv_temperature, ptr(row_lse), ptr(row_pos), ptr(loss),
+    check(lib.molclr_ntxent_fwd(ptr(rep), ptr(cols), R, Rc, Cc, row_offset, row_offset2, inv_temperature, int(bool(unit_rows)), ptr(row_lse), ptr(row_pos), ptr(loss),
                                 ptr(ws, torch.uint8), nbytes, stream()), "ntxent_fwd")
     return loss, row_lse, row_pos
 
 
-def ntxent_bwd(rep, cols, row_offset, inv_temperature, row_lse, col_lse, row_offset2=None):
+def ntxent_bwd(rep, cols, row_offset, inv_temperature, row_lse, col_lse, row_offset2=None, unit_rows=False):
     lib = _lib.load()
     R, Cc = rep.shape
     Rc = cols.shape[0]
@@ -360,6 +360,6 @@ def ntxent_bwd(rep, cols, row_offset, inv_temperature, row_lse, col_lse, row_off
     ws = torch.empty(nbytes, dtype=torch.uint8, device=rep.device)
     g = torch.empty_like(rep)
     row_offset2 = row_offset + R // 2 if row_offset2 is None else row_offset2
-    check(lib.molclr_ntxent_bwd(ptr(rep), ptr(cols), R, Rc, Cc, row_offset, row_offset2, inv_temperature, ptr(row_lse), ptr(col_lse), 1.0 / Rc,
+    check(lib.molclr_ntxent_bwd(ptr(rep), ptr(cols), R, Rc, Cc, row_offset, row_offset2, inv_temperature, int(bool(unit_rows)), ptr(row_lse), ptr(col_lse), 1.0 / Rc,
                                 ptr(g), ptr(ws, torch.uint8), nbytes, stream()), "ntxent_bwd")
     return g

@@ -50,7 +50,7 @@ class TorchKernels:
         return lg, self_mask, pos
 
     @classmethod
-    def ntxent_fwd(cls, rep, cols, row_offset, inv_t, row_offset2=None):
+    def ntxent_fwd(cls, rep, cols, row_offset, inv_t, row_offset2=None, unit_rows=False):
         lg, self_mask, pos = cls._logits(rep, cols, row_offset, inv_t, row_offset2)
         row_pos = lg[torch.arange(rep.shape[0]), pos]
         row_lse = torch.logsumexp(lg.masked_fill(self_mask, float("-inf")), dim=1)
@@ -58,7 +58,7 @@ class TorchKernels:
         return loss.to(rep.dtype), row_lse.to(rep.dtype), row_pos.to(rep.dtype)
 
     @classmethod
-    def ntxent_bwd(cls, rep, cols, row_offset, inv_t, row_lse, col_lse, row_offset2=None):
+    def ntxent_bwd(cls, rep, cols, row_offset, inv_t, row_lse, col_lse, row_offset2=None, unit_rows=False):
         lg, self_mask, pos = cls._logits(rep, cols, row_offset, inv_t, row_offset2)
         Rc = cols.shape[0]
         w = torch.exp(lg - row_lse.double()[:, None]) + torch.exp(lg - col_lse.double()[None, :])

@@ -48,7 +48,9 @@ def test_ntxent_matches_reference_golden(path):
     assert rel_err(zjs.grad, torch.tensor(g["dzjs"])) < RTOL_GRAD
 
 
-@pytest.mark.parametrize("n,c,tau,cos", [(512, 256, 0.1, True), (1500, 256, 0.1, True), (256, 64, 0.5, False)])
+# (6, 12): candidate count 12 = 4 mod 8 (ragged fp16 chunks); (2500, 256): two W stripes, the second one partial
+@pytest.mark.parametrize("n,c,tau,cos", [(512, 256, 0.1, True), (1500, 256, 0.1, True), (256, 64, 0.5, False), (6, 12, 0.1, True), (2500, 256, 0.1, True),
+                                         (2500, 64, 0.5, False)])
 def test_ntxent_matches_closed_form(n, c, tau, cos):
     torch.manual_seed(n)
     a = torch.randn(n, c)
@@ -65,6 +67,37 @@ def test_ntxent_matches_closed_form(n, c, tau, cos):
     loss.backward()
     assert abs(loss.item() - ref.item()) < 1e-3 * abs(ref.item()), (loss.item(), ref.item())
     assert rel_err(zis.grad, a64.grad) < RTOL_GRAD and rel_err(zjs.grad, b64.grad) < RTOL_GRAD
+
+
+@pytest.mark.parametrize("R,Rc,C", [(1024, 1024, 256), (512, 6000, 256), (64, 200, 40)])
+def test_ntxent_fp16_operands_equal_tf32_operands(R, Rc, C):
+    """unit_rows=True (fp16 tensor-core operands, fp16 W stripes) against unit_rows=False (TF32 operands, fp32 W): both carry
+    11-bit significands, so losses / log-sum-exps / gradients agree to rounding, local rows inside a larger candidate set."""
+    from molclr_b200 import ops
+    g = torch.Generator().manual_seed(R + Rc)
+    cols = ops.round_tf32(torch.nn.functional.normalize(torch.randn(Rc, C, generator=g), dim=1).to(DEV))
+    rep = torch.cat([cols[:R // 2], cols[Rc // 2:Rc // 2 + R // 2]]).contiguous()
+    res = []
+    for unit in (True, False):
+        loss, lse, pos = ops.ntxent_fwd(rep, cols, 0, 10.0, Rc // 2, unit_rows=unit)
+        col_lse = torch.full((Rc,), float(lse.mean()), device=DEV)
+        col_lse[:R // 2], col_lse[Rc // 2:Rc // 2 + R // 2] = lse[:R // 2], lse[R // 2:]
+        res.append((loss, lse, pos, ops.ntxent_bwd(rep, cols, 0, 10.0, lse, col_lse, Rc // 2, unit_rows=unit), col_lse))
+    (l1, s1, p1, g1, _), (l0, s0, p0, g0, cl) = res
+    assert abs(float(l1) - float(l0)) < 2e-5 * abs(float(l0))
+    assert (s1 - s0).abs().max() < 1e-4 and (p1 - p0).abs().max() < 1e-4
+    assert rel_err(g1, g0) < 2e-3, rel_err(g1, g0)
+    # and against the dense fp64 evaluation of the same formula
+    lg = (rep.double() @ cols.double().T) * 10.0
+    rows = torch.cat([torch.arange(R // 2), torch.arange(R // 2) + Rc // 2]).to(DEV)
+    self_mask = torch.arange(Rc, device=DEV)[None, :] == rows[:, None]
+    w = torch.exp(lg - s0.double()[:, None]) + torch.exp(lg - cl.double()[None, :])
+    w = w.masked_fill(self_mask, 0.0)
+    w[torch.arange(R, device=DEV), (rows + Rc // 2) % Rc] -= 2.0
+    ref = (10.0 / Rc) * (w @ cols.double())
+    assert rel_err(g1, ref) < 2e-3 and rel_err(g0, ref) < 2e-3, (rel_err(g1, ref), rel_err(g0, ref))
+    ref_lse = torch.logsumexp(lg.masked_fill(self_mask, float("-inf")), dim=1)
+    assert (s1.double() - ref_lse).abs().max() < 2e-3
 
 
 def test_ntxent_batch_size_mismatch_raises():
