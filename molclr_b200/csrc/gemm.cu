@@ -167,13 +167,17 @@ __device__ __forceinline__ void colstat_warp(const float* stage, int rows, int c
 // STAGES-deep smem ring; accumulators are double-buffered in TMEM so the epilogue warps drain tile i while the
 // tensor core works on tile i+1.
 // KIND selects the epilogue at compile time so that each variant is a short, branch-free loop:
-enum : int { K_PLAIN = 0, K_LATE = 1, K_NTX_W = 2, K_NTX_FWD = 3, K_ATOMIC = 4 };
+enum : int { K_PLAIN = 0, K_LATE = 1, K_NTX_W = 2, K_NTX_FWD = 3, K_ATOMIC = 4, K_PLAIN16 = 5, K_NTX_W16 = 6, K_NTX_FWD16 = 7 };
 
 template <int BN, bool FOUR, int KIND, bool TWO>
 __global__ void __launch_bounds__(GemmCfg<BN, FOUR, TWO>::THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
   using Cfg = GemmCfg<BN, FOUR, TWO>;
+  // fp16-operand instances (K-major tiles of 64 halves per 128-byte row, kind::f16 MMAs) share the epilogue of their TF32 kind
+  constexpr bool H16 = KIND >= K_PLAIN16;
+  constexpr int EK = KIND == K_PLAIN16 ? K_PLAIN : KIND == K_NTX_W16 ? K_NTX_W : KIND == K_NTX_FWD16 ? K_NTX_FWD : KIND;
+  static_assert(!(H16 && FOUR), "fp16 operands: single-pass instances only");
   extern __shared__ __align__(1024) uint8_t smem[];
   float* staging = reinterpret_cast<float*>(smem + Cfg::PIPE_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::PIPE_BYTES + Cfg::STAGING_BYTES);
@@ -245,7 +249,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
           uint8_t* b_dst = a_dst + (FOUR ? 2 : 1) * Cfg::A_BYTES;
           const int seg = FOUR ? 0 : i / nkb_seg;
-          const int kc = (kb0 + (i - seg * nkb_seg)) * (p.half16 ? 2 * Cfg::BK : Cfg::BK);   // fp16: 64 elements per 128-byte tile row
+          const int kc = (kb0 + (i - seg * nkb_seg)) * (H16 ? 2 * Cfg::BK : Cfg::BK);   // fp16: 64 elements per 128-byte tile row
 #pragma unroll
           for (int h = 0; h < (FOUR ? 2 : 1); ++h) {
             const CUtensorMap* ma = (FOUR ? h == 1 : seg == 1) ? &tmA2 : &tmA;
@@ -281,7 +285,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0 && rank == 0) {
       // fp16 operands (K-major): the same 128-byte-row tiles and descriptors, K = 16 (32 bytes) per kind::f16 instruction
-      const bool h16 = !FOUR && p.half16 != 0;
+      constexpr bool h16 = H16;
       const uint32_t idesc = h16 ? ptx::make_idesc_f16(Cfg::N1, TILE_M) : ptx::make_idesc_tf32(Cfg::N1, p.a_mn != 0, p.b_mn != 0, TILE_M);
       const uint32_t idesc2 = ptx::make_idesc_tf32(Cfg::N2 > 0 ? Cfg::N2 : 16, p.a_mn != 0, p.b_mn != 0, TILE_M);
       const uint32_t idesc16 = ptx::make_idesc_bf16(Cfg::N1, TILE_M);
@@ -444,30 +448,32 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         return (c0 < BN && n0 + c0 < p.N && grow < p.M) ? __ldg(p.bits_in + (size_t)grow * p.ld_bits + ((n0 + c0) >> 5)) : 0u;
       };
       uint32_t mw_next = 0u;
-      if (KIND == K_PLAIN && !FOUR && p.bits_in) mw_next = mask_word(0);
+      if (EK == K_PLAIN && !FOUR && p.bits_in) mw_next = mask_word(0);
       // this tile's bias slice goes to shared memory once (double-buffered across tiles; one named barrier per tile
       // among the epilogue warps), so that the register stage reads it with broadcast LDS instead of dependent LDGs
       const float* bias_t = bias_s + (tl & 1) * 256;
-      if (KIND == K_PLAIN && Cfg::BIAS_SMEM && p.bias) {
+      if (EK == K_PLAIN && Cfg::BIAS_SMEM && p.bias) {
         for (int e = threadIdx.x - 64; e < BN; e += Cfg::EPI_WARPS * 32)
           bias_s[(tl & 1) * 256 + e] = (n0 + e < p.N) ? __ldg(p.bias + n0 + e) : 0.f;
         ptx::named_bar_sync(1, Cfg::EPI_WARPS * 32);
       }
       float nlr = 0.f;                  // K_NTX_W, fp16 output: 10 - log2e * (log-sum-exp of this thread's row)
-      if (KIND == K_NTX_W) {            // the candidates' log-sum-exps of this column tile, pre-scaled for ex2
+      if (EK == K_NTX_W) {            // the candidates' log-sum-exps of this column tile, pre-scaled for ex2
         // (fp16 output: negated and shifted by 10, so that ex2(fma(s, k2, .)) is the softmax weight times 2^10)
-        const bool w16 = p.out16 != nullptr;
+        constexpr bool w16 = H16;
         for (int e = threadIdx.x - 64; e < BN; e += Cfg::EPI_WARPS * 32) {
           const float l2 = (n0 + e < p.N) ? __ldg(p.col_lse + p.col_offset + n0 + e) * 1.4426950408889634f : 0.f;
-          bias_s[(tl & 1) * 256 + e] = w16 ? 10.f - l2 : l2;
+          // (bounded logits: the column factor 2^(10 + bound - lse_k) itself)
+          bias_s[(tl & 1) * 256 + e] = !w16 ? l2 : p.ntx_bound2 > 0.f ? ptx::ex2_approx(10.f + p.ntx_bound2 - l2) : 10.f - l2;
         }
         if (w16) nlr = 10.f - (grow < p.M ? __ldg(p.row_lse + grow) : 0.f) * 1.4426950408889634f;
+        if (w16 && p.ntx_bound2 > 0.f) nlr = ptx::ex2_approx(nlr + p.ntx_bound2);
         ptx::named_bar_sync(1, Cfg::EPI_WARPS * 32);
       }
       ptx::mbar_wait(tfull_bar + buf, (tl >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + buf * 256u + ((uint32_t)(q * 32) << 16);
-      if (KIND == K_NTX_FWD) {
+      if (EK == K_NTX_FWD) {
         // per-row (max, sum exp) of this warp's share of the column tile, own column masked; thread <-> row straight
         // from TMEM, one pass with a running maximum.  Partials are indexed [n_tile * NSHARE + half][row].
         // 32 columns per step, the next step's TMEM loads in flight while this one is reduced; per element the loop costs
@@ -476,7 +482,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         long long pos = gr + p.num_cand / 2;
         if (pos >= p.num_cand) pos -= p.num_cand;
         const float k2 = p.inv_tau * 1.4426950408889634f;            // logits in base-2 units
-        float mx = -INFINITY, sum = 0.f;
+        float mx = (H16 && p.ntx_bound2 > 0.f) ? p.ntx_bound2 : -INFINITY, sum = 0.f;
         constexpr int NBLK = (BN / 32 + NSHARE - 1) / NSHARE;        // 32-column blocks of this warp: c0 = 32 (half + b NSHARE)
         auto blk_c0 = [&](int b) { return 32 * (half + b * NSHARE); };
         auto blk_ok = [&](int b) { return blk_c0(b) < BN && n0 + blk_c0(b) < p.N; };
@@ -503,6 +509,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int ds = (int)d_self;
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = j == ds ? -INFINITY : v[j];
+          }
+          if (H16 && p.ntx_bound2 > 0.f) {       // logits bounded a priori: no maximum pass (mx stays at the bound)
+            float cs0 = 0.f, cs1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) { cs0 += ptx::ex2_approx(fmaf(v[j], k2, -mx)); cs1 += ptx::ex2_approx(fmaf(v[j + 1], k2, -mx)); }
+            sum += cs0 + cs1;
+            return;
           }
           float cm0 = fmaxf(v[0], v[1]), cm1 = fmaxf(v[2], v[3]);
 #pragma unroll
@@ -533,7 +546,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           p.part_max[((size_t)n_tile * NSHARE + half) * p.M + grow] = mx * 0.6931471805599453f;
           p.part_sum[((size_t)n_tile * NSHARE + half) * p.M + grow] = sum;
         }
-      } else if (KIND == K_NTX_W && p.out16 != nullptr) {
+      } else if (EK == K_NTX_W && H16) {
         // Softmax-weight tile W[r][k] = P[r][k] + P[k][r] - 2 [k == pos(r)]  (nt_xent.py:53-65 differentiated) written as fp16,
         // scaled by 2^10 (weights are <= 2; the scale keeps the ~1/Rc entries out of the fp16 subnormals), for the fp16 dZ GEMM.
         // 32 columns per step (next step's TMEM loads in flight), thread = row; per element 2 FFMA + 2 EX2 + FADD + half a CVT.
@@ -554,6 +567,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int c0 = blk_c0(b);
           const long long gc0 = (long long)n0 + c0 + p.col_offset;
           const unsigned long long d_self = (unsigned long long)(gr - gc0), d_pos = (unsigned long long)(pos - gc0);
+          if (p.ntx_bound2 > 0.f) {
+            // bounded logits: W 2^10 = 2^(t - bound) (2^(10 + bound - lse_r) + 2^(10 + bound - lse_k)): one EX2 per element
+            const float nb = -p.ntx_bound2;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 ec = *reinterpret_cast<const float4*>(bias_t + c0 + j);     // broadcast
+              v[j] = ptx::ex2_approx(fmaf(v[j], k2, nb)) * (nlr + ec.x);
+              v[j + 1] = ptx::ex2_approx(fmaf(v[j + 1], k2, nb)) * (nlr + ec.y);
+              v[j + 2] = ptx::ex2_approx(fmaf(v[j + 2], k2, nb)) * (nlr + ec.z);
+              v[j + 3] = ptx::ex2_approx(fmaf(v[j + 3], k2, nb)) * (nlr + ec.w);
+            }
+          } else
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 nlc = *reinterpret_cast<const float4*>(bias_t + c0 + j);     // broadcast
@@ -604,10 +629,21 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (b + 2 < NBLK && blk_ok(b + 2)) blk_load(b + 2, va);
           blk_emit(b + 1, vb);
         }
-      } else if (KIND == K_ATOMIC) {
+      } else if (EK == K_ATOMIC) {
         for (int c0 = 16 * half; c0 < BN; c0 += 16 * NSHARE) {
           float v[16];
           ptx::tmem_ld_x16(taddr + c0, v);
+          if (p.debug & 8) continue;                  // timing experiment: no atomics
+          if (p.atomic_out == 2) {                    // row-major output with 16-byte aligned rows: vector reductions (4x fewer L2 requests)
+            if (grow < p.M)
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const int col = n0 + c0 + j;
+              if (col < p.N)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.out + (size_t)grow * p.ldo + col), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+            }
+            continue;
+          }
           if (grow < p.M) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -638,9 +674,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::tmem_ld_x16_nowait(taddr + c0, v);
           if (CH == 32) ptx::tmem_ld_x16_nowait(taddr + c0 + 16, v + (CH == 32 ? 16 : 0));
           uint32_t mw = mw_next;
-          if (KIND == K_PLAIN && !FOUR && has_bits_in && k + 1 < NCHUNK) mw_next = mask_word(k + 1);
+          if (EK == K_PLAIN && !FOUR && has_bits_in && k + 1 < NCHUNK) mw_next = mask_word(k + 1);
           ptx::tmem_ld_wait();
-          if (KIND == K_NTX_W) {
+          if (EK == K_NTX_W) {
             // W[r][k] = P[r][k] + P[k][r] - 2 [k == pos(r)],  P[i][k] = exp(l - lse_i) for k != i (nt_xent.py:53-65 differentiated)
             const long long gr = grow < p.row_split ? grow + p.row_offset : grow - p.row_split + p.row_offset2;
             long long pos = gr + p.num_cand / 2;
@@ -656,7 +692,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               v[j] = (gc0 + j == pos) ? w - 2.f : w;
             }
           }
-          if (KIND == K_PLAIN) {
+          if (EK == K_PLAIN) {
             if (has_bias || alpha != 1.f || p.relu) {
 #pragma unroll
               for (int j = 0; j < CH; j += 4) {
@@ -688,7 +724,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < CH; j += 4) st_f4(stg + stg_off<LD>(lane, j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
           __syncwarp();
           const int col = n0 + c0 + cq;
-          if ((KIND == K_PLAIN || KIND == K_NTX_W) && rows_w == 32 && n0 + c0 + CH <= p.N) {
+          if ((EK == K_PLAIN || EK == K_NTX_W) && rows_w == 32 && n0 + c0 + CH <= p.N) {
             // full chunk: straight-line copy-out (predicated stores only)
             const size_t gr0 = (size_t)(m0 + q * 32 + r_in);
             float* po = p.out + gr0 * p.ldo + col;
@@ -710,7 +746,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (r < rows_w && col_ok) {
                 const int gr = m0 + q * 32 + r;
                 float4 x = *reinterpret_cast<const float4*>(stg + stg_off<LD>(r, cq));
-                if (KIND != K_PLAIN && KIND != K_NTX_W) {
+                if (EK != K_PLAIN && EK != K_NTX_W) {
                   x = epilogue_apply(x, p, gr, col);
                   if (has_stat) st_f4(stg + stg_off<LD>(r, cq), x);
                 }
@@ -987,7 +1023,7 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   if (splits > p.num_kb) splits = p.num_kb;
   p.kb_per_split = (p.num_kb + splits - 1) / splits;
   splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;          // no empty split
-  p.atomic_out = atomic ? 1 : 0;
+  p.atomic_out = !atomic ? 0 : (!p.transpose_out && p.ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) ? 2 : 1;
   p.debug = gemm_debug_flags();
   // split-K weight gradients stay on single CTAs: their 300/600-wide outputs pad badly to 256-row pair tiles (MMA-bound)
   const bool wide = atomic && job.wide && gemm_pair() && !gemm_impl_simt();
@@ -1010,10 +1046,13 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   const int kind = p.epi == EPI_NTX_FWD ? K_NTX_FWD : atomic ? K_ATOMIC : p.epi == EPI_NTX_W ? K_NTX_W
                    : (p.mask || p.addend) ? K_LATE : K_PLAIN;
   MOLCLR_REQUIRE(p.segments == 1 || kind == K_PLAIN, "gemm: the compensated product supports the plain epilogue only");
+  MOLCLR_REQUIRE(!p.half16 || kind == K_PLAIN || kind == K_NTX_W || kind == K_NTX_FWD, "gemm: fp16 operands: plain and NT-Xent epilogues only");
+  MOLCLR_REQUIRE(kind != K_NTX_W || (p.out16 != nullptr) == (p.half16 != 0), "gemm: the NT-Xent weight epilogue writes fp16 iff its operands are fp16");
+  const int kind_i = !p.half16 ? kind : kind == K_PLAIN ? K_PLAIN16 : kind == K_NTX_W ? K_NTX_W16 : K_NTX_FWD16;
   const int bn = wide ? 320 : (job.bn_hint && pair) ? job.bn_hint : gemm_bn(p.N, p.b_mn != 0, pair, kind == K_PLAIN || kind == K_LATE), nt = (p.N + bn - 1) / bn;
   if (wide) MOLCLR_REQUIRE((long long)nt * m_tiles * splits <= gemm_workers(true), "gemm: a wide split-K launch must be one wave");
 #define MOLCLR_GEMM_CASE(BN_, FOUR_, KIND_, TWO_) \
-  if (bn == BN_ && (p.segments > 1) == FOUR_ && kind == KIND_ && pair == TWO_) return launch_tc<BN_, FOUR_, KIND_, TWO_>(job, p, nt, m_tiles, splits, stream);
+  if (bn == BN_ && (p.segments > 1) == FOUR_ && kind_i == KIND_ && pair == TWO_) return launch_tc<BN_, FOUR_, KIND_, TWO_>(job, p, nt, m_tiles, splits, stream);
 #define MOLCLR_GEMM_KINDS(BN_, TWO_) \
   MOLCLR_GEMM_CASE(BN_, false, K_PLAIN, TWO_) MOLCLR_GEMM_CASE(BN_, true, K_PLAIN, TWO_) MOLCLR_GEMM_CASE(BN_, false, K_LATE, TWO_) \
   MOLCLR_GEMM_CASE(BN_, false, K_NTX_W, TWO_) MOLCLR_GEMM_CASE(BN_, false, K_NTX_FWD, TWO_) MOLCLR_GEMM_CASE(BN_, false, K_ATOMIC, TWO_)
@@ -1021,9 +1060,14 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   MOLCLR_GEMM_KINDS(160, true) MOLCLR_GEMM_KINDS(192, true) MOLCLR_GEMM_KINDS(256, true)
   MOLCLR_GEMM_CASE(224, false, K_PLAIN, true) MOLCLR_GEMM_CASE(224, true, K_PLAIN, true) MOLCLR_GEMM_CASE(224, false, K_LATE, true)
   MOLCLR_GEMM_CASE(128, false, K_PLAIN, true) MOLCLR_GEMM_CASE(320, false, K_ATOMIC, true)
+#define MOLCLR_GEMM_KINDS16(BN_, TWO_) \
+  MOLCLR_GEMM_CASE(BN_, false, K_PLAIN16, TWO_) MOLCLR_GEMM_CASE(BN_, false, K_NTX_W16, TWO_) MOLCLR_GEMM_CASE(BN_, false, K_NTX_FWD16, TWO_)
+  MOLCLR_GEMM_KINDS16(160, false) MOLCLR_GEMM_KINDS16(256, false)
+  MOLCLR_GEMM_KINDS16(160, true) MOLCLR_GEMM_KINDS16(192, true) MOLCLR_GEMM_KINDS16(256, true) MOLCLR_GEMM_CASE(128, false, K_PLAIN16, true)
+#undef MOLCLR_GEMM_KINDS16
 #undef MOLCLR_GEMM_KINDS
 #undef MOLCLR_GEMM_CASE
-  set_error("gemm: no kernel instance for bn=%d segments=%d kind=%d", bn, p.segments, kind);
+  set_error("gemm: no kernel instance for bn=%d segments=%d kind=%d", bn, p.segments, kind_i);
   return -2;
 }
 

@@ -33,6 +33,8 @@ struct GemmParams {
   // ---- NT-Xent epilogues (nt_xent.py:47-65); logits l = acc * inv_tau
   int epi;
   float inv_tau;
+  float ntx_bound2;            // > 0: every |logit| * log2(e) <= ntx_bound2 (unit-norm rows, moderate 1/tau): exponentials are taken relative to this
+                               // a-priori bound instead of a running maximum (forward), and factored ex2(t) * (ex2(-lse_r) + ex2(-lse_k)) (weights)
   long long row_offset;        // global candidate index of A row r is r + row_offset (its own column: masked out) ...
   long long row_split, row_offset2;   // ... for r < row_split, and r - row_split + row_offset2 for the remaining rows
   long long col_offset;        // global candidate index of B row n is n + col_offset

@@ -130,6 +130,14 @@ __global__ void __launch_bounds__(256) ntx_sum_partials_kernel(const float* __re
 
 using namespace molclr;
 
+// unit-norm rows: |logit| <= 1/tau (with a margin for rounding).  For moderate 1/tau the kernels take exponentials relative to
+// this bound (no running maximum, one EX2 per weight); 0 = fall back to the general forms (tau < ~0.045: 2^(-2 bound) would
+// leave the fp32 range comfortably representable sums)
+static float ntx_bound2(float inv_temperature) {
+  const float b = 1.4426950408889634f * inv_temperature * 1.001f;
+  return (b > 0.f && b <= 32.f && !getenv("MOLCLR_NTX_NOBOUND")) ? b : 0.f;
+}
+
 static int64_t num_stripes(int64_t Rc, int w = kStripe) { return (Rc + w - 1) / w; }
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -204,7 +212,7 @@ extern "C" int molclr_ntxent_fwd(const float* rep, const float* cols, int64_t R,
     if (rc) return rc;
     j.A = reinterpret_cast<const float*>(rep16); j.lda = l.ld16;
     j.B = reinterpret_cast<const float*>(ws + l.f_cols16); j.ldb = l.ld16;
-    j.p.half16 = 1;
+    j.p.half16 = 1; j.p.ntx_bound2 = ntx_bound2(inv_temperature);
   }
   GemmParams& p = j.p;
   p.M = (int)R; p.N = (int)Rc; p.K = C; p.alpha = 1.f;
@@ -254,7 +262,7 @@ extern "C" int molclr_ntxent_bwd(const float* rep, const float* cols, int64_t R,
     if (f16) {
       w.A = reinterpret_cast<const float*>(rep16); w.lda = l.ld16;
       w.B = reinterpret_cast<const float*>(cols16 + (size_t)c0 * l.ld16); w.ldb = l.ld16;
-      w.p.half16 = 1; w.p.out16 = stripe; w.p.ldo16 = sw;
+      w.p.half16 = 1; w.p.out16 = stripe; w.p.ldo16 = sw; w.p.ntx_bound2 = ntx_bound2(inv_temperature);
     } else {
       w.p.out = stripe; w.p.ldo = kStripe; w.p.round_out = 1;
     }

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""Top stalled SASS instructions (with source line) of the first kernel in an .ncu-rep; also key raw metrics.
-    python tools/ncu_hot.py file.ncu-rep [topN]"""
+"""Top stalled SASS instructions (with source line) of the k-th kernel (default: first) in an .ncu-rep; also key raw metrics.
+    python tools/ncu_hot.py file.ncu-rep [topN] [k]"""
 import csv, subprocess, sys, io, collections
-rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 30; kidx = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 h = rows[0]
@@ -11,11 +11,11 @@ want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'launch__registers_per_thread', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__inst_executed.sum', 'smsp__cycles_active.avg', 'sm__cycles_elapsed.max']
-for r in rows[2:3]:
+for r in rows[2 + kidx:3 + kidx]:
     print(r[h.index('Kernel Name')][:100])
     for w in want:
         if w in h: print(f"   {w} = {r[h.index(w)]} {rows[1][h.index(w)]}")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda" if False else "sass"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "--launch-skip", str(kidx), "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h = rows[1]
 isrc = h.index('Source'); isamp = h.index('# Samples'); iex = h.index('Instructions Executed')
