@@ -982,6 +982,10 @@ static int gemm_bn(long long N, bool b_mn, bool pair, bool allow224 = false) {
 
 bool gemm_f16_ok() { return !gemm_impl_simt(); }
 
+int gemm_make_tmap_f16(CUtensorMap* m, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_outer) {
+  return make_tmap(m, reinterpret_cast<const float*>(base), inner, outer, ld, box_outer, false, 64, true);
+}
+
 int gemm_n_tiles(long long N) {     // number of NT-Xent forward partials per row
   if (gemm_impl_simt()) return (int)((N + 31) / 32);
   const int bn = gemm_bn(N, false, gemm_pair());

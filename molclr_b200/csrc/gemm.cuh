@@ -1,5 +1,6 @@
 // Internal GEMM job description shared by gemm.cu and ntxent.cu.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -57,6 +58,9 @@ struct GemmJob {
 
 // Validates, builds the tensor maps and launches.  Returns 0 or a negative error code.
 int gemm_run(const GemmJob& job, cudaStream_t stream);
+// Tensor map over a row-major fp16 matrix [outer][inner] (ld in halves, % 8 == 0): boxes of box_outer rows x 64 halves (128-byte
+// rows, 128-byte swizzle, zero fill out of bounds)
+int gemm_make_tmap_f16(CUtensorMap* m, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_outer);
 bool gemm_f16_ok();               // false only under the scalar debug implementation (MOLCLR_GEMM_IMPL=simt)
 int gemm_n_tiles(long long N);   // number of column tiles the launcher will use for this N
 

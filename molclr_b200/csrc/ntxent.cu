@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include "molclr_b200.h"
+#include "ntxent.cuh"
 
 namespace molclr {
 
@@ -138,6 +139,12 @@ static float ntx_bound2(float inv_temperature) {
   return (b > 0.f && b <= 32.f && !getenv("MOLCLR_NTX_NOBOUND")) ? b : 0.f;
 }
 
+static bool ntx_fused_enabled() {      // MOLCLR_NTX_FUSED=0: the striped two-GEMM backward (A/B timing, and the path of C > 256)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MOLCLR_NTX_FUSED"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  return v != 0;
+}
+
 static int64_t num_stripes(int64_t Rc, int w = kStripe) { return (Rc + w - 1) / w; }
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -145,7 +152,7 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 struct NtxLayout {
   int ld16; long long ldT;
   size_t part, f_rep16, f_cols16, fwd_total;                          // forward
-  size_t stripe, partials, b_rep16, b_cols16, b_colsT16, bwd_total;   // backward
+  size_t stripe, partials, b_rep16, b_cols16, b_colsT16, b_ecol, bwd_total;   // backward
 };
 static NtxLayout ntx_layout(int64_t R, int64_t Rc, int C) {
   NtxLayout l;
@@ -157,10 +164,12 @@ static NtxLayout ntx_layout(int64_t R, int64_t Rc, int C) {
   l.fwd_total = l.f_cols16 + cols16;
   l.stripe = 0;                                                       // [R][2048] fp32 or [R][4096] fp16
   l.partials = align256((size_t)R * kStripe * sizeof(float));
-  l.b_rep16 = l.partials + align256((size_t)num_stripes(Rc) * R * C * sizeof(float));
+  const int64_t slots = num_stripes(Rc) > kNtxFusedMaxSplits ? num_stripes(Rc) : kNtxFusedMaxSplits;
+  l.b_rep16 = l.partials + align256((size_t)slots * R * C * sizeof(float));
   l.b_cols16 = l.b_rep16 + rep16;
   l.b_colsT16 = l.b_cols16 + cols16;
-  l.bwd_total = l.b_colsT16 + colsT16;
+  l.b_ecol = l.b_colsT16 + colsT16;
+  l.bwd_total = l.b_ecol + align256(ntx_fused_ecol_floats(Rc) * sizeof(float));
   return l;
 }
 
@@ -244,9 +253,23 @@ extern "C" int molclr_ntxent_bwd(const float* rep, const float* cols, int64_t R,
   const __half* rep16 = nullptr;
   const __half* cols16 = reinterpret_cast<const __half*>(ws + l.b_cols16);
   __half* colsT16 = reinterpret_cast<__half*>(ws + l.b_colsT16);
+  const float bound2 = ntx_bound2(inv_temperature);
   if (f16) {
     int rc = ntx_operands16(rep, cols, R, Rc, C, l.ld16, reinterpret_cast<__half*>(ws + l.b_rep16), reinterpret_cast<__half*>(ws + l.b_cols16), &rep16, stream);
     if (rc) return rc;
+    if (bound2 > 0.f && C <= 256 && ntx_fused_enabled()) {
+      // fused: S tile -> softmax weights -> second product, all on chip (ntxent_fused.cu)
+      const int splits = ntx_fused_splits(R, Rc);
+      rc = ntx_bwd_fused(rep16, cols16, l.ld16, R, Rc, C, row_offset, row_offset2, inv_temperature, bound2, row_lse, col_lse, gscale,
+                         reinterpret_cast<float*>(ws + l.b_ecol), partials, splits, stream);
+      if (rc) return rc;
+      const long long len4 = (long long)R * C / 4;
+      long long blocks = (len4 + 255) / 256;
+      if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+      ntx_sum_partials_kernel<<<(int)blocks, 256, 0, stream>>>(partials, splits, len4, g_rep);
+      MOLCLR_CHECK_LAUNCH("ntx_sum_partials");
+      return 0;
+    }
     ntx_to_half_t_kernel<<<dim3((unsigned)((Rc + 63) / 64), (unsigned)((C + 31) / 32)), dim3(32, 8), 0, stream>>>(cols, Rc, C, l.ldT, colsT16);
     MOLCLR_CHECK_LAUNCH("ntx_to_half_t");
   }

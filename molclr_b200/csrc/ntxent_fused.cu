@@ -1,0 +1,331 @@
+// Fused NT-Xent backward (utils/nt_xent.py:47-65 differentiated) for unit-norm rows: the softmax-weight matrix W never leaves the SM.
+//
+//   g_rep[r] = (gscale / tau) * sum_k W[r][k] cols[k],   W[r][k] = P[r][k] + P[k][r] - 2 [k == pos(r)],  P[i][k] = exp(S[i][k]/tau - lse_i)
+//
+// One CTA owns a tile of 128 local rows (its fp16 rows stay in shared memory) and walks a range of 64-candidate blocks:
+//   TMA      : block j of cols (fp16 [64][C], 128-byte swizzle) + its 64 column factors -> 4-stage ring (a stage is held from
+//              the first product of its block to the second, so the ring has to cover the TMA latency with two blocks of work)
+//   MMA warp : S_j = Q . K_j^T (kind::f16, accumulator double-buffered in TMEM), then  dZ += W_j . K_j  with the SAME shared
+//              memory tile read MN-major as the "V" operand (dZ [128][C] fp32 stays in TMEM for the whole range)
+//   8 warps  : S_j TMEM -> registers (thread = row) -> W_j 2^10 = 2^(s k2 - bound) (2^(10 + bound - lse_r) + 2^(10 + bound - lse_k))
+//              -> fp16 -> K-major swizzled shared-memory tile (the A operand of the second product)
+// i.e. the flash-attention forward loop with a fixed shift instead of a running maximum (|logit| <= 1/tau is known a priori)
+// and no normalisation (the log-sum-exps come from the forward pass).  Row tiles x candidate splits fill the GPU; each
+// (tile, split) writes a partial gradient which ntx_sum_partials adds in split order (deterministic).
+#include <cuda_fp16.h>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "gemm.cuh"
+#include "ntxent.cuh"
+#include "ptx.cuh"
+
+namespace molclr {
+
+constexpr int NF_BM = 128, NF_BN = 64, NF_CMAX = 256, NF_STAGES = 4;
+constexpr int NF_Q_SUB = NF_BM * 128;                     // one [128 rows][64 halves] sub-tile of Q: 16 KB
+constexpr int NF_KV_SUB = NF_BN * 128;                    // one [64 candidates][64 halves] sub-tile of a block: 8 KB
+constexpr int NF_Q_BYTES = (NF_CMAX / 64) * NF_Q_SUB;     // 64 KB
+constexpr int NF_KV_BYTES = (NF_CMAX / 64) * NF_KV_SUB;   // 32 KB
+constexpr int NF_STAGE_BYTES = NF_KV_BYTES;
+constexpr int NF_P_BYTES = NF_BM * NF_BN * 2;             // 16 KB
+constexpr int NF_EC_OFF = NF_Q_BYTES + NF_STAGES * NF_STAGE_BYTES + 2 * NF_P_BYTES;      // [stages][64] column factors of the staged blocks
+constexpr int NF_BAR_OFF = NF_EC_OFF + NF_STAGES * NF_BN * 4;
+constexpr int NF_SMEM_BYTES = NF_BAR_OFF + 256;
+static_assert(NF_SMEM_BYTES <= 232448, "shared memory budget");
+constexpr int NF_THREADS = 64 + 8 * 32;
+constexpr int NF_TMEM_S = 256;                            // TMEM columns [0, 256): dZ; [256, 512): four S buffers
+constexpr int NF_AHEAD = 2;                               // S products issued ahead of the block whose weights are being formed
+
+struct NtxFusedParams {
+  int R, C, nsub, ksteps, npv;     // nsub = ceil(C/64) sub-tiles, ksteps = ceil(C/16) MMAs per S tile, npv = 16 ksteps (dZ columns)
+  int nblocks, row_tiles, splits;
+  long long row_offset, row_split, row_offset2, num_cand;
+  float k2, bound2, alpha;
+  int swap_lbo;                    // (bring-up switch for the MN-major descriptor)
+  const float* row_lse;
+  const float* ecol;               // [nblocks * 64] column factors 2^(10 + bound - lse_k), 0 beyond Rc
+  float* partials;                 // [splits][R][C]
+};
+
+__global__ void __launch_bounds__(256) ntx_ecol_kernel(const float* __restrict__ col_lse, long long Rc, long long n, float bound2, float* __restrict__ ecol) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) ecol[i] = i < Rc ? ptx::ex2_approx(10.f + bound2 - col_lse[i] * 1.4426950408889634f) : 0.f;
+}
+
+__global__ void __launch_bounds__(NF_THREADS, 1)
+ntx_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const NtxFusedParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* q_s = smem;
+  uint8_t* kv_s = smem + NF_Q_BYTES;
+  uint8_t* p_s = kv_s + NF_STAGES * NF_STAGE_BYTES;
+  float* ec_s = reinterpret_cast<float*>(smem + NF_EC_OFF);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NF_BAR_OFF);
+  uint64_t* q_full = bars;              // Q tile of this item landed
+  uint64_t* q_empty = bars + 1;         // all S products of the item issued and complete: Q may be overwritten
+  uint64_t* kv_full = bars + 2;         // [4]
+  uint64_t* kv_empty = bars + 6;        // [4] released by the second product of the block
+  uint64_t* s_full = bars + 10;         // [4] S_j complete in TMEM
+  uint64_t* s_empty = bars + 14;        // [4] the 8 weight warps have read S_j
+  uint64_t* p_full = bars + 18;         // [2] W_j written to shared memory
+  uint64_t* p_empty = bars + 20;        // [2] second product of the block has read W_j
+  uint64_t* dz_full = bars + 22;        // all products of the item complete
+  uint64_t* dz_empty = bars + 23;       // the 8 warps have drained dZ
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = p.row_tiles * p.splits;
+
+  if (threadIdx.x == 0) {
+    if ((ptx::smem_u32(smem) & 1023u) != 0) { printf("molclr ntx_bwd_fused: dynamic smem base not 1024B aligned\n"); __trap(); }
+    ptx::mbar_init(q_full, 1); ptx::mbar_init(q_empty, 1);
+    for (int s = 0; s < NF_STAGES; ++s) { ptx::mbar_init(kv_full + s, 1); ptx::mbar_init(kv_empty + s, 1); }
+    for (int b = 0; b < 4; ++b) { ptx::mbar_init(s_full + b, 1); ptx::mbar_init(s_empty + b, 8); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(p_full + b, 8); ptx::mbar_init(p_empty + b, 1); }
+    ptx::mbar_init(dz_full, 1); ptx::mbar_init(dz_empty, 8);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tmQ);
+    ptx::prefetch_tensormap(&tmK);
+  }
+  if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto block_range = [&](int sp, int& b0, int& b1) {
+    b0 = (int)((long long)sp * p.nblocks / p.splits);
+    b1 = (int)((long long)(sp + 1) * p.nblocks / p.splits);
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0, li = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x, ++li) {
+        const int rt = item % p.row_tiles, sp = item / p.row_tiles;
+        int b0, b1;
+        block_range(sp, b0, b1);
+        ptx::mbar_wait(q_empty, (li & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(q_full, (uint32_t)p.nsub * NF_Q_SUB);
+        for (int s = 0; s < p.nsub; ++s) ptx::tma_load_2d(q_s + s * NF_Q_SUB, &tmQ, q_full, 64 * s, rt * NF_BM);
+        for (int b = b0; b < b1; ++b, ++it) {
+          const int st = it % NF_STAGES;
+          ptx::mbar_wait(kv_empty + st, ((it / NF_STAGES) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(kv_full + st, (uint32_t)p.nsub * NF_KV_SUB + NF_BN * 4);
+          uint8_t* dst = kv_s + st * NF_STAGE_BYTES;
+          for (int s = 0; s < p.nsub; ++s) ptx::tma_load_2d(dst + s * NF_KV_SUB, &tmK, kv_full + st, 64 * s, b * NF_BN);
+          ptx::bulk_load_1d(ec_s + st * NF_BN, p.ecol + (size_t)b * NF_BN, NF_BN * 4, kv_full + st);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer: the whole warp walks the loop (warp-uniform
+    // descriptors and barrier addresses), one elected lane issues the tcgen05 instructions
+    {
+      const uint32_t idesc_qk = ptx::make_idesc_f16(NF_BN, NF_BM);
+      const uint32_t idesc_pv = ptx::make_idesc_f16(p.npv, NF_BM) | (1u << 16);        // B (the candidate rows as "V") MN-major
+      const uint32_t kv_base = ptx::smem_u32(kv_s);
+      // descriptors with the address of the operand's first byte; the 14-bit address field (bytes / 16) is advanced by plain adds
+      const uint64_t q_desc = ptx::make_smem_desc(ptx::smem_u32(q_s), 16u, 1024u, ptx::kLayoutSw128);
+      const uint64_t k_desc = ptx::make_smem_desc(kv_base, 16u, 1024u, ptx::kLayoutSw128);
+      const uint64_t p_desc = ptx::make_smem_desc(ptx::smem_u32(p_s), 16u, 1024u, ptx::kLayoutSw128);
+      // V descriptor: [64 candidates][64 halves] sub-tiles, 128-byte swizzle; along N (features) the sub-tiles are NF_KV_SUB apart,
+      // along K (candidates) the 8-row groups 1024 B apart
+      const uint64_t v_desc = p.swap_lbo ? ptx::make_smem_desc(kv_base, 1024u, (uint32_t)NF_KV_SUB, ptx::kLayoutSw128)
+                                         : ptx::make_smem_desc(kv_base, (uint32_t)NF_KV_SUB, 1024u, ptx::kLayoutSw128);
+      const int ksteps = p.ksteps;
+      uint32_t it = 0, li = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x, ++li) {
+        const int sp = item / p.row_tiles;
+        int b0, b1;
+        block_range(sp, b0, b1);
+        const int nb = b1 - b0;
+        ptx::mbar_wait(q_full, li & 1);
+        ptx::tc_fence_after();
+        auto issue_qk = [&](uint32_t g, bool last) {          // S_g = Q . K_g^T into S buffer g % 4
+          const uint32_t st = g % NF_STAGES, sb = g & 3;
+          ptx::mbar_wait(kv_full + st, (g / NF_STAGES) & 1);
+          ptx::mbar_wait(s_empty + sb, ((g >> 2) & 1) ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t d = tmem_base + NF_TMEM_S + NF_BN * sb;
+          const uint64_t kd = k_desc + (uint64_t)((st * NF_STAGE_BYTES) >> 4);
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < NF_CMAX / 16; ++k) {
+              if (k < ksteps) {
+                const uint32_t qoff = (uint32_t)(((k >> 2) * NF_Q_SUB + (k & 3) * 32) >> 4), koff = (uint32_t)(((k >> 2) * NF_KV_SUB + (k & 3) * 32) >> 4);
+                ptx::mma_f16_ss(d, q_desc + qoff, kd + koff, idesc_qk, k != 0 ? 1u : 0u);
+              }
+            }
+            ptx::mma_commit(s_full + sb);
+            if (last) ptx::mma_commit(q_empty);
+          }
+          __syncwarp();
+        };
+        // the S products run NF_AHEAD blocks ahead of the weight warps, so that neither side waits for the other's latency
+        for (int a = 0; a < NF_AHEAD && a < nb; ++a) issue_qk(it + a, a == nb - 1);
+        for (int j = 0; j < nb; ++j) {
+          if (j + NF_AHEAD < nb) issue_qk(it + j + NF_AHEAD, j + NF_AHEAD == nb - 1);
+          const uint32_t g = it + j, st = g % NF_STAGES, pb = g & 1;       // dZ += W_j . K_j
+          ptx::mbar_wait(p_full + pb, (g >> 1) & 1);
+          if (j == 0) ptx::mbar_wait(dz_empty, (li & 1) ^ 1);
+          ptx::tc_fence_after();
+          const uint64_t pd = p_desc + (uint64_t)((pb * NF_P_BYTES) >> 4), vd = v_desc + (uint64_t)((st * NF_STAGE_BYTES) >> 4);
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < NF_BN / 16; ++k)
+              ptx::mma_f16_ss(tmem_base, pd + (uint64_t)((k * 32) >> 4), vd + (uint64_t)((k * 2048) >> 4), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+            ptx::mma_commit(kv_empty + st);
+            ptx::mma_commit(p_empty + pb);
+            if (j == nb - 1) ptx::mma_commit(dz_full);
+          }
+          __syncwarp();
+        }
+        it += nb;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ weight warps: (q, half) = TMEM lane quadrant, 32-column share of a block
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float nb2 = -p.bound2;
+    uint32_t it = 0, li = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x, ++li) {
+      const int rt = item % p.row_tiles, sp = item / p.row_tiles;
+      int b0, b1;
+      block_range(sp, b0, b1);
+      const int grow = rt * NF_BM + row;
+      const long long gr = grow < p.row_split ? grow + p.row_offset : grow - p.row_split + p.row_offset2;
+      long long pos = gr + p.num_cand / 2;
+      if (pos >= p.num_cand) pos -= p.num_cand;
+      const float er = grow < p.R ? ptx::ex2_approx(10.f + p.bound2 - __ldg(p.row_lse + grow) * 1.4426950408889634f) : 0.f;
+      for (int b = b0; b < b1; ++b, ++it) {
+        const uint32_t sb = it & 3, pb = it & 1, st = it % NF_STAGES;
+        ptx::mbar_wait(s_full + sb, (it >> 2) & 1);
+        ptx::mbar_wait(kv_full + st, (it / NF_STAGES) & 1);      // (already complete: S_j was computed from this stage; orders the factor reads)
+        ptx::tc_fence_after();
+        float v[32];
+        const uint32_t taddr = lane_addr + NF_TMEM_S + NF_BN * sb + 32 * half;
+        ptx::tmem_ld_x16_nowait(taddr, v);
+        ptx::tmem_ld_x16_nowait(taddr + 16, v + 16);
+        ptx::tmem_ld_wait_dep(v);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(s_empty + sb);
+        const float* ec = ec_s + st * NF_BN + 32 * half;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 e = *reinterpret_cast<const float4*>(ec + j);     // broadcast
+          v[j] = ptx::ex2_approx(fmaf(v[j], p.k2, nb2)) * (er + e.x);
+          v[j + 1] = ptx::ex2_approx(fmaf(v[j + 1], p.k2, nb2)) * (er + e.y);
+          v[j + 2] = ptx::ex2_approx(fmaf(v[j + 2], p.k2, nb2)) * (er + e.z);
+          v[j + 3] = ptx::ex2_approx(fmaf(v[j + 3], p.k2, nb2)) * (er + e.w);
+        }
+        const long long gc0 = (long long)b * NF_BN + 32 * half;
+        const unsigned long long d_self = (unsigned long long)(gr - gc0), d_pos = (unsigned long long)(pos - gc0);
+        if (d_self < 32ull) {
+          const int ds = (int)d_self;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = j == ds ? 0.f : v[j];
+        }
+        if (d_pos < 32ull) {
+          const int dp = (int)d_pos;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = j == dp ? v[j] - 2048.f : v[j];
+        }
+        uint32_t h[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const __half2 hh = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+          h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
+        ptx::mbar_wait(p_empty + pb, ((it >> 1) & 1) ^ 1);
+        // K-major tile [128 rows][64 halves = 128 B], 128-byte swizzle: 16-byte chunk c of row r lives at chunk c ^ (r & 7)
+        uint8_t* prow = p_s + pb * NF_P_BYTES + row * 128;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          *reinterpret_cast<uint4*>(prow + (((4 * half + jj) ^ (row & 7)) << 4)) = make_uint4(h[4 * jj], h[4 * jj + 1], h[4 * jj + 2], h[4 * jj + 3]);
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(p_full + pb);
+      }
+      // drain this item's dZ: thread = row, this warp's 128-column half, straight to the partial gradient of the split
+      ptx::mbar_wait(dz_full, li & 1);
+      ptx::tc_fence_after();
+      float* orow = p.partials + ((size_t)sp * p.R + (size_t)(grow < p.R ? grow : 0)) * p.C;
+      for (int c0 = 128 * half; c0 < 128 * half + 128 && c0 < p.npv; c0 += 32) {
+        float v[32];
+        ptx::tmem_ld_x16_nowait(lane_addr + c0, v);
+        ptx::tmem_ld_x16_nowait(lane_addr + c0 + 16, v + 16);
+        ptx::tmem_ld_wait_dep(v);
+        if (grow < p.R) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (c0 + j < p.C) st_f4(orow + c0 + j, make_float4(v[j] * p.alpha, v[j + 1] * p.alpha, v[j + 2] * p.alpha, v[j + 3] * p.alpha));
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(dz_empty);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 512); }
+}
+
+// Candidate splits: fill the GPU in whole waves with at least ~12 blocks per (row tile, split) item
+int ntx_fused_splits(int64_t R, int64_t Rc) {
+  const int row_tiles = (int)((R + NF_BM - 1) / NF_BM), nblocks = (int)((Rc + NF_BN - 1) / NF_BN), sms = sm_count();
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= kNtxFusedMaxSplits && s <= nblocks; ++s) {
+    if (s > 1 && nblocks / s < 12) break;
+    const long long items = (long long)row_tiles * s, waves = (items + sms - 1) / sms;
+    const double eff = (double)items / (double)(waves * sms);
+    if (eff > best_eff * 1.01) { best_eff = eff; best = s; }
+  }
+  return best;
+}
+
+size_t ntx_fused_ecol_floats(int64_t Rc) { return (size_t)((Rc + NF_BN - 1) / NF_BN) * NF_BN; }
+
+int ntx_bwd_fused(const __half* rep16, const __half* cols16, int ld16, int64_t R, int64_t Rc, int C, int64_t row_offset, int64_t row_offset2,
+                  float inv_temperature, float bound2, const float* row_lse, const float* col_lse, float gscale, float* ecol, float* partials,
+                  int splits, cudaStream_t stream) {
+  MOLCLR_REQUIRE(C <= NF_CMAX && C % 4 == 0 && bound2 > 0.f, "ntx_bwd_fused: needs C <= 256 and bounded logits");
+  NtxFusedParams p;
+  memset(&p, 0, sizeof(p));
+  p.R = (int)R; p.C = C; p.nsub = (C + 63) / 64; p.ksteps = (C + 15) / 16; p.npv = 16 * p.ksteps;
+  p.nblocks = (int)((Rc + NF_BN - 1) / NF_BN); p.row_tiles = (int)((R + NF_BM - 1) / NF_BM); p.splits = splits;
+  p.row_offset = row_offset; p.row_split = R / 2; p.row_offset2 = row_offset2; p.num_cand = Rc;
+  p.k2 = inv_temperature * 1.4426950408889634f; p.bound2 = bound2; p.alpha = inv_temperature * gscale * (1.f / 1024.f);
+  static int swap = -1;
+  if (swap < 0) { const char* e = getenv("MOLCLR_NTX_SWAP_LBO"); swap = e ? atoi(e) : 0; }
+  p.swap_lbo = swap;
+  p.row_lse = row_lse; p.ecol = ecol; p.partials = partials;
+  const long long n = (long long)ntx_fused_ecol_floats(Rc);
+  ntx_ecol_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(col_lse, Rc, n, bound2, ecol);
+  MOLCLR_CHECK_LAUNCH("ntx_ecol");
+  CUtensorMap tmQ, tmK;
+  int rc = gemm_make_tmap_f16(&tmQ, rep16, C, R, ld16, NF_BM);
+  if (rc) return rc;
+  rc = gemm_make_tmap_f16(&tmK, cols16, C, Rc, ld16, NF_BN);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(ntx_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NF_SMEM_BYTES);
+    if (e != cudaSuccess) return cuda_fail(e, "ntx_bwd_fused: cudaFuncSetAttribute");
+    attr_set = true;
+  }
+  const int total = p.row_tiles * p.splits;
+  const int grid = total < sm_count() ? total : sm_count();
+  ntx_bwd_fused_kernel<<<grid, NF_THREADS, NF_SMEM_BYTES, stream>>>(tmQ, tmK, p);
+  MOLCLR_CHECK_LAUNCH("ntx_bwd_fused");
+  return 0;
+}
+
+}  // namespace molclr
