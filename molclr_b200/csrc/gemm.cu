@@ -226,8 +226,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------ TMA producer (whole warp walks the loop with warp-uniform
+    // coordinates and addresses; one elected lane issues the copies)
+    {
       uint32_t it = 0;                                  // global k-block counter -> ring slot / phase
       for (int t = worker; t < total; t += num_workers) {
         const int nb0 = (t % n_tiles) * BN;                                  // first column of the tile
@@ -238,6 +239,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = 0; i < nkb; ++i, ++it) {
           const int s = it % Cfg::STAGES;
           ptx::mbar_wait(empty_bar + s, ((it / Cfg::STAGES) & 1) ^ 1);
+          if (ptx::elect_one()) {
           // derive_lo: the fp32 A tile goes to a CTA-local barrier (the converter warps of THIS CTA consume it) and no A_lo is loaded
           // mixed: both raw tiles go to the CTA-local barrier and the MMA issuer waits for the converters only
           if (rank == 0 && !mixed) ptx::mbar_arrive_expect_tx(full_bar + s, derive ? (TWO ? 2 : 1) * 2 * Cfg::B_BYTES : Cfg::TX_BYTES);
@@ -277,15 +279,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 load(bd + j * Cfg::MN_BLOCK_BYTES, mb, colb, kc);
               }
           }
+          }
+          __syncwarp();
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0 && rank == 0) {
-      // fp16 operands (K-major): the same 128-byte-row tiles and descriptors, K = 16 (32 bytes) per kind::f16 instruction
+    // The whole warp walks the loop, so that descriptors and barrier addresses are warp-uniform values (uniform registers, no
+    // per-lane "waterfall" moves into them); one elected lane issues the tcgen05 instructions.  This thread sits between "stage
+    // full" and "stage free again": every instruction here is on the ring's critical path.
+    if (rank == 0) {
       constexpr bool h16 = H16;
+      // fp16 operands (K-major): the same 128-byte-row tiles and descriptors, K = 16 (32 bytes) per kind::f16 instruction
       const uint32_t idesc = h16 ? ptx::make_idesc_f16(Cfg::N1, TILE_M) : ptx::make_idesc_tf32(Cfg::N1, p.a_mn != 0, p.b_mn != 0, TILE_M);
       const uint32_t idesc2 = ptx::make_idesc_tf32(Cfg::N2 > 0 ? Cfg::N2 : 16, p.a_mn != 0, p.b_mn != 0, TILE_M);
       const uint32_t idesc16 = ptx::make_idesc_bf16(Cfg::N1, TILE_M);
@@ -302,6 +309,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t a_sbo = p.a_mn ? 512u : kmaj_sbo, b_sbo = p.b_mn ? 512u : kmaj_sbo;
       const uint32_t a_lay = p.a_mn ? ptx::kLayoutSw128Base32 : kmaj_lay, b_lay = p.b_mn ? ptx::kLayoutSw128Base32 : kmaj_lay;
       const uint32_t a_kstep = p.a_mn ? 1024u : 32u, b_kstep = p.b_mn ? 1024u : 32u;   // bytes per K=8 slice
+      // descriptors without the start address: its 14-bit field (bytes / 16; shared memory is < 256 KB) is added per MMA
+      const uint64_t a_d0 = ptx::make_smem_desc(0u, a_lbo, a_sbo, a_lay), b_d0 = ptx::make_smem_desc(0u, b_lbo, b_sbo, b_lay);
+      const uint64_t h_d0 = ptx::make_smem_desc(0u, 16u, 512u, ptx::kLayoutSw64);
+      const uint32_t smem_base = ptx::smem_u32(smem);
       uint32_t it = 0, tl = 0;                          // tl = local tile counter -> accumulator buffer / phase
       for (int t = worker; t < total; t += num_workers, ++tl) {
         const int kb0 = (t / (n_tiles * m_tiles)) * p.kb_per_split;
@@ -316,41 +327,40 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (!mixed) ptx::mbar_wait(full_bar + s, (it / Cfg::STAGES) & 1);
           if (derive) ptx::mbar_wait(conv_bar + s, (it / Cfg::STAGES) & 1);
           ptx::tc_fence_after();
-          const uint32_t a_base = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint32_t a_base = smem_base + s * Cfg::STAGE_BYTES;
           const uint32_t b_base = a_base + (FOUR ? 2 : 1) * Cfg::A_BYTES;
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < Cfg::BK / 8; ++k) {
-            const uint64_t ad = ptx::make_smem_desc(a_base + k * a_kstep, a_lbo, a_sbo, a_lay);
-            const uint64_t bd = ptx::make_smem_desc(b_base + k * b_kstep, b_lbo, b_sbo, b_lay);
-            mma(d_tmem, ad, bd, (i | k) != 0 ? 1u : 0u);
-            if (Cfg::N2 > 0) {     // wide tile: the remaining N2 columns (MN-major B: its blocks follow those of the first MMA)
-              constexpr uint32_t b2_off = (uint32_t)((TWO ? Cfg::N1 / 2 : Cfg::N1) / 32) * Cfg::MN_BLOCK_BYTES;
-              const uint64_t bdw = ptx::make_smem_desc(b_base + b2_off + k * b_kstep, b_lbo, b_sbo, b_lay);
-              mma_i(d_tmem + Cfg::N1, ad, bdw, idesc2, (i | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < Cfg::BK / 8; ++k) {
+              const uint64_t ad = a_d0 + ((a_base + k * a_kstep) >> 4);
+              const uint64_t bd = b_d0 + ((b_base + k * b_kstep) >> 4);
+              mma(d_tmem, ad, bd, (i | k) != 0 ? 1u : 0u);
+              if (Cfg::N2 > 0) {     // wide tile: the remaining N2 columns (MN-major B: its blocks follow those of the first MMA)
+                constexpr uint32_t b2_off = (uint32_t)((TWO ? Cfg::N1 / 2 : Cfg::N1) / 32) * Cfg::MN_BLOCK_BYTES;
+                mma_i(d_tmem + Cfg::N1, ad, bd + (b2_off >> 4), idesc2, (i | k) != 0 ? 1u : 0u);
+              }
+              if (FOUR && !mixed) {
+                const uint64_t ad2 = ad + (Cfg::A_BYTES >> 4), bd2 = bd + (Cfg::B_BYTES >> 4);
+                mma(d_tmem, ad2, bd, 1u);          // A_lo * B_hi
+                mma(d_tmem, ad, bd2, 1u);          // A_hi * B_lo
+              }
             }
-            if (FOUR && !mixed) {
-              const uint64_t ad2 = ptx::make_smem_desc(a_base + Cfg::A_BYTES + k * a_kstep, a_lbo, a_sbo, a_lay);
-              const uint64_t bd2 = ptx::make_smem_desc(b_base + Cfg::B_BYTES + k * b_kstep, b_lbo, b_sbo, b_lay);
-              mma(d_tmem, ad2, bd, 1u);          // A_lo * B_hi
-              mma(d_tmem, ad, bd2, 1u);          // A_hi * B_lo
-            }
-          }
-          if (mixed && !(p.debug & 4)) {
-            // correction passes on the bf16 tiles: K-major rows of 32 bf16 = 64 bytes (64B swizzle, 8-row groups 512 B apart),
-            // K = 16 (32 bytes) per instruction
+            if (mixed && !(p.debug & 4)) {
+              // correction passes on the bf16 tiles: K-major rows of 32 bf16 = 64 bytes (64B swizzle, 8-row groups 512 B apart),
+              // K = 16 (32 bytes) per instruction
 #pragma unroll
-            for (int k = 0; k < Cfg::BK / 16; ++k) {
-              const uint64_t ah = ptx::make_smem_desc(a_base + Cfg::A_BYTES + k * 32u, 16u, 512u, ptx::kLayoutSw64);
-              const uint64_t al = ptx::make_smem_desc(a_base + Cfg::A_BYTES + Cfg::A_BYTES / 2 + k * 32u, 16u, 512u, ptx::kLayoutSw64);
-              const uint64_t bh = ptx::make_smem_desc(b_base + Cfg::B_BYTES + k * 32u, 16u, 512u, ptx::kLayoutSw64);
-              const uint64_t bl = ptx::make_smem_desc(b_base + Cfg::B_BYTES + Cfg::B_BYTES / 2 + k * 32u, 16u, 512u, ptx::kLayoutSw64);
-              if (TWO) { ptx::mma_f16_ss_2cta(d_tmem, al, bh, idesc16, 1u); ptx::mma_f16_ss_2cta(d_tmem, ah, bl, idesc16, 1u); }
-              else { ptx::mma_f16_ss(d_tmem, al, bh, idesc16, 1u); ptx::mma_f16_ss(d_tmem, ah, bl, idesc16, 1u); }
+              for (int k = 0; k < Cfg::BK / 16; ++k) {
+                const uint64_t ah = h_d0 + ((a_base + Cfg::A_BYTES + k * 32u) >> 4), al = ah + (Cfg::A_BYTES / 2 >> 4);
+                const uint64_t bh = h_d0 + ((b_base + Cfg::B_BYTES + k * 32u) >> 4), bl = bh + (Cfg::B_BYTES / 2 >> 4);
+                if (TWO) { ptx::mma_f16_ss_2cta(d_tmem, al, bh, idesc16, 1u); ptx::mma_f16_ss_2cta(d_tmem, ah, bl, idesc16, 1u); }
+                else { ptx::mma_f16_ss(d_tmem, al, bh, idesc16, 1u); ptx::mma_f16_ss(d_tmem, ah, bl, idesc16, 1u); }
+              }
             }
+            commit(empty_bar + s);          // frees the smem slot (of both CTAs) once these MMAs have read it
+            if (i == nkb - 1) commit(tfull_bar + buf);          // accumulator complete
           }
-          commit(empty_bar + s);          // frees the smem slot (of both CTAs) once these MMAs have read it
+          __syncwarp();
         }
-        commit(tfull_bar + buf);          // accumulator complete
       }
     }
     __syncwarp();

@@ -7,7 +7,7 @@
 //              the first product of its block to the second, so the ring has to cover the TMA latency with two blocks of work)
 //   MMA warp : S_j = Q . K_j^T (kind::f16, accumulator double-buffered in TMEM), then  dZ += W_j . K_j  with the SAME shared
 //              memory tile read MN-major as the "V" operand (dZ [128][C] fp32 stays in TMEM for the whole range)
-//   8 warps  : S_j TMEM -> registers (thread = row) -> W_j 2^10 = 2^(s k2 - bound) (2^(10 + bound - lse_r) + 2^(10 + bound - lse_k))
+//   2 x 8 warps (alternating blocks): S_j TMEM -> registers (thread = row) -> W_j 2^10 = 2^(s k2 - bound) (2^(10 + bound - lse_r) + 2^(10 + bound - lse_k))
 //              -> fp16 -> K-major swizzled shared-memory tile (the A operand of the second product)
 // i.e. the flash-attention forward loop with a fixed shift instead of a running maximum (|logit| <= 1/tau is known a priori)
 // and no normalisation (the log-sum-exps come from the forward pass).  Row tiles x candidate splits fill the GPU; each
@@ -34,9 +34,10 @@ constexpr int NF_EC_OFF = NF_Q_BYTES + NF_STAGES * NF_STAGE_BYTES + 2 * NF_P_BYT
 constexpr int NF_BAR_OFF = NF_EC_OFF + NF_STAGES * NF_BN * 4;
 constexpr int NF_SMEM_BYTES = NF_BAR_OFF + 256;
 static_assert(NF_SMEM_BYTES <= 232448, "shared memory budget");
-constexpr int NF_THREADS = 64 + 8 * 32;
+constexpr int NF_WGROUPS = 2;                             // weight-warp groups of 8 warps: group g forms the weights of blocks j = g mod 2
+constexpr int NF_THREADS = 64 + NF_WGROUPS * 8 * 32;
 constexpr int NF_TMEM_S = 256;                            // TMEM columns [0, 256): dZ; [256, 512): four S buffers
-constexpr int NF_AHEAD = 2;                               // S products issued ahead of the block whose weights are being formed
+constexpr int NF_AHEAD = 2;                               // S products issued ahead of the block whose weights are being formed (default; <= 3)
 
 struct NtxFusedParams {
   int R, C, nsub, ksteps, npv;     // nsub = ceil(C/64) sub-tiles, ksteps = ceil(C/16) MMAs per S tile, npv = 16 ksteps (dZ columns)
@@ -44,6 +45,7 @@ struct NtxFusedParams {
   long long row_offset, row_split, row_offset2, num_cand;
   float k2, bound2, alpha;
   int swap_lbo;                    // (bring-up switch for the MN-major descriptor)
+  int ahead;                       // S products in flight ahead of the second product (1..3)
   const float* row_lse;
   const float* ecol;               // [nblocks * 64] column factors 2^(10 + bound - lse_k), 0 beyond Rc
   float* partials;                 // [splits][R][C]
@@ -82,7 +84,7 @@ ntx_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     for (int s = 0; s < NF_STAGES; ++s) { ptx::mbar_init(kv_full + s, 1); ptx::mbar_init(kv_empty + s, 1); }
     for (int b = 0; b < 4; ++b) { ptx::mbar_init(s_full + b, 1); ptx::mbar_init(s_empty + b, 8); }
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(p_full + b, 8); ptx::mbar_init(p_empty + b, 1); }
-    ptx::mbar_init(dz_full, 1); ptx::mbar_init(dz_empty, 8);
+    ptx::mbar_init(dz_full, 1); ptx::mbar_init(dz_empty, 8 * NF_WGROUPS);
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tmQ);
     ptx::prefetch_tensormap(&tmK);
@@ -165,9 +167,10 @@ ntx_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           __syncwarp();
         };
         // the S products run NF_AHEAD blocks ahead of the weight warps, so that neither side waits for the other's latency
-        for (int a = 0; a < NF_AHEAD && a < nb; ++a) issue_qk(it + a, a == nb - 1);
+        const int ahead = p.ahead;
+        for (int a = 0; a < ahead && a < nb; ++a) issue_qk(it + a, a == nb - 1);
         for (int j = 0; j < nb; ++j) {
-          if (j + NF_AHEAD < nb) issue_qk(it + j + NF_AHEAD, j + NF_AHEAD == nb - 1);
+          if (j + ahead < nb) issue_qk(it + j + ahead, j + ahead == nb - 1);
           const uint32_t g = it + j, st = g % NF_STAGES, pb = g & 1;       // dZ += W_j . K_j
           ptx::mbar_wait(p_full + pb, (g >> 1) & 1);
           if (j == 0) ptx::mbar_wait(dz_empty, (li & 1) ^ 1);
@@ -188,7 +191,7 @@ ntx_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
   } else {
     // ------------------------------------------------------------ weight warps: (q, half) = TMEM lane quadrant, 32-column share of a block
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int q = warp & 3, half = ((warp - 2) >> 2) & 1, grp = (warp - 2) >> 3;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float nb2 = -p.bound2;
@@ -203,6 +206,7 @@ ntx_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (pos >= p.num_cand) pos -= p.num_cand;
       const float er = grow < p.R ? ptx::ex2_approx(10.f + p.bound2 - __ldg(p.row_lse + grow) * 1.4426950408889634f) : 0.f;
       for (int b = b0; b < b1; ++b, ++it) {
+        if ((int)(it & 1) != grp) continue;                  // the other group's block (P buffer it & 1 belongs to group it & 1)
         const uint32_t sb = it & 3, pb = it & 1, st = it % NF_STAGES;
         ptx::mbar_wait(s_full + sb, (it >> 2) & 1);
         ptx::mbar_wait(kv_full + st, (it / NF_STAGES) & 1);      // (already complete: S_j was computed from this stage; orders the factor reads)
@@ -252,11 +256,12 @@ ntx_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(p_full + pb);
       }
-      // drain this item's dZ: thread = row, this warp's 128-column half, straight to the partial gradient of the split
+      // drain this item's dZ: thread = row, this warp's 64-column share, straight to the partial gradient of the split
       ptx::mbar_wait(dz_full, li & 1);
       ptx::tc_fence_after();
       float* orow = p.partials + ((size_t)sp * p.R + (size_t)(grow < p.R ? grow : 0)) * p.C;
-      for (int c0 = 128 * half; c0 < 128 * half + 128 && c0 < p.npv; c0 += 32) {
+      const int cw = 64 * (2 * grp + half);
+      for (int c0 = cw; c0 < cw + 64 && c0 < p.npv; c0 += 32) {
         float v[32];
         ptx::tmem_ld_x16_nowait(lane_addr + c0, v);
         ptx::tmem_ld_x16_nowait(lane_addr + c0 + 16, v + 16);
@@ -306,6 +311,9 @@ int ntx_bwd_fused(const __half* rep16, const __half* cols16, int ld16, int64_t R
   static int swap = -1;
   if (swap < 0) { const char* e = getenv("MOLCLR_NTX_SWAP_LBO"); swap = e ? atoi(e) : 0; }
   p.swap_lbo = swap;
+  static int ahead = -1;
+  if (ahead < 0) { const char* e = getenv("MOLCLR_NTX_AHEAD"); ahead = e ? atoi(e) : NF_AHEAD; if (ahead < 1 || ahead > 3) ahead = NF_AHEAD; }
+  p.ahead = ahead;
   p.row_lse = row_lse; p.ecol = ecol; p.partials = partials;
   const long long n = (long long)ntx_fused_ecol_floats(Rc);
   ntx_ecol_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(col_lse, Rc, n, bound2, ecol);
