@@ -248,6 +248,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           auto load = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
             if (TWO) ptx::tma_load_2d_2cta(dst, m, fb, c0, c1); else ptx::tma_load_2d(dst, m, full_bar + s, c0, c1);
           };
+          auto load3 = [&](void* dst, const CUtensorMap* m, int k0, int blk) {      // MN-major: several [k][32 mn] blocks at once
+            if (TWO) ptx::tma_load_3d_2cta(dst, m, fb, 0, k0, blk); else ptx::tma_load_3d(dst, m, full_bar + s, 0, k0, blk);
+          };
           uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
           uint8_t* b_dst = a_dst + (FOUR ? 2 : 1) * Cfg::A_BYTES;
           const int seg = FOUR ? 0 : i / nkb_seg;
@@ -265,12 +268,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   for (int j = 0; j < GEMM_BM / 32; ++j) ptx::tma_load_2d(ad + j * Cfg::MN_BLOCK_BYTES, ma, afull_bar + s, m0 + 32 * j, kc);
               }
             } else if (!p.a_mn) load(ad, ma, kc, m0);
+            else if (!FOUR && p.a_mn3d) load3(ad, &tmA2, kc, m0 >> 5);               // 4 blocks in one box
             else
               for (int j = 0; j < GEMM_BM / 32; ++j) load(ad + j * Cfg::MN_BLOCK_BYTES, ma, m0 + 32 * j, kc);
             if (mixed) {
               if (h == 0) ptx::tma_load_2d(bd, &tmB, afull_bar + s, kc, n0);
             } else if (!p.b_mn) load(bd, mb, kc, n0);
-            else
+            else if (!FOUR && p.b_mn3d) {
+              // this CTA's blocks of the first MMA (N1) in one box; the (shorter) N2 group of a wide tile keeps per-block copies
+              constexpr int J1 = (TWO ? Cfg::N1 / 2 : Cfg::N1) / 32;
+              load3(bd, &tmB2, kc, (nb0 + (int)rank * (TWO ? Cfg::N1 / 2 : 0)) >> 5);
+              for (int j = J1; j < Cfg::BN_CTA / 32; ++j)
+                load(bd + j * Cfg::MN_BLOCK_BYTES, mb, nb0 + Cfg::N1 + (int)rank * (Cfg::N2 / 2) + 32 * (j - J1), kc);
+            } else
               for (int j = 0; j < Cfg::BN_CTA / 32; ++j) {
                 // blocks of the first MMA (N1) first, then those of the second (N2); each CTA of a pair stages its half of both
                 constexpr int J1 = (TWO ? Cfg::N1 / 2 : Cfg::N1) / 32;
@@ -910,6 +920,26 @@ static int make_tmap(CUtensorMap* m, const float* base, int64_t inner, int64_t o
   return 0;
 }
 
+static bool gemm_no_mn3d();
+
+// 3-D tensor map over an MN-major operand [K][MN] (row pitch ld floats): dims {32 mn of a block, K, blocks of 32 mn}, box
+// {32, bk, nblk}: one copy lands nblk consecutive [bk k][32 mn] blocks in shared memory, each in the 32B-atom 128-byte swizzle
+// the tensor core wants.  Blocks beyond ceil(MN / 32) are zero-filled; the last block may read up to 31 floats of the row's
+// own padding (the caller checks ld >= MN rounded up to 32).
+static int make_tmap_mn3d(CUtensorMap* m, const float* base, int64_t mn, int64_t k, int64_t ld, int bk, int nblk) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  MOLCLR_REQUIRE(enc != nullptr, "gemm: cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {32u, (cuuint64_t)k, (cuuint64_t)((mn + 31) / 32)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(float), 128u};
+  cuuint32_t box[3] = {32u, (cuuint32_t)bk, (cuuint32_t)nblk};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MOLCLR_REQUIRE(r == CUDA_SUCCESS, "gemm: cuTensorMapEncodeTiled (3-D) failed with CUresult %d (mn=%lld k=%lld ld=%lld nblk=%d)", (int)r,
+                 (long long)mn, (long long)k, (long long)ld, nblk);
+  return 0;
+}
+
 template <int BN, bool FOUR, int KIND, bool TWO>
 static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, int splits, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, FOUR, TWO>;
@@ -925,6 +955,20 @@ static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, i
   rc = p.b_mn ? make_tmap(&tmB, j.B, p.N, p.K, j.ldb, 32, true, Cfg::BK) : make_tmap(&tmB, j.B, p.K, p.N, j.ldb, Cfg::BN_CTA, false, bk_el, h16);
   if (rc) return rc;
   tmA2 = tmA; tmB2 = tmB;
+  p.a_mn3d = p.b_mn3d = 0;
+  if (p.segments == 1 && !gemm_no_mn3d()) {
+    if (p.a_mn && j.lda >= (p.M + 31) / 32 * 32) {
+      rc = make_tmap_mn3d(&tmA2, j.A, p.M, p.K, j.lda, Cfg::BK, GEMM_BM / 32);
+      if (rc) return rc;
+      p.a_mn3d = 1;
+    }
+    constexpr int J1 = (TWO ? Cfg::N1 / 2 : Cfg::N1) / 32;
+    if (p.b_mn && J1 > 0 && j.ldb >= (p.N + 31) / 32 * 32) {
+      rc = make_tmap_mn3d(&tmB2, j.B, p.N, p.K, j.ldb, Cfg::BK, J1);
+      if (rc) return rc;
+      p.b_mn3d = 1;
+    }
+  }
   if (p.segments > 1) {
     if (j.A_lo) {
       rc = p.a_mn ? make_tmap(&tmA2, j.A_lo, p.M, p.K, j.lda, 32, true, Cfg::BK) : make_tmap(&tmA2, j.A_lo, p.K, p.M, j.lda, GEMM_BM, false, Cfg::BK);
@@ -958,6 +1002,12 @@ static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, i
   ++g_launches;
   if (e != cudaSuccess) return cuda_fail(e, "gemm_tf32 launch");
   return 0;
+}
+
+static bool gemm_no_mn3d() {          // MOLCLR_GEMM_MN3D=0: per-block 2-D copies for MN-major operands (A/B timing)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MOLCLR_GEMM_MN3D"); v = (e && atoi(e) == 0) ? 1 : 0; }
+  return v != 0;
 }
 
 static int gemm_debug_flags() {

@@ -11,6 +11,8 @@ enum GemmEpilogue : int { EPI_GENERIC = 0, EPI_NTX_FWD = 1, EPI_NTX_W = 2 };
 struct GemmParams {
   int M, N, K;
   int a_mn, b_mn;
+  int a_mn3d, b_mn3d;          // MN-major operand fetched with ONE 3-D TMA box per group of [k][32 mn] blocks (needs a row pitch >= the extent rounded
+                               // up to 32: the last block reads the row's own padding); the 3-D map travels in the tmA2 / tmB2 slot
   int half16;                  // operands are fp16 (K-major only, 64 elements per 128-byte tile row): tcgen05 kind::f16, fp32 accumulation
   int num_kb, kb_per_split;
   int n_tiles, m_tiles, splits;   // tile grid walked by the persistent CTAs (filled by the launcher)
