@@ -44,7 +44,6 @@ struct NtxFusedParams {
   int nblocks, row_tiles, splits;
   long long row_offset, row_split, row_offset2, num_cand;
   float k2, bound2, alpha;
-  int swap_lbo;                    // (bring-up switch for the MN-major descriptor)
   int ahead;                       // S products in flight ahead of the second product (1..3)
   const float* row_lse;
   const float* ecol;               // [nblocks * 64] column factors 2^(10 + bound - lse_k), 0 beyond Rc
@@ -135,8 +134,7 @@ ntx_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint64_t p_desc = ptx::make_smem_desc(ptx::smem_u32(p_s), 16u, 1024u, ptx::kLayoutSw128);
       // V descriptor: [64 candidates][64 halves] sub-tiles, 128-byte swizzle; along N (features) the sub-tiles are NF_KV_SUB apart,
       // along K (candidates) the 8-row groups 1024 B apart
-      const uint64_t v_desc = p.swap_lbo ? ptx::make_smem_desc(kv_base, 1024u, (uint32_t)NF_KV_SUB, ptx::kLayoutSw128)
-                                         : ptx::make_smem_desc(kv_base, (uint32_t)NF_KV_SUB, 1024u, ptx::kLayoutSw128);
+      const uint64_t v_desc = ptx::make_smem_desc(kv_base, (uint32_t)NF_KV_SUB, 1024u, ptx::kLayoutSw128);   // (LBO, SBO) checked on the GPU: the swapped pair fails parity
       const int ksteps = p.ksteps;
       uint32_t it = 0, li = 0;
       for (int item = blockIdx.x; item < total; item += gridDim.x, ++li) {
@@ -308,9 +306,6 @@ int ntx_bwd_fused(const __half* rep16, const __half* cols16, int ld16, int64_t R
   p.nblocks = (int)((Rc + NF_BN - 1) / NF_BN); p.row_tiles = (int)((R + NF_BM - 1) / NF_BM); p.splits = splits;
   p.row_offset = row_offset; p.row_split = R / 2; p.row_offset2 = row_offset2; p.num_cand = Rc;
   p.k2 = inv_temperature * 1.4426950408889634f; p.bound2 = bound2; p.alpha = inv_temperature * gscale * (1.f / 1024.f);
-  static int swap = -1;
-  if (swap < 0) { const char* e = getenv("MOLCLR_NTX_SWAP_LBO"); swap = e ? atoi(e) : 0; }
-  p.swap_lbo = swap;
   static int ahead = -1;
   if (ahead < 0) { const char* e = getenv("MOLCLR_NTX_AHEAD"); ahead = e ? atoi(e) : NF_AHEAD; if (ahead < 1 || ahead > 3) ahead = NF_AHEAD; }
   p.ahead = ahead;
