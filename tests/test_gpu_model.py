@@ -48,9 +48,11 @@ def test_ntxent_matches_reference_golden(path):
     assert rel_err(zjs.grad, torch.tensor(g["dzjs"])) < RTOL_GRAD
 
 
-# (6, 12): candidate count 12 = 4 mod 8 (ragged fp16 chunks); (2500, 256): two W stripes, the second one partial
+# (6, 12): candidate count 12 = 4 mod 8 (ragged fp16 chunks); (2500, 256): several candidate splits of the fused backward
 @pytest.mark.parametrize("n,c,tau,cos", [(512, 256, 0.1, True), (1500, 256, 0.1, True), (256, 64, 0.5, False), (6, 12, 0.1, True), (2500, 256, 0.1, True),
-                                         (2500, 64, 0.5, False)])
+                                         (2500, 64, 0.5, False),
+                                         # C > 256: the striped fp16 backward (W stripes + K-major cols^T) instead of the fused kernel
+                                         (300, 320, 0.1, True)])
 def test_ntxent_matches_closed_form(n, c, tau, cos):
     torch.manual_seed(n)
     a = torch.randn(n, c)
