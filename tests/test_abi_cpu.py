@@ -35,6 +35,20 @@ def test_library_loads_and_reports_version(lib_path):
     assert lib.molclr_gemm_colstat_tiles(129) == 8 and lib.molclr_gemm_colstat_tile_rows() == 32
 
 
+def test_ntxent_workspace_covers_both_backward_variants(lib_path):
+    """Host-only sizing: one buffer serves the forward partials, the fp16 operand copies, the striped backward (W stripe +
+    per-stripe partial gradients + cols^T) and the fused backward (32 split slots + column factors), for any shape."""
+    from molclr_b200 import _lib
+    lib = _lib.load()
+    for R, Rc, C in ((8, 8, 16), (12, 12, 12), (8192, 8192, 256), (8192, 65536, 256), (600, 600, 320)):
+        n = lib.molclr_ntxent_workspace_bytes(R, Rc, C)
+        ld16 = (C + 7) // 8 * 8
+        fused = 32 * R * C * 4 + (R + Rc) * ld16 * 2 + (Rc + 63) // 64 * 64 * 4
+        striped = R * 8192 + ((Rc + 2047) // 2048) * R * C * 4 + (R + Rc) * ld16 * 2 + C * ((Rc + 7) // 8 * 8) * 2
+        assert n >= fused and n >= striped, (R, Rc, C, n, fused, striped)
+        assert lib.molclr_ntxent_workspace_bytes(R, 2 * Rc, C) > n
+
+
 def test_gemm_args_struct_matches_header_layout():
     from molclr_b200._lib import GemmArgs
     # 8-byte aligned fields in header order; guards against silent drift between header and ctypes mirror
