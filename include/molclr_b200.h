@@ -261,8 +261,11 @@ int molclr_l2_normalize_bwd(const float* gy, const float* y, const float* inv_no
  *   backward: g_rep[r] = (gscale/tau) * sum_k (P[r][k] + P[k][r] - 2*[k = pos(r)]) * cols[k],
  *             P[i][k] = exp(S[i][k]/tau - lse[i]) for k != i; col_lse[Rc] holds the log-sum-exp of every
  *             candidate row (== row_lse on one GPU, all-gathered for global negatives); gscale = 1/Rc.
- * The Rc x Rc similarity matrix is never written to memory: backward works in L2-resident stripes of candidate columns
- * (64 MB at R = 8192); per-stripe partial gradients are summed in stripe order.  Requires R even, Rc % 4 == 0, C % 4 == 0.
+ * The Rc x Rc similarity matrix is never written to memory.  Backward, unit_rows with C <= 256 and 1/tau <= ~22: one fused
+ * kernel per call (S tile -> softmax weights -> second product on chip, the [128][C] gradient tile resident in TMEM) over
+ * row tiles x candidate splits, whose partial gradients are summed in split order (deterministic).  Otherwise: column
+ * stripes of W (2048 fp32 / 4096 fp16 candidates) staged through L2 between two GEMMs, partials summed in stripe order.
+ * Requires R even, Rc % 4 == 0, C % 4 == 0.
  * unit_rows != 0 promises that every row of rep and cols has norm <= 1 (the cosine similarity of nt_xent.py:40-45, rows
  * normalised by the caller): the tensor-core passes then run on FP16 copies of the rows (the 11-bit significand of TF32,
  * fp32 accumulation, twice the tensor rate; the softmax weights are staged as fp16 x 2^10).  unit_rows == 0 (dot similarity, nt_xent.py:32-38, rows of
