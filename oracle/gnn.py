@@ -275,6 +275,74 @@ class GINetFinetune(nn.Module):
         return h, self.pred_head(h)
 
 
+# ----------------------------------------------------------------------------- fine-tune GIN-E with motif attention
+def _group_softmax(src, index, num_groups):
+    """torch_geometric.utils.softmax 1.6.3 over dim 0: exp(src - max_g) / (sum_g exp + 1e-16); ATen primitives as PyG calls them
+    (scatter-max via ``scatter_reduce(amax)``, ``zeros.scatter_add_``)."""
+    idx = index.view(-1, 1).expand_as(src)
+    mx = torch.full((num_groups, src.shape[1]), float("-inf"), dtype=src.dtype).scatter_reduce(0, idx, src, reduce="amax", include_self=True)
+    out = (src - mx[index]).exp()
+    den = torch.zeros(num_groups, src.shape[1], dtype=src.dtype).scatter_add_(0, idx, out)
+    return out / (den[index] + 1e-16)
+
+
+class GINetMotif(nn.Module):
+    """models/ginet_finetune_mp.py:52-163 (the motif-level fine-tune model; SURVEY 8f item 3, not built as a kernel path yet):
+    the GIN-E encoder and ``feat_lin`` of the fine-tune model, then ``hp = motif_lin(GlobalAttention([motif_embedding[clique_idx];
+    h], mol_idx))`` and ``pred_head(cat(h, hp))`` with a ``2 * feat_dim`` wide first layer.  ``forward(data, mol_idx, clique_idx)``
+    returns ``(cat(h, hp), pred)``.  ``mol_idx`` lists the molecule of every clique followed by ``arange(G)`` (finetune.py:202-210)."""
+
+    def __init__(self, num_motifs, task="classification", num_layer=5, emb_dim=300, feat_dim=512, drop_ratio=0, pool="mean",
+                 pred_n_layer=2, pred_act="softplus"):
+        super().__init__()
+        self.num_motifs, self.num_layer, self.emb_dim, self.feat_dim = num_motifs, num_layer, emb_dim, feat_dim
+        self.drop_ratio, self.task = drop_ratio, task
+        self.x_embedding1 = nn.Embedding(num_atom_type, emb_dim)
+        self.x_embedding2 = nn.Embedding(num_chirality_tag, emb_dim)
+        nn.init.xavier_uniform_(self.x_embedding1.weight.data)
+        nn.init.xavier_uniform_(self.x_embedding2.weight.data)
+        self.motif_embedding = nn.Embedding(num_motifs, feat_dim)                   # ginet_finetune_mp.py:79
+        self.gnns = nn.ModuleList([GINEConv(emb_dim) for _ in range(num_layer)])
+        self.batch_norms = nn.ModuleList([nn.BatchNorm1d(emb_dim) for _ in range(num_layer)])
+        if pool in _POOLS:
+            self.pool = _POOLS[pool]
+        self.feat_lin = nn.Linear(emb_dim, feat_dim)
+        out_dim = {"classification": 2, "regression": 1}[task]
+        self.motif_lin = nn.Linear(feat_dim, feat_dim)                              # :104-105
+        nn.init.xavier_uniform_(self.motif_lin.weight.data)
+        self.motif_pool = nn.Module()                                               # GlobalAttention(gate_nn=Sequential(Linear(feat_dim, 1))), :107
+        self.motif_pool.gate_nn = nn.Sequential(nn.Linear(feat_dim, 1))
+        self.motif_pool.nn = None
+        self.pred_n_layer = max(1, pred_n_layer)
+        if pred_act not in ("relu", "softplus"):
+            raise ValueError("Undefined activation function")
+        act = {"relu": lambda: nn.ReLU(inplace=True), "softplus": nn.Softplus}[pred_act]   # :111-133
+        head = [nn.Linear(2 * feat_dim, feat_dim // 2), act()]
+        for _ in range(self.pred_n_layer - 1):
+            head.extend([nn.Linear(feat_dim // 2, feat_dim // 2), act()])
+        head.append(nn.Linear(feat_dim // 2, out_dim))
+        self.pred_head = nn.Sequential(*head)
+
+    def forward(self, data, mol_idx, clique_idx):
+        h = self.x_embedding1(data.x[:, 0]) + self.x_embedding2(data.x[:, 1])
+        for layer in range(self.num_layer):                                         # :146-152
+            h = self.gnns[layer](h, data.edge_index, data.edge_attr)
+            h = self.batch_norms[layer](h)
+            if layer == self.num_layer - 1:
+                h = _dropout(self, layer, h)
+            else:
+                h = _dropout(self, layer, F.relu(h))
+        h = self.pool(h, data.batch)
+        h = self.feat_lin(h)
+        hp = torch.cat((self.motif_embedding(clique_idx), h), dim=0)                # :157-158
+        groups = int(mol_idx[-1]) + 1                                               # GlobalAttention: size = batch[-1] + 1
+        gate = _group_softmax(self.motif_pool.gate_nn(hp).view(-1, 1), mol_idx, groups)
+        hp = torch.zeros(groups, hp.shape[1], dtype=hp.dtype).scatter_add_(0, mol_idx.view(-1, 1).expand_as(hp), gate * hp)
+        hp = self.motif_lin(hp)                                                     # :160
+        h = torch.cat((h, hp), dim=1)
+        return h, self.pred_head(h)
+
+
 # ----------------------------------------------------------------------------- fine-tune GCN
 class GCNFinetune(nn.Module):
     """models/gcn_finetune.py:94-163: the GCN encoder, ``feat_lin`` and ``pred_lin`` = Linear -> Softplus -> Linear(., 2 | 1);

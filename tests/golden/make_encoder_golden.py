@@ -33,6 +33,7 @@ from models.ginet_molclr import GINet as RefGINet            # noqa: E402  (the 
 from models.gcn_molclr import GCN as RefGCN                  # noqa: E402
 from models.ginet_finetune import GINet as RefGINetFinetune  # noqa: E402
 from models.gcn_finetune import GCN as RefGCNFinetune        # noqa: E402
+from models.ginet_finetune_mp import GINet as RefGINetMotif   # noqa: E402
 from utils.nt_xent import NTXentLoss                         # noqa: E402
 
 from molclr_b200.synth import make_pair_batch, make_plain_batch   # noqa: E402
@@ -150,6 +151,37 @@ def finetune_case(name, task, graphs, seed, wseed, gcn=False):
     print(name, float(loss))
 
 
+def motif_case(name, task, graphs, num_motifs, seed, wseed):
+    """models/ginet_finetune_mp.py GINet (motif embedding + GlobalAttention over [cliques of the molecule; the molecule]) with
+    ``mol_idx`` / ``clique_idx`` built as finetune.py:202-210 builds them, and the criteria of finetune.py:70-77."""
+    model = RefGINetMotif(num_motifs, task, 5, 300, 512, 0, "mean")
+    model.load_state_dict(golden_weights(model.state_dict(), wseed))
+    model.train()
+    b = make_plain_batch(graphs, seed=seed, mean_atoms=30.0, std_atoms=10.0)
+    g = torch.Generator().manual_seed(seed)
+    mol_idx, clique_idx = [], []
+    for i in range(graphs):                                    # every molecule owns 1..4 motifs (finetune.py:204-207)
+        for c in torch.randperm(num_motifs, generator=g)[:int(torch.randint(1, 5, (1,), generator=g))].tolist():
+            mol_idx.append(i)
+            clique_idx.append(c)
+    mol_idx.extend([i for i in range(max(mol_idx) + 1)])       # finetune.py:208
+    mol_idx, clique_idx = torch.tensor(mol_idx), torch.tensor(clique_idx)
+    if task == "classification":
+        y = (torch.rand(graphs, 1, generator=g) < 0.77).long()
+        crit = torch.nn.CrossEntropyLoss()
+    else:
+        y = -3.05 + 2.1 * torch.randn(graphs, 1, generator=g)
+        crit = torch.nn.MSELoss()
+    h, pred = model(b, mol_idx, clique_idx)
+    loss = crit(pred, y.flatten()) if task == "classification" else crit(pred, y)
+    loss.backward()
+    out = {"weight_seed": np.int64(wseed), "task": np.str_(task), "num_motifs": np.int64(num_motifs), "y": y.numpy(), "loss": loss.detach().numpy(),
+           "h": h.detach().numpy(), "pred": pred.detach().numpy(), "mol_idx": mol_idx.numpy(), "clique_idx": clique_idx.numpy()}
+    out.update(batch_arrays(b, "b")); out.update(grad_arrays(model))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, float(loss))
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     pretrain_case("enc_gin_pretrain", RefGINet, 24, seed=11, wseed=1)
@@ -162,3 +194,5 @@ if __name__ == "__main__":
     finetune_case("enc_finetune_reg", "regression", 12, seed=31, wseed=7)
     finetune_case("enc_gcn_finetune_cls", "classification", 12, seed=32, wseed=8, gcn=True)
     finetune_case("enc_gcn_finetune_reg", "regression", 12, seed=33, wseed=9, gcn=True)
+    motif_case("enc_motif_cls", "classification", 12, 20, seed=40, wseed=10)
+    motif_case("enc_motif_reg", "regression", 12, 20, seed=41, wseed=11)

@@ -16,6 +16,9 @@ What is restated, with the published algorithm of the pinned versions:
   per-segment count clamped to >= 1; max = segment maximum with empty segments left at 0.
 * ``add_self_loops``: ``cat([edge_index, arange(N).repeat(2, 1)], dim=1)`` -- the loops go LAST.
 * ``global_{add,mean,max}_pool(x, batch)``: ``scatter(x, batch, dim=0, dim_size=batch.max() + 1, reduce=...)``.
+* ``GlobalAttention(gate_nn)`` and ``utils.softmax`` (the motif model, ``models/ginet_finetune_mp.py:107,158``): group-wise
+  softmax of the gate (max-shifted, ``+ 1e-16`` in the denominator) and ``scatter_add`` of ``gate * x``; the number of groups
+  defaults to ``batch[-1] + 1``.
 """
 import inspect
 import sys
@@ -190,6 +193,34 @@ class MessagePassing(torch.nn.Module):
         return inputs
 
 
+def softmax(src, index, ptr=None, num_nodes=None):
+    """torch_geometric.utils.softmax, 1.6.3: group-wise softmax over dim 0 -- subtract the group maximum, exponentiate, divide by
+    (group sum + 1e-16)."""
+    N = maybe_num_nodes(index, num_nodes)
+    out = src - scatter_max(src, index, dim=0, dim_size=N)[0][index]
+    out = out.exp()
+    return out / (scatter_add(out, index, dim=0, dim_size=N)[index] + 1e-16)
+
+
+class GlobalAttention(torch.nn.Module):
+    """torch_geometric.nn.GlobalAttention, 1.6.3: r_g = sum_{n in g} softmax_g(gate_nn(x_n)) * nn(x_n); ``size`` defaults to
+    ``batch[-1].item() + 1`` (the LAST entry of ``batch``, not its maximum)."""
+
+    def __init__(self, gate_nn, nn=None):
+        super().__init__()
+        self.gate_nn = gate_nn
+        self.nn = nn
+
+    def forward(self, x, batch, size=None):
+        x = x.unsqueeze(-1) if x.dim() == 1 else x
+        size = batch[-1].item() + 1 if size is None else size
+        gate = self.gate_nn(x).view(-1, 1)
+        x = self.nn(x) if self.nn is not None else x
+        assert gate.dim() == x.dim() and gate.size(0) == x.size(0)
+        gate = softmax(gate, batch, num_nodes=size)
+        return scatter_add(gate * x, batch, dim=0, dim_size=size)
+
+
 def _unused(name):
     def f(*a, **k):
         raise NotImplementedError(f"{name}: imported by the reference but not on the MolCLR hot path (pyg163_stub)")
@@ -210,9 +241,10 @@ def install():
     tsp = mod("torch_sparse", SparseTensor=type("SparseTensor", (), {}), matmul=_unused("matmul"), fill_diag=_unused("fill_diag"),
               sum=_unused("sum"), mul=_unused("mul"))
     nn = mod("torch_geometric.nn", MessagePassing=MessagePassing, GCNConv=type("GCNConv", (), {}), global_add_pool=global_add_pool,
-             global_mean_pool=global_mean_pool, global_max_pool=global_max_pool, GlobalAttention=_unused("GlobalAttention"))
+             global_mean_pool=global_mean_pool, global_max_pool=global_max_pool, GlobalAttention=GlobalAttention,
+             Set2Set=_unused("Set2Set"))
     num_nodes = mod("torch_geometric.utils.num_nodes", maybe_num_nodes=maybe_num_nodes)
-    utils = mod("torch_geometric.utils", add_self_loops=add_self_loops, degree=_unused("degree"), softmax=_unused("softmax"),
+    utils = mod("torch_geometric.utils", add_self_loops=add_self_loops, degree=_unused("degree"), softmax=softmax,
                 num_nodes=num_nodes)
     mod("torch_geometric", nn=nn, utils=utils, __version__="1.6.3-restated")
     return ts, tsp

@@ -72,6 +72,22 @@ def test_oracle_finetune_matches_reference_model(task, gcn):
     assert not check_golden_grads(m, g, TOL_GRAD)
 
 
+@pytest.mark.parametrize("task", ["cls", "reg"])
+def test_oracle_motif_model_matches_reference_model(task):
+    """models/ginet_finetune_mp.py (motif embedding + GlobalAttention): the oracle of the next widening row,
+    pinned before a kernel path exists."""
+    g = np.load(os.path.join(GOLDEN, f"enc_motif_{task}.npz"))
+    m = _load(ognn.GINetMotif(int(g["num_motifs"]), str(g["task"]), 5, 300, 512, 0, "mean"), g)
+    h, pred = m(golden_batch(g, "b"), torch.from_numpy(g["mol_idx"]), torch.from_numpy(g["clique_idx"]))
+    y = torch.from_numpy(g["y"])
+    loss = torch.nn.CrossEntropyLoss()(pred, y.flatten()) if task == "cls" else torch.nn.MSELoss()(pred, y)
+    loss.backward()
+    assert h.shape[1] == 2 * 512
+    assert max_rel(h, torch.from_numpy(g["h"])) < TOL and max_rel(pred, torch.from_numpy(g["pred"])) < TOL
+    np.testing.assert_allclose(loss.item(), float(g["loss"]), rtol=2e-6)
+    assert not check_golden_grads(m, g, TOL_GRAD)
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference not mounted")
 def test_fixtures_reproduce_from_the_live_reference():
     """Dev container only: re-running the unmodified reference GINet on the restated PyG base reproduces the fixture bit for bit."""
