@@ -240,55 +240,55 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int s = it % Cfg::STAGES;
           ptx::mbar_wait(empty_bar + s, ((it / Cfg::STAGES) & 1) ^ 1);
           if (ptx::elect_one()) {
-          // derive_lo: the fp32 A tile goes to a CTA-local barrier (the converter warps of THIS CTA consume it) and no A_lo is loaded
-          // mixed: both raw tiles go to the CTA-local barrier and the MMA issuer waits for the converters only
-          if (rank == 0 && !mixed) ptx::mbar_arrive_expect_tx(full_bar + s, derive ? (TWO ? 2 : 1) * 2 * Cfg::B_BYTES : Cfg::TX_BYTES);
-          if (derive) ptx::mbar_arrive_expect_tx(afull_bar + s, mixed ? Cfg::A_BYTES + Cfg::B_BYTES : Cfg::A_BYTES);
-          const uint32_t fb = TWO ? ptx::mapa(ptx::smem_u32(full_bar + s), 0u) : 0u;     // the leader's barrier
-          auto load = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
-            if (TWO) ptx::tma_load_2d_2cta(dst, m, fb, c0, c1); else ptx::tma_load_2d(dst, m, full_bar + s, c0, c1);
-          };
-          auto load3 = [&](void* dst, const CUtensorMap* m, int k0, int blk) {      // MN-major: several [k][32 mn] blocks at once
-            if (TWO) ptx::tma_load_3d_2cta(dst, m, fb, 0, k0, blk); else ptx::tma_load_3d(dst, m, full_bar + s, 0, k0, blk);
-          };
-          uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
-          uint8_t* b_dst = a_dst + (FOUR ? 2 : 1) * Cfg::A_BYTES;
-          const int seg = FOUR ? 0 : i / nkb_seg;
-          const int kc = (kb0 + (i - seg * nkb_seg)) * (H16 ? 2 * Cfg::BK : Cfg::BK);   // fp16: 64 elements per 128-byte tile row
-#pragma unroll
-          for (int h = 0; h < (FOUR ? 2 : 1); ++h) {
-            const CUtensorMap* ma = (FOUR ? h == 1 : seg == 1) ? &tmA2 : &tmA;
-            const CUtensorMap* mb = (FOUR ? h == 1 : seg == 2) ? &tmB2 : &tmB;
-            uint8_t* ad = a_dst + h * Cfg::A_BYTES;
-            uint8_t* bd = b_dst + h * Cfg::B_BYTES;
-            if (derive) {
-              if (h == 0) {
-                if (!p.a_mn) ptx::tma_load_2d(ad, ma, afull_bar + s, kc, m0);
-                else
-                  for (int j = 0; j < GEMM_BM / 32; ++j) ptx::tma_load_2d(ad + j * Cfg::MN_BLOCK_BYTES, ma, afull_bar + s, m0 + 32 * j, kc);
-              }
-            } else if (!p.a_mn) load(ad, ma, kc, m0);
-            else if (!FOUR && p.a_mn3d) load3(ad, &tmA2, kc, m0 >> 5);               // 4 blocks in one box
-            else
-              for (int j = 0; j < GEMM_BM / 32; ++j) load(ad + j * Cfg::MN_BLOCK_BYTES, ma, m0 + 32 * j, kc);
-            if (mixed) {
-              if (h == 0) ptx::tma_load_2d(bd, &tmB, afull_bar + s, kc, n0);
-            } else if (!p.b_mn) load(bd, mb, kc, n0);
-            else if (!FOUR && p.b_mn3d) {
-              // this CTA's blocks of the first MMA (N1) in one box; the (shorter) N2 group of a wide tile keeps per-block copies
-              constexpr int J1 = (TWO ? Cfg::N1 / 2 : Cfg::N1) / 32;
-              load3(bd, &tmB2, kc, (nb0 + (int)rank * (TWO ? Cfg::N1 / 2 : 0)) >> 5);
-              for (int j = J1; j < Cfg::BN_CTA / 32; ++j)
-                load(bd + j * Cfg::MN_BLOCK_BYTES, mb, nb0 + Cfg::N1 + (int)rank * (Cfg::N2 / 2) + 32 * (j - J1), kc);
-            } else
-              for (int j = 0; j < Cfg::BN_CTA / 32; ++j) {
-                // blocks of the first MMA (N1) first, then those of the second (N2); each CTA of a pair stages its half of both
+            // derive_lo: the fp32 A tile goes to a CTA-local barrier (the converter warps of THIS CTA consume it) and no A_lo is loaded
+            // mixed: both raw tiles go to the CTA-local barrier and the MMA issuer waits for the converters only
+            if (rank == 0 && !mixed) ptx::mbar_arrive_expect_tx(full_bar + s, derive ? (TWO ? 2 : 1) * 2 * Cfg::B_BYTES : Cfg::TX_BYTES);
+            if (derive) ptx::mbar_arrive_expect_tx(afull_bar + s, mixed ? Cfg::A_BYTES + Cfg::B_BYTES : Cfg::A_BYTES);
+            const uint32_t fb = TWO ? ptx::mapa(ptx::smem_u32(full_bar + s), 0u) : 0u;     // the leader's barrier
+            auto load = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
+              if (TWO) ptx::tma_load_2d_2cta(dst, m, fb, c0, c1); else ptx::tma_load_2d(dst, m, full_bar + s, c0, c1);
+            };
+            auto load3 = [&](void* dst, const CUtensorMap* m, int k0, int blk) {      // MN-major: several [k][32 mn] blocks at once
+              if (TWO) ptx::tma_load_3d_2cta(dst, m, fb, 0, k0, blk); else ptx::tma_load_3d(dst, m, full_bar + s, 0, k0, blk);
+            };
+            uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
+            uint8_t* b_dst = a_dst + (FOUR ? 2 : 1) * Cfg::A_BYTES;
+            const int seg = FOUR ? 0 : i / nkb_seg;
+            const int kc = (kb0 + (i - seg * nkb_seg)) * (H16 ? 2 * Cfg::BK : Cfg::BK);   // fp16: 64 elements per 128-byte tile row
+  #pragma unroll
+            for (int h = 0; h < (FOUR ? 2 : 1); ++h) {
+              const CUtensorMap* ma = (FOUR ? h == 1 : seg == 1) ? &tmA2 : &tmA;
+              const CUtensorMap* mb = (FOUR ? h == 1 : seg == 2) ? &tmB2 : &tmB;
+              uint8_t* ad = a_dst + h * Cfg::A_BYTES;
+              uint8_t* bd = b_dst + h * Cfg::B_BYTES;
+              if (derive) {
+                if (h == 0) {
+                  if (!p.a_mn) ptx::tma_load_2d(ad, ma, afull_bar + s, kc, m0);
+                  else
+                    for (int j = 0; j < GEMM_BM / 32; ++j) ptx::tma_load_2d(ad + j * Cfg::MN_BLOCK_BYTES, ma, afull_bar + s, m0 + 32 * j, kc);
+                }
+              } else if (!p.a_mn) load(ad, ma, kc, m0);
+              else if (!FOUR && p.a_mn3d) load3(ad, &tmA2, kc, m0 >> 5);               // 4 blocks in one box
+              else
+                for (int j = 0; j < GEMM_BM / 32; ++j) load(ad + j * Cfg::MN_BLOCK_BYTES, ma, m0 + 32 * j, kc);
+              if (mixed) {
+                if (h == 0) ptx::tma_load_2d(bd, &tmB, afull_bar + s, kc, n0);
+              } else if (!p.b_mn) load(bd, mb, kc, n0);
+              else if (!FOUR && p.b_mn3d) {
+                // this CTA's blocks of the first MMA (N1) in one box; the (shorter) N2 group of a wide tile keeps per-block copies
                 constexpr int J1 = (TWO ? Cfg::N1 / 2 : Cfg::N1) / 32;
-                const int colb = j < J1 ? nb0 + (int)rank * (TWO ? Cfg::N1 / 2 : 0) + 32 * j
-                                        : nb0 + Cfg::N1 + (int)rank * (Cfg::N2 / 2) + 32 * (j - J1);
-                load(bd + j * Cfg::MN_BLOCK_BYTES, mb, colb, kc);
-              }
-          }
+                load3(bd, &tmB2, kc, (nb0 + (int)rank * (TWO ? Cfg::N1 / 2 : 0)) >> 5);
+                for (int j = J1; j < Cfg::BN_CTA / 32; ++j)
+                  load(bd + j * Cfg::MN_BLOCK_BYTES, mb, nb0 + Cfg::N1 + (int)rank * (Cfg::N2 / 2) + 32 * (j - J1), kc);
+              } else
+                for (int j = 0; j < Cfg::BN_CTA / 32; ++j) {
+                  // blocks of the first MMA (N1) first, then those of the second (N2); each CTA of a pair stages its half of both
+                  constexpr int J1 = (TWO ? Cfg::N1 / 2 : Cfg::N1) / 32;
+                  const int colb = j < J1 ? nb0 + (int)rank * (TWO ? Cfg::N1 / 2 : 0) + 32 * j
+                                          : nb0 + Cfg::N1 + (int)rank * (Cfg::N2 / 2) + 32 * (j - J1);
+                  load(bd + j * Cfg::MN_BLOCK_BYTES, mb, colb, kc);
+                }
+            }
           }
           __syncwarp();
         }
