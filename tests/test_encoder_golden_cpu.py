@@ -88,6 +88,32 @@ def test_oracle_motif_model_matches_reference_model(task):
     assert not check_golden_grads(m, g, TOL_GRAD)
 
 
+@pytest.mark.parametrize("task", ["cls", "reg"])
+def test_motif_dropin_head_and_layout_match_reference_model(task):
+    """The drop-in ``molclr_b200.ginet_finetune_mp.GINet``: same state_dict layout as the reference class (through the oracle, whose
+    layout the fixture loader pins), and its motif branch -- plain tensor operations, device-agnostic -- reproduces the reference's
+    outputs and head gradients when fed the reference's molecule features ``h[:, :feat_dim]``.  (The encoder in front of it needs the GPU.)"""
+    from molclr_b200 import ginet_finetune_mp
+    g = np.load(os.path.join(GOLDEN, f"enc_motif_{task}.npz"))
+    m = ginet_finetune_mp.GINet(int(g["num_motifs"]), str(g["task"]), 5, 300, 512, 0, "mean")
+    o = ognn.GINetMotif(int(g["num_motifs"]), str(g["task"]), 5, 300, 512, 0, "mean")
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in o.state_dict().items()}
+    _load(m, g)
+    feat = torch.from_numpy(g["h"])[:, :512].clone().requires_grad_(True)
+    h, pred = m.motif_head(feat, torch.from_numpy(g["mol_idx"]), torch.from_numpy(g["clique_idx"]))
+    y = torch.from_numpy(g["y"])
+    loss = torch.nn.CrossEntropyLoss()(pred, y.flatten()) if task == "cls" else torch.nn.MSELoss()(pred, y)
+    loss.backward()
+    assert max_rel(h, torch.from_numpy(g["h"])) < TOL and max_rel(pred, torch.from_numpy(g["pred"])) < TOL
+    np.testing.assert_allclose(loss.item(), float(g["loss"]), rtol=2e-6)
+    head = [k for k, _ in m.named_parameters() if k.startswith(("motif_", "pred_head"))]
+    assert len(head) >= 9
+    bad = check_golden_grads(m, g, TOL_GRAD, skip=tuple(k for k, _ in m.named_parameters() if k not in head))
+    assert not bad, bad
+    with pytest.raises(RuntimeError):        # no CPU path for the encoder
+        m(golden_batch(g, "b"), torch.from_numpy(g["mol_idx"]), torch.from_numpy(g["clique_idx"]))
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference not mounted")
 def test_fixtures_reproduce_from_the_live_reference():
     """Dev container only: re-running the unmodified reference GINet on the restated PyG base reproduces the fixture bit for bit."""
