@@ -86,8 +86,8 @@ def test_finetune_matches_reference_model(task, gcn):
     assert not bad, bad
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: the encoder + feat_lin Function of "
-                                        "ginet_finetune_mp.py has not run on a GPU yet (its motif head is pinned on CPU)")
+@pytest.mark.xfail(strict=False, reason="written when the round's GPU budget was spent: one 5-second GPU run failed before the zero-gradient "
+                                        "gate bias was excluded from the gradient comparison; not re-run since (the motif head is pinned on CPU)")
 @pytest.mark.parametrize("task", ["cls", "reg"])
 def test_motif_model_matches_reference_model(task):
     """models/ginet_finetune_mp.py (motif embedding + GlobalAttention) against the reference class's golden vectors."""
@@ -99,5 +99,6 @@ def test_motif_model_matches_reference_model(task):
     loss.backward()
     assert max_rel(h, torch.from_numpy(g["h"])) < RTOL_OUT and max_rel(pred, torch.from_numpy(g["pred"])) < RTOL_OUT
     assert abs(loss.item() - float(g["loss"])) < RTOL_LOSS * abs(float(g["loss"]))
-    bad = check_golden_grads(m, g, RTOL_GRAD, skip=_zero_grad_skips(m))
+    # the gate bias shifts every logit of a softmax group alike: its true gradient is 0 and both sides hold rounding noise
+    bad = check_golden_grads(m, g, RTOL_GRAD, skip=_zero_grad_skips(m) + ("motif_pool.gate_nn.0.bias",))
     assert not bad, bad
