@@ -5,7 +5,7 @@
 // One CTA owns a tile of 128 local rows (its fp16 rows stay in shared memory) and walks a range of 64-candidate blocks:
 //   TMA      : block j of cols (fp16 [64][C], 128-byte swizzle) + its 64 column factors -> 4-stage ring (a stage is held from
 //              the first product of its block to the second, so the ring has to cover the TMA latency with two blocks of work)
-//   MMA warp : S_j = Q . K_j^T (kind::f16, accumulator double-buffered in TMEM), then  dZ += W_j . K_j  with the SAME shared
+//   MMA warp : S_j = Q . K_j^T (kind::f16, four S buffers in TMEM, issued two blocks ahead), then  dZ += W_j . K_j  with the SAME shared
 //              memory tile read MN-major as the "V" operand (dZ [128][C] fp32 stays in TMEM for the whole range)
 //   2 x 8 warps (alternating blocks): S_j TMEM -> registers (thread = row) -> W_j 2^10 = 2^(s k2 - bound) (2^(10 + bound - lse_r) + 2^(10 + bound - lse_k))
 //              -> fp16 -> K-major swizzled shared-memory tile (the A operand of the second product)
