@@ -111,18 +111,41 @@ def cpu_reference_run(batch, steps, warmup, threads=None):
     return batch / dt, torch.get_num_threads(), dt
 
 
+def cpu_reference_split(batch):
+    """Where the reference step spends its time on the host: one forward + backward of the two encoder passes
+    alone (loss = sum of squares of the projections) and one forward + backward of the reference's NT-Xent formulation alone on
+    random unit projections.  Returns seconds per step of each part."""
+    from oracle import gnn as ognn
+    from oracle.nt_xent import NTXentRestated
+    from molclr_b200.synth import make_pair_batch
+    torch.manual_seed(0)
+    model = ognn.GINet(5, 300, 512, 0, "mean")
+    bi, bj = make_pair_batch(batch, seed=100)
+    t0 = time.perf_counter()
+    (model(bi)[1].square().sum() + model(bj)[1].square().sum()).backward()
+    t_enc = time.perf_counter() - t0
+    crit = NTXentRestated("cpu", batch, 0.1, True)
+    z = torch.nn.functional.normalize(torch.randn(2 * batch, 256), dim=1).requires_grad_(True)
+    t0 = time.perf_counter()
+    crit(z[:batch], z[batch:]).backward()
+    t_ntx = time.perf_counter() - t0
+    return t_enc, t_ntx
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
     mols, threads, dt = cpu_reference_run(args.cpu_batch, steps, warmup)
+    t_enc, t_ntx = cpu_reference_split(args.cpu_batch)
     sample = (f"{warmup} warm-up + {steps} full steps of {args.cpu_batch} pairs (the reference's default batch; its NT-Xent "
               f"[2N,2N,C] broadcast needs 68.7 GB at 4096 pairs), oracle port: torch_geometric is not installable")
     line = {"impl": "reference", "metric": METRIC, "value": mols, "unit": "molecules/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample_batch": args.cpu_batch},
-            "cpu_baseline": {"value": mols, "unit": "molecules/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": mols, "unit": "molecules/s", "cores": threads, "kind": "port", "sample": sample,
+                             "split_s_per_step": {"encoder_fwd_bwd": t_enc, "ntxent_fwd_bwd": t_ntx, "full_step": dt}},
             "e2e": {"value": mols, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
