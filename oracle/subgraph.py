@@ -14,8 +14,11 @@ before its BEGIN atom is silently dropped: that quirk is part of the reference's
 ``temp = list(set(neighbors))`` (:87) is kept verbatim: the iteration order of a CPython set of small ints decides which atoms
 of the last breadth-first level are removed when the budget runs out inside a level.
 
+``mix_view`` restates the mixed augmentation of /root/reference/dataset/dataset_mix.py:128-215 (subgraph removal with a random
+fraction, then random atom masking / bond deletion up to the 25 % budgets) on the same graph model.
+
 Pinned by tests/golden/subgraph_*.npz (made by tests/golden/make_subgraph_golden.py, which executes the reference's own
-``removeSubgraph`` on networkx graphs)."""
+``removeSubgraph`` / ``remove_subgraph`` on networkx graphs)."""
 import numpy as np
 
 MASK_TOKEN = (118, 0)             # [len(ATOM_LIST), 0], dataset_subgraph.py:139,143
@@ -34,9 +37,11 @@ def build_graph(bonds):
     return adj
 
 
-def remove_subgraph(adj, center, percent=0.2):
+def remove_subgraph(adj, center, percent=0.2, stop_when_exhausted=False):
     """dataset_subgraph.py:70-88 on the dict-of-dicts graph.  Returns (reduced graph, removed atoms in removal order).
-    Like the reference it raises (KeyError here, NetworkXError there) when ``center`` is not a node of the graph."""
+    Like the reference it raises (KeyError here, NetworkXError there) when ``center`` is not a node of the graph.
+    ``stop_when_exhausted``: the variant of dataset_mix.py:45-68, which leaves the loop when a breadth-first level is empty
+    (a connected component smaller than the budget) instead of spinning."""
     assert percent <= 1
     # Graph.copy(): nodes in the original order, then add_edges_from over (u in node order, v in u's adjacency order) -- which
     # can permute the adjacency order of a node relative to the original graph
@@ -50,6 +55,8 @@ def remove_subgraph(adj, center, percent=0.2):
     temp = [center]
     while len(removed) < num:
         neighbors = []
+        if stop_when_exhausted and len(temp) < 1:                            # dataset_mix.py:55-56
+            break
         for n in temp:
             neighbors.extend([i for i in g[n] if i not in temp])             # G.neighbors(n): adjacency insertion order
         for n in temp:
@@ -92,3 +99,41 @@ def subgraph_view(x, bonds, battr, center, percent=0.25):
     ei = np.array([row, col], dtype=np.int64).reshape(2, len(row))
     ea = np.array(feat, dtype=np.int64).reshape(len(row), 2)
     return xv, ei, ea, removed
+
+
+def mix_mask_counts(n_atoms, n_bonds, n_removed, n_surviving_bonds):
+    """dataset_mix.py:175-178: random masking tops the view up to floor(0.25 N) hidden atoms and down to ceil(0.75 M) bonds."""
+    import math
+    return max(0, math.floor(0.25 * n_atoms) - n_removed), max(0, n_surviving_bonds - math.ceil(0.75 * n_bonds))
+
+
+def mix_view(x, bonds, battr, center, percent, mask_nodes, mask_bonds_single):
+    """One view of the mixed augmentation (dataset_mix.py:128-215) with every random draw given explicitly: the centre and the
+    fraction of the subgraph removal (:137-139, percent ~ U(0, 0.2)), the extra atoms to mask (drawn from the atoms that remain,
+    :179) and the extra bonds to delete (indices into the bonds that SURVIVED the removal, :181).  Unlike dataset_subgraph.py the
+    survival test accepts either orientation of the bond (:156,161).  Returns x_v, edge_index_v, edge_attr_v, removed."""
+    g, removed = remove_subgraph(build_graph(bonds), int(center), percent, stop_when_exhausted=True)
+    g_edges = edge_list(g)
+    row, col, feat = [], [], []
+    for (s, e), a in zip(bonds, battr):                                       # :150-165
+        if (int(s), int(e)) in g_edges or (int(e), int(s)) in g_edges:
+            row += [int(s), int(e)]
+            col += [int(e), int(s)]
+            feat += [list(a), list(a)]
+    ei = np.array([row, col], dtype=np.int64).reshape(2, len(row))
+    ea = np.array(feat, dtype=np.int64).reshape(len(row), 2)
+    mask_edges = [2 * i for i in mask_bonds_single] + [2 * i + 1 for i in mask_bonds_single]       # :183-184
+    xv = np.array(x, dtype=np.int64, copy=True)
+    for a in range(len(x)):                                                   # :187-190
+        if a in mask_nodes or a in removed:
+            xv[a, :] = MASK_TOKEN
+    k = len(mask_bonds_single)
+    ei_f = np.zeros((2, ei.shape[1] - 2 * k), dtype=np.int64)                 # :191-198
+    ea_f = np.zeros((ea.shape[0] - 2 * k, 2), dtype=np.int64)
+    count = 0
+    for b in range(ea.shape[0]):
+        if b not in mask_edges:
+            ei_f[:, count] = ei[:, b]
+            ea_f[count, :] = ea[b, :]
+            count += 1
+    return xv, ei_f, ea_f, removed

@@ -51,3 +51,28 @@ def test_view_construction_matches_the_reference_loop(golden):
         alive = [(int(s), int(e)) for s, e in bonds if not rm[s] and not rm[e]]
         dropped_by_orientation += len(alive) - ei.shape[1] // 2
     assert dropped_by_orientation > 0     # (the quirk is real and the fixtures contain it)
+
+
+def test_mixed_augmentation_matches_the_reference(golden):
+    """dataset_mix.py:45-68 (``remove_subgraph`` with the empty-level exit, executed by the fixture generator) and the view loops of
+    :150-198 with explicit draws: removed atoms, masked features and surviving edges, including disconnected molecule graphs and a
+    random removal fraction."""
+    n = int(golden["num_mix_cases"])
+    assert n >= 30
+    extra_nodes = extra_bonds = short_budget = 0
+    for c in range(n):
+        k = f"m{c}"
+        x, bonds, battr = golden[k + "_x"], golden[k + "_bonds"], golden[k + "_battr"]
+        mask_nodes, mask_bonds = golden[k + "_mask_nodes"].tolist(), golden[k + "_mask_bonds"].tolist()
+        xv, ei, ea, removed = osub.mix_view(x, bonds, battr, int(golden[k + "_center"]), float(golden[k + "_percent"]), mask_nodes, mask_bonds)
+        assert removed == golden[k + "_removed"].tolist(), c
+        assert np.array_equal(xv, golden[k + "_xv"]) and np.array_equal(ei, golden[k + "_edge_index"]) and np.array_equal(ea, golden[k + "_edge_attr"]), c
+        # the budgets of dataset_mix.py:175-178, recomputed from the oracle's own intermediate counts
+        surviving = ei.shape[1] // 2 + len(mask_bonds)
+        kn, ke = osub.mix_mask_counts(len(x), len(bonds), len(removed), surviving)
+        assert (kn, ke) == (len(mask_nodes), len(mask_bonds)), c
+        nodes = len(osub.build_graph(bonds))
+        short_budget += int(len(removed) < int(np.floor(nodes * float(golden[k + "_percent"]))))
+        extra_nodes += len(mask_nodes)
+        extra_bonds += len(mask_bonds)
+    assert extra_nodes > 0 and extra_bonds > 0
