@@ -6,7 +6,7 @@
 set -u
 mkdir -p gpurun_out
 TAG=${1:-next}
-timeout 300 python -m pytest tests/test_gpu_golden.py -m gpu -q -k motif --runxfail 2>&1 | tail -40 | tee gpurun_out/motif_$TAG.log
+timeout 300 python -m pytest tests/test_gpu_zz_pending.py -m gpu -q --runxfail 2>&1 | tail -40 | tee gpurun_out/motif_$TAG.log
 MOLCLR_NTX_NOBOUND=1 timeout 300 python tools/bench_ntxent.py 2>&1 | tee gpurun_out/ntx_nobound_$TAG.log
 timeout 900 python -m pytest tests -m gpu -q -rxX > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest_$TAG.log
 timeout 600 python bench.py --no-cpu-baseline 2>/dev/null | python tools/bench_line.py
