@@ -29,7 +29,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define MOLCLR_ABI_VERSION 1
+#define MOLCLR_ABI_VERSION 2
 
 /* ---- library ------------------------------------------------------------------------------- */
 int molclr_abi_version(void);
@@ -85,9 +85,10 @@ int molclr_augment_views(const int32_t* atom_ptr, const int32_t* atoms, const in
 /* ---- node embedding: ginet_molclr.py:103 / gcn_molclr.py:144 ------------------------------------- */
 int molclr_embed_nodes_fwd(const int32_t* xpacked, const float* E1, const float* E2, int64_t N, int D, float* out,
                            cudaStream_t stream);
-/* dE is ONE buffer [(119+3)][D]: rows 0..118 = grad of x_embedding1, 119..121 = grad of x_embedding2
- * (= onehot^T . g, a split-K tensor-core contraction; g rows ld_g floats apart).
- * workspace: molclr_embed_nodes_bwd_workspace_bytes(N) bytes, 16-byte aligned (holds the [N][128] one-hot matrix). */
+/* dE is ONE buffer [(119+3)][D]: rows 0..118 = grad of x_embedding1, 119..121 = grad of x_embedding2 (g rows ld_g floats apart):
+ * embedding_dense_backward of the reference, in plain fp32 with a FIXED summation order (bit-reproducible): every CTA sums its
+ * contiguous block of nodes sequentially into a [122][D] tile in shared memory, the per-CTA tiles go to `workspace` and are summed
+ * in CTA order.  workspace: molclr_embed_nodes_bwd_workspace_bytes(N) bytes, 16-byte aligned. */
 size_t molclr_embed_nodes_bwd_workspace_bytes(int64_t N);
 int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, int64_t ld_g, int64_t N, int D, float* dE, void* workspace,
                            cudaStream_t stream);
@@ -134,9 +135,13 @@ int molclr_bn_apply_fwd(const float* z, const float* bn_coef, int relu, int64_t 
  * epilogue emits for the GIN path, for outputs that do not come from a GEMM. */
 int molclr_bn_tile_stats(const float* z, int64_t N, int D, int T, float* tile_stats, cudaStream_t stream);
 /* Gradients of edge_embedding1/2 (embedding_dense_backward over E' rows in the reference):
- * dB [8][D] = cnt^T . ga: rows 0..4 = d edge_embedding1, rows 5..7 = d edge_embedding2 (a split-K tensor-core contraction;
- * ga rows ld_ga floats apart). */
-int molclr_edge_table_grad(const float* ga, int64_t ld_ga, const float* cnt, int64_t N, int D, float* dB, cudaStream_t stream);
+ * dB [8][D] = cnt^T . ga: rows 0..4 = d edge_embedding1, rows 5..7 = d edge_embedding2 (ga rows ld_ga floats apart).  These are
+ * heavy-cancellation sums over all nodes, so they run as exact fp32 FMAs with a FIXED order (bit-reproducible): every CTA sums its
+ * contiguous block of nodes sequentially, the per-CTA [8][D] partials go to `workspace` and are summed in CTA order.
+ * workspace: molclr_edge_table_grad_workspace_bytes(D) bytes, 16-byte aligned. */
+size_t molclr_edge_table_grad_workspace_bytes(int D);
+int molclr_edge_table_grad(const float* ga, int64_t ld_ga, const float* cnt, int64_t N, int D, float* dB, void* workspace,
+                           cudaStream_t stream);
 
 /* out[c] (+)= scale * sum_p partials[p][c], p in increasing order (deterministic). */
 int molclr_reduce_partials(const float* partials, int P, int len, float scale, int accumulate, float* out,
@@ -216,6 +221,12 @@ typedef struct {
                                  every low half derived on chip -- pass 1 in TF32 on the raw tiles (the tensor core truncates),
                                  the corrections (A - trunc A) * B and A * (B - trunc B) as kind::f16 MMAs on bf16 tiles the
                                  kernel forms in shared memory (their 2^-9 rounding applies to terms 2^-10 of the product)    */
+  const void* B16;            /* compensate = 1, optional: the bf16 correction tiles of B pre-split once per optimizer step by
+                                 molclr_prepare_weights -- bf16 [2][rows16][ld16]: bf16(B) then bf16(B - trunc_tf32(B)), zero padded;
+                                 TMA then lands them in shared memory and the converter warps touch A only (B is a WEIGHT on every
+                                 compensated product of the path: it does not change between the row tiles of a launch, nor
+                                 between the launches of a step)                                                               */
+  int64_t ld16, rows16;       /* row pitch (bf16 elements, % 8 == 0) and rows per half (>= N rounded up to 256)               */
 } molclr_gemm_args;
 /* column statistics are emitted per group of molclr_gemm_colstat_tile_rows() (= 32) consecutive rows;
  * molclr_gemm_colstat_tiles(M) groups are written (a multiple of 4; trailing groups may be empty). */
@@ -230,6 +241,28 @@ int molclr_gemm_tf32(const molclr_gemm_args* args /* host */, cudaStream_t strea
  * (autograd of ginet_molclr.py:19-23,90-96; gcn_molclr.py:76).  Split-K over R, one wave, atomic accumulation. */
 int molclr_gemm_dw(const float* dY, int64_t ldy, const float* X, int64_t ldx, int64_t R, int64_t O, int64_t I, float* dW,
                    int64_t ldw, cudaStream_t stream);
+/* The same contraction with a FIXED summation order (bit-reproducible run to run): every K split writes its partial [O][I]
+ * tile product to `workspace` with plain stores and a second kernel sums the splits in split order.
+ * workspace: molclr_gemm_dw_workspace_bytes(R, O, I) bytes, 16-byte aligned. */
+size_t molclr_gemm_dw_workspace_bytes(int64_t R, int64_t O, int64_t I);
+int molclr_gemm_dw_ordered(const float* dY, int64_t ldy, const float* X, int64_t ldx, int64_t R, int64_t O, int64_t I, float* dW,
+                           int64_t ldw, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ---- weight shadows: once per forward, ONE launch for every Linear / GCNConv weight of the model -----------------------
+ * The tensor-core operand forms of a weight W (nn.Linear [out][in], ginet_molclr.py:19-23,90-96; GCNConv [in][out],
+ * gcn_molclr.py:47) are functions of the parameter only, so they are derived once per forward instead of per tile:
+ *   hi  [rows][ld_hi]   = tf32(W)            (single-pass products, every backward dX product), same orientation as W
+ *   lo  [rows][ld_hi]   = tf32(W - hi)       (explicit 3-pass product of the head)
+ *   raw [rows_t][ld_raw] = W or W^T (transpose_raw: K-major copy of a weight stored [in][out]), unrounded, 128-byte rows
+ *   b16 [2][rows16][ld16] bf16 = bf16(raw), bf16(raw - trunc_tf32(raw)), zero padded (see molclr_gemm_args.B16)
+ * Any output pointer may be NULL.  Padding columns (up to the row pitch) are written as zeros. */
+typedef struct {
+  const float* src; int64_t ld_src; int32_t rows, cols;
+  float* hi; float* lo; int64_t ld_hi;
+  float* raw; int64_t ld_raw; int32_t transpose_raw;
+  void* b16; int64_t ld16; int32_t rows16;
+} molclr_weight_desc;
+int molclr_prepare_weights(const molclr_weight_desc* descs /* host */, int n, cudaStream_t stream);
 
 /* ---- small elementwise ops ---------------------------------------------------------------------- */
 /* hi = tf32(src); lo (optional) = tf32(src - hi) */

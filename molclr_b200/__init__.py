@@ -9,7 +9,6 @@ from .gcn import GCN, GCNConv  # noqa: F401
 from . import ginet_finetune  # noqa: F401  (ginet_finetune.GINet: models/ginet_finetune.py)
 from . import gcn_finetune  # noqa: F401  (gcn_finetune.GCN: models/gcn_finetune.py)
 from . import ginet_finetune_mp  # noqa: F401  (ginet_finetune_mp.GINet: models/ginet_finetune_mp.py, motif attention)
-from . import ginet_finetune_link  # noqa: F401  (ginet_finetune_link.GINet: models/ginet_finetune_link.py, label-conditioned head)
 from .nt_xent import NTXentLoss  # noqa: F401
 from .graph import GraphPlan, get_plan  # noqa: F401
 from .functional import normalize, pretrain_loss  # noqa: F401

@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MOLCLR_B200_LIB") or os.path.join(_HERE, "libmolclr_b200.so")   # (override: A/B timing of builds)
 
 vp, i64, i32, f32, sz, u32 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t, C.c_uint32
+ABI_VERSION = 2        # MOLCLR_ABI_VERSION of include/molclr_b200.h
 
 
 class GemmArgs(C.Structure):
@@ -32,6 +33,17 @@ class GemmArgs(C.Structure):
         ("split_k", C.c_int32),
         ("relu_bits", vp), ("mask_bits", vp), ("ld_bits", i64),
         ("compensate", C.c_int32),
+        ("B16", vp), ("ld16", i64), ("rows16", i64),
+    ]
+
+
+class WeightDesc(C.Structure):
+    """Mirror of ``molclr_weight_desc`` (include/molclr_b200.h)."""
+    _fields_ = [
+        ("src", vp), ("ld_src", i64), ("rows", C.c_int32), ("cols", C.c_int32),
+        ("hi", vp), ("lo", vp), ("ld_hi", i64),
+        ("raw", vp), ("ld_raw", i64), ("transpose_raw", C.c_int32),
+        ("b16", vp), ("ld16", i64), ("rows16", C.c_int32),
     ]
 
 
@@ -47,6 +59,10 @@ SIGNATURES = {
                                    vp, vp]),
     "molclr_embed_nodes_fwd": (i32, [vp, vp, vp, i64, i32, vp, vp]),
     "molclr_embed_nodes_bwd_workspace_bytes": (sz, [i64]),
+    "molclr_edge_table_grad_workspace_bytes": (sz, [i32]),
+    "molclr_prepare_weights": (i32, [C.POINTER(WeightDesc), i32, vp]),
+    "molclr_gemm_dw_workspace_bytes": (sz, [i64, i64, i64]),
+    "molclr_gemm_dw_ordered": (i32, [vp, i64, vp, i64, i64, i64, i64, vp, i64, vp, sz, vp]),
     "molclr_embed_nodes_bwd": (i32, [vp, vp, i64, i64, i32, vp, vp, vp]),
     "molclr_gine_aggregate_fwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, vp, i64, i32, vp, u32, f32, vp]),
     "molclr_rowwise_max_blocks": (i32, []),
@@ -56,7 +72,7 @@ SIGNATURES = {
     "molclr_row_sum": (i32, [vp, i32, i32, vp, vp]),
     "molclr_bn_apply_fwd": (i32, [vp, vp, i32, i64, i32, vp, vp, i64, i32, u32, f32, vp]),
     "molclr_bn_tile_stats": (i32, [vp, i64, i32, i32, vp, vp]),
-    "molclr_edge_table_grad": (i32, [vp, i64, vp, i64, i32, vp, vp]),
+    "molclr_edge_table_grad": (i32, [vp, i64, vp, i64, i32, vp, vp, vp]),
     "molclr_reduce_partials": (i32, [vp, i32, i32, f32, i32, vp, vp]),
     "molclr_bn_finalize_workspace_bytes": (sz, [i32]),
     "molclr_bn_fwd_finalize": (i32, [vp, i32, i32, i64, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp]),
@@ -99,7 +115,7 @@ def load():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)         # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
-        if lib.molclr_abi_version() != 1:
+        if lib.molclr_abi_version() != ABI_VERSION:
             raise RuntimeError("molclr_b200: ABI version mismatch between _lib.py and libmolclr_b200.so")
         _lib = lib
     return _lib

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #ifndef __CUDA_ARCH__
 #define MOLCLR_HOST 1
@@ -29,6 +30,18 @@ extern unsigned long long g_launches;   // kernels launched by this library (dia
   } while (0)
 
 int sm_count();   // cached multiprocessor count of the current device
+
+// Tuning / debugging switches (MOLCLR_GEMM_*, MOLCLR_AGG_*, MOLCLR_NTX_*) are read from the environment ONLY in a library built
+// with -DMOLCLR_DEBUG_SWITCHES (python -m molclr_b200.build --debug-switches -> libmolclr_b200_dbg.so, used by tools/);
+// the product library never looks at the environment, so a stray variable cannot change its results or its speed.
+inline const char* debug_env(const char* name) {
+#ifdef MOLCLR_DEBUG_SWITCHES
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
 
 // ---------------------------------------------------------------- device helpers
 __device__ __forceinline__ float round_tf32(float x) {

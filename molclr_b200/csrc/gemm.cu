@@ -243,7 +243,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // derive_lo: the fp32 A tile goes to a CTA-local barrier (the converter warps of THIS CTA consume it) and no A_lo is loaded
             // mixed: both raw tiles go to the CTA-local barrier and the MMA issuer waits for the converters only
             if (rank == 0 && !mixed) ptx::mbar_arrive_expect_tx(full_bar + s, derive ? (TWO ? 2 : 1) * 2 * Cfg::B_BYTES : Cfg::TX_BYTES);
-            if (derive) ptx::mbar_arrive_expect_tx(afull_bar + s, mixed ? Cfg::A_BYTES + Cfg::B_BYTES : Cfg::A_BYTES);
+            if (derive) ptx::mbar_arrive_expect_tx(afull_bar + s, mixed ? Cfg::A_BYTES + Cfg::B_BYTES + (p.b_presplit ? Cfg::B_BYTES : 0) : Cfg::A_BYTES);
             const uint32_t fb = TWO ? ptx::mapa(ptx::smem_u32(full_bar + s), 0u) : 0u;     // the leader's barrier
             auto load = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
               if (TWO) ptx::tma_load_2d_2cta(dst, m, fb, c0, c1); else ptx::tma_load_2d(dst, m, full_bar + s, c0, c1);
@@ -272,7 +272,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               else
                 for (int j = 0; j < GEMM_BM / 32; ++j) load(ad + j * Cfg::MN_BLOCK_BYTES, ma, m0 + 32 * j, kc);
               if (mixed) {
-                if (h == 0) ptx::tma_load_2d(bd, &tmB, afull_bar + s, kc, n0);
+                if (h == 0) {
+                  ptx::tma_load_2d(bd, &tmB, afull_bar + s, kc, n0);
+                  if (p.b_presplit) {      // bf16(B) and bf16(B - trunc B) tiles (rows of 32 bf16 = 64 bytes, 64-byte swizzle), pre-split once per step
+                    ptx::tma_load_2d(bd + Cfg::B_BYTES, &tmB2, afull_bar + s, kc, n0);
+                    ptx::tma_load_2d(bd + Cfg::B_BYTES + Cfg::B_BYTES / 2, &tmB2, afull_bar + s, kc, p.rows16 + n0);
+                  }
+                }
               } else if (!p.b_mn) load(bd, mb, kc, n0);
               else if (!FOUR && p.b_mn3d) {
                 // this CTA's blocks of the first MMA (N1) in one box; the (shorter) N2 group of a wide tile keeps per-block copies
@@ -423,7 +429,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint8_t* st = smem + s * Cfg::STAGE_BYTES;
             if (!(p.debug & 2)) {      // (timing experiments: skip the conversion)
               convert(st, st + Cfg::A_BYTES, Cfg::A_BYTES / 16);
-              convert(st + 2 * Cfg::A_BYTES, st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, Cfg::B_BYTES / 16);
+              if (!p.b_presplit) convert(st + 2 * Cfg::A_BYTES, st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, Cfg::B_BYTES / 16);
             }
           } else
 #pragma unroll 4
@@ -654,6 +660,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float v[16];
           ptx::tmem_ld_x16(taddr + c0, v);
           if (p.debug & 8) continue;                  // timing experiment: no atomics
+          if (p.atomic_out == 3) {                    // ordered split-K: this split's partial tile, plain vector stores
+            if (grow < p.M) {
+              float* dst = p.out + ((size_t)(t / (n_tiles * m_tiles)) * p.M + grow) * p.ldo;
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const int col = n0 + c0 + j;
+                if (col < p.N) st_f4(dst + col, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+              }
+            }
+            continue;
+          }
           if (p.atomic_out == 2) {                    // row-major output with 16-byte aligned rows: vector reductions (4x fewer L2 requests)
             if (grow < p.M)
 #pragma unroll
@@ -974,8 +991,10 @@ static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, i
       rc = p.a_mn ? make_tmap(&tmA2, j.A_lo, p.M, p.K, j.lda, 32, true, Cfg::BK) : make_tmap(&tmA2, j.A_lo, p.K, p.M, j.lda, GEMM_BM, false, Cfg::BK);
       if (rc) return rc;
     }
-    if (p.derive_lo != 2)            // (mixed: no second B tensor at all)
+    if (p.derive_lo != 2)            // (mixed: no second fp32 B tensor)
       rc = p.b_mn ? make_tmap(&tmB2, j.B_lo, p.N, p.K, j.ldb, 32, true, Cfg::BK) : make_tmap(&tmB2, j.B_lo, p.K, p.N, j.ldb, Cfg::BN_CTA, false, Cfg::BK);
+    else if (p.b_presplit)           // bf16 [2 rows16][K]: boxes of BN_CTA rows x 32 elements (64-byte rows, 64-byte swizzle, zero fill beyond K)
+      rc = make_tmap(&tmB2, reinterpret_cast<const float*>(j.B16), p.K, 2ll * j.rows16, j.ld16, Cfg::BN_CTA, false, Cfg::BK, true);
     if (rc) return rc;
   }
   auto kernel = gemm_tf32_kernel<BN, FOUR, KIND, TWO>;
@@ -1006,26 +1025,26 @@ static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, i
 
 static bool gemm_no_mn3d() {          // MOLCLR_GEMM_MN3D=0: per-block 2-D copies for MN-major operands (A/B timing)
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MOLCLR_GEMM_MN3D"); v = (e && atoi(e) == 0) ? 1 : 0; }
+  if (v < 0) { const char* e = debug_env("MOLCLR_GEMM_MN3D"); v = (e && atoi(e) == 0) ? 1 : 0; }
   return v != 0;
 }
 
 static int gemm_debug_flags() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MOLCLR_GEMM_DEBUG"); v = e ? atoi(e) : 0; }
+  if (v < 0) { const char* e = debug_env("MOLCLR_GEMM_DEBUG"); v = e ? atoi(e) : 0; }
   return v;
 }
 
 static int gemm_impl_simt() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MOLCLR_GEMM_IMPL"); v = (e && strcmp(e, "simt") == 0) ? 1 : 0; }
+  if (v < 0) { const char* e = debug_env("MOLCLR_GEMM_IMPL"); v = (e && strcmp(e, "simt") == 0) ? 1 : 0; }
   return v;
 }
 
 // CTA pairs (cluster of 2, 256-row tiles) unless MOLCLR_GEMM_PAIR=0
 static bool gemm_pair() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MOLCLR_GEMM_PAIR"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  if (v < 0) { const char* e = debug_env("MOLCLR_GEMM_PAIR"); v = (e && atoi(e) == 0) ? 0 : 1; }
   return v != 0;
 }
 
@@ -1052,6 +1071,14 @@ int gemm_n_tiles(long long N) {     // number of NT-Xent forward partials per ro
   return 2 * (int)((N + bn - 1) / bn);          // two epilogue warps share the columns of a tile
 }
 
+// Number of K splits a launch really uses for a requested split_k (no empty split).
+static int effective_splits(int num_kb, int split_k) {
+  int splits = split_k > 1 ? split_k : 1;
+  if (splits > num_kb) splits = num_kb;
+  const int per = (num_kb + splits - 1) / splits;
+  return (num_kb + per - 1) / per;
+}
+
 int gemm_run(const GemmJob& job, cudaStream_t stream) {
   GemmParams p = job.p;
   MOLCLR_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
@@ -1063,6 +1090,12 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   // compensated product with the low halves derived on chip: 1 = A_lo (fp32 tile) from an unrounded A, B_hi/B_lo from the caller;
   // 2 = "mixed": both operands unrounded, bf16 correction tiles of both formed on chip
   p.derive_lo = job.compensate ? 2 : (job.B_lo && !job.A_lo) ? 1 : 0;
+  p.b_presplit = (job.compensate && job.B16) ? 1 : 0;
+  p.rows16 = job.rows16;
+  MOLCLR_REQUIRE(!job.B16 || job.compensate, "gemm: B16 (pre-split bf16 tiles of B) belongs to the compensated product");
+  if (p.b_presplit)
+    MOLCLR_REQUIRE(job.ld16 % 8 == 0 && job.ld16 >= p.K && job.rows16 >= (p.N + 255) / 256 * 256 && (reinterpret_cast<uintptr_t>(job.B16) & 15) == 0,
+                   "gemm: B16 needs ld16 %% 8 == 0, ld16 >= K, rows16 >= N rounded up to 256, a 16-byte aligned base");
   MOLCLR_REQUIRE((!p.bits_in && !p.bits_out) || (p.epi == EPI_GENERIC && !atomic && !p.mask && !p.addend),
                  "gemm: ReLU bit masks need the plain epilogue (no float mask / addend / split-K)");
   MOLCLR_REQUIRE(!p.bits_in || p.segments == 1, "gemm: mask_bits is not supported by the compensated product");
@@ -1083,11 +1116,15 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   MOLCLR_REQUIRE(!p.out16 || (p.epi == EPI_NTX_W && p.ldo16 % 8 == 0 && !p.out), "gemm: out16 is the fp16 output of the NT-Xent weight epilogue");
   const int bk = p.half16 ? 2 * GEMM_BK : p.segments > 1 ? GEMM_BK4 : GEMM_BK;
   p.num_kb = (p.K + bk - 1) / bk;
-  int splits = job.split_k > 1 ? job.split_k : 1;
-  if (splits > p.num_kb) splits = p.num_kb;
+  const int splits = effective_splits(p.num_kb, job.split_k);
   p.kb_per_split = (p.num_kb + splits - 1) / splits;
-  splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;          // no empty split
   p.atomic_out = !atomic ? 0 : (!p.transpose_out && p.ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) ? 2 : 1;
+  if (job.ordered_ws) {           // ordered split-K: partial tiles to the workspace (the caller sums them in split order)
+    MOLCLR_REQUIRE(atomic && !p.transpose_out && p.ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(job.ordered_ws) & 15) == 0,
+                   "gemm: ordered split-K writes [splits][M][ldo] partials (no transposed output), 16-byte aligned");
+    p.out = job.ordered_ws;
+    p.atomic_out = 3;
+  }
   p.debug = gemm_debug_flags();
   // split-K weight gradients stay on single CTAs: their 300/600-wide outputs pad badly to 256-row pair tiles (MMA-bound)
   const bool wide = atomic && job.wide && gemm_pair() && !gemm_impl_simt();
@@ -1096,7 +1133,7 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   const int tile_m = pair ? 2 * GEMM_BM : GEMM_BM;
   const int m_tiles = (p.M + tile_m - 1) / tile_m;
   p.stat_groups = molclr_gemm_colstat_tiles(p.M);
-  if (atomic) {
+  if (atomic && p.atomic_out != 3) {
     const size_t w = (size_t)(p.transpose_out ? p.M : p.N) * sizeof(float), h = (size_t)(p.transpose_out ? p.N : p.M);
     cudaError_t e = cudaMemset2DAsync(p.out, (size_t)p.ldo * sizeof(float), 0, w, h, stream);
     if (e != cudaSuccess) return cuda_fail(e, "gemm: zeroing split-K output");
@@ -1156,11 +1193,13 @@ extern "C" int molclr_gemm_tile_count(int64_t M, int64_t N, int b_mn) {
 extern "C" int molclr_gemm_workers(void) { return gemm_workers(false); }
 
 // dW [O][I] = dY^T X for row-major dY [R][O], X [R][I]: the weight gradient of a Linear.  Both operands are consumed MN-major
-// in place; the reduction over R is split across one wave of workers and accumulated atomically.  Orientation (which operand
-// is "M") and tile shape (128 x 160/256 on single CTAs, or 256 x 320 on CTA pairs) are chosen to minimise the operand bytes
-// every K row costs on the L2 -> shared-memory path, n_tiles * M + m_tiles * N, which is what bounds this kernel.
-extern "C" int molclr_gemm_dw(const float* dY, int64_t ldy, const float* X, int64_t ldx, int64_t R, int64_t O, int64_t I, float* dW,
-                              int64_t ldw, cudaStream_t stream) {
+// in place; the reduction over R is split across one wave of workers and accumulated atomically (molclr_gemm_dw) or written as
+// per-split partial tiles that are then summed in split order (molclr_gemm_dw_ordered: bit-reproducible).  Orientation (which
+// operand is "M") and tile shape (128 x 160/256 on single CTAs, or 256 x 320 on CTA pairs) are chosen to minimise the operand
+// bytes every K row costs on the L2 -> shared-memory path, n_tiles * M + m_tiles * N, which is what bounds this kernel.
+struct DwPlan { int swap, wide, split, splits; long long M, N; };
+
+static int dw_plan(int64_t R, int64_t O, int64_t I, DwPlan* out) {
   MOLCLR_REQUIRE(R > 0 && O > 0 && I > 0 && R < (1ll << 31) && O < (1ll << 31) && I < (1ll << 31), "gemm_dw: bad extents");
   long long best = -1;
   int best_swap = 0, best_wide = 0, best_tiles = 1;
@@ -1178,14 +1217,79 @@ extern "C" int molclr_gemm_dw(const float* dY, int64_t ldy, const float* X, int6
   int split = gemm_workers(best_wide != 0) / best_tiles;
   if (split > num_kb / 8) split = num_kb / 8;
   if (split < 1) split = 1;
-  GemmJob j;
+  out->swap = best_swap; out->wide = best_wide; out->split = split; out->splits = effective_splits(num_kb, split);
+  out->M = best_swap ? I : O; out->N = best_swap ? O : I;
+  return 0;
+}
+
+static void dw_job(GemmJob& j, const DwPlan& pl, const float* dY, int64_t ldy, const float* X, int64_t ldx, int64_t R) {
   memset(&j, 0, sizeof(j));
-  j.A = best_swap ? X : dY; j.lda = best_swap ? ldx : ldy;
-  j.B = best_swap ? dY : X; j.ldb = best_swap ? ldy : ldx;
-  j.p.M = (int)(best_swap ? I : O); j.p.N = (int)(best_swap ? O : I); j.p.K = (int)R; j.p.a_mn = 1; j.p.b_mn = 1;
-  j.p.out = dW; j.p.ldo = ldw; j.p.transpose_out = best_swap; j.p.alpha = 1.f; j.p.epi = EPI_GENERIC;
-  j.split_k = split; j.wide = best_wide;
+  j.A = pl.swap ? X : dY; j.lda = pl.swap ? ldx : ldy;
+  j.B = pl.swap ? dY : X; j.ldb = pl.swap ? ldy : ldx;
+  j.p.M = (int)pl.M; j.p.N = (int)pl.N; j.p.K = (int)R; j.p.a_mn = 1; j.p.b_mn = 1;
+  j.p.alpha = 1.f; j.p.epi = EPI_GENERIC;
+  j.split_k = pl.split; j.wide = pl.wide;
+}
+
+extern "C" int molclr_gemm_dw(const float* dY, int64_t ldy, const float* X, int64_t ldx, int64_t R, int64_t O, int64_t I, float* dW,
+                              int64_t ldw, cudaStream_t stream) {
+  DwPlan pl;
+  if (int rc = dw_plan(R, O, I, &pl)) return rc;
+  GemmJob j;
+  dw_job(j, pl, dY, ldy, X, ldx, R);
+  j.p.out = dW; j.p.ldo = ldw; j.p.transpose_out = pl.swap;
   return gemm_run(j, stream);
+}
+
+// out[m][n] (or out[n][m]) = sum_s ws[s][m][n], s in increasing order.  32 x 32 tiles, block (32, 8).
+__global__ void __launch_bounds__(256) dw_reduce_kernel(const float* __restrict__ ws, int S, int M, int N, long long ldws, float* __restrict__ out,
+                                                        long long ldo, int transpose) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int m = blockIdx.y * 32 + threadIdx.y + 8 * k;
+    float a = 0.f;
+    if (m < M && n < N)
+      for (int s = 0; s < S; ++s) a += ws[((size_t)s * M + m) * ldws + n];
+    if (!transpose) { if (m < M && n < N) out[(size_t)m * ldo + n] = a; }
+    else tile[threadIdx.y + 8 * k][threadIdx.x] = a;
+  }
+  if (transpose) {
+    __syncthreads();
+    const int mo = blockIdx.y * 32 + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int no = blockIdx.x * 32 + threadIdx.y + 8 * k;
+      if (mo < M && no < N) out[(size_t)no * ldo + mo] = tile[threadIdx.x][threadIdx.y + 8 * k];
+    }
+  }
+}
+
+extern "C" size_t molclr_gemm_dw_workspace_bytes(int64_t R, int64_t O, int64_t I) {
+  DwPlan pl;
+  if (dw_plan(R, O, I, &pl)) return 0;
+  return (size_t)pl.splits * (size_t)pl.M * (size_t)((pl.N + 3) / 4 * 4) * sizeof(float);
+}
+
+extern "C" int molclr_gemm_dw_ordered(const float* dY, int64_t ldy, const float* X, int64_t ldx, int64_t R, int64_t O, int64_t I, float* dW,
+                                      int64_t ldw, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  DwPlan pl;
+  if (int rc = dw_plan(R, O, I, &pl)) return rc;
+  const long long ldws = (pl.N + 3) / 4 * 4;
+  MOLCLR_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)pl.splits * pl.M * ldws * sizeof(float),
+                 "gemm_dw_ordered: workspace too small (%zu bytes, need molclr_gemm_dw_workspace_bytes)", workspace_bytes);
+  GemmJob j;
+  dw_job(j, pl, dY, ldy, X, ldx, R);
+  j.p.out = reinterpret_cast<float*>(workspace); j.p.ldo = ldws;
+  j.ordered_ws = reinterpret_cast<float*>(workspace);
+  if (j.split_k < 2) j.split_k = 2;           // (selects the split-K kernel kind; one effective split is fine)
+  if (int rc = gemm_run(j, stream)) return rc;
+  const int S = effective_splits((int)((R + GEMM_BK - 1) / GEMM_BK), j.split_k);
+  dw_reduce_kernel<<<dim3((unsigned)((pl.N + 31) / 32), (unsigned)((pl.M + 31) / 32), 1), dim3(32, 8, 1), 0, stream>>>(
+      reinterpret_cast<const float*>(workspace), S, (int)pl.M, (int)pl.N, ldws, dW, ldw, pl.swap);
+  MOLCLR_CHECK_LAUNCH("gemm_dw_ordered reduce");
+  return 0;
 }
 
 extern "C" int molclr_gemm_tf32(const molclr_gemm_args* args, cudaStream_t stream) {
@@ -1196,6 +1300,7 @@ extern "C" int molclr_gemm_tf32(const molclr_gemm_args* args, cudaStream_t strea
   j.A = a.A; j.lda = a.lda; j.B = a.B; j.ldb = a.ldb; j.split_k = a.split_k;
   j.A_lo = a.A_lo; j.B_lo = a.B_lo;
   j.compensate = a.compensate;
+  j.B16 = a.B16; j.ld16 = a.ld16; j.rows16 = (int)a.rows16;
   GemmParams& p = j.p;
   p.M = (int)a.M; p.N = (int)a.N; p.K = (int)a.K; p.a_mn = a.a_mn; p.b_mn = a.b_mn;
   p.out = a.out; p.ldo = a.ldo; p.transpose_out = a.transpose_out; p.out2 = a.out2; p.ldo2 = a.ldo2;

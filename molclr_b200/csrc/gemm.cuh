@@ -19,6 +19,8 @@ struct GemmParams {
   int derive_lo;               // compensated product with low halves derived on chip: 1 = A_lo from an unrounded A; 2 = "mixed": A and B
                                // both unrounded, bf16 correction tiles of both formed in shared memory (see gemm.cu)
   int segments;                // 1: plain TF32.  3: error-compensated  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (~fp32 accuracy)
+  int b_presplit;              // mixed: the bf16 correction tiles of B arrive by TMA (tmB2 over [2][rows16][K] bf16); the converters touch A only
+  int rows16;                  // rows per half of that tensor
   float* out; long long ldo; int transpose_out;
   float* out2; long long ldo2;
   float* out_lo; long long ldo_lo;   // tf32-rounded residual  v - round_tf32(v)  (compensated-precision consumers)
@@ -52,6 +54,9 @@ struct GemmJob {
   const float* A; long long lda; const float* B; long long ldb;   // p.half16: __half tensors, leading dimensions in halves (% 8 == 0)
   const float* A_lo; const float* B_lo;   // both non-null selects the 3-segment compensated product (same layout/ld as A, B)
   int compensate;              // 1: A and B are unrounded K-major fp32; ~fp32-accurate product, everything derived on chip ("mixed")
+  const void* B16; long long ld16; int rows16;   // compensate: optional pre-split bf16 correction tiles of B (molclr_prepare_weights)
+  float* ordered_ws;           // split-K: write the per-split partial products here ([splits][M][ldws] fp32) with plain stores and sum them
+                               // in split order afterwards (bit-reproducible) instead of accumulating atomically
   int split_k;
   int wide;                    // split-K only: 256 x 320 tiles on CTA pairs (both operands MN-major)
   int bn_hint;                 // 0, or a column-tile width to use instead of the default (more tiles for narrow outputs)

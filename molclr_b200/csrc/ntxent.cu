@@ -30,7 +30,7 @@ constexpr int kStripe16Max = 4096;   // fp16 W stripe [R][4096]: the same bytes
 static int stripe16() {              // MOLCLR_NTX_STRIPE16 = 1024 | 2048 | 4096 (tuning)
   static int v = 0;
   if (!v) {
-    const char* e = getenv("MOLCLR_NTX_STRIPE16");
+    const char* e = debug_env("MOLCLR_NTX_STRIPE16");
     const int x = e ? atoi(e) : 0;
     v = (x == 1024 || x == 2048 || x == 4096) ? x : kStripe16Max;
   }
@@ -136,12 +136,12 @@ using namespace molclr;
 // leave the fp32 range comfortably representable sums)
 static float ntx_bound2(float inv_temperature) {
   const float b = 1.4426950408889634f * inv_temperature * 1.001f;
-  return (b > 0.f && b <= 32.f && !getenv("MOLCLR_NTX_NOBOUND")) ? b : 0.f;
+  return (b > 0.f && b <= 32.f && !debug_env("MOLCLR_NTX_NOBOUND")) ? b : 0.f;
 }
 
 static bool ntx_fused_enabled() {      // MOLCLR_NTX_FUSED=0: the striped two-GEMM backward (A/B timing, and the path of C > 256)
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MOLCLR_NTX_FUSED"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  if (v < 0) { const char* e = debug_env("MOLCLR_NTX_FUSED"); v = (e && atoi(e) == 0) ? 0 : 1; }
   return v != 0;
 }
 
@@ -164,7 +164,9 @@ static NtxLayout ntx_layout(int64_t R, int64_t Rc, int C) {
   l.fwd_total = l.f_cols16 + cols16;
   l.stripe = 0;                                                       // [R][2048] fp32 or [R][4096] fp16
   l.partials = align256((size_t)R * kStripe * sizeof(float));
-  const int64_t slots = num_stripes(Rc) > kNtxFusedMaxSplits ? num_stripes(Rc) : kNtxFusedMaxSplits;
+  // one partial-gradient slot per stripe of the NARROWEST stripe width either path may use (fp32: kStripe; fp16: stripe16())
+  const int64_t nstr = num_stripes(Rc, stripe16() < kStripe ? stripe16() : kStripe);
+  const int64_t slots = nstr > kNtxFusedMaxSplits ? nstr : kNtxFusedMaxSplits;
   l.b_rep16 = l.partials + align256((size_t)slots * R * C * sizeof(float));
   l.b_cols16 = l.b_rep16 + rep16;
   l.b_colsT16 = l.b_cols16 + cols16;

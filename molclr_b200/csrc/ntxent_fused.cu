@@ -307,7 +307,7 @@ int ntx_bwd_fused(const __half* rep16, const __half* cols16, int ld16, int64_t R
   p.row_offset = row_offset; p.row_split = R / 2; p.row_offset2 = row_offset2; p.num_cand = Rc;
   p.k2 = inv_temperature * 1.4426950408889634f; p.bound2 = bound2; p.alpha = inv_temperature * gscale * (1.f / 1024.f);
   static int ahead = -1;
-  if (ahead < 0) { const char* e = getenv("MOLCLR_NTX_AHEAD"); ahead = e ? atoi(e) : NF_AHEAD; if (ahead < 1 || ahead > 3) ahead = NF_AHEAD; }
+  if (ahead < 0) { const char* e = debug_env("MOLCLR_NTX_AHEAD"); ahead = e ? atoi(e) : NF_AHEAD; if (ahead < 1 || ahead > 3) ahead = NF_AHEAD; }
   p.ahead = ahead;
   p.row_lse = row_lse; p.ecol = ecol; p.partials = partials;
   const long long n = (long long)ntx_fused_ecol_floats(Rc);

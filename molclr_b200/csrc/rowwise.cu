@@ -91,22 +91,6 @@ __global__ void __launch_bounds__(kRowThreads) embed_nodes_fwd_kernel(
   }
 }
 
-// Backward of the node embedding: dE1[t] = sum_{n: x[n,0]=t} g[n], dE2[c] likewise, i.e. dE [122][D] = onehot^T [122][N] . g
-// (embedding_dense_backward in the reference).  The one-hot matrix (two ones per row: atom type, 119 + chirality) is
-// written once to a [N][128] fp32 workspace and the contraction runs as a split-K tensor-core GEMM.
-__global__ void __launch_bounds__(256) embed_onehot_kernel(const int32_t* __restrict__ xpacked, int N, float* __restrict__ onehot) {
-  const int lane = threadIdx.x & 31;
-  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
-  for (int n = warp; n < N; n += nwarps) {
-    const int xp = __ldg(xpacked + n), a = xp & 0xff, c = kNumAtomType + (xp >> 8);
-    const int c0 = 4 * lane;
-    float4 v;
-    v.x = (c0 == a || c0 == c) ? 1.f : 0.f; v.y = (c0 + 1 == a || c0 + 1 == c) ? 1.f : 0.f;
-    v.z = (c0 + 2 == a || c0 + 2 == c) ? 1.f : 0.f; v.w = (c0 + 3 == a || c0 + 3 == c) ? 1.f : 0.f;
-    st_f4(onehot + (size_t)n * 128 + c0, v);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // GINE neighbour aggregation, forward.
 //   a[i] = sum_{e in row i, input order} ( f(src[col[e]]) + (B1[t_e] + B2[d_e]) )  +  ( f(src[i]) + (B1[4] + B2[0]) )
@@ -258,7 +242,7 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_fwd_kernel(
 constexpr int kTileThreads = 1024;
 constexpr int kTileConsumers = kTileThreads - 32;      // the last warp hosts the producer thread
 constexpr int kTileMaxStages = 12;
-static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+static int env_int(const char* name, int dflt) { const char* e = debug_env(name); return e ? atoi(e) : dflt; }
 // ring depth and rows of a stage handled by one consumer thread (overridable for measurements; sweep on B200 at the bench
 // shape, tools/sweep_aggregate.sh: 3 x 3 and 4 x 2 are best, deeper rings are SLOWER -- more reads in flight delay the writes)
 static const int g_tile_stages = env_int("MOLCLR_AGG_STAGES", 3), g_tile_rows_per_slot = env_int("MOLCLR_AGG_ROWS", 3);
@@ -266,7 +250,7 @@ static const int g_tile_store_cs = env_int("MOLCLR_AGG_STORE_CS", 0), g_tile_blo
 constexpr uint32_t kNbrLong = 0xFFFFFFFEu;      // entries >= kNbrLong end a row's list: 0xFFFFFFFF = empty, kNbrLong in [0] = use the CSR
 
 // A/B switch for measurements: MOLCLR_AGG_TILE=0 forces the warp-per-row kernel
-static const bool g_aggregate_tile = [] { const char* e = getenv("MOLCLR_AGG_TILE"); return !(e && e[0] == '0'); }();
+static const bool g_aggregate_tile = [] { const char* e = debug_env("MOLCLR_AGG_TILE"); return !(e && e[0] == '0'); }();
 
 static size_t aggregate_tile_smem(int D, int T, int stages) {
   return (size_t)kNumEdgeClass * D * 4 + (size_t)stages * T * (D * 4 + 32) + 2 * kTileMaxStages * sizeof(uint64_t);
@@ -1142,31 +1126,6 @@ extern "C" int molclr_reduce_partials(const float* partials, int P, int len, flo
   return 0;
 }
 
-extern "C" size_t molclr_embed_nodes_bwd_workspace_bytes(int64_t N) { return (size_t)N * 128 * sizeof(float); }
-
-extern "C" int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, int64_t ld_g, int64_t N, int D, float* dE,
-                                      void* workspace, cudaStream_t stream) {
-  REQUIRE_D(D);
-  MOLCLR_REQUIRE(N > 0 && N < (1ll << 31), "embed_nodes_bwd: N out of range");
-  MOLCLR_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "embed_nodes_bwd: workspace must be 16-byte aligned");
-  float* onehot = reinterpret_cast<float*>(workspace);
-  int blocks = (int)((N + 7) / 8);
-  if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
-  embed_onehot_kernel<<<blocks, 256, 0, stream>>>(xpacked, (int)N, onehot);
-  MOLCLR_CHECK_LAUNCH("embed_onehot");
-  const int rows = kNumAtomType + kNumChirality;
-  GemmJob j;
-  memset(&j, 0, sizeof(j));
-  j.A = onehot; j.lda = 128; j.B = g; j.ldb = ld_g;
-  j.p.M = rows; j.p.N = D; j.p.K = (int)N; j.p.a_mn = 1; j.p.b_mn = 1;
-  j.p.out = dE; j.p.ldo = D; j.p.alpha = 1.f; j.p.epi = EPI_GENERIC;
-  const int tiles = molclr_gemm_tile_count(rows, D, 1), num_kb = (int)((N + 31) / 32);
-  int split = molclr_gemm_workers() / (tiles > 0 ? tiles : 1);
-  if (split > num_kb / 8) split = num_kb / 8;
-  j.split_k = split < 2 ? 2 : split;
-  return gemm_run(j, stream);
-}
-
 template <bool HAS_BN, bool DROP>
 static void launch_fwd_tile(const float* src, const float* bn_coef, int relu, const int32_t* rowptr, const int32_t* col,
                             const uint8_t* eattr, const uint32_t* nbr, const float* B1, const float* B2, int64_t N, int D, int T,
@@ -1333,21 +1292,6 @@ extern "C" int molclr_relu_bn_bwd_stats(const float* g, const float* z_prev, con
 // counts node i's in-edges per bond type / direction (self loop included) -- the E' x D embedding_dense_backward of the
 // reference collapsed to dB [8][D] = cnt^T [8][N] . g_a [N][D], which is a skinny split-K contraction: it runs
 // on the tensor-core GEMM (both operands consumed MN-major in place; counts <= 2048 are exact in TF32).
-extern "C" int molclr_edge_table_grad(const float* ga, int64_t ld_ga, const float* cnt, int64_t N, int D, float* dB, cudaStream_t stream) {
-  REQUIRE_D(D);
-  MOLCLR_REQUIRE(N > 0 && N < (1ll << 31), "edge_table_grad: N out of range");
-  GemmJob j;
-  memset(&j, 0, sizeof(j));
-  j.A = cnt; j.lda = 8; j.B = ga; j.ldb = ld_ga;
-  j.p.M = 8; j.p.N = D; j.p.K = (int)N; j.p.a_mn = 1; j.p.b_mn = 1;
-  j.p.out = dB; j.p.ldo = D; j.p.alpha = 1.f; j.p.epi = EPI_GENERIC;
-  const int tiles = molclr_gemm_tile_count(8, D, 1), num_kb = (int)((N + 31) / 32);
-  int split = molclr_gemm_workers() / (tiles > 0 ? tiles : 1);
-  if (split > num_kb / 8) split = num_kb / 8;
-  j.split_k = split < 2 ? 2 : split;          // >= 2 selects the zero-initialised atomic accumulation path
-  return gemm_run(j, stream);
-}
-
 extern "C" size_t molclr_bn_finalize_workspace_bytes(int D) { return (size_t)kBnSplits * 3 * D * sizeof(double); }
 
 extern "C" int molclr_bn_fwd_finalize(const float* tile_stats, int T, int tile_rows, int64_t N, int D, const float* gamma,

@@ -108,7 +108,7 @@ def _gcn_encoder_forward(m, plan, comp, training, pool_mode):
         W_hi, _ = rw.get(g.weight)
         y = torch.empty(N, D, device=dev)
         if comp:
-            ops.gemm(x, rw.raw(g.weight, transpose=True), N, D, D, compensate=True, out=y)    # x @ weight
+            ops.gemm(x, rw.raw(g.weight, transpose=True), N, D, D, compensate=True, B16=rw.b16(g.weight), out=y)    # x @ weight
         else:
             ops.gemm(x, W_hi, N, D, D, b_mn=True, out=y)
         z = ops.gcn_aggregate_fwd(plan, y, g.edge_embedding1.weight.detach(), g.edge_embedding2.weight.detach(), g.bias.detach())
@@ -147,7 +147,7 @@ def _gcn_encoder_backward(m, plan, saved, g_p, training, pool_mode):
         ds = ops.row_sum(ops.edge_table_grad_raw(plan, g_z))                          # scalar bond tables: [8]
         grads[base + 2], grads[base + 3] = ds[:5].reshape(5, 1), ds[5:].reshape(3, 1)
         g_y, _, _ = ops.gine_aggregate_bwd(plan, g_z, round_out=True)                 # (A + I)^T g_z, tf32 for the GEMMs
-        grads[base + 0] = ops.gemm_dw(x_hi, g_y)                                      # dW [in, out] = x^T g_y
+        grads[base + 0] = ops.gemm_dw(x_hi, g_y, ordered=m.deterministic)                                      # dW [in, out] = x^T g_y
         g_x = torch.empty(N, D, device=dev)
         ops.gemm(g_y, W_hi, N, D, D, out=g_x)                                         # g_x = g_y W^T
         if l > 0:
@@ -173,6 +173,7 @@ class _GCNFunction(torch.autograd.Function):
     def forward(ctx, m, plan, *params):
         comp = _gcn_precision(m)
         training, pool_mode = m.training, ops.POOL_MODES[m.pool_name]
+        m._refresh_weights(comp)
         p, p_lo, saved = _gcn_encoder_forward(m, plan, comp, training, pool_mode)
         h, out, head_saved = _head_forward(m, p, p_lo, m._rounded, comp)
         ctx.m, ctx.plan, ctx.saved, ctx.p, ctx.head_saved = m, plan, saved, p, head_saved

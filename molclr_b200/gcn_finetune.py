@@ -24,6 +24,9 @@ class GCN(_EncoderBase):
     def __init__(self, task="classification", num_layer=5, emb_dim=300, feat_dim=256, drop_ratio=0, pool="mean"):
         super().__init__()
         self.num_layer, self.emb_dim, self.feat_dim, self.drop_ratio, self.task = num_layer, emb_dim, feat_dim, drop_ratio, task
+        if feat_dim % 8 != 0 or emb_dim % 4 != 0:
+            # feat_dim // 2 is the width of the head's hidden activations -- tensor-core operands, whose widths are multiples of 4
+            raise ValueError(f"molclr_b200: feat_dim must be a multiple of 8 and emb_dim a multiple of 4, got feat_dim={feat_dim}, emb_dim={emb_dim}")
         if self.num_layer < 2:
             raise ValueError("Number of GNN layers must be greater than 1.")          # gcn_finetune.py:103-104
         if pool not in ("mean", "add", "max"):
@@ -75,6 +78,7 @@ class _GCNFinetuneFunction(torch.autograd.Function):
     def forward(ctx, m, plan, *params):
         comp = _gcn_precision(m)
         training, pool_mode = m.training, ops.POOL_MODES[m.pool_name]
+        m._refresh_weights(comp)
         p, p_lo, saved = _gcn_encoder_forward(m, plan, comp, training, pool_mode)
         mode = ops.ACT_MODES["softplus"]
         h, pred, head_saved, Wf = finetune_head_forward(m, p, p_lo, [m.pred_lin[0], m.pred_lin[2]], mode, comp)

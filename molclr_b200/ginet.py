@@ -41,33 +41,44 @@ class GINEConv(nn.Module):
 
 
 class _RoundedWeights:
-    """TF32 (hi, lo) shadow copies of the GEMM weights -- hi = tf32(w), lo = tf32(w - hi) -- refreshed only
-    when a parameter changed (tracked through the tensor version counter the optimizer bumps)."""
+    """Tensor-core operand forms of the GEMM weights -- hi = tf32(w), lo = tf32(w - hi), an unrounded copy with 128-byte rows
+    (of the transpose, for weights stored [in, out]) and its bf16 correction tiles -- derived from the CURRENT parameter values
+    by ONE kernel launch at the start of every forward (``refresh``).  Nothing is cached across forwards: in-place parameter
+    updates (``torch.optim.Adam(fused=True)``, ``param.data`` writes, ``dist.broadcast``) do not bump tensor version counters,
+    so any cache keyed on them serves stale weights."""
 
     def __init__(self):
-        self._cache = {}
+        self._cur = {}
+
+    def refresh(self, specs):
+        """specs: [(parameter, ops.W_* flags)].  The shadows of exactly these parameters are valid until the next refresh."""
+        outs = ops.prepare_weights([(p.detach(), f) for p, f in specs])
+        self._cur = {id(p): (p.data_ptr(), o) for (p, _), o in zip(specs, outs)}
+
+    def _entry(self, p, key):
+        hit = self._cur.get(id(p))
+        if hit is not None and hit[0] == p.data_ptr() and hit[1][key] is not None:
+            return hit[1]
+        return None
 
     def get(self, p):
-        key = id(p)
-        hit = self._cache.get(key)
-        if hit is not None and hit[0] == p._version and hit[2] == p.data_ptr():
-            return hit[1]
-        r = ops.split_tf32(p.detach())
-        self._cache[key] = (p._version, r, p.data_ptr())
-        return r
+        e = self._entry(p, "hi")
+        if e is not None:
+            return e["hi"], e["lo"]
+        return ops.split_tf32(p.detach())                 # not part of the last refresh: derived now, never cached
 
     def raw(self, p, transpose=False):
         """Unrounded copy (of the transpose, for weights stored [in, out]) with 128-byte aligned rows: the K-major B operand of
-        the compensated GEMM that derives every low half on chip."""
-        key = ("raw", id(p), transpose)
-        hit = self._cache.get(key)
-        if hit is not None and hit[0] == p._version and hit[2] == p.data_ptr():
-            return hit[1]
-        src = p.detach().t() if transpose else p.detach()
-        r = ops.padded(src.shape[0], src.shape[1], p.device)
-        r.copy_(src)
-        self._cache[key] = (p._version, r, p.data_ptr())
-        return r
+        the compensated GEMM."""
+        e = self._entry(p, "raw")
+        if e is not None:
+            return e["raw"]
+        return ops.prepare_weights([(p.detach(), ops.W_RAW_T if transpose else ops.W_RAW)])[0]["raw"]
+
+    def b16(self, p):
+        """bf16 correction tiles [2, rows16, ld16] of ``raw(p)`` (None unless part of the last refresh)."""
+        e = self._entry(p, "b16")
+        return None if e is None else e["b16"]
 
 
 PRECISIONS = ("tf32x3", "tf32")
@@ -91,6 +102,31 @@ class _EncoderBase(nn.Module):
         if self.pool_name not in ops.POOL_MODES:
             # the reference leaves self.pool unset for unknown names and fails at forward (ginet_molclr.py:83-88,113)
             raise AttributeError(f"'{type(self).__name__}' object has no attribute 'pool'")
+
+    deterministic = False      # True: weight gradients are summed in a fixed order (bit-reproducible run to run); see DESIGN.md
+
+    def _gemm_weights(self, comp):
+        """(parameter, ops.W_* operand forms) of every contraction of the model.  GINEConv MLP weights / GCNConv weights: hi
+        (backward dX products, single-pass forward) and, for the compensated forward, the unrounded K-major copy + its bf16
+        correction tiles; every other nn.Linear (projection / prediction heads): hi (+ lo for the explicit 3-pass product)."""
+        enc = ops.W_HI | (ops.W_B16 if comp else 0)
+        head = ops.W_HI | (ops.W_LO if comp else 0)
+        specs, seen = [], set()
+        for g in self.gnns:
+            if hasattr(g, "mlp"):
+                ws = [(g.mlp[0].weight, enc | (ops.W_RAW if comp else 0)), (g.mlp[2].weight, enc | (ops.W_RAW if comp else 0))]
+            else:                                         # GCNConv: stored [in, out]
+                ws = [(g.weight, enc | (ops.W_RAW_T if comp else 0))]
+            specs += ws
+            seen.update(id(w) for w, _ in ws)
+        for mod in self.modules():
+            if isinstance(mod, nn.Linear) and id(mod.weight) not in seen:
+                seen.add(id(mod.weight))
+                specs.append((mod.weight, head))
+        return specs
+
+    def _refresh_weights(self, comp):
+        self._rounded.refresh(self._gemm_weights(comp))
 
     def _dropout_seeds(self):
         """One counter-hash seed per layer and forward call (drawn from torch's CPU generator, so torch.manual_seed makes
@@ -172,7 +208,7 @@ def _head_backward(m, p, saved, g_h, g_out):
     dev = p.device
     g_out = g_out.contiguous()
     g_out_r = ops.round_tf32(g_out)
-    dW2 = ops.gemm_dw(g_out_r, r)
+    dW2 = ops.gemm_dw(g_out_r, r, ordered=m.deterministic)
     db2 = ops.colsum(g_out)
     T = ops.colstat_tiles(G)
     # g_r = (g_out W2) * [r > 0]
@@ -180,14 +216,14 @@ def _head_backward(m, p, saved, g_h, g_out):
     part = torch.empty(T, Fd, device=dev)
     ops.gemm(g_out_r, W2, G, Fd, Fd // 2, b_mn=True, out=g_r, mask=r, round_out=True, colstat=part, colstat_mode=1)
     db0 = ops.reduce_partials(part, T, Fd, torch.empty(Fd, device=dev))
-    dW0 = ops.gemm_dw(g_r, h_r)
+    dW0 = ops.gemm_dw(g_r, h_r, ordered=m.deterministic)
     # g_h(total) = g_r W0 (+ the gradient arriving on the returned representation h)
     g_hh_r = torch.empty(G, Fd, device=dev)
     part2 = torch.empty(T, Fd, device=dev)
     ops.gemm(g_r, W0, G, Fd, Fd, b_mn=True, out2=g_hh_r, addend=None if g_h is None else g_h.contiguous(),
              colstat=part2, colstat_mode=1)
     dbf = ops.reduce_partials(part2, T, Fd, torch.empty(Fd, device=dev))
-    dWf = ops.gemm_dw(g_hh_r, p)
+    dWf = ops.gemm_dw(g_hh_r, p, ordered=m.deterministic)
     g_p = torch.empty(G, D, device=dev)
     ops.gemm(g_hh_r, Wf, G, D, Fd, b_mn=True, out=g_p)
     return g_p, (dWf, dbf, dW0, db0, dW2, db2)
@@ -214,18 +250,19 @@ def _encoder_forward(m, plan, comp, training, pool_mode):
         # compensated GEMM derives the bf16 correction tiles of both operands on chip
         (W1, _), (W2, _) = rw.get(g.mlp[0].weight), rw.get(g.mlp[2].weight)
         B1, B2 = (rw.raw(g.mlp[0].weight), rw.raw(g.mlp[2].weight)) if comp else (W1, W2)
+        S1, S2 = (rw.b16(g.mlp[0].weight), rw.b16(g.mlp[2].weight)) if comp else (None, None)
         u = ops.padded(N, H, dev)
         ubits = ops.relu_bits_buffer(N, H, dev)       # [u > 0] as bits: the backward GEMM's mask (8 MB instead of 246)
-        ops.gemm(a, B1, N, H, D, compensate=comp, out=u, bias=g.mlp[0].bias.detach(), relu=True, relu_bits=ubits)
+        ops.gemm(a, B1, N, H, D, compensate=comp, B16=S1, out=u, bias=g.mlp[0].bias.detach(), relu=True, relu_bits=ubits)
         z = torch.empty(N, D, device=dev)
         if training:
             stats = torch.empty(T, 2, D, device=dev)
-            ops.gemm(u, B2, N, D, H, compensate=comp, out=z, bias=g.mlp[2].bias.detach(), colstat=stats, colstat_mode=2)
+            ops.gemm(u, B2, N, D, H, compensate=comp, B16=S2, out=z, bias=g.mlp[2].bias.detach(), colstat=stats, colstat_mode=2)
             momentum = 0.1 if bn.momentum is None else bn.momentum
             coef = ops.bn_fwd_finalize(stats, T, N, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
                                        bn.num_batches_tracked, momentum, bn.eps)
         else:
-            ops.gemm(u, B2, N, D, H, compensate=comp, out=z, bias=g.mlp[2].bias.detach())
+            ops.gemm(u, B2, N, D, H, compensate=comp, B16=S2, out=z, bias=g.mlp[2].bias.detach())
             coef = ops.bn_eval_coef(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
         layers.append((a, u, z, coef, W1, W2, ubits))
         src, coef_prev = z, coef
@@ -259,10 +296,10 @@ def _encoder_backward(m, plan, layers, g_p, training, pool_mode):
         part = torch.empty(T, H, device=dev)
         ops.gemm(g_z, W2, N, H, D, b_mn=True, out=g_u, mask_bits=ubits, round_out=True, colstat=part, colstat_mode=1)
         grads[base + 1] = ops.reduce_partials(part, T, H, torch.empty(H, device=dev))
-        grads[base + 2] = ops.gemm_dw(g_z, u)                 # dW2 [D, H]
+        grads[base + 2] = ops.gemm_dw(g_z, u, ordered=m.deterministic)                 # dW2 [D, H]
         g_a = torch.empty(N, D, device=dev)
         ops.gemm(g_u, W1, N, D, H, b_mn=True, out=g_a)
-        grads[base + 0] = ops.gemm_dw(g_u, a)                 # dW1 [H, D]
+        grads[base + 0] = ops.gemm_dw(g_u, a, ordered=m.deterministic)                 # dW1 [H, D]
         grads[base + 4], grads[base + 5] = ops.edge_table_grad(plan, g_a)
         if l > 0:
             _, _, zp, coefp, _, _, _ = layers[l - 1]
@@ -289,6 +326,7 @@ class _GINetFunction(torch.autograd.Function):
         comp = _check_precision(m)
         training = m.training
         pool_mode = ops.POOL_MODES[m.pool_name]
+        m._refresh_weights(comp)
         p, p_lo, layers = _encoder_forward(m, plan, comp, training, pool_mode)
         h, out, head_saved = _head_forward(m, p, p_lo, m._rounded, comp)
         ctx.m, ctx.plan, ctx.layers, ctx.p, ctx.head_saved = m, plan, layers, p, head_saved

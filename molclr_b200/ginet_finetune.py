@@ -27,6 +27,9 @@ class GINet(_EncoderBase):
                  pred_n_layer=2, pred_act="softplus"):
         super().__init__()
         self.num_layer, self.emb_dim, self.feat_dim, self.drop_ratio, self.task = num_layer, emb_dim, feat_dim, drop_ratio, task
+        if feat_dim % 8 != 0 or emb_dim % 4 != 0:
+            # feat_dim // 2 is the width of the head's hidden activations -- tensor-core operands, whose widths are multiples of 4
+            raise ValueError(f"molclr_b200: feat_dim must be a multiple of 8 and emb_dim a multiple of 4, got feat_dim={feat_dim}, emb_dim={emb_dim}")
         self.pool_name = pool
         self.x_embedding1 = nn.Embedding(num_atom_type, emb_dim)
         self.x_embedding2 = nn.Embedding(num_chirality_tag, emb_dim)
@@ -142,7 +145,7 @@ def finetune_head_backward(m, p, saved, Wf, g_h, g_pred, mode):
     for k in range(len(saved) - 1, -1, -1):
         x_hi, t, W, O = saved[k]
         I = x_hi.shape[1]
-        dW = ops.gemm_dw(g_t, x_hi)                          # [O4, I]
+        dW = ops.gemm_dw(g_t, x_hi, ordered=m.deterministic)                          # [O4, I]
         head_grads[2 * k], head_grads[2 * k + 1] = dW[:O], ops.colsum(g_t)[:O]
         g_x = torch.empty(G, I, device=dev)
         if k > 0:
@@ -151,7 +154,7 @@ def finetune_head_backward(m, p, saved, Wf, g_h, g_pred, mode):
         else:                                                # reaches h: add the gradient arriving on the returned h
             g_hh_r = torch.empty(G, I, device=dev)
             ops.gemm(g_t, W, G, I, t.shape[1], b_mn=True, out=g_x, out2=g_hh_r, addend=None if g_h is None else g_h.contiguous())
-    dWf = ops.gemm_dw(g_hh_r, p)
+    dWf = ops.gemm_dw(g_hh_r, p, ordered=m.deterministic)
     dbf = ops.colsum(g_x)
     g_p = torch.empty(G, D, device=dev)
     ops.gemm(g_hh_r, Wf, G, D, Fd, b_mn=True, out=g_p)
@@ -164,6 +167,7 @@ class _FinetuneFunction(torch.autograd.Function):
     def forward(ctx, m, plan, *params):
         comp = _check_precision(m)
         training, pool_mode = m.training, ops.POOL_MODES[m.pool_name]
+        m._refresh_weights(comp)
         p, p_lo, layers = _encoder_forward(m, plan, comp, training, pool_mode)
         mode = ops.ACT_MODES[m.pred_act]
         h, pred, saved, Wf = finetune_head_forward(m, p, p_lo, m._head_linears(), mode, comp)

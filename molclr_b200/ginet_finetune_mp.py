@@ -62,6 +62,9 @@ class GINet(_EncoderBase):
                  pred_n_layer=2, pred_act="softplus"):
         super().__init__()
         self.num_motifs, self.num_layer, self.emb_dim, self.feat_dim = num_motifs, num_layer, emb_dim, feat_dim
+        if feat_dim % 8 != 0 or emb_dim % 4 != 0:
+            # feat_dim // 2 is the width of the head's hidden activations -- tensor-core operands, whose widths are multiples of 4
+            raise ValueError(f"molclr_b200: feat_dim must be a multiple of 8 and emb_dim a multiple of 4, got feat_dim={feat_dim}, emb_dim={emb_dim}")
         self.drop_ratio, self.task = drop_ratio, task
         self.pool_name = pool
         self.x_embedding1 = nn.Embedding(num_atom_type, emb_dim)
@@ -141,6 +144,7 @@ class _EncoderFeatFunction(torch.autograd.Function):
     def forward(ctx, m, plan, *params):
         comp = _check_precision(m)
         training, pool_mode = m.training, ops.POOL_MODES[m.pool_name]
+        m._refresh_weights(comp)
         p, p_lo, layers = _encoder_forward(m, plan, comp, training, pool_mode)
         G, D, Fd = p.shape[0], m.emb_dim, m.feat_dim
         Wf, Wf_lo = m._rounded.get(m.feat_lin.weight)
@@ -156,7 +160,7 @@ class _EncoderFeatFunction(torch.autograd.Function):
         G, D, Fd = p.shape[0], m.emb_dim, m.feat_dim
         g_h = g_h.contiguous()
         g_r = ops.round_tf32(g_h)
-        dWf = ops.gemm_dw(g_r, p)                                   # [feat_dim, emb_dim]
+        dWf = ops.gemm_dw(g_r, p, ordered=m.deterministic)                                   # [feat_dim, emb_dim]
         dbf = ops.colsum(g_h)
         g_p = torch.empty(G, D, device=p.device)
         ops.gemm(g_r, Wf, G, D, Fd, b_mn=True, out=g_p)

@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import GemmArgs, check, ptr, ptr2d, stream
+from ._lib import GemmArgs, WeightDesc, check, ptr, ptr2d, stream
 
 F32 = torch.float32
 
@@ -30,7 +30,7 @@ def max_blocks():
 # ------------------------------------------------------------------------------------------- GEMM
 def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=None, out2=None, out_lo=None, bias=None,
          addend=None, mask=None, relu=False, round_out=False, colstat=None, colstat_mode=0, transpose_out=False,
-         split_k=1, lda=None, ldb=None, relu_bits=None, mask_bits=None, compensate=False):
+         split_k=1, lda=None, ldb=None, relu_bits=None, mask_bits=None, compensate=False, B16=None):
     """C[M,N] = sum_k A(m,k) B(n,k) on tcgen05 (TF32 in, FP32 accumulate) with the fused epilogue of
     ``molclr_gemm_tf32`` (see include/molclr_b200.h)."""
     lib = _lib.load()
@@ -52,6 +52,8 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=Non
     a.relu_bits, a.mask_bits = ptr(relu_bits, torch.int32), ptr(mask_bits, torch.int32)
     a.ld_bits = bits.stride(0) if bits is not None else 0
     a.compensate = int(compensate)      # A, B unrounded fp32 (K-major): ~fp32-accurate product, low halves derived on chip
+    if B16 is not None:                 # (tensor bf16 [2, rows16, ld16]): B's correction tiles pre-split by prepare_weights
+        a.B16, a.ld16, a.rows16 = B16.data_ptr(), B16.stride(1), B16.shape[1]
     check(lib.molclr_gemm_tf32(C.byref(a), stream()), "gemm_tf32")
     return out
 
@@ -69,16 +71,70 @@ def colstat_tile_rows():
     return _lib.load().molclr_gemm_colstat_tile_rows()
 
 
-def gemm_dw(dY, X):
+def gemm_dw(dY, X, ordered=False):
     """dW[O,I] = dY^T X for row-major dY [R,O], X [R,I] (both tf32-rounded): the weight gradient of a
     Linear (autograd of ginet_molclr.py:19-23,90-96).  Both operands are consumed MN-major in place;
-    the reduction over R is split across CTAs and accumulated atomically."""
+    the reduction over R is split across CTAs and accumulated atomically (default), or -- ``ordered`` -- written as
+    per-split partials and summed in split order (bit-reproducible run to run)."""
     R, O = dY.shape
     I = X.shape[1]
     dW = _empty(O, I, device=dY.device)
-
-    check(_lib.load().molclr_gemm_dw(ptr2d(dY), dY.stride(0), ptr2d(X), X.stride(0), R, O, I, ptr(dW), dW.stride(0), stream()), "gemm_dw")
+    lib = _lib.load()
+    if ordered:
+        nbytes = lib.molclr_gemm_dw_workspace_bytes(R, O, I)
+        ws = torch.empty(max(nbytes, 16) // 4, dtype=F32, device=dY.device)
+        check(lib.molclr_gemm_dw_ordered(ptr2d(dY), dY.stride(0), ptr2d(X), X.stride(0), R, O, I, ptr(dW), dW.stride(0), ptr(ws), nbytes,
+                                         stream()), "gemm_dw_ordered")
+    else:
+        check(lib.molclr_gemm_dw(ptr2d(dY), dY.stride(0), ptr2d(X), X.stride(0), R, O, I, ptr(dW), dW.stride(0), stream()), "gemm_dw")
     return dW
+
+
+W_HI, W_LO, W_RAW, W_RAW_T, W_B16 = 1, 2, 4, 8, 16
+
+
+def prepare_weights(specs):
+    """ONE launch deriving the tensor-core operand forms of several weights (molclr_prepare_weights).  specs: [(w, flags)] with w a
+    2-D fp32 matrix and flags a combination of W_HI (tf32(w)), W_LO (tf32 residual), W_RAW (unrounded copy, 128-byte rows),
+    W_RAW_T (W_RAW of w^T: K-major copy of a weight stored [in, out]), W_B16 (bf16 correction tiles [2, rows16, ld16] of the raw
+    orientation).  Returns a list of dicts with the keys 'hi', 'lo', 'raw', 'b16' (None where not requested)."""
+    if not specs:
+        return []
+    dev = specs[0][0].device
+    r32 = lambda n: (n + 31) // 32 * 32
+    plans, n32, n16 = [], 0, 0
+    for w, flags in specs:
+        rows, cols = w.shape
+        tr = bool(flags & W_RAW_T)
+        rt, ct = (cols, rows) if tr else (rows, cols)
+        ld_hi, ld_raw, ld16, rows16 = r32(cols), r32(ct), (ct + 63) // 64 * 64, (rt + 255) // 256 * 256
+        o_hi = o_lo = o_raw = o_16 = None
+        if flags & W_HI:
+            o_hi, n32 = n32, n32 + rows * ld_hi
+        if flags & W_LO:
+            o_lo, n32 = n32, n32 + rows * ld_hi
+        if flags & (W_RAW | W_RAW_T):
+            o_raw, n32 = n32, n32 + rt * ld_raw
+        if flags & W_B16:
+            o_16, n16 = n16, n16 + 2 * rows16 * ld16
+        plans.append((rows, cols, tr, rt, ct, ld_hi, ld_raw, ld16, rows16, o_hi, o_lo, o_raw, o_16))
+    buf32 = torch.empty(max(n32, 1), dtype=F32, device=dev)
+    buf16 = torch.empty(max(n16, 1), dtype=torch.bfloat16, device=dev)
+    descs = (WeightDesc * len(specs))()
+    out = []
+    b32, b16 = buf32.data_ptr(), buf16.data_ptr()
+    for d, (w, _), (rows, cols, tr, rt, ct, ld_hi, ld_raw, ld16, rows16, o_hi, o_lo, o_raw, o_16) in zip(descs, specs, plans):
+        d.src, d.ld_src, d.rows, d.cols = ptr2d(w), w.stride(0), rows, cols
+        d.ld_hi, d.ld_raw, d.transpose_raw, d.ld16, d.rows16 = ld_hi, ld_raw, int(tr), ld16, rows16
+        d.hi = b32 + 4 * o_hi if o_hi is not None else None
+        d.lo = b32 + 4 * o_lo if o_lo is not None else None
+        d.raw = b32 + 4 * o_raw if o_raw is not None else None
+        d.b16 = b16 + 2 * o_16 if o_16 is not None else None
+        view = lambda o, r, ld, c: None if o is None else buf32[o:o + r * ld].view(r, ld)[:, :c]
+        out.append({"hi": view(o_hi, rows, ld_hi, cols), "lo": view(o_lo, rows, ld_hi, cols), "raw": view(o_raw, rt, ld_raw, ct),
+                    "b16": None if o_16 is None else buf16[o_16:o_16 + 2 * rows16 * ld16].view(2, rows16, ld16)})
+    check(_lib.load().molclr_prepare_weights(descs, len(specs), stream()), "prepare_weights")
+    return out
 
 
 def colsum(Mx):
@@ -207,10 +263,12 @@ def bn_tile_stats(z):
 
 
 def edge_table_grad_raw(plan, ga):
-    """dB [8, D]: rows 0..4 = gradient of the bond-type table, rows 5..7 = of the bond-direction table."""
+    """dB [8, D]: rows 0..4 = gradient of the bond-type table, rows 5..7 = of the bond-direction table (exact fp32, fixed order)."""
     D = ga.shape[1]
+    lib = _lib.load()
     dB = _empty(8, D, device=ga.device)
-    check(_lib.load().molclr_edge_table_grad(ptr2d(ga), ga.stride(0), ptr(plan.cnt), plan.N, D, ptr(dB), stream()), "edge_table_grad")
+    ws = torch.empty(lib.molclr_edge_table_grad_workspace_bytes(D) // 4, dtype=F32, device=ga.device)
+    check(lib.molclr_edge_table_grad(ptr2d(ga), ga.stride(0), ptr(plan.cnt), plan.N, D, ptr(dB), ptr(ws), stream()), "edge_table_grad")
     return dB
 
 

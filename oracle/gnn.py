@@ -343,55 +343,6 @@ class GINetMotif(nn.Module):
         return h, self.pred_head(h)
 
 
-class GINetLink(nn.Module):
-    """models/ginet_finetune_link.py:52-161 (label-conditioned fine-tune model): the GIN-E encoder and ``feat_lin``; the molecule
-    feature is concatenated with ``label_lin(label_embedding[c])`` for c = 0 and c = 1 and the SAME ``pred_head`` (first layer
-    ``2 * feat_dim`` wide, one output) scores both: ``forward(data, device)`` returns ``(h, cat(score_0, score_1))``."""
-
-    def __init__(self, task="classification", num_layer=5, emb_dim=300, feat_dim=512, drop_ratio=0, pool="mean",
-                 pred_n_layer=2, pred_act="softplus"):
-        super().__init__()
-        self.num_layer, self.emb_dim, self.feat_dim, self.drop_ratio, self.task = num_layer, emb_dim, feat_dim, drop_ratio, task
-        self.x_embedding1 = nn.Embedding(num_atom_type, emb_dim)
-        self.x_embedding2 = nn.Embedding(num_chirality_tag, emb_dim)
-        nn.init.xavier_uniform_(self.x_embedding1.weight.data)
-        nn.init.xavier_uniform_(self.x_embedding2.weight.data)
-        self.label_embedding = nn.Embedding(2, feat_dim)                            # ginet_finetune_link.py:78
-        self.gnns = nn.ModuleList([GINEConv(emb_dim) for _ in range(num_layer)])
-        self.batch_norms = nn.ModuleList([nn.BatchNorm1d(emb_dim) for _ in range(num_layer)])
-        if pool in _POOLS:
-            self.pool = _POOLS[pool]
-        self.feat_lin = nn.Linear(emb_dim, feat_dim)
-        self.label_lin = nn.Linear(feat_dim, feat_dim)                              # :100-101
-        nn.init.xavier_uniform_(self.label_lin.weight)
-        self.pred_n_layer = max(1, pred_n_layer)
-        if pred_act not in ("relu", "softplus"):
-            raise ValueError("Undefined activation function")
-        act = {"relu": lambda: nn.ReLU(inplace=True), "softplus": nn.Softplus}[pred_act]   # :105-127
-        head = [nn.Linear(2 * feat_dim, feat_dim // 2), act()]
-        for _ in range(self.pred_n_layer - 1):
-            head.extend([nn.Linear(feat_dim // 2, feat_dim // 2), act()])
-        head.append(nn.Linear(feat_dim // 2, 1))                                    # out_dim = 1 whatever the task (:98)
-        self.pred_head = nn.Sequential(*head)
-
-    def forward(self, data, device="cpu"):
-        h = self.x_embedding1(data.x[:, 0]) + self.x_embedding2(data.x[:, 1])
-        for layer in range(self.num_layer):                                         # :140-146
-            h = self.gnns[layer](h, data.edge_index, data.edge_attr)
-            h = self.batch_norms[layer](h)
-            if layer == self.num_layer - 1:
-                h = _dropout(self, layer, h)
-            else:
-                h = _dropout(self, layer, F.relu(h))
-        h = self.pool(h, data.batch)
-        h = self.feat_lin(h)
-        G = h.shape[0]
-        h1 = self.label_lin(self.label_embedding(torch.zeros(G, dtype=torch.long)))    # :151-154
-        h2 = self.label_lin(self.label_embedding(torch.ones(G, dtype=torch.long)))
-        p = torch.cat((self.pred_head(torch.cat((h, h1), dim=1)), self.pred_head(torch.cat((h, h2), dim=1))), dim=1)
-        return h, p
-
-
 # ----------------------------------------------------------------------------- fine-tune GCN
 class GCNFinetune(nn.Module):
     """models/gcn_finetune.py:94-163: the GCN encoder, ``feat_lin`` and ``pred_lin`` = Linear -> Softplus -> Linear(., 2 | 1);

@@ -34,7 +34,6 @@ from models.gcn_molclr import GCN as RefGCN                  # noqa: E402
 from models.ginet_finetune import GINet as RefGINetFinetune  # noqa: E402
 from models.gcn_finetune import GCN as RefGCNFinetune        # noqa: E402
 from models.ginet_finetune_mp import GINet as RefGINetMotif   # noqa: E402
-from models.ginet_finetune_link import GINet as RefGINetLink   # noqa: E402
 from utils.nt_xent import NTXentLoss                         # noqa: E402
 
 from molclr_b200.synth import make_pair_batch, make_plain_batch   # noqa: E402
@@ -183,24 +182,6 @@ def motif_case(name, task, graphs, num_motifs, seed, wseed):
     print(name, float(loss))
 
 
-def link_case(name, graphs, seed, wseed):
-    """models/ginet_finetune_link.py GINet: both label-conditioned scores per molecule; trained as a 2-way classification
-    (CrossEntropyLoss over the two scores, the use finetune.py makes of a [G, 2] prediction)."""
-    model = RefGINetLink("classification", 5, 300, 512, 0, "mean")
-    model.load_state_dict(golden_weights(model.state_dict(), wseed))
-    model.train()
-    b = make_plain_batch(graphs, seed=seed, mean_atoms=30.0, std_atoms=10.0)
-    g = torch.Generator().manual_seed(seed)
-    y = (torch.rand(graphs, 1, generator=g) < 0.5).long()
-    h, pred = model(b, "cpu")
-    loss = torch.nn.CrossEntropyLoss()(pred, y.flatten())
-    loss.backward()
-    out = {"weight_seed": np.int64(wseed), "y": y.numpy(), "loss": loss.detach().numpy(), "h": h.detach().numpy(), "pred": pred.detach().numpy()}
-    out.update(batch_arrays(b, "b")); out.update(grad_arrays(model))
-    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
-    print(name, float(loss))
-
-
 if __name__ == "__main__":
     torch.manual_seed(0)
     pretrain_case("enc_gin_pretrain", RefGINet, 24, seed=11, wseed=1)
@@ -215,4 +196,3 @@ if __name__ == "__main__":
     finetune_case("enc_gcn_finetune_reg", "regression", 12, seed=33, wseed=9, gcn=True)
     motif_case("enc_motif_cls", "classification", 12, 20, seed=40, wseed=10)
     motif_case("enc_motif_reg", "regression", 12, 20, seed=41, wseed=11)
-    link_case("enc_link", 12, seed=42, wseed=12)

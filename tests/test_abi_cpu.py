@@ -30,7 +30,8 @@ def test_library_exports_every_declared_symbol(lib_path):
 def test_library_loads_and_reports_version(lib_path):
     from molclr_b200 import _lib
     lib = _lib.load()
-    assert lib.molclr_abi_version() == 1
+    hdr = open(os.path.join(ROOT, "include", "molclr_b200.h")).read()
+    assert lib.molclr_abi_version() == _lib.ABI_VERSION == int(re.search(r"#define MOLCLR_ABI_VERSION (\d+)", hdr).group(1))
     assert lib.molclr_plan_workspace_bytes(10, 20, 3) >= 4 * 23
     assert lib.molclr_gemm_colstat_tiles(129) == 8 and lib.molclr_gemm_colstat_tile_rows() == 32
 
@@ -49,12 +50,26 @@ def test_ntxent_workspace_covers_both_backward_variants(lib_path):
         assert lib.molclr_ntxent_workspace_bytes(R, 2 * Rc, C) > n
 
 
-def test_gemm_args_struct_matches_header_layout():
-    from molclr_b200._lib import GemmArgs
-    # 8-byte aligned fields in header order; guards against silent drift between header and ctypes mirror
-    assert GemmArgs.A.offset == 0 and GemmArgs.lda.offset == 8 and GemmArgs.a_mn.offset == 16
-    assert GemmArgs.B.offset == 24 and GemmArgs.A_lo.offset == 48 and GemmArgs.M.offset == 64 and GemmArgs.out.offset == 88
-    assert GemmArgs.out_lo.offset == 128 and ctypes.sizeof(GemmArgs) == 240 and GemmArgs.relu_bits.offset == 208 and GemmArgs.compensate.offset == 232
+def test_struct_mirrors_match_the_header_as_compiled_by_gcc(tmp_path):
+    """The ctypes mirrors of molclr_gemm_args / molclr_weight_desc have exactly the layout a C compiler gives the header's structs
+    (guards against silent drift between header and binding)."""
+    import subprocess
+    from molclr_b200._lib import GemmArgs, WeightDesc
+    fields = {"molclr_gemm_args": [f[0] for f in GemmArgs._fields_], "molclr_weight_desc": [f[0] for f in WeightDesc._fields_]}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "molclr_b200.h"', 'int main(void) {']
+    for st, fs in fields.items():
+        src.append(f'  printf("{st} %zu\\n", sizeof({st}));')
+        src += [f'  printf("{st}.{f} %zu\\n", offsetof({st}, {f}));' for f in fs]
+    src += ['  return 0;', '}']
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for st, cls in (("molclr_gemm_args", GemmArgs), ("molclr_weight_desc", WeightDesc)):
+        assert int(got[st]) == ctypes.sizeof(cls), st
+        for f in fields[st]:
+            assert int(got[f"{st}.{f}"]) == getattr(cls, f).offset, (st, f)
 
 
 def test_product_has_no_cpu_fallback():

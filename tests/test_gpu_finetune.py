@@ -77,3 +77,33 @@ def test_finetune_loads_pretrained_encoder_and_eval_mode():
 def test_finetune_constructor_errors():
     with pytest.raises(ValueError):
         ginet_finetune.GINet("classification", pred_act="tanh")
+
+
+@pytest.mark.parametrize("task", ["cls", "reg"])
+def test_motif_model_matches_reference_model(task):
+    """models/ginet_finetune_mp.py (motif embedding + GlobalAttention) against golden vectors produced by the reference class
+    (passed twice on the round-1 driver box while still marked xfail; a plain test since round 2)."""
+    import os
+    import numpy as np
+    from molclr_b200 import ginet_finetune_mp
+    from tests.util import golden_weights, golden_batch, check_golden_grads
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"enc_motif_{task}.npz"))
+    m = ginet_finetune_mp.GINet(int(g["num_motifs"]), str(g["task"]), 5, 300, 512, 0, "mean")
+    m.load_state_dict(golden_weights(m.state_dict(), int(g["weight_seed"])))
+    m = m.to(DEV).train()
+    h, pred = m(golden_batch(g, "b").to(DEV), torch.from_numpy(g["mol_idx"]).to(DEV), torch.from_numpy(g["clique_idx"]).to(DEV))
+    y = torch.from_numpy(g["y"]).to(DEV)
+    loss = torch.nn.CrossEntropyLoss()(pred, y.flatten()) if task == "cls" else torch.nn.MSELoss()(pred, y)
+    loss.backward()
+    assert max_rel(h, torch.from_numpy(g["h"])) < 2e-5 and max_rel(pred, torch.from_numpy(g["pred"])) < 2e-5
+    assert abs(loss.item() - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    # zero-gradient parameters (a bias in front of a BatchNorm; the attention gate bias shifts every logit of a softmax group
+    # alike): both sides hold rounding noise only
+    bad = check_golden_grads(m, g, RTOL_GRAD, skip=("mlp.2.bias", "motif_pool.gate_nn.0.bias"))
+    assert not bad, bad
+
+
+def test_feat_dim_must_keep_head_widths_tensor_core_aligned():
+    """feat_dim // 2 is the width of the hidden head activations: a GEMM operand, so it must be a multiple of 4."""
+    with pytest.raises(ValueError):
+        ginet_finetune.GINet("classification", 5, 300, 300)
