@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=512, help="pairs per step of the CPU baseline sample")
     ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the few-step measurements of BASELINE configs 1 (on the GPU), 3 and 4")
     ap.add_argument("--local-negatives", action="store_true", help="N>1: NT-Xent over the local batch only")
     ap.add_argument("--model", default="gin", choices=["gin", "gcn"], help="gin = BASELINE configs 1/2/5 (headline), gcn = config 3")
     return ap.parse_args()
@@ -88,6 +89,15 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------------------------- CPU / reference arm
+def host_cores():
+    """Host threads this process may use: torchrun exports OMP_NUM_THREADS=1 for its workers, which would silently turn the
+    "all host cores" baseline into a single-threaded one -- so the count comes from the scheduler affinity, not the environment."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_run(batch, steps, warmup, threads=None):
     """The reference path on the host cores: oracle restatement of the PyG encoder + the reference's NT-Xent
     formulation (oracle/), full step incl. Adam (molclr.py:109-127).  Returns (molecules/s, threads, s/step)."""
@@ -95,8 +105,7 @@ def cpu_reference_run(batch, steps, warmup, threads=None):
     from oracle.nt_xent import NTXentRestated
     from oracle.step import train_step
     from molclr_b200.synth import make_pair_batch
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or host_cores())
     torch.manual_seed(0)
     model = ognn.GINet(5, 300, 512, 0, "mean")
     crit = NTXentRestated("cpu", batch, 0.1, True)
@@ -132,18 +141,30 @@ def cpu_reference_split(batch):
     return t_enc, t_ntx
 
 
+def workload_config(args, world):
+    """The `config` object both arms print: what the workload IS (BASELINE.json configs[1]; configs[4] for N > 1), not how an arm ran it."""
+    return {"workload": WORKLOAD if args.model == "gin" else WORKLOAD.replace("GIN-5", "GCN-5 (un-normalised GCNConv as the reference computes it)"),
+            "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+            "parallelism": f"dp{world}" + ("" if world == 1 else ("-localneg" if args.local_negatives else "-globalneg")),
+            "l2": "no flush: per-step working set (~5 GB of activations) >> 126 MB L2"}
+
+
 def run_reference(args):
+    """The reference's own CPU implementation of the path (the oracle port: torch_geometric is not installable), all host cores,
+    EXACTLY --steps timed steps after --warmup, each step a bounded sample of the workload: 512 of its 4096 pairs (the reference's
+    default batch; its NT-Xent [2N,2N,C] broadcast needs 68.7 GB at 4096 pairs and ~1.5 s per step at 512)."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     mols, threads, dt = cpu_reference_run(args.cpu_batch, steps, warmup)
     t_enc, t_ntx = cpu_reference_split(args.cpu_batch)
-    sample = (f"{warmup} warm-up + {steps} full steps of {args.cpu_batch} pairs (the reference's default batch; its NT-Xent "
-              f"[2N,2N,C] broadcast needs 68.7 GB at 4096 pairs), oracle port: torch_geometric is not installable")
+    sample = (f"{warmup} warm-up + {steps} full steps (zero_grad, 2 encoder passes, normalize, NT-Xent, backward, Adam) of {args.cpu_batch} pairs "
+              f"out of the workload's {args.batch} per step, {threads} host threads; oracle port of the PyG path + the reference's NT-Xent formulation")
     line = {"impl": "reference", "metric": METRIC, "value": mols, "unit": "molecules/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample_batch": args.cpu_batch},
+            "config": workload_config(args, world),
             "cpu_baseline": {"value": mols, "unit": "molecules/s", "cores": threads, "kind": "port", "sample": sample,
                              "split_s_per_step": {"encoder_fwd_bwd": t_enc, "ntxent_fwd_bwd": t_ntx, "full_step": dt}},
             "e2e": {"value": mols, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -346,10 +367,30 @@ def run_ours(args):
                              "bound by L2<->SM traffic (operand tiles in, output tiles out), see DESIGN.md section 6"}
     ncu_traffic = os.path.join(ROOT, "profiles", "aggregate_traffic.json")
     if roof is not None and os.path.exists(ncu_traffic):
-        try:
-            roof["traffic"] = json.load(open(ncu_traffic))["dram_bytes_per_launch"]
+        try:      # DRAM bytes per launch of this kernel from an `ncu --set full` capture of the same command (cannot be measured outside a profiler)
+            tj = json.load(open(ncu_traffic))
+            roof["traffic"] = tj["dram_bytes_per_launch"]
+            roof["traffic_source"] = tj.get("source", "profiles/aggregate_traffic.json")
         except Exception:
             pass
+
+    # ---------------- whole-step roofline: useful FLOPs of one step / step time, against the TF32 and BF16 tensor peaks
+    n_nodes = sum(int(b.x.size(0)) for b in resident[0])                      # both views
+    D, H, Fd = 300, 600, 512
+    mlp_flops = (3 * 4.0 * D * H if args.model == "gin" else 3 * 2.0 * D * D) * 5 * n_nodes      # fwd + dX + dW, 5 layers
+    head_flops = 3 * 2.0 * (D * Fd + Fd * Fd + Fd * Fd // 2) * 2 * B
+    rows_glob = 2 * B * (1 if (world == 1 or args.local_negatives) else world)
+    ntx_flops = 4 * 2.0 * (2 * B) * rows_glob * (Fd // 2)                      # S forward, S recomputed, dZ (row and column terms)
+    step_flops = mlp_flops + head_flops + ntx_flops
+    try:
+        bf16_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+        bf16_src = "MEASURED_PEAKS.json bf16_tflops_sustained (TF32 = half)"
+    except Exception:
+        bf16_peak, bf16_src = 2250.0, "fallback: nominal dense bf16 (TF32 = half)"
+    step_tfl = step_flops / (ms_step * 1e-3) / 1e12
+    roof_step = {"useful_flops_per_step_per_gpu": step_flops, "achieved_tflops_per_gpu": step_tfl, "frac_of_tf32_peak": step_tfl / (bf16_peak / 2),
+                 "frac_of_bf16_peak": step_tfl / bf16_peak, "peak_source": bf16_src,
+                 "breakdown_gflop": {"encoder_gemms": mlp_flops / 1e9, "head": head_flops / 1e9, "ntxent": ntx_flops / 1e9}}
 
     if rank != 0:
         if world > 1:
@@ -357,23 +398,96 @@ def run_ours(args):
         return
     line = {"metric": METRIC if args.model == "gin" else METRIC.replace("GIN", "GCN"), "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
-            "config": {"workload": WORKLOAD if args.model == "gin" else WORKLOAD.replace("GIN-5", "GCN-5 (un-normalised GCNConv as the reference computes it)"),
-                       "batch_per_gpu": B, "global_batch": B * world, "precision": args.precision, "ntxent_operands": "fp16 (kind::f16; same 11-bit significand as tf32), fp32 accumulation",
-                       "parallelism": f"dp{world}" + ("" if world == 1 else ("-localneg" if args.local_negatives else "-globalneg")),
-                       "l2": "no flush: per-step working set (~5 GB of activations) >> 126 MB L2", "loss": last_loss,
-                       "nodes_per_view": int(resident[0][0].x.size(0)), "edges_per_view": int(resident[0][0].edge_index.size(1))},
+            "config": workload_config(args, world),
+            "run": {"precision": args.precision, "ntxent_operands": "fp16 (kind::f16; same 11-bit significand as tf32), fp32 accumulation",
+                    "loss": last_loss, "nodes_per_view": int(resident[0][0].x.size(0)), "edges_per_view": int(resident[0][0].edge_index.size(1))},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "molecules/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms},
-            "roofline": roof, "roofline_gemm": roof_gemm}
+            "roofline": roof, "roofline_gemm": roof_gemm, "roofline_step": roof_step}
+    if world == 1 and not args.no_extra:
+        line["extra"] = extra_configs(args, dev)
     if world == 1 and not args.no_cpu_baseline:
-        mols, threads, dt = cpu_reference_run(args.cpu_batch, 2, 1)
+        mols, threads, dt = cpu_reference_run(args.cpu_batch, 3, 1)
+        t_enc, t_ntx = cpu_reference_split(args.cpu_batch)
         line["cpu_baseline"] = {"value": mols, "unit": "molecules/s", "cores": threads, "kind": "port",
-                                "sample": f"1 warm-up + 2 full steps of {args.cpu_batch} pairs ({dt:.2f} s/step); oracle port of the PyG path + "
-                                          "the reference's NT-Xent formulation (infeasible at 4096 pairs: 68.7 GB temporaries)"}
+                                "sample": f"1 warm-up + 3 full steps of {args.cpu_batch} pairs ({dt:.2f} s/step) on {threads} host threads; oracle port of the "
+                                          "PyG path + the reference's NT-Xent formulation (infeasible at 4096 pairs: 68.7 GB temporaries)",
+                                "split_s_per_step": {"encoder_fwd_bwd": t_enc, "ntxent_fwd_bwd": t_ntx, "full_step": dt}}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def extra_configs(args, dev):
+    """The other BASELINE.json configurations, measured in the same run with a few steps each (resident inputs, CUDA events):
+    config 1 on the GPU (512 pairs: the like-for-like batch of the CPU arm), config 3 (GCN, 4096 pairs), config 4 (fine-tune
+    GINet, 1024 graphs, BBBP- and ESOL-shaped, drop_ratio 0 and 0.3) and the single-pass `tf32` precision mode of config 2."""
+    from molclr_b200 import Batch, GCN, GINet, NTXentLoss, ginet_finetune, pretrain_loss
+    from molclr_b200.synth import make_pair_batch, make_plain_batch
+
+    def timed(step, warm=5, n=10):
+        for _ in range(warm):
+            step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    fresh = lambda b: Batch(b.x, b.edge_index, b.edge_attr, b.batch, b.num_graphs)
+
+    def pretrain(cls, B, precision):
+        torch.manual_seed(0)
+        model = cls(5, 300, 512, 0, "mean").to(dev)
+        model.precision = precision
+        crit = NTXentLoss(dev, B, 0.1, True)
+        opt = torch.optim.Adam(model.parameters(), 5e-4, weight_decay=1e-5, fused=True)
+        data = [tuple(b.to(dev) for b in make_pair_batch(B, seed=500 + i)) for i in range(2)]
+        k = [0]
+
+        def step():
+            bi, bj = data[k[0] % 2]
+            k[0] += 1
+            opt.zero_grad(set_to_none=True)
+            pretrain_loss(model, crit, fresh(bi), fresh(bj)).backward()
+            opt.step()
+        ms = timed(step)
+        return {"molecules_per_s": B / (ms * 1e-3), "ms_per_step": ms, "batch": B, "precision": precision}
+
+    def finetune(task, atoms, std, drop):
+        torch.manual_seed(0)
+        G = 1024
+        model = ginet_finetune.GINet(task, 5, 300, 512, drop, "mean").to(dev)
+        opt = torch.optim.Adam(model.parameters(), 5e-4, weight_decay=1e-6, fused=True)
+        data = [make_plain_batch(G, seed=700 + i, mean_atoms=atoms, std_atoms=std).to(dev) for i in range(2)]
+        if task == "classification":
+            y, crit = (torch.rand(G, device=dev) < 0.77).long(), torch.nn.CrossEntropyLoss()
+        else:
+            y, crit = torch.randn(G, 1, device=dev) * 2.1 - 3.05, torch.nn.MSELoss()
+        k = [0]
+
+        def step():
+            b = data[k[0] % 2]
+            k[0] += 1
+            opt.zero_grad(set_to_none=True)
+            _h, pred = model(fresh(b))
+            crit(pred, y).backward()
+            opt.step()
+        ms = timed(step)
+        return {"graphs_per_s": G / (ms * 1e-3), "ms_per_step": ms, "graphs": G, "nodes": int(data[0].x.size(0)), "drop_ratio": drop}
+
+    out = {"config1_gpu_512_pairs": pretrain(GINet, 512, "tf32x3"),
+           "config3_gcn_4096_pairs": pretrain(GCN, 4096, "tf32x3"),
+           "config2_precision_tf32": pretrain(GINet, 4096, "tf32"),
+           "config4_finetune_bbbp_cls_drop0": finetune("classification", 46.0, 18.0, 0.0),
+           "config4_finetune_bbbp_cls_drop0.3": finetune("classification", 46.0, 18.0, 0.3),
+           "config4_finetune_esol_reg_drop0": finetune("regression", 26.0, 13.0, 0.0),
+           "config4_finetune_esol_reg_drop0.3": finetune("regression", 26.0, 13.0, 0.3)}
+    return out
 
 
 if __name__ == "__main__":

@@ -281,6 +281,14 @@ int molclr_act_bwd(const float* gy, const float* x, int mode, int64_t n, float* 
 int molclr_l2_normalize_fwd(const float* z, int64_t R, int C, float eps, float* y, float* inv_norm, cudaStream_t stream);
 int molclr_l2_normalize_bwd(const float* gy, const float* y, const float* inv_norm, int64_t R, int C, float eps, float* gz,
                             cudaStream_t stream);
+/* the same with g_y multiplied by the DEVICE scalar *gscale first (the gradient arriving on a scalar loss: no host round trip) */
+int molclr_l2_normalize_bwd_scaled(const float* gy, const float* y, const float* inv_norm, int64_t R, int C, float eps,
+                                   const float* gscale, float* gz, cudaStream_t stream);
+/* Row preparation of NTXentLoss.forward (nt_xent.py:48 and :40-45) in one pass: rep = cat([zA, zB]) (zA = zjs FIRST), each row
+ * divided by max(||row||, eps) when `normalise` (torch.nn.CosineSimilarity, eps 1e-8); y (optional) = the rows, y_r = tf32-rounded
+ * (the tensor-core operand), inv_norm (optional) [RA + RB]. */
+int molclr_ntxent_rows_fwd(const float* zA, const float* zB, int64_t RA, int64_t RB, int C, float eps, int normalise, float* y,
+                           float* y_r, float* inv_norm, cudaStream_t stream);
 
 /* ---- NT-Xent: utils/nt_xent.py:47-65 -------------------------------------------------------------
  * rep [R][C] fp32, R = 2N rows ordered [zjs; zis] (nt_xent.py:48), already L2-normalised when

@@ -1217,7 +1217,8 @@ static int dw_plan(int64_t R, int64_t O, int64_t I, DwPlan* out) {
   int split = gemm_workers(best_wide != 0) / best_tiles;
   if (split > num_kb / 8) split = num_kb / 8;
   if (split < 1) split = 1;
-  out->swap = best_swap; out->wide = best_wide; out->split = split; out->splits = effective_splits(num_kb, split);
+  // `splits`: what the ORDERED variant uses -- it always takes the split-K kernel kind (split_k >= 2), also for a single K split
+  out->swap = best_swap; out->wide = best_wide; out->split = split; out->splits = effective_splits(num_kb, split < 2 ? 2 : split);
   out->M = best_swap ? I : O; out->N = best_swap ? O : I;
   return 0;
 }
@@ -1284,8 +1285,9 @@ extern "C" int molclr_gemm_dw_ordered(const float* dY, int64_t ldy, const float*
   j.p.out = reinterpret_cast<float*>(workspace); j.p.ldo = ldws;
   j.ordered_ws = reinterpret_cast<float*>(workspace);
   if (j.split_k < 2) j.split_k = 2;           // (selects the split-K kernel kind; one effective split is fine)
-  if (int rc = gemm_run(j, stream)) return rc;
   const int S = effective_splits((int)((R + GEMM_BK - 1) / GEMM_BK), j.split_k);
+  MOLCLR_REQUIRE(S == pl.splits, "gemm_dw_ordered: internal: split count %d != planned %d", S, pl.splits);
+  if (int rc = gemm_run(j, stream)) return rc;
   dw_reduce_kernel<<<dim3((unsigned)((pl.N + 31) / 32), (unsigned)((pl.M + 31) / 32), 1), dim3(32, 8, 1), 0, stream>>>(
       reinterpret_cast<const float*>(workspace), S, (int)pl.M, (int)pl.N, ldws, dW, ldw, pl.swap);
   MOLCLR_CHECK_LAUNCH("gemm_dw_ordered reduce");

@@ -1083,18 +1083,43 @@ __global__ void l2_normalize_fwd_kernel(const float* __restrict__ z, int R, int 
   if (lane == 0 && inv_norm) inv_norm[row] = inv;
 }
 
+// The row preparation of NTXentLoss.forward in one pass (nt_xent.py:48 + :40-45): rep = cat([zjs, zis]) -- rows [0, RA) from zA,
+// [RA, RA + RB) from zB -- optionally divided by max(||row||, eps) (torch.nn.CosineSimilarity's normalisation), written
+// unrounded (y, for the backward) and tf32-rounded (y_r, the tensor-core operand).
+__global__ void l2_normalize_cat_fwd_kernel(const float* __restrict__ zA, const float* __restrict__ zB, int RA, int RB, int C, float eps,
+                                            int normalise, float* __restrict__ y, float* __restrict__ y_r, float* __restrict__ inv_norm) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= RA + RB) return;
+  const float* z = row < RA ? zA + (size_t)row * C : zB + (size_t)(row - RA) * C;
+  float inv = 1.f;
+  if (normalise) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) { const float v = z[c]; s = fmaf(v, v, s); }
+    s = warp_sum(s);
+    inv = 1.f / fmaxf(sqrtf(s), eps);
+  }
+  for (int c = lane; c < C; c += 32) {
+    const float v = z[c] * inv;
+    if (y) y[(size_t)row * C + c] = v;
+    y_r[(size_t)row * C + c] = round_tf32(v);
+  }
+  if (lane == 0 && inv_norm) inv_norm[row] = inv;
+}
+
 // backward: g_z = (g_y - y * <g_y, y>) * inv_norm          (rows with ||z|| < eps: g_z = g_y * inv_norm)
+// gscale (optional, device scalar): g_y is multiplied by *gscale first (the incoming gradient of a scalar loss).
 __global__ void l2_normalize_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ y,
-                                        const float* __restrict__ inv_norm, int R, int C, float eps,
+                                        const float* __restrict__ inv_norm, int R, int C, float eps, const float* __restrict__ gscale,
                                         float* __restrict__ gz) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= R) return;
+  const float gs = gscale ? __ldg(gscale) : 1.f;
   float d = 0.f;
-  for (int c = lane; c < C; c += 32) d = fmaf(gy[(size_t)row * C + c], y[(size_t)row * C + c], d);
+  for (int c = lane; c < C; c += 32) d = fmaf(gy[(size_t)row * C + c] * gs, y[(size_t)row * C + c], d);
   d = warp_sum(d);
   const float inv = inv_norm[row];
   if (inv >= 1.f / eps) d = 0.f;          // clamped norm: y = z / eps is linear in z
-  for (int c = lane; c < C; c += 32) gz[(size_t)row * C + c] = (gy[(size_t)row * C + c] - y[(size_t)row * C + c] * d) * inv;
+  for (int c = lane; c < C; c += 32) gz[(size_t)row * C + c] = (gy[(size_t)row * C + c] * gs - y[(size_t)row * C + c] * d) * inv;
 }
 
 }  // namespace molclr
@@ -1501,7 +1526,24 @@ extern "C" int molclr_l2_normalize_fwd(const float* z, int64_t R, int C, float e
 extern "C" int molclr_l2_normalize_bwd(const float* gy, const float* y, const float* inv_norm, int64_t R, int C, float eps, float* gz,
                                        cudaStream_t stream) {
   if (R == 0) return 0;
-  l2_normalize_bwd_kernel<<<(int)((R + 7) / 8), 256, 0, stream>>>(gy, y, inv_norm, (int)R, C, eps, gz);
+  l2_normalize_bwd_kernel<<<(int)((R + 7) / 8), 256, 0, stream>>>(gy, y, inv_norm, (int)R, C, eps, nullptr, gz);
   MOLCLR_CHECK_LAUNCH("l2_normalize_bwd");
+  return 0;
+}
+
+extern "C" int molclr_l2_normalize_bwd_scaled(const float* gy, const float* y, const float* inv_norm, int64_t R, int C, float eps,
+                                              const float* gscale, float* gz, cudaStream_t stream) {
+  if (R == 0) return 0;
+  l2_normalize_bwd_kernel<<<(int)((R + 7) / 8), 256, 0, stream>>>(gy, y, inv_norm, (int)R, C, eps, gscale, gz);
+  MOLCLR_CHECK_LAUNCH("l2_normalize_bwd_scaled");
+  return 0;
+}
+
+extern "C" int molclr_ntxent_rows_fwd(const float* zA, const float* zB, int64_t RA, int64_t RB, int C, float eps, int normalise,
+                                      float* y, float* y_r, float* inv_norm, cudaStream_t stream) {
+  MOLCLR_REQUIRE(y_r != nullptr && RA >= 0 && RB >= 0 && RA + RB < (1ll << 31), "ntxent_rows_fwd: bad arguments");
+  if (RA + RB == 0) return 0;
+  l2_normalize_cat_fwd_kernel<<<(int)((RA + RB + 7) / 8), 256, 0, stream>>>(zA, zB, (int)RA, (int)RB, C, eps, normalise, y, y_r, inv_norm);
+  MOLCLR_CHECK_LAUNCH("ntxent_rows_fwd");
   return 0;
 }

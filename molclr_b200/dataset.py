@@ -100,13 +100,15 @@ class PackedMolecules:
         return ex(n), ex(e), ex(m), int(n.sum()), int(e.sum()), int(m.sum())
 
 
-def augment_pair(store, mol_ids, seed, return_selection=False):
+def augment_pair(store, mol_ids, seed, return_selection=False, aug="node"):
     """The two augmented views (Batch_i, Batch_j) of the molecules ``mol_ids`` (a sequence of store indices), built on the
     store's device by one kernel launch.  ``seed``: any 64-bit integer; the result is a pure function of (store, mol_ids, seed).
     With ``return_selection`` also returns (node_masked [2, N] uint8, bond_deleted [2, sum M] uint8), the subsets drawn."""
     dev = store.device
     if dev.type != "cuda":
         raise RuntimeError("molclr_b200: augment_pair needs the store on a CUDA device (no CPU path exists)")
+    if aug != "node":
+        raise NotImplementedError(f"molclr_b200: augmentation {aug!r} has no device kernel yet (oracle/subgraph.py pins its semantics)")
     node_off, edge_off, bond_off, N, E, M = store.batch_layout(mol_ids)
     B = len(node_off)
     ids = torch.as_tensor(np.asarray(mol_ids, dtype=np.int64)).to(dev, non_blocking=True)

@@ -64,21 +64,76 @@ class GraphPlan:
             self.check()
 
     def check(self):
-        """Raises IndexError for out-of-range inputs (one 16-byte D2H read; the reference's embedding
+        """Raises IndexError for out-of-range inputs (one 16-byte D2H read that drains the stream; the reference's embedding
         lookups raise the same way on CPU)."""
         if not self._checked:
             bits = int(self.status[0].item())
-            if bits:
-                raise IndexError("molclr_b200: invalid batch: " + "; ".join(m for b, m in _ERR_BITS.items() if bits & b))
+            self._checked = True
+            _raise_for(bits)
+        return self
+
+    def check_deferred(self):
+        """The same check without stalling the stream: the status word is copied to pinned host memory behind the plan kernels
+        and examined by a later ``poll_checks`` (the next ``get_plan`` call, or ``poll_checks(block=True)``).  Safe because the
+        plan kernels sanitise what they flag (out-of-range features read row 0, bad edges are dropped): the step that consumed
+        a bad batch computes on the sanitised graph, and the IndexError is raised one call late instead of never."""
+        if not self._checked:
+            _enqueue(self)
             self._checked = True
         return self
 
 
-def get_plan(data, validate=True):
-    """Returns the cached plan of a batch object, building it on first use."""
+def _raise_for(bits):
+    if bits:
+        raise IndexError("molclr_b200: invalid batch: " + "; ".join(m for b, m in _ERR_BITS.items() if bits & b))
+
+
+_RING = 16
+_slots = {}          # device index -> {"host": pinned int32 [_RING][4], "events": [...], "next": int, "pending": [slot, ...]}
+
+
+def _enqueue(plan):
+    dev = plan.status.device
+    st = _slots.get(dev.index)
+    if st is None:
+        st = _slots[dev.index] = {"host": torch.zeros(_RING, 4, dtype=torch.int32).pin_memory(),
+                                  "events": [torch.cuda.Event() for _ in range(_RING)], "next": 0, "pending": []}
+    if len(st["pending"]) == _RING:
+        poll_checks(block=True, device=dev)
+    slot = st["next"]
+    st["next"] = (slot + 1) % _RING
+    st["host"][slot].copy_(plan.status, non_blocking=True)
+    st["events"][slot].record(torch.cuda.current_stream(dev))
+    st["pending"].append(slot)
+
+
+def poll_checks(block=False, device=None):
+    """Examines the deferred batch checks whose status words have arrived (all of them if ``block``); raises IndexError for the
+    first invalid batch found."""
+    for idx, st in list(_slots.items()):
+        if device is not None and device.index != idx:
+            continue
+        while st["pending"]:
+            slot = st["pending"][0]
+            ev = st["events"][slot]
+            if block:
+                ev.synchronize()
+            elif not ev.query():
+                break
+            st["pending"].pop(0)
+            _raise_for(int(st["host"][slot, 0]))
+
+
+def get_plan(data, validate="deferred"):
+    """Returns the cached plan of a batch object, building it on first use.  validate: "deferred" (default: no device sync, see
+    ``GraphPlan.check_deferred``), True / "sync" (raise here, one stream drain), False (no check)."""
     plan = getattr(data, "_molclr_plan", None)
     if plan is None or plan.xpacked.device != data.x.device:
-        plan = GraphPlan(data, validate=validate)
+        if validate == "deferred":
+            poll_checks(device=data.x.device)
+        plan = GraphPlan(data, validate=validate in (True, "sync"))
+        if validate == "deferred":
+            plan.check_deferred()
         try:
             data._molclr_plan = plan
         except AttributeError:

@@ -14,15 +14,10 @@ class _NTXentFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, zis, zjs, temperature, use_cosine, group):
         n = zis.shape[0]
-        rep = torch.cat([zjs, zis], dim=0).contiguous().float()          # nt_xent.py:48 (zjs FIRST)
-        if use_cosine:
-            # torch.nn.CosineSimilarity(dim=-1), eps 1e-8 (nt_xent.py:19,44): x.y / (max(|x|,eps) max(|y|,eps))
-            rep_n, inv = ops.l2_normalize_fwd(rep, 1e-8)
-        else:
-            rep_n, inv = rep, None
-        rep_r = ops.round_tf32(rep_n)
-        cols, row_offset = rep_r, 0
-        loss, row_lse, _row_pos = ops.ntxent_fwd(rep_r, cols, row_offset, 1.0 / temperature, unit_rows=use_cosine)
+        # rep = cat([zjs, zis]) (nt_xent.py:48, zjs FIRST), rows divided by max(|row|, 1e-8) for the cosine similarity
+        # (torch.nn.CosineSimilarity(dim=-1), nt_xent.py:19,44), and the tf32-rounded operand copy: one kernel
+        rep_n, rep_r, inv = ops.ntxent_rows_fwd(zjs.contiguous(), zis.contiguous(), 1e-8, use_cosine)
+        loss, row_lse, _row_pos = ops.ntxent_fwd(rep_r, rep_r, 0, 1.0 / temperature, unit_rows=use_cosine)
         ctx.save_for_backward(rep_n, inv, rep_r, row_lse)
         ctx.n, ctx.temperature, ctx.use_cosine = n, temperature, use_cosine
         return loss[0]
@@ -31,9 +26,10 @@ class _NTXentFunction(torch.autograd.Function):
     def backward(ctx, g_loss):
         rep_n, inv, rep_r, row_lse = ctx.saved_tensors
         g = ops.ntxent_bwd(rep_r, rep_r, 0, 1.0 / ctx.temperature, row_lse, row_lse, unit_rows=ctx.use_cosine)
-        g = g * g_loss
         if ctx.use_cosine:
-            g = ops.l2_normalize_bwd(g.contiguous(), rep_n, inv, 1e-8)
+            g = ops.l2_normalize_bwd(g, rep_n, inv, 1e-8, gscale=g_loss.contiguous())      # (* g_loss folded in: no eager multiply)
+        else:
+            g = g * g_loss
         n = ctx.n
         return g[n:], g[:n], None, None, None
 

@@ -388,11 +388,28 @@ def l2_normalize_fwd(z, eps):
     return y, inv
 
 
-def l2_normalize_bwd(gy, y, inv, eps):
+def l2_normalize_bwd(gy, y, inv, eps, gscale=None):
+    """gscale: optional 0-dim / 1-element DEVICE tensor multiplied into gy first."""
     R, Cc = y.shape
     gz = torch.empty_like(y)
-    check(_lib.load().molclr_l2_normalize_bwd(ptr(gy), ptr(y), ptr(inv), R, Cc, eps, ptr(gz), stream()), "l2_normalize_bwd")
+    if gscale is None:
+        check(_lib.load().molclr_l2_normalize_bwd(ptr(gy), ptr(y), ptr(inv), R, Cc, eps, ptr(gz), stream()), "l2_normalize_bwd")
+    else:
+        check(_lib.load().molclr_l2_normalize_bwd_scaled(ptr(gy), ptr(y), ptr(inv), R, Cc, eps, ptr(gscale.reshape(1)), ptr(gz), stream()),
+              "l2_normalize_bwd_scaled")
     return gz
+
+
+def ntxent_rows_fwd(zA, zB, eps, normalise):
+    """rep = cat([zA, zB]) with rows optionally L2-normalised: returns (y or None, y_r tf32-rounded, inv_norm or None)."""
+    RA, Cc = zA.shape
+    RB = zB.shape[0]
+    y = _empty(RA + RB, Cc, device=zA.device) if normalise else None
+    y_r = _empty(RA + RB, Cc, device=zA.device)
+    inv = _empty(RA + RB, device=zA.device) if normalise else None
+    check(_lib.load().molclr_ntxent_rows_fwd(ptr(zA), ptr(zB), RA, RB, Cc, eps, int(bool(normalise)), ptr(y), ptr(y_r), ptr(inv), stream()),
+          "ntxent_rows_fwd")
+    return y, y_r, inv
 
 
 def ntxent_fwd(rep, cols, row_offset, inv_temperature, row_offset2=None, unit_rows=False):

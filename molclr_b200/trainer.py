@@ -22,6 +22,7 @@ import time
 import torch
 
 from . import GCN, GINet, NTXentLoss, normalize
+from .graph import poll_checks
 from .synth import make_pair_batch
 
 DEFAULT_CONFIG = {
@@ -70,8 +71,9 @@ class _DeviceLoader:
     """Iterable of (xis, xjs) built ON THE GPU from a packed store: ids = a fresh permutation of the subset every epoch
     (SubsetRandomSampler, dataset.py:166-177), views from ``augment_pair`` (one kernel per batch, no host batch at all)."""
 
-    def __init__(self, store, ids, batch_size, seed, reshuffle):
+    def __init__(self, store, ids, batch_size, seed, reshuffle, aug="node"):
         self.store, self.ids, self.batch_size, self.seed, self.reshuffle, self.epoch = store, ids, batch_size, seed, reshuffle, 0
+        self.aug = aug
 
     def __len__(self):
         return len(self.ids) // self.batch_size                 # drop_last=True (dataset.py:179-184)
@@ -83,7 +85,8 @@ class _DeviceLoader:
         self.epoch += 1
         order = np.random.default_rng(self.seed + e).permutation(self.ids) if self.reshuffle else self.ids
         for k in range(len(self)):
-            yield augment_pair(self.store, order[k * self.batch_size:(k + 1) * self.batch_size], seed=(self.seed + e) * 1_000_003 + k)
+            yield augment_pair(self.store, order[k * self.batch_size:(k + 1) * self.batch_size], seed=(self.seed + e) * 1_000_003 + k,
+                               aug=self.aug)
 
 
 class PackedMoleculeDatasetWrapper:
@@ -91,8 +94,11 @@ class PackedMoleculeDatasetWrapper:
     ``molclr-packed v1`` .npz file (``PackedMolecules.save``) or ``"synthetic:<count>"``; the train / validation split by
     ``valid_size`` over a seeded shuffle of the indices follows dataset.py:166-175."""
 
-    def __init__(self, batch_size, num_workers, valid_size, data_path, device="cuda:0", seed=0):
+    def __init__(self, batch_size, num_workers, valid_size, data_path, device="cuda:0", seed=0, aug="node"):
         import numpy as np
+        if aug not in ("node", "subgraph", "mix"):
+            raise ValueError("Not defined molecule augmentation!")                    # molclr.py:186-191
+        self.aug = aug
         from .dataset import PackedMolecules
         from .synth import random_molecule
         self.batch_size, self.num_workers, self.valid_size = batch_size, num_workers, valid_size
@@ -107,8 +113,8 @@ class PackedMoleculeDatasetWrapper:
         self.valid_idx, self.train_idx = idx[:split], idx[split:]
 
     def get_data_loaders(self):
-        return (_DeviceLoader(self.store, self.train_idx, self.batch_size, seed=1, reshuffle=True),
-                _DeviceLoader(self.store, self.valid_idx, self.batch_size, seed=900_000_007, reshuffle=False))
+        return (_DeviceLoader(self.store, self.train_idx, self.batch_size, seed=1, reshuffle=True, aug=self.aug),
+                _DeviceLoader(self.store, self.valid_idx, self.batch_size, seed=900_000_007, reshuffle=False, aug=self.aug))
 
 
 class MolCLR:
@@ -169,6 +175,7 @@ class MolCLR:
                 loss.backward()
                 optimizer.step()
                 n_iter += 1
+            poll_checks(block=True)                        # deferred batch validation (graph.py): raise here at the latest
             if epoch % cfg["eval_every_n_epochs"] == 0:
                 valid_loss = self._validate(model, valid_loader)
                 print(epoch, valid_loss, "(validation)")
@@ -204,6 +211,25 @@ class MolCLR:
         return total / max(count, 1)
 
 
+def build_dataset(config):
+    """The dataset wrapper a config selects.  Nothing is substituted silently: ``synthetic:<count>`` and ``molclr-packed v1``
+    .npz stores are served; a SMILES file (the reference's ``data/pubchem-10m-clean.txt``) needs RDKit, which is not a dependency
+    here -- convert it offline to a packed store (``PackedMolecules.from_graphs(...).save``)."""
+    if config["aug"] not in ("node", "subgraph", "mix"):
+        raise ValueError("Not defined molecule augmentation!")                        # molclr.py:186-191
+    if config.get("fp16_precision"):
+        raise ValueError("molclr_b200.trainer: fp16_precision (apex AMP, molclr.py:93-98) is not supported: the kernels choose their "
+                         "own operand precision (model.precision = 'tf32x3' | 'tf32')")
+    data_path = str(config["dataset"]["data_path"])
+    if data_path.startswith("synthetic:") and config["aug"] == "node" and not config["dataset"].get("packed"):
+        return SyntheticMoleculeDatasetWrapper(config["batch_size"], **{k: v for k, v in config["dataset"].items() if k != "packed"})
+    if data_path.startswith("synthetic:") or data_path.endswith(".npz"):
+        kw = {k: v for k, v in config["dataset"].items() if k != "packed"}
+        return PackedMoleculeDatasetWrapper(config["batch_size"], device=config["gpu"], aug=config["aug"], **kw)
+    raise ValueError(f"molclr_b200.trainer: data_path {data_path!r} is neither 'synthetic:<count>' nor a molclr-packed v1 .npz store; "
+                     "SMILES text needs RDKit (not available here): convert it offline with PackedMolecules.from_graphs(...).save(path)")
+
+
 def main(argv=None):
     import argparse
     import copy
@@ -218,13 +244,7 @@ def main(argv=None):
         config.update(yaml.load(open(args.config), Loader=yaml.FullLoader))
     if args.epochs is not None:
         config["epochs"] = args.epochs
-    if config["aug"] != "node":
-        raise ValueError("Not defined molecule augmentation!" if config["aug"] not in ("subgraph", "mix") else
-                         "molclr_b200.trainer: only the 'node' augmentation (dataset.py) has a synthetic stand-in")
-    data_path = config["dataset"]["data_path"]
-    if not str(data_path).startswith("synthetic:"):
-        config["dataset"]["data_path"] = "synthetic:20000"            # SMILES parsing needs RDKit (out of scope)
-    dataset = SyntheticMoleculeDatasetWrapper(config["batch_size"], **config["dataset"])
+    dataset = build_dataset(config)
     MolCLR(dataset, config).train(max_steps_per_epoch=args.steps_per_epoch)
 
 

@@ -392,3 +392,24 @@ def test_l2_normalize():
     y, inv = ops.l2_normalize_fwd(z.detach().float().to(DEV), 1e-12)
     gz = ops.l2_normalize_bwd(gy.to(DEV), y, inv, 1e-12)
     assert rel_err(y, torch.nn.functional.normalize(z.detach(), dim=1)) < 1e-6 and rel_err(gz, z.grad) < 1e-5
+
+
+def test_plan_deferred_check_raises_one_call_late_without_a_sync():
+    """get_plan (what model.forward calls) validates without draining the stream: the status word travels to pinned memory behind
+    the plan kernels and the IndexError surfaces at the next poll -- the kernels sanitise what they flag, so nothing reads out
+    of bounds in between."""
+    from molclr_b200.graph import get_plan, poll_checks
+    poll_checks(block=True)
+    x = torch.tensor([[5, 0], [119, 0]])
+    bad = Batch(x, torch.zeros(2, 0, dtype=torch.long), torch.zeros(0, 2, dtype=torch.long), torch.zeros(2, dtype=torch.long)).to(DEV)
+    plan = get_plan(bad)                      # no exception here
+    assert plan.N == 2
+    with pytest.raises(IndexError):
+        poll_checks(block=True)
+    poll_checks(block=True)                   # reported once
+    good = make_plain_batch(3, seed=1).to(DEV)
+    get_plan(good)
+    get_plan(make_plain_batch(3, seed=2).to(DEV))
+    poll_checks(block=True)
+    with pytest.raises(IndexError):           # explicit synchronous validation still available
+        get_plan(Batch(bad.x, bad.edge_index, bad.edge_attr, bad.batch), validate=True)
