@@ -288,15 +288,16 @@ int molclr_l2_normalize_bwd_scaled(const float* gy, const float* y, const float*
  * divided by max(||row||, eps) when `normalise` (torch.nn.CosineSimilarity, eps 1e-8); y (optional) = the rows, y_r = tf32-rounded
  * (the tensor-core operand), inv_norm (optional) [RA + RB]. */
 int molclr_ntxent_rows_fwd(const float* zA, const float* zB, int64_t RA, int64_t RB, int C, float eps, int normalise, float* y,
-                           float* y_r, float* inv_norm, cudaStream_t stream);
+                           float* y_r /* optional */, float* inv_norm, void* y16 /* optional: fp16 rows, pitch ld16 halves, zero padded */,
+                           int64_t ld16, cudaStream_t stream);
 
 /* ---- NT-Xent: utils/nt_xent.py:47-65 -------------------------------------------------------------
  * rep [R][C] fp32, R = 2N rows ordered [zjs; zis] (nt_xent.py:48), already L2-normalised when
  * use_cosine (the cosine similarity's own normalisation is applied by the caller-side kernels
  * molclr_l2_normalize_*).  `cols` [Rc][C] are the candidate rows (== rep for one GPU; the all-gathered
  * projections of every rank for global negatives).  rep is this rank's [zjs_local; zis_local]: its first R/2 rows are
- * candidates row_offset + r, the other R/2 rows candidates row_offset2 + (r - R/2) (one GPU: 0 and R/2); the positive of
- * global row g is column (g + Rc/2) mod Rc.
+ * candidates row_offset + r, the other R/2 rows candidates row_offset2 + (r - R/2) (one GPU: 0 and R/2); the positive of a
+ * local row is the row at the same position of the OTHER block (nt_xent.py:53-55), wherever the blocks of other ranks lie.
  *   forward : row_lse[r] = log sum_{k != self} exp(S[r][k]/tau),  row_pos[r] = S[r][pos(r)]/tau,
  *             loss[0] = sum_r (row_lse[r] - row_pos[r]) / Rc  (this rank's share of the mean over Rc anchors).
  *   backward: g_rep[r] = (gscale/tau) * sum_k (P[r][k] + P[k][r] - 2*[k = pos(r)]) * cols[k],
@@ -312,6 +313,16 @@ int molclr_ntxent_rows_fwd(const float* zA, const float* zB, int64_t RA, int64_t
  * fp32 accumulation, twice the tensor rate; the softmax weights are staged as fp16 x 2^10).  unit_rows == 0 (dot similarity, nt_xent.py:32-38, rows of
  * any magnitude): TF32 operands, fp32 weights. */
 size_t molclr_ntxent_workspace_bytes(int64_t R, int64_t Rc, int C);
+/* The same two calls on FP16 operands supplied by the caller (unit-norm rows; row pitch ld16 halves, a multiple of 8): what the
+ * data-parallel path all-gathers -- half the NVLink bytes of fp32 rows and no conversion pass over the gathered candidates.
+ * Available when molclr_ntxent_h_supported(C, 1/tau) (the fused-backward conditions: C <= 256, C % 8 == 0, 1/tau <= ~22). */
+int molclr_ntxent_h_supported(int C, float inv_temperature);
+int molclr_ntxent_fwd_h(const void* rep16, const void* cols16, int64_t ld16, int64_t R, int64_t Rc, int C, int64_t row_offset,
+                        int64_t row_offset2, float inv_temperature, float* row_lse, float* row_pos, float* loss /* [1], optional */,
+                        void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int molclr_ntxent_bwd_h(const void* rep16, const void* cols16, int64_t ld16, int64_t R, int64_t Rc, int C, int64_t row_offset,
+                        int64_t row_offset2, float inv_temperature, const float* row_lse, const float* col_lse, float gscale,
+                        float* g_rep, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int molclr_ntxent_fwd(const float* rep, const float* cols, int64_t R, int64_t Rc, int C, int64_t row_offset,
                       int64_t row_offset2, float inv_temperature, int unit_rows, float* row_lse, float* row_pos,
                       float* loss /* [1], optional */, void* workspace, size_t workspace_bytes, cudaStream_t stream);

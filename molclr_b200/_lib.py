@@ -97,7 +97,10 @@ SIGNATURES = {
     "molclr_l2_normalize_fwd": (i32, [vp, i64, i32, f32, vp, vp, vp]),
     "molclr_l2_normalize_bwd": (i32, [vp, vp, vp, i64, i32, f32, vp, vp]),
     "molclr_l2_normalize_bwd_scaled": (i32, [vp, vp, vp, i64, i32, f32, vp, vp, vp]),
-    "molclr_ntxent_rows_fwd": (i32, [vp, vp, i64, i64, i32, f32, i32, vp, vp, vp, vp]),
+    "molclr_ntxent_rows_fwd": (i32, [vp, vp, i64, i64, i32, f32, i32, vp, vp, vp, vp, i64, vp]),
+    "molclr_ntxent_h_supported": (i32, [i32, f32]),
+    "molclr_ntxent_fwd_h": (i32, [vp, vp, i64, i64, i64, i32, i64, i64, f32, vp, vp, vp, vp, sz, vp]),
+    "molclr_ntxent_bwd_h": (i32, [vp, vp, i64, i64, i64, i32, i64, i64, f32, vp, vp, f32, vp, vp, sz, vp]),
     "molclr_ntxent_workspace_bytes": (sz, [i64, i64, i32]),
     "molclr_ntxent_fwd": (i32, [vp, vp, i64, i64, i32, i64, i64, f32, i32, vp, vp, vp, vp, sz, vp]),
     "molclr_ntxent_bwd": (i32, [vp, vp, i64, i64, i32, i64, i64, f32, i32, vp, vp, f32, vp, vp, sz, vp]),

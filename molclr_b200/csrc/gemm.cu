@@ -77,13 +77,18 @@ struct GemmCfg {
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
 };
 
-__device__ __forceinline__ float ntx_w_elem(float acc, const GemmParams& p, float lse_r, long long grow_g, long long gcol) {
+// Global candidate index of the POSITIVE of local row `grow`: rows [0, row_split) are this rank's zjs block (candidates row_offset + r),
+// the rest its zis block (candidates row_offset2 + r - row_split); partners sit at the same position of the other block
+// (nt_xent.py:53-55: the +-N diagonals).  Independent of how the blocks of different ranks are laid out among the candidates.
+__device__ __forceinline__ long long ntx_pos(const GemmParams& p, long long grow) {
+  return grow < p.row_split ? grow + p.row_offset2 : grow - p.row_split + p.row_offset;
+}
+
+__device__ __forceinline__ float ntx_w_elem(float acc, const GemmParams& p, float lse_r, long long grow_g, long long pos, long long gcol) {
   // W[r][k] = P[r][k] + P[k][r] - 2*[k == pos(r)],  P[i][k] = exp(l - lse_i) for k != i   (nt_xent.py:53-65 differentiated)
   if (gcol == grow_g) return 0.f;
   const float l = acc * p.inv_tau;
   float w = __expf(l - lse_r) + __expf(l - __ldg(p.col_lse + gcol));
-  long long pos = grow_g + p.num_cand / 2;
-  if (pos >= p.num_cand) pos -= p.num_cand;
   if (gcol == pos) w -= 2.f;
   return w;
 }
@@ -92,8 +97,9 @@ __device__ __forceinline__ float4 epilogue_apply(float4 v, const GemmParams& p, 
   if (p.epi == EPI_NTX_W) {
     const float lse_r = __ldg(p.row_lse + grow);
     const long long gr = grow < p.row_split ? grow + p.row_offset : grow - p.row_split + p.row_offset2, gc = col + p.col_offset;
-    v.x = ntx_w_elem(v.x, p, lse_r, gr, gc); v.y = ntx_w_elem(v.y, p, lse_r, gr, gc + 1);
-    v.z = ntx_w_elem(v.z, p, lse_r, gr, gc + 2); v.w = ntx_w_elem(v.w, p, lse_r, gr, gc + 3);
+    const long long pos = ntx_pos(p, grow);
+    v.x = ntx_w_elem(v.x, p, lse_r, gr, pos, gc); v.y = ntx_w_elem(v.y, p, lse_r, gr, pos, gc + 1);
+    v.z = ntx_w_elem(v.z, p, lse_r, gr, pos, gc + 2); v.w = ntx_w_elem(v.w, p, lse_r, gr, pos, gc + 3);
     return v;
   }
   if (p.alpha != 1.f) { v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha; }
@@ -505,8 +511,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // 32 columns per step, the next step's TMEM loads in flight while this one is reduced; per element the loop costs
         // FMNMX + FFMA + EX2 + FADD: the self column and the positive are looked for only in the blocks that hold them.
         const long long gr = grow < p.row_split ? grow + p.row_offset : grow - p.row_split + p.row_offset2;
-        long long pos = gr + p.num_cand / 2;
-        if (pos >= p.num_cand) pos -= p.num_cand;
+        const long long pos = ntx_pos(p, grow);
         const float k2 = p.inv_tau * 1.4426950408889634f;            // logits in base-2 units
         float mx = (H16 && p.ntx_bound2 > 0.f) ? p.ntx_bound2 : -INFINITY, sum = 0.f;
         constexpr int NBLK = (BN / 32 + NSHARE - 1) / NSHARE;        // 32-column blocks of this warp: c0 = 32 (half + b NSHARE)
@@ -577,8 +582,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // scaled by 2^10 (weights are <= 2; the scale keeps the ~1/Rc entries out of the fp16 subnormals), for the fp16 dZ GEMM.
         // 32 columns per step (next step's TMEM loads in flight), thread = row; per element 2 FFMA + 2 EX2 + FADD + half a CVT.
         const long long gr = grow < p.row_split ? grow + p.row_offset : grow - p.row_split + p.row_offset2;
-        long long pos = gr + p.num_cand / 2;
-        if (pos >= p.num_cand) pos -= p.num_cand;
+        const long long pos = ntx_pos(p, grow);
         const float k2 = p.inv_tau * 1.4426950408889634f;
         constexpr int NBLK = (BN / 32 + NSHARE - 1) / NSHARE;
         uint8_t* stg8 = reinterpret_cast<uint8_t*>(stg);             // 32 rows x 64 bytes, 16-byte chunk j of row r at j ^ ((r >> 1) & 3)
@@ -716,8 +720,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (EK == K_NTX_W) {
             // W[r][k] = P[r][k] + P[k][r] - 2 [k == pos(r)],  P[i][k] = exp(l - lse_i) for k != i (nt_xent.py:53-65 differentiated)
             const long long gr = grow < p.row_split ? grow + p.row_offset : grow - p.row_split + p.row_offset2;
-            long long pos = gr + p.num_cand / 2;
-            if (pos >= p.num_cand) pos -= p.num_cand;
+            const long long pos = ntx_pos(p, grow);
             const float k2 = p.inv_tau * 1.4426950408889634f;
             const float lr2 = (grow < p.M ? __ldg(p.row_lse + grow) : 0.f) * 1.4426950408889634f;
             const long long gc0 = n0 + c0 + p.col_offset;
@@ -846,8 +849,7 @@ __global__ void __launch_bounds__(128) gemm_simt_kernel(const float* __restrict_
   if (p.epi == EPI_NTX_FWD) {
     if (grow < p.M) {
       const long long gr = grow < p.row_split ? grow + p.row_offset : grow - p.row_split + p.row_offset2;
-      long long pos = gr + p.num_cand / 2;
-      if (pos >= p.num_cand) pos -= p.num_cand;
+      const long long pos = ntx_pos(p, grow);
       float mx = -INFINITY, sum = 0.f;
       for (int j = 0; j < 32; ++j) {
         const long long gc = n0 + j + p.col_offset;

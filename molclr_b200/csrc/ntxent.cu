@@ -202,9 +202,11 @@ static int ntx_operands16(const float* rep, const float* cols, int64_t R, int64_
   return to_half(rep, R, C, ld16, rep16_buf, stream);
 }
 
-extern "C" int molclr_ntxent_fwd(const float* rep, const float* cols, int64_t R, int64_t Rc, int C, int64_t row_offset,
-                                 int64_t row_offset2, float inv_temperature, int unit_rows, float* row_lse, float* row_pos, float* loss,
-                                 void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+// rep16 / cols16 (optional, both or neither): fp16 copies of the operands supplied by the caller (row pitch ld16_in halves); then rep /
+// cols may be NULL and nothing is converted here.
+static int ntxent_fwd_impl(const float* rep, const float* cols, const __half* rep16_in, const __half* cols16_in, int64_t ld16_in, int64_t R,
+                           int64_t Rc, int C, int64_t row_offset, int64_t row_offset2, float inv_temperature, int unit_rows, float* row_lse,
+                           float* row_pos, float* loss, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   MOLCLR_REQUIRE(R > 0 && R % 2 == 0 && Rc >= R && Rc % 4 == 0 && C % 4 == 0, "ntxent: need R > 0 and even, Rc >= R, Rc %% 4 == 0, C %% 4 == 0 (R=%lld Rc=%lld C=%d)",
                  (long long)R, (long long)Rc, C);
   MOLCLR_REQUIRE(workspace_bytes >= molclr_ntxent_workspace_bytes(R, Rc, C), "ntxent_fwd: workspace too small");
@@ -218,11 +220,16 @@ extern "C" int molclr_ntxent_fwd(const float* rep, const float* cols, int64_t R,
   memset(&j, 0, sizeof(j));
   j.A = rep; j.lda = C; j.B = cols; j.ldb = C; j.split_k = 1;
   if (f16) {
-    const __half* rep16;
-    int rc = ntx_operands16(rep, cols, R, Rc, C, l.ld16, reinterpret_cast<__half*>(ws + l.f_rep16), reinterpret_cast<__half*>(ws + l.f_cols16), &rep16, stream);
-    if (rc) return rc;
-    j.A = reinterpret_cast<const float*>(rep16); j.lda = l.ld16;
-    j.B = reinterpret_cast<const float*>(ws + l.f_cols16); j.ldb = l.ld16;
+    const __half* rep16 = rep16_in;
+    const __half* cols16 = cols16_in;
+    int64_t ld16 = ld16_in;
+    if (!cols16_in) {
+      int rc = ntx_operands16(rep, cols, R, Rc, C, l.ld16, reinterpret_cast<__half*>(ws + l.f_rep16), reinterpret_cast<__half*>(ws + l.f_cols16), &rep16, stream);
+      if (rc) return rc;
+      cols16 = reinterpret_cast<const __half*>(ws + l.f_cols16); ld16 = l.ld16;
+    }
+    j.A = reinterpret_cast<const float*>(rep16); j.lda = ld16;
+    j.B = reinterpret_cast<const float*>(cols16); j.ldb = ld16;
     j.p.half16 = 1; j.p.ntx_bound2 = ntx_bound2(inv_temperature);
   }
   GemmParams& p = j.p;
@@ -237,6 +244,49 @@ extern "C" int molclr_ntxent_fwd(const float* rep, const float* cols, int64_t R,
     ntx_loss_kernel<<<1, 1024, 0, stream>>>(row_lse, row_pos, (int)R, 1.0f / (float)Rc, loss);
     MOLCLR_CHECK_LAUNCH("ntx_loss");
   }
+  return 0;
+}
+
+extern "C" int molclr_ntxent_fwd(const float* rep, const float* cols, int64_t R, int64_t Rc, int C, int64_t row_offset,
+                                 int64_t row_offset2, float inv_temperature, int unit_rows, float* row_lse, float* row_pos, float* loss,
+                                 void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  return ntxent_fwd_impl(rep, cols, nullptr, nullptr, 0, R, Rc, C, row_offset, row_offset2, inv_temperature, unit_rows, row_lse, row_pos, loss,
+                         workspace, workspace_bytes, stream);
+}
+
+// fp16 operands supplied by the caller (unit-norm rows): what the data-parallel path all-gathers, at half the bytes of fp32
+extern "C" int molclr_ntxent_h_supported(int C, float inv_temperature) {
+  return (gemm_f16_ok() && ntx_bound2(inv_temperature) > 0.f && C <= 256 && C % 8 == 0 && ntx_fused_enabled()) ? 1 : 0;
+}
+
+extern "C" int molclr_ntxent_fwd_h(const void* rep16, const void* cols16, int64_t ld16, int64_t R, int64_t Rc, int C, int64_t row_offset,
+                                   int64_t row_offset2, float inv_temperature, float* row_lse, float* row_pos, float* loss, void* workspace,
+                                   size_t workspace_bytes, cudaStream_t stream) {
+  MOLCLR_REQUIRE(rep16 && cols16 && ld16 >= C && ld16 % 8 == 0, "ntxent_fwd_h: fp16 operands with a row pitch that is a multiple of 8 halves");
+  MOLCLR_REQUIRE(molclr_ntxent_h_supported(C, inv_temperature), "ntxent_fwd_h: not supported for C=%d, 1/tau=%g (see molclr_ntxent_h_supported)", C, inv_temperature);
+  return ntxent_fwd_impl(nullptr, nullptr, reinterpret_cast<const __half*>(rep16), reinterpret_cast<const __half*>(cols16), ld16, R, Rc, C, row_offset,
+                         row_offset2, inv_temperature, 1, row_lse, row_pos, loss, workspace, workspace_bytes, stream);
+}
+
+extern "C" int molclr_ntxent_bwd_h(const void* rep16, const void* cols16, int64_t ld16, int64_t R, int64_t Rc, int C, int64_t row_offset,
+                                   int64_t row_offset2, float inv_temperature, const float* row_lse, const float* col_lse, float gscale, float* g_rep,
+                                   void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  MOLCLR_REQUIRE(R > 0 && R % 2 == 0 && Rc >= R && Rc % 4 == 0 && C % 4 == 0, "ntxent: need R > 0 and even, Rc >= R, Rc %% 4 == 0, C %% 4 == 0");
+  MOLCLR_REQUIRE(rep16 && cols16 && ld16 >= C && ld16 % 8 == 0, "ntxent_bwd_h: fp16 operands with a row pitch that is a multiple of 8 halves");
+  MOLCLR_REQUIRE(molclr_ntxent_h_supported(C, inv_temperature), "ntxent_bwd_h: not supported for C=%d, 1/tau=%g (see molclr_ntxent_h_supported)", C, inv_temperature);
+  MOLCLR_REQUIRE(workspace_bytes >= molclr_ntxent_workspace_bytes(R, Rc, C), "ntxent_bwd_h: workspace too small");
+  const NtxLayout l = ntx_layout(R, Rc, C);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  float* partials = reinterpret_cast<float*>(ws + l.partials);
+  const int splits = ntx_fused_splits(R, Rc);
+  int rc = ntx_bwd_fused(reinterpret_cast<const __half*>(rep16), reinterpret_cast<const __half*>(cols16), (int)ld16, R, Rc, C, row_offset, row_offset2,
+                         inv_temperature, ntx_bound2(inv_temperature), row_lse, col_lse, gscale, reinterpret_cast<float*>(ws + l.b_ecol), partials, splits, stream);
+  if (rc) return rc;
+  const long long len4 = (long long)R * C / 4;
+  long long blocks = (len4 + 255) / 256;
+  if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+  ntx_sum_partials_kernel<<<(int)blocks, 256, 0, stream>>>(partials, splits, len4, g_rep);
+  MOLCLR_CHECK_LAUNCH("ntx_sum_partials");
   return 0;
 }
 

@@ -200,8 +200,7 @@ ntx_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       block_range(sp, b0, b1);
       const int grow = rt * NF_BM + row;
       const long long gr = grow < p.row_split ? grow + p.row_offset : grow - p.row_split + p.row_offset2;
-      long long pos = gr + p.num_cand / 2;
-      if (pos >= p.num_cand) pos -= p.num_cand;
+      const long long pos = grow < p.row_split ? grow + p.row_offset2 : grow - p.row_split + p.row_offset;     // partner row of the other block
       const float er = grow < p.R ? ptx::ex2_approx(10.f + p.bound2 - __ldg(p.row_lse + grow) * 1.4426950408889634f) : 0.f;
       for (int b = b0; b < b1; ++b, ++it) {
         if ((int)(it & 1) != grp) continue;                  // the other group's block (P buffer it & 1 belongs to group it & 1)

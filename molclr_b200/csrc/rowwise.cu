@@ -9,6 +9,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "gemm.cuh"
 #include "molclr_b200.h"
@@ -1087,7 +1089,8 @@ __global__ void l2_normalize_fwd_kernel(const float* __restrict__ z, int R, int 
 // [RA, RA + RB) from zB -- optionally divided by max(||row||, eps) (torch.nn.CosineSimilarity's normalisation), written
 // unrounded (y, for the backward) and tf32-rounded (y_r, the tensor-core operand).
 __global__ void l2_normalize_cat_fwd_kernel(const float* __restrict__ zA, const float* __restrict__ zB, int RA, int RB, int C, float eps,
-                                            int normalise, float* __restrict__ y, float* __restrict__ y_r, float* __restrict__ inv_norm) {
+                                            int normalise, float* __restrict__ y, float* __restrict__ y_r, float* __restrict__ inv_norm,
+                                            __half* __restrict__ y16, int ld16) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= RA + RB) return;
   const float* z = row < RA ? zA + (size_t)row * C : zB + (size_t)(row - RA) * C;
@@ -1101,8 +1104,10 @@ __global__ void l2_normalize_cat_fwd_kernel(const float* __restrict__ zA, const 
   for (int c = lane; c < C; c += 32) {
     const float v = z[c] * inv;
     if (y) y[(size_t)row * C + c] = v;
-    y_r[(size_t)row * C + c] = round_tf32(v);
+    if (y_r) y_r[(size_t)row * C + c] = round_tf32(v);
+    if (y16) y16[(size_t)row * ld16 + c] = __float2half_rn(v);
   }
+  if (y16) for (int c = C + lane; c < ld16; c += 32) y16[(size_t)row * ld16 + c] = __float2half_rn(0.f);
   if (lane == 0 && inv_norm) inv_norm[row] = inv;
 }
 
@@ -1540,10 +1545,12 @@ extern "C" int molclr_l2_normalize_bwd_scaled(const float* gy, const float* y, c
 }
 
 extern "C" int molclr_ntxent_rows_fwd(const float* zA, const float* zB, int64_t RA, int64_t RB, int C, float eps, int normalise,
-                                      float* y, float* y_r, float* inv_norm, cudaStream_t stream) {
-  MOLCLR_REQUIRE(y_r != nullptr && RA >= 0 && RB >= 0 && RA + RB < (1ll << 31), "ntxent_rows_fwd: bad arguments");
+                                      float* y, float* y_r, float* inv_norm, void* y16, int64_t ld16, cudaStream_t stream) {
+  MOLCLR_REQUIRE((y_r != nullptr || y16 != nullptr) && RA >= 0 && RB >= 0 && RA + RB < (1ll << 31), "ntxent_rows_fwd: bad arguments");
+  MOLCLR_REQUIRE(y16 == nullptr || (ld16 >= C && ld16 % 8 == 0), "ntxent_rows_fwd: ld16 must be >= C and a multiple of 8 halves");
   if (RA + RB == 0) return 0;
-  l2_normalize_cat_fwd_kernel<<<(int)((RA + RB + 7) / 8), 256, 0, stream>>>(zA, zB, (int)RA, (int)RB, C, eps, normalise, y, y_r, inv_norm);
+  l2_normalize_cat_fwd_kernel<<<(int)((RA + RB + 7) / 8), 256, 0, stream>>>(zA, zB, (int)RA, (int)RB, C, eps, normalise, y, y_r, inv_norm,
+                                                                          reinterpret_cast<__half*>(y16), (int)ld16);
   MOLCLR_CHECK_LAUNCH("ntxent_rows_fwd");
   return 0;
 }

@@ -53,71 +53,148 @@ __global__ void __launch_bounds__(256) prepare_weights_kernel(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------ table gradients
-constexpr int kTableUnroll = 8;
+constexpr int kTabRY = 4;          // row lanes per CTA (at most)
+constexpr int kTabUnroll = 6;
 
-// partials[blockIdx.x][c][col] = sum over this block's rows n (increasing) of w[n][c] * g[n][col], c < 8.  Thread = column.
-__global__ void __launch_bounds__(1024) class_weighted_colsum_kernel(const float* __restrict__ g, long long ld_g, const float* __restrict__ w,
+// partials[blockIdx.x][c][:] = sum over this CTA's rows n of w[n][c] * g[n][:], c < 8.  Thread (tx, ty): float4 column chunk tx, row
+// lane ty takes rows r0 + ty, r0 + ty + RY, ... in increasing order (registers); the RY lane sums are then added in lane order.
+__global__ void __launch_bounds__(384, 2) class_weighted_colsum_kernel(const float* __restrict__ g, long long ld_g, const float* __restrict__ w,
                                                                      int N, int D, int rows_per_block, float* __restrict__ partials) {
-  const int col = threadIdx.x;
+  extern __shared__ float red[];          // [RY][8][D]
+  const int tx = threadIdx.x, ty = threadIdx.y, D4 = D >> 2, RY = blockDim.y;
   const int r0 = blockIdx.x * rows_per_block, r1 = min(N, r0 + rows_per_block);
-  float acc[8];
+  float4 acc[8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-  if (col < D) {
-    for (int n = r0; n < r1; n += kTableUnroll) {
-      float gv[kTableUnroll];
+  for (int c = 0; c < 8; ++c) acc[c] = f4_zero();
+  if (tx < D4) {
+    for (int n = r0 + ty; n < r1; n += RY * kTabUnroll) {
+      float4 gv[kTabUnroll];
 #pragma unroll
-      for (int u = 0; u < kTableUnroll; ++u) gv[u] = (n + u < r1) ? __ldg(g + (size_t)(n + u) * ld_g + col) : 0.f;
+      for (int u = 0; u < kTabUnroll; ++u) {
+        const int row = n + u * RY;
+        gv[u] = row < r1 ? ldg_f4(g + (size_t)row * ld_g + 4 * tx) : f4_zero();
+      }
 #pragma unroll
-      for (int u = 0; u < kTableUnroll; ++u) {
-        if (n + u >= r1) break;
-        const float4 w0 = ldg_f4(w + (size_t)(n + u) * 8), w1 = ldg_f4(w + (size_t)(n + u) * 8 + 4);     // same address in every thread: broadcast
-        acc[0] = fmaf(w0.x, gv[u], acc[0]); acc[1] = fmaf(w0.y, gv[u], acc[1]); acc[2] = fmaf(w0.z, gv[u], acc[2]); acc[3] = fmaf(w0.w, gv[u], acc[3]);
-        acc[4] = fmaf(w1.x, gv[u], acc[4]); acc[5] = fmaf(w1.y, gv[u], acc[5]); acc[6] = fmaf(w1.z, gv[u], acc[6]); acc[7] = fmaf(w1.w, gv[u], acc[7]);
+      for (int u = 0; u < kTabUnroll; ++u) {
+        const int row = n + u * RY;
+        if (row >= r1) break;
+        const float4 w0 = ldg_f4(w + (size_t)row * 8), w1 = ldg_f4(w + (size_t)row * 8 + 4);     // one address per warp: broadcast
+        const float wc[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          acc[c].x = fmaf(wc[c], gv[u].x, acc[c].x); acc[c].y = fmaf(wc[c], gv[u].y, acc[c].y);
+          acc[c].z = fmaf(wc[c], gv[u].z, acc[c].z); acc[c].w = fmaf(wc[c], gv[u].w, acc[c].w);
+        }
       }
     }
 #pragma unroll
-    for (int c = 0; c < 8; ++c) partials[((size_t)blockIdx.x * 8 + c) * D + col] = acc[c];
+    for (int c = 0; c < 8; ++c) st_f4(red + ((size_t)ty * 8 + c) * D + 4 * tx, acc[c]);
+  }
+  __syncthreads();
+  const int tid = ty * blockDim.x + tx, nth = blockDim.x * blockDim.y;
+  for (int e = tid; e < 8 * D; e += nth) {
+    float s = red[e];
+    for (int l = 1; l < RY; ++l) s += red[(size_t)l * 8 * D + e];
+    partials[(size_t)blockIdx.x * 8 * D + e] = s;
   }
 }
 
-// partials[blockIdx.x][t][col0 + col] for t < 122: rows 0..118 by atom type (key & 0xff), 119..121 by chirality (key >> 8).
-// The atom-type rows live in a [119][CW] shared-memory tile (thread = column: its read-modify-write chain over the block's rows
-// is sequential, hence ordered); the three chirality rows in registers.
-constexpr int kOnehotCW = 160;      // columns per CTA: 119 x 160 x 4 B = 76 KB -> two CTAs per SM
-__global__ void __launch_bounds__(kOnehotCW) onehot_colsum_kernel(const float* __restrict__ g, long long ld_g, const int32_t* __restrict__ key,
-                                                                  int N, int D, int rows_per_block, float* __restrict__ partials) {
-  extern __shared__ float tile[];          // [119][kOnehotCW]
-  const int tx = threadIdx.x, col = blockIdx.y * kOnehotCW + tx;
-  const int r0 = blockIdx.x * rows_per_block, r1 = min(N, r0 + rows_per_block);
-  for (int t = 0; t < kNumAtomType; ++t) tile[t * kOnehotCW + tx] = 0.f;
-  float ch0 = 0.f, ch1 = 0.f, ch2 = 0.f;
-  if (col < D) {
-    constexpr int U = 16;
-    for (int n = r0; n < r1; n += U) {
-      float gv[U];
-      int kv[U];
+// Atom / chirality table gradients: partials[blockIdx.x][t][cols of this CTA] for t < 122 (rows 0..118 by atom type = key & 0xff,
+// 119..121 by chirality = key >> 8).  A CTA walks its nodes in chunks of 128: the chunk's rows are ordered by atom type with a stable
+// in-CTA counting rank, each row lane then sums a contiguous piece of that order in REGISTERS, run by run, and adds a finished
+// run to the CTA's [119][CW] shared-memory tile -- one read-modify-write per run instead of per node.  Only the first run of a
+// lane can share its class with another lane (the order is sorted): it goes to a per-lane spill row that is added in lane order.
+// Everything has a fixed order: bit-reproducible.
+constexpr int kOhChunk = 128, kOhRY = 4, kOhUnroll = 8, kOhMaxCW = 384;
+__global__ void __launch_bounds__(512, 1) onehot_colsum_kernel(const float* __restrict__ g, long long ld_g, const int32_t* __restrict__ key,
+                                                             int N, int D, int CW, int chunks_per_block, float* __restrict__ partials) {
+  extern __shared__ float sm[];
+  float* tile = sm;                                        // [119][CW]
+  float* spill = tile + (size_t)kNumAtomType * CW;         // [RY][CW]
+  float* chbuf = spill + (size_t)kOhRY * CW;               // [RY][3][CW]
+  int* keys = reinterpret_cast<int*>(chbuf + (size_t)kOhRY * 3 * CW);     // [128]
+  int* order = keys + kOhChunk;                            // [128] chunk-local row index at each sorted position
+  int* spill_cls = order + kOhChunk;                       // [RY]
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * blockDim.x + tx, nth = blockDim.x * blockDim.y;
+  const int col0 = blockIdx.y * CW, cw = min(CW, D - col0), cw4 = cw >> 2;
+  const bool active = tx < cw4;
+  for (int e = tid; e < kNumAtomType * CW; e += nth) tile[e] = 0.f;
+  float4 ch0 = f4_zero(), ch1 = f4_zero(), ch2 = f4_zero();
+  const int chunk_lo = blockIdx.x * chunks_per_block, nchunks = (N + kOhChunk - 1) / kOhChunk;
+  const int chunk_hi = min(nchunks, chunk_lo + chunks_per_block);
+  for (int chunk = chunk_lo; chunk < chunk_hi; ++chunk) {
+    const int base = chunk * kOhChunk, cnt = min(kOhChunk, N - base);
+    __syncthreads();                                       // previous chunk fully consumed (keys / order / spill reuse)
+    if (tid < kOhChunk) keys[tid] = tid < cnt ? __ldg(key + base + tid) : 0;
+    if (tid < kOhRY) spill_cls[tid] = -1;
+    __syncthreads();
+    if (tid < cnt) {                                       // stable rank of row tid in atom-type order
+      const int a = keys[tid] & 0xff;
+      int rank = 0;
+      for (int j = 0; j < cnt; ++j) { const int aj = keys[j] & 0xff; rank += (aj < a || (aj == a && j < tid)) ? 1 : 0; }
+      order[rank] = tid;
+    }
+    __syncthreads();
+    const int seg = (cnt + kOhRY - 1) / kOhRY, p0 = ty * seg, p1 = min(cnt, p0 + seg);
+    if (active && p0 < p1) {
+      float4 acc = f4_zero();
+      int cur = -1;
+      bool first = true;
+      auto flush = [&]() {
+        if (cur < 0) return;
+        if (first && ty > 0) { st_f4(spill + (size_t)ty * CW + 4 * tx, acc); if (tx == 0) spill_cls[ty] = cur; }
+        else { float* t = tile + (size_t)cur * CW + 4 * tx; st_f4(t, f4_add(*reinterpret_cast<const float4*>(t), acc)); }
+        first = false;
+      };
+      for (int p = p0; p < p1; p += kOhUnroll) {
+        float4 v[kOhUnroll];
+        int kk[kOhUnroll];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const bool ok = n + u < r1;
-        gv[u] = ok ? __ldg(g + (size_t)(n + u) * ld_g + col) : 0.f;
-        kv[u] = ok ? __ldg(key + n + u) : 0;
+        for (int u = 0; u < kOhUnroll; ++u) {
+          const bool ok = p + u < p1;
+          const int r = ok ? order[p + u] : 0;
+          kk[u] = ok ? keys[r] : -1;
+          v[u] = ok ? ldg_f4(g + (size_t)(base + r) * ld_g + col0 + 4 * tx) : f4_zero();
+        }
+#pragma unroll
+        for (int u = 0; u < kOhUnroll; ++u) {
+          if (kk[u] < 0) break;
+          const int a = kk[u] & 0xff, c = kk[u] >> 8;
+          if (a != cur) { flush(); cur = a; acc = f4_zero(); }
+          acc = f4_add(acc, v[u]);
+          if (c == 0) ch0 = f4_add(ch0, v[u]); else if (c == 1) ch1 = f4_add(ch1, v[u]); else if (c == 2) ch2 = f4_add(ch2, v[u]);
+        }
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (n + u >= r1) break;
-        const int a = kv[u] & 0xff, c = kv[u] >> 8;
-        if (a < kNumAtomType) tile[a * kOnehotCW + tx] += gv[u];
-        ch0 += c == 0 ? gv[u] : 0.f; ch1 += c == 1 ? gv[u] : 0.f; ch2 += c == 2 ? gv[u] : 0.f;
+      flush();
+    }
+    __syncthreads();
+    if (ty == 0 && active) {                               // split runs, in lane order
+      for (int l = 1; l < kOhRY; ++l) {
+        const int cls = spill_cls[l];
+        if (cls < 0) continue;
+        float* t = tile + (size_t)cls * CW + 4 * tx;
+        st_f4(t, f4_add(*reinterpret_cast<const float4*>(t), *reinterpret_cast<const float4*>(spill + (size_t)l * CW + 4 * tx)));
       }
     }
-    float* out = partials + (size_t)blockIdx.x * (kNumAtomType + kNumChirality) * D + col;
-    for (int t = 0; t < kNumAtomType; ++t) out[(size_t)t * D] = tile[t * kOnehotCW + tx];
-    out[(size_t)kNumAtomType * D] = ch0; out[(size_t)(kNumAtomType + 1) * D] = ch1; out[(size_t)(kNumAtomType + 2) * D] = ch2;
+  }
+  if (active) {
+    st_f4(chbuf + ((size_t)ty * 3 + 0) * CW + 4 * tx, ch0);
+    st_f4(chbuf + ((size_t)ty * 3 + 1) * CW + 4 * tx, ch1);
+    st_f4(chbuf + ((size_t)ty * 3 + 2) * CW + 4 * tx, ch2);
+  }
+  __syncthreads();
+  float* out = partials + (size_t)blockIdx.x * (kNumAtomType + kNumChirality) * D + col0;
+  for (int e = tid; e < kNumAtomType * cw; e += nth) { const int t = e / cw, c = e - t * cw; out[(size_t)t * D + c] = tile[(size_t)t * CW + c]; }
+  for (int e = tid; e < kNumChirality * cw; e += nth) {
+    const int t = e / cw, c = e - t * cw;
+    float s = chbuf[(size_t)t * CW + c];
+#pragma unroll
+    for (int l = 1; l < kOhRY; ++l) s += chbuf[((size_t)l * 3 + t) * CW + c];
+    out[(size_t)(kNumAtomType + t) * D + c] = s;
   }
 }
 
-static int table_blocks() { return 4 * sm_count(); }
+static int table_blocks() { return 2 * sm_count(); }
 static int onehot_blocks() { return sm_count(); }
 
 }  // namespace molclr
@@ -157,14 +234,24 @@ extern "C" size_t molclr_edge_table_grad_workspace_bytes(int D) { return (size_t
 
 extern "C" int molclr_edge_table_grad(const float* ga, int64_t ld_ga, const float* cnt, int64_t N, int D, float* dB, void* workspace,
                                       cudaStream_t stream) {
-  MOLCLR_REQUIRE(D > 0 && D <= 1024, "edge_table_grad: D=%d must be in 1..1024", D);
+  MOLCLR_REQUIRE(D > 0 && D % 4 == 0 && D <= 512 && ld_ga % 4 == 0 && (reinterpret_cast<uintptr_t>(ga) & 15) == 0,
+                 "edge_table_grad: D=%d must be a multiple of 4, <= 512; rows 16-byte aligned", D);
   MOLCLR_REQUIRE(N > 0 && N < (1ll << 31), "edge_table_grad: N out of range");
   MOLCLR_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "edge_table_grad: workspace must be 16-byte aligned");
   const int P = table_blocks();
-  const int rpb = (int)((N + P - 1) / P);
+  const int tx = (D / 4 + 31) / 32 * 32, ry = 384 / tx < kTabRY ? 384 / tx : kTabRY;      // <= 384 threads (two CTAs per SM)
+  int rpb = (int)((N + P - 1) / P);
+  rpb = (rpb + ry - 1) / ry * ry;
   const int used = (int)((N + rpb - 1) / rpb);
   float* partials = reinterpret_cast<float*>(workspace);
-  class_weighted_colsum_kernel<<<used, (D + 31) / 32 * 32, 0, stream>>>(ga, ld_ga, cnt, (int)N, D, rpb, partials);
+  const size_t smem = (size_t)ry * 8 * D * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(class_weighted_colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabRY * 8 * 512 * (int)sizeof(float));
+    if (e != cudaSuccess) return cuda_fail(e, "edge_table_grad: cudaFuncSetAttribute");
+    attr_set = true;
+  }
+  class_weighted_colsum_kernel<<<used, dim3((unsigned)tx, (unsigned)ry, 1), smem, stream>>>(ga, ld_ga, cnt, (int)N, D, rpb, partials);
   MOLCLR_CHECK_LAUNCH("edge_table_grad");
   return molclr_reduce_partials(partials, used, 8 * D, 1.f, 0, dB, stream);
 }
@@ -176,22 +263,29 @@ extern "C" size_t molclr_embed_nodes_bwd_workspace_bytes(int64_t N) {
 
 extern "C" int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, int64_t ld_g, int64_t N, int D, float* dE,
                                       void* workspace, cudaStream_t stream) {
-  MOLCLR_REQUIRE(D > 0 && D <= 1024, "embed_nodes_bwd: D=%d must be in 1..1024", D);
+  MOLCLR_REQUIRE(D > 0 && D % 4 == 0 && D <= 1024 && ld_g % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0,
+                 "embed_nodes_bwd: D=%d must be a multiple of 4, <= 1024; rows 16-byte aligned", D);
   MOLCLR_REQUIRE(N > 0 && N < (1ll << 31), "embed_nodes_bwd: N out of range");
   MOLCLR_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "embed_nodes_bwd: workspace must be 16-byte aligned");
+  const int slices = (D + kOhMaxCW - 1) / kOhMaxCW;
+  const int CW = ((D + slices - 1) / slices + 3) / 4 * 4;               // columns per CTA (a multiple of 4, <= 384)
+  const int nchunks = (int)((N + kOhChunk - 1) / kOhChunk);
   const int P = onehot_blocks();
-  const int rpb = (int)((N + P - 1) / P);
-  const int used = (int)((N + rpb - 1) / rpb);
-  const size_t smem = (size_t)kNumAtomType * kOnehotCW * sizeof(float);
+  const int cpb = (nchunks + P - 1) / P;
+  const int used = (nchunks + cpb - 1) / cpb;
+  const size_t smem = ((size_t)kNumAtomType + kOhRY + 3 * kOhRY) * CW * sizeof(float) + (2 * kOhChunk + kOhRY) * sizeof(int);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(onehot_colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t mx = ((size_t)kNumAtomType + kOhRY + 3 * kOhRY) * kOhMaxCW * sizeof(float) + (2 * kOhChunk + kOhRY) * sizeof(int);
+    cudaError_t e = cudaFuncSetAttribute(onehot_colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx);
     if (e != cudaSuccess) return cuda_fail(e, "embed_nodes_bwd: cudaFuncSetAttribute");
     attr_set = true;
   }
   float* partials = reinterpret_cast<float*>(workspace);
-  onehot_colsum_kernel<<<dim3((unsigned)used, (unsigned)((D + kOnehotCW - 1) / kOnehotCW), 1), kOnehotCW, smem, stream>>>(
-      g, ld_g, xpacked, (int)N, D, rpb, partials);
+  int tx = (CW / 4 + 31) / 32 * 32;
+  if (tx * kOhRY < kOhChunk) tx = kOhChunk / kOhRY;                       // the first 128 threads load / rank the chunk's keys
+  onehot_colsum_kernel<<<dim3((unsigned)used, (unsigned)slices, 1), dim3((unsigned)tx, kOhRY, 1), smem, stream>>>(
+      g, ld_g, xpacked, (int)N, D, CW, cpb, partials);
   MOLCLR_CHECK_LAUNCH("embed_nodes_bwd");
   return molclr_reduce_partials(partials, used, (kNumAtomType + kNumChirality) * D, 1.f, 0, dE, stream);
 }

@@ -4,14 +4,16 @@ One process per GPU (``torch.distributed``, NCCL over NVLink/NVSwitch).  Molecul
 through the whole encoder, so every rank runs the encoder kernels on its own batch of B pairs with its own
 BatchNorm statistics; the path has exactly two exchange steps:
 
-1. **NT-Xent with global negatives** -- the (cosine-normalised, tf32-rounded) projections of all ranks
-   are all-gathered into the candidate matrix ``cols [2][W*B][C]`` (rows ``[all zjs ; all zis]``, the
-   reference's ordering of nt_xent.py:48 extended over ranks), each rank computes the log-sum-exp of ITS
-   2B anchor rows against all 2*W*B candidates, the 2B row log-sum-exps are all-gathered, and the backward
+1. **NT-Xent with global negatives** -- the (cosine-normalised) projections of all ranks are all-gathered
+   (ONE collective, fp16 rows when the fp16 kernels apply) into the candidate matrix ``cols [W][2B][C]``
+   (rank-major blocks ``[zjs_r ; zis_r]``: the loss does not depend on the candidate order, and a row's positive
+   is found in its own rank's other block), each rank computes the log-sum-exp of ITS
+   2B anchor rows against all 2*W*B candidates, the 2B row log-sum-exps are all-gathered (ONE collective), and the backward
    uses the symmetry of the loss (``molclr_ntxent_bwd``: the column-softmax term of a local row is
    recomputed from the same similarity tile with the other row's gathered log-sum-exp), so the gradient of
    the GLOBAL mean loss w.r.t. the local projections needs no reduce-scatter of a [2*W*B, C] gradient.
-2. **Gradient all-reduce** -- one flat fp32 buffer (2.4 M elements for GIN-5/300/512), summed over ranks.
+2. **Gradient all-reduce** -- one flat fp32 buffer (2.4 M elements for GIN-5/300/512) in buckets by backward-pass
+   readiness, each bucket's all-reduce launched from a gradient hook so that it overlaps the rest of the backward.
 
 Loss / gradient scale: the objective is the mean over all 2*W*B anchors.  With global negatives every rank
 holds the exact partial derivative of that objective through its own projections, so parameter gradients
@@ -34,51 +36,63 @@ class CudaKernels:
         from . import functional, ops
         self._ops = ops
         self.normalize = functional.normalize
-        self.l2_normalize_fwd = ops.l2_normalize_fwd
         self.l2_normalize_bwd = ops.l2_normalize_bwd
-        self.round_tf32 = ops.round_tf32
-        self.ntxent_fwd = ops.ntxent_fwd
-        self.ntxent_bwd = ops.ntxent_bwd
 
+    def rows_fwd(self, zjs, zis, eps, normalise, inv_temperature):
+        """(y, operand, inv): the local rows [zjs; zis], optionally unit-normalised; `operand` is what gets all-gathered and fed to
+        the tensor cores -- fp16 rows when the fp16 path applies (cosine similarity, C <= 256, moderate 1/tau), else tf32-rounded fp32."""
+        ops = self._ops
+        if normalise and ops.ntxent_h_supported(zjs.shape[1], inv_temperature):
+            y, _, inv, y16 = ops.ntxent_rows_fwd(zjs.contiguous(), zis.contiguous(), eps, True, want_r=False, want16=True)
+            return y, y16, inv
+        y, y_r, inv = ops.ntxent_rows_fwd(zjs.contiguous(), zis.contiguous(), eps, normalise)
+        return y, y_r, inv
 
-def _gather_rows(dst, src, group):
-    """dst [W*R, ...] <- concatenation over ranks of src [R, ...] (rank order)."""
-    dist.all_gather_into_tensor(dst, src.contiguous(), group=group)
+    def ntxent_fwd(self, rep, cols, C, row_offset, inv_temperature, row_offset2, unit_rows):
+        if cols.dtype == torch.float16:
+            return self._ops.ntxent_fwd_h(rep, cols, C, row_offset, row_offset2, inv_temperature)
+        return self._ops.ntxent_fwd(rep, cols, row_offset, inv_temperature, row_offset2, unit_rows=unit_rows)
+
+    def ntxent_bwd(self, rep, cols, C, row_offset, inv_temperature, row_lse, col_lse, row_offset2, unit_rows):
+        if cols.dtype == torch.float16:
+            return self._ops.ntxent_bwd_h(rep, cols, C, row_offset, row_offset2, inv_temperature, row_lse, col_lse)
+        return self._ops.ntxent_bwd(rep, cols, row_offset, inv_temperature, row_lse, col_lse, row_offset2, unit_rows=unit_rows)
 
 
 class _GlobalNTXentFunction(torch.autograd.Function):
-    """NT-Xent (nt_xent.py:47-65) of this rank's 2B anchors against the candidates of all ranks."""
+    """NT-Xent (nt_xent.py:47-65) of this rank's 2B anchors against the candidates of all ranks.
+
+    Exchange steps: ONE all-gather of the local operand rows [zjs_r; zis_r] ([2B, C], fp16 when the fp16 kernels apply: half the
+    bytes) into the candidate matrix [W][2B][C] -- rank-major, so this rank's rows are a VIEW of it -- and ONE all-gather of the
+    2B row log-sum-exps.  The kernels find a row's positive at the same position of its rank's other block
+    (row_offset = r 2B, row_offset2 = r 2B + B); the loss does not depend on how the candidates are ordered."""
 
     @staticmethod
     def forward(ctx, zis, zjs, temperature, use_cosine, group, kern):
         W, r = dist.get_world_size(group), dist.get_rank(group)
         B, C = zis.shape
-        local = torch.cat([zjs, zis], dim=0).contiguous()                    # nt_xent.py:48 (zjs FIRST)
-        if use_cosine:                                                       # CosineSimilarity eps 1e-8 (nt_xent.py:19,44)
-            local_n, inv = kern.l2_normalize_fwd(local, 1e-8)
-        else:
-            local_n, inv = local, None
-        local_r = kern.round_tf32(local_n)
-        Bg = W * B
-        cols = torch.empty(2 * Bg, C, dtype=local_r.dtype, device=local_r.device)
-        _gather_rows(cols[:Bg], local_r[:B], group)                          # all zjs
-        _gather_rows(cols[Bg:], local_r[B:], group)                          # all zis
-        # local rows [zjs; zis] are candidates r*B.. and Bg + r*B.. of the global ordering
-        share, lse, _pos = kern.ntxent_fwd(local_r, cols, r * B, 1.0 / temperature, Bg + r * B, unit_rows=use_cosine)
-        col_lse = torch.empty(2 * Bg, dtype=lse.dtype, device=lse.device)
-        _gather_rows(col_lse[:Bg], lse[:B], group)
-        _gather_rows(col_lse[Bg:], lse[B:], group)
-        ctx.save_for_backward(local_n, inv, local_r, cols, lse, col_lse)
-        ctx.meta = (B, Bg, r, temperature, use_cosine, kern)
+        # rows [zjs; zis] (nt_xent.py:48), CosineSimilarity's normalisation (eps 1e-8, nt_xent.py:19,44), operand copy: one kernel
+        local_n, local_op, inv = kern.rows_fwd(zjs, zis, 1e-8, use_cosine, 1.0 / temperature)
+        cols = torch.empty(W * 2 * B, local_op.shape[1], dtype=local_op.dtype, device=local_op.device)
+        dist.all_gather_into_tensor(cols, local_op, group=group)
+        rep = cols[r * 2 * B:(r + 1) * 2 * B]
+        share, lse, _pos = kern.ntxent_fwd(rep, cols, C, r * 2 * B, 1.0 / temperature, r * 2 * B + B, use_cosine)
+        col_lse = torch.empty(W * 2 * B, dtype=lse.dtype, device=lse.device)
+        dist.all_gather_into_tensor(col_lse, lse, group=group)
+        ctx.save_for_backward(local_n, inv, cols, lse, col_lse)
+        ctx.meta = (B, C, r, temperature, use_cosine, kern)
         return share[0]
 
     @staticmethod
     def backward(ctx, g_loss):
-        local_n, inv, local_r, cols, lse, col_lse = ctx.saved_tensors
-        B, Bg, r, temperature, use_cosine, kern = ctx.meta
-        g = kern.ntxent_bwd(local_r, cols, r * B, 1.0 / temperature, lse, col_lse, Bg + r * B, unit_rows=use_cosine) * g_loss
+        local_n, inv, cols, lse, col_lse = ctx.saved_tensors
+        B, C, r, temperature, use_cosine, kern = ctx.meta
+        rep = cols[r * 2 * B:(r + 1) * 2 * B]
+        g = kern.ntxent_bwd(rep, cols, C, r * 2 * B, 1.0 / temperature, lse, col_lse, r * 2 * B + B, use_cosine)
         if use_cosine:
-            g = kern.l2_normalize_bwd(g.contiguous(), local_n, inv, 1e-8)
+            g = kern.l2_normalize_bwd(g, local_n, inv, 1e-8, gscale=g_loss.contiguous())
+        else:
+            g = g * g_loss
         return g[B:], g[:B], None, None, None, None
 
 
@@ -90,6 +104,17 @@ def global_ntxent(zis, zjs, temperature, use_cosine_similarity=True, group=None,
     return _GlobalNTXentFunction.apply(zis, zjs, float(temperature), bool(use_cosine_similarity), group, kern or CudaKernels())
 
 
+def _bucket_of(name, num_layer):
+    """Readiness order of the gradients in the backward pass: head first, then encoder layers from the last to the first, the
+    node-embedding tables with layer 0."""
+    parts = name.split(".")
+    if parts[0] in ("gnns", "batch_norms") and len(parts) > 1 and parts[1].isdigit():
+        return 1 + (num_layer - 1 - int(parts[1]))
+    if parts[0].startswith("x_embedding"):
+        return num_layer
+    return 0
+
+
 class DataParallelStep:
     """The loop body of molclr.py:109-127 for one rank of a data-parallel job.
 
@@ -98,10 +123,16 @@ class DataParallelStep:
         stepper.allreduce_gradients(); optimizer.step()
 
     Construction broadcasts rank 0's parameters and buffers so that all replicas start identical.
+
+    Gradient exchange: the parameters are grouped into buckets by the order in which the backward pass finishes them (head,
+    layer L-1, ..., layer 0 + embeddings); each bucket is one contiguous slice of a flat fp32 buffer.  With ``overlap`` (default)
+    a post-accumulate hook counts the finished gradients of a bucket and, when the last one lands, copies them into the slice
+    (one fused copy) and launches that slice's all-reduce asynchronously -- it runs on NCCL's stream underneath the rest of the
+    backward pass.  ``allreduce_gradients()`` then only waits (and handles buckets that did not complete).
     """
 
     def __init__(self, model, batch_size, temperature, use_cosine_similarity, global_negatives=True, group=None, kern=None,
-                 local_criterion=None):
+                 local_criterion=None, overlap=True):
         if not dist.is_initialized():
             raise RuntimeError("DataParallelStep: torch.distributed is not initialised")
         self.model, self.batch_size, self.temperature = model, batch_size, float(temperature)
@@ -112,17 +143,67 @@ class DataParallelStep:
         if not self.global_negatives and self._criterion is None:
             from .nt_xent import NTXentLoss
             self._criterion = NTXentLoss(None, batch_size, temperature, use_cosine_similarity)
-        self._flat, self._views = None, None
         with torch.no_grad():
             for t in list(model.parameters()) + list(model.buffers()):
                 dist.broadcast(t, src=0, group=group)
+        # ---- buckets over a flat buffer
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        L = getattr(model, "num_layer", 0)
+        order = sorted(range(len(named)), key=lambda i: (_bucket_of(named[i][0], L), i))
+        self._params = [named[i][1] for i in order]
+        bucket_ids = [_bucket_of(named[i][0], L) for i in order]
+        total = sum(p.numel() for p in self._params)
+        self._flat = torch.zeros(total, dtype=self._params[0].dtype, device=self._params[0].device)
+        self._views, self._buckets, off = [], [], 0          # bucket: dict(lo, hi, idx=[param indices])
+        for i, (p, b) in enumerate(zip(self._params, bucket_ids)):
+            self._views.append(self._flat[off:off + p.numel()].view_as(p))
+            if not self._buckets or self._buckets[-1]["id"] != b:
+                self._buckets.append({"id": b, "lo": off, "hi": off, "idx": []})
+            self._buckets[-1]["idx"].append(i)
+            off += p.numel()
+            self._buckets[-1]["hi"] = off
+        self._bucket_of_param = {}
+        for bi, bk in enumerate(self._buckets):
+            for i in bk["idx"]:
+                self._bucket_of_param[i] = bi
+        self._ready = [0] * len(self._buckets)
+        self._work = [None] * len(self._buckets)
+        self.overlap = bool(overlap)
+        if self.overlap:
+            for i, p in enumerate(self._params):
+                p.register_post_accumulate_grad_hook(self._make_hook(i))
 
     # gradients are summed (global negatives) or averaged (local negatives) over ranks -- see the module docstring
     @property
     def grad_scale(self):
         return 1.0 if self.global_negatives else 1.0 / self.world
 
+    def _make_hook(self, i):
+        def hook(_param):
+            bi = self._bucket_of_param[i]
+            self._ready[bi] += 1
+            if self._ready[bi] == len(self._buckets[bi]["idx"]):
+                self._flush(bi, async_op=True)
+        return hook
+
+    def _flush(self, bi, async_op):
+        bk = self._buckets[bi]
+        src, dst = [], []
+        for i in bk["idx"]:
+            p, v = self._params[i], self._views[i]
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                src.append(p.grad); dst.append(v)
+        if src:
+            torch._foreach_copy_(dst, src)
+        for i in bk["idx"]:
+            self._params[i].grad = self._views[i]
+        self._work[bi] = dist.all_reduce(self._flat[bk["lo"]:bk["hi"]], op=dist.ReduceOp.SUM, group=self.group, async_op=async_op) or True
+
     def loss(self, xis, xjs):
+        self._ready = [0] * len(self._buckets)
+        self._work = [None] * len(self._buckets)
         _ris, zis = self.model(xis)                         # molclr.py:57
         _rjs, zjs = self.model(xjs)                         # molclr.py:60
         zis = self.kern.normalize(zis, dim=1)               # molclr.py:63-64
@@ -141,23 +222,15 @@ class DataParallelStep:
         return t * self.grad_scale
 
     def allreduce_gradients(self):
-        """One all-reduce of a flat fp32 buffer holding every parameter gradient; ``p.grad`` then aliases it."""
-        params = [p for p in self.model.parameters() if p.requires_grad]
-        if self._flat is None or self._flat.device != params[0].device:
-            total = sum(p.numel() for p in params)
-            self._flat = torch.zeros(total, dtype=params[0].dtype, device=params[0].device)
-            self._views, off = [], 0
-            for p in params:
-                self._views.append(self._flat[off:off + p.numel()].view_as(p))
-                off += p.numel()
-        have = [(v, p.grad) for v, p in zip(self._views, params) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
-        if have:
-            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
-        for v, p in zip(self._views, params):
-            if p.grad is None:
-                v.zero_()
-        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group)
+        """Completes the gradient exchange: buckets whose all-reduce was launched from the backward hooks are waited for, the others
+        are reduced now; afterwards ``p.grad`` of every parameter aliases its slice of the flat buffer."""
+        for bi in range(len(self._buckets)):
+            if self._work[bi] is None:
+                self._flush(bi, async_op=False)
+        for w in self._work:
+            if w is not None and w is not True:
+                w.wait()
         if self.grad_scale != 1.0:
             self._flat.mul_(self.grad_scale)
-        for v, p in zip(self._views, params):
-            p.grad = v
+        self._ready = [0] * len(self._buckets)
+        self._work = [None] * len(self._buckets)

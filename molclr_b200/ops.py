@@ -400,16 +400,45 @@ def l2_normalize_bwd(gy, y, inv, eps, gscale=None):
     return gz
 
 
-def ntxent_rows_fwd(zA, zB, eps, normalise):
-    """rep = cat([zA, zB]) with rows optionally L2-normalised: returns (y or None, y_r tf32-rounded, inv_norm or None)."""
+def ntxent_rows_fwd(zA, zB, eps, normalise, want_r=True, want16=False):
+    """rep = cat([zA, zB]) with rows optionally L2-normalised: returns (y or None, y_r tf32-rounded or None, inv_norm or None[, y16])."""
     RA, Cc = zA.shape
     RB = zB.shape[0]
     y = _empty(RA + RB, Cc, device=zA.device) if normalise else None
-    y_r = _empty(RA + RB, Cc, device=zA.device)
+    y_r = _empty(RA + RB, Cc, device=zA.device) if want_r else None
     inv = _empty(RA + RB, device=zA.device) if normalise else None
-    check(_lib.load().molclr_ntxent_rows_fwd(ptr(zA), ptr(zB), RA, RB, Cc, eps, int(bool(normalise)), ptr(y), ptr(y_r), ptr(inv), stream()),
-          "ntxent_rows_fwd")
-    return y, y_r, inv
+    ld16 = (Cc + 7) // 8 * 8
+    y16 = torch.empty(RA + RB, ld16, dtype=torch.float16, device=zA.device) if want16 else None
+    check(_lib.load().molclr_ntxent_rows_fwd(ptr(zA), ptr(zB), RA, RB, Cc, eps, int(bool(normalise)), ptr(y), ptr(y_r), ptr(inv),
+                                             ptr(y16, torch.float16), ld16, stream()), "ntxent_rows_fwd")
+    return (y, y_r, inv, y16) if want16 else (y, y_r, inv)
+
+
+def ntxent_h_supported(C_, inv_temperature):
+    return bool(_lib.load().molclr_ntxent_h_supported(int(C_), float(inv_temperature)))
+
+
+def ntxent_fwd_h(rep16, cols16, C_, row_offset, row_offset2, inv_temperature):
+    """ntxent_fwd on fp16 rows (rep16 may be a row slice of cols16).  Returns (loss[1], row_lse[R], row_pos[R])."""
+    lib = _lib.load()
+    R, Rc, ld16 = rep16.shape[0], cols16.shape[0], cols16.stride(0)
+    nbytes = lib.molclr_ntxent_workspace_bytes(R, Rc, C_)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=cols16.device)
+    row_lse, row_pos, loss = _empty(R, device=cols16.device), _empty(R, device=cols16.device), _empty(1, device=cols16.device)
+    check(lib.molclr_ntxent_fwd_h(rep16.data_ptr(), cols16.data_ptr(), ld16, R, Rc, C_, row_offset, row_offset2, inv_temperature, ptr(row_lse),
+                                  ptr(row_pos), ptr(loss), ptr(ws, torch.uint8), nbytes, stream()), "ntxent_fwd_h")
+    return loss, row_lse, row_pos
+
+
+def ntxent_bwd_h(rep16, cols16, C_, row_offset, row_offset2, inv_temperature, row_lse, col_lse):
+    lib = _lib.load()
+    R, Rc, ld16 = rep16.shape[0], cols16.shape[0], cols16.stride(0)
+    nbytes = lib.molclr_ntxent_workspace_bytes(R, Rc, C_)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=cols16.device)
+    g = _empty(R, C_, device=cols16.device)
+    check(lib.molclr_ntxent_bwd_h(rep16.data_ptr(), cols16.data_ptr(), ld16, R, Rc, C_, row_offset, row_offset2, inv_temperature, ptr(row_lse),
+                                  ptr(col_lse), 1.0 / Rc, ptr(g), ptr(ws, torch.uint8), nbytes, stream()), "ntxent_bwd_h")
+    return g
 
 
 def ntxent_fwd(rep, cols, row_offset, inv_temperature, row_offset2=None, unit_rows=False):

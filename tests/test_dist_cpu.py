@@ -25,32 +25,34 @@ class TorchKernels:
         return torch.nn.functional.normalize(z, dim=dim, eps=eps)
 
     @staticmethod
-    def l2_normalize_fwd(z, eps):
-        inv = 1.0 / z.norm(dim=1).clamp_min(eps)
-        return z * inv[:, None], inv
+    def rows_fwd(zjs, zis, eps, normalise, inv_temperature):
+        rep = torch.cat([zjs, zis])
+        if not normalise:
+            return None, rep.clone(), None
+        inv = 1.0 / rep.norm(dim=1).clamp_min(eps)
+        y = rep * inv[:, None]
+        return y, y.clone(), inv
 
     @staticmethod
-    def l2_normalize_bwd(gy, y, inv, eps):
+    def l2_normalize_bwd(gy, y, inv, eps, gscale=None):
+        if gscale is not None:
+            gy = gy * gscale
         d = (gy * y).sum(dim=1, keepdim=True)
         d = torch.where((inv >= 1.0 / eps)[:, None], torch.zeros_like(d), d)
         return (gy - y * d) * inv[:, None]
 
     @staticmethod
-    def round_tf32(x):
-        return x.clone()
-
-    @staticmethod
-    def _logits(rep, cols, row_offset, inv_t, row_offset2=None):
+    def _logits(rep, cols, row_offset, inv_t, row_offset2):
         R, Rc = rep.shape[0], cols.shape[0]
         lg = (rep.double() @ cols.double().T) * inv_t
-        row_offset2 = row_offset + R // 2 if row_offset2 is None else row_offset2
-        rows = torch.cat([torch.arange(R // 2) + row_offset, torch.arange(R - R // 2) + row_offset2])
+        h = R // 2
+        rows = torch.cat([torch.arange(h) + row_offset, torch.arange(R - h) + row_offset2])
         self_mask = torch.arange(Rc)[None, :] == rows[:, None]
-        pos = (rows + Rc // 2) % Rc
+        pos = torch.cat([torch.arange(h) + row_offset2, torch.arange(R - h) + row_offset])     # partner row of the other block
         return lg, self_mask, pos
 
     @classmethod
-    def ntxent_fwd(cls, rep, cols, row_offset, inv_t, row_offset2=None, unit_rows=False):
+    def ntxent_fwd(cls, rep, cols, C, row_offset, inv_t, row_offset2, unit_rows):
         lg, self_mask, pos = cls._logits(rep, cols, row_offset, inv_t, row_offset2)
         row_pos = lg[torch.arange(rep.shape[0]), pos]
         row_lse = torch.logsumexp(lg.masked_fill(self_mask, float("-inf")), dim=1)
@@ -58,7 +60,7 @@ class TorchKernels:
         return loss.to(rep.dtype), row_lse.to(rep.dtype), row_pos.to(rep.dtype)
 
     @classmethod
-    def ntxent_bwd(cls, rep, cols, row_offset, inv_t, row_lse, col_lse, row_offset2=None, unit_rows=False):
+    def ntxent_bwd(cls, rep, cols, C, row_offset, inv_t, row_lse, col_lse, row_offset2, unit_rows):
         lg, self_mask, pos = cls._logits(rep, cols, row_offset, inv_t, row_offset2)
         Rc = cols.shape[0]
         w = torch.exp(lg - row_lse.double()[:, None]) + torch.exp(lg - col_lse.double()[None, :])

@@ -35,6 +35,10 @@ def report(name, us, nbytes):
 
 
 idx = 4 * (N + 1) + 5 * E
+if os.environ.get("ONLY_TABLES"):
+    report("edge_table_grad (fp32, fixed order)", timeit(lambda k: ops.edge_table_grad_raw(plan, srcs[k % 3])), 4 * D * N + 32 * N)
+    report("embed_nodes_bwd (fp32, fixed order)", timeit(lambda k: ops.embed_nodes_bwd(plan, srcs[k % 3])), 4 * D * N + 4 * N)
+    sys.exit(0)
 if os.environ.get("ONLY_AGG"):
     report("aggregate fwd (BN+ReLU, fp32 out, tile kernel)", timeit(lambda k: ops.gine_aggregate_fwd(plan, srcs[k % 3], B1, B2, bn_coef=coef, round_out=False)),
            4 * D * N * 2 + idx)
@@ -59,6 +63,6 @@ report("aggregate bwd (plain, row kernel)", timeit(lambda k: ops.gine_aggregate_
 report("aggregate bwd (plain)", timeit(lambda k: ops.gine_aggregate_bwd(plan, srcs[k % 3])), 4 * D * N * 2 + 4 * (N + 1) + 4 * E)
 bc = torch.randn(3, D).to(dev)
 report("bn_bwd_apply", timeit(lambda k: ops.bn_bwd_apply(srcs[k % 3], bc, gy=srcs[(k + 1) % 3])), 4 * D * N * 3)
-report("edge_table_grad (split-K GEMM)", timeit(lambda k: ops.edge_table_grad_raw(plan, srcs[k % 3])), 4 * D * N + 32 * N)
-report("embed_nodes_bwd (one-hot GEMM)", timeit(lambda k: ops.embed_nodes_bwd(plan, srcs[k % 3])), 4 * D * N + 2 * 512 * N)
+report("edge_table_grad (fp32, fixed order)", timeit(lambda k: ops.edge_table_grad_raw(plan, srcs[k % 3])), 4 * D * N + 32 * N)
+report("embed_nodes_bwd (fp32, fixed order)", timeit(lambda k: ops.embed_nodes_bwd(plan, srcs[k % 3])), 4 * D * N + 4 * N)
 report("pool_fwd", timeit(lambda k: ops.pool_fwd(plan, srcs[k % 3], coef, 0)), 4 * D * (N + plan.G))
