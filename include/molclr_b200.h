@@ -264,6 +264,66 @@ typedef struct {
 } molclr_weight_desc;
 int molclr_prepare_weights(const molclr_weight_desc* descs /* host */, int n, cudaStream_t stream);
 
+/* ---- whole-pass entry points: GINet.forward / its backward as ONE call each ---------------------------------------------
+ * The kernel sequence of ginet_molclr.py:98-117 (node embedding -> L x (aggregate, MLP, BatchNorm statistics) -> pool) and of
+ * its autograd backward, issued from C instead of ~50 / ~80 calls from the host language; same kernels, same order, same results
+ * as calling the entry points above one by one.  All pointers are device pointers unless noted; the structs live on the host.
+ * Buffers: `ctx` (molclr_gin_ctx_bytes) holds what the backward reads and stays alive between the two passes; `scratch`
+ * (molclr_gin_scratch_bytes) is free after each call; `grads` is one flat fp32 buffer (molclr_gin_grad_layout). */
+#define MOLCLR_MAX_LAYERS 16
+typedef struct {                       /* one GINEConv + BatchNorm1d (ginet_molclr.py:16-27,79-81) */
+  const float* w1_hi; const float* w1_raw; const void* w1_b16;     /* mlp.0.weight [2D][D]: molclr_prepare_weights outputs */
+  const float* b1;
+  const float* w2_hi; const float* w2_raw; const void* w2_b16;     /* mlp.2.weight [D][2D] */
+  const float* b2;
+  const float* bond_type; const float* bond_dir;                   /* edge_embedding1 [5][D], edge_embedding2 [3][D] */
+  const float* gamma; const float* beta; float* running_mean; float* running_var; int64_t* num_batches_tracked;
+  float momentum, eps;
+} molclr_gin_layer;
+typedef struct {
+  int32_t num_layer, emb_dim, feat_dim;
+  const float* x_emb1; const float* x_emb2;                         /* x_embedding1 [119][D], x_embedding2 [3][D] */
+  const molclr_gin_layer* layers;                                   /* host array [num_layer] */
+  int64_t w1_ld16, w1_rows16, w2_ld16, w2_rows16;                   /* extents of the bf16 tiles (see molclr_gemm_args.B16) */
+  /* projection head (ginet_molclr.py:90-96): weight shadows hi / lo with row pitch = cols rounded up to 32 floats */
+  const float* wf_hi; const float* wf_lo; const float* bf;          /* feat_lin [F][D] */
+  const float* w0_hi; const float* w0_lo; const float* b0;          /* out_lin.0 [F][F] */
+  const float* w2_hi; const float* w2_lo; const float* b2;          /* out_lin.2 [F/2][F] */
+} molclr_gin_model;
+typedef struct {                       /* the outputs of molclr_plan_build */
+  int64_t N, E, G;
+  const int32_t* xpacked; const int32_t* node2graph; const int32_t* rowptr; const int32_t* col; const uint8_t* eattr;
+  const int32_t* rowptr_t; const int32_t* col_t; const float* cnt; const uint32_t* nbr; const uint32_t* nbr_t;
+  const int32_t* gptr; const int32_t* gperm;
+} molclr_plan_view;
+size_t molclr_gin_ctx_bytes(const molclr_gin_model* m, int64_t N, int64_t G, int comp, int pool_mode);
+size_t molclr_gin_scratch_bytes(const molclr_gin_model* m, int64_t N, int64_t G, int ordered);
+/* floats of the flat gradient buffer; offsets (host, optional) [2 + 8 L + 6] in the order x_embedding1, x_embedding2, per layer
+ * (mlp.0.weight, mlp.0.bias, mlp.2.weight, mlp.2.bias, edge_embedding1, edge_embedding2, bn.weight, bn.bias), feat_lin.weight,
+ * .bias, out_lin.0.weight, .bias, out_lin.2.weight, .bias */
+int64_t molclr_gin_grad_layout(const molclr_gin_model* m, int64_t* offsets);
+/* comp: 1 = error-compensated forward products ("tf32x3"); drop_seeds (host) [L] + drop_p: dropout (NULL / 0 = none) */
+int molclr_gin_encoder_fwd(const molclr_gin_model* m, const molclr_plan_view* plan, int comp, int training, int pool_mode,
+                           const uint32_t* drop_seeds, float drop_p, void* ctx, size_t ctx_bytes, void* scratch, size_t scratch_bytes,
+                           cudaStream_t stream);
+/* the pooled operand pair inside ctx (tf32-rounded p [G][ld] and, comp, its residual): the input of any head */
+int molclr_gin_ctx_pooled(const molclr_gin_model* m, int64_t N, int64_t G, int comp, int pool_mode, void* ctx, float** p, float** p_lo,
+                          int64_t* ld);
+int molclr_proj_head_fwd(const molclr_gin_model* m, int64_t N, int64_t G, int comp, int pool_mode, void* ctx, float* h /* [G][F] */,
+                         float* out /* [G][F/2] */, cudaStream_t stream);
+int molclr_proj_head_bwd(const molclr_gin_model* m, int64_t N, int64_t G, int comp, int pool_mode, void* ctx, const float* g_h /* optional */,
+                         const float* g_out, int ordered, float* grads, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+/* g_p [G][D] = gradient of the pooled vectors; NULL = the one molclr_proj_head_bwd left in `scratch` (same scratch buffer).
+ * on_layer_done (optional, host callback): called as (l, user) right after the kernels producing the eight gradients of layer l
+ * (l = L-1 .. 0) have been enqueued, and as (-1, user) after the node-embedding gradients: a data-parallel caller launches
+ * that slice's all-reduce there, so that it overlaps the rest of the backward pass. */
+typedef void (*molclr_layer_cb)(int layer, void* user);
+int molclr_gin_encoder_bwd(const molclr_gin_model* m, const molclr_plan_view* plan, int comp, int training, int pool_mode,
+                           const uint32_t* drop_seeds, float drop_p, void* ctx, const float* g_p, int ordered, float* grads, void* scratch,
+                           size_t scratch_bytes, molclr_layer_cb on_layer_done, void* user, cudaStream_t stream);
+/* y += x (n floats): the gradients of the two views of a step, summed by one launch */
+int molclr_add_inplace(float* y, const float* x, int64_t n, cudaStream_t stream);
+
 /* ---- small elementwise ops ---------------------------------------------------------------------- */
 /* hi = tf32(src); lo (optional) = tf32(src - hi) */
 int molclr_round_tf32(const float* src, float* hi, float* lo, int64_t n, cudaStream_t stream);

@@ -47,6 +47,29 @@ class WeightDesc(C.Structure):
     ]
 
 
+LAYER_CB = C.CFUNCTYPE(None, C.c_int, C.c_void_p)          # molclr_layer_cb
+
+
+class GinLayer(C.Structure):
+    """Mirror of ``molclr_gin_layer``."""
+    _fields_ = [("w1_hi", vp), ("w1_raw", vp), ("w1_b16", vp), ("b1", vp), ("w2_hi", vp), ("w2_raw", vp), ("w2_b16", vp), ("b2", vp),
+                ("bond_type", vp), ("bond_dir", vp), ("gamma", vp), ("beta", vp), ("running_mean", vp), ("running_var", vp),
+                ("num_batches_tracked", vp), ("momentum", f32), ("eps", f32)]
+
+
+class GinModel(C.Structure):
+    """Mirror of ``molclr_gin_model``."""
+    _fields_ = [("num_layer", C.c_int32), ("emb_dim", C.c_int32), ("feat_dim", C.c_int32), ("x_emb1", vp), ("x_emb2", vp),
+                ("layers", C.POINTER(GinLayer)), ("w1_ld16", i64), ("w1_rows16", i64), ("w2_ld16", i64), ("w2_rows16", i64),
+                ("wf_hi", vp), ("wf_lo", vp), ("bf", vp), ("w0_hi", vp), ("w0_lo", vp), ("b0", vp), ("w2_hi", vp), ("w2_lo", vp), ("b2", vp)]
+
+
+class PlanView(C.Structure):
+    """Mirror of ``molclr_plan_view``."""
+    _fields_ = [("N", i64), ("E", i64), ("G", i64), ("xpacked", vp), ("node2graph", vp), ("rowptr", vp), ("col", vp), ("eattr", vp),
+                ("rowptr_t", vp), ("col_t", vp), ("cnt", vp), ("nbr", vp), ("nbr_t", vp), ("gptr", vp), ("gperm", vp)]
+
+
 # name -> (restype, argtypes); every symbol include/molclr_b200.h declares
 SIGNATURES = {
     "molclr_abi_version": (i32, []),
@@ -89,6 +112,15 @@ SIGNATURES = {
     "molclr_gemm_workers": (i32, []),
     "molclr_gemm_tf32": (i32, [C.POINTER(GemmArgs), vp]),
     "molclr_gemm_dw": (i32, [vp, i64, vp, i64, i64, i64, i64, vp, i64, vp]),
+    "molclr_gin_ctx_bytes": (sz, [C.POINTER(GinModel), i64, i64, i32, i32]),
+    "molclr_gin_scratch_bytes": (sz, [C.POINTER(GinModel), i64, i64, i32]),
+    "molclr_gin_grad_layout": (i64, [C.POINTER(GinModel), C.POINTER(i64)]),
+    "molclr_gin_encoder_fwd": (i32, [C.POINTER(GinModel), C.POINTER(PlanView), i32, i32, i32, C.POINTER(u32), f32, vp, sz, vp, sz, vp]),
+    "molclr_gin_ctx_pooled": (i32, [C.POINTER(GinModel), i64, i64, i32, i32, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]),
+    "molclr_proj_head_fwd": (i32, [C.POINTER(GinModel), i64, i64, i32, i32, vp, vp, vp, vp]),
+    "molclr_proj_head_bwd": (i32, [C.POINTER(GinModel), i64, i64, i32, i32, vp, vp, vp, i32, vp, vp, sz, vp]),
+    "molclr_gin_encoder_bwd": (i32, [C.POINTER(GinModel), C.POINTER(PlanView), i32, i32, i32, C.POINTER(u32), f32, vp, vp, i32, vp, vp, sz, LAYER_CB, vp, vp]),
+    "molclr_add_inplace": (i32, [vp, vp, i64, vp]),
     "molclr_round_tf32": (i32, [vp, vp, vp, i64, vp]),
     "molclr_round_tf32_2d": (i32, [vp, i64, vp, vp, i64, i64, i64, vp]),
     "molclr_copy_2d": (i32, [vp, sz, vp, sz, sz, sz, vp]),

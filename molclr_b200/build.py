@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmolclr_b200.so")
-SOURCES = ["api.cu", "plan.cu", "rowwise.cu", "tables.cu", "gemm.cu", "ntxent.cu", "ntxent_fused.cu", "augment.cu"]
+SOURCES = ["api.cu", "plan.cu", "rowwise.cu", "tables.cu", "gin_step.cu", "gemm.cu", "ntxent.cu", "ntxent_fused.cu", "augment.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

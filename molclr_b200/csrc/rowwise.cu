@@ -1051,6 +1051,12 @@ __global__ void dropout_mask_kernel(int N, int D, float* __restrict__ out, const
 // ------------------------------------------------------------------------------------------------
 // Small elementwise helpers
 // ------------------------------------------------------------------------------------------------
+__global__ void add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, int64_t n4, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = i; k < n4; k += stride) st_f4(y + 4 * k, f4_add(*reinterpret_cast<const float4*>(y + 4 * k), ldg_f4(x + 4 * k)));
+  for (int64_t k = 4 * n4 + i; k < n; k += stride) y[k] += x[k];
+}
+
 __global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -1552,5 +1558,16 @@ extern "C" int molclr_ntxent_rows_fwd(const float* zA, const float* zB, int64_t 
   l2_normalize_cat_fwd_kernel<<<(int)((RA + RB + 7) / 8), 256, 0, stream>>>(zA, zB, (int)RA, (int)RB, C, eps, normalise, y, y_r, inv_norm,
                                                                           reinterpret_cast<__half*>(y16), (int)ld16);
   MOLCLR_CHECK_LAUNCH("ntxent_rows_fwd");
+  return 0;
+}
+
+extern "C" int molclr_add_inplace(float* y, const float* x, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  MOLCLR_REQUIRE(((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x)) & 15) == 0, "add_inplace: 16-byte aligned buffers");
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+  if (blocks < 1) blocks = 1;
+  add_inplace_kernel<<<(int)blocks, 256, 0, stream>>>(y, x, n / 4, n);
+  MOLCLR_CHECK_LAUNCH("add_inplace");
   return 0;
 }

@@ -62,12 +62,16 @@ __global__ void __launch_bounds__(384, 2) class_weighted_colsum_kernel(const flo
                                                                      int N, int D, int rows_per_block, float* __restrict__ partials) {
   extern __shared__ float red[];          // [RY][8][D]
   const int tx = threadIdx.x, ty = threadIdx.y, D4 = D >> 2, RY = blockDim.y;
-  const int r0 = blockIdx.x * rows_per_block, r1 = min(N, r0 + rows_per_block);
+  // row tiles of RY * kTabUnroll rows are dealt round-robin to the CTAs, so that at any time the grid reads ONE contiguous,
+  // DRAM-page-friendly window of the matrix; a CTA still adds its tiles in a fixed (increasing) order
+  const int tile_rows = RY * kTabUnroll, r1 = N;
+  (void)rows_per_block;
   float4 acc[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) acc[c] = f4_zero();
   if (tx < D4) {
-    for (int n = r0 + ty; n < r1; n += RY * kTabUnroll) {
+    for (long long t0 = (long long)blockIdx.x * tile_rows; t0 < N; t0 += (long long)gridDim.x * tile_rows) {
+      const int n = (int)t0 + ty;
       float4 gv[kTabUnroll];
 #pragma unroll
       for (int u = 0; u < kTabUnroll; ++u) {
@@ -120,9 +124,10 @@ __global__ void __launch_bounds__(512, 1) onehot_colsum_kernel(const float* __re
   const bool active = tx < cw4;
   for (int e = tid; e < kNumAtomType * CW; e += nth) tile[e] = 0.f;
   float4 ch0 = f4_zero(), ch1 = f4_zero(), ch2 = f4_zero();
-  const int chunk_lo = blockIdx.x * chunks_per_block, nchunks = (N + kOhChunk - 1) / kOhChunk;
-  const int chunk_hi = min(nchunks, chunk_lo + chunks_per_block);
-  for (int chunk = chunk_lo; chunk < chunk_hi; ++chunk) {
+  // chunks are dealt round-robin to the CTAs (one contiguous window of the matrix in flight at any time); fixed order per CTA
+  const int nchunks = (N + kOhChunk - 1) / kOhChunk;
+  (void)chunks_per_block;
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
     const int base = chunk * kOhChunk, cnt = min(kOhChunk, N - base);
     __syncthreads();                                       // previous chunk fully consumed (keys / order / spill reuse)
     if (tid < kOhChunk) keys[tid] = tid < cnt ? __ldg(key + base + tid) : 0;
@@ -240,9 +245,9 @@ extern "C" int molclr_edge_table_grad(const float* ga, int64_t ld_ga, const floa
   MOLCLR_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "edge_table_grad: workspace must be 16-byte aligned");
   const int P = table_blocks();
   const int tx = (D / 4 + 31) / 32 * 32, ry = 384 / tx < kTabRY ? 384 / tx : kTabRY;      // <= 384 threads (two CTAs per SM)
-  int rpb = (int)((N + P - 1) / P);
-  rpb = (rpb + ry - 1) / ry * ry;
-  const int used = (int)((N + rpb - 1) / rpb);
+  const int rpb = 0;
+  const long long tiles = (N + ry * kTabUnroll - 1) / (ry * kTabUnroll);
+  const int used = (int)(tiles < P ? tiles : P);
   float* partials = reinterpret_cast<float*>(workspace);
   const size_t smem = (size_t)ry * 8 * D * sizeof(float);
   static bool attr_set = false;
@@ -271,8 +276,8 @@ extern "C" int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, in
   const int CW = ((D + slices - 1) / slices + 3) / 4 * 4;               // columns per CTA (a multiple of 4, <= 384)
   const int nchunks = (int)((N + kOhChunk - 1) / kOhChunk);
   const int P = onehot_blocks();
-  const int cpb = (nchunks + P - 1) / P;
-  const int used = (nchunks + cpb - 1) / cpb;
+  const int cpb = 0;
+  const int used = nchunks < P ? nchunks : P;
   const size_t smem = ((size_t)kNumAtomType + kOhRY + 3 * kOhRY) * CW * sizeof(float) + (2 * kOhChunk + kOhRY) * sizeof(int);
   static bool attr_set = false;
   if (!attr_set) {

@@ -115,6 +115,38 @@ def _bucket_of(name, num_layer):
     return 0
 
 
+class _GradSink:
+    """Receives finished slices of the flat gradient buffer from inside ``GINet``'s pair backward and all-reduces them."""
+
+    def __init__(self, stepper):
+        self.stepper = stepper
+        self.reset()
+
+    def reset(self):
+        self.works, self.flat, self.views, self.covered = [], None, None, 0
+
+    def slice_ready(self, flat, lo, hi, name):
+        if self.stepper.overlap:
+            self.works.append(dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.stepper.group, async_op=True))
+            self.covered += hi - lo
+
+    def backward_done(self, flat, views):
+        self.flat, self.views = flat, views
+
+    def finish(self, scale):
+        if self.covered == 0:                                 # overlap off: one all-reduce of the whole buffer now
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.stepper.group)
+        elif self.covered != self.flat.numel():
+            raise RuntimeError(f"DataParallelStep: the backward pass announced {self.covered} of {self.flat.numel()} gradient elements")
+        for w in self.works:
+            w.wait()
+        if scale != 1.0:
+            self.flat.mul_(scale)
+        for p, v in zip(self.stepper.model._params(), self.views):
+            p.grad = v
+        self.reset()
+
+
 class DataParallelStep:
     """The loop body of molclr.py:109-127 for one rank of a data-parallel job.
 
@@ -169,7 +201,12 @@ class DataParallelStep:
         self._ready = [0] * len(self._buckets)
         self._work = [None] * len(self._buckets)
         self.overlap = bool(overlap)
-        if self.overlap:
+        # Models with ``forward_pair`` (GINet) run both views in one autograd node and hand finished gradient SLICES (head, layer
+        # L-1, ..., layer 0, embeddings) to a sink from inside the backward pass: the all-reduce of a slice overlaps the rest of
+        # the second view's backward.  Other models: post-accumulate hooks per parameter bucket.
+        self._pair = hasattr(model, "forward_pair")
+        self._sink = _GradSink(self) if self._pair else None
+        if self.overlap and not self._pair:
             for i, p in enumerate(self._params):
                 p.register_post_accumulate_grad_hook(self._make_hook(i))
 
@@ -204,8 +241,12 @@ class DataParallelStep:
     def loss(self, xis, xjs):
         self._ready = [0] * len(self._buckets)
         self._work = [None] * len(self._buckets)
-        _ris, zis = self.model(xis)                         # molclr.py:57
-        _rjs, zjs = self.model(xjs)                         # molclr.py:60
+        if self._pair:
+            self._sink.reset()
+            (_ris, zis), (_rjs, zjs) = self.model.forward_pair(xis, xjs, grad_sink=self._sink)      # molclr.py:57,60
+        else:
+            _ris, zis = self.model(xis)                     # molclr.py:57
+            _rjs, zjs = self.model(xjs)                     # molclr.py:60
         zis = self.kern.normalize(zis, dim=1)               # molclr.py:63-64
         zjs = self.kern.normalize(zjs, dim=1)
         if zis.shape[0] != self.batch_size:
@@ -224,6 +265,9 @@ class DataParallelStep:
     def allreduce_gradients(self):
         """Completes the gradient exchange: buckets whose all-reduce was launched from the backward hooks are waited for, the others
         are reduced now; afterwards ``p.grad`` of every parameter aliases its slice of the flat buffer."""
+        if self._pair and self._sink.flat is not None:
+            self._sink.finish(self.grad_scale)
+            return
         for bi in range(len(self._buckets)):
             if self._work[bi] is None:
                 self._flush(bi, async_op=False)

@@ -27,9 +27,13 @@ def normalize(z, dim=1, eps=1e-12):
 
 
 def pretrain_loss(model, criterion, xis, xjs):
-    """``MolCLR._step`` (molclr.py:55-67): two separate encoder passes, L2 normalisation, NT-Xent."""
-    _ris, zis = model(xis)
-    _rjs, zjs = model(xjs)
+    """``MolCLR._step`` (molclr.py:55-67): two encoder passes (view i, then view j), L2 normalisation, NT-Xent.  Models that offer
+    ``forward_pair`` run the two passes as one autograd node (same values; fewer gradient-accumulation launches)."""
+    if hasattr(model, "forward_pair"):
+        (_ris, zis), (_rjs, zjs) = model.forward_pair(xis, xjs)
+    else:
+        _ris, zis = model(xis)
+        _rjs, zjs = model(xjs)
     zis = normalize(zis, dim=1)
     zjs = normalize(zjs, dim=1)
     return criterion(zis, zjs)

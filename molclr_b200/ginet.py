@@ -18,7 +18,7 @@ and the backward mirrors it (see ``_backward``).  Nothing here falls back to PyT
 import torch
 from torch import nn
 
-from . import ops
+from . import native, ops
 from .graph import get_plan
 
 num_atom_type = 119      # including the extra mask token   (ginet_molclr.py:9)
@@ -178,6 +178,13 @@ class GINet(_EncoderBase):
         h, out = _GINetFunction.apply(self, plan, *self._params())
         return h, out
 
+    def forward_pair(self, xis, xjs, grad_sink=None):
+        """``(model(xis), model(xjs))`` -- the two encoder passes of ``MolCLR._step`` (molclr.py:57-60), in that order -- as ONE
+        autograd node (see ``_GINetPairFunction``).  Same values as two separate calls."""
+        self._check_input(xis)
+        h_i, out_i, h_j, out_j = _GINetPairFunction.apply(self, get_plan(xis), get_plan(xjs), grad_sink, *self._params())
+        return (h_i, out_i), (h_j, out_j)
+
 
 def _lo(x, comp):
     return x if comp else None
@@ -230,87 +237,21 @@ def _head_backward(m, p, saved, g_h, g_out):
 
 
 def _encoder_forward(m, plan, comp, training, pool_mode):
-    """Node embedding -> L x (aggregate, MLP, BatchNorm statistics) -> pooled graph vectors (ginet_molclr.py:103-113).
-    Returns (p, p_lo, layers): the pooled operand pair and the per-layer tensors the backward needs."""
-    L, D, H, N = m.num_layer, m.emb_dim, 2 * m.emb_dim, plan.N
-    dev = m.x_embedding1.weight.device
-    rw = m._rounded
-    h0 = ops.embed_nodes_fwd(plan, m.x_embedding1.weight.detach(), m.x_embedding2.weight.detach())
-    src, coef_prev = h0, None
-    layers = []
-    T = ops.colstat_tiles(N)
-    drops = m._dropout_seeds()                # drops[l]: dropout applied to layer l's output (ginet_molclr.py:108-111)
-    for l in range(L):
-        g, bn = m.gnns[l], m.batch_norms[l]
-        dp = drops[l - 1] if l > 0 else (0, 0.0)
-        # a and u stay UNROUNDED fp32 (one tensor each): the compensated GEMMs derive their low halves on chip
-        a = ops.gine_aggregate_fwd(plan, src, g.edge_embedding1.weight.detach(), g.edge_embedding2.weight.detach(),
-                                   bn_coef=coef_prev, relu=True, round_out=False, drop=dp)
-        # W1 / W2: tf32-rounded copies (single-pass forward, and the backward's dX GEMMs); tf32x3: the raw weights, the
-        # compensated GEMM derives the bf16 correction tiles of both operands on chip
-        (W1, _), (W2, _) = rw.get(g.mlp[0].weight), rw.get(g.mlp[2].weight)
-        B1, B2 = (rw.raw(g.mlp[0].weight), rw.raw(g.mlp[2].weight)) if comp else (W1, W2)
-        S1, S2 = (rw.b16(g.mlp[0].weight), rw.b16(g.mlp[2].weight)) if comp else (None, None)
-        u = ops.padded(N, H, dev)
-        ubits = ops.relu_bits_buffer(N, H, dev)       # [u > 0] as bits: the backward GEMM's mask (8 MB instead of 246)
-        ops.gemm(a, B1, N, H, D, compensate=comp, B16=S1, out=u, bias=g.mlp[0].bias.detach(), relu=True, relu_bits=ubits)
-        z = torch.empty(N, D, device=dev)
-        if training:
-            stats = torch.empty(T, 2, D, device=dev)
-            ops.gemm(u, B2, N, D, H, compensate=comp, B16=S2, out=z, bias=g.mlp[2].bias.detach(), colstat=stats, colstat_mode=2)
-            momentum = 0.1 if bn.momentum is None else bn.momentum
-            coef = ops.bn_fwd_finalize(stats, T, N, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
-                                       bn.num_batches_tracked, momentum, bn.eps)
-        else:
-            ops.gemm(u, B2, N, D, H, compensate=comp, B16=S2, out=z, bias=g.mlp[2].bias.detach())
-            coef = ops.bn_eval_coef(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
-        layers.append((a, u, z, coef, W1, W2, ubits))
-        src, coef_prev = z, coef
-    argmax = torch.empty(plan.G, D, dtype=torch.int32, device=dev) if pool_mode == 2 else None
-    p, p_lo = ops.pool_fwd(plan, src, coef_prev, pool_mode, relu=False, round_out=True, want_lo=True, argmax=argmax, drop=drops[L - 1]) \
-        if comp else (ops.pool_fwd(plan, src, coef_prev, pool_mode, relu=False, round_out=True, argmax=argmax, drop=drops[L - 1]), None)
-    layers.append((drops, argmax))            # trailing entry: what the backward needs besides the per-layer tensors
-    return p, p_lo, layers
+    """Node embedding -> L x (aggregate, MLP, BatchNorm statistics) -> pooled graph vectors (ginet_molclr.py:103-113): ONE native
+    call (csrc/gin_step.cu issues the kernel sequence listed in the module docstring).  Returns (p, p_lo, context): the pooled
+    operand pair and what ``_encoder_backward`` needs.  Used by every GIN-E model of the package (pre-train and fine-tune heads)."""
+    e = native.encoder_forward(m, plan, comp, training, pool_mode, with_head=hasattr(m, "out_lin"))
+    return e.p, e.p_lo, e
 
 
-def _encoder_backward(m, plan, layers, g_p, training, pool_mode):
+def _encoder_backward(m, plan, e, g_p, training, pool_mode):
     """Backward of ``_encoder_forward`` given the gradient of the pooled vectors.  Returns the gradients of
-    [x_embedding1, x_embedding2] + per layer [mlp0.w, mlp0.b, mlp2.w, mlp2.b, edge_emb1, edge_emb2, bn.w, bn.b]."""
-    L, D, H, N = m.num_layer, m.emb_dim, 2 * m.emb_dim, plan.N
-    dev = g_p.device
-    grads = [None] * (2 + 8 * L)
-    drops, argmax = layers[L]
-    # last layer: BatchNorm backward fed by the pool backward (g_y is never materialised)
-    a, u, z, coef, W1, W2, ubits = layers[L - 1]
-    bn = m.batch_norms[L - 1]
-    partials, P = ops.pool_bwd_stats(plan, g_p, z, coef, pool_mode, argmax=argmax, drop=drops[L - 1])
-    dgamma, dbeta, bcoef = ops.bn_bwd_finalize(partials, P, N, bn.weight.detach(), coef, training)
-    g_z, db2 = ops.bn_bwd_apply(z, bcoef, gp=g_p, plan=plan, pool_mode=pool_mode, argmax=argmax, drop=drops[L - 1])
-    T = ops.colstat_tiles(N)
-    for l in range(L - 1, -1, -1):
-        a, u, z, coef, W1, W2, ubits = layers[l]
-        base = 2 + 8 * l
-        grads[base + 6], grads[base + 7], grads[base + 3] = dgamma, dbeta, db2
-        # g_u = (g_z W2) * [u > 0];  db1 = colsum(g_u)
-        g_u = ops.padded(N, H, dev)
-        part = torch.empty(T, H, device=dev)
-        ops.gemm(g_z, W2, N, H, D, b_mn=True, out=g_u, mask_bits=ubits, round_out=True, colstat=part, colstat_mode=1)
-        grads[base + 1] = ops.reduce_partials(part, T, H, torch.empty(H, device=dev))
-        grads[base + 2] = ops.gemm_dw(g_z, u, ordered=m.deterministic)                 # dW2 [D, H]
-        g_a = torch.empty(N, D, device=dev)
-        ops.gemm(g_u, W1, N, D, H, b_mn=True, out=g_a)
-        grads[base + 0] = ops.gemm_dw(g_u, a, ordered=m.deterministic)                 # dW1 [H, D]
-        grads[base + 4], grads[base + 5] = ops.edge_table_grad(plan, g_a)
-        if l > 0:
-            _, _, zp, coefp, _, _, _ = layers[l - 1]
-            bnp = m.batch_norms[l - 1]
-            g_y, partials, P = ops.gine_aggregate_bwd(plan, g_a, z_prev=zp, bn_coef=coefp, relu=True, drop=drops[l - 1])
-            dgamma, dbeta, bcoef = ops.bn_bwd_finalize(partials, P, N, bnp.weight.detach(), coefp, training)
-            g_z, db2 = ops.bn_bwd_apply(zp, bcoef, gy=g_y)
-        else:
-            g_h0, _, _ = ops.gine_aggregate_bwd(plan, g_a)
-            grads[0], grads[1] = ops.embed_nodes_bwd(plan, g_h0)
-    return grads
+    [x_embedding1, x_embedding2] + per layer [mlp0.w, mlp0.b, mlp2.w, mlp2.b, edge_emb1, edge_emb2, bn.w, bn.b] (views of one
+    flat buffer)."""
+    flat = native.grad_buffer(m, e)
+    native.encoder_backward(m, e, g_p, flat, m.deterministic)
+    views, _ = native.grad_views(m, e, flat, 0, 2 + 8 * m.num_layer)
+    return views
 
 
 def _check_precision(m):
@@ -320,25 +261,70 @@ def _check_precision(m):
 
 
 class _GINetFunction(torch.autograd.Function):
+    """One view: encoder + projection head, forward and backward as two native calls each."""
 
     @staticmethod
     def forward(ctx, m, plan, *params):
         comp = _check_precision(m)
-        training = m.training
-        pool_mode = ops.POOL_MODES[m.pool_name]
         m._refresh_weights(comp)
-        p, p_lo, layers = _encoder_forward(m, plan, comp, training, pool_mode)
-        h, out, head_saved = _head_forward(m, p, p_lo, m._rounded, comp)
-        ctx.m, ctx.plan, ctx.layers, ctx.p, ctx.head_saved = m, plan, layers, p, head_saved
-        ctx.training, ctx.pool_mode = training, pool_mode
+        e = native.encoder_forward(m, plan, comp, m.training, ops.POOL_MODES[m.pool_name])
+        h, out = native.proj_head_forward(m, e)
+        ctx.m, ctx.e = m, e
         return h, out
 
     @staticmethod
     def backward(ctx, g_h, g_out):
-        m, plan, layers, p = ctx.m, ctx.plan, ctx.layers, ctx.p
-        if g_out is None:
-            g_out = torch.zeros(p.shape[0], m.feat_dim // 2, device=p.device)
-        g_p, head_grads = _head_backward(m, p, ctx.head_saved, g_h, g_out)
-        grads = _encoder_backward(m, plan, layers, g_p, ctx.training, ctx.pool_mode)
-        ctx.layers = None
-        return (None, None, *grads, *head_grads)
+        m, e = ctx.m, ctx.e
+        flat = native.grad_buffer(m, e)
+        _view_backward(m, e, g_h, g_out, flat)
+        ctx.e = None
+        views, _ = native.grad_views(m, e, flat, 0, 2 + 8 * m.num_layer + 6)
+        return (None, None, *views)
+
+
+def _view_backward(m, e, g_h, g_out, flat, on_layer_done=None):
+    if g_out is None:
+        g_out = torch.zeros(e.plan.G, m.feat_dim // 2, device=e.dev)
+    native.proj_head_backward(m, e, g_h, g_out, flat, m.deterministic)
+    native.encoder_backward(m, e, None, flat, m.deterministic, on_layer_done)
+
+
+class _GINetPairFunction(torch.autograd.Function):
+    """Both views of a pre-training step (molclr.py:57-60) in one autograd node: the weight shadows are derived once, the two
+    backward passes fill two flat gradient buffers that are summed slice by slice (no per-parameter accumulation kernels), and a
+    data-parallel caller can start the all-reduce of a slice as soon as the second view's backward has produced it (``sink``)."""
+
+    @staticmethod
+    def forward(ctx, m, plan_i, plan_j, sink, *params):
+        comp = _check_precision(m)
+        m._refresh_weights(comp)
+        pool_mode = ops.POOL_MODES[m.pool_name]
+        e_i = native.encoder_forward(m, plan_i, comp, m.training, pool_mode)        # view i first: the order of the two
+        h_i, out_i = native.proj_head_forward(m, e_i)                                # BatchNorm running-statistics updates
+        e_j = native.encoder_forward(m, plan_j, comp, m.training, pool_mode)
+        h_j, out_j = native.proj_head_forward(m, e_j)
+        ctx.m, ctx.e_i, ctx.e_j, ctx.sink = m, e_i, e_j, sink
+        return h_i, out_i, h_j, out_j
+
+    @staticmethod
+    def backward(ctx, g_hi, g_oi, g_hj, g_oj):
+        m, e_i, e_j, sink = ctx.m, ctx.e_i, ctx.e_j, ctx.sink
+        flat, flat2 = native.grad_buffer(m, e_j), native.grad_buffer(m, e_i)
+        _view_backward(m, e_j, g_hj, g_oj, flat)
+        sl = native.grad_slices(m, e_i)
+
+        def merge(lo, hi, name):
+            native.add_inplace(flat[lo:hi], flat2[lo:hi])
+            if sink is not None:
+                sink.slice_ready(flat, lo, hi, name)
+        if g_oi is None:
+            g_oi = torch.zeros(e_i.plan.G, m.feat_dim // 2, device=e_i.dev)
+        native.proj_head_backward(m, e_i, g_hi, g_oi, flat2, m.deterministic)
+        merge(*sl["head"], "head")
+        native.encoder_backward(m, e_i, None, flat2, m.deterministic,
+                                lambda l: merge(*(sl["embed"] if l < 0 else sl["layer"][l]), "embed" if l < 0 else f"layer{l}"))
+        ctx.e_i = ctx.e_j = None
+        views, _ = native.grad_views(m, e_i, flat, 0, 2 + 8 * m.num_layer + 6)
+        if sink is not None:
+            sink.backward_done(flat, views)
+        return (None, None, None, None, *views)

@@ -51,11 +51,13 @@ def test_ntxent_workspace_covers_both_backward_variants(lib_path):
 
 
 def test_struct_mirrors_match_the_header_as_compiled_by_gcc(tmp_path):
-    """The ctypes mirrors of molclr_gemm_args / molclr_weight_desc have exactly the layout a C compiler gives the header's structs
+    """The ctypes mirrors of every struct of the header (GEMM arguments, weight descriptors, model / layer / plan views) have exactly the layout a C compiler gives the header's structs
     (guards against silent drift between header and binding)."""
     import subprocess
-    from molclr_b200._lib import GemmArgs, WeightDesc
-    fields = {"molclr_gemm_args": [f[0] for f in GemmArgs._fields_], "molclr_weight_desc": [f[0] for f in WeightDesc._fields_]}
+    from molclr_b200._lib import GemmArgs, WeightDesc, GinLayer, GinModel, PlanView
+    mirrors = {"molclr_gemm_args": GemmArgs, "molclr_weight_desc": WeightDesc, "molclr_gin_layer": GinLayer, "molclr_gin_model": GinModel,
+               "molclr_plan_view": PlanView}
+    fields = {st: [f[0] for f in cls._fields_] for st, cls in mirrors.items()}
     src = ['#include <stdio.h>', '#include <stddef.h>', '#include "molclr_b200.h"', 'int main(void) {']
     for st, fs in fields.items():
         src.append(f'  printf("{st} %zu\\n", sizeof({st}));')
@@ -66,7 +68,7 @@ def test_struct_mirrors_match_the_header_as_compiled_by_gcc(tmp_path):
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
     got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
-    for st, cls in (("molclr_gemm_args", GemmArgs), ("molclr_weight_desc", WeightDesc)):
+    for st, cls in mirrors.items():
         assert int(got[st]) == ctypes.sizeof(cls), st
         for f in fields[st]:
             assert int(got[f"{st}.{f}"]) == getattr(cls, f).offset, (st, f)
