@@ -298,73 +298,54 @@ def run_ours(args):
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
     h2d = sum(batch_bytes(b) for b in host[0])
 
-    # ---------------- roofline: GINE aggregation (layers >= 1: fused BN+ReLU gather), timed in situ
-    times = []
-    orig = ops.gine_aggregate_fwd
-
-    def timed_aggregate(plan, src, B1, B2, bn_coef=None, **kw):
-        if bn_coef is None:
-            return orig(plan, src, B1, B2, bn_coef=bn_coef, **kw)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        out = orig(plan, src, B1, B2, bn_coef=bn_coef, **kw)
-        b.record()
-        times.append((a, b, plan.N, plan.E, bool(kw.get("want_lo"))))
-        return out
-    # ... and the row GEMMs of the GIN MLP (the largest share of the step), same in-situ timing: useful FLOPs 2 M N K per call
-    gemm_times = []
-    orig_gemm = ops.gemm
-
-    def timed_gemm(A, B, M, N, K, **kw):
-        if M < 50000:                               # head GEMMs: not the ones that matter
-            return orig_gemm(A, B, M, N, K, **kw)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        out = orig_gemm(A, B, M, N, K, **kw)
-        b.record()
-        gemm_times.append((a, b, 2.0 * M * N * K, bool(kw.get("compensate"))))
-        return out
-    ops.gine_aggregate_fwd = timed_aggregate
-    ops.gemm = timed_gemm
-    for i in range(3 if args.model == "gin" else 0):
-        step(*resident[i % NB])
-    torch.cuda.synchronize()
-    ops.gine_aggregate_fwd = orig
-    ops.gemm = orig_gemm
+    # ---------------- roofline: GINE aggregation (layers >= 1: fused BN+ReLU gather) and the GIN MLP products, timed IN SITU:
+    # CUDA event pairs recorded by the native whole-pass calls around those launches, on the stream they are launched on
+    import ctypes as C
+    roof, roof_gemm = None, None
     D = 300
-    # algorithmic bytes per launch (DESIGN.md / SURVEY 8d): read src rows once, write the aggregate (one tensor; plus the tf32
-    # residual when the caller asks for it), CSR rowptr/col/eattr, BN coefficients and bond tables
-    def alg_bytes(N, E, lo):
-        return 4 * D * N + (2 if lo else 1) * 4 * D * N + 4 * (N + 1) + 5 * E + 4 * D * (2 + 8)
-    peak, peak_src = peaks()
-    if times:
-        agg_ms = sum(t[0].elapsed_time(t[1]) for t in times) / len(times)
-        agg_bytes = sum(alg_bytes(*t[2:]) for t in times) / len(times)
-        achieved = agg_bytes / (agg_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "gine_aggregate_fwd_tile_kernel<1, 0> (BatchNorm+ReLU-fused gather, layers >= 1)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "us_per_launch": agg_ms * 1e3,
-                "algorithmic_bytes_per_launch": agg_bytes, "launches_timed": len(times)}
-    else:
-        roof = None
-    roof_gemm = None
-    if gemm_times:
+    if args.model == "gin":
+        lib.molclr_step_timing(1)
+        n_timed = 3
+        for i in range(n_timed):
+            step(*resident[i % NB])
+        torch.cuda.synchronize()
+
+        def read(cat):
+            ms, n = C.c_double(0.0), C.c_int(0)
+            lib.molclr_step_timing_read(cat, C.byref(ms), C.byref(n))
+            return ms.value, n.value
+        (agg_ms, n_agg), (fwd_ms, n_fwd), (bwd_ms, n_bwd), (dw_ms, n_dw) = read(0), read(1), read(2), read(3)
+        lib.molclr_step_timing(0)
+        # algorithmic bytes per launch (DESIGN.md / SURVEY 8d): read the source rows once, write the aggregate once, CSR
+        # rowptr / col / packed attributes, BatchNorm coefficients and bond tables
+        nodes = [int(b.x.size(0)) for i in range(n_timed) for b in resident[i % NB]]
+        edges = [int(b.edge_index.size(1)) for i in range(n_timed) for b in resident[i % NB]]
+        alg = lambda N, E: 4 * D * N + 4 * D * N + 4 * (N + 1) + 5 * E + 4 * D * (2 + 8)
+        peak, peak_src = peaks()
+        if n_agg:
+            agg_bytes = sum(alg(N, E) for N, E in zip(nodes, edges)) / len(nodes)
+            us = agg_ms * 1e3 / n_agg
+            achieved = agg_bytes / (us * 1e-6) / 1e9
+            roof = {"bound": "hbm", "kernel": "gine_aggregate_fwd_tile_kernel<1, 0> (BatchNorm+ReLU-fused gather, layers >= 1)", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "us_per_launch": us,
+                    "algorithmic_bytes_per_launch": agg_bytes, "launches_timed": n_agg}
         try:
             tf32_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]) / 2
             tf32_src = "measured sustained bf16 cuBLAS throughput / 2 (MEASURED_PEAKS.json; TF32 runs at half the bf16 rate)"
         except Exception:
             tf32_peak, tf32_src = 1100.0, "fallback: nominal dense TF32"
-        def tfl(sel):
-            ts = [t for t in gemm_times if sel(t)]
-            return (sum(t[2] for t in ts) / (sum(t[0].elapsed_time(t[1]) for t in ts) * 1e-3) / 1e12, len(ts)) if ts else (None, 0)
-        fwd, n_fwd = tfl(lambda t: t[3])
-        bwd, n_bwd = tfl(lambda t: not t[3])
-        roof_gemm = {"bound": "tensor", "kernel": "gemm_tf32_kernel, row GEMMs of the GIN MLP (M = nodes)", "unit": "TFLOP/s", "peak": tf32_peak,
-                     "peak_source": tf32_src, "achieved": fwd if fwd is not None else bwd,
-                     "frac": (fwd if fwd is not None else bwd) / tf32_peak,
-                     "forward_compensated_useful_tflops": fwd, "forward_calls_timed": n_fwd,
-                     "backward_single_pass_tflops": bwd, "backward_calls_timed": n_bwd,
-                     "note": "useful FLOPs 2MNK per product (the compensated forward issues 2x that in tensor work); these loops are "
-                             "bound by L2<->SM traffic (operand tiles in, output tiles out), see DESIGN.md section 6"}
+        flops_per_product = 2.0 * 300 * 600 * (sum(nodes) / len(nodes))          # one [N, 300] x [300, 600] (or transposed) product
+        tfl = lambda ms, n: (flops_per_product * n / (ms * 1e-3) / 1e12) if n and ms > 0 else None
+        fwd, bwd, dwt = tfl(fwd_ms, n_fwd), tfl(bwd_ms, n_bwd), tfl(dw_ms, n_dw)
+        if fwd:
+            roof_gemm = {"bound": "tensor", "kernel": "gemm_tf32_kernel, products of the GIN MLP (M or K = nodes)", "unit": "TFLOP/s", "peak": tf32_peak,
+                         "peak_source": tf32_src, "achieved": fwd, "frac": fwd / tf32_peak,
+                         "forward_compensated_useful_tflops": fwd, "forward_frac": fwd / tf32_peak, "forward_calls_timed": n_fwd,
+                         "backward_single_pass_tflops": bwd, "backward_frac": bwd / tf32_peak if bwd else None, "backward_calls_timed": n_bwd,
+                         "weight_gradient_tflops": dwt, "weight_gradient_frac": dwt / tf32_peak if dwt else None, "weight_gradient_calls_timed": n_dw,
+                         "us_per_call": {"forward": fwd_ms * 1e3 / max(n_fwd, 1), "backward": bwd_ms * 1e3 / max(n_bwd, 1), "weight_gradient": dw_ms * 1e3 / max(n_dw, 1)},
+                         "note": "useful FLOPs 2MNK per product (the compensated forward issues 2x that in tensor work: one TF32 pass + two "
+                                 "bf16 correction passes); see DESIGN.md section 6"}
     ncu_traffic = os.path.join(ROOT, "profiles", "aggregate_traffic.json")
     if roof is not None and os.path.exists(ncu_traffic):
         try:      # DRAM bytes per launch of this kernel from an `ncu --set full` capture of the same command (cannot be measured outside a profiler)

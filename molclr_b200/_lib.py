@@ -121,6 +121,8 @@ SIGNATURES = {
     "molclr_proj_head_bwd": (i32, [C.POINTER(GinModel), i64, i64, i32, i32, vp, vp, vp, i32, vp, vp, sz, vp]),
     "molclr_gin_encoder_bwd": (i32, [C.POINTER(GinModel), C.POINTER(PlanView), i32, i32, i32, C.POINTER(u32), f32, vp, vp, i32, vp, vp, sz, LAYER_CB, vp, vp]),
     "molclr_add_inplace": (i32, [vp, vp, i64, vp]),
+    "molclr_step_timing": (i32, [i32]),
+    "molclr_step_timing_read": (i32, [i32, C.POINTER(C.c_double), C.POINTER(i32)]),
     "molclr_round_tf32": (i32, [vp, vp, vp, i64, vp]),
     "molclr_round_tf32_2d": (i32, [vp, i64, vp, vp, i64, i64, i64, vp]),
     "molclr_copy_2d": (i32, [vp, sz, vp, sz, sz, sz, vp]),
@@ -165,7 +167,9 @@ def check(rc, what):
 
 
 def stream():
-    return torch.cuda.current_stream().cuda_stream
+    """Raw cudaStream_t of the current stream of the current device (the fast private accessor: torch.cuda.current_stream() costs
+    ~15 us per call, and every launch asks)."""
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 def ptr(t, dtype=torch.float32):

@@ -4,6 +4,7 @@
 // directly: it sequences the entry points of this library on the caller's stream, carving every intermediate tensor out of
 // caller-owned buffers (`ctx`: what the backward needs; `scratch`: temporaries).
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 #include "molclr_b200.h"
@@ -66,6 +67,24 @@ static bool gin_ctx_carve(const GinDims& d, Carve& c, GinCtx* x) {
 }
 
 static void gemm_args_init(molclr_gemm_args& a) { memset(&a, 0, sizeof(a)); a.split_k = 1; }
+
+// Optional in-situ timing (bench.py's roofline lines): CUDA event pairs around selected launches of the whole-pass calls, on the
+// stream they are launched on.  Off by default; costs nothing then.
+enum : int { TIME_AGG_FWD = 0, TIME_GEMM_FWD = 1, TIME_GEMM_BWD = 2, TIME_GEMM_DW = 3, TIME_CATS = 4 };
+struct StepTimer {
+  bool on = false;
+  std::vector<cudaEvent_t> ev[TIME_CATS];
+};
+static StepTimer g_timer;
+struct TimeScope {
+  int cat; cudaStream_t st; bool on;
+  TimeScope(int c, cudaStream_t s, bool enable = true) : cat(c), st(s), on(g_timer.on && enable) {
+    if (on) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); g_timer.ev[cat].push_back(e); }
+  }
+  ~TimeScope() {
+    if (on) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); g_timer.ev[cat].push_back(e); }
+  }
+};
 
 }  // namespace molclr
 
@@ -147,20 +166,23 @@ extern "C" int molclr_gin_encoder_fwd(const molclr_gin_model* m, const molclr_pl
   for (int l = 0; l < L; ++l) {
     const molclr_gin_layer& ly = m->layers[l];
     // a_l = sum_j f(z_{l-1})[j] + bond table, self loop last (:29-44); f = BatchNorm + ReLU (+ dropout) of layer l-1, fused
-    GIN_CALL(molclr_gine_aggregate_fwd(src, coef_prev, 1, pl->rowptr, pl->col, pl->eattr, pl->nbr, ly.bond_type, ly.bond_dir, N, D, x.a[l], d.ldD, 0,
-                                       nullptr, l > 0 ? seed(l - 1) : 0u, l > 0 ? dp : 0.f, stream));
+    {
+      TimeScope ts(TIME_AGG_FWD, stream, l > 0);
+      GIN_CALL(molclr_gine_aggregate_fwd(src, coef_prev, 1, pl->rowptr, pl->col, pl->eattr, pl->nbr, ly.bond_type, ly.bond_dir, N, D, x.a[l], d.ldD, 0,
+                                         nullptr, l > 0 ? seed(l - 1) : 0u, l > 0 ? dp : 0.f, stream));
+    }
     molclr_gemm_args g;
     gemm_args_init(g);                                                                                // u = relu(a W1^T + b1)  (:19-23,46-47)
     g.A = x.a[l]; g.lda = d.ldD; g.B = comp ? ly.w1_raw : ly.w1_hi; g.ldb = d.ldD; g.M = N; g.N = H; g.K = D;
     g.compensate = comp; g.B16 = comp ? ly.w1_b16 : nullptr; g.ld16 = m->w1_ld16; g.rows16 = m->w1_rows16;
     g.out = x.u[l]; g.ldo = d.ldH; g.bias = ly.b1; g.relu = 1; g.relu_bits = x.ubits[l]; g.ld_bits = d.words;
-    GIN_CALL(molclr_gemm_tf32(&g, stream));
+    { TimeScope ts(TIME_GEMM_FWD, stream); GIN_CALL(molclr_gemm_tf32(&g, stream)); }
     gemm_args_init(g);                                                                                // z = u W2^T + b2 (+ BatchNorm tile statistics)
     g.A = x.u[l]; g.lda = d.ldH; g.B = comp ? ly.w2_raw : ly.w2_hi; g.ldb = d.ldH; g.M = N; g.N = D; g.K = H;
     g.compensate = comp; g.B16 = comp ? ly.w2_b16 : nullptr; g.ld16 = m->w2_ld16; g.rows16 = m->w2_rows16;
     g.out = x.z[l]; g.ldo = D; g.bias = ly.b2;
     if (training) { g.colstat = stats; g.colstat_mode = 2; }
-    GIN_CALL(molclr_gemm_tf32(&g, stream));
+    { TimeScope ts(TIME_GEMM_FWD, stream); GIN_CALL(molclr_gemm_tf32(&g, stream)); }
     if (training)                                                                                     // :107
       GIN_CALL(molclr_bn_fwd_finalize(stats, d.T, molclr_gemm_colstat_tile_rows(), N, D, ly.gamma, ly.beta, ly.running_mean, ly.running_var,
                                       ly.num_batches_tracked, ly.momentum, ly.eps, x.coef[l], bn_ws, stream));
@@ -316,14 +338,14 @@ extern "C" int molclr_gin_encoder_bwd(const molclr_gin_model* m, const molclr_pl
     gemm_args_init(g);                                // g_u = (g_z W2) * [u > 0];  db1 = colsum(g_u)
     g.A = s.g_z; g.lda = d.ldD; g.B = ly.w2_hi; g.ldb = d.ldH; g.b_mn = 1; g.M = N; g.N = H; g.K = D;
     g.out = s.g_u; g.ldo = d.ldH; g.mask_bits = x.ubits[l]; g.ld_bits = d.words; g.round_out = 1; g.colstat = s.part; g.colstat_mode = 1;
-    GIN_CALL(molclr_gemm_tf32(&g, stream));
+    { TimeScope ts(TIME_GEMM_BWD, stream); GIN_CALL(molclr_gemm_tf32(&g, stream)); }
     GIN_CALL(molclr_reduce_partials(s.part, d.T, H, 1.f, 0, G_(l, 1), stream));
-    GIN_CALL(dw(s.g_z, d.ldD, x.u[l], d.ldH, N, D, H, G_(l, 2), ordered, s.dw_ws, s.dw_bytes, stream));     // dW2 [D][H]
+    { TimeScope ts(TIME_GEMM_DW, stream); GIN_CALL(dw(s.g_z, d.ldD, x.u[l], d.ldH, N, D, H, G_(l, 2), ordered, s.dw_ws, s.dw_bytes, stream)); }   // dW2 [D][H]
     gemm_args_init(g);                                // g_a = g_u W1
     g.A = s.g_u; g.lda = d.ldH; g.B = ly.w1_hi; g.ldb = d.ldD; g.b_mn = 1; g.M = N; g.N = D; g.K = H;
     g.out = s.g_a; g.ldo = D;
-    GIN_CALL(molclr_gemm_tf32(&g, stream));
-    GIN_CALL(dw(s.g_u, d.ldH, x.a[l], d.ldD, N, H, D, G_(l, 0), ordered, s.dw_ws, s.dw_bytes, stream));     // dW1 [H][D]
+    { TimeScope ts(TIME_GEMM_BWD, stream); GIN_CALL(molclr_gemm_tf32(&g, stream)); }
+    { TimeScope ts(TIME_GEMM_DW, stream); GIN_CALL(dw(s.g_u, d.ldH, x.a[l], d.ldD, N, H, D, G_(l, 0), ordered, s.dw_ws, s.dw_bytes, stream)); }   // dW1 [H][D]
     GIN_CALL(molclr_edge_table_grad(s.g_a, D, pl->cnt, N, D, G_(l, 4), s.tab_ws, stream));                  // [8][D]: edge_embedding1 | edge_embedding2
     if (on_layer_done) on_layer_done(l, user);        // all eight gradients of layer l are enqueued (data-parallel: launch their all-reduce now)
     if (l > 0) {
@@ -338,5 +360,35 @@ extern "C" int molclr_gin_encoder_bwd(const molclr_gin_model* m, const molclr_pl
       if (on_layer_done) on_layer_done(-1, user);     // the node-embedding tables
     }
   }
+  return 0;
+}
+
+// In-situ timing of the whole-pass calls (measurement aid of bench.py): molclr_step_timing(1) starts collecting CUDA event pairs around
+// the BatchNorm-fused aggregation launches (category 0), the forward MLP products (1), the backward row products (2) and the
+// weight-gradient products (3); molclr_step_timing(0) stops.  molclr_step_timing_read synchronises the events of a category and
+// returns their summed milliseconds and the number of timed launches.
+extern "C" int molclr_step_timing(int enable) {
+  for (int c = 0; c < TIME_CATS; ++c) {
+    for (cudaEvent_t e : g_timer.ev[c]) cudaEventDestroy(e);
+    g_timer.ev[c].clear();
+  }
+  g_timer.on = enable != 0;
+  return 0;
+}
+
+extern "C" int molclr_step_timing_read(int category, double* total_ms, int* count) {
+  MOLCLR_REQUIRE(category >= 0 && category < TIME_CATS && total_ms && count, "step_timing_read: bad arguments");
+  const std::vector<cudaEvent_t>& ev = g_timer.ev[category];
+  double tot = 0.0;
+  int n = 0;
+  for (size_t i = 0; i + 1 < ev.size(); i += 2) {
+    cudaError_t e = cudaEventSynchronize(ev[i + 1]);
+    if (e != cudaSuccess) return cuda_fail(e, "step_timing_read");
+    float ms = 0.f;
+    e = cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+    if (e != cudaSuccess) return cuda_fail(e, "step_timing_read");
+    tot += ms; ++n;
+  }
+  *total_ms = tot; *count = n;
   return 0;
 }

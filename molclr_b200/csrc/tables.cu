@@ -60,42 +60,46 @@ constexpr int kTabUnroll = 6;
 // lane ty takes rows r0 + ty, r0 + ty + RY, ... in increasing order (registers); the RY lane sums are then added in lane order.
 __global__ void __launch_bounds__(384, 2) class_weighted_colsum_kernel(const float* __restrict__ g, long long ld_g, const float* __restrict__ w,
                                                                      int N, int D, int rows_per_block, float* __restrict__ partials) {
-  extern __shared__ float red[];          // [RY][8][D]
+  extern __shared__ float red[];          // [RY][8][D], then the weight rows of the current tile: [RY * U][8]
   const int tx = threadIdx.x, ty = threadIdx.y, D4 = D >> 2, RY = blockDim.y;
+  const int tid = ty * blockDim.x + tx, nth = blockDim.x * blockDim.y;
   // row tiles of RY * kTabUnroll rows are dealt round-robin to the CTAs, so that at any time the grid reads ONE contiguous,
   // DRAM-page-friendly window of the matrix; a CTA still adds its tiles in a fixed (increasing) order
-  const int tile_rows = RY * kTabUnroll, r1 = N;
+  const int tile_rows = RY * kTabUnroll;
   (void)rows_per_block;
+  float4* wt = reinterpret_cast<float4*>(red + (size_t)RY * 8 * D);       // [tile_rows][2] float4
   float4 acc[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) acc[c] = f4_zero();
-  if (tx < D4) {
-    for (long long t0 = (long long)blockIdx.x * tile_rows; t0 < N; t0 += (long long)gridDim.x * tile_rows) {
-      const int n = (int)t0 + ty;
-      float4 gv[kTabUnroll];
+  for (long long t0 = (long long)blockIdx.x * tile_rows; t0 < N; t0 += (long long)gridDim.x * tile_rows) {
+    const int n = (int)t0 + ty;
+    // the tile's feature rows go to registers first (their DRAM latency then overlaps the staging of the weight rows) ...
+    float4 gv[kTabUnroll];
 #pragma unroll
-      for (int u = 0; u < kTabUnroll; ++u) {
-        const int row = n + u * RY;
-        gv[u] = row < r1 ? ldg_f4(g + (size_t)row * ld_g + 4 * tx) : f4_zero();
-      }
+    for (int u = 0; u < kTabUnroll; ++u) {
+      const int row = n + u * RY;
+      gv[u] = (row < N && tx < D4) ? ldg_f4(g + (size_t)row * ld_g + 4 * tx) : f4_zero();
+    }
+    // ... the [tile_rows][8] weights to shared memory: one coalesced load per tile instead of a dependent L2 round trip per row
+    __syncthreads();
+    if (tid < 2 * tile_rows) wt[tid] = ((int)t0 + (tid >> 1) < N) ? ldg_f4(w + ((size_t)t0 + (tid >> 1)) * 8 + 4 * (tid & 1)) : f4_zero();
+    __syncthreads();
 #pragma unroll
-      for (int u = 0; u < kTabUnroll; ++u) {
-        const int row = n + u * RY;
-        if (row >= r1) break;
-        const float4 w0 = ldg_f4(w + (size_t)row * 8), w1 = ldg_f4(w + (size_t)row * 8 + 4);     // one address per warp: broadcast
-        const float wc[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    for (int u = 0; u < kTabUnroll; ++u) {
+      const float4 w0 = wt[2 * (ty + u * RY)], w1 = wt[2 * (ty + u * RY) + 1];              // broadcast
+      const float wc[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          acc[c].x = fmaf(wc[c], gv[u].x, acc[c].x); acc[c].y = fmaf(wc[c], gv[u].y, acc[c].y);
-          acc[c].z = fmaf(wc[c], gv[u].z, acc[c].z); acc[c].w = fmaf(wc[c], gv[u].w, acc[c].w);
-        }
+      for (int c = 0; c < 8; ++c) {
+        acc[c].x = fmaf(wc[c], gv[u].x, acc[c].x); acc[c].y = fmaf(wc[c], gv[u].y, acc[c].y);
+        acc[c].z = fmaf(wc[c], gv[u].z, acc[c].z); acc[c].w = fmaf(wc[c], gv[u].w, acc[c].w);
       }
     }
+  }
+  if (tx < D4) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) st_f4(red + ((size_t)ty * 8 + c) * D + 4 * tx, acc[c]);
   }
   __syncthreads();
-  const int tid = ty * blockDim.x + tx, nth = blockDim.x * blockDim.y;
   for (int e = tid; e < 8 * D; e += nth) {
     float s = red[e];
     for (int l = 1; l < RY; ++l) s += red[(size_t)l * 8 * D + e];
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(384, 2) class_weighted_colsum_kernel(const flo
 // run to the CTA's [119][CW] shared-memory tile -- one read-modify-write per run instead of per node.  Only the first run of a
 // lane can share its class with another lane (the order is sorted): it goes to a per-lane spill row that is added in lane order.
 // Everything has a fixed order: bit-reproducible.
-constexpr int kOhChunk = 128, kOhRY = 4, kOhUnroll = 8, kOhMaxCW = 384;
+constexpr int kOhChunk = 128, kOhRY = 4, kOhUnroll = 16, kOhMaxCW = 384;
 __global__ void __launch_bounds__(512, 1) onehot_colsum_kernel(const float* __restrict__ g, long long ld_g, const int32_t* __restrict__ key,
                                                              int N, int D, int CW, int chunks_per_block, float* __restrict__ partials) {
   extern __shared__ float sm[];
@@ -127,12 +131,17 @@ __global__ void __launch_bounds__(512, 1) onehot_colsum_kernel(const float* __re
   // chunks are dealt round-robin to the CTAs (one contiguous window of the matrix in flight at any time); fixed order per CTA
   const int nchunks = (N + kOhChunk - 1) / kOhChunk;
   (void)chunks_per_block;
+  int next_key = (tid < kOhChunk && (int)blockIdx.x * kOhChunk + tid < N) ? __ldg(key + (size_t)blockIdx.x * kOhChunk + tid) : 0;
   for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
     const int base = chunk * kOhChunk, cnt = min(kOhChunk, N - base);
     __syncthreads();                                       // previous chunk fully consumed (keys / order / spill reuse)
-    if (tid < kOhChunk) keys[tid] = tid < cnt ? __ldg(key + base + tid) : 0;
+    if (tid < kOhChunk) keys[tid] = next_key;
     if (tid < kOhRY) spill_cls[tid] = -1;
     __syncthreads();
+    {                                                      // the keys of this CTA's NEXT chunk: in flight while this one is summed
+      const long long nb = ((long long)chunk + gridDim.x) * kOhChunk + tid;
+      next_key = (tid < kOhChunk && nb < N) ? __ldg(key + nb) : 0;
+    }
     if (tid < cnt) {                                       // stable rank of row tid in atom-type order
       const int a = keys[tid] & 0xff;
       int rank = 0;
@@ -249,10 +258,10 @@ extern "C" int molclr_edge_table_grad(const float* ga, int64_t ld_ga, const floa
   const long long tiles = (N + ry * kTabUnroll - 1) / (ry * kTabUnroll);
   const int used = (int)(tiles < P ? tiles : P);
   float* partials = reinterpret_cast<float*>(workspace);
-  const size_t smem = (size_t)ry * 8 * D * sizeof(float);
+  const size_t smem = (size_t)ry * 8 * D * sizeof(float) + (size_t)ry * kTabUnroll * 8 * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(class_weighted_colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabRY * 8 * 512 * (int)sizeof(float));
+    cudaError_t e = cudaFuncSetAttribute(class_weighted_colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTabRY * 8 * 512 * (int)sizeof(float) + kTabRY * kTabUnroll * 8 * (int)sizeof(float));
     if (e != cudaSuccess) return cuda_fail(e, "edge_table_grad: cudaFuncSetAttribute");
     attr_set = true;
   }

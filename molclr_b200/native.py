@@ -22,7 +22,20 @@ def _dp(t):
 
 
 def model_struct(m, comp, with_head=True):
-    """(GinModel, keepalive): device pointers of the parameters and of the weight shadows of the LAST ``m._refresh_weights``."""
+    """(GinModel, keepalive): device pointers of the parameters and of the weight shadows of the LAST ``m._refresh_weights``.
+    Cached while the shadow buffers (``_RoundedWeights.generation``) and the BatchNorm buffers stay where they are."""
+    rw = m._rounded
+    key = (getattr(rw, "generation", None), bool(comp), bool(with_head), tuple(p.data_ptr() for p in m._params()),
+           tuple((bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), bn.momentum, bn.eps) for bn in m.batch_norms))
+    hit = m.__dict__.get("_native_struct")
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    gm, keep = _build_model_struct(m, comp, with_head)
+    m.__dict__["_native_struct"] = (key, gm, keep)
+    return gm, keep
+
+
+def _build_model_struct(m, comp, with_head):
     rw = m._rounded
     L = m.num_layer
     layers = (GinLayer * L)()

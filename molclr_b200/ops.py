@@ -93,11 +93,12 @@ def gemm_dw(dY, X, ordered=False):
 W_HI, W_LO, W_RAW, W_RAW_T, W_B16 = 1, 2, 4, 8, 16
 
 
-def prepare_weights(specs):
+def prepare_weights(specs, want_relaunch=False):
     """ONE launch deriving the tensor-core operand forms of several weights (molclr_prepare_weights).  specs: [(w, flags)] with w a
     2-D fp32 matrix and flags a combination of W_HI (tf32(w)), W_LO (tf32 residual), W_RAW (unrounded copy, 128-byte rows),
     W_RAW_T (W_RAW of w^T: K-major copy of a weight stored [in, out]), W_B16 (bf16 correction tiles [2, rows16, ld16] of the raw
-    orientation).  Returns a list of dicts with the keys 'hi', 'lo', 'raw', 'b16' (None where not requested)."""
+    orientation).  Returns a list of dicts with the keys 'hi', 'lo', 'raw', 'b16' (None where not requested); with
+    ``want_relaunch`` also a callable that re-derives every output from the CURRENT values of the sources into the same buffers."""
     if not specs:
         return []
     dev = specs[0][0].device
@@ -133,8 +134,13 @@ def prepare_weights(specs):
         view = lambda o, r, ld, c: None if o is None else buf32[o:o + r * ld].view(r, ld)[:, :c]
         out.append({"hi": view(o_hi, rows, ld_hi, cols), "lo": view(o_lo, rows, ld_hi, cols), "raw": view(o_raw, rt, ld_raw, ct),
                     "b16": None if o_16 is None else buf16[o_16:o_16 + 2 * rows16 * ld16].view(2, rows16, ld16)})
-    check(_lib.load().molclr_prepare_weights(descs, len(specs), stream()), "prepare_weights")
-    return out
+    fn, n = _lib.load().molclr_prepare_weights, len(specs)
+
+    def launch():          # (descs holds raw pointers into buf32 / buf16 / the sources: the closure keeps all of them alive)
+        check(fn(descs, n, stream()), "prepare_weights")
+    launch._keep = (buf32, buf16, [w for w, _ in specs])
+    launch()
+    return (out, launch) if want_relaunch else out
 
 
 def colsum(Mx):
