@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the few-step measurements of BASELINE configs 1 (on the GPU), 3 and 4")
     ap.add_argument("--local-negatives", action="store_true", help="N>1: NT-Xent over the local batch only")
+    ap.add_argument("--same-batches", action="store_true", help="N>1 diagnostic: every rank processes the SAME batches (no rank skew from batch sizes)")
+    ap.add_argument("--dp-bucket", type=int, default=None, help="N>1: gradient all-reduce bucket size in floats (0 = no overlap: one all-reduce after the backward)")
     ap.add_argument("--model", default="gin", choices=["gin", "gcn"], help="gin = BASELINE configs 1/2/5 (headline), gcn = config 3")
     return ap.parse_args()
 
@@ -196,14 +198,15 @@ def run_ours(args):
     model.precision = args.precision
     if world > 1:
         from molclr_b200.dist import DataParallelStep
-        stepper = DataParallelStep(model, B, 0.1, True, global_negatives=not args.local_negatives)
+        kw = {} if args.dp_bucket is None else ({"overlap": False} if args.dp_bucket == 0 else {"bucket_floats": args.dp_bucket})
+        stepper = DataParallelStep(model, B, 0.1, True, global_negatives=not args.local_negatives, **kw)
     else:
         stepper = None
     crit = NTXentLoss(dev, B, 0.1, True)
     opt = torch.optim.Adam(model.parameters(), 5e-4, weight_decay=1e-5, fused=True)
 
     NB = 3   # distinct batches cycled through (per rank: seed + rank)
-    host = [tuple(b.pin_memory() for b in make_pair_batch(B, seed=1000 * rank + i)) for i in range(NB)]
+    host = [tuple(b.pin_memory() for b in make_pair_batch(B, seed=(0 if args.same_batches else 1000 * rank) + i)) for i in range(NB)]
     resident = [tuple(b.to(dev) for b in pair) for pair in host]
     torch.cuda.synchronize()
 

@@ -82,6 +82,29 @@ int molclr_augment_views(const int32_t* atom_ptr, const int32_t* atoms, const in
                          int64_t* edge_attr_j, int64_t* batch_j, uint8_t* node_masked, uint8_t* bond_deleted, int32_t* status,
                          cudaStream_t stream);
 
+/* ---- subgraph-removal / mixed augmentation: dataset/dataset_subgraph.py:70-88,125-172, dataset/dataset_mix.py:45-68,128-215 ----
+ * mode 1: breadth-first removal of floor(0.25 * graph nodes) atoms from a random start atom (removed atoms are masked to [118, 0],
+ * not deleted); a bond survives iff neither endpoint was removed AND its begin atom entered the networkx graph before its end atom
+ * (the reference's `(start, end) in list(G.edges)` test).  mode 2: removal fraction ~ U(0, 0.2), either orientation survives, then
+ * random atom masking / bond deletion up to floor(0.25 N) hidden atoms / ceil(0.75 M) bonds.  The kernel emulates the ordered
+ * containers the reference's result depends on (networkx insertion order, CPython's set of small ints): see csrc/augment.cu.
+ * Two phases because the number of surviving edges is data dependent: _select writes atoms, batch vectors, per-bond keep flags
+ * (0 gone, 1 kept, 2 deleted by the mixed variant's random masking), edge counts / offsets [2][B] and totals[2] (device: the
+ * caller reads them to size the edge tensors), plus the draws made (centres [2][B], fractions [2][B] double, removed /
+ * extra-masked atoms [2][N]) so that the oracle can replay them; _fill emits the edges.
+ * status bits: 1 molecule id out of range, 2 start atom without bonds (the reference raises), 4 molecule too large for the kernel
+ * (more than 128 atoms or an atom with more than 8 distinct neighbours). */
+int molclr_subgraph_select(const int32_t* atom_ptr, const int32_t* atoms, const int32_t* bond_ptr, const int32_t* bonds,
+                           int64_t n_mols, const int64_t* mol_ids, int64_t B, const int32_t* node_off, const int32_t* bond_off,
+                           uint64_t seed, int mode, int64_t N_total, int64_t M_total, int64_t* x_i, int64_t* batch_i, int64_t* x_j,
+                           int64_t* batch_j, uint8_t* bond_keep, int32_t* edge_count, int32_t* edge_off, int32_t* totals,
+                           int32_t* centers, double* percents, uint8_t* removed, uint8_t* extra_masked, int32_t* status,
+                           cudaStream_t stream);
+int molclr_subgraph_fill(const int32_t* bond_ptr, const int32_t* bonds, int64_t n_mols, const int64_t* mol_ids, int64_t B,
+                         const int32_t* node_off, const int32_t* bond_off, const int32_t* edge_off, const uint8_t* bond_keep,
+                         int64_t M_total, int64_t* edge_index_i, int64_t* edge_attr_i, int64_t E_i, int64_t* edge_index_j,
+                         int64_t* edge_attr_j, int64_t E_j, cudaStream_t stream);
+
 /* ---- node embedding: ginet_molclr.py:103 / gcn_molclr.py:144 ------------------------------------- */
 int molclr_embed_nodes_fwd(const int32_t* xpacked, const float* E1, const float* E2, int64_t N, int D, float* out,
                            cudaStream_t stream);

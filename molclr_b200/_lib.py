@@ -80,6 +80,9 @@ SIGNATURES = {
     "molclr_plan_build": (i32, [vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp]),
     "molclr_augment_views": (i32, [vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, C.c_uint64, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                    vp, vp]),
+    "molclr_subgraph_select": (i32, [vp, vp, vp, vp, i64, vp, i64, vp, vp, C.c_uint64, i32, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                     vp]),
+    "molclr_subgraph_fill": (i32, [vp, vp, i64, vp, i64, vp, vp, vp, vp, i64, vp, vp, i64, vp, vp, i64, vp]),
     "molclr_embed_nodes_fwd": (i32, [vp, vp, vp, i64, i32, vp, vp]),
     "molclr_embed_nodes_bwd_workspace_bytes": (sz, [i64]),
     "molclr_edge_table_grad_workspace_bytes": (sz, [i32]),

@@ -107,8 +107,10 @@ def augment_pair(store, mol_ids, seed, return_selection=False, aug="node"):
     dev = store.device
     if dev.type != "cuda":
         raise RuntimeError("molclr_b200: augment_pair needs the store on a CUDA device (no CPU path exists)")
+    if aug in ("subgraph", "mix"):
+        return _subgraph_pair(store, mol_ids, seed, aug, return_selection)
     if aug != "node":
-        raise NotImplementedError(f"molclr_b200: augmentation {aug!r} has no device kernel yet (oracle/subgraph.py pins its semantics)")
+        raise ValueError("Not defined molecule augmentation!")                        # molclr.py:186-191
     node_off, edge_off, bond_off, N, E, M = store.batch_layout(mol_ids)
     B = len(node_off)
     ids = torch.as_tensor(np.asarray(mol_ids, dtype=np.int64)).to(dev, non_blocking=True)
@@ -126,3 +128,49 @@ def augment_pair(store, mol_ids, seed, return_selection=False, aug="node"):
         ptr(sel_n, torch.uint8), ptr(sel_b, torch.uint8), ptr(status, i32), stream()), "augment_views")
     out = (Batch(xi, eii, eai, bi, num_graphs=B), Batch(xj, eij, eaj, bj, num_graphs=B))
     return out + ((sel_n, sel_b),) if return_selection else out
+
+
+def _subgraph_pair(store, mol_ids, seed, aug, return_selection):
+    """The views of ``dataset_subgraph.py`` (aug="subgraph") / ``dataset_mix.py`` (aug="mix"): two kernel launches and ONE read-back
+    of the two surviving-edge totals in between (their number depends on the draws)."""
+    dev = store.device
+    node_off, _edge_off, bond_off, N, _E, M = store.batch_layout(mol_ids)
+    B = len(node_off)
+    lib = _lib.load()
+    ids = torch.as_tensor(np.asarray(mol_ids, dtype=np.int64)).to(dev, non_blocking=True)
+    offs = torch.from_numpy(np.concatenate([node_off, bond_off])).to(dev, non_blocking=True)
+    i32, i64, u8 = torch.int32, torch.int64, torch.uint8
+    new = lambda *shape: torch.empty(*shape, dtype=i64, device=dev)
+    xi, xj, bi, bj = new(N, 2), new(N, 2), new(N), new(N)
+    keep = torch.empty(2, max(M, 1), dtype=u8, device=dev)
+    counts = torch.empty(2, max(B, 1), dtype=i32, device=dev)
+    eoff = torch.empty(2, max(B, 1), dtype=i32, device=dev)
+    totals = torch.empty(2, dtype=i32, device=dev)
+    centers = torch.empty(2, max(B, 1), dtype=i32, device=dev)
+    percents = torch.empty(2, max(B, 1), dtype=torch.float64, device=dev)
+    removed = torch.empty(2, max(N, 1), dtype=u8, device=dev)
+    extra = torch.empty(2, max(N, 1), dtype=u8, device=dev)
+    status = torch.empty(1, dtype=i32, device=dev)
+    check(lib.molclr_subgraph_select(
+        ptr(store.atom_ptr, i32), ptr(store.atoms, i32), ptr(store.bond_ptr, i32), ptr(store.bonds, i32), len(store), ptr(ids, i64), B,
+        ptr(offs[:B], i32), ptr(offs[B:], i32), int(seed) & (2 ** 64 - 1), 1 if aug == "subgraph" else 2, N, M,
+        ptr(xi, i64), ptr(bi, i64), ptr(xj, i64), ptr(bj, i64), ptr(keep, u8), ptr(counts, i32), ptr(eoff, i32), ptr(totals, i32),
+        ptr(centers, i32), ptr(percents, torch.float64), ptr(removed, u8), ptr(extra, u8), ptr(status, i32), stream()), "subgraph_select")
+    E_i, E_j, bits = (int(v) for v in torch.cat([totals, status]).tolist())           # the one host read-back (sizes the edge tensors)
+    if bits & 1:
+        raise IndexError("molecule id out of range")
+    if bits & 2:
+        raise ValueError("molclr_b200: a start atom of the subgraph removal has no bonds (the reference's networkx call raises here, "
+                         "dataset_subgraph.py:79)")
+    if bits & 4:
+        raise ValueError("molclr_b200: subgraph augmentation supports molecules of up to 128 atoms with at most 8 distinct neighbours per atom")
+    eii, eij, eai, eaj = new(2, E_i), new(2, E_j), new(E_i, 2), new(E_j, 2)
+    check(lib.molclr_subgraph_fill(ptr(store.bond_ptr, i32), ptr(store.bonds, i32), len(store), ptr(ids, i64), B, ptr(offs[:B], i32), ptr(offs[B:], i32),
+                                   ptr(eoff, i32), ptr(keep, u8), M, ptr(eii, i64), ptr(eai, i64), E_i, ptr(eij, i64), ptr(eaj, i64), E_j, stream()),
+          "subgraph_fill")
+    out = (Batch(xi, eii, eai, bi, num_graphs=B), Batch(xj, eij, eaj, bj, num_graphs=B))
+    if return_selection:
+        sel = {"center": centers[:, :B], "percent": percents[:, :B], "removed": removed[:, :N], "extra_masked": extra[:, :N], "bond_keep": keep[:, :M],
+               "edge_offset": eoff[:, :B], "edge_count": counts[:, :B]}
+        return out + (sel,)
+    return out

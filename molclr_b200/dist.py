@@ -116,22 +116,43 @@ def _bucket_of(name, num_layer):
 
 
 class _GradSink:
-    """Receives finished slices of the flat gradient buffer from inside ``GINet``'s pair backward and all-reduces them."""
+    """Receives finished slices of the flat gradient buffer from inside ``GINet``'s pair backward and all-reduces them.  The slices
+    arrive from the END of the buffer towards its start (head, layer L-1, ..., layer 0, embeddings) and are contiguous, so they are
+    coalesced: an all-reduce is launched once at least ``bucket_floats`` elements are pending (and for the remainder when the
+    backward pass is done) -- few enough launches not to crowd the GEMMs off the SMs, early enough to hide under the backward."""
 
     def __init__(self, stepper):
         self.stepper = stepper
         self.reset()
 
     def reset(self):
-        self.works, self.flat, self.views, self.covered = [], None, None, 0
+        self.works, self.flat, self.views, self.covered, self.pending = [], None, None, 0, None
+
+    def _launch(self, flat):
+        lo, hi = self.pending
+        self.works.append(dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.stepper.group, async_op=True))
+        self.covered += hi - lo
+        self.pending = None
 
     def slice_ready(self, flat, lo, hi, name):
-        if self.stepper.overlap:
-            self.works.append(dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.stepper.group, async_op=True))
-            self.covered += hi - lo
+        if not self.stepper.overlap:
+            return
+        if self.pending is None:
+            self.pending = (lo, hi)
+        elif hi == self.pending[0]:
+            self.pending = (lo, self.pending[1])
+        elif lo == self.pending[1]:
+            self.pending = (self.pending[0], hi)
+        else:                                                 # not adjacent: flush what is pending, start a new range
+            self._launch(flat)
+            self.pending = (lo, hi)
+        if self.pending[1] - self.pending[0] >= self.stepper.bucket_floats:
+            self._launch(flat)
 
     def backward_done(self, flat, views):
         self.flat, self.views = flat, views
+        if self.pending is not None:
+            self._launch(flat)
 
     def finish(self, scale):
         if self.covered == 0:                                 # overlap off: one all-reduce of the whole buffer now
@@ -164,7 +185,7 @@ class DataParallelStep:
     """
 
     def __init__(self, model, batch_size, temperature, use_cosine_similarity, global_negatives=True, group=None, kern=None,
-                 local_criterion=None, overlap=True):
+                 local_criterion=None, overlap=True, bucket_floats=1 << 20):
         if not dist.is_initialized():
             raise RuntimeError("DataParallelStep: torch.distributed is not initialised")
         self.model, self.batch_size, self.temperature = model, batch_size, float(temperature)
@@ -201,6 +222,7 @@ class DataParallelStep:
         self._ready = [0] * len(self._buckets)
         self._work = [None] * len(self._buckets)
         self.overlap = bool(overlap)
+        self.bucket_floats = int(bucket_floats)
         # Models with ``forward_pair`` (GINet) run both views in one autograd node and hand finished gradient SLICES (head, layer
         # L-1, ..., layer 0, embeddings) to a sink from inside the backward pass: the all-reduce of a slice overlaps the rest of
         # the second view's backward.  Other models: post-accumulate hooks per parameter bucket.

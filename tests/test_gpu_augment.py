@@ -84,3 +84,94 @@ def test_store_round_trip_errors_and_training_step(tmp_path):
     m = GINet(2, 32, 32, 0, "mean").to(DEV)
     h, out = m(bi)
     assert out.shape == (30, 16) and torch.isfinite(out).all()
+
+
+def _structured_graphs(seed, n_random):
+    """Random molecules (some with shuffled / flipped bond lists, which changes the networkx insertion orders the result depends
+    on) plus hand-made shapes: a ring, a star, a long chain, a hub with six neighbours, a 70-atom molecule."""
+    rng = np.random.default_rng(seed)
+    graphs = []
+    for t in range(n_random):
+        x, bonds, battr = random_molecule(rng, float(rng.choice([8, 25, 45, 70])), 8.0)
+        if t % 3 == 0 and len(bonds) > 3:
+            perm = rng.permutation(len(bonds))
+            bonds, battr = bonds[perm], battr[perm]
+            flip = rng.random(len(bonds)) < 0.5
+            bonds = np.where(flip[:, None], bonds[:, ::-1], bonds)
+        graphs.append((x, np.ascontiguousarray(bonds), battr))
+    xs = lambda n: np.stack([np.full(n, 5), np.zeros(n, np.int64)], 1)
+    attr = lambda m: np.zeros((m, 2), np.int64)
+    ring = np.array([[i, (i + 1) % 12] for i in range(12)])
+    star = np.array([[0, i] for i in range(1, 5)])
+    chain = np.array([[i + 1, i] for i in range(30)])                    # every bond "backwards"
+    hub = np.array([[3, i] for i in (0, 1, 2, 4, 5, 6)] + [[6, 7], [7, 8]])
+    graphs += [(xs(12), ring, attr(12)), (xs(5), star, attr(4)), (xs(31), chain, attr(30)), (xs(9), hub, attr(8))]
+    return graphs
+
+
+@pytest.mark.parametrize("aug", ["subgraph", "mix"])
+def test_subgraph_and_mix_views_equal_the_reference_algorithm(aug):
+    """dataset_subgraph.py:70-88,125-172 / dataset_mix.py:45-68,128-215: the kernel's views against oracle/subgraph.py (networkx
+    insertion orders and CPython set iteration order on Python's own containers) replayed with the kernel's random draws."""
+    from oracle import subgraph as osg
+    graphs = _structured_graphs(5, 160)
+    store = PackedMolecules.from_graphs(graphs)
+    ids = np.concatenate([np.arange(len(graphs)), np.random.default_rng(9).integers(0, len(graphs), 90)])
+    bi, bj, sel = augment_pair(store.to(DEV), ids, seed=777, return_selection=True, aug=aug)
+    node_off, _e, bond_off, N, _E, M = store.batch_layout(ids)
+    center, percent = sel["center"].cpu().numpy(), sel["percent"].cpu().numpy()
+    removed, extra, keep = sel["removed"].cpu().numpy(), sel["extra_masked"].cpu().numpy(), sel["bond_keep"].cpu().numpy()
+    eoff, ecnt = sel["edge_offset"].cpu().numpy(), sel["edge_count"].cpu().numpy()
+    assert (center[0] != center[1]).all()                                 # random.sample(range(N), 2): two different start atoms
+    n_removed_total = 0
+    for v, got in enumerate((bi, bj)):
+        gx, gei, gea, gb = (t.cpu().numpy() for t in (got.x, got.edge_index, got.edge_attr, got.batch))
+        assert gei.shape[1] == int(ecnt[v].sum()) and gea.shape[0] == gei.shape[1]
+        for s, mol in enumerate(ids):
+            x, bonds, battr = graphs[mol]
+            n, m = len(x), len(bonds)
+            no, bo = node_off[s], bond_off[s]
+            c, pct = int(center[v, s]), float(percent[v, s])
+            k = keep[v, bo:bo + m]
+            if aug == "subgraph":
+                assert pct == 0.25
+                xv, ei, ea, rem = osg.subgraph_view(x, bonds, battr, c, pct)
+                assert (k != 2).all()
+            else:
+                assert 0.0 <= pct < 0.2
+                surviving = np.nonzero(k > 0)[0]                          # survived the removal, in bond order
+                mask_bonds_single = [int(np.nonzero(surviving == b)[0][0]) for b in np.nonzero(k == 2)[0]]
+                mask_nodes = [int(a) for a in np.nonzero(extra[v, no:no + n])[0]]
+                xv, ei, ea, rem = osg.mix_view(x, bonds, battr, c, pct, mask_nodes, mask_bonds_single)
+                want_n, want_b = osg.mix_mask_counts(n, m, len(rem), len(surviving))
+                assert len(mask_nodes) == want_n and len(mask_bonds_single) == want_b         # budgets of dataset_mix.py:175-178
+                assert not set(mask_nodes) & set(rem)                                          # drawn from the atoms that remain
+            n_removed_total += len(rem)
+            assert sorted(rem) == np.nonzero(removed[v, no:no + n])[0].tolist(), (mol, v)
+            assert np.array_equal(gx[no:no + n], xv), (mol, v)
+            assert (gb[no:no + n] == s).all()
+            e0, e1 = int(eoff[v, s]), int(eoff[v, s]) + int(ecnt[v, s])
+            assert e1 - e0 == ei.shape[1], (mol, v, e1 - e0, ei.shape[1])
+            assert np.array_equal(gei[:, e0:e1], ei + no) and np.array_equal(gea[e0:e1], ea), (mol, v)
+    assert n_removed_total > 500
+    # the views feed the encoder like any other Batch, and are a pure function of the seed
+    m = GINet(2, 32, 32, 0, "mean").to(DEV)
+    assert torch.isfinite(m(bi)[1]).all()
+    bi2, bj2 = augment_pair(store.to(DEV), ids, seed=777, aug=aug)
+    assert torch.equal(bi2.edge_index, bi.edge_index) and torch.equal(bj2.x, bj.x)
+
+
+def test_subgraph_start_atom_without_bonds_fails_like_the_reference():
+    """networkx raises when the start atom is not a node of the bond graph (dataset_subgraph.py:79 via G.neighbors)."""
+    xs = np.stack([np.full(3, 5), np.zeros(3, np.int64)], 1)
+    lone = (xs, np.array([[0, 1]]), np.zeros((1, 2), np.int64))          # atom 2 has no bond; 2 graph nodes: floor(0.25 * 2) = 0 removed
+    big = (np.stack([np.full(9, 5), np.zeros(9, np.int64)], 1), np.array([[i, i + 1] for i in range(7)]), np.zeros((7, 2), np.int64))   # atom 8 isolated
+    store = PackedMolecules.from_graphs([lone, big]).to(DEV)
+    augment_pair(store, [0], seed=1, aug="subgraph")                     # budget 0: the start atom is never looked up, as in the reference
+    raised = 0
+    for seed in range(40):
+        try:
+            augment_pair(store, [1], seed=seed, aug="subgraph")
+        except ValueError:
+            raised += 1
+    assert 0 < raised < 40                                                # raises exactly when a view starts from the isolated atom

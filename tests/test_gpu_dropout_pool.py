@@ -6,7 +6,7 @@ oracle explicitly and compare outputs and every parameter gradient value by valu
 import pytest
 import torch
 
-from tests.util import rel_err, max_rel, sync_oracle_from
+from tests.util import rel_err, max_rel, sync_oracle_from, tol
 
 pytestmark = pytest.mark.gpu
 
@@ -16,7 +16,7 @@ if torch.cuda.is_available():
     from oracle import gnn as ognn
 
 DEV = "cuda:0"
-RTOL_OUT, RTOL_GRAD = 5e-5, 2e-2
+RTOL_OUT, RTOL_GRAD = 5e-5, tol("RTOL_GRAD", 5e-3)
 
 
 def test_dropout_mask_statistics():

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import golden_weights, golden_batch, check_golden_grads, max_rel
+from tests.util import golden_weights, golden_batch, check_golden_grads, max_rel, tol, SMALL_BATCH_TABLE_TOL
 
 pytestmark = pytest.mark.gpu
 
@@ -17,8 +17,9 @@ if torch.cuda.is_available():
 
 DEV = "cuda:0"
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-# same policy as tests/test_gpu_model.py: compensated (tf32x3) forward ~ fp32, single-pass TF32 backward
-RTOL_OUT, RTOL_LOSS, RTOL_GRAD = 2e-5, 1e-4, 2e-2
+# same policy as tests/test_gpu_model.py: compensated (tf32x3) forward ~ fp32, single-pass TF32 backward; measured worst 4.2e-3
+# (profiles/parity_r2.json, tools/measure_test_errors.sh)
+RTOL_OUT, RTOL_LOSS, RTOL_GRAD = 2e-5, 1e-4, tol("RTOL_GRAD", 5e-3)
 ZERO_GRADS = ("mlp.2.bias",)          # a bias in front of a BatchNorm: true gradient 0, both sides hold rounding noise
 
 
@@ -44,7 +45,7 @@ def test_pretrain_step_matches_reference_models(name, cls):
     loss = pretrain_loss(m, NTXentLoss(DEV, int(g["batch_size"]), 0.1, True), bi, bj)
     loss.backward()
     assert abs(loss.item() - float(g["loss"])) < RTOL_LOSS * abs(float(g["loss"])), (loss.item(), float(g["loss"]))
-    bad = check_golden_grads(m, g, RTOL_GRAD, skip=_zero_grad_skips(m))
+    bad = check_golden_grads(m, g, RTOL_GRAD, skip=_zero_grad_skips(m), overrides=SMALL_BATCH_TABLE_TOL)      # 24 pairs
     assert not bad, bad
     for l in (0, 4):     # two forwards (view i, view j) = two momentum updates, as in the reference
         assert max_rel(m.batch_norms[l].running_mean, torch.from_numpy(g[f"running_mean.{l}"])) < 10 * RTOL_OUT

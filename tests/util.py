@@ -1,6 +1,15 @@
 """Shared helpers for the parity tests."""
+import os
+
 import numpy as np
 import torch
+
+
+def tol(name, default):
+    """A test tolerance; MOLCLR_TEST_<name>=<value> overrides it (used by tools/measure_test_errors.sh, which runs the GPU suite with
+    vanishing tolerances and reads the measured errors out of the assertion messages: the committed defaults are set from those)."""
+    return float(os.environ.get("MOLCLR_TEST_" + name, default))
+
 
 
 def tf32_round(x):
@@ -61,9 +70,23 @@ def golden_batch(g, tag):
     return Batch(t("x"), t("edge_index"), t("edge_attr"), t("batch"))
 
 
-def check_golden_grads(model, g, tol, skip=()):
+SMALL_BATCH_TABLE_TOL = {"gnns.0.edge_embedding": 1e-2}
+"""Per-parameter exception for batches of <= 64 graphs: the first layer's 5- and 3-row bond tables are sums over every node of a
+gradient that passed through ALL ReLU masks of the network; with ~1.5 k nodes a handful of mask flips (pre-activations within fp32
+rounding distance of zero -- the fp32 reference differs from its own fp64 run the same way) moves them by up to 8.3e-3 (measured,
+tools/measure_test_errors.sh); every other tensor, and these at >= 128 graphs, stay below 5e-3."""
+
+
+def grad_tolerance(key, base, overrides=None):
+    for prefix, t in (overrides or {}).items():
+        if key.startswith(prefix):
+            return max(base, t) if base >= 1e-6 else base      # (a vanishing base = measurement mode: report everything)
+    return base
+
+
+def check_golden_grads(model, g, tol, skip=(), overrides=None):
     """Compares every parameter gradient with the reference's: norm-relative error on tensors stored in full, the norm and
-    the strided sample otherwise.  Returns the list of (key, error) that exceed `tol`."""
+    the strided sample otherwise.  Returns the list of (key, error) that exceed `tol` (`overrides`: {key prefix: tolerance})."""
     bad = []
     for k, p in model.named_parameters():
         if f"gradnorm.{k}" not in g.files or any(k.endswith(s) for s in skip):
@@ -79,6 +102,6 @@ def check_golden_grads(model, g, tol, skip=()):
             flat = gr.reshape(-1)
             got = flat[::flat.numel() // want.numel()][:want.numel()]
             e = max(float((got - want).norm() / want.norm().clamp_min(1e-30)), abs(float(gr.norm()) - want_norm) / max(want_norm, 1e-30))
-        if not e < tol:
+        if not e < grad_tolerance(k, tol, overrides):
             bad.append((k, e))
     return bad
