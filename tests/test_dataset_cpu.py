@@ -1,4 +1,6 @@
 """CPU tests of the packed molecule format and of the augmentation oracle (no GPU, no compute through the library)."""
+import copy
+
 import numpy as np
 import pytest
 
@@ -39,3 +41,19 @@ def test_oracle_replay_matches_the_synthetic_generator():
         mask_bonds = rng.choice(len(bonds), size=k_m, replace=False) if k_m else []
         xo, eio, eao = oaug.augment_view(x, bonds, battr, list(mask_nodes), list(mask_bonds))
         assert np.array_equal(xv, xo) and np.array_equal(ei, eio) and np.array_equal(ea, eao)
+
+
+def test_build_dataset_substitutes_nothing_silently():
+    from molclr_b200.trainer import DEFAULT_CONFIG, build_dataset
+    cfg = copy.deepcopy(DEFAULT_CONFIG)
+    cfg["dataset"]["data_path"] = "data/pubchem-10m-clean.txt"          # the reference's config.yaml value: SMILES text needs RDKit
+    with pytest.raises(ValueError):
+        build_dataset(cfg)
+    cfg["dataset"]["data_path"] = "synthetic:100"
+    cfg["fp16_precision"] = True
+    with pytest.raises(ValueError):
+        build_dataset(cfg)
+    cfg["fp16_precision"] = False
+    cfg["aug"] = "bogus"
+    with pytest.raises(ValueError):
+        build_dataset(cfg)

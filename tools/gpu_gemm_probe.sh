@@ -1,4 +1,6 @@
 #!/bin/bash
+# the MOLCLR_* tuning switches exist only in the debug-switch build of the library
+python -m molclr_b200.build --debug-switches > /dev/null && export MOLCLR_B200_LIB=$PWD/molclr_b200/libmolclr_b200_dbg.so
 # GEMM microbenchmarks (with and without the epilogue) + full ncu captures of the backward GEMM variants.
 mkdir -p gpurun_out
 TAG=${1:-x}

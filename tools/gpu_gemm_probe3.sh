@@ -1,4 +1,6 @@
 #!/bin/bash
+# the MOLCLR_* tuning switches exist only in the debug-switch build of the library
+python -m molclr_b200.build --debug-switches > /dev/null && export MOLCLR_B200_LIB=$PWD/molclr_b200/libmolclr_b200_dbg.so
 mkdir -p gpurun_out
 TAG=${1:-x}
 MOLCLR_GEMM_DEBUG=1 timeout 120 python tools/bench_gemm.py > gpurun_out/gemm_bench_noepi_$TAG.log 2>&1; cat gpurun_out/gemm_bench_noepi_$TAG.log

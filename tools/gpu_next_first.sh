@@ -1,4 +1,6 @@
 #!/bin/bash
+# the MOLCLR_* tuning switches exist only in the debug-switch build of the library
+python -m molclr_b200.build --debug-switches > /dev/null && export MOLCLR_B200_LIB=$PWD/molclr_b200/libmolclr_b200_dbg.so
 # First GPU call of the next session: what the last one could not run any more.
 #  1. the motif-attention drop-in's parity test with its xfail marker ignored (shows the traceback if it still fails)
 #  2. the general (running-maximum) NT-Xent forms, taken for tau < 0.045: microbenchmark with the bounded forms switched off

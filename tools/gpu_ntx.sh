@@ -1,4 +1,6 @@
 #!/bin/bash
+# the MOLCLR_* tuning switches exist only in the debug-switch build of the library
+python -m molclr_b200.build --debug-switches > /dev/null && export MOLCLR_B200_LIB=$PWD/molclr_b200/libmolclr_b200_dbg.so
 # One GPU-box call for the fp16 NT-Xent path: its parity tests first, the NT-Xent microbenchmark (fp16 vs TF32 operands, stripe
 # widths), then the whole GPU suite and a short bench line.  Every stage under its own timeout.
 set -u

@@ -1,4 +1,6 @@
 #!/bin/bash
+# the MOLCLR_* tuning switches exist only in the debug-switch build of the library
+python -m molclr_b200.build --debug-switches > /dev/null && export MOLCLR_B200_LIB=$PWD/molclr_b200/libmolclr_b200_dbg.so
 # A/B sweep of the tile-kernel knobs (ring depth, rows per slot, streaming stores, blocked tiles)
 for cfg in "3 3 0 0" "2 3 0 0" "3 2 0 0" "2 4 0 0" "3 4 0 0" "2 5 0 0" "2 6 0 0" "3 3 0 1" "4 2 0 1" "2 4 0 1" "3 3 1 1" "3 3 1 0"; do
   set -- $cfg
