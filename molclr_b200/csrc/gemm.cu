@@ -59,6 +59,8 @@ struct GemmCfg {
   // 32-column chunks are staged unpadded with an XOR swizzle of the 16-byte column groups (stg_off); 16-column ones padded
   static constexpr int CHUNK_LD = CHUNK == 32 ? 32 : CHUNK + 4;
   // epilogue warps: two per TMEM lane quadrant (splitting the column chunks) where shared memory allows
+  // (sixteen epilogue warps -- four per scheduler -- were tried in round 2: no gain, the single-pass row GEMMs are bound by shared-memory
+  // bandwidth, not by the epilogue's instruction latency)
   static constexpr int EPI_WARPS = SMALL_EPI ? 4 : 8;
   // converter warps (compensated product with derive_lo): compute the A_lo tile from the fp32 A tile in shared memory
   static constexpr int CONV_WARPS = FOUR ? 8 : 0;
@@ -178,7 +180,8 @@ enum : int { K_PLAIN = 0, K_LATE = 1, K_NTX_W = 2, K_NTX_FWD = 3, K_ATOMIC = 4, 
 template <int BN, bool FOUR, int KIND, bool TWO>
 __global__ void __launch_bounds__(GemmCfg<BN, FOUR, TWO>::THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmO,
+                 const GemmParams p) {
   using Cfg = GemmCfg<BN, FOUR, TWO>;
   // fp16-operand instances (K-major tiles of 64 halves per 128-byte row, kind::f16 MMAs) share the epilogue of their TF32 kind
   constexpr bool H16 = KIND >= K_PLAIN16;
@@ -221,6 +224,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
     if (p.segments > 1) { ptx::prefetch_tensormap(&tmA2); ptx::prefetch_tensormap(&tmB2); }
+    if (p.tma_store) ptx::prefetch_tensormap(&tmO);
   }
   if (warp == 1) {
     if (TWO) { ptx::tmem_alloc_2cta(tmem_slot, GEMM_TMEM_COLS); ptx::tmem_relinquish_2cta(); }
@@ -706,6 +710,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                    has_out2 = p.out2 != nullptr, has_lo = p.out_lo != nullptr, has_stat = p.colstat != nullptr,
                    has_bits_in = p.bits_in != nullptr, has_bits_out = p.bits_out != nullptr;
         const int cq = 4 * (lane % LPR), r_in = lane / LPR;
+        // One output, 32-column chunks: the staged chunk (32 rows x 128 bytes, XOR-swizzled = the 128-byte TMA swizzle; every warp's
+        // staging area is 4 KB aligned) leaves through ONE bulk tensor store per chunk -- rows >= M and columns >= N are clipped by the
+        // tensor map -- instead of 8 x (ld.shared + predicated st.global) per thread.
+        const bool tma_out = EK == K_PLAIN && CH == 32 && p.tma_store != 0;
 #pragma unroll 1
         for (int k = 0; k < NCHUNK; ++k) {
           const int c0 = CH * (half + k * NSHARE);
@@ -760,8 +768,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           }
+          if (tma_out) {
+            if (do_round) {
+#pragma unroll
+              for (int j = 0; j < CH; ++j) v[j] = round_tf32(v[j]);
+            }
+            if (lane == 0) ptx::bulk_wait_group_read0();      // the previous chunk's store has finished reading this staging area
+            __syncwarp();
+          }
 #pragma unroll
           for (int j = 0; j < CH; j += 4) st_f4(stg + stg_off<LD>(lane, j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+          if (tma_out) {
+            ptx::fence_proxy_async_smem();                    // generic-proxy writes -> visible to the async proxy (TMA)
+            __syncwarp();
+            if (lane == 0 && rows_w > 0) { ptx::tma_store_2d(&tmO, stg, n0 + c0, m0 + q * 32); ptx::bulk_commit_group(); }
+            if (has_stat) colstat_warp<CH, LD>(stg, rows_w, n0 + c0, group, p, lane);
+            continue;
+          }
           __syncwarp();
           const int col = n0 + c0 + cq;
           if ((EK == K_PLAIN || EK == K_NTX_W) && rows_w == 32 && n0 + c0 + CH <= p.N) {
@@ -810,6 +833,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (TWO) ptx::mbar_arrive_cluster(tempty_leader + buf * 8u); else ptx::mbar_arrive(tempty_bar + buf);
       }
     }
+    if (p.tma_store && lane == 0) ptx::bulk_wait_group0();      // this thread's bulk stores are complete before the CTA exits
   }
   ptx::tc_fence_before();
   if (TWO) ptx::cluster_sync(); else __syncthreads();     // nobody leaves (or frees TMEM) while the peer may still signal / be read
@@ -959,6 +983,24 @@ static int make_tmap_mn3d(CUtensorMap* m, const float* base, int64_t mn, int64_t
   return 0;
 }
 
+// Tensor map over a row-major fp32 OUTPUT [rows][cols] (row pitch ld floats): boxes of 32 rows x 32 columns, 128-byte swizzle -- the layout
+// of an epilogue staging chunk.  Stores clip at the extents, so ragged M / N need no masking.
+static int make_tmap_out(CUtensorMap* m, float* base, int64_t cols, int64_t rows, int64_t ld) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  MOLCLR_REQUIRE(enc != nullptr, "gemm: cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MOLCLR_REQUIRE(r == CUDA_SUCCESS, "gemm: cuTensorMapEncodeTiled (output) failed with CUresult %d (cols=%lld rows=%lld ld=%lld)", (int)r,
+                 (long long)cols, (long long)rows, (long long)ld);
+  return 0;
+}
+
+static bool gemm_tma_store();
+
 template <int BN, bool FOUR, int KIND, bool TWO>
 static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, int splits, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, FOUR, TWO>;
@@ -999,6 +1041,15 @@ static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, i
       rc = make_tmap(&tmB2, reinterpret_cast<const float*>(j.B16), p.K, 2ll * j.rows16, j.ld16, Cfg::BN_CTA, false, Cfg::BK, true);
     if (rc) return rc;
   }
+  CUtensorMap tmO = tmA;
+  p.tma_store = 0;
+  constexpr bool kPlain = KIND == K_PLAIN || KIND == K_PLAIN16;
+  if (kPlain && Cfg::CHUNK == 32 && p.out && !p.out2 && !p.out_lo && !p.transpose_out && gemm_tma_store() && p.ldo % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
+    rc = make_tmap_out(&tmO, p.out, p.N, p.M, p.ldo);
+    if (rc) return rc;
+    p.tma_store = 1;
+  }
   auto kernel = gemm_tf32_kernel<BN, FOUR, KIND, TWO>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1019,7 +1070,7 @@ static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, i
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = TWO ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmA2, tmB2, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmA2, tmB2, tmO, p);
   ++g_launches;
   if (e != cudaSuccess) return cuda_fail(e, "gemm_tf32 launch");
   return 0;
@@ -1028,6 +1079,13 @@ static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, i
 static bool gemm_no_mn3d() {          // MOLCLR_GEMM_MN3D=0: per-block 2-D copies for MN-major operands (A/B timing)
   static int v = -1;
   if (v < 0) { const char* e = debug_env("MOLCLR_GEMM_MN3D"); v = (e && atoi(e) == 0) ? 1 : 0; }
+  return v != 0;
+}
+
+// epilogue through TMA stores unless MOLCLR_GEMM_TMA_STORE=0 (debug-switch builds: A/B timing)
+static bool gemm_tma_store() {
+  static int v = -1;
+  if (v < 0) { const char* e = debug_env("MOLCLR_GEMM_TMA_STORE"); v = (e && atoi(e) == 0) ? 0 : 1; }
   return v != 0;
 }
 

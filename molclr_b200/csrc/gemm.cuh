@@ -32,6 +32,7 @@ struct GemmParams {
   int relu, round_out;
   float* colstat; int colstat_mode;
   int stat_groups;             // number of 32-row groups the colstat buffer holds (filled by the launcher)
+  int tma_store;               // plain epilogue, one output: staged 32 x 32 chunks leave through TMA stores (tensor map tmO) instead of ld.shared + st.global
   int atomic_out;
   int debug;                   // MOLCLR_GEMM_DEBUG bit 0: skip the generic epilogue (timing experiments only)
   float alpha;                 // out = alpha * acc (+ bias + addend ...)

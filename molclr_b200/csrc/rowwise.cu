@@ -625,6 +625,28 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __re
   }
 }
 
+// The same for many partial rows and few columns: 19 CTAs of the kernel above cannot pull 7.7 MB fast enough.  Fixed order:
+// lane y sums p = y, y + 128, ...; the 128 lane sums are added in lane order.
+__global__ void __launch_bounds__(1024) reduce_partials_tall_kernel(const float* __restrict__ partials, int P, int len,
+                                                                    float scale, int accumulate, float* __restrict__ out) {
+  __shared__ float red[128][9];
+  const int c = blockIdx.x * 8 + threadIdx.x;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < len) {
+    int p = threadIdx.y;
+    for (; p + 128 < P; p += 256) { s0 += partials[(size_t)p * len + c]; s1 += partials[(size_t)(p + 128) * len + c]; }
+    if (p < P) s0 += partials[(size_t)p * len + c];
+  }
+  red[threadIdx.y][threadIdx.x] = s0 + s1;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < len) {
+    float t = red[0][threadIdx.x];
+    for (int k = 1; k < 128; ++k) t += red[k][threadIdx.x];
+    t *= scale;
+    out[c] = accumulate ? out[c] + t : t;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // BatchNorm1d, training mode (ginet_molclr.py:107; torch.nn.BatchNorm1d defaults eps=1e-5,
 // momentum=0.1).  The producing GEMM epilogue leaves per-128-row-tile column (mean, M2); this
@@ -1157,6 +1179,11 @@ extern "C" int molclr_embed_nodes_fwd(const int32_t* xpacked, const float* E1, c
 extern "C" int molclr_reduce_partials(const float* partials, int P, int len, float scale, int accumulate, float* out,
                                       cudaStream_t stream) {
   if (len == 0) return 0;
+  if (P >= 1024 && len <= 2048) {      // many partial rows, few columns (bias gradients from per-32-row column sums): 8 columns x 128 lanes per CTA
+    reduce_partials_tall_kernel<<<(len + 7) / 8, dim3(8, 128), 0, stream>>>(partials, P, len, scale, accumulate, out);
+    MOLCLR_CHECK_LAUNCH("reduce_partials");
+    return 0;
+  }
   reduce_partials_kernel<<<(len + 31) / 32, dim3(32, 32), 0, stream>>>(partials, P, len, scale, accumulate, out);
   MOLCLR_CHECK_LAUNCH("reduce_partials");
   return 0;

@@ -24,7 +24,7 @@ def timeit(fn, iters=int(os.environ.get('ITERS', 10))):
 ONLY = os.environ.get("CASE")
 
 
-def case(name, M, N, K, comp=False, b_mn=False, relu=False, pad_k=0, dw=False, masked=False, stat=0, derive=False, mixed=False):
+def case(name, M, N, K, comp=False, b_mn=False, relu=False, pad_k=0, dw=False, masked=False, stat=0, derive=False, mixed=False, presplit=False):
     if ONLY and not name.startswith(ONLY):
         return
     g = torch.Generator().manual_seed(0)
@@ -60,8 +60,17 @@ def case(name, M, N, K, comp=False, b_mn=False, relu=False, pad_k=0, dw=False, m
     if mixed:
         lo = None
     bias = torch.randn(N, device=dev)
-    fn = lambda: ops.gemm(A, B, M, N, K, b_mn=b_mn, A_lo=A_lo, B_lo=B_lo, out=out, out_lo=lo, bias=bias, relu=relu, round_out=True,
-                          lda=K + pad_k, ldb=(N if b_mn else K + pad_k), compensate=mixed)
+    B16 = None
+    if presplit:          # the product path: weight shadows from molclr_prepare_weights (unrounded K-major copy + pre-split bf16 tiles)
+        sh = ops.prepare_weights([(B.contiguous(), ops.W_RAW | ops.W_B16)])[0]
+        B, B16 = sh["raw"], sh["b16"]
+        A2 = ops.padded(M, K, dev); A2.copy_(A); A = A2
+        bits = ops.relu_bits_buffer(M, N, dev)
+        out = ops.padded(M, N, dev)
+        fn = lambda: ops.gemm(A, B, M, N, K, compensate=True, B16=B16, out=out, bias=bias, relu=relu, relu_bits=bits if relu else None)
+    else:
+        fn = lambda: ops.gemm(A, B, M, N, K, b_mn=b_mn, A_lo=A_lo, B_lo=B_lo, out=out, out_lo=lo, bias=bias, relu=relu, round_out=True,
+                              lda=K + pad_k, ldb=(N if b_mn else K + pad_k), compensate=mixed)
     us = timeit(fn)
     flops = 2.0 * M * N * K * (3 if comp else 1)
     print(f"{name:34s} {us:9.1f} us  {flops / us / 1e6:8.1f} TFLOP/s (tensor work)  out {M * N * 4 * (2 if comp else 1) / us / 1e3:7.1f} GB/s")
@@ -74,6 +83,8 @@ if os.environ.get("QUICK"):
     case("sq   x1   [M,512]x[512,512]", M, 512, 512)
     sys.exit(0)
 case("fwd1 x1   [M,300]x[600,300]", M, 600, 300)
+case("step fwd1 mixed+presplit B, relu bits", M, 600, 300, comp=True, mixed=True, presplit=True, relu=True)
+case("step fwd2 mixed+presplit B", M, 300, 600, comp=True, mixed=True, presplit=True)
 case("fwd1 x3   [M,300]x[600,300]", M, 600, 300, comp=True)
 case("fwd1 x3 derive, aligned", M, 600, 300, comp=True, derive=True, pad_k=20)
 case("fwd1 mixed (on-chip bf16 corr.)", M, 600, 300, comp=True, mixed=True, pad_k=20)
