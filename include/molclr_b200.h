@@ -213,7 +213,7 @@ int molclr_dropout_mask(uint32_t drop_seed, float drop_p, int64_t N, int D, floa
  * C[M][N] = sum_k A(m,k) * B(n,k).
  *   a_mn = 0: A is row-major [M][K] (ld = lda);  a_mn = 1: A is row-major [K][M].   Same for B with N.
  * Epilogue, in this order: + bias[n]; + addend[m][n]; relu; * (mask[m][n] > 0) or the mask_bits bit; column statistics of the
- * result (with round_out and a single output: of the result as stored, i.e. tf32-rounded) per 32-row group (colstat_mode 1: sums -> colstat[group][N]; 2: mean and M2 -> colstat[group][2][N]);
+ * result (before the optional tf32 rounding of `out`) per 32-row group (colstat_mode 1: sums -> colstat[group][N]; 2: mean and M2 -> colstat[group][2][N]);
  * out = (round_out ? tf32-rounded : exact); out2 = tf32-rounded copy.
  * A_lo/B_lo (same shape and ld as A/B; B_lo alone is allowed, see below): the tf32-rounded residuals x - tf32(x) of the true
  * fp32 operands whose tf32-rounded values are in A/B.  When given, the product is error-compensated,

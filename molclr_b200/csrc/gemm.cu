@@ -170,6 +170,49 @@ __device__ __forceinline__ void colstat_warp(const float* stage, int rows, int c
   }
 }
 
+// Register version for the TMA-store epilogue (thread = row, v = its 32 columns of the chunk; the staging area then holds the values AS
+// STORED, possibly rounded, so the statistics are taken from the exact registers instead): a butterfly transpose-reduction over the
+// warp -- 31 shuffles leave the sum of column `lane` in lane `lane` -- which also takes the 32 column reads per thread off the
+// shared-memory pipe that bounds these kernels.  Fixed order (pairwise), deterministic.
+__device__ __forceinline__ float warp_colsum32(float (&s)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      const float keep = up ? s[j + off] : s[j];
+      const float give = up ? s[j] : s[j + off];
+      s[j] = keep + __shfl_xor_sync(0xffffffffu, give, off);
+    }
+  }
+  return s[0];
+}
+
+__device__ __forceinline__ void colstat_regs(const float (&v)[32], int rows, int col0, int group, const GemmParams& p, int lane) {
+  if (group >= p.stat_groups) return;          // (warp-uniform)
+  const bool valid = lane < rows;
+  float s[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) s[j] = valid ? v[j] : 0.f;
+  const float colsum = warp_colsum32(s, lane);
+  const int col = col0 + lane;
+  if (p.colstat_mode == 1) {
+    if (col < p.N) p.colstat[(size_t)group * p.N + col] = colsum;
+    return;
+  }
+  const float mean = rows > 0 ? colsum / (float)rows : 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float d = v[j] - __shfl_sync(0xffffffffu, mean, j);
+    s[j] = valid ? d * d : 0.f;
+  }
+  const float m2 = warp_colsum32(s, lane);
+  if (col < p.N) {
+    p.colstat[((size_t)group * 2) * p.N + col] = mean;
+    p.colstat[((size_t)group * 2 + 1) * p.N + col] = m2;
+  }
+}
+
 // Persistent, warp-specialised tcgen05 GEMM.  Each CTA (one per SM) walks tiles t = blockIdx.x + i*gridDim.x of the
 // (n_tile fastest, m_tile, k_split) grid.  The TMA producer and the MMA issuer run ahead across tiles through a
 // STAGES-deep smem ring; accumulators are double-buffered in TMEM so the epilogue warps drain tile i while the
@@ -769,22 +812,21 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           if (tma_out) {
-            if (do_round) {
-#pragma unroll
-              for (int j = 0; j < CH; ++j) v[j] = round_tf32(v[j]);
-            }
             if (lane == 0) ptx::bulk_wait_group_read0();      // the previous chunk's store has finished reading this staging area
             __syncwarp();
+            if (CH == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                st_f4(stg + stg_off<LD>(lane, j), do_round ? f4_tf32(make_float4(v[j], v[j + 1], v[j + 2], v[j + 3])) : make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+              ptx::fence_proxy_async_smem();                  // generic-proxy writes -> visible to the async proxy (TMA)
+              __syncwarp();
+              if (lane == 0 && rows_w > 0) { ptx::tma_store_2d(&tmO, stg, n0 + c0, m0 + q * 32); ptx::bulk_commit_group(); }
+              if (has_stat) colstat_regs(reinterpret_cast<const float (&)[32]>(v), rows_w, n0 + c0, group, p, lane);      // of the exact values
+            }
+            continue;
           }
 #pragma unroll
           for (int j = 0; j < CH; j += 4) st_f4(stg + stg_off<LD>(lane, j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-          if (tma_out) {
-            ptx::fence_proxy_async_smem();                    // generic-proxy writes -> visible to the async proxy (TMA)
-            __syncwarp();
-            if (lane == 0 && rows_w > 0) { ptx::tma_store_2d(&tmO, stg, n0 + c0, m0 + q * 32); ptx::bulk_commit_group(); }
-            if (has_stat) colstat_warp<CH, LD>(stg, rows_w, n0 + c0, group, p, lane);
-            continue;
-          }
           __syncwarp();
           const int col = n0 + c0 + cq;
           if ((EK == K_PLAIN || EK == K_NTX_W) && rows_w == 32 && n0 + c0 + CH <= p.N) {

@@ -6,7 +6,7 @@ oracle explicitly and compare outputs and every parameter gradient value by valu
 import pytest
 import torch
 
-from tests.util import rel_err, max_rel, sync_oracle_from, tol
+from tests.util import rel_err, max_rel, sync_oracle_from, tol, SMALL_BATCH_RTOL_GRAD
 
 pytestmark = pytest.mark.gpu
 
@@ -16,7 +16,7 @@ if torch.cuda.is_available():
     from oracle import gnn as ognn
 
 DEV = "cuda:0"
-RTOL_OUT, RTOL_GRAD = 5e-5, tol("RTOL_GRAD", 5e-3)
+RTOL_OUT, RTOL_GRAD = 5e-5, tol("RTOL_GRAD", SMALL_BATCH_RTOL_GRAD)
 
 
 def test_dropout_mask_statistics():

@@ -5,7 +5,7 @@ import os
 import pytest
 import torch
 
-from tests.util import rel_err, max_rel, sync_oracle_from, tol
+from tests.util import rel_err, max_rel, sync_oracle_from, tol, SMALL_BATCH_RTOL_GRAD
 
 pytestmark = pytest.mark.gpu
 
@@ -19,7 +19,7 @@ if torch.cuda.is_available():
 
 DEV = "cuda:0"
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-RTOL_OUT, RTOL_LOSS, RTOL_GRAD = 2e-5, 1e-4, tol("RTOL_GRAD", 5e-3)      # same policy as tests/test_gpu_model.py (tf32x3 forward)
+RTOL_OUT, RTOL_LOSS, RTOL_GRAD = 2e-5, 1e-4, tol("RTOL_GRAD", SMALL_BATCH_RTOL_GRAD)      # same policy as tests/test_gpu_model.py (tf32x3 forward)
 
 
 def _models(seed=0, emb=300, feat=512):

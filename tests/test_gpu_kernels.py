@@ -224,9 +224,7 @@ def test_gemm_epilogues():
     ops.gemm(A, B, M, N, K, out=out, bias=bias, relu=True, round_out=True, colstat=part, colstat_mode=1)
     want = torch.relu(ref + bias.double().cpu())
     assert max_rel(out, want) < 1e-3 and torch.equal(out, tf32_round(out))
-    # the column statistics describe the result AS STORED (here: tf32-rounded); against the exact result they carry its rounding
-    assert rel_err(part.double().sum(0), out.double().sum(0).cpu()) < 1e-6
-    assert rel_err(part.double().sum(0), want.sum(0)) < 1e-4
+    assert rel_err(part.double().sum(0), want.sum(0)) < 1e-5          # statistics of the exact result, not of the rounded copy
     # addend + mask, exact output + rounded copy
     out, out2 = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
     ops.gemm(A, B, M, N, K, out=out, out2=out2, addend=addend, mask=mask)
