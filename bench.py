@@ -346,6 +346,9 @@ def run_ours(args):
                          "forward_compensated_useful_tflops": fwd, "forward_frac": fwd / tf32_peak, "forward_calls_timed": n_fwd,
                          "backward_single_pass_tflops": bwd, "backward_frac": bwd / tf32_peak if bwd else None, "backward_calls_timed": n_bwd,
                          "weight_gradient_tflops": dwt, "weight_gradient_frac": dwt / tf32_peak if dwt else None, "weight_gradient_calls_timed": n_dw,
+                         # the weight-gradient products read 3 [N, 300]-sized operand blocks once and write 0.7 MB: they sit on the HBM roofline
+                         "weight_gradient_hbm_gbs": (4.0 * 900 * (sum(nodes) / len(nodes)) * n_dw / (dw_ms * 1e-3) / 1e9) if n_dw and dw_ms > 0 else None,
+                         "weight_gradient_hbm_frac": (4.0 * 900 * (sum(nodes) / len(nodes)) * n_dw / (dw_ms * 1e-3) / 1e9 / peak) if n_dw and dw_ms > 0 else None,
                          "us_per_call": {"forward": fwd_ms * 1e3 / max(n_fwd, 1), "backward": bwd_ms * 1e3 / max(n_bwd, 1), "weight_gradient": dw_ms * 1e3 / max(n_dw, 1)},
                          "note": "useful FLOPs 2MNK per product (the compensated forward issues 2x that in tensor work: one TF32 pass + two "
                                  "bf16 correction passes); see DESIGN.md section 6"}

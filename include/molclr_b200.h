@@ -264,6 +264,10 @@ int molclr_gemm_tf32(const molclr_gemm_args* args /* host */, cudaStream_t strea
  * (autograd of ginet_molclr.py:19-23,90-96; gcn_molclr.py:76).  Split-K over R, one wave, atomic accumulation. */
 int molclr_gemm_dw(const float* dY, int64_t ldy, const float* X, int64_t ldx, int64_t R, int64_t O, int64_t I, float* dW,
                    int64_t ldw, cudaStream_t stream);
+/* dW += dY^T X: the same launch without the zero-fill of dW (a caller that produces many weight gradients into one buffer zero-fills
+ * the buffer ONCE: the per-call 2-D memsets cost more than they look, ~20 us each in the step) */
+int molclr_gemm_dw_acc(const float* dY, int64_t ldy, const float* X, int64_t ldx, int64_t R, int64_t O, int64_t I, float* dW,
+                       int64_t ldw, cudaStream_t stream);
 /* The same contraction with a FIXED summation order (bit-reproducible run to run): every K split writes its partial [O][I]
  * tile product to `workspace` with plain stores and a second kernel sums the splits in split order.
  * workspace: molclr_gemm_dw_workspace_bytes(R, O, I) bytes, 16-byte aligned. */
@@ -276,12 +280,15 @@ int molclr_gemm_dw_ordered(const float* dY, int64_t ldy, const float* X, int64_t
  * gcn_molclr.py:47) are functions of the parameter only, so they are derived once per forward instead of per tile:
  *   hi  [rows][ld_hi]   = tf32(W)            (single-pass products, every backward dX product), same orientation as W
  *   lo  [rows][ld_hi]   = tf32(W - hi)       (explicit 3-pass product of the head)
+ *   hi_t [cols][ld_hi_t] = tf32(W^T)         (dX = dY W reads W^T K-major: column tiles of any multiple of 8 instead of whole
+ *                                             32-column blocks, i.e. 6 - 12 % instead of 22 - 28 % padded tensor work at N = 300 / 600)
  *   raw [rows_t][ld_raw] = W or W^T (transpose_raw: K-major copy of a weight stored [in][out]), unrounded, 128-byte rows
  *   b16 [2][rows16][ld16] bf16 = bf16(raw), bf16(raw - trunc_tf32(raw)), zero padded (see molclr_gemm_args.B16)
  * Any output pointer may be NULL.  Padding columns (up to the row pitch) are written as zeros. */
 typedef struct {
   const float* src; int64_t ld_src; int32_t rows, cols;
   float* hi; float* lo; int64_t ld_hi;
+  float* hi_t; int64_t ld_hi_t;                 /* tf32(W^T) [cols][ld_hi_t]: the K-major B operand of the backward dX product */
   float* raw; int64_t ld_raw; int32_t transpose_raw;
   void* b16; int64_t ld16; int32_t rows16;
 } molclr_weight_desc;
@@ -299,6 +306,7 @@ typedef struct {                       /* one GINEConv + BatchNorm1d (ginet_molc
   const float* b1;
   const float* w2_hi; const float* w2_raw; const void* w2_b16;     /* mlp.2.weight [D][2D] */
   const float* b2;
+  const float* w1_hi_t; const float* w2_hi_t;                      /* tf32(W1^T) [D][2D], tf32(W2^T) [2D][D] (optional: backward dX operands) */
   const float* bond_type; const float* bond_dir;                   /* edge_embedding1 [5][D], edge_embedding2 [3][D] */
   const float* gamma; const float* beta; float* running_mean; float* running_var; int64_t* num_batches_tracked;
   float momentum, eps;

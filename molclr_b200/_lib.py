@@ -42,6 +42,7 @@ class WeightDesc(C.Structure):
     _fields_ = [
         ("src", vp), ("ld_src", i64), ("rows", C.c_int32), ("cols", C.c_int32),
         ("hi", vp), ("lo", vp), ("ld_hi", i64),
+        ("hi_t", vp), ("ld_hi_t", i64),
         ("raw", vp), ("ld_raw", i64), ("transpose_raw", C.c_int32),
         ("b16", vp), ("ld16", i64), ("rows16", C.c_int32),
     ]
@@ -53,7 +54,7 @@ LAYER_CB = C.CFUNCTYPE(None, C.c_int, C.c_void_p)          # molclr_layer_cb
 class GinLayer(C.Structure):
     """Mirror of ``molclr_gin_layer``."""
     _fields_ = [("w1_hi", vp), ("w1_raw", vp), ("w1_b16", vp), ("b1", vp), ("w2_hi", vp), ("w2_raw", vp), ("w2_b16", vp), ("b2", vp),
-                ("bond_type", vp), ("bond_dir", vp), ("gamma", vp), ("beta", vp), ("running_mean", vp), ("running_var", vp),
+                ("w1_hi_t", vp), ("w2_hi_t", vp), ("bond_type", vp), ("bond_dir", vp), ("gamma", vp), ("beta", vp), ("running_mean", vp), ("running_var", vp),
                 ("num_batches_tracked", vp), ("momentum", f32), ("eps", f32)]
 
 
@@ -115,6 +116,7 @@ SIGNATURES = {
     "molclr_gemm_workers": (i32, []),
     "molclr_gemm_tf32": (i32, [C.POINTER(GemmArgs), vp]),
     "molclr_gemm_dw": (i32, [vp, i64, vp, i64, i64, i64, i64, vp, i64, vp]),
+    "molclr_gemm_dw_acc": (i32, [vp, i64, vp, i64, i64, i64, i64, vp, i64, vp]),
     "molclr_gin_ctx_bytes": (sz, [C.POINTER(GinModel), i64, i64, i32, i32]),
     "molclr_gin_scratch_bytes": (sz, [C.POINTER(GinModel), i64, i64, i32]),
     "molclr_gin_grad_layout": (i64, [C.POINTER(GinModel), C.POINTER(i64)]),

@@ -1235,7 +1235,7 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   const int tile_m = pair ? 2 * GEMM_BM : GEMM_BM;
   const int m_tiles = (p.M + tile_m - 1) / tile_m;
   p.stat_groups = molclr_gemm_colstat_tiles(p.M);
-  if (atomic && p.atomic_out != 3) {
+  if (atomic && p.atomic_out != 3 && !job.accumulate) {
     const size_t w = (size_t)(p.transpose_out ? p.M : p.N) * sizeof(float), h = (size_t)(p.transpose_out ? p.N : p.M);
     cudaError_t e = cudaMemset2DAsync(p.out, (size_t)p.ldo * sizeof(float), 0, w, h, stream);
     if (e != cudaSuccess) return cuda_fail(e, "gemm: zeroing split-K output");
@@ -1334,14 +1334,28 @@ static void dw_job(GemmJob& j, const DwPlan& pl, const float* dY, int64_t ldy, c
   j.split_k = pl.split; j.wide = pl.wide;
 }
 
-extern "C" int molclr_gemm_dw(const float* dY, int64_t ldy, const float* X, int64_t ldx, int64_t R, int64_t O, int64_t I, float* dW,
-                              int64_t ldw, cudaStream_t stream) {
+static int gemm_dw_atomic(const float* dY, int64_t ldy, const float* X, int64_t ldx, int64_t R, int64_t O, int64_t I, float* dW, int64_t ldw,
+                          int accumulate, cudaStream_t stream) {
   DwPlan pl;
   if (int rc = dw_plan(R, O, I, &pl)) return rc;
   GemmJob j;
   dw_job(j, pl, dY, ldy, X, ldx, R);
   j.p.out = dW; j.p.ldo = ldw; j.p.transpose_out = pl.swap;
+  if (accumulate) {
+    j.accumulate = 1;
+    if (j.split_k < 2 && !j.p.transpose_out) j.split_k = 2;       // the accumulating (atomic) kernel kind, also for a single K split
+  }
   return gemm_run(j, stream);
+}
+
+extern "C" int molclr_gemm_dw(const float* dY, int64_t ldy, const float* X, int64_t ldx, int64_t R, int64_t O, int64_t I, float* dW,
+                              int64_t ldw, cudaStream_t stream) {
+  return gemm_dw_atomic(dY, ldy, X, ldx, R, O, I, dW, ldw, 0, stream);
+}
+
+extern "C" int molclr_gemm_dw_acc(const float* dY, int64_t ldy, const float* X, int64_t ldx, int64_t R, int64_t O, int64_t I, float* dW,
+                                  int64_t ldw, cudaStream_t stream) {
+  return gemm_dw_atomic(dY, ldy, X, ldx, R, O, I, dW, ldw, 1, stream);
 }
 
 // out[m][n] (or out[n][m]) = sum_s ws[s][m][n], s in increasing order.  32 x 32 tiles, block (32, 8).

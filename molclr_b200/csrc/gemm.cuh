@@ -56,6 +56,7 @@ struct GemmJob {
   const float* A_lo; const float* B_lo;   // both non-null selects the 3-segment compensated product (same layout/ld as A, B)
   int compensate;              // 1: A and B are unrounded K-major fp32; ~fp32-accurate product, everything derived on chip ("mixed")
   const void* B16; long long ld16; int rows16;   // compensate: optional pre-split bf16 correction tiles of B (molclr_prepare_weights)
+  int accumulate;              // split-K: add into `out` as it is (the caller zero-filled it, or wants out += product) instead of zero-filling it first
   float* ordered_ws;           // split-K: write the per-split partial products here ([splits][M][ldws] fp32) with plain stores and sum them
                                // in split order afterwards (bit-reproducible) instead of accumulating atomically
   int split_k;

@@ -31,6 +31,13 @@ __global__ void __launch_bounds__(256) prepare_weights_kernel(const __grid_const
       if (d.lo) d.lo[i] = round_tf32(v - h);
     }
   }
+  if (d.hi_t) {
+    const long long n = (long long)d.cols * d.ld_hi_t;
+    for (long long i = tid; i < n; i += nth) {
+      const int r = (int)(i / d.ld_hi_t), c = (int)(i % d.ld_hi_t);          // element (r, c) of W^T = W[c][r]
+      d.hi_t[i] = c < d.rows ? round_tf32(__ldg(d.src + (size_t)c * d.ld_src + r)) : 0.f;
+    }
+  }
   const int rows_t = d.transpose_raw ? d.cols : d.rows, cols_t = d.transpose_raw ? d.rows : d.cols;
   auto at = [&](int r, int c) -> float {           // element (r, c) of the raw orientation, 0 outside
     if (r >= rows_t || c >= cols_t) return 0.f;
@@ -221,6 +228,7 @@ extern "C" int molclr_prepare_weights(const molclr_weight_desc* descs, int n, cu
     const molclr_weight_desc& d = descs[i];
     MOLCLR_REQUIRE(d.src && d.rows > 0 && d.cols > 0 && d.ld_src >= d.cols, "prepare_weights: descriptor %d: bad source", i);
     MOLCLR_REQUIRE((!d.hi && !d.lo) || d.ld_hi >= d.cols, "prepare_weights: descriptor %d: ld_hi < cols", i);
+    MOLCLR_REQUIRE(!d.hi_t || d.ld_hi_t >= d.rows, "prepare_weights: descriptor %d: ld_hi_t < rows", i);
     MOLCLR_REQUIRE(!d.raw || d.ld_raw >= (d.transpose_raw ? d.rows : d.cols), "prepare_weights: descriptor %d: ld_raw too small", i);
     MOLCLR_REQUIRE(!d.b16 || (d.ld16 % 8 == 0 && d.ld16 >= (d.transpose_raw ? d.rows : d.cols) && d.rows16 >= (d.transpose_raw ? d.cols : d.rows)),
                    "prepare_weights: descriptor %d: bf16 tile extents (ld16 %% 8 == 0, ld16 >= K, rows16 >= N)", i);

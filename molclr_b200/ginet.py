@@ -84,6 +84,11 @@ class _RoundedWeights:
             return e["raw"]
         return ops.prepare_weights([(p.detach(), ops.W_RAW_T if transpose else ops.W_RAW)])[0]["raw"]
 
+    def hi_t(self, p):
+        """tf32(p^T) with 128-byte rows (None unless part of the last refresh)."""
+        e = self._entry(p, "hi_t")
+        return None if e is None else e["hi_t"]
+
     def b16(self, p):
         """bf16 correction tiles [2, rows16, ld16] of ``raw(p)`` (None unless part of the last refresh)."""
         e = self._entry(p, "b16")
@@ -122,8 +127,8 @@ class _EncoderBase(nn.Module):
         head = ops.W_HI | (ops.W_LO if comp else 0)
         specs, seen = [], set()
         for g in self.gnns:
-            if hasattr(g, "mlp"):
-                ws = [(g.mlp[0].weight, enc | (ops.W_RAW if comp else 0)), (g.mlp[2].weight, enc | (ops.W_RAW if comp else 0))]
+            if hasattr(g, "mlp"):                         # (+ the transposed tf32 copies: K-major operands of the backward dX products)
+                ws = [(g.mlp[0].weight, enc | ops.W_HI_T | (ops.W_RAW if comp else 0)), (g.mlp[2].weight, enc | ops.W_HI_T | (ops.W_RAW if comp else 0))]
             else:                                         # GCNConv: stored [in, out]
                 ws = [(g.weight, enc | (ops.W_RAW_T if comp else 0))]
             specs += ws

@@ -47,6 +47,7 @@ def _build_model_struct(m, comp, with_head):
         g, bn, ly = m.gnns[l], m.batch_norms[l], layers[l]
         w1, w2 = g.mlp[0].weight, g.mlp[2].weight
         ly.w1_hi, ly.w2_hi = rw.get(w1)[0].data_ptr(), rw.get(w2)[0].data_ptr()
+        ly.w1_hi_t, ly.w2_hi_t = _dp(rw.hi_t(w1)), _dp(rw.hi_t(w2))
         if comp:
             s1, s2 = rw.b16(w1), rw.b16(w2)
             ly.w1_raw, ly.w2_raw, ly.w1_b16, ly.w2_b16 = rw.raw(w1).data_ptr(), rw.raw(w2).data_ptr(), s1.data_ptr(), s2.data_ptr()

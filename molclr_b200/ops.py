@@ -71,15 +71,19 @@ def colstat_tile_rows():
     return _lib.load().molclr_gemm_colstat_tile_rows()
 
 
-def gemm_dw(dY, X, ordered=False):
+def gemm_dw(dY, X, ordered=False, accumulate_into=None):
     """dW[O,I] = dY^T X for row-major dY [R,O], X [R,I] (both tf32-rounded): the weight gradient of a
     Linear (autograd of ginet_molclr.py:19-23,90-96).  Both operands are consumed MN-major in place;
     the reduction over R is split across CTAs and accumulated atomically (default), or -- ``ordered`` -- written as
     per-split partials and summed in split order (bit-reproducible run to run)."""
     R, O = dY.shape
     I = X.shape[1]
-    dW = _empty(O, I, device=dY.device)
     lib = _lib.load()
+    if accumulate_into is not None:       # dW += dY^T X (atomic accumulation, no zero-fill)
+        dW = accumulate_into
+        check(lib.molclr_gemm_dw_acc(ptr2d(dY), dY.stride(0), ptr2d(X), X.stride(0), R, O, I, ptr2d(dW), dW.stride(0), stream()), "gemm_dw_acc")
+        return dW
+    dW = _empty(O, I, device=dY.device)
     if ordered:
         nbytes = lib.molclr_gemm_dw_workspace_bytes(R, O, I)
         ws = torch.empty(max(nbytes, 16) // 4, dtype=F32, device=dY.device)
@@ -90,14 +94,15 @@ def gemm_dw(dY, X, ordered=False):
     return dW
 
 
-W_HI, W_LO, W_RAW, W_RAW_T, W_B16 = 1, 2, 4, 8, 16
+W_HI, W_LO, W_RAW, W_RAW_T, W_B16, W_HI_T = 1, 2, 4, 8, 16, 32
 
 
 def prepare_weights(specs, want_relaunch=False):
     """ONE launch deriving the tensor-core operand forms of several weights (molclr_prepare_weights).  specs: [(w, flags)] with w a
     2-D fp32 matrix and flags a combination of W_HI (tf32(w)), W_LO (tf32 residual), W_RAW (unrounded copy, 128-byte rows),
     W_RAW_T (W_RAW of w^T: K-major copy of a weight stored [in, out]), W_B16 (bf16 correction tiles [2, rows16, ld16] of the raw
-    orientation).  Returns a list of dicts with the keys 'hi', 'lo', 'raw', 'b16' (None where not requested); with
+    orientation), W_HI_T (tf32(w^T): the K-major operand of the backward dX product).  Returns a list of dicts with the keys 'hi',
+    'lo', 'raw', 'b16', 'hi_t' (None where not requested); with
     ``want_relaunch`` also a callable that re-derives every output from the CURRENT values of the sources into the same buffers."""
     if not specs:
         return []
@@ -109,7 +114,10 @@ def prepare_weights(specs, want_relaunch=False):
         tr = bool(flags & W_RAW_T)
         rt, ct = (cols, rows) if tr else (rows, cols)
         ld_hi, ld_raw, ld16, rows16 = r32(cols), r32(ct), (ct + 63) // 64 * 64, (rt + 255) // 256 * 256
-        o_hi = o_lo = o_raw = o_16 = None
+        ld_hi_t = r32(rows)
+        o_hi = o_lo = o_raw = o_16 = o_hit = None
+        if flags & W_HI_T:
+            o_hit, n32 = n32, n32 + cols * ld_hi_t
         if flags & W_HI:
             o_hi, n32 = n32, n32 + rows * ld_hi
         if flags & W_LO:
@@ -118,21 +126,23 @@ def prepare_weights(specs, want_relaunch=False):
             o_raw, n32 = n32, n32 + rt * ld_raw
         if flags & W_B16:
             o_16, n16 = n16, n16 + 2 * rows16 * ld16
-        plans.append((rows, cols, tr, rt, ct, ld_hi, ld_raw, ld16, rows16, o_hi, o_lo, o_raw, o_16))
+        plans.append((rows, cols, tr, rt, ct, ld_hi, ld_raw, ld16, rows16, o_hi, o_lo, o_raw, o_16, ld_hi_t, o_hit))
     buf32 = torch.empty(max(n32, 1), dtype=F32, device=dev)
     buf16 = torch.empty(max(n16, 1), dtype=torch.bfloat16, device=dev)
     descs = (WeightDesc * len(specs))()
     out = []
     b32, b16 = buf32.data_ptr(), buf16.data_ptr()
-    for d, (w, _), (rows, cols, tr, rt, ct, ld_hi, ld_raw, ld16, rows16, o_hi, o_lo, o_raw, o_16) in zip(descs, specs, plans):
+    for d, (w, _), (rows, cols, tr, rt, ct, ld_hi, ld_raw, ld16, rows16, o_hi, o_lo, o_raw, o_16, ld_hi_t, o_hit) in zip(descs, specs, plans):
         d.src, d.ld_src, d.rows, d.cols = ptr2d(w), w.stride(0), rows, cols
         d.ld_hi, d.ld_raw, d.transpose_raw, d.ld16, d.rows16 = ld_hi, ld_raw, int(tr), ld16, rows16
         d.hi = b32 + 4 * o_hi if o_hi is not None else None
         d.lo = b32 + 4 * o_lo if o_lo is not None else None
         d.raw = b32 + 4 * o_raw if o_raw is not None else None
         d.b16 = b16 + 2 * o_16 if o_16 is not None else None
+        d.hi_t, d.ld_hi_t = (b32 + 4 * o_hit if o_hit is not None else None), ld_hi_t
         view = lambda o, r, ld, c: None if o is None else buf32[o:o + r * ld].view(r, ld)[:, :c]
         out.append({"hi": view(o_hi, rows, ld_hi, cols), "lo": view(o_lo, rows, ld_hi, cols), "raw": view(o_raw, rt, ld_raw, ct),
+                    "hi_t": view(o_hit, cols, ld_hi_t, rows),
                     "b16": None if o_16 is None else buf16[o_16:o_16 + 2 * rows16 * ld16].view(2, rows16, ld16)})
     fn, n = _lib.load().molclr_prepare_weights, len(specs)
 

@@ -21,7 +21,7 @@ import time
 
 import torch
 
-from . import GCN, GINet, NTXentLoss, normalize
+from . import GCN, GINet, NTXentLoss, pretrain_loss
 from .graph import poll_checks
 from .synth import make_pair_batch
 
@@ -134,9 +134,9 @@ class MolCLR:
 
     # the hot path: molclr.py:55-67
     def _step(self, model, xis, xjs, n_iter=None):
-        _ris, zis = model(xis)
-        _rjs, zjs = model(xjs)
-        return self.nt_xent_criterion(normalize(zis, dim=1), normalize(zjs, dim=1))
+        # two encoder passes (view i, then view j), F.normalize, NT-Xent: molclr_b200.pretrain_loss runs the two passes as one
+        # autograd node when the model offers forward_pair (same values)
+        return pretrain_loss(model, self.nt_xent_criterion, xis, xjs)
 
     def _scalar(self, tag, value, step):
         if self.writer is not None:

@@ -101,4 +101,15 @@ def test_ordered_weight_gradient_matches_and_is_bit_reproducible(R, O, I):
     b = ops.gemm_dw(dY, X, ordered=True)
     assert torch.equal(a, b)
     assert rel_err(a, ref) < 1e-5
-    assert rel_err(ops.gemm_dw(dY, X), ref) < 1e-5
+    c = ops.gemm_dw(dY, X)
+    assert rel_err(c, ref) < 1e-5
+    acc = c.clone()
+    ops.gemm_dw(dY, X, accumulate_into=acc)                   # dW += dY^T X (no zero-fill)
+    assert rel_err(acc, 2 * ref) < 1e-5
+
+
+def test_prepare_weights_transposed_tf32_copy():
+    torch.manual_seed(3)
+    w = torch.randn(600, 300, device=DEV)
+    o = ops.prepare_weights([(w, ops.W_HI | ops.W_HI_T)])[0]
+    assert torch.equal(o["hi_t"], tf32_round(w.t().contiguous())) and o["hi_t"].stride(0) % 32 == 0 and o["hi_t"].shape == (300, 600)

@@ -44,8 +44,9 @@ def case(name, M, N, K, comp=False, b_mn=False, relu=False, pad_k=0, dw=False, m
     if dw:
         dY, X = torch.randn(M, N, generator=g).to(dev), torch.randn(M, K, generator=g).to(dev)
         us = timeit(lambda: ops.gemm_dw(dY, X))
+        us_o = timeit(lambda: ops.gemm_dw(dY, X, ordered=True))
         flops = 2.0 * M * N * K
-        print(f"{name:34s} {us:9.1f} us  {flops / us / 1e6:8.1f} TFLOP/s")
+        print(f"{name:34s} {us:9.1f} us  {flops / us / 1e6:8.1f} TFLOP/s   ordered (fixed-order split-K): {us_o:9.1f} us")
         return
     A = torch.randn(M, K + pad_k, generator=g).to(dev)[:, :K]
     B = (torch.randn(K, N, generator=g) if b_mn else torch.randn(N, K + pad_k, generator=g)).to(dev)
