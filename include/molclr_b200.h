@@ -109,9 +109,10 @@ int molclr_subgraph_fill(const int32_t* bond_ptr, const int32_t* bonds, int64_t 
 int molclr_embed_nodes_fwd(const int32_t* xpacked, const float* E1, const float* E2, int64_t N, int D, float* out,
                            cudaStream_t stream);
 /* dE is ONE buffer [(119+3)][D]: rows 0..118 = grad of x_embedding1, 119..121 = grad of x_embedding2 (g rows ld_g floats apart):
- * embedding_dense_backward of the reference, in plain fp32 with a FIXED summation order (bit-reproducible): every CTA sums its
- * contiguous block of nodes sequentially into a [122][D] tile in shared memory, the per-CTA tiles go to `workspace` and are summed
- * in CTA order.  workspace: molclr_embed_nodes_bwd_workspace_bytes(N) bytes, 16-byte aligned. */
+ * embedding_dense_backward of the reference, in plain fp32 with a FIXED summation order (bit-reproducible): chunks of 128 nodes are
+ * dealt round-robin to the CTAs; a CTA orders a chunk by atom type (stable in-CTA rank), sums it run by run in registers and adds
+ * the runs to its [119][D] shared-memory tile; the per-CTA tiles go to `workspace` and are summed in CTA order.
+ * workspace: molclr_embed_nodes_bwd_workspace_bytes(N) bytes, 16-byte aligned. */
 size_t molclr_embed_nodes_bwd_workspace_bytes(int64_t N);
 int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, int64_t ld_g, int64_t N, int D, float* dE, void* workspace,
                            cudaStream_t stream);
@@ -159,8 +160,9 @@ int molclr_bn_apply_fwd(const float* z, const float* bn_coef, int relu, int64_t 
 int molclr_bn_tile_stats(const float* z, int64_t N, int D, int T, float* tile_stats, cudaStream_t stream);
 /* Gradients of edge_embedding1/2 (embedding_dense_backward over E' rows in the reference):
  * dB [8][D] = cnt^T . ga: rows 0..4 = d edge_embedding1, rows 5..7 = d edge_embedding2 (ga rows ld_ga floats apart).  These are
- * heavy-cancellation sums over all nodes, so they run as exact fp32 FMAs with a FIXED order (bit-reproducible): every CTA sums its
- * contiguous block of nodes sequentially, the per-CTA [8][D] partials go to `workspace` and are summed in CTA order.
+ * heavy-cancellation sums over all nodes, so they run as exact fp32 FMAs with a FIXED order (bit-reproducible): row tiles are dealt
+ * round-robin to the CTAs, each of a CTA's four row lanes sums its rows in increasing order, lanes are added in lane order, the
+ * per-CTA [8][D] partials go to `workspace` and are summed in CTA order.
  * workspace: molclr_edge_table_grad_workspace_bytes(D) bytes, 16-byte aligned. */
 size_t molclr_edge_table_grad_workspace_bytes(int D);
 int molclr_edge_table_grad(const float* ga, int64_t ld_ga, const float* cnt, int64_t N, int D, float* dB, void* workspace,

@@ -2,8 +2,8 @@
 //   * molclr_prepare_weights: the tensor-core operand forms of every Linear / GCNConv weight, one launch per forward;
 //   * molclr_edge_table_grad / molclr_embed_nodes_bwd: the gradients of the bond / atom embedding tables
 //     (embedding_dense_backward in the reference; ginet_molclr.py:33-39,103).  They are heavy-cancellation sums over all
-//     nodes into 8 / 122 rows, so they run as plain fp32 FMAs with a fixed summation order (contiguous node blocks summed
-//     sequentially by one CTA each, block partials summed in block order) instead of a split-K tensor-core contraction.
+//     nodes into 8 / 122 rows, so they run as plain fp32 FMAs with a fixed summation order (row tiles dealt round-robin to the
+//     CTAs and summed in increasing order by each, CTA partials summed in CTA order) instead of a split-K tensor-core contraction.
 #include <cuda_bf16.h>
 #include <cstring>
 

@@ -206,10 +206,11 @@ class DataParallelStep:
         self._params = [named[i][1] for i in order]
         bucket_ids = [_bucket_of(named[i][0], L) for i in order]
         total = sum(p.numel() for p in self._params)
-        self._flat = torch.zeros(total, dtype=self._params[0].dtype, device=self._params[0].device)
+        pair = hasattr(model, "forward_pair")            # (pair models bring their own flat buffer: see _GradSink)
+        self._flat = torch.zeros(0 if pair else total, dtype=self._params[0].dtype, device=self._params[0].device)
         self._views, self._buckets, off = [], [], 0          # bucket: dict(lo, hi, idx=[param indices])
         for i, (p, b) in enumerate(zip(self._params, bucket_ids)):
-            self._views.append(self._flat[off:off + p.numel()].view_as(p))
+            self._views.append(None if pair else self._flat[off:off + p.numel()].view_as(p))
             if not self._buckets or self._buckets[-1]["id"] != b:
                 self._buckets.append({"id": b, "lo": off, "hi": off, "idx": []})
             self._buckets[-1]["idx"].append(i)
@@ -287,7 +288,9 @@ class DataParallelStep:
     def allreduce_gradients(self):
         """Completes the gradient exchange: buckets whose all-reduce was launched from the backward hooks are waited for, the others
         are reduced now; afterwards ``p.grad`` of every parameter aliases its slice of the flat buffer."""
-        if self._pair and self._sink.flat is not None:
+        if self._pair:
+            if self._sink.flat is None:
+                raise RuntimeError("DataParallelStep.allreduce_gradients: no gradients to reduce -- call loss(xis, xjs).backward() first")
             self._sink.finish(self.grad_scale)
             return
         for bi in range(len(self._buckets)):

@@ -13,7 +13,9 @@ Per view the kernel sequence is (N nodes, D=emb_dim, H=2D; SURVEY.md section 3.2
     pool_fwd                   p = mean_g( BN_L(z_L) )                                 :113
     gemm x3                    h = feat_lin(p); out = out_lin(h)                       :114-115
 
-and the backward mirrors it (see ``_backward``).  Nothing here falls back to PyTorch operators.
+and the backward mirrors it.  Both sequences are issued from C in ONE call each (``molclr_gin_encoder_fwd/bwd``,
+``molclr_proj_head_fwd/bwd`` in csrc/gin_step.cu, driven by ``molclr_b200/native.py``); the per-kernel wrappers of ``ops.py`` remain
+for the GCN path, the fine-tune heads and the tests.  Nothing here falls back to PyTorch operators.
 """
 import torch
 from torch import nn
