@@ -1,7 +1,8 @@
-"""Per-parameter parity report (GPU): the full MolCLR pre-training step (molclr.py:55-67) on the CUDA path against the CPU
+"""TEST INFRASTRUCTURE (it lives under tests/ because it runs the oracle; pytest does not collect it).
+Per-parameter parity report (GPU): the full MolCLR pre-training step (molclr.py:55-67) on the CUDA path against the CPU
 oracle in fp32 AND in fp64, so that every measured error is printed next to its floor (oracle fp32 vs oracle fp64).
 
-    python tools/parity_report.py [--batches 128,512] [--precision tf32x3] [--out profiles/parity_r2.json]
+    python tests/parity_report.py [--batches 128,512] [--precision tf32x3] [--out profiles/parity_r2.json]
 
 Also checks (a) run-twice bit-reproducibility of loss and gradients and (b) that an optimizer step on the parameters is
 picked up by the next forward.  The JSON it writes is what the test tolerances are set from (tests/test_gpu_config_sizes.py).
@@ -12,7 +13,7 @@ import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))          # repo root
 import torch
 
 from tests.util import rel_err, max_rel, sync_oracle_from

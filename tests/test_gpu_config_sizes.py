@@ -1,5 +1,5 @@
 """GPU parity tests at the BASELINE.json configuration sizes, with per-tensor gradient tolerances set from the
-measured errors in profiles/parity_r2.json (tools/parity_report.py prints every error next to its floor: the fp32 oracle
+measured errors in profiles/parity_r2.json (tests/parity_report.py prints every error next to its floor: the fp32 oracle
 against the fp64 oracle, which is ~1e-3 for this ReLU network because a pre-activation within rounding distance of zero flips
 its mask).
 

@@ -26,7 +26,7 @@ NTX = sorted(glob.glob(os.path.join(GOLDEN, "ntxent_*.npz")))
 # backward contractions single-pass TF32 (operands rounded to 10 mantissa bits, fp32 accumulate); everything
 # else is fp32.  Gradients of a ReLU network are only sqrt-continuous in the activations (a pre-activation
 # within rounding distance of 0 flips its mask), so even the fp32 CPU reference differs from its own fp64
-# run by ~1e-3 in the norm of a gradient (tools/debug_parity.py prints that floor); RTOL_GRAD sits above it.
+# run by ~1e-3 in the norm of a gradient (tests/parity_report.py prints that floor); RTOL_GRAD sits above it.
 RTOL_OUT = 2e-5        # max-relative error of activations / outputs (compensated forward)
 RTOL_LOSS = 1e-4       # relative error of the scalar loss
 RTOL_GRAD = tol("RTOL_GRAD", 5e-3)       # norm-relative error of EVERY parameter gradient (measured: <= 3.7e-3 from 128 pairs up, profiles/parity_r2.json)

@@ -9,5 +9,5 @@ timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_$TAG.log 2>&1;
 tail -15 gpurun_out/pytest_$TAG.log
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.log 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
 cat gpurun_out/bench_$TAG.log; tail -3 gpurun_out/bench_$TAG.err
-timeout 600 python tools/parity_report.py --batches 128,512,4096 --out gpurun_out/parity_$TAG.json > gpurun_out/parity_$TAG.log 2>&1; echo "parity rc=$?"
+timeout 600 python tests/parity_report.py --batches 128,512,4096 --out gpurun_out/parity_$TAG.json > gpurun_out/parity_$TAG.log 2>&1; echo "parity rc=$?"
 grep -v "^   " gpurun_out/parity_$TAG.log | tail -8
