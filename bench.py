@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--local-negatives", action="store_true", help="N>1: NT-Xent over the local batch only")
     ap.add_argument("--same-batches", action="store_true", help="N>1 diagnostic: every rank processes the SAME batches (no rank skew from batch sizes)")
     ap.add_argument("--dp-bucket", type=int, default=None, help="N>1: gradient all-reduce bucket size in floats (0 = no overlap: one all-reduce after the backward)")
+    ap.add_argument("--no-pdl", action="store_true", help="launch every kernel in plain stream order (no programmatic dependent launch): A/B timing")
     ap.add_argument("--model", default="gin", choices=["gin", "gcn"], help="gin = BASELINE configs 1/2/5 (headline), gcn = config 3")
     return ap.parse_args()
 
@@ -191,6 +192,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    if args.no_pdl:
+        lib.molclr_set_pdl(0)
+    pdl = bool(lib.molclr_set_pdl(-1))
     B = args.batch
 
     torch.manual_seed(0)
@@ -386,7 +390,7 @@ def run_ours(args):
     line = {"metric": METRIC if args.model == "gin" else METRIC.replace("GIN", "GCN"), "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
             "config": workload_config(args, world),
-            "run": {"precision": args.precision, "ntxent_operands": "fp16 (kind::f16; same 11-bit significand as tf32), fp32 accumulation",
+            "run": {"precision": args.precision, "programmatic_dependent_launch": pdl, "ntxent_operands": "fp16 (kind::f16; same 11-bit significand as tf32), fp32 accumulation",
                     "loss": last_loss, "nodes_per_view": int(resident[0][0].x.size(0)), "edges_per_view": int(resident[0][0].edge_index.size(1))},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "molecules/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
@@ -409,9 +413,11 @@ def run_ours(args):
 def extra_configs(args, dev):
     """The other BASELINE.json configurations, measured in the same run with a few steps each (resident inputs, CUDA events):
     config 1 on the GPU (512 pairs: the like-for-like batch of the CPU arm), config 3 (GCN, 4096 pairs), config 4 (fine-tune
-    GINet, 1024 graphs, BBBP- and ESOL-shaped, drop_ratio 0 and 0.3) and the single-pass `tf32` precision mode of config 2."""
-    from molclr_b200 import Batch, GCN, GINet, NTXentLoss, ginet_finetune, pretrain_loss
+    GINet, 1024 graphs, BBBP- and ESOL-shaped, drop_ratio 0 and 0.3), the single-pass `tf32` precision mode of config 2, and
+    configs 1 / 2 with plain stream-ordered launches (the A/B of programmatic dependent launch)."""
+    from molclr_b200 import Batch, GCN, GINet, NTXentLoss, _lib, ginet_finetune, pretrain_loss
     from molclr_b200.synth import make_pair_batch, make_plain_batch
+    lib = _lib.load()
 
     def timed(step, warm=5, n=10):
         for _ in range(warm):
@@ -427,7 +433,15 @@ def extra_configs(args, dev):
 
     fresh = lambda b: Batch(b.x, b.edge_index, b.edge_attr, b.batch, b.num_graphs)
 
-    def pretrain(cls, B, precision):
+    def pretrain(cls, B, precision, pdl=None):
+        if pdl is not None:
+            before = lib.molclr_set_pdl(int(pdl))
+            try:
+                r = pretrain(cls, B, precision)
+            finally:
+                lib.molclr_set_pdl(before)
+            r["programmatic_dependent_launch"] = bool(pdl)
+            return r
         torch.manual_seed(0)
         model = cls(5, 300, 512, 0, "mean").to(dev)
         model.precision = precision
@@ -470,6 +484,9 @@ def extra_configs(args, dev):
     out = {"config1_gpu_512_pairs": pretrain(GINet, 512, "tf32x3"),
            "config3_gcn_4096_pairs": pretrain(GCN, 4096, "tf32x3"),
            "config2_precision_tf32": pretrain(GINet, 4096, "tf32"),
+           # A/B of programmatic dependent launch: the same steps with plain stream-ordered launches
+           "config1_gpu_512_pairs_plain_launches": pretrain(GINet, 512, "tf32x3", pdl=False),
+           "config2_plain_launches": pretrain(GINet, 4096, "tf32x3", pdl=False),
            "config4_finetune_bbbp_cls_drop0": finetune("classification", 46.0, 18.0, 0.0),
            "config4_finetune_bbbp_cls_drop0.3": finetune("classification", 46.0, 18.0, 0.3),
            "config4_finetune_esol_reg_drop0": finetune("regression", 26.0, 13.0, 0.0),

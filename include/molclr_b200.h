@@ -36,6 +36,11 @@ int molclr_abi_version(void);
 const char* molclr_last_error(void);
 /* number of kernels this library has launched so far in this process (diagnostics) */
 uint64_t molclr_launch_count(void);
+/* Programmatic dependent launch (default on): every kernel of the library is launched with programmatic stream serialization, so
+ * that its launch overlaps the tail of the kernel before it; each kernel waits for the COMPLETION of its predecessors before its
+ * first global-memory access, so results are those of plain stream order.  enable = 0 / 1 sets the switch, < 0 only queries;
+ * returns the previous value.  (A measurement aid and an escape hatch; the reference has no counterpart: it is eager PyTorch.) */
+int molclr_set_pdl(int enable);
 /* host out-params; cc = compute capability major*10+minor */
 int molclr_device_info(int* sm_count, int* cc);
 

@@ -76,6 +76,7 @@ SIGNATURES = {
     "molclr_abi_version": (i32, []),
     "molclr_last_error": (C.c_char_p, []),
     "molclr_launch_count": (C.c_uint64, []),
+    "molclr_set_pdl": (i32, [i32]),
     "molclr_device_info": (i32, [C.POINTER(i32), C.POINTER(i32)]),
     "molclr_plan_workspace_bytes": (sz, [i64, i64, i64]),
     "molclr_plan_build": (i32, [vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp]),
@@ -161,6 +162,8 @@ def load():
             fn.restype, fn.argtypes = res, args
         if lib.molclr_abi_version() != ABI_VERSION:
             raise RuntimeError("molclr_b200: ABI version mismatch between _lib.py and libmolclr_b200.so")
+        if os.environ.get("MOLCLR_B200_PDL", "1") == "0":      # escape hatch / A-B timing: plain stream-ordered launches
+            lib.molclr_set_pdl(0)
         _lib = lib
     return _lib
 

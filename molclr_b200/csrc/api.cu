@@ -9,6 +9,7 @@ namespace molclr {
 
 static thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
+int g_pdl = 1;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -37,6 +38,11 @@ int sm_count() {
 extern "C" int molclr_abi_version(void) { return MOLCLR_ABI_VERSION; }
 extern "C" const char* molclr_last_error(void) { return molclr::g_err; }
 extern "C" uint64_t molclr_launch_count(void) { return molclr::g_launches; }
+extern "C" int molclr_set_pdl(int enable) {
+  const int before = molclr::g_pdl;
+  if (enable >= 0) molclr::g_pdl = enable != 0;
+  return before;
+}
 
 extern "C" int molclr_device_info(int* sm_count_out, int* cc) {
   int dev = 0, major = 0, minor = 0;

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(256) augment_views_kernel(
     int64_t* __restrict__ x1, int64_t* __restrict__ ei1, int64_t* __restrict__ ea1, int64_t* __restrict__ batch1,
     int64_t E_total, uint8_t* __restrict__ node_masked /* [2][N] or null */, uint8_t* __restrict__ bond_deleted /* [2][sum M] or null */,
     int64_t N_total, int64_t M_total, int32_t* __restrict__ status) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), view = blockIdx.y;
   if (slot >= B) return;
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(128) subgraph_select_kernel(
     int64_t* __restrict__ x1, int64_t* __restrict__ batch1, int64_t N_total, int64_t M_total, uint8_t* __restrict__ bond_keep /* [2][M] */,
     int32_t* __restrict__ edge_count /* [2][B] */, int32_t* __restrict__ center_out /* [2][B] */, double* __restrict__ percent_out /* [2][B] */,
     uint8_t* __restrict__ removed_out /* [2][N] */, uint8_t* __restrict__ extra_masked_out /* [2][N] */, int32_t* __restrict__ status) {
+  pdl_sync();
   const int task = blockIdx.x * blockDim.x + threadIdx.x;
   if (task >= 2 * B) return;
   const int view = task / B, slot = task - view * B;
@@ -307,6 +309,7 @@ __global__ void __launch_bounds__(128) subgraph_select_kernel(
 // exclusive scan of the per-task edge counts (one block; B is at most a few 10^4) -> edge_off [2][B], totals [2]
 __global__ void __launch_bounds__(1024) subgraph_scan_kernel(const int32_t* __restrict__ edge_count, int B, int32_t* __restrict__ edge_off,
                                                              int32_t* __restrict__ totals) {
+  pdl_sync();
   __shared__ int32_t part[1024];
   const int view = blockIdx.x, tid = threadIdx.x;
   const int per = (B + 1023) / 1024, lo = min(B, tid * per), hi = min(B, lo + per);
@@ -327,6 +330,7 @@ __global__ void __launch_bounds__(256) subgraph_fill_kernel(const int32_t* __res
                                                             const uint8_t* __restrict__ bond_keep, int64_t M_total, int64_t n_mols,
                                                             int64_t* __restrict__ ei0, int64_t* __restrict__ ea0, int64_t E0,
                                                             int64_t* __restrict__ ei1, int64_t* __restrict__ ea1, int64_t E1) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), view = blockIdx.y;
   if (slot >= B) return;
@@ -369,7 +373,7 @@ extern "C" int molclr_augment_views(const int32_t* atom_ptr, const int32_t* atom
   if (e != cudaSuccess) return cuda_fail(e, "augment_views memset");
   if (B == 0) return 0;
   const int warps = 8;
-  augment_views_kernel<<<dim3((unsigned)((B + warps - 1) / warps), 2), 32 * warps, 0, stream>>>(
+  MOLCLR_LAUNCH(augment_views_kernel, dim3((unsigned)((B + warps - 1) / warps), 2), 32 * warps, 0, stream,
       atom_ptr, atoms, bond_ptr, bonds, mol_ids, (int)B, node_off, edge_off, bond_off, seed, n_mols, x_i, edge_index_i, edge_attr_i,
       batch_i, x_j, edge_index_j, edge_attr_j, batch_j, E_total, node_masked, bond_deleted, N_total, M_total, status);
   MOLCLR_CHECK_LAUNCH("augment_views");
@@ -394,11 +398,11 @@ extern "C" int molclr_subgraph_select(const int32_t* atom_ptr, const int32_t* at
   e = cudaMemsetAsync(totals, 0, 2 * sizeof(int32_t), stream);
   if (e != cudaSuccess) return cuda_fail(e, "subgraph_select memset");
   if (B == 0) return 0;
-  subgraph_select_kernel<<<(unsigned)((2 * B + 127) / 128), 128, 0, stream>>>(atom_ptr, atoms, bond_ptr, bonds, mol_ids, (int)B, node_off, bond_off, seed,
+  MOLCLR_LAUNCH(subgraph_select_kernel, (unsigned)((2 * B + 127) / 128), 128, 0, stream, atom_ptr, atoms, bond_ptr, bonds, mol_ids, (int)B, node_off, bond_off, seed,
                                                                               n_mols, mode, x_i, batch_i, x_j, batch_j, N_total, M_total, bond_keep,
                                                                               edge_count, centers, percents, removed, extra_masked, status);
   MOLCLR_CHECK_LAUNCH("subgraph_select");
-  subgraph_scan_kernel<<<2, 1024, 0, stream>>>(edge_count, (int)B, edge_off, totals);
+  MOLCLR_LAUNCH(subgraph_scan_kernel, 2, 1024, 0, stream, edge_count, (int)B, edge_off, totals);
   MOLCLR_CHECK_LAUNCH("subgraph_scan");
   return 0;
 }
@@ -409,7 +413,7 @@ extern "C" int molclr_subgraph_fill(const int32_t* bond_ptr, const int32_t* bond
                                     int64_t* edge_attr_j, int64_t E_j, cudaStream_t stream) {
   if (B == 0) return 0;
   const int warps = 8;
-  subgraph_fill_kernel<<<dim3((unsigned)((B + warps - 1) / warps), 2), 32 * warps, 0, stream>>>(
+  MOLCLR_LAUNCH(subgraph_fill_kernel, dim3((unsigned)((B + warps - 1) / warps), 2), 32 * warps, 0, stream,
       bond_ptr, bonds, mol_ids, (int)B, node_off, bond_off, edge_off, bond_keep, M_total, n_mols, edge_index_i, edge_attr_i, E_i, edge_index_j,
       edge_attr_j, E_j);
   MOLCLR_CHECK_LAUNCH("subgraph_fill");

@@ -4,6 +4,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <utility>
 
 #ifndef __CUDA_ARCH__
 #define MOLCLR_HOST 1
@@ -31,6 +33,27 @@ extern unsigned long long g_launches;   // kernels launched by this library (dia
 
 int sm_count();   // cached multiprocessor count of the current device
 
+// ---------------------------------------------------------------- kernel launches (programmatic dependent launch)
+// A training step is ~230 dependent launches of 3 - 170 us each on one stream.  Every kernel of this library is launched with
+// programmatic stream serialization: its launch (grid set-up, CTA scheduling, the prologue before pdl_sync()) overlaps the tail of
+// the kernel before it, and pdl_sync() -- the first thing every kernel does before it touches global memory -- waits until that
+// kernel has COMPLETED and its writes are visible.  Results are exactly those of plain stream order; molclr_set_pdl(0) switches
+// the attribute off (the device-side instructions are then no-ops).
+extern int g_pdl;
+
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);     // (errors: cudaGetLastError in MOLCLR_CHECK_LAUNCH)
+}
+#define MOLCLR_LAUNCH(kernel, grid, block, smem, stream, ...) ::molclr::launch_kernel(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
+
 // Tuning / debugging switches (MOLCLR_GEMM_*, MOLCLR_AGG_*, MOLCLR_NTX_*) are read from the environment ONLY in a library built
 // with -DMOLCLR_DEBUG_SWITCHES (python -m molclr_b200.build --debug-switches -> libmolclr_b200_dbg.so, used by tools/);
 // the product library never looks at the environment, so a stray variable cannot change its results or its speed.
@@ -44,6 +67,14 @@ inline const char* debug_env(const char* name) {
 }
 
 // ---------------------------------------------------------------- device helpers
+// Executed by every thread at the top of every kernel, before its first global-memory access: wait for the preceding kernels of the
+// stream (complete, writes visible), then allow the NEXT kernel's launch to begin (its CTAs become resident as this kernel's CTAs
+// exit and wait at their own pdl_sync()).  No-ops in a kernel launched without the programmatic attribute.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ float round_tf32(float x) {
   // round-to-nearest (ties away) to 10 mantissa bits; low 13 bits of the result are zero, so the
   // tensor core's operand truncation is exact on it.

@@ -238,8 +238,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tempty_bar = tfull_bar + 2;              // [2] accumulator drained
   uint64_t* afull_bar = tempty_bar + 2;              // [STAGES] derive_lo: this CTA's fp32 A tile has landed
   uint64_t* conv_bar = afull_bar + Cfg::STAGES;      // [STAGES] derive_lo: A_lo tiles of the worker converted (leader's copy is used)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv_bar + Cfg::STAGES);
-  static_assert((4 * Cfg::STAGES + 4) * 8 + 4 <= 512, "barrier area");
+  uint64_t* raw_bar = conv_bar + Cfg::STAGES;        // [STAGES] mixed: the raw fp32 tiles of the worker have landed (leader's copy is used)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_bar + Cfg::STAGES);
+  static_assert((5 * Cfg::STAGES + 4) * 8 + 4 <= 512, "barrier area");
   float* bias_s = reinterpret_cast<float*>(smem + Cfg::PIPE_BYTES + Cfg::STAGING_BYTES + 512);   // [2][256]
   const bool derive = FOUR && p.derive_lo != 0;
   // derive_lo == 2 ("mixed"): A and B are both UNROUNDED fp32, K-major; stage = [A][A_hi16|A_lo16][B][B_hi16|B_lo16]: the tensor core
@@ -261,6 +262,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < Cfg::STAGES; ++s) {
       ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1);
       ptx::mbar_init(afull_bar + s, 1); ptx::mbar_init(conv_bar + s, (TWO ? 2 : 1) * (Cfg::CONV_WARPS > 0 ? Cfg::CONV_WARPS : 1));
+      ptx::mbar_init(raw_bar + s, TWO ? 2 : 1);
     }
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(tfull_bar + b, 1); ptx::mbar_init(tempty_bar + b, (TWO ? 2 : 1) * Cfg::EPI_WARPS); }
     ptx::fence_barrier_init();
@@ -277,6 +279,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (TWO) ptx::cluster_sync(); else __syncthreads();     // barriers initialised and TMEM allocated in BOTH CTAs
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();          // everything above overlaps the tail of the previous kernel of the stream; global memory is touched only from here
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (whole warp walks the loop with warp-uniform
@@ -391,10 +394,34 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::mbar_wait(tempty_bar + buf, ((tl >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * 256u;
+        // (both run on the elected lane only)  mixed: correction passes of a stage on its bf16 tiles: K-major rows of 32 bf16 = 64 bytes
+        // (64B swizzle, 8-row groups 512 B apart), K = 16 (32 bytes) per instruction
+        auto corrections = [&](uint32_t a_base, uint32_t b_base) {
+          if constexpr (FOUR) {
+            if (mixed && !(p.debug & 4)) {
+#pragma unroll
+              for (int k = 0; k < Cfg::BK / 16; ++k) {
+                const uint64_t ah = h_d0 + ((a_base + Cfg::A_BYTES + k * 32u) >> 4), al = ah + (Cfg::A_BYTES / 2 >> 4);
+                const uint64_t bh = h_d0 + ((b_base + Cfg::B_BYTES + k * 32u) >> 4), bl = bh + (Cfg::B_BYTES / 2 >> 4);
+                if (TWO) { ptx::mma_f16_ss_2cta(d_tmem, al, bh, idesc16, 1u); ptx::mma_f16_ss_2cta(d_tmem, ah, bl, idesc16, 1u); }
+                else { ptx::mma_f16_ss(d_tmem, al, bh, idesc16, 1u); ptx::mma_f16_ss(d_tmem, ah, bl, idesc16, 1u); }
+              }
+            }
+          }
+        };
+        auto finish = [&](int s, bool last) {
+          commit(empty_bar + s);                    // frees the smem slot (of both CTAs) once these MMAs have read it
+          if (last) commit(tfull_bar + buf);        // accumulator complete
+        };
         for (int i = 0; i < nkb; ++i, ++it) {
           const int s = it % Cfg::STAGES;
+          // mixed: the TF32 pass reads only the raw tiles, so it is issued as soon as they have LANDED in both CTAs (raw_bar) and runs on
+          // the tensor pipe while the converter warps are still forming the bf16 tiles of the same stage; the correction passes wait
+          // for conv_bar.  Same instruction order as issuing all eight after the conversion: bit-identical results.
+          const bool early = mixed && !(p.debug & 16);
           if (!mixed) ptx::mbar_wait(full_bar + s, (it / Cfg::STAGES) & 1);
-          if (derive) ptx::mbar_wait(conv_bar + s, (it / Cfg::STAGES) & 1);
+          if (early) ptx::mbar_wait(raw_bar + s, (it / Cfg::STAGES) & 1);
+          else if (derive) ptx::mbar_wait(conv_bar + s, (it / Cfg::STAGES) & 1);
           ptx::tc_fence_after();
           const uint32_t a_base = smem_base + s * Cfg::STAGE_BYTES;
           const uint32_t b_base = a_base + (FOUR ? 2 : 1) * Cfg::A_BYTES;
@@ -414,19 +441,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mma(d_tmem, ad, bd2, 1u);          // A_hi * B_lo
               }
             }
-            if (mixed && !(p.debug & 4)) {
-              // correction passes on the bf16 tiles: K-major rows of 32 bf16 = 64 bytes (64B swizzle, 8-row groups 512 B apart),
-              // K = 16 (32 bytes) per instruction
-#pragma unroll
-              for (int k = 0; k < Cfg::BK / 16; ++k) {
-                const uint64_t ah = h_d0 + ((a_base + Cfg::A_BYTES + k * 32u) >> 4), al = ah + (Cfg::A_BYTES / 2 >> 4);
-                const uint64_t bh = h_d0 + ((b_base + Cfg::B_BYTES + k * 32u) >> 4), bl = bh + (Cfg::B_BYTES / 2 >> 4);
-                if (TWO) { ptx::mma_f16_ss_2cta(d_tmem, al, bh, idesc16, 1u); ptx::mma_f16_ss_2cta(d_tmem, ah, bl, idesc16, 1u); }
-                else { ptx::mma_f16_ss(d_tmem, al, bh, idesc16, 1u); ptx::mma_f16_ss(d_tmem, ah, bl, idesc16, 1u); }
-              }
-            }
-            commit(empty_bar + s);          // frees the smem slot (of both CTAs) once these MMAs have read it
-            if (i == nkb - 1) commit(tfull_bar + buf);          // accumulator complete
+            if (!(FOUR && early)) { corrections(a_base, b_base); finish(s, i == nkb - 1); }
+          }
+          if (FOUR && early) {
+            __syncwarp();
+            ptx::mbar_wait(conv_bar + s, (it / Cfg::STAGES) & 1);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) { corrections(a_base, b_base); finish(s, i == nkb - 1); }
           }
           __syncwarp();
         }
@@ -447,6 +468,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = 0; i < nkb; ++i, ++it) {
           const int s = it % Cfg::STAGES;
           ptx::mbar_wait(afull_bar + s, (it / Cfg::STAGES) & 1);
+          if (mixed && ct == 0) {      // this CTA's raw tiles have landed: the leader's MMA warp may start the TF32 pass of the stage
+            if (TWO) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(raw_bar + s), 0u)); else ptx::mbar_arrive(raw_bar + s);
+          }
           const float4* hi = reinterpret_cast<const float4*>(smem + s * Cfg::STAGE_BYTES);
           float4* lo = reinterpret_cast<float4*>(smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES);
           if (mixed) {
@@ -891,6 +915,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 __global__ void __launch_bounds__(128) gemm_simt_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B,
                                                         long long ldb, const float* __restrict__ A_lo, const float* __restrict__ B_lo,
                                                         const GemmParams p) {
+  pdl_sync();
   __shared__ float stage[GEMM_BM * 33];
   const int n0 = blockIdx.x * 32, m_tile = blockIdx.y, m0 = m_tile * GEMM_BM;
   const int row = threadIdx.x, grow = m0 + row;
@@ -1108,10 +1133,12 @@ static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, i
   cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = TWO ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // see common.cuh: launch_kernel / pdl_sync
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_pdl ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmA2, tmB2, tmO, p);
   ++g_launches;
   if (e != cudaSuccess) return cuda_fail(e, "gemm_tf32 launch");
@@ -1242,7 +1269,7 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   }
   if (gemm_impl_simt()) {
     p.kb_per_split = p.num_kb;
-    gemm_simt_kernel<<<dim3((unsigned)((p.N + 31) / 32), (p.M + GEMM_BM - 1) / GEMM_BM, 1), 128, 0, stream>>>(job.A, job.lda, job.B, job.ldb, job.A_lo, job.B_lo, p);
+    MOLCLR_LAUNCH(gemm_simt_kernel, dim3((unsigned)((p.N + 31) / 32), (p.M + GEMM_BM - 1) / GEMM_BM, 1), 128, 0, stream, job.A, job.lda, job.B, job.ldb, job.A_lo, job.B_lo, p);
     MOLCLR_CHECK_LAUNCH("gemm_simt");
     return 0;
   }
@@ -1361,6 +1388,7 @@ extern "C" int molclr_gemm_dw_acc(const float* dY, int64_t ldy, const float* X, 
 // out[m][n] (or out[n][m]) = sum_s ws[s][m][n], s in increasing order.  32 x 32 tiles, block (32, 8).
 __global__ void __launch_bounds__(256) dw_reduce_kernel(const float* __restrict__ ws, int S, int M, int N, long long ldws, float* __restrict__ out,
                                                         long long ldo, int transpose) {
+  pdl_sync();
   __shared__ float tile[32][33];
   const int n = blockIdx.x * 32 + threadIdx.x;
 #pragma unroll
@@ -1404,7 +1432,7 @@ extern "C" int molclr_gemm_dw_ordered(const float* dY, int64_t ldy, const float*
   const int S = effective_splits((int)((R + GEMM_BK - 1) / GEMM_BK), j.split_k);
   MOLCLR_REQUIRE(S == pl.splits, "gemm_dw_ordered: internal: split count %d != planned %d", S, pl.splits);
   if (int rc = gemm_run(j, stream)) return rc;
-  dw_reduce_kernel<<<dim3((unsigned)((pl.N + 31) / 32), (unsigned)((pl.M + 31) / 32), 1), dim3(32, 8, 1), 0, stream>>>(
+  MOLCLR_LAUNCH(dw_reduce_kernel, dim3((unsigned)((pl.N + 31) / 32), (unsigned)((pl.M + 31) / 32), 1), dim3(32, 8, 1), 0, stream,
       reinterpret_cast<const float*>(workspace), S, (int)pl.M, (int)pl.N, ldws, dW, ldw, pl.swap);
   MOLCLR_CHECK_LAUNCH("gemm_dw_ordered reduce");
   return 0;

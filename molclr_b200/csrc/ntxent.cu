@@ -39,6 +39,7 @@ static int stripe16() {              // MOLCLR_NTX_STRIPE16 = 1024 | 2048 | 4096
 
 // dst[r][0..C) = fp16(src[r][0..C)), row pitch ld16 halves (a multiple of 8); one thread per 4 elements
 __global__ void __launch_bounds__(256) ntx_to_half_kernel(const float* __restrict__ src, long long rows, int C, int ld16, __half* __restrict__ dst) {
+  pdl_sync();
   const int c4 = C / 4;
   const long long total = rows * c4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(256) ntx_to_half_kernel(const float* __restric
 
 // dstT[c][r] = fp16(src[r][c]), row pitch ldT halves: the K-major "B" operand of the dZ contraction over candidates
 __global__ void __launch_bounds__(256) ntx_to_half_t_kernel(const float* __restrict__ src, long long rows, int C, long long ldT, __half* __restrict__ dstT) {
+  pdl_sync();
   __shared__ float tile[64][33];
   const long long r0 = (long long)blockIdx.x * 64;
   const int c0 = blockIdx.y * 32;
@@ -75,6 +77,7 @@ __global__ void __launch_bounds__(256) ntx_to_half_t_kernel(const float* __restr
 // the 8 y-partials of a row are merged through shared memory in a fixed order (deterministic).
 __global__ void __launch_bounds__(256) ntx_merge_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum, int tiles, int R,
                                                         float* __restrict__ row_lse) {
+  pdl_sync();
   __shared__ float s_m[8][33], s_s[8][33];
   const int r = blockIdx.x * 32 + threadIdx.x;
   float m = -INFINITY, s = 0.f;
@@ -105,6 +108,7 @@ __global__ void __launch_bounds__(256) ntx_merge_kernel(const float* __restrict_
 // loss = (1/Rc) * sum_r (row_lse[r] - row_pos[r]); single block, fixed order -> deterministic.
 __global__ void __launch_bounds__(1024) ntx_loss_kernel(const float* __restrict__ row_lse, const float* __restrict__ row_pos, int R,
                                                         float inv_rc, float* __restrict__ loss) {
+  pdl_sync();
   __shared__ double red[1024];
   double s = 0.0;
   for (int r = threadIdx.x; r < R; r += blockDim.x) s += (double)row_lse[r] - (double)row_pos[r];
@@ -120,6 +124,7 @@ __global__ void __launch_bounds__(1024) ntx_loss_kernel(const float* __restrict_
 // out[i] = sum_s partials[s][i] in stripe order (float4, coalesced)
 __global__ void __launch_bounds__(256) ntx_sum_partials_kernel(const float* __restrict__ partials, int ns, long long len4,
                                                                float* __restrict__ out) {
+  pdl_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < len4; i += (long long)gridDim.x * blockDim.x) {
     float4 a = ld_stream_f4(partials + 4 * i);
     for (int s = 1; s < ns; ++s) a = f4_add(a, ld_stream_f4(partials + (size_t)s * len4 * 4 + 4 * i));
@@ -184,7 +189,7 @@ static int to_half(const float* src, int64_t rows, int C, int ld16, __half* dst,
   const long long total = rows * (C / 4);
   long long blocks = (total + 255) / 256;
   if (blocks > 16 * sm_count()) blocks = 16 * sm_count();
-  ntx_to_half_kernel<<<(int)blocks, 256, 0, stream>>>(src, rows, C, ld16, dst);
+  MOLCLR_LAUNCH(ntx_to_half_kernel, (int)blocks, 256, 0, stream, src, rows, C, ld16, dst);
   MOLCLR_CHECK_LAUNCH("ntx_to_half");
   return 0;
 }
@@ -238,10 +243,10 @@ static int ntxent_fwd_impl(const float* rep, const float* cols, const __half* re
   p.part_max = part_max; p.part_sum = part_sum; p.row_pos = row_pos;
   int rc = gemm_run(j, stream);
   if (rc) return rc;
-  ntx_merge_kernel<<<(int)((R + 31) / 32), dim3(32, 8), 0, stream>>>(part_max, part_sum, tiles, (int)R, row_lse);
+  MOLCLR_LAUNCH(ntx_merge_kernel, (int)((R + 31) / 32), dim3(32, 8), 0, stream, part_max, part_sum, tiles, (int)R, row_lse);
   MOLCLR_CHECK_LAUNCH("ntx_merge");
   if (loss) {
-    ntx_loss_kernel<<<1, 1024, 0, stream>>>(row_lse, row_pos, (int)R, 1.0f / (float)Rc, loss);
+    MOLCLR_LAUNCH(ntx_loss_kernel, 1, 1024, 0, stream, row_lse, row_pos, (int)R, 1.0f / (float)Rc, loss);
     MOLCLR_CHECK_LAUNCH("ntx_loss");
   }
   return 0;
@@ -285,7 +290,7 @@ extern "C" int molclr_ntxent_bwd_h(const void* rep16, const void* cols16, int64_
   const long long len4 = (long long)R * C / 4;
   long long blocks = (len4 + 255) / 256;
   if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
-  ntx_sum_partials_kernel<<<(int)blocks, 256, 0, stream>>>(partials, splits, len4, g_rep);
+  MOLCLR_LAUNCH(ntx_sum_partials_kernel, (int)blocks, 256, 0, stream, partials, splits, len4, g_rep);
   MOLCLR_CHECK_LAUNCH("ntx_sum_partials");
   return 0;
 }
@@ -318,11 +323,11 @@ extern "C" int molclr_ntxent_bwd(const float* rep, const float* cols, int64_t R,
       const long long len4 = (long long)R * C / 4;
       long long blocks = (len4 + 255) / 256;
       if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
-      ntx_sum_partials_kernel<<<(int)blocks, 256, 0, stream>>>(partials, splits, len4, g_rep);
+      MOLCLR_LAUNCH(ntx_sum_partials_kernel, (int)blocks, 256, 0, stream, partials, splits, len4, g_rep);
       MOLCLR_CHECK_LAUNCH("ntx_sum_partials");
       return 0;
     }
-    ntx_to_half_t_kernel<<<dim3((unsigned)((Rc + 63) / 64), (unsigned)((C + 31) / 32)), dim3(32, 8), 0, stream>>>(cols, Rc, C, l.ldT, colsT16);
+    MOLCLR_LAUNCH(ntx_to_half_t_kernel, dim3((unsigned)((Rc + 63) / 64), (unsigned)((C + 31) / 32)), dim3(32, 8), 0, stream, cols, Rc, C, l.ldT, colsT16);
     MOLCLR_CHECK_LAUNCH("ntx_to_half_t");
   }
   for (int64_t si = 0; si < ns; ++si) {
@@ -362,7 +367,7 @@ extern "C" int molclr_ntxent_bwd(const float* rep, const float* cols, int64_t R,
   const long long len4 = (long long)R * C / 4;
   long long blocks = (len4 + 255) / 256;
   if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
-  ntx_sum_partials_kernel<<<(int)blocks, 256, 0, stream>>>(partials, (int)ns, len4, g_rep);
+  MOLCLR_LAUNCH(ntx_sum_partials_kernel, (int)blocks, 256, 0, stream, partials, (int)ns, len4, g_rep);
   MOLCLR_CHECK_LAUNCH("ntx_sum_partials");
   return 0;
 }

@@ -51,6 +51,7 @@ struct NtxFusedParams {
 };
 
 __global__ void __launch_bounds__(256) ntx_ecol_kernel(const float* __restrict__ col_lse, long long Rc, long long n, float bound2, float* __restrict__ ecol) {
+  pdl_sync();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < n) ecol[i] = i < Rc ? ptx::ex2_approx(10.f + bound2 - col_lse[i] * 1.4426950408889634f) : 0.f;
 }
@@ -93,6 +94,7 @@ ntx_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();          // barrier set-up and the TMEM allocation above overlap the tail of the previous kernel; global memory only from here
 
   auto block_range = [&](int sp, int& b0, int& b1) {
     b0 = (int)((long long)sp * p.nblocks / p.splits);
@@ -310,7 +312,7 @@ int ntx_bwd_fused(const __half* rep16, const __half* cols16, int ld16, int64_t R
   p.ahead = ahead;
   p.row_lse = row_lse; p.ecol = ecol; p.partials = partials;
   const long long n = (long long)ntx_fused_ecol_floats(Rc);
-  ntx_ecol_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(col_lse, Rc, n, bound2, ecol);
+  MOLCLR_LAUNCH(ntx_ecol_kernel, (int)((n + 255) / 256), 256, 0, stream, col_lse, Rc, n, bound2, ecol);
   MOLCLR_CHECK_LAUNCH("ntx_ecol");
   CUtensorMap tmQ, tmK;
   int rc = gemm_make_tmap_f16(&tmQ, rep16, C, R, ld16, NF_BM);
@@ -325,7 +327,7 @@ int ntx_bwd_fused(const __half* rep16, const __half* cols16, int ld16, int64_t R
   }
   const int total = p.row_tiles * p.splits;
   const int grid = total < sm_count() ? total : sm_count();
-  ntx_bwd_fused_kernel<<<grid, NF_THREADS, NF_SMEM_BYTES, stream>>>(tmQ, tmK, p);
+  MOLCLR_LAUNCH(ntx_bwd_fused_kernel, grid, NF_THREADS, NF_SMEM_BYTES, stream, tmQ, tmK, p);
   MOLCLR_CHECK_LAUNCH("ntx_bwd_fused");
   return 0;
 }

@@ -18,6 +18,7 @@ __global__ void plan_count_kernel(const int64_t* __restrict__ x, const int64_t* 
                                   int64_t N, int64_t E, int64_t G, int32_t* __restrict__ xpacked,
                                   int32_t* __restrict__ node2graph, int32_t* deg_in, int32_t* deg_out,
                                   int32_t* gcount, int32_t* status) {
+  pdl_sync();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int err = 0;
@@ -64,6 +65,7 @@ __device__ __forceinline__ int32_t block_exclusive_scan(int32_t v, int32_t* warp
 }
 
 __global__ void __launch_bounds__(kScanThreads) plan_scan_sums_kernel(ScanJobs jobs) {
+  pdl_sync();
   const ScanJob job = jobs.j[blockIdx.y];
   const int64_t c0 = (int64_t)blockIdx.x * kScanChunk;
   if (c0 >= job.n) return;
@@ -79,6 +81,7 @@ __global__ void __launch_bounds__(kScanThreads) plan_scan_sums_kernel(ScanJobs j
 }
 
 __global__ void __launch_bounds__(1024) plan_scan_offsets_kernel(ScanJobs jobs) {
+  pdl_sync();
   const ScanJob job = jobs.j[blockIdx.x];
   int32_t* bs = jobs.bsum + blockIdx.x * jobs.nb_max;
   const int64_t nb = (job.n + kScanChunk - 1) / kScanChunk;
@@ -93,6 +96,7 @@ __global__ void __launch_bounds__(1024) plan_scan_offsets_kernel(ScanJobs jobs) 
 }
 
 __global__ void __launch_bounds__(kScanThreads) plan_scan_apply_kernel(ScanJobs jobs) {
+  pdl_sync();
   const ScanJob job = jobs.j[blockIdx.y];
   const int64_t c0 = (int64_t)blockIdx.x * kScanChunk;
   if (c0 >= job.n) return;
@@ -113,6 +117,7 @@ __global__ void plan_fill_kernel(const int64_t* __restrict__ ei, int64_t N, int6
                                  const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rowptr_t,
                                  const int32_t* __restrict__ gptr, int32_t* deg_in, int32_t* deg_out,
                                  int32_t* gcount, int32_t* col, int32_t* col_t, int32_t* gperm) {
+  pdl_sync();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = i; e < E; e += stride) {
@@ -142,6 +147,7 @@ __global__ void plan_rows_kernel(const int64_t* __restrict__ ei, const int64_t* 
                                  const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ gptr,
                                  int32_t* col, uint8_t* __restrict__ eattr, int32_t* col_t,
                                  float* __restrict__ cnt, uint32_t* __restrict__ nbr, uint32_t* __restrict__ nbr_t, int32_t* gperm, int32_t* status) {
+  pdl_sync();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t n = i; n < N; n += stride) {
@@ -224,7 +230,7 @@ extern "C" int molclr_plan_build(const int64_t* x, const int64_t* edge_index, co
   int64_t work = N > E ? N : E;
   int blocks = (int)((work + threads - 1) / threads);
   blocks = blocks < 1 ? 1 : (blocks > 8 * sm_count() ? 8 * sm_count() : blocks);
-  plan_count_kernel<<<blocks, threads, 0, stream>>>(x, edge_index, edge_attr, batch, N, E, G, xpacked,
+  MOLCLR_LAUNCH(plan_count_kernel, blocks, threads, 0, stream, x, edge_index, edge_attr, batch, N, E, G, xpacked,
                                                     node2graph, deg_in, deg_out, gcount, status);
   MOLCLR_CHECK_LAUNCH("plan_count");
   ScanJobs jobs;
@@ -234,19 +240,19 @@ extern "C" int molclr_plan_build(const int64_t* x, const int64_t* edge_index, co
   jobs.nb_max = scan_chunks(N > G ? N : G);
   jobs.bsum = gcount + G + 16;
   const dim3 sgrid((unsigned)jobs.nb_max, 3);
-  plan_scan_sums_kernel<<<sgrid, kScanThreads, 0, stream>>>(jobs);
+  MOLCLR_LAUNCH(plan_scan_sums_kernel, sgrid, kScanThreads, 0, stream, jobs);
   MOLCLR_CHECK_LAUNCH("plan_scan_sums");
-  plan_scan_offsets_kernel<<<3, 1024, 0, stream>>>(jobs);
+  MOLCLR_LAUNCH(plan_scan_offsets_kernel, 3, 1024, 0, stream, jobs);
   MOLCLR_CHECK_LAUNCH("plan_scan_offsets");
-  plan_scan_apply_kernel<<<sgrid, kScanThreads, 0, stream>>>(jobs);
+  MOLCLR_LAUNCH(plan_scan_apply_kernel, sgrid, kScanThreads, 0, stream, jobs);
   MOLCLR_CHECK_LAUNCH("plan_scan_apply");
-  plan_fill_kernel<<<blocks, threads, 0, stream>>>(edge_index, N, E, node2graph, rowptr, rowptr_t, gptr,
+  MOLCLR_LAUNCH(plan_fill_kernel, blocks, threads, 0, stream, edge_index, N, E, node2graph, rowptr, rowptr_t, gptr,
                                                    deg_in, deg_out, gcount, col, col_t, gperm);
   MOLCLR_CHECK_LAUNCH("plan_fill");
   int64_t work2 = N > G ? N : G;
   int blocks2 = (int)((work2 + threads - 1) / threads);
   blocks2 = blocks2 < 1 ? 1 : blocks2;
-  plan_rows_kernel<<<blocks2, threads, 0, stream>>>(edge_index, edge_attr, N, E, G, rowptr, rowptr_t, gptr,
+  MOLCLR_LAUNCH(plan_rows_kernel, blocks2, threads, 0, stream, edge_index, edge_attr, N, E, G, rowptr, rowptr_t, gptr,
                                                     col, eattr, col_t, cnt, nbr, nbr_t, gperm, status);
   MOLCLR_CHECK_LAUNCH("plan_rows");
   return 0;

@@ -79,6 +79,7 @@ template <int NCH>
 __global__ void __launch_bounds__(kRowThreads) embed_nodes_fwd_kernel(
     const int32_t* __restrict__ xpacked, const float* __restrict__ E1, const float* __restrict__ E2,
     int N, int D, float* __restrict__ out) {
+  pdl_sync();
   const int lane = threadIdx.x & 31, D4 = D >> 2;
   const int warp = blockIdx.x * kRowWarps + (threadIdx.x >> 5), nwarps = gridDim.x * kRowWarps;
   for (int n = warp; n < N; n += nwarps) {
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_fwd_kernel(
     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const uint8_t* __restrict__ eattr,
     const float* __restrict__ B1, const float* __restrict__ B2, const float* __restrict__ bias, int N, int D,
     float* __restrict__ out, long long ld_out, int round_out, float* __restrict__ out_lo, const DropCfg drop) {
+  pdl_sync();
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* ee = sm4;                       // [15][D4]
@@ -271,6 +273,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) gine_aggregate_fwd_tile_kerne
     const uint32_t* __restrict__ nbr, const float* __restrict__ B1, const float* __restrict__ B2, int N, int D, int T,
     int kTileStages, int store_cs, int blocked, float* __restrict__ out, long long ld_out, int round_out, float* __restrict__ out_lo,
     const DropCfg drop) {
+  pdl_sync();
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* ee = sm4;                                                  // [15][D4]
@@ -418,6 +421,7 @@ __global__ void __launch_bounds__(kRowThreads) gine_aggregate_bwd_kernel(
     const float* __restrict__ ga, const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ col_t,
     const float* __restrict__ z, const float* __restrict__ coef, int relu, int N, int D,
     float* __restrict__ gy, float* __restrict__ partials, int round_out, const DropCfg drop) {
+  pdl_sync();
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* cf = sm4;                          // [4][D4] scale, shift, mean, invstd
@@ -496,6 +500,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) gine_aggregate_bwd_tile_kerne
     const float* __restrict__ ga, const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ col_t,
     const uint32_t* __restrict__ nbr_t, const float* __restrict__ z, const float* __restrict__ coef, int relu, int N, int D, int T,
     int n_stages, float* __restrict__ gy, float* __restrict__ partials, int round_out, const DropCfg drop) {
+  pdl_sync();
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* feat = sm4;                                                // [stages][T][D4]   (reused for the final reduction)
@@ -610,6 +615,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) gine_aggregate_bwd_tile_kerne
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __restrict__ partials, int P, int len,
                                                                float scale, int accumulate, float* __restrict__ out) {
+  pdl_sync();
   __shared__ float red[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
@@ -629,6 +635,7 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const float* __re
 // lane y sums p = y, y + 128, ...; the 128 lane sums are added in lane order.
 __global__ void __launch_bounds__(1024) reduce_partials_tall_kernel(const float* __restrict__ partials, int P, int len,
                                                                     float scale, int accumulate, float* __restrict__ out) {
+  pdl_sync();
   __shared__ float red[128][9];
   const int c = blockIdx.x * 8 + threadIdx.x;
   float s0 = 0.f, s1 = 0.f;
@@ -673,6 +680,7 @@ __device__ __forceinline__ void bn_merge(BnAcc& a, double nb, double mb, double 
 __global__ void __launch_bounds__(512) bn_merge_tiles_kernel(
     const float* __restrict__ tile_stats /* [T][2][D] */, int T, int tile_rows, int N, int D, int per,
     double* __restrict__ ws) {
+  pdl_sync();
   __shared__ double s_n[16][33], s_mean[16][33], s_m2[16][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int t0 = blockIdx.y * per, t1 = min(T, t0 + per);
@@ -699,6 +707,7 @@ __global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(
     const double* __restrict__ ws /* [S][3][D] */, int S, int D,
     const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean, float* running_var,
     long long* num_batches_tracked, float momentum, float eps, float* __restrict__ coef) {
+  pdl_sync();
   const int lane = threadIdx.x & 31, c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c < D) {
     BnAcc a = {0.0, 0.0, 0.0};
@@ -731,6 +740,7 @@ __global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(
 __global__ void bn_eval_coef_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const float* __restrict__ running_mean, const float* __restrict__ running_var,
                                     float eps, int D, float* __restrict__ coef) {
+  pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= D) return;
   const float is = 1.0f / sqrtf(running_var[c] + eps);
@@ -749,6 +759,7 @@ __global__ void __launch_bounds__(512) bn_bwd_finalize_kernel(
     const float* __restrict__ partials /* [P][2][D] */, int P, int N, int D, const float* __restrict__ gamma,
     const float* __restrict__ coef, int use_batch_stats, float* __restrict__ dgamma, float* __restrict__ dbeta,
     float* __restrict__ bcoef /* [3][D] */) {
+  pdl_sync();
   __shared__ float r1[16][33], r2[16][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float s1 = 0.f, s2 = 0.f;
@@ -782,6 +793,7 @@ __global__ void __launch_bounds__(kRowThreads) bn_bwd_apply_kernel(
     const int32_t* __restrict__ gptr, int pool_mode, const int32_t* __restrict__ arg, const float* __restrict__ z,
     const float* __restrict__ bcoef, int N, int D, float* __restrict__ gz, long long ld_gz, float* __restrict__ partials,
     int round_out, const DropCfg drop) {
+  pdl_sync();
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* cf = sm4;                 // [3][D4]
@@ -840,6 +852,7 @@ __global__ void __launch_bounds__(kRowThreads) pool_fwd_kernel(
     const float* __restrict__ z, const float* __restrict__ coef, int relu, const int32_t* __restrict__ gptr,
     const int32_t* __restrict__ gperm, int pool_mode, int G, int D, float* __restrict__ out, long long ld_out, int round_out,
     float* __restrict__ out_lo, int32_t* __restrict__ arg, const DropCfg drop) {
+  pdl_sync();
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* sc = sm4; float4* sh = sm4 + D4;
@@ -914,6 +927,7 @@ __global__ void __launch_bounds__(kRowThreads) pool_bwd_stats_kernel(
     const float* __restrict__ gp, const int32_t* __restrict__ node2graph, const int32_t* __restrict__ gptr,
     int pool_mode, const int32_t* __restrict__ arg, const float* __restrict__ z, const float* __restrict__ coef, int N, int D,
     float* __restrict__ partials, const DropCfg drop) {
+  pdl_sync();
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* cf = sm4;                 // mean, invstd
@@ -959,6 +973,7 @@ template <int NCH>
 __global__ void __launch_bounds__(kRowThreads) bn_apply_fwd_kernel(
     const float* __restrict__ z, const float* __restrict__ coef, int relu, int N, int D, float* __restrict__ hi,
     float* __restrict__ lo, long long ld, int round_hi, const DropCfg drop) {
+  pdl_sync();
   extern __shared__ float4 sm4[];
   const int D4 = D >> 2;
   float4* sc = sm4; float4* sh = sm4 + D4;
@@ -992,6 +1007,7 @@ __global__ void __launch_bounds__(kRowThreads) bn_apply_fwd_kernel(
 template <int NCH>
 __global__ void __launch_bounds__(kRowThreads) bn_tile_stats_kernel(const float* __restrict__ z, int N, int D, int T,
                                                                     float* __restrict__ tile_stats) {
+  pdl_sync();
   const int D4 = D >> 2, lane = threadIdx.x & 31;
   const int warp = blockIdx.x * kRowWarps + (threadIdx.x >> 5), nwarps = gridDim.x * kRowWarps;
   for (int t = warp; t < T; t += nwarps) {
@@ -1031,6 +1047,7 @@ __global__ void __launch_bounds__(kRowThreads) bn_tile_stats_kernel(const float*
 
 // out[r] = sum_c in[r][c] (one warp per row, fixed order): collapses the [8][D] bond-table gradient to the GCN's [8][1].
 __global__ void row_sum_kernel(const float* __restrict__ in, int R, int C, float* __restrict__ out) {
+  pdl_sync();
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= R) return;
   float s = 0.f;
@@ -1045,6 +1062,7 @@ __global__ void row_sum_kernel(const float* __restrict__ in, int R, int C, float
 // gradient (it only ever feeds GEMMs).
 // ------------------------------------------------------------------------------------------------
 __global__ void act_fwd_kernel(const float* __restrict__ x, int mode, int64_t n, float* __restrict__ hi, float* __restrict__ lo) {
+  pdl_sync();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = x[i];
     const float y = mode == 0 ? (v > 20.f ? v : log1pf(expf(v))) : fmaxf(v, 0.f);
@@ -1054,6 +1072,7 @@ __global__ void act_fwd_kernel(const float* __restrict__ x, int mode, int64_t n,
   }
 }
 __global__ void act_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, int mode, int64_t n, float* __restrict__ gx) {
+  pdl_sync();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = x[i];
     const float d = mode == 0 ? (v > 20.f ? 1.f : 1.f / (1.f + expf(-v))) : (v > 0.f ? 1.f : 0.f);
@@ -1063,6 +1082,7 @@ __global__ void act_bwd_kernel(const float* __restrict__ gy, const float* __rest
 
 // The dropout mask itself (0 or 1/(1-p)) as a matrix: what the fused consumers apply.  Test / diagnostics hook.
 __global__ void dropout_mask_kernel(int N, int D, float* __restrict__ out, const DropCfg drop) {
+  pdl_sync();
   const int D4 = D >> 2;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)N * D4; t += (long long)gridDim.x * blockDim.x) {
     const int row = (int)(t / D4), q = (int)(t - (long long)row * D4);
@@ -1074,12 +1094,14 @@ __global__ void dropout_mask_kernel(int N, int D, float* __restrict__ out, const
 // Small elementwise helpers
 // ------------------------------------------------------------------------------------------------
 __global__ void add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, int64_t n4, int64_t n) {
+  pdl_sync();
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t k = i; k < n4; k += stride) st_f4(y + 4 * k, f4_add(*reinterpret_cast<const float4*>(y + 4 * k), ldg_f4(x + 4 * k)));
   for (int64_t k = 4 * n4 + i; k < n; k += stride) y[k] += x[k];
 }
 
 __global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+  pdl_sync();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -1091,6 +1113,7 @@ __global__ void round_tf32_kernel(const float* __restrict__ src, float* __restri
 
 __global__ void round_tf32_2d_kernel(const float* __restrict__ src, long long ld_src, float* __restrict__ hi, float* __restrict__ lo,
                                      long long ld_dst, int rows, int cols) {
+  pdl_sync();
   const long long n = (long long)rows * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
@@ -1103,6 +1126,7 @@ __global__ void round_tf32_2d_kernel(const float* __restrict__ src, long long ld
 // F.normalize(z, dim=1) (molclr.py:63-64; eps = 1e-12): y = z / max(||z||, eps).  One warp per row.
 __global__ void l2_normalize_fwd_kernel(const float* __restrict__ z, int R, int C, float eps, float* __restrict__ y,
                                         float* __restrict__ inv_norm) {
+  pdl_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= R) return;
   float s = 0.f;
@@ -1119,6 +1143,7 @@ __global__ void l2_normalize_fwd_kernel(const float* __restrict__ z, int R, int 
 __global__ void l2_normalize_cat_fwd_kernel(const float* __restrict__ zA, const float* __restrict__ zB, int RA, int RB, int C, float eps,
                                             int normalise, float* __restrict__ y, float* __restrict__ y_r, float* __restrict__ inv_norm,
                                             __half* __restrict__ y16, int ld16) {
+  pdl_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= RA + RB) return;
   const float* z = row < RA ? zA + (size_t)row * C : zB + (size_t)(row - RA) * C;
@@ -1144,6 +1169,7 @@ __global__ void l2_normalize_cat_fwd_kernel(const float* __restrict__ zA, const 
 __global__ void l2_normalize_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ y,
                                         const float* __restrict__ inv_norm, int R, int C, float eps, const float* __restrict__ gscale,
                                         float* __restrict__ gz) {
+  pdl_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= R) return;
   const float gs = gscale ? __ldg(gscale) : 1.f;
@@ -1170,7 +1196,7 @@ extern "C" int molclr_embed_nodes_fwd(const int32_t* xpacked, const float* E1, c
   if (N == 0) return 0;
   NCH_DISPATCH(D / 4, {
     auto k = embed_nodes_fwd_kernel<NCH>;
-    k<<<persistent_grid(k, kRowThreads, 0, kRowWarps, N), kRowThreads, 0, stream>>>(xpacked, E1, E2, (int)N, D, out);
+    MOLCLR_LAUNCH(k, persistent_grid(k, kRowThreads, 0, kRowWarps, N), kRowThreads, 0, stream, xpacked, E1, E2, (int)N, D, out);
   });
   MOLCLR_CHECK_LAUNCH("embed_nodes_fwd");
   return 0;
@@ -1180,11 +1206,11 @@ extern "C" int molclr_reduce_partials(const float* partials, int P, int len, flo
                                       cudaStream_t stream) {
   if (len == 0) return 0;
   if (P >= 1024 && len <= 2048) {      // many partial rows, few columns (bias gradients from per-32-row column sums): 8 columns x 128 lanes per CTA
-    reduce_partials_tall_kernel<<<(len + 7) / 8, dim3(8, 128), 0, stream>>>(partials, P, len, scale, accumulate, out);
+    MOLCLR_LAUNCH(reduce_partials_tall_kernel, (len + 7) / 8, dim3(8, 128), 0, stream, partials, P, len, scale, accumulate, out);
     MOLCLR_CHECK_LAUNCH("reduce_partials");
     return 0;
   }
-  reduce_partials_kernel<<<(len + 31) / 32, dim3(32, 32), 0, stream>>>(partials, P, len, scale, accumulate, out);
+  MOLCLR_LAUNCH(reduce_partials_kernel, (len + 31) / 32, dim3(32, 32), 0, stream, partials, P, len, scale, accumulate, out);
   MOLCLR_CHECK_LAUNCH("reduce_partials");
   return 0;
 }
@@ -1200,7 +1226,7 @@ static void launch_fwd_tile(const float* src, const float* bn_coef, int relu, co
   if (!attr_set) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
   const int64_t ntiles = (N + T - 1) / T;
   const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
-  k<<<grid, kTileThreads, smem, stream>>>(src, bn_coef, relu, rowptr, col, eattr, nbr, B1, B2, (int)N, D, T, stages, g_tile_store_cs, g_tile_blocked, out,
+  MOLCLR_LAUNCH(k, grid, kTileThreads, smem, stream, src, bn_coef, relu, rowptr, col, eattr, nbr, B1, B2, (int)N, D, T, stages, g_tile_store_cs, g_tile_blocked, out,
                                           ld_out, round_out, out_lo, drop);
 }
 
@@ -1231,19 +1257,19 @@ static int aggregate_fwd_launch(const float* src, const float* bn_coef, int relu
   NCH_DISPATCH(D / 4, {
     if (scalar) {
       auto k = gine_aggregate_fwd_kernel<NCH, false, true, false>;
-      k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
+      MOLCLR_LAUNCH(k, persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream,
           src, nullptr, 0, rowptr, col, eattr, B1, B2, bias, (int)N, D, out, ld_out, round_tf32_out, out_lo, drop);
     } else if (bn_coef && drop.thr) {
       auto k = gine_aggregate_fwd_kernel<NCH, true, false, true>;
-      k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
+      MOLCLR_LAUNCH(k, persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream,
           src, bn_coef, relu, rowptr, col, eattr, B1, B2, nullptr, (int)N, D, out, ld_out, round_tf32_out, out_lo, drop);
     } else if (bn_coef) {
       auto k = gine_aggregate_fwd_kernel<NCH, true, false, false>;
-      k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
+      MOLCLR_LAUNCH(k, persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream,
           src, bn_coef, relu, rowptr, col, eattr, B1, B2, nullptr, (int)N, D, out, ld_out, round_tf32_out, out_lo, drop);
     } else {
       auto k = gine_aggregate_fwd_kernel<NCH, false, false, false>;
-      k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(
+      MOLCLR_LAUNCH(k, persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream,
           src, nullptr, 0, rowptr, col, eattr, B1, B2, nullptr, (int)N, D, out, ld_out, round_tf32_out, out_lo, drop);
     }
   });
@@ -1276,7 +1302,7 @@ static int launch_bwd_fused(const float* ga, const int32_t* rowptr_t, const int3
                             cudaStream_t stream) {
   auto k = gine_aggregate_bwd_kernel<NCH, 1, GATHER, DROP>;
   const int grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
-  k<<<grid, kRowThreads, smem, stream>>>(ga, rowptr_t, col_t, z_prev, bn_coef, relu, (int)N, D, gy, partials, round_out, drop);
+  MOLCLR_LAUNCH(k, grid, kRowThreads, smem, stream, ga, rowptr_t, col_t, z_prev, bn_coef, relu, (int)N, D, gy, partials, round_out, drop);
   return grid;
 }
 
@@ -1292,7 +1318,7 @@ static int launch_bwd_tile(const float* ga, const int32_t* rowptr_t, const int32
   if (!attr_set) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set = true; }
   const int64_t ntiles = (N + T - 1) / T;
   const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
-  k<<<grid, kTileThreads, smem, stream>>>(ga, rowptr_t, col_t, nbr_t, z_prev, bn_coef, relu, (int)N, D, T, stages, gy, partials, round_out, drop);
+  MOLCLR_LAUNCH(k, grid, kTileThreads, smem, stream, ga, rowptr_t, col_t, nbr_t, z_prev, bn_coef, relu, (int)N, D, T, stages, gy, partials, round_out, drop);
   return grid;
 }
 
@@ -1326,7 +1352,7 @@ if (gather && drop.thr) grid = launch_bwd_fused<NCH, true, true>(ga, rowptr_t, c
     } else {
       MOLCLR_REQUIRE(gather, "relu_bn_bwd_stats: z_prev is required");
       auto k = gine_aggregate_bwd_kernel<NCH, 0, true, false>;
-      k<<<persistent_grid(k, kRowThreads, 0, kRowWarps, N), kRowThreads, 0, stream>>>(ga, rowptr_t, col_t, nullptr, nullptr, 0,
+      MOLCLR_LAUNCH(k, persistent_grid(k, kRowThreads, 0, kRowWarps, N), kRowThreads, 0, stream, ga, rowptr_t, col_t, nullptr, nullptr, 0,
                                                                                         (int)N, D, gy, nullptr, round_out, drop);
     }
   });
@@ -1367,9 +1393,9 @@ extern "C" int molclr_bn_fwd_finalize(const float* tile_stats, int T, int tile_r
   const int per = (T + S - 1) / S;
   S = (T + per - 1) / per;
   double* ws = reinterpret_cast<double*>(workspace);
-  bn_merge_tiles_kernel<<<dim3((D + 31) / 32, S), dim3(32, 16), 0, stream>>>(tile_stats, T, tile_rows, (int)N, D, per, ws);
+  MOLCLR_LAUNCH(bn_merge_tiles_kernel, dim3((D + 31) / 32, S), dim3(32, 16), 0, stream, tile_stats, T, tile_rows, (int)N, D, per, ws);
   MOLCLR_CHECK_LAUNCH("bn_merge_tiles");
-  bn_fwd_finalize_kernel<<<(D + 7) / 8, 256, 0, stream>>>(ws, S, D, gamma, beta, running_mean, running_var,
+  MOLCLR_LAUNCH(bn_fwd_finalize_kernel, (D + 7) / 8, 256, 0, stream, ws, S, D, gamma, beta, running_mean, running_var,
                                                               reinterpret_cast<long long*>(num_batches_tracked), momentum, eps, coef);
   MOLCLR_CHECK_LAUNCH("bn_fwd_finalize");
   return 0;
@@ -1377,14 +1403,14 @@ extern "C" int molclr_bn_fwd_finalize(const float* tile_stats, int T, int tile_r
 
 extern "C" int molclr_bn_eval_coef(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                                    float eps, int D, float* coef, cudaStream_t stream) {
-  bn_eval_coef_kernel<<<(D + 127) / 128, 128, 0, stream>>>(gamma, beta, running_mean, running_var, eps, D, coef);
+  MOLCLR_LAUNCH(bn_eval_coef_kernel, (D + 127) / 128, 128, 0, stream, gamma, beta, running_mean, running_var, eps, D, coef);
   MOLCLR_CHECK_LAUNCH("bn_eval_coef");
   return 0;
 }
 
 extern "C" int molclr_bn_bwd_finalize(const float* partials, int P, int64_t N, int D, const float* gamma, const float* coef,
                                       int use_batch_stats, float* dgamma, float* dbeta, float* bcoef, cudaStream_t stream) {
-  bn_bwd_finalize_kernel<<<(D + 31) / 32, dim3(32, 16), 0, stream>>>(partials, P, (int)N, D, gamma, coef, use_batch_stats, dgamma,
+  MOLCLR_LAUNCH(bn_bwd_finalize_kernel, (D + 31) / 32, dim3(32, 16), 0, stream, partials, P, (int)N, D, gamma, coef, use_batch_stats, dgamma,
                                                                        dbeta, bcoef);
   MOLCLR_CHECK_LAUNCH("bn_bwd_finalize");
   return 0;
@@ -1410,12 +1436,12 @@ extern "C" int molclr_bn_bwd_apply(const float* gy, const float* gp, const int32
     if (gp) {
       auto k = bn_bwd_apply_kernel<NCH, 1>;
       grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
-      k<<<grid, kRowThreads, smem, stream>>>(nullptr, gp, node2graph, gptr, pool_mode, argmax, z, bcoef, (int)N, D, gz, ld_gz, partials,
+      MOLCLR_LAUNCH(k, grid, kRowThreads, smem, stream, nullptr, gp, node2graph, gptr, pool_mode, argmax, z, bcoef, (int)N, D, gz, ld_gz, partials,
                                              round_tf32_out, drop);
     } else {
       auto k = bn_bwd_apply_kernel<NCH, 0>;
       grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
-      k<<<grid, kRowThreads, smem, stream>>>(gy, nullptr, nullptr, nullptr, 0, nullptr, z, bcoef, (int)N, D, gz, ld_gz, partials,
+      MOLCLR_LAUNCH(k, grid, kRowThreads, smem, stream, gy, nullptr, nullptr, nullptr, 0, nullptr, z, bcoef, (int)N, D, gz, ld_gz, partials,
                                              round_tf32_out, drop);
     }
   });
@@ -1434,7 +1460,7 @@ extern "C" int molclr_pool_fwd(const float* z, const float* bn_coef, int relu, c
   const size_t smem = (size_t)2 * D * sizeof(float);
   NCH_DISPATCH(D / 4, {
     auto k = pool_fwd_kernel<NCH>;
-    k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, G), kRowThreads, smem, stream>>>(z, bn_coef, relu, gptr, gperm,
+    MOLCLR_LAUNCH(k, persistent_grid(k, kRowThreads, smem, kRowWarps, G), kRowThreads, smem, stream, z, bn_coef, relu, gptr, gperm,
                                                                                           pool_mode, (int)G, D, out, ld_out, round_tf32_out, out_lo, argmax,
                                                                                           make_drop(drop_seed, drop_p));
   });
@@ -1454,7 +1480,7 @@ extern "C" int molclr_pool_bwd_stats(const float* gp, const int32_t* node2graph,
   NCH_DISPATCH(D / 4, {
     auto k = pool_bwd_stats_kernel<NCH>;
     const int grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
-    k<<<grid, kRowThreads, smem, stream>>>(gp, node2graph, gptr, pool_mode, argmax, z, bn_coef, (int)N, D, partials, make_drop(drop_seed, drop_p));
+    MOLCLR_LAUNCH(k, grid, kRowThreads, smem, stream, gp, node2graph, gptr, pool_mode, argmax, z, bn_coef, (int)N, D, partials, make_drop(drop_seed, drop_p));
     if (num_partials) *num_partials = grid;
   });
   MOLCLR_CHECK_LAUNCH("pool_bwd_stats");
@@ -1470,7 +1496,7 @@ extern "C" int molclr_bn_apply_fwd(const float* z, const float* bn_coef, int rel
   const size_t smem = (size_t)2 * D * sizeof(float);
   NCH_DISPATCH(D / 4, {
     auto k = bn_apply_fwd_kernel<NCH>;
-    k<<<persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream>>>(z, bn_coef, relu, (int)N, D, hi, lo, ld, round_hi,
+    MOLCLR_LAUNCH(k, persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream, z, bn_coef, relu, (int)N, D, hi, lo, ld, round_hi,
                                                                                           make_drop(drop_seed, bn_coef ? drop_p : 0.f));
   });
   MOLCLR_CHECK_LAUNCH("bn_apply_fwd");
@@ -1483,7 +1509,7 @@ extern "C" int molclr_bn_tile_stats(const float* z, int64_t N, int D, int T, flo
   if (T == 0) return 0;
   NCH_DISPATCH(D / 4, {
     auto k = bn_tile_stats_kernel<NCH>;
-    k<<<persistent_grid(k, kRowThreads, 0, kRowWarps, T), kRowThreads, 0, stream>>>(z, (int)N, D, T, tile_stats);
+    MOLCLR_LAUNCH(k, persistent_grid(k, kRowThreads, 0, kRowWarps, T), kRowThreads, 0, stream, z, (int)N, D, T, tile_stats);
   });
   MOLCLR_CHECK_LAUNCH("bn_tile_stats");
   return 0;
@@ -1495,14 +1521,14 @@ extern "C" int molclr_dropout_mask(uint32_t drop_seed, float drop_p, int64_t N, 
   if (N == 0) return 0;
   int64_t blocks = (N * (D / 4) + 255) / 256;
   if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
-  dropout_mask_kernel<<<(int)blocks, 256, 0, stream>>>((int)N, D, out, make_drop(drop_seed, drop_p));
+  MOLCLR_LAUNCH(dropout_mask_kernel, (int)blocks, 256, 0, stream, (int)N, D, out, make_drop(drop_seed, drop_p));
   MOLCLR_CHECK_LAUNCH("dropout_mask");
   return 0;
 }
 
 extern "C" int molclr_row_sum(const float* in, int R, int C, float* out, cudaStream_t stream) {
   if (R == 0) return 0;
-  row_sum_kernel<<<(R + 7) / 8, 256, 0, stream>>>(in, R, C, out);
+  MOLCLR_LAUNCH(row_sum_kernel, (R + 7) / 8, 256, 0, stream, in, R, C, out);
   MOLCLR_CHECK_LAUNCH("row_sum");
   return 0;
 }
@@ -1520,7 +1546,7 @@ extern "C" int molclr_act_fwd(const float* x, int mode, int64_t n, float* hi, fl
   if (n == 0) return 0;
   int64_t blocks = (n + 255) / 256;
   if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
-  act_fwd_kernel<<<(int)blocks, 256, 0, stream>>>(x, mode, n, hi, lo);
+  MOLCLR_LAUNCH(act_fwd_kernel, (int)blocks, 256, 0, stream, x, mode, n, hi, lo);
   MOLCLR_CHECK_LAUNCH("act_fwd");
   return 0;
 }
@@ -1530,7 +1556,7 @@ extern "C" int molclr_act_bwd(const float* gy, const float* x, int mode, int64_t
   if (n == 0) return 0;
   int64_t blocks = (n + 255) / 256;
   if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
-  act_bwd_kernel<<<(int)blocks, 256, 0, stream>>>(gy, x, mode, n, gx);
+  MOLCLR_LAUNCH(act_bwd_kernel, (int)blocks, 256, 0, stream, gy, x, mode, n, gx);
   MOLCLR_CHECK_LAUNCH("act_bwd");
   return 0;
 }
@@ -1539,7 +1565,7 @@ extern "C" int molclr_round_tf32(const float* src, float* dst, float* lo, int64_
   if (n == 0) return 0;
   int64_t blocks = (n + 1023) / 1024;
   if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
-  round_tf32_kernel<<<(int)blocks, 256, 0, stream>>>(src, dst, lo, n);
+  MOLCLR_LAUNCH(round_tf32_kernel, (int)blocks, 256, 0, stream, src, dst, lo, n);
   MOLCLR_CHECK_LAUNCH("round_tf32");
   return 0;
 }
@@ -1549,14 +1575,14 @@ extern "C" int molclr_round_tf32_2d(const float* src, int64_t ld_src, float* hi,
   if (rows * cols == 0) return 0;
   int64_t blocks = (rows * cols + 1023) / 1024;
   if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
-  round_tf32_2d_kernel<<<(int)blocks, 256, 0, stream>>>(src, ld_src, hi, lo, ld_dst, (int)rows, (int)cols);
+  MOLCLR_LAUNCH(round_tf32_2d_kernel, (int)blocks, 256, 0, stream, src, ld_src, hi, lo, ld_dst, (int)rows, (int)cols);
   MOLCLR_CHECK_LAUNCH("round_tf32_2d");
   return 0;
 }
 
 extern "C" int molclr_l2_normalize_fwd(const float* z, int64_t R, int C, float eps, float* y, float* inv_norm, cudaStream_t stream) {
   if (R == 0) return 0;
-  l2_normalize_fwd_kernel<<<(int)((R + 7) / 8), 256, 0, stream>>>(z, (int)R, C, eps, y, inv_norm);
+  MOLCLR_LAUNCH(l2_normalize_fwd_kernel, (int)((R + 7) / 8), 256, 0, stream, z, (int)R, C, eps, y, inv_norm);
   MOLCLR_CHECK_LAUNCH("l2_normalize_fwd");
   return 0;
 }
@@ -1564,7 +1590,7 @@ extern "C" int molclr_l2_normalize_fwd(const float* z, int64_t R, int C, float e
 extern "C" int molclr_l2_normalize_bwd(const float* gy, const float* y, const float* inv_norm, int64_t R, int C, float eps, float* gz,
                                        cudaStream_t stream) {
   if (R == 0) return 0;
-  l2_normalize_bwd_kernel<<<(int)((R + 7) / 8), 256, 0, stream>>>(gy, y, inv_norm, (int)R, C, eps, nullptr, gz);
+  MOLCLR_LAUNCH(l2_normalize_bwd_kernel, (int)((R + 7) / 8), 256, 0, stream, gy, y, inv_norm, (int)R, C, eps, nullptr, gz);
   MOLCLR_CHECK_LAUNCH("l2_normalize_bwd");
   return 0;
 }
@@ -1572,7 +1598,7 @@ extern "C" int molclr_l2_normalize_bwd(const float* gy, const float* y, const fl
 extern "C" int molclr_l2_normalize_bwd_scaled(const float* gy, const float* y, const float* inv_norm, int64_t R, int C, float eps,
                                               const float* gscale, float* gz, cudaStream_t stream) {
   if (R == 0) return 0;
-  l2_normalize_bwd_kernel<<<(int)((R + 7) / 8), 256, 0, stream>>>(gy, y, inv_norm, (int)R, C, eps, gscale, gz);
+  MOLCLR_LAUNCH(l2_normalize_bwd_kernel, (int)((R + 7) / 8), 256, 0, stream, gy, y, inv_norm, (int)R, C, eps, gscale, gz);
   MOLCLR_CHECK_LAUNCH("l2_normalize_bwd_scaled");
   return 0;
 }
@@ -1582,7 +1608,7 @@ extern "C" int molclr_ntxent_rows_fwd(const float* zA, const float* zB, int64_t 
   MOLCLR_REQUIRE((y_r != nullptr || y16 != nullptr) && RA >= 0 && RB >= 0 && RA + RB < (1ll << 31), "ntxent_rows_fwd: bad arguments");
   MOLCLR_REQUIRE(y16 == nullptr || (ld16 >= C && ld16 % 8 == 0), "ntxent_rows_fwd: ld16 must be >= C and a multiple of 8 halves");
   if (RA + RB == 0) return 0;
-  l2_normalize_cat_fwd_kernel<<<(int)((RA + RB + 7) / 8), 256, 0, stream>>>(zA, zB, (int)RA, (int)RB, C, eps, normalise, y, y_r, inv_norm,
+  MOLCLR_LAUNCH(l2_normalize_cat_fwd_kernel, (int)((RA + RB + 7) / 8), 256, 0, stream, zA, zB, (int)RA, (int)RB, C, eps, normalise, y, y_r, inv_norm,
                                                                           reinterpret_cast<__half*>(y16), (int)ld16);
   MOLCLR_CHECK_LAUNCH("ntxent_rows_fwd");
   return 0;
@@ -1594,7 +1620,7 @@ extern "C" int molclr_add_inplace(float* y, const float* x, int64_t n, cudaStrea
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
   if (blocks < 1) blocks = 1;
-  add_inplace_kernel<<<(int)blocks, 256, 0, stream>>>(y, x, n / 4, n);
+  MOLCLR_LAUNCH(add_inplace_kernel, (int)blocks, 256, 0, stream, y, x, n / 4, n);
   MOLCLR_CHECK_LAUNCH("add_inplace");
   return 0;
 }

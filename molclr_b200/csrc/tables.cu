@@ -19,6 +19,7 @@ struct WeightBatch { molclr_weight_desc d[kWeightBatch]; };
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 __global__ void __launch_bounds__(256) prepare_weights_kernel(const __grid_constant__ WeightBatch wb) {
+  pdl_sync();
   const molclr_weight_desc& d = wb.d[blockIdx.y];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   if (d.hi || d.lo) {
@@ -67,6 +68,7 @@ constexpr int kTabUnroll = 6;
 // lane ty takes rows r0 + ty, r0 + ty + RY, ... in increasing order (registers); the RY lane sums are then added in lane order.
 __global__ void __launch_bounds__(384, 2) class_weighted_colsum_kernel(const float* __restrict__ g, long long ld_g, const float* __restrict__ w,
                                                                      int N, int D, int rows_per_block, float* __restrict__ partials) {
+  pdl_sync();
   extern __shared__ float red[];          // [RY][8][D], then the weight rows of the current tile: [RY * U][8]
   const int tx = threadIdx.x, ty = threadIdx.y, D4 = D >> 2, RY = blockDim.y;
   const int tid = ty * blockDim.x + tx, nth = blockDim.x * blockDim.y;
@@ -123,6 +125,7 @@ __global__ void __launch_bounds__(384, 2) class_weighted_colsum_kernel(const flo
 constexpr int kOhChunk = 128, kOhRY = 4, kOhUnroll = 16, kOhMaxCW = 384;
 __global__ void __launch_bounds__(512, 1) onehot_colsum_kernel(const float* __restrict__ g, long long ld_g, const int32_t* __restrict__ key,
                                                              int N, int D, int CW, int chunks_per_block, float* __restrict__ partials) {
+  pdl_sync();
   extern __shared__ float sm[];
   float* tile = sm;                                        // [119][CW]
   float* spill = tile + (size_t)kNumAtomType * CW;         // [RY][CW]
@@ -246,7 +249,7 @@ extern "C" int molclr_prepare_weights(const molclr_weight_desc* descs, int n, cu
     int bx = (int)((biggest + 256 * 4 - 1) / (256 * 4));
     if (bx < 1) bx = 1;
     if (bx > 64) bx = 64;
-    prepare_weights_kernel<<<dim3((unsigned)bx, (unsigned)m, 1), 256, 0, stream>>>(wb);
+    MOLCLR_LAUNCH(prepare_weights_kernel, dim3((unsigned)bx, (unsigned)m, 1), 256, 0, stream, wb);
     MOLCLR_CHECK_LAUNCH("prepare_weights");
   }
   return 0;
@@ -273,7 +276,7 @@ extern "C" int molclr_edge_table_grad(const float* ga, int64_t ld_ga, const floa
     if (e != cudaSuccess) return cuda_fail(e, "edge_table_grad: cudaFuncSetAttribute");
     attr_set = true;
   }
-  class_weighted_colsum_kernel<<<used, dim3((unsigned)tx, (unsigned)ry, 1), smem, stream>>>(ga, ld_ga, cnt, (int)N, D, rpb, partials);
+  MOLCLR_LAUNCH(class_weighted_colsum_kernel, used, dim3((unsigned)tx, (unsigned)ry, 1), smem, stream, ga, ld_ga, cnt, (int)N, D, rpb, partials);
   MOLCLR_CHECK_LAUNCH("edge_table_grad");
   return molclr_reduce_partials(partials, used, 8 * D, 1.f, 0, dB, stream);
 }
@@ -306,7 +309,7 @@ extern "C" int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, in
   float* partials = reinterpret_cast<float*>(workspace);
   int tx = (CW / 4 + 31) / 32 * 32;
   if (tx * kOhRY < kOhChunk) tx = kOhChunk / kOhRY;                       // the first 128 threads load / rank the chunk's keys
-  onehot_colsum_kernel<<<dim3((unsigned)used, (unsigned)slices, 1), dim3((unsigned)tx, kOhRY, 1), smem, stream>>>(
+  MOLCLR_LAUNCH(onehot_colsum_kernel, dim3((unsigned)used, (unsigned)slices, 1), dim3((unsigned)tx, kOhRY, 1), smem, stream,
       g, ld_g, xpacked, (int)N, D, CW, cpb, partials);
   MOLCLR_CHECK_LAUNCH("embed_nodes_bwd");
   return molclr_reduce_partials(partials, used, (kNumAtomType + kNumChirality) * D, 1.f, 0, dE, stream);
