@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="molecule pairs per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=512, help="pairs per step of the CPU baseline sample")
-    ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "tf32"])
+    ap.add_argument("--precision", default=None, choices=["fp16x3", "tf32x3", "tf32"], help="default: the package default (molclr_b200.GINet.precision)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the few-step measurements of BASELINE configs 1 (on the GPU), 3 and 4")
     ap.add_argument("--local-negatives", action="store_true", help="N>1: NT-Xent over the local batch only")
@@ -199,6 +199,8 @@ def run_ours(args):
 
     torch.manual_seed(0)
     model = (GINet if args.model == "gin" else GCN)(5, 300, 512, 0, "mean").to(dev)
+    if args.precision is None:
+        args.precision = model.precision
     model.precision = args.precision
     if world > 1:
         from molclr_b200.dist import DataParallelStep
@@ -481,12 +483,15 @@ def extra_configs(args, dev):
         ms = timed(step)
         return {"graphs_per_s": G / (ms * 1e-3), "ms_per_step": ms, "graphs": G, "nodes": int(data[0].x.size(0)), "drop_ratio": drop}
 
-    out = {"config1_gpu_512_pairs": pretrain(GINet, 512, "tf32x3"),
-           "config3_gcn_4096_pairs": pretrain(GCN, 4096, "tf32x3"),
+    P = args.precision
+    other = "tf32x3" if P == "fp16x3" else "fp16x3"       # the other form of the compensated forward products
+    out = {"config1_gpu_512_pairs": pretrain(GINet, 512, P),
+           "config3_gcn_4096_pairs": pretrain(GCN, 4096, P),
            "config2_precision_tf32": pretrain(GINet, 4096, "tf32"),
+           f"config2_precision_{other}": pretrain(GINet, 4096, other),
            # A/B of programmatic dependent launch: the same steps with plain stream-ordered launches
-           "config1_gpu_512_pairs_plain_launches": pretrain(GINet, 512, "tf32x3", pdl=False),
-           "config2_plain_launches": pretrain(GINet, 4096, "tf32x3", pdl=False),
+           "config1_gpu_512_pairs_plain_launches": pretrain(GINet, 512, P, pdl=False),
+           "config2_plain_launches": pretrain(GINet, 4096, P, pdl=False),
            "config4_finetune_bbbp_cls_drop0": finetune("classification", 46.0, 18.0, 0.0),
            "config4_finetune_bbbp_cls_drop0.3": finetune("classification", 46.0, 18.0, 0.3),
            "config4_finetune_esol_reg_drop0": finetune("regression", 26.0, 13.0, 0.0),

@@ -29,7 +29,7 @@ extern "C" {
 typedef struct CUstream_st* cudaStream_t;
 #endif
 
-#define MOLCLR_ABI_VERSION 2
+#define MOLCLR_ABI_VERSION 3
 
 /* ---- library ------------------------------------------------------------------------------- */
 int molclr_abi_version(void);
@@ -250,14 +250,28 @@ typedef struct {
   int32_t compensate;         /* 1: A and B are UNROUNDED fp32, both K-major, A_lo = B_lo = NULL: ~fp32-accurate product with
                                  every low half derived on chip -- pass 1 in TF32 on the raw tiles (the tensor core truncates),
                                  the corrections (A - trunc A) * B and A * (B - trunc B) as kind::f16 MMAs on bf16 tiles the
-                                 kernel forms in shared memory (their 2^-9 rounding applies to terms 2^-10 of the product)    */
+                                 kernel forms in shared memory (their 2^-9 rounding applies to terms 2^-10 of the product).
+                                 2: the fp16 three-product form of the same product: A (unrounded fp32, K-major) is split on chip
+                                 into fp16(a) and fp16(a - fp16(a)) -- 22 significand bits --, B16 (mandatory, b16_kind = 1 of
+                                 molclr_prepare_weights) holds B split the same way, B itself is not read (may be NULL), and the
+                                 product runs as A_h B_h + A_l B_h + A_h B_l in three kind::f16 MMAs: 3/4 of the tensor time and
+                                 2/3 of the operand bytes of form 1, smaller rounding error (hi halves rounded, not truncated;
+                                 11-bit corrections).  Price: fp16's RANGE.  |a| > 65504 is clamped (the result is then wrong)
+                                 and reported through `status`; |a| < 6e-5 keeps an absolute error of 3e-8 (relative accuracy
+                                 degrades gracefully towards TF32's as a whole row of A falls below ~1e-3).  The activations of
+                                 the path (BatchNorm outputs and their neighbourhood sums) sit in the middle of that range.   */
   const void* B16;            /* compensate = 1, optional: the bf16 correction tiles of B pre-split once per optimizer step by
                                  molclr_prepare_weights -- bf16 [2][rows16][ld16]: bf16(B) then bf16(B - trunc_tf32(B)), zero padded;
                                  TMA then lands them in shared memory and the converter warps touch A only (B is a WEIGHT on every
                                  compensated product of the path: it does not change between the row tiles of a launch, nor
                                  between the launches of a step)                                                               */
   int64_t ld16, rows16;       /* row pitch (bf16 elements, % 8 == 0) and rows per half (>= N rounded up to 256)               */
+  int32_t* status;            /* compensate = 2, optional: device word; MOLCLR_STATUS_FP16_RANGE is OR-ed in (sticky) when an
+                                 element of A exceeded fp16's finite range                                                     */
 } molclr_gemm_args;
+#define MOLCLR_STATUS_FP16_RANGE 1
+#define MOLCLR_H16_SCALE 64   /* the fp16 tiles of a weight hold 2^6 W: the low halves of typical weights (1e-3 .. 1) stay normal
+                                 fp16 numbers, |W| up to 1023 stays finite; the GEMM epilogue multiplies by 2^-6 (exact)          */
 /* column statistics are emitted per group of molclr_gemm_colstat_tile_rows() (= 32) consecutive rows;
  * molclr_gemm_colstat_tiles(M) groups are written (a multiple of 4; trailing groups may be empty). */
 int molclr_gemm_colstat_tiles(int64_t M);
@@ -290,7 +304,8 @@ int molclr_gemm_dw_ordered(const float* dY, int64_t ldy, const float* X, int64_t
  *   hi_t [cols][ld_hi_t] = tf32(W^T)         (dX = dY W reads W^T K-major: column tiles of any multiple of 8 instead of whole
  *                                             32-column blocks, i.e. 6 - 12 % instead of 22 - 28 % padded tensor work at N = 300 / 600)
  *   raw [rows_t][ld_raw] = W or W^T (transpose_raw: K-major copy of a weight stored [in][out]), unrounded, 128-byte rows
- *   b16 [2][rows16][ld16] bf16 = bf16(raw), bf16(raw - trunc_tf32(raw)), zero padded (see molclr_gemm_args.B16)
+ *   b16 [2][rows16][ld16] bf16 = bf16(raw), bf16(raw - trunc_tf32(raw)), zero padded (see molclr_gemm_args.B16);
+ *       with b16_kind = 1: fp16 instead -- h = fp16(2^6 raw), fp16(2^6 raw - h) (molclr_gemm_args.compensate = 2)
  * Any output pointer may be NULL.  Padding columns (up to the row pitch) are written as zeros. */
 typedef struct {
   const float* src; int64_t ld_src; int32_t rows, cols;
@@ -298,6 +313,7 @@ typedef struct {
   float* hi_t; int64_t ld_hi_t;                 /* tf32(W^T) [cols][ld_hi_t]: the K-major B operand of the backward dX product */
   float* raw; int64_t ld_raw; int32_t transpose_raw;
   void* b16; int64_t ld16; int32_t rows16;
+  int32_t b16_kind;                             /* 0: bf16 correction tiles; 1: fp16 halves of 2^6 W */
 } molclr_weight_desc;
 int molclr_prepare_weights(const molclr_weight_desc* descs /* host */, int n, cudaStream_t stream);
 
@@ -327,6 +343,7 @@ typedef struct {
   const float* wf_hi; const float* wf_lo; const float* bf;          /* feat_lin [F][D] */
   const float* w0_hi; const float* w0_lo; const float* b0;          /* out_lin.0 [F][F] */
   const float* w2_hi; const float* w2_lo; const float* b2;          /* out_lin.2 [F/2][F] */
+  int32_t* status;                                                  /* optional device word: see molclr_gemm_args.status (comp = 2) */
 } molclr_gin_model;
 typedef struct {                       /* the outputs of molclr_plan_build */
   int64_t N, E, G;
@@ -340,7 +357,8 @@ size_t molclr_gin_scratch_bytes(const molclr_gin_model* m, int64_t N, int64_t G,
  * (mlp.0.weight, mlp.0.bias, mlp.2.weight, mlp.2.bias, edge_embedding1, edge_embedding2, bn.weight, bn.bias), feat_lin.weight,
  * .bias, out_lin.0.weight, .bias, out_lin.2.weight, .bias */
 int64_t molclr_gin_grad_layout(const molclr_gin_model* m, int64_t* offsets);
-/* comp: 1 = error-compensated forward products ("tf32x3"); drop_seeds (host) [L] + drop_p: dropout (NULL / 0 = none) */
+/* comp: 1 = error-compensated forward products, TF32 pass + bf16 corrections ("tf32x3"); 2 = the same products in the fp16
+ * three-product form ("fp16x3": w1_b16 / w2_b16 are then the fp16 tiles, b16_kind = 1); drop_seeds (host) [L] + drop_p: dropout (NULL / 0 = none) */
 int molclr_gin_encoder_fwd(const molclr_gin_model* m, const molclr_plan_view* plan, int comp, int training, int pool_mode,
                            const uint32_t* drop_seeds, float drop_p, void* ctx, size_t ctx_bytes, void* scratch, size_t scratch_bytes,
                            cudaStream_t stream);

@@ -12,7 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MOLCLR_B200_LIB") or os.path.join(_HERE, "libmolclr_b200.so")   # (override: A/B timing of builds)
 
 vp, i64, i32, f32, sz, u32 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t, C.c_uint32
-ABI_VERSION = 2        # MOLCLR_ABI_VERSION of include/molclr_b200.h
+STATUS_FP16_RANGE = 1  # MOLCLR_STATUS_FP16_RANGE
+ABI_VERSION = 3        # MOLCLR_ABI_VERSION of include/molclr_b200.h
 
 
 class GemmArgs(C.Structure):
@@ -33,7 +34,7 @@ class GemmArgs(C.Structure):
         ("split_k", C.c_int32),
         ("relu_bits", vp), ("mask_bits", vp), ("ld_bits", i64),
         ("compensate", C.c_int32),
-        ("B16", vp), ("ld16", i64), ("rows16", i64),
+        ("B16", vp), ("ld16", i64), ("rows16", i64), ("status", vp),
     ]
 
 
@@ -44,7 +45,7 @@ class WeightDesc(C.Structure):
         ("hi", vp), ("lo", vp), ("ld_hi", i64),
         ("hi_t", vp), ("ld_hi_t", i64),
         ("raw", vp), ("ld_raw", i64), ("transpose_raw", C.c_int32),
-        ("b16", vp), ("ld16", i64), ("rows16", C.c_int32),
+        ("b16", vp), ("ld16", i64), ("rows16", C.c_int32), ("b16_kind", C.c_int32),
     ]
 
 
@@ -62,7 +63,8 @@ class GinModel(C.Structure):
     """Mirror of ``molclr_gin_model``."""
     _fields_ = [("num_layer", C.c_int32), ("emb_dim", C.c_int32), ("feat_dim", C.c_int32), ("x_emb1", vp), ("x_emb2", vp),
                 ("layers", C.POINTER(GinLayer)), ("w1_ld16", i64), ("w1_rows16", i64), ("w2_ld16", i64), ("w2_rows16", i64),
-                ("wf_hi", vp), ("wf_lo", vp), ("bf", vp), ("w0_hi", vp), ("w0_lo", vp), ("b0", vp), ("w2_hi", vp), ("w2_lo", vp), ("b2", vp)]
+                ("wf_hi", vp), ("wf_lo", vp), ("bf", vp), ("w0_hi", vp), ("w0_lo", vp), ("b0", vp), ("w2_hi", vp), ("w2_lo", vp), ("b2", vp),
+                ("status", vp)]
 
 
 class PlanView(C.Structure):

@@ -41,7 +41,9 @@ static int gemm_workers(bool pair) { return pair ? sm_count() / 2 : sm_count(); 
 // TWO = CTA pair (cluster of 2, tcgen05 cta_group::2): the pair computes a 256 x BN tile; each CTA stages its own 128 rows
 // of A and HALF of the B tile, which cuts the L2 -> shared-memory traffic that bounds these loops (the weights are
 // re-read per row tile) by 28..45%.
-template <int BN, bool FOUR, bool TWO>
+// H3 (with FOUR) = the fp16 three-product form of the compensated product: stage = [A fp32][A_h16 | A_l16][B_h16 | B_l16], no fp32 B tile
+// (see K_PLAIN_H3 below).
+template <int BN, bool FOUR, bool TWO, bool H3 = false>
 struct GemmCfg {
   static constexpr int BK = FOUR ? GEMM_BK4 : GEMM_BK;
   // BN = 320 ("wide", split-K weight gradients on CTA pairs only): the tile is covered by two MMAs per K slice, N1 = 256
@@ -51,7 +53,8 @@ struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * BK * 4;
   static constexpr int B_BYTES = BN_CTA * BK * 4;
   static constexpr int MN_BLOCK_BYTES = 32 * BK * 4;      // one [BK k][32 mn] block of an MN-major operand
-  static constexpr int STAGE_BYTES = (FOUR ? 2 : 1) * (A_BYTES + B_BYTES);
+  static constexpr int STAGE_BYTES = H3 ? 2 * A_BYTES + B_BYTES : (FOUR ? 2 : 1) * (A_BYTES + B_BYTES);
+  static_assert(!H3 || FOUR, "H3 is a form of the compensated (FOUR) product");
   // epilogue column chunk staged per warp, and its pitch in floats (conflict-free float4 rows); the 72 KB stages of
   // the compensated product leave room for four warps with 16-column chunks only
   static constexpr bool SMALL_EPI = FOUR && (GEMM_SMEM_LIMIT - 8 * 32 * 32 * 4 - 512 - 2048) / STAGE_BYTES < 3;
@@ -218,18 +221,26 @@ __device__ __forceinline__ void colstat_regs(const float (&v)[32], int rows, int
 // STAGES-deep smem ring; accumulators are double-buffered in TMEM so the epilogue warps drain tile i while the
 // tensor core works on tile i+1.
 // KIND selects the epilogue at compile time so that each variant is a short, branch-free loop:
-enum : int { K_PLAIN = 0, K_LATE = 1, K_NTX_W = 2, K_NTX_FWD = 3, K_ATOMIC = 4, K_PLAIN16 = 5, K_NTX_W16 = 6, K_NTX_FWD16 = 7 };
+// K_PLAIN_H3 (compensate = 2): the plain epilogue on the fp16 three-product compensated main loop -- A is split on chip into
+// fp16(x) and fp16(x - fp16(x)) (22 significand bits), B arrives pre-split the same way (molclr_prepare_weights, scaled by 2^6 so
+// that the low halves of typical weights stay normal fp16 numbers; the epilogue's alpha undoes it), and the product is
+// A_h B_h + A_l B_h + A_h B_l as three kind::f16 MMAs per K = 16: 3/4 of the tensor time and 2/3 of the L2 -> shared-memory
+// bytes of the TF32 + bf16 form (no fp32 B tile), one more ring stage, and a smaller rounding error (hi halves rounded to
+// nearest instead of truncated, 11-bit instead of 8-bit corrections).  Price: fp16's range -- see molclr_gemm_args.compensate.
+enum : int { K_PLAIN = 0, K_LATE = 1, K_NTX_W = 2, K_NTX_FWD = 3, K_ATOMIC = 4, K_PLAIN16 = 5, K_NTX_W16 = 6, K_NTX_FWD16 = 7, K_PLAIN_H3 = 8 };
 
 template <int BN, bool FOUR, int KIND, bool TWO>
-__global__ void __launch_bounds__(GemmCfg<BN, FOUR, TWO>::THREADS, 1)
+__global__ void __launch_bounds__(GemmCfg<BN, FOUR, TWO, KIND == K_PLAIN_H3>::THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmO,
                  const GemmParams p) {
-  using Cfg = GemmCfg<BN, FOUR, TWO>;
+  constexpr bool H3 = KIND == K_PLAIN_H3;
+  using Cfg = GemmCfg<BN, FOUR, TWO, H3>;
   // fp16-operand instances (K-major tiles of 64 halves per 128-byte row, kind::f16 MMAs) share the epilogue of their TF32 kind
-  constexpr bool H16 = KIND >= K_PLAIN16;
-  constexpr int EK = KIND == K_PLAIN16 ? K_PLAIN : KIND == K_NTX_W16 ? K_NTX_W : KIND == K_NTX_FWD16 ? K_NTX_FWD : KIND;
+  constexpr bool H16 = KIND >= K_PLAIN16 && !H3;
+  constexpr int EK = (KIND == K_PLAIN16 || H3) ? K_PLAIN : KIND == K_NTX_W16 ? K_NTX_W : KIND == K_NTX_FWD16 ? K_NTX_FWD : KIND;
   static_assert(!(H16 && FOUR), "fp16 operands: single-pass instances only");
+  static_assert(!H3 || FOUR, "the fp16 three-product form is a compensated (FOUR) instance");
   extern __shared__ __align__(1024) uint8_t smem[];
   float* staging = reinterpret_cast<float*>(smem + Cfg::PIPE_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::PIPE_BYTES + Cfg::STAGING_BYTES);
@@ -246,7 +257,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // derive_lo == 2 ("mixed"): A and B are both UNROUNDED fp32, K-major; stage = [A][A_hi16|A_lo16][B][B_hi16|B_lo16]: the tensor core
   // truncates the raw tiles for the TF32 pass, the converter warps form bf16(x) and bf16(x - trunc_tf32(x)) of both tiles for the
   // two correction passes, which run as kind::f16 MMAs -- no rounded or split copy of either operand is ever read from HBM / L2
-  const bool mixed = FOUR && p.derive_lo == 2;
+  const bool mixed = H3 || (FOUR && p.derive_lo == 2);     // (H3: as mixed, without an fp32 B tile; the B16 tiles are mandatory)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = p.n_tiles, m_tiles = p.m_tiles;
@@ -299,7 +310,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // derive_lo: the fp32 A tile goes to a CTA-local barrier (the converter warps of THIS CTA consume it) and no A_lo is loaded
             // mixed: both raw tiles go to the CTA-local barrier and the MMA issuer waits for the converters only
             if (rank == 0 && !mixed) ptx::mbar_arrive_expect_tx(full_bar + s, derive ? (TWO ? 2 : 1) * 2 * Cfg::B_BYTES : Cfg::TX_BYTES);
-            if (derive) ptx::mbar_arrive_expect_tx(afull_bar + s, mixed ? Cfg::A_BYTES + Cfg::B_BYTES + (p.b_presplit ? Cfg::B_BYTES : 0) : Cfg::A_BYTES);
+            if (derive)
+              ptx::mbar_arrive_expect_tx(afull_bar + s, H3 ? Cfg::A_BYTES + Cfg::B_BYTES
+                                                           : mixed ? Cfg::A_BYTES + Cfg::B_BYTES + (p.b_presplit ? Cfg::B_BYTES : 0) : Cfg::A_BYTES);
             const uint32_t fb = TWO ? ptx::mapa(ptx::smem_u32(full_bar + s), 0u) : 0u;     // the leader's barrier
             auto load = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
               if (TWO) ptx::tma_load_2d_2cta(dst, m, fb, c0, c1); else ptx::tma_load_2d(dst, m, full_bar + s, c0, c1);
@@ -329,10 +342,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int j = 0; j < GEMM_BM / 32; ++j) load(ad + j * Cfg::MN_BLOCK_BYTES, ma, m0 + 32 * j, kc);
               if (mixed) {
                 if (h == 0) {
-                  ptx::tma_load_2d(bd, &tmB, afull_bar + s, kc, n0);
-                  if (p.b_presplit) {      // bf16(B) and bf16(B - trunc B) tiles (rows of 32 bf16 = 64 bytes, 64-byte swizzle), pre-split once per step
-                    ptx::tma_load_2d(bd + Cfg::B_BYTES, &tmB2, afull_bar + s, kc, n0);
-                    ptx::tma_load_2d(bd + Cfg::B_BYTES + Cfg::B_BYTES / 2, &tmB2, afull_bar + s, kc, p.rows16 + n0);
+                  if (!H3) ptx::tma_load_2d(bd, &tmB, afull_bar + s, kc, n0);
+                  if (H3 || p.b_presplit) {
+                    // the two 16-bit tiles of B (rows of 32 elements = 64 bytes, 64-byte swizzle), pre-split once per step: bf16(B) and
+                    // bf16(B - trunc B) behind the fp32 tile, or (H3) fp16(s B) and fp16(s B - hi) in its place
+                    uint8_t* b16d = H3 ? bd : bd + Cfg::B_BYTES;
+                    ptx::tma_load_2d(b16d, &tmB2, afull_bar + s, kc, n0);
+                    ptx::tma_load_2d(b16d + Cfg::B_BYTES / 2, &tmB2, afull_bar + s, kc, p.rows16 + n0);
                   }
                 }
               } else if (!p.b_mn) load(bd, mb, kc, n0);
@@ -368,6 +384,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t idesc = h16 ? ptx::make_idesc_f16(Cfg::N1, TILE_M) : ptx::make_idesc_tf32(Cfg::N1, p.a_mn != 0, p.b_mn != 0, TILE_M);
       const uint32_t idesc2 = ptx::make_idesc_tf32(Cfg::N2 > 0 ? Cfg::N2 : 16, p.a_mn != 0, p.b_mn != 0, TILE_M);
       const uint32_t idesc16 = ptx::make_idesc_bf16(Cfg::N1, TILE_M);
+      const uint32_t idesc_h3 = ptx::make_idesc_f16(Cfg::N1, TILE_M);
       auto mma_i = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
         if (h16) { if (TWO) ptx::mma_f16_ss_2cta(d, a, b, id, acc); else ptx::mma_f16_ss(d, a, b, id, acc); }
         else if (TWO) ptx::mma_tf32_ss_2cta(d, a, b, id, acc); else ptx::mma_tf32_ss(d, a, b, id, acc);
@@ -418,6 +435,30 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // mixed: the TF32 pass reads only the raw tiles, so it is issued as soon as they have LANDED in both CTAs (raw_bar) and runs on
           // the tensor pipe while the converter warps are still forming the bf16 tiles of the same stage; the correction passes wait
           // for conv_bar.  Same instruction order as issuing all eight after the conversion: bit-identical results.
+          if constexpr (H3) {
+            // fp16 three-product form: every MMA reads converted tiles, K = 16 (32 bytes of the 64-byte-swizzle rows) per instruction
+            ptx::mbar_wait(conv_bar + s, (it / Cfg::STAGES) & 1);
+            ptx::tc_fence_after();
+            const uint32_t a16 = smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES, b16 = a16 + Cfg::A_BYTES;
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int k = 0; k < Cfg::BK / 16; ++k) {
+                const uint64_t ah = h_d0 + ((a16 + k * 32u) >> 4), al = ah + (Cfg::A_BYTES / 2 >> 4);
+                const uint64_t bh = h_d0 + ((b16 + k * 32u) >> 4), bl = bh + (Cfg::B_BYTES / 2 >> 4);
+                const uint32_t acc0 = (i | k) != 0 ? 1u : 0u;
+                if (TWO) {
+                  ptx::mma_f16_ss_2cta(d_tmem, ah, bh, idesc_h3, acc0);
+                  if (!(p.debug & 4)) { ptx::mma_f16_ss_2cta(d_tmem, al, bh, idesc_h3, 1u); ptx::mma_f16_ss_2cta(d_tmem, ah, bl, idesc_h3, 1u); }
+                } else {
+                  ptx::mma_f16_ss(d_tmem, ah, bh, idesc_h3, acc0);
+                  if (!(p.debug & 4)) { ptx::mma_f16_ss(d_tmem, al, bh, idesc_h3, 1u); ptx::mma_f16_ss(d_tmem, ah, bl, idesc_h3, 1u); }
+                }
+              }
+              finish(s, i == nkb - 1);
+            }
+            __syncwarp();
+            continue;
+          }
           const bool early = mixed && !(p.debug & 16);
           if (!mixed) ptx::mbar_wait(full_bar + s, (it / Cfg::STAGES) & 1);
           if (early) ptx::mbar_wait(raw_bar + s, (it / Cfg::STAGES) & 1);
@@ -461,6 +502,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (derive) {
       const int ct = threadIdx.x - 32 * (2 + Cfg::EPI_WARPS);
       const uint32_t conv_leader = TWO ? ptx::mapa(ptx::smem_u32(conv_bar), 0u) : 0u;
+      float amax = 0.f;                // H3: largest |A element| this thread has converted
       uint32_t it = 0;
       for (int t = worker; t < total; t += num_workers) {
         const int kb0 = (t / (n_tiles * m_tiles)) * p.kb_per_split;
@@ -468,7 +510,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int i = 0; i < nkb; ++i, ++it) {
           const int s = it % Cfg::STAGES;
           ptx::mbar_wait(afull_bar + s, (it / Cfg::STAGES) & 1);
-          if (mixed && ct == 0) {      // this CTA's raw tiles have landed: the leader's MMA warp may start the TF32 pass of the stage
+          if (mixed && !H3 && ct == 0) {      // this CTA's raw tiles have landed: the leader's MMA warp may start the TF32 pass of the stage
             if (TWO) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(raw_bar + s), 0u)); else ptx::mbar_arrive(raw_bar + s);
           }
           const float4* hi = reinterpret_cast<const float4*>(smem + s * Cfg::STAGE_BYTES);
@@ -503,8 +545,33 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
               }
             };
+            // H3: h = fp16(x) (round to nearest; saturating, so that an out-of-range value stays finite and is reported through
+            // p.status instead of poisoning the tile), l = fp16(x - h): 22 significand bits in two fp16 tiles of the same layout
+            auto convert_h3 = [&](const uint8_t* src, uint8_t* hi16, int chunks) {
+              uint8_t* lo16 = hi16 + chunks * 8;
+              constexpr int U = 4;
+              for (int e0 = ct; e0 < chunks; e0 += U * NT) {
+                float4 v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) v[u] = (e0 + u * NT < chunks) ? reinterpret_cast<const float4*>(src)[e0 + u * NT] : f4_zero();
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                  if (e0 + u * NT >= chunks) break;
+                  const int off = off0 + ((e0 - ct) / NT + u) * (NT / 8) * 64;
+                  const float4 x = v[u];
+                  const uint32_t h0 = ptx::cvt_f16x2_sat(x.x, x.y), h1 = ptx::cvt_f16x2_sat(x.z, x.w);
+                  const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&h0)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
+                  const uint32_t l0 = ptx::cvt_f16x2_sat(x.x - f0.x, x.y - f0.y), l1 = ptx::cvt_f16x2_sat(x.z - f1.x, x.w - f1.y);
+                  *reinterpret_cast<uint2*>(hi16 + off) = make_uint2(h0, h1);
+                  *reinterpret_cast<uint2*>(lo16 + off) = make_uint2(l0, l1);
+                  amax = fmaxf(amax, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
+                }
+              }
+            };
             uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-            if (!(p.debug & 2)) {      // (timing experiments: skip the conversion)
+            if (H3) {
+              if (!(p.debug & 2)) convert_h3(st, st + Cfg::A_BYTES, Cfg::A_BYTES / 16);
+            } else if (!(p.debug & 2)) {      // (timing experiments: skip the conversion)
               convert(st, st + Cfg::A_BYTES, Cfg::A_BYTES / 16);
               if (!p.b_presplit) convert(st + 2 * Cfg::A_BYTES, st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, Cfg::B_BYTES / 16);
             }
@@ -526,6 +593,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      // H3: an A element beyond fp16's largest finite value was clamped -- the product is wrong; tell the caller (sticky status word)
+      if (H3 && amax > 65504.f && p.status) atomicOr(p.status, MOLCLR_STATUS_FP16_RANGE);
     }
   } else {
     // ------------------------------------------------------------ epilogue: warp q owns accumulator rows 32q..32q+31
@@ -1070,7 +1139,8 @@ static bool gemm_tma_store();
 
 template <int BN, bool FOUR, int KIND, bool TWO>
 static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, int splits, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, FOUR, TWO>;
+  constexpr bool H3 = KIND == K_PLAIN_H3;
+  using Cfg = GemmCfg<BN, FOUR, TWO, H3>;
   p.n_tiles = n_tiles; p.m_tiles = m_tiles; p.splits = splits;
   MOLCLR_REQUIRE(!p.b_mn || Cfg::BN_CTA % 32 == 0, "gemm: internal: MN-major B needs whole 32-column blocks per CTA (BN=%d)", BN);
   CUtensorMap tmA, tmB, tmA2, tmB2;
@@ -1080,7 +1150,8 @@ static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, i
   const int bk_el = h16 ? 2 * Cfg::BK : Cfg::BK;          // elements per 128-byte tile row
   rc = p.a_mn ? make_tmap(&tmA, j.A, p.M, p.K, j.lda, 32, true, Cfg::BK) : make_tmap(&tmA, j.A, p.K, p.M, j.lda, GEMM_BM, false, bk_el, h16);
   if (rc) return rc;
-  rc = p.b_mn ? make_tmap(&tmB, j.B, p.N, p.K, j.ldb, 32, true, Cfg::BK) : make_tmap(&tmB, j.B, p.K, p.N, j.ldb, Cfg::BN_CTA, false, bk_el, h16);
+  if (H3) tmB = tmA;            // (no fp32 B tile: the slot is unused)
+  else rc = p.b_mn ? make_tmap(&tmB, j.B, p.N, p.K, j.ldb, 32, true, Cfg::BK) : make_tmap(&tmB, j.B, p.K, p.N, j.ldb, Cfg::BN_CTA, false, bk_el, h16);
   if (rc) return rc;
   tmA2 = tmA; tmB2 = tmB;
   p.a_mn3d = p.b_mn3d = 0;
@@ -1102,15 +1173,15 @@ static int launch_tc(const GemmJob& j, GemmParams p, int n_tiles, int m_tiles, i
       rc = p.a_mn ? make_tmap(&tmA2, j.A_lo, p.M, p.K, j.lda, 32, true, Cfg::BK) : make_tmap(&tmA2, j.A_lo, p.K, p.M, j.lda, GEMM_BM, false, Cfg::BK);
       if (rc) return rc;
     }
-    if (p.derive_lo != 2)            // (mixed: no second fp32 B tensor)
+    if (p.derive_lo < 2)             // (mixed / fp16 three-product: no second fp32 B tensor)
       rc = p.b_mn ? make_tmap(&tmB2, j.B_lo, p.N, p.K, j.ldb, 32, true, Cfg::BK) : make_tmap(&tmB2, j.B_lo, p.K, p.N, j.ldb, Cfg::BN_CTA, false, Cfg::BK);
-    else if (p.b_presplit)           // bf16 [2 rows16][K]: boxes of BN_CTA rows x 32 elements (64-byte rows, 64-byte swizzle, zero fill beyond K)
+    else if (p.b_presplit)           // 16-bit [2 rows16][K]: boxes of BN_CTA rows x 32 elements (64-byte rows, 64-byte swizzle, zero fill beyond K)
       rc = make_tmap(&tmB2, reinterpret_cast<const float*>(j.B16), p.K, 2ll * j.rows16, j.ld16, Cfg::BN_CTA, false, Cfg::BK, true);
     if (rc) return rc;
   }
   CUtensorMap tmO = tmA;
   p.tma_store = 0;
-  constexpr bool kPlain = KIND == K_PLAIN || KIND == K_PLAIN16;
+  constexpr bool kPlain = KIND == K_PLAIN || KIND == K_PLAIN16 || KIND == K_PLAIN_H3;
   if (kPlain && Cfg::CHUNK == 32 && p.out && !p.out2 && !p.out_lo && !p.transpose_out && gemm_tma_store() && p.ldo % 4 == 0 &&
       (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
     rc = make_tmap_out(&tmO, p.out, p.N, p.M, p.ldo);
@@ -1214,11 +1285,17 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   MOLCLR_REQUIRE(p.N % 4 == 0, "gemm: N=%d must be a multiple of 4", p.N);
   const bool atomic = job.split_k > 1 || p.transpose_out;
   MOLCLR_REQUIRE(job.A_lo == nullptr || job.B_lo != nullptr, "gemm: A_lo needs B_lo");
-  MOLCLR_REQUIRE(!job.compensate || (!job.A_lo && !job.B_lo && !p.a_mn && !p.b_mn), "gemm: compensate = 1 takes unrounded K-major A and B and no lo tensors");
+  MOLCLR_REQUIRE(job.compensate >= 0 && job.compensate <= 2, "gemm: compensate must be 0, 1 or 2");
+  MOLCLR_REQUIRE(!job.compensate || (!job.A_lo && !job.B_lo && !p.a_mn && !p.b_mn), "gemm: compensate takes unrounded K-major A and B and no lo tensors");
+  const bool h3 = job.compensate == 2;
+  MOLCLR_REQUIRE(!h3 || job.B16, "gemm: compensate = 2 needs B16, the fp16 tiles of B (molclr_prepare_weights, b16_kind = 1)");
+  MOLCLR_REQUIRE(h3 || job.B, "gemm: B is null");
   p.segments = (job.B_lo || job.compensate) ? 3 : 1;
   // compensated product with the low halves derived on chip: 1 = A_lo (fp32 tile) from an unrounded A, B_hi/B_lo from the caller;
   // 2 = "mixed": both operands unrounded, bf16 correction tiles of both formed on chip
-  p.derive_lo = job.compensate ? 2 : (job.B_lo && !job.A_lo) ? 1 : 0;
+  p.derive_lo = h3 ? 3 : job.compensate ? 2 : (job.B_lo && !job.A_lo) ? 1 : 0;
+  p.status = job.status;
+  if (h3) p.alpha *= 1.f / (float)MOLCLR_H16_SCALE;      // B16 holds the weights times 2^6 (exact); the epilogue undoes it
   p.b_presplit = (job.compensate && job.B16) ? 1 : 0;
   p.rows16 = job.rows16;
   MOLCLR_REQUIRE(!job.B16 || job.compensate, "gemm: B16 (pre-split bf16 tiles of B) belongs to the compensated product");
@@ -1278,7 +1355,8 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   MOLCLR_REQUIRE(p.segments == 1 || kind == K_PLAIN, "gemm: the compensated product supports the plain epilogue only");
   MOLCLR_REQUIRE(!p.half16 || kind == K_PLAIN || kind == K_NTX_W || kind == K_NTX_FWD, "gemm: fp16 operands: plain and NT-Xent epilogues only");
   MOLCLR_REQUIRE(kind != K_NTX_W || (p.out16 != nullptr) == (p.half16 != 0), "gemm: the NT-Xent weight epilogue writes fp16 iff its operands are fp16");
-  const int kind_i = !p.half16 ? kind : kind == K_PLAIN ? K_PLAIN16 : kind == K_NTX_W ? K_NTX_W16 : K_NTX_FWD16;
+  MOLCLR_REQUIRE(!h3 || !gemm_impl_simt(), "gemm: compensate = 2 has no scalar debug implementation");
+  const int kind_i = h3 ? K_PLAIN_H3 : !p.half16 ? kind : kind == K_PLAIN ? K_PLAIN16 : kind == K_NTX_W ? K_NTX_W16 : K_NTX_FWD16;
   const int bn = wide ? 320 : (job.bn_hint && pair) ? job.bn_hint : gemm_bn(p.N, p.b_mn != 0, pair, kind == K_PLAIN || kind == K_LATE), nt = (p.N + bn - 1) / bn;
   if (wide) MOLCLR_REQUIRE((long long)nt * m_tiles * splits <= gemm_workers(true), "gemm: a wide split-K launch must be one wave");
 #define MOLCLR_GEMM_CASE(BN_, FOUR_, KIND_, TWO_) \
@@ -1290,6 +1368,8 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
   MOLCLR_GEMM_KINDS(160, true) MOLCLR_GEMM_KINDS(192, true) MOLCLR_GEMM_KINDS(256, true)
   MOLCLR_GEMM_CASE(224, false, K_PLAIN, true) MOLCLR_GEMM_CASE(224, true, K_PLAIN, true) MOLCLR_GEMM_CASE(224, false, K_LATE, true)
   MOLCLR_GEMM_CASE(128, false, K_PLAIN, true) MOLCLR_GEMM_CASE(320, false, K_ATOMIC, true)
+  MOLCLR_GEMM_CASE(160, true, K_PLAIN_H3, true) MOLCLR_GEMM_CASE(192, true, K_PLAIN_H3, true) MOLCLR_GEMM_CASE(224, true, K_PLAIN_H3, true)
+  MOLCLR_GEMM_CASE(256, true, K_PLAIN_H3, true) MOLCLR_GEMM_CASE(160, true, K_PLAIN_H3, false) MOLCLR_GEMM_CASE(256, true, K_PLAIN_H3, false)
 #define MOLCLR_GEMM_KINDS16(BN_, TWO_) \
   MOLCLR_GEMM_CASE(BN_, false, K_PLAIN16, TWO_) MOLCLR_GEMM_CASE(BN_, false, K_NTX_W16, TWO_) MOLCLR_GEMM_CASE(BN_, false, K_NTX_FWD16, TWO_)
   MOLCLR_GEMM_KINDS16(160, false) MOLCLR_GEMM_KINDS16(256, false)
@@ -1445,7 +1525,7 @@ extern "C" int molclr_gemm_tf32(const molclr_gemm_args* args, cudaStream_t strea
   memset(&j, 0, sizeof(j));
   j.A = a.A; j.lda = a.lda; j.B = a.B; j.ldb = a.ldb; j.split_k = a.split_k;
   j.A_lo = a.A_lo; j.B_lo = a.B_lo;
-  j.compensate = a.compensate;
+  j.compensate = a.compensate; j.status = a.status;
   j.B16 = a.B16; j.ld16 = a.ld16; j.rows16 = (int)a.rows16;
   GemmParams& p = j.p;
   p.M = (int)a.M; p.N = (int)a.N; p.K = (int)a.K; p.a_mn = a.a_mn; p.b_mn = a.b_mn;

@@ -17,7 +17,9 @@ struct GemmParams {
   int num_kb, kb_per_split;
   int n_tiles, m_tiles, splits;   // tile grid walked by the persistent CTAs (filled by the launcher)
   int derive_lo;               // compensated product with low halves derived on chip: 1 = A_lo from an unrounded A; 2 = "mixed": A and B
-                               // both unrounded, bf16 correction tiles of both formed in shared memory (see gemm.cu)
+                               // both unrounded, bf16 correction tiles of both formed in shared memory (see gemm.cu); 3 = fp16
+                               // three-product form (K_PLAIN_H3): A split into two fp16 tiles on chip, B pre-split (b_presplit)
+  int* status;                 // derive_lo 3: sticky status word (MOLCLR_STATUS_FP16_RANGE), may be null
   int segments;                // 1: plain TF32.  3: error-compensated  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (~fp32 accuracy)
   int b_presplit;              // mixed: the bf16 correction tiles of B arrive by TMA (tmB2 over [2][rows16][K] bf16); the converters touch A only
   int rows16;                  // rows per half of that tensor
@@ -54,7 +56,9 @@ struct GemmParams {
 struct GemmJob {
   const float* A; long long lda; const float* B; long long ldb;   // p.half16: __half tensors, leading dimensions in halves (% 8 == 0)
   const float* A_lo; const float* B_lo;   // both non-null selects the 3-segment compensated product (same layout/ld as A, B)
-  int compensate;              // 1: A and B are unrounded K-major fp32; ~fp32-accurate product, everything derived on chip ("mixed")
+  int compensate;              // 1: A and B are unrounded K-major fp32; ~fp32-accurate product, everything derived on chip ("mixed");
+                               // 2: the fp16 three-product form: A unrounded fp32, B16 = fp16 tiles of B (mandatory), B unused
+  int* status;                 // compensate 2: see GemmParams::status
   const void* B16; long long ld16; int rows16;   // compensate: optional pre-split bf16 correction tiles of B (molclr_prepare_weights)
   int accumulate;              // split-K: add into `out` as it is (the caller zero-filled it, or wants out += product) instead of zero-filling it first
   float* ordered_ws;           // split-K: write the per-split partial products here ([splits][M][ldws] fp32) with plain stores and sum them

@@ -173,13 +173,13 @@ extern "C" int molclr_gin_encoder_fwd(const molclr_gin_model* m, const molclr_pl
     }
     molclr_gemm_args g;
     gemm_args_init(g);                                                                                // u = relu(a W1^T + b1)  (:19-23,46-47)
-    g.A = x.a[l]; g.lda = d.ldD; g.B = comp ? ly.w1_raw : ly.w1_hi; g.ldb = d.ldD; g.M = N; g.N = H; g.K = D;
-    g.compensate = comp; g.B16 = comp ? ly.w1_b16 : nullptr; g.ld16 = m->w1_ld16; g.rows16 = m->w1_rows16;
+    g.A = x.a[l]; g.lda = d.ldD; g.B = comp == 2 ? nullptr : comp ? ly.w1_raw : ly.w1_hi; g.ldb = d.ldD; g.M = N; g.N = H; g.K = D;
+    g.compensate = comp; g.B16 = comp ? ly.w1_b16 : nullptr; g.ld16 = m->w1_ld16; g.rows16 = m->w1_rows16; g.status = m->status;
     g.out = x.u[l]; g.ldo = d.ldH; g.bias = ly.b1; g.relu = 1; g.relu_bits = x.ubits[l]; g.ld_bits = d.words;
     { TimeScope ts(TIME_GEMM_FWD, stream); GIN_CALL(molclr_gemm_tf32(&g, stream)); }
     gemm_args_init(g);                                                                                // z = u W2^T + b2 (+ BatchNorm tile statistics)
-    g.A = x.u[l]; g.lda = d.ldH; g.B = comp ? ly.w2_raw : ly.w2_hi; g.ldb = d.ldH; g.M = N; g.N = D; g.K = H;
-    g.compensate = comp; g.B16 = comp ? ly.w2_b16 : nullptr; g.ld16 = m->w2_ld16; g.rows16 = m->w2_rows16;
+    g.A = x.u[l]; g.lda = d.ldH; g.B = comp == 2 ? nullptr : comp ? ly.w2_raw : ly.w2_hi; g.ldb = d.ldH; g.M = N; g.N = D; g.K = H;
+    g.compensate = comp; g.B16 = comp ? ly.w2_b16 : nullptr; g.ld16 = m->w2_ld16; g.rows16 = m->w2_rows16; g.status = m->status;
     g.out = x.z[l]; g.ldo = D; g.bias = ly.b2;
     if (training) { g.colstat = stats; g.colstat_mode = 2; }
     { TimeScope ts(TIME_GEMM_FWD, stream); GIN_CALL(molclr_gemm_tf32(&g, stream)); }

@@ -141,6 +141,12 @@ __device__ __forceinline__ void tmem_ld_wait_dep(float (&v)[32]) {
                  "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
                :: "memory");
 }
+// {lo, hi} = fp16(a), fp16(b), round to nearest even, saturating at +-65504 instead of overflowing to infinity
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));     // (first source -> upper half)
+  return r;
+}
 // 2^x on the SFU (ex2.approx: 2 ulp, -inf -> +0), without the denormal-range fix-ups of exp2f()
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 

@@ -5,10 +5,12 @@
 //     nodes into 8 / 122 rows, so they run as plain fp32 FMAs with a fixed summation order (row tiles dealt round-robin to the
 //     CTAs and summed in increasing order by each, CTA partials summed in CTA order) instead of a split-K tensor-core contraction.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstring>
 
 #include "common.cuh"
 #include "molclr_b200.h"
+#include "ptx.cuh"
 
 namespace molclr {
 
@@ -48,7 +50,20 @@ __global__ void __launch_bounds__(256) prepare_weights_kernel(const __grid_const
     const long long n = (long long)rows_t * d.ld_raw;
     for (long long i = tid; i < n; i += nth) d.raw[i] = at((int)(i / d.ld_raw), (int)(i % d.ld_raw));
   }
-  if (d.b16) {
+  if (d.b16 && d.b16_kind == 1) {
+    // fp16 halves of 2^6 W (exact scaling): h = fp16(s w), l = fp16(s w - h); |s w| beyond fp16's range saturates (weights of
+    // magnitude >= 1024 do not occur)
+    uint16_t* hi16 = reinterpret_cast<uint16_t*>(d.b16);
+    uint16_t* lo16 = hi16 + (size_t)d.rows16 * d.ld16;
+    const long long n = (long long)d.rows16 * d.ld16;
+    for (long long i = tid; i < n; i += nth) {
+      const float v = at((int)(i / d.ld16), (int)(i % d.ld16)) * (float)MOLCLR_H16_SCALE;
+      const uint32_t h = ptx::cvt_f16x2_sat(v, 0.f) & 0xFFFFu;
+      const float hf = __half2float(__ushort_as_half((unsigned short)h));
+      hi16[i] = (uint16_t)h;
+      lo16[i] = (uint16_t)(ptx::cvt_f16x2_sat(v - hf, 0.f) & 0xFFFFu);
+    }
+  } else if (d.b16) {
     __nv_bfloat16* hi16 = reinterpret_cast<__nv_bfloat16*>(d.b16);
     __nv_bfloat16* lo16 = hi16 + (size_t)d.rows16 * d.ld16;
     const long long n = (long long)d.rows16 * d.ld16;

@@ -164,7 +164,7 @@ def _gcn_encoder_backward(m, plan, saved, g_p, training, pool_mode):
 def _gcn_precision(m):
     if m.precision not in PRECISIONS:
         raise ValueError(f"molclr_b200: precision must be one of {PRECISIONS}, got {m.precision!r}")
-    return m.precision == "tf32x3"
+    return m.precision in ("tf32x3", "fp16x3")      # (the fp16 three-product form exists for the GINEConv MLP products only)
 
 
 class _GCNFunction(torch.autograd.Function):

@@ -17,10 +17,12 @@ and the backward mirrors it.  Both sequences are issued from C in ONE call each 
 ``molclr_proj_head_fwd/bwd`` in csrc/gin_step.cu, driven by ``molclr_b200/native.py``); the per-kernel wrappers of ``ops.py`` remain
 for the GCN path, the fine-tune heads and the tests.  Nothing here falls back to PyTorch operators.
 """
+import os
+
 import torch
 from torch import nn
 
-from . import native, ops
+from . import _lib, native, ops
 from .graph import get_plan
 
 num_atom_type = 119      # including the extra mask token   (ginet_molclr.py:9)
@@ -97,7 +99,7 @@ class _RoundedWeights:
         return None if e is None else e["b16"]
 
 
-PRECISIONS = ("tf32x3", "tf32")
+PRECISIONS = ("fp16x3", "tf32x3", "tf32")
 
 
 class _EncoderBase(nn.Module):
@@ -107,10 +109,16 @@ class _EncoderBase(nn.Module):
       * ``"tf32x3"`` (default): every FORWARD contraction is the error-compensated 3-pass TF32 product
         (~fp32 accuracy), so pre-activations -- and with them the ReLU masks the backward pass depends on --
         match the fp32 reference; BACKWARD contractions are single-pass TF32.
+      * ``"fp16x3"``: the same compensated forward with the GINEConv MLP products in the fp16 three-product form
+        (``molclr_gemm_args.compensate = 2``: operands split into two fp16 halves, 22 significand bits): a smaller
+        rounding error than ``"tf32x3"`` at 3/4 of its tensor work and 2/3 of its operand traffic, valid while the
+        activations stay inside fp16's range -- |a| <= 65504; a violation is detected on the device and raised as
+        ``FloatingPointError`` by the next forward (BatchNorm keeps the activations of this network at O(1)).
+        GCN models, whose contractions take another route, treat it as ``"tf32x3"``.
       * ``"tf32"``: single-pass TF32 everywhere (fastest; activations carry ~1e-3 relative error and the
         resulting ReLU mask flips show up as percent-level noise in gradients).
     """
-    precision = "tf32x3"
+    precision = os.environ.get("MOLCLR_B200_PRECISION", "fp16x3")      # class default; the environment variable overrides it process-wide
 
     def _check_input(self, data):
         if not 0 <= self.drop_ratio < 1:
@@ -125,14 +133,16 @@ class _EncoderBase(nn.Module):
         """(parameter, ops.W_* operand forms) of every contraction of the model.  GINEConv MLP weights / GCNConv weights: hi
         (backward dX products, single-pass forward) and, for the compensated forward, the unrounded K-major copy + its bf16
         correction tiles; every other nn.Linear (projection / prediction heads): hi (+ lo for the explicit 3-pass product)."""
-        enc = ops.W_HI | (ops.W_B16 if comp else 0)
+        h3 = int(comp) == 2      # fp16 three-product form: the fp16 halves of the weight instead of the raw copy + bf16 correction tiles
+        enc = ops.W_HI | ((ops.W_H16 if h3 else ops.W_B16) if comp else 0)
         head = ops.W_HI | (ops.W_LO if comp else 0)
+        raw = ops.W_RAW if (comp and not h3) else 0
         specs, seen = [], set()
         for g in self.gnns:
             if hasattr(g, "mlp"):                         # (+ the transposed tf32 copies: K-major operands of the backward dX products)
-                ws = [(g.mlp[0].weight, enc | ops.W_HI_T | (ops.W_RAW if comp else 0)), (g.mlp[2].weight, enc | ops.W_HI_T | (ops.W_RAW if comp else 0))]
+                ws = [(g.mlp[0].weight, enc | ops.W_HI_T | raw), (g.mlp[2].weight, enc | ops.W_HI_T | raw)]
             else:                                         # GCNConv: stored [in, out]
-                ws = [(g.weight, enc | (ops.W_RAW_T if comp else 0))]
+                ws = [(g.weight, ops.W_HI | ((ops.W_B16 | ops.W_RAW_T) if comp else 0))]
             specs += ws
             seen.update(id(w) for w, _ in ws)
         for mod in self.modules():
@@ -143,10 +153,40 @@ class _EncoderBase(nn.Module):
 
     def _refresh_weights(self, comp):
         cache = self.__dict__.setdefault("_gemm_weight_specs", {})
-        specs = cache.get(bool(comp))
+        specs = cache.get(int(comp))
         if specs is None:
-            specs = cache[bool(comp)] = self._gemm_weights(comp)
+            specs = cache[int(comp)] = self._gemm_weights(comp)
         self._rounded.refresh(specs)
+        if int(comp) == 2:
+            self._fp16_range_check()
+
+    def _fp16_range_check(self):
+        """``precision = "fp16x3"``: the forward products report an activation beyond fp16's finite range through a sticky device
+        word (``molclr_gin_model.status``).  It is copied to pinned memory behind each forward and examined by the NEXT one -- no
+        stream drain; the error arrives one call late."""
+        st = self.__dict__.get("_fp16_status")
+        if st is None:
+            dev = next(self.parameters()).device
+            st = self.__dict__["_fp16_status"] = {"dev": torch.zeros(1, dtype=torch.int32, device=dev),
+                                                  "host": torch.zeros(1, dtype=torch.int32).pin_memory(), "ev": None}
+        if st["ev"] is not None and st["ev"].query():
+            st["ev"] = None
+            if int(st["host"][0]) & _lib.STATUS_FP16_RANGE:
+                st["dev"].zero_()
+                raise FloatingPointError("molclr_b200: an activation exceeded fp16's finite range (65504) in a forward product of "
+                                         "precision 'fp16x3' (the value was clamped: results since the last check are wrong); "
+                                         "use model.precision = 'tf32x3'")
+        if st["ev"] is None:
+            # the 4-byte copy runs on a side stream behind everything enqueued so far: on the compute stream it would queue behind any
+            # host-to-device batch copy in flight on the same copy engine (measured: 0.25 ms per step in bench.py's e2e loop)
+            side = st.get("stream")
+            if side is None:
+                side = st["stream"] = torch.cuda.Stream(device=st["dev"].device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                st["host"].copy_(st["dev"], non_blocking=True)
+                st["ev"] = torch.cuda.Event()
+                st["ev"].record(side)
 
     def _dropout_seeds(self):
         """One counter-hash seed per layer and forward call (drawn from torch's CPU generator, so torch.manual_seed makes
@@ -277,7 +317,7 @@ def _encoder_backward(m, plan, e, g_p, training, pool_mode):
 def _check_precision(m):
     if m.precision not in PRECISIONS:
         raise ValueError(f"molclr_b200: precision must be one of {PRECISIONS}, got {m.precision!r}")
-    return m.precision == "tf32x3"
+    return {"fp16x3": 2, "tf32x3": 1, "tf32": 0}[m.precision]      # = `comp` of the native calls
 
 
 class _GINetFunction(torch.autograd.Function):

@@ -25,7 +25,7 @@ def model_struct(m, comp, with_head=True):
     """(GinModel, keepalive): device pointers of the parameters and of the weight shadows of the LAST ``m._refresh_weights``.
     Cached while the shadow buffers (``_RoundedWeights.generation``) and the BatchNorm buffers stay where they are."""
     rw = m._rounded
-    key = (getattr(rw, "generation", None), bool(comp), bool(with_head), tuple(p.data_ptr() for p in m._params()),
+    key = (getattr(rw, "generation", None), int(comp), bool(with_head), tuple(p.data_ptr() for p in m._params()),
            tuple((bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), bn.momentum, bn.eps) for bn in m.batch_norms))
     hit = m.__dict__.get("_native_struct")
     if hit is not None and hit[0] == key:
@@ -49,8 +49,10 @@ def _build_model_struct(m, comp, with_head):
         ly.w1_hi, ly.w2_hi = rw.get(w1)[0].data_ptr(), rw.get(w2)[0].data_ptr()
         ly.w1_hi_t, ly.w2_hi_t = _dp(rw.hi_t(w1)), _dp(rw.hi_t(w2))
         if comp:
-            s1, s2 = rw.b16(w1), rw.b16(w2)
-            ly.w1_raw, ly.w2_raw, ly.w1_b16, ly.w2_b16 = rw.raw(w1).data_ptr(), rw.raw(w2).data_ptr(), s1.data_ptr(), s2.data_ptr()
+            s1, s2 = rw.b16(w1), rw.b16(w2)          # bf16 correction tiles (comp 1) or the fp16 halves (comp 2: no raw copy)
+            ly.w1_b16, ly.w2_b16 = s1.data_ptr(), s2.data_ptr()
+            if int(comp) != 2:
+                ly.w1_raw, ly.w2_raw = rw.raw(w1).data_ptr(), rw.raw(w2).data_ptr()
             gm.w1_ld16, gm.w1_rows16, gm.w2_ld16, gm.w2_rows16 = s1.stride(1), s1.shape[1], s2.stride(1), s2.shape[1]
         ly.b1, ly.b2 = g.mlp[0].bias.data_ptr(), g.mlp[2].bias.data_ptr()
         ly.bond_type, ly.bond_dir = g.edge_embedding1.weight.data_ptr(), g.edge_embedding2.weight.data_ptr()
@@ -58,6 +60,10 @@ def _build_model_struct(m, comp, with_head):
         ly.running_mean, ly.running_var, ly.num_batches_tracked = bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr()
         ly.momentum, ly.eps = (0.1 if bn.momentum is None else bn.momentum), bn.eps
     gm.layers = layers
+    st = m.__dict__.get("_fp16_status")
+    if int(comp) == 2 and st is not None:
+        gm.status = st["dev"].data_ptr()
+        keep.append(st["dev"])
     if with_head:
         (wf, wfl), (w0, w0l), (w2, w2l) = rw.get(m.feat_lin.weight), rw.get(m.out_lin[0].weight), rw.get(m.out_lin[2].weight)
         gm.wf_hi, gm.wf_lo, gm.bf = wf.data_ptr(), _dp(wfl), m.feat_lin.bias.data_ptr()

@@ -30,13 +30,13 @@ def max_blocks():
 # ------------------------------------------------------------------------------------------- GEMM
 def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=None, out2=None, out_lo=None, bias=None,
          addend=None, mask=None, relu=False, round_out=False, colstat=None, colstat_mode=0, transpose_out=False,
-         split_k=1, lda=None, ldb=None, relu_bits=None, mask_bits=None, compensate=False, B16=None):
+         split_k=1, lda=None, ldb=None, relu_bits=None, mask_bits=None, compensate=False, B16=None, status=None):
     """C[M,N] = sum_k A(m,k) B(n,k) on tcgen05 (TF32 in, FP32 accumulate) with the fused epilogue of
     ``molclr_gemm_tf32`` (see include/molclr_b200.h)."""
     lib = _lib.load()
     a = GemmArgs()
     a.A, a.lda, a.a_mn = ptr2d(A), (A.stride(0) if lda is None else lda), int(a_mn)
-    a.B, a.ldb, a.b_mn = ptr2d(B), (B.stride(0) if ldb is None else ldb), int(b_mn)
+    a.B, a.ldb, a.b_mn = ptr2d(B), ((B.stride(0) if B is not None else 0) if ldb is None else ldb), int(b_mn)
     a.A_lo, a.B_lo = ptr2d(A_lo), ptr2d(B_lo)
     a.M, a.N, a.K = M, N, K
     a.out, a.ldo, a.transpose_out = ptr2d(out), (out.stride(0) if out is not None else 0), int(transpose_out)
@@ -51,9 +51,12 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, A_lo=None, B_lo=None, out=Non
     bits = relu_bits if relu_bits is not None else mask_bits
     a.relu_bits, a.mask_bits = ptr(relu_bits, torch.int32), ptr(mask_bits, torch.int32)
     a.ld_bits = bits.stride(0) if bits is not None else 0
-    a.compensate = int(compensate)      # A, B unrounded fp32 (K-major): ~fp32-accurate product, low halves derived on chip
-    if B16 is not None:                 # (tensor bf16 [2, rows16, ld16]): B's correction tiles pre-split by prepare_weights
+    # compensate: 1 = A, B unrounded fp32 (K-major): ~fp32-accurate product, TF32 pass + bf16 corrections derived on chip;
+    # 2 = the fp16 three-product form (B16 = the fp16 tiles of B: prepare_weights W_H16; B may be None)
+    a.compensate = int(compensate)
+    if B16 is not None:                 # (16-bit tensor [2, rows16, ld16]): B's tiles pre-split by prepare_weights
         a.B16, a.ld16, a.rows16 = B16.data_ptr(), B16.stride(1), B16.shape[1]
+    a.status = ptr(status, torch.int32)
     check(lib.molclr_gemm_tf32(C.byref(a), stream()), "gemm_tf32")
     return out
 
@@ -94,14 +97,14 @@ def gemm_dw(dY, X, ordered=False, accumulate_into=None):
     return dW
 
 
-W_HI, W_LO, W_RAW, W_RAW_T, W_B16, W_HI_T = 1, 2, 4, 8, 16, 32
+W_HI, W_LO, W_RAW, W_RAW_T, W_B16, W_HI_T, W_H16 = 1, 2, 4, 8, 16, 32, 64
 
 
 def prepare_weights(specs, want_relaunch=False):
     """ONE launch deriving the tensor-core operand forms of several weights (molclr_prepare_weights).  specs: [(w, flags)] with w a
     2-D fp32 matrix and flags a combination of W_HI (tf32(w)), W_LO (tf32 residual), W_RAW (unrounded copy, 128-byte rows),
     W_RAW_T (W_RAW of w^T: K-major copy of a weight stored [in, out]), W_B16 (bf16 correction tiles [2, rows16, ld16] of the raw
-    orientation), W_HI_T (tf32(w^T): the K-major operand of the backward dX product).  Returns a list of dicts with the keys 'hi',
+    orientation) or W_H16 (instead: the fp16 halves of 2^6 w, same shape, returned under 'b16' as a float16 view), W_HI_T (tf32(w^T): the K-major operand of the backward dX product).  Returns a list of dicts with the keys 'hi',
     'lo', 'raw', 'b16', 'hi_t' (None where not requested); with
     ``want_relaunch`` also a callable that re-derives every output from the CURRENT values of the sources into the same buffers."""
     if not specs:
@@ -124,7 +127,8 @@ def prepare_weights(specs, want_relaunch=False):
             o_lo, n32 = n32, n32 + rows * ld_hi
         if flags & (W_RAW | W_RAW_T):
             o_raw, n32 = n32, n32 + rt * ld_raw
-        if flags & W_B16:
+        if flags & (W_B16 | W_H16):
+            assert not (flags & W_B16 and flags & W_H16), "W_B16 and W_H16 share the 16-bit slot"
             o_16, n16 = n16, n16 + 2 * rows16 * ld16
         plans.append((rows, cols, tr, rt, ct, ld_hi, ld_raw, ld16, rows16, o_hi, o_lo, o_raw, o_16, ld_hi_t, o_hit))
     buf32 = torch.empty(max(n32, 1), dtype=F32, device=dev)
@@ -132,18 +136,20 @@ def prepare_weights(specs, want_relaunch=False):
     descs = (WeightDesc * len(specs))()
     out = []
     b32, b16 = buf32.data_ptr(), buf16.data_ptr()
-    for d, (w, _), (rows, cols, tr, rt, ct, ld_hi, ld_raw, ld16, rows16, o_hi, o_lo, o_raw, o_16, ld_hi_t, o_hit) in zip(descs, specs, plans):
+    for d, (w, flags), (rows, cols, tr, rt, ct, ld_hi, ld_raw, ld16, rows16, o_hi, o_lo, o_raw, o_16, ld_hi_t, o_hit) in zip(descs, specs, plans):
         d.src, d.ld_src, d.rows, d.cols = ptr2d(w), w.stride(0), rows, cols
         d.ld_hi, d.ld_raw, d.transpose_raw, d.ld16, d.rows16 = ld_hi, ld_raw, int(tr), ld16, rows16
         d.hi = b32 + 4 * o_hi if o_hi is not None else None
         d.lo = b32 + 4 * o_lo if o_lo is not None else None
         d.raw = b32 + 4 * o_raw if o_raw is not None else None
         d.b16 = b16 + 2 * o_16 if o_16 is not None else None
+        d.b16_kind = 1 if flags & W_H16 else 0
         d.hi_t, d.ld_hi_t = (b32 + 4 * o_hit if o_hit is not None else None), ld_hi_t
         view = lambda o, r, ld, c: None if o is None else buf32[o:o + r * ld].view(r, ld)[:, :c]
         out.append({"hi": view(o_hi, rows, ld_hi, cols), "lo": view(o_lo, rows, ld_hi, cols), "raw": view(o_raw, rt, ld_raw, ct),
                     "hi_t": view(o_hit, cols, ld_hi_t, rows),
-                    "b16": None if o_16 is None else buf16[o_16:o_16 + 2 * rows16 * ld16].view(2, rows16, ld16)})
+                    "b16": None if o_16 is None else
+                    (buf16[o_16:o_16 + 2 * rows16 * ld16].view(torch.float16) if flags & W_H16 else buf16[o_16:o_16 + 2 * rows16 * ld16]).view(2, rows16, ld16)})
     fn, n = _lib.load().molclr_prepare_weights, len(specs)
 
     def launch():          # (descs holds raw pointers into buf32 / buf16 / the sources: the closure keeps all of them alive)

@@ -219,7 +219,7 @@ def build_dataset(config):
         raise ValueError("Not defined molecule augmentation!")                        # molclr.py:186-191
     if config.get("fp16_precision"):
         raise ValueError("molclr_b200.trainer: fp16_precision (apex AMP, molclr.py:93-98) is not supported: the kernels choose their "
-                         "own operand precision (model.precision = 'tf32x3' | 'tf32')")
+                         "own operand precision (model.precision = 'fp16x3' | 'tf32x3' | 'tf32')")
     data_path = str(config["dataset"]["data_path"])
     if data_path.startswith("synthetic:") and config["aug"] == "node" and not config["dataset"].get("packed"):
         return SyntheticMoleculeDatasetWrapper(config["batch_size"], **{k: v for k, v in config["dataset"].items() if k != "packed"})

@@ -2,7 +2,7 @@
 Per-parameter parity report (GPU): the full MolCLR pre-training step (molclr.py:55-67) on the CUDA path against the CPU
 oracle in fp32 AND in fp64, so that every measured error is printed next to its floor (oracle fp32 vs oracle fp64).
 
-    python tests/parity_report.py [--batches 128,512] [--precision tf32x3] [--out profiles/parity_r2.json]
+    python tests/parity_report.py [--batches 128,512] [--precision fp16x3|tf32x3|tf32] [--out profiles/parity_r2.json]
 
 Also checks (a) run-twice bit-reproducibility of loss and gradients and (b) that an optimizer step on the parameters is
 picked up by the next forward.  The JSON it writes is what the test tolerances are set from (tests/test_gpu_config_sizes.py).
@@ -125,7 +125,7 @@ def weight_update_pickup(precision):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--batches", default="128,512")
-    ap.add_argument("--precision", default="tf32x3")
+    ap.add_argument("--precision", default="fp16x3")
     ap.add_argument("--models", default="gin")
     ap.add_argument("--out", default="gpurun_out/parity.json")
     a = ap.parse_args()

@@ -22,7 +22,7 @@ DEV = "cuda:0"
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 NTX = sorted(glob.glob(os.path.join(GOLDEN, "ntxent_*.npz")))
 
-# Tolerances.  Default precision "tf32x3": forward contractions are error-compensated 3-pass TF32 (~fp32),
+# Tolerances.  Precisions "fp16x3" (default) and "tf32x3": forward contractions are error-compensated three-product forms (~fp32),
 # backward contractions single-pass TF32 (operands rounded to 10 mantissa bits, fp32 accumulate); everything
 # else is fp32.  Gradients of a ReLU network are only sqrt-continuous in the activations (a pre-activation
 # within rounding distance of 0 flips its mask), so even the fp32 CPU reference differs from its own fp64
@@ -108,10 +108,11 @@ def test_ntxent_batch_size_mismatch_raises():
         crit(torch.randn(6, 16, device=DEV), torch.randn(6, 16, device=DEV))
 
 
-def _models(num_layer=5, emb=300, feat=512, seed=0, precision="tf32x3"):
+def _models(num_layer=5, emb=300, feat=512, seed=0, precision=None):
     torch.manual_seed(seed)
     m = GINet(num_layer, emb, feat, 0, "mean").to(DEV)
-    m.precision = precision
+    if precision is not None:              # (None: the class default)
+        m.precision = precision
     with torch.no_grad():                      # non-trivial BN affine so gamma/beta gradients are exercised
         for bn in m.batch_norms:
             bn.weight.uniform_(0.5, 1.5); bn.bias.uniform_(-0.3, 0.3)
@@ -126,10 +127,10 @@ def test_ginet_state_dict_matches_oracle_layout():
     assert all(sm[k].shape == so[k].shape and sm[k].dtype == so[k].dtype for k in sm)
 
 
-@pytest.mark.parametrize("bs,precision", [(3, "tf32x3"), (64, "tf32x3"), (64, "tf32")])
+@pytest.mark.parametrize("bs,precision", [(3, "tf32x3"), (64, "tf32x3"), (3, "fp16x3"), (64, "fp16x3"), (64, "tf32")])
 def test_ginet_forward_train_and_eval(bs, precision):
     m, o = _models(precision=precision)
-    RTOL_OUT = globals()["RTOL_OUT"] if precision == "tf32x3" else RTOL_OUT_TF32
+    RTOL_OUT = globals()["RTOL_OUT"] if precision != "tf32" else RTOL_OUT_TF32
     bi, _ = make_pair_batch(bs, seed=11)
     h, out = m(bi.to(DEV))
     ho, oo = o(bi)
@@ -147,10 +148,10 @@ def test_ginet_forward_train_and_eval(bs, precision):
     assert int(m.batch_norms[0].num_batches_tracked) == 1
 
 
-@pytest.mark.parametrize("precision", ["tf32x3", "tf32"])
+@pytest.mark.parametrize("precision", ["tf32x3", "fp16x3", "tf32"])
 def test_ginet_backward_all_parameter_gradients(precision):
     m, o = _models(precision=precision)
-    RTOL_GRAD = globals()["RTOL_GRAD"] if precision == "tf32x3" else RTOL_GRAD_TF32
+    RTOL_GRAD = globals()["RTOL_GRAD"] if precision != "tf32" else RTOL_GRAD_TF32
     bi, _ = make_pair_batch(64, seed=12)
     torch.manual_seed(5)
     wh, wo = torch.randn(64, 512), torch.randn(64, 256)
@@ -170,10 +171,11 @@ def test_ginet_backward_all_parameter_gradients(precision):
     assert not bad, bad
 
 
-def test_pretrain_step_loss_and_gradients_config1_shape():
+@pytest.mark.parametrize("precision", ["tf32x3", "fp16x3"])
+def test_pretrain_step_loss_and_gradients_config1_shape(precision):
     """BASELINE config 1 scaled to 128 pairs: MolCLR._step with the unmodified loss formulation."""
     bs = 128
-    m, o = _models(seed=3)
+    m, o = _models(seed=3, precision=precision)
     bi, bj = make_pair_batch(bs, seed=21)
     loss = pretrain_loss(m, NTXentLoss(DEV, bs, 0.1, True), bi.to(DEV), bj.to(DEV))
     loss.backward()
@@ -189,6 +191,29 @@ def test_pretrain_step_loss_and_gradients_config1_shape():
         if not e < RTOL_GRAD:
             bad.append((k, e))
     assert not bad, bad
+
+
+def test_fp16x3_range_violation_is_reported_by_the_next_forward():
+    """An activation beyond fp16's finite range under precision 'fp16x3' is clamped on the device, recorded in a sticky status word
+    and raised by the NEXT forward (no stream drain in between); 'tf32x3' computes the same input without complaint."""
+    torch.manual_seed(0)
+    m = GINet(2, 32, 16).to(DEV)
+    m.precision = "fp16x3"
+    bi, _ = make_pair_batch(4, seed=1)
+    h, _ = m(bi.to(DEV))                                    # in range: nothing is flagged
+    torch.cuda.synchronize()
+    m(bi.to(DEV))
+    with torch.no_grad():
+        m.x_embedding1.weight.fill_(1.0e5)
+    m(bi.to(DEV))
+    torch.cuda.synchronize()
+    m(bi.to(DEV))                                           # (its own copy of the status word is taken here ...)
+    torch.cuda.synchronize()
+    with pytest.raises(FloatingPointError):
+        m(bi.to(DEV))                                       # ... and examined here at the latest
+    m.precision = "tf32x3"
+    h, _ = m(bi.to(DEV))
+    assert bool(torch.isfinite(h).all())
 
 
 def test_unknown_pool_and_cpu_input_fail_loudly():

@@ -24,7 +24,7 @@ def timeit(fn, iters=int(os.environ.get('ITERS', 10))):
 ONLY = os.environ.get("CASE")
 
 
-def case(name, M, N, K, comp=False, b_mn=False, relu=False, pad_k=0, dw=False, masked=False, stat=0, derive=False, mixed=False, presplit=False):
+def case(name, M, N, K, comp=False, b_mn=False, relu=False, pad_k=0, dw=False, masked=False, stat=0, derive=False, mixed=False, presplit=False, h3=False):
     if ONLY and not name.startswith(ONLY):
         return
     g = torch.Generator().manual_seed(0)
@@ -62,7 +62,16 @@ def case(name, M, N, K, comp=False, b_mn=False, relu=False, pad_k=0, dw=False, m
         lo = None
     bias = torch.randn(N, device=dev)
     B16 = None
-    if presplit:          # the product path: weight shadows from molclr_prepare_weights (unrounded K-major copy + pre-split bf16 tiles)
+    if h3:                # the fp16 three-product form (compensate = 2): fp16 halves of the weight from molclr_prepare_weights
+        B16 = ops.prepare_weights([(B.contiguous(), ops.W_H16)])[0]["b16"]
+        A2 = ops.padded(M, K, dev); A2.copy_(A); A = A2
+        bits = ops.relu_bits_buffer(M, N, dev)
+        out = ops.padded(M, N, dev)
+        T = ops.colstat_tiles(M)
+        part = torch.empty(T, 2 * N, device=dev) if stat else None
+        fn = lambda: ops.gemm(A, None, M, N, K, compensate=2, B16=B16, out=out, bias=bias, relu=relu, relu_bits=bits if relu else None,
+                              colstat=part, colstat_mode=stat)
+    elif presplit:          # the product path: weight shadows from molclr_prepare_weights (unrounded K-major copy + pre-split bf16 tiles)
         sh = ops.prepare_weights([(B.contiguous(), ops.W_RAW | ops.W_B16)])[0]
         B, B16 = sh["raw"], sh["b16"]
         A2 = ops.padded(M, K, dev); A2.copy_(A); A = A2
@@ -86,6 +95,8 @@ if os.environ.get("QUICK"):
 case("fwd1 x1   [M,300]x[600,300]", M, 600, 300)
 case("step fwd1 mixed+presplit B, relu bits", M, 600, 300, comp=True, mixed=True, presplit=True, relu=True)
 case("step fwd2 mixed+presplit B", M, 300, 600, comp=True, mixed=True, presplit=True)
+case("step fwd1 fp16x3, relu bits", M, 600, 300, comp=True, h3=True, relu=True)
+case("step fwd2 fp16x3, bn stats", M, 300, 600, comp=True, h3=True, stat=2)
 case("fwd1 x3   [M,300]x[600,300]", M, 600, 300, comp=True)
 case("fwd1 x3 derive, aligned", M, 600, 300, comp=True, derive=True, pad_k=20)
 case("fwd1 mixed (on-chip bf16 corr.)", M, 600, 300, comp=True, mixed=True, pad_k=20)

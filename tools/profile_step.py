@@ -10,7 +10,7 @@ B = int(os.environ.get("BATCH", 4096))
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 model = (GCN if os.environ.get("MODEL") == "gcn" else GINet)(5, 300, 512).to(dev)
-model.precision = os.environ.get("PREC", "tf32x3")
+model.precision = os.environ.get("PREC", model.precision)
 crit = NTXentLoss(dev, B, 0.1, True)
 opt = torch.optim.Adam(model.parameters(), 5e-4, weight_decay=1e-5, fused=True)
 bi, bj = (b.to(dev) for b in make_pair_batch(B, seed=0))
