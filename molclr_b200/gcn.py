@@ -107,7 +107,9 @@ def _gcn_encoder_forward(m, plan, comp, training, pool_mode):
         g, bn = m.gnns[l], m.batch_norms[l]
         W_hi, _ = rw.get(g.weight)
         y = torch.empty(N, D, device=dev)
-        if comp:
+        if comp == 2:          # fp16 three-product form: the fp16 halves of weight^T, no fp32 B operand
+            ops.gemm(x, None, N, D, D, compensate=2, B16=rw.b16(g.weight), out=y, status=m._fp16_status["dev"])
+        elif comp:
             ops.gemm(x, rw.raw(g.weight, transpose=True), N, D, D, compensate=True, B16=rw.b16(g.weight), out=y)    # x @ weight
         else:
             ops.gemm(x, W_hi, N, D, D, b_mn=True, out=y)
@@ -164,7 +166,7 @@ def _gcn_encoder_backward(m, plan, saved, g_p, training, pool_mode):
 def _gcn_precision(m):
     if m.precision not in PRECISIONS:
         raise ValueError(f"molclr_b200: precision must be one of {PRECISIONS}, got {m.precision!r}")
-    return m.precision in ("tf32x3", "fp16x3")      # (the fp16 three-product form exists for the GINEConv MLP products only)
+    return {"fp16x3": 2, "tf32x3": 1, "tf32": 0}[m.precision]      # = molclr_gemm_args.compensate of the x @ weight products
 
 
 class _GCNFunction(torch.autograd.Function):

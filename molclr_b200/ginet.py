@@ -106,15 +106,15 @@ class _EncoderBase(nn.Module):
     """Shared plumbing of the GINet / GCN drop-ins.
 
     ``precision`` (attribute, not a constructor argument -- the constructor is the reference's):
-      * ``"tf32x3"`` (default): every FORWARD contraction is the error-compensated 3-pass TF32 product
+      * ``"fp16x3"`` (default) and ``"tf32x3"``: every FORWARD contraction is an error-compensated three-product form
         (~fp32 accuracy), so pre-activations -- and with them the ReLU masks the backward pass depends on --
-        match the fp32 reference; BACKWARD contractions are single-pass TF32.
-      * ``"fp16x3"``: the same compensated forward with the GINEConv MLP products in the fp16 three-product form
+        match the fp32 reference; BACKWARD contractions are single-pass TF32.  ``"tf32x3"``: a TF32 pass plus two bf16
+        correction passes.  ``"fp16x3"``: the GINEConv MLP / GCNConv products in the fp16 three-product form instead
         (``molclr_gemm_args.compensate = 2``: operands split into two fp16 halves, 22 significand bits): a smaller
         rounding error than ``"tf32x3"`` at 3/4 of its tensor work and 2/3 of its operand traffic, valid while the
         activations stay inside fp16's range -- |a| <= 65504; a violation is detected on the device and raised as
-        ``FloatingPointError`` by the next forward (BatchNorm keeps the activations of this network at O(1)).
-        GCN models, whose contractions take another route, treat it as ``"tf32x3"``.
+        ``FloatingPointError`` by the next forward (BatchNorm keeps the activations of this network at O(1));
+        the projection / prediction heads keep the TF32 form.
       * ``"tf32"``: single-pass TF32 everywhere (fastest; activations carry ~1e-3 relative error and the
         resulting ReLU mask flips show up as percent-level noise in gradients).
     """
@@ -142,7 +142,7 @@ class _EncoderBase(nn.Module):
             if hasattr(g, "mlp"):                         # (+ the transposed tf32 copies: K-major operands of the backward dX products)
                 ws = [(g.mlp[0].weight, enc | ops.W_HI_T | raw), (g.mlp[2].weight, enc | ops.W_HI_T | raw)]
             else:                                         # GCNConv: stored [in, out]
-                ws = [(g.weight, ops.W_HI | ((ops.W_B16 | ops.W_RAW_T) if comp else 0))]
+                ws = [(g.weight, ops.W_HI | ((ops.W_H16 | ops.W_T16) if h3 else (ops.W_B16 | ops.W_RAW_T) if comp else 0))]
             specs += ws
             seen.update(id(w) for w, _ in ws)
         for mod in self.modules():

@@ -97,14 +97,15 @@ def gemm_dw(dY, X, ordered=False, accumulate_into=None):
     return dW
 
 
-W_HI, W_LO, W_RAW, W_RAW_T, W_B16, W_HI_T, W_H16 = 1, 2, 4, 8, 16, 32, 64
+W_HI, W_LO, W_RAW, W_RAW_T, W_B16, W_HI_T, W_H16, W_T16 = 1, 2, 4, 8, 16, 32, 64, 128
 
 
 def prepare_weights(specs, want_relaunch=False):
     """ONE launch deriving the tensor-core operand forms of several weights (molclr_prepare_weights).  specs: [(w, flags)] with w a
     2-D fp32 matrix and flags a combination of W_HI (tf32(w)), W_LO (tf32 residual), W_RAW (unrounded copy, 128-byte rows),
     W_RAW_T (W_RAW of w^T: K-major copy of a weight stored [in, out]), W_B16 (bf16 correction tiles [2, rows16, ld16] of the raw
-    orientation) or W_H16 (instead: the fp16 halves of 2^6 w, same shape, returned under 'b16' as a float16 view), W_HI_T (tf32(w^T): the K-major operand of the backward dX product).  Returns a list of dicts with the keys 'hi',
+    orientation) or W_H16 (instead: the fp16 halves of 2^6 w, same shape, returned under 'b16' as a float16 view; with W_T16 the 16-bit
+    tiles are those of w^T without a raw copy: weights stored [in, out]), W_HI_T (tf32(w^T): the K-major operand of the backward dX product).  Returns a list of dicts with the keys 'hi',
     'lo', 'raw', 'b16', 'hi_t' (None where not requested); with
     ``want_relaunch`` also a callable that re-derives every output from the CURRENT values of the sources into the same buffers."""
     if not specs:
@@ -114,7 +115,7 @@ def prepare_weights(specs, want_relaunch=False):
     plans, n32, n16 = [], 0, 0
     for w, flags in specs:
         rows, cols = w.shape
-        tr = bool(flags & W_RAW_T)
+        tr = bool(flags & (W_RAW_T | W_T16))
         rt, ct = (cols, rows) if tr else (rows, cols)
         ld_hi, ld_raw, ld16, rows16 = r32(cols), r32(ct), (ct + 63) // 64 * 64, (rt + 255) // 256 * 256
         ld_hi_t = r32(rows)

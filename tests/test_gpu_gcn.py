@@ -22,9 +22,11 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 RTOL_OUT, RTOL_LOSS, RTOL_GRAD = 2e-5, 1e-4, tol("RTOL_GRAD", SMALL_BATCH_RTOL_GRAD)      # same policy as tests/test_gpu_model.py (tf32x3 forward)
 
 
-def _models(seed=0, emb=300, feat=512):
+def _models(seed=0, emb=300, feat=512, precision=None):
     torch.manual_seed(seed)
     m = GCN(5, emb, feat, 0, "mean").to(DEV)
+    if precision is not None:              # (None: the class default, "fp16x3")
+        m.precision = precision
     with torch.no_grad():
         for bn in m.batch_norms:
             bn.weight.uniform_(0.5, 1.5); bn.bias.uniform_(-0.3, 0.3)
@@ -83,9 +85,9 @@ def test_gcn_state_dict_loads_reference_checkpoint_layout():
         assert list(v.shape) == man[k]["shape"] and str(v.dtype).replace("torch.", "") == man[k]["dtype"], k
 
 
-@pytest.mark.parametrize("bs", [3, 64])
-def test_gcn_forward_train_and_eval(bs):
-    m, o = _models()
+@pytest.mark.parametrize("bs,precision", [(3, None), (64, None), (64, "tf32x3")])
+def test_gcn_forward_train_and_eval(bs, precision):
+    m, o = _models(precision=precision)
     bi, _ = make_pair_batch(bs, seed=11)
     h, out = m(bi.to(DEV))
     ho, oo = o(bi)
@@ -100,8 +102,9 @@ def test_gcn_forward_train_and_eval(bs):
     assert max_rel(h, ho) < RTOL_OUT and max_rel(out, oo) < RTOL_OUT
 
 
-def test_gcn_backward_all_parameter_gradients():
-    m, o = _models()
+@pytest.mark.parametrize("precision", [None, "tf32x3"])
+def test_gcn_backward_all_parameter_gradients(precision):
+    m, o = _models(precision=precision)
     bi, _ = make_pair_batch(64, seed=12)
     torch.manual_seed(5)
     wh, wo = torch.randn(64, 512), torch.randn(64, 256)
