@@ -323,7 +323,8 @@ def run_ours(args):
             ms, n = C.c_double(0.0), C.c_int(0)
             lib.molclr_step_timing_read(cat, C.byref(ms), C.byref(n))
             return ms.value, n.value
-        (agg_ms, n_agg), (fwd_ms, n_fwd), (bwd_ms, n_bwd), (dw_ms, n_dw) = read(0), read(1), read(2), read(3)
+        (agg_ms, n_agg), (fwd1_ms, n_fwd1), (bwd_ms, n_bwd), (dw_ms, n_dw), (fwd2_ms, n_fwd2) = read(0), read(1), read(2), read(3), read(4)
+        fwd_ms, n_fwd = fwd1_ms + fwd2_ms, n_fwd1 + n_fwd2
         lib.molclr_step_timing(0)
         # algorithmic bytes per launch (DESIGN.md / SURVEY 8d): read the source rows once, write the aggregate once, CSR
         # rowptr / col / packed attributes, BatchNorm coefficients and bond tables
@@ -355,9 +356,11 @@ def run_ours(args):
                          # the weight-gradient products read 3 [N, 300]-sized operand blocks once and write 0.7 MB: they sit on the HBM roofline
                          "weight_gradient_hbm_gbs": (4.0 * 900 * (sum(nodes) / len(nodes)) * n_dw / (dw_ms * 1e-3) / 1e9) if n_dw and dw_ms > 0 else None,
                          "weight_gradient_hbm_frac": (4.0 * 900 * (sum(nodes) / len(nodes)) * n_dw / (dw_ms * 1e-3) / 1e9 / peak) if n_dw and dw_ms > 0 else None,
-                         "us_per_call": {"forward": fwd_ms * 1e3 / max(n_fwd, 1), "backward": bwd_ms * 1e3 / max(n_bwd, 1), "weight_gradient": dw_ms * 1e3 / max(n_dw, 1)},
-                         "note": "useful FLOPs 2MNK per product (the compensated forward issues 2x that in tensor work: one TF32 pass + two "
-                                 "bf16 correction passes); see DESIGN.md section 6"}
+                         "us_per_call": {"forward": fwd_ms * 1e3 / max(n_fwd, 1), "forward_a_to_u": fwd1_ms * 1e3 / max(n_fwd1, 1),
+                                         "forward_u_to_z": fwd2_ms * 1e3 / max(n_fwd2, 1), "backward": bwd_ms * 1e3 / max(n_bwd, 1), "weight_gradient": dw_ms * 1e3 / max(n_dw, 1)},
+                         "note": "useful FLOPs 2MNK per product (the compensated forward issues three products per K slice: fp16x3 = three kind::f16 "
+                                 "passes, tf32x3 = one TF32 pass + two bf16 correction passes); per-call times are event pairs around single "
+                                 "launches and include their launch latency; see DESIGN.md section 6"}
     ncu_traffic = os.path.join(ROOT, "profiles", "aggregate_traffic.json")
     if roof is not None and os.path.exists(ncu_traffic):
         try:      # DRAM bytes per launch of this kernel from an `ncu --set full` capture of the same command (cannot be measured outside a profiler)

@@ -378,8 +378,9 @@ int molclr_gin_encoder_bwd(const molclr_gin_model* m, const molclr_plan_view* pl
                            const uint32_t* drop_seeds, float drop_p, void* ctx, const float* g_p, int ordered, float* grads, void* scratch,
                            size_t scratch_bytes, molclr_layer_cb on_layer_done, void* user, cudaStream_t stream);
 /* In-situ timing of the whole-pass calls (a measurement aid; off by default): molclr_step_timing(1) starts collecting CUDA event
- * pairs, on the launching stream, around the BatchNorm-fused aggregation launches (category 0), the forward MLP products (1), the
- * backward row products (2) and the weight-gradient products (3); (0) stops.  _read waits for a category's events and returns
+ * pairs, on the launching stream, around the BatchNorm-fused aggregation launches (category 0), the first forward MLP products
+ * u = relu(a W1^T + b1) (1), the backward row products (2), the weight-gradient products (3) and the second forward products
+ * z = u W2^T + b2 (4); (0) stops.  _read waits for a category's events and returns
  * their summed milliseconds and the number of timed launches (host out-params). */
 int molclr_step_timing(int enable);
 int molclr_step_timing_read(int category, double* total_ms, int* count);

@@ -70,7 +70,7 @@ static void gemm_args_init(molclr_gemm_args& a) { memset(&a, 0, sizeof(a)); a.sp
 
 // Optional in-situ timing (bench.py's roofline lines): CUDA event pairs around selected launches of the whole-pass calls, on the
 // stream they are launched on.  Off by default; costs nothing then.
-enum : int { TIME_AGG_FWD = 0, TIME_GEMM_FWD = 1, TIME_GEMM_BWD = 2, TIME_GEMM_DW = 3, TIME_CATS = 4 };
+enum : int { TIME_AGG_FWD = 0, TIME_GEMM_FWD = 1, TIME_GEMM_BWD = 2, TIME_GEMM_DW = 3, TIME_GEMM_FWD2 = 4, TIME_CATS = 5 };
 struct StepTimer {
   bool on = false;
   std::vector<cudaEvent_t> ev[TIME_CATS];
@@ -182,7 +182,7 @@ extern "C" int molclr_gin_encoder_fwd(const molclr_gin_model* m, const molclr_pl
     g.compensate = comp; g.B16 = comp ? ly.w2_b16 : nullptr; g.ld16 = m->w2_ld16; g.rows16 = m->w2_rows16; g.status = m->status;
     g.out = x.z[l]; g.ldo = D; g.bias = ly.b2;
     if (training) { g.colstat = stats; g.colstat_mode = 2; }
-    { TimeScope ts(TIME_GEMM_FWD, stream); GIN_CALL(molclr_gemm_tf32(&g, stream)); }
+    { TimeScope ts(TIME_GEMM_FWD2, stream); GIN_CALL(molclr_gemm_tf32(&g, stream)); }
     if (training)                                                                                     // :107
       GIN_CALL(molclr_bn_fwd_finalize(stats, d.T, molclr_gemm_colstat_tile_rows(), N, D, ly.gamma, ly.beta, ly.running_mean, ly.running_var,
                                       ly.num_batches_tracked, ly.momentum, ly.eps, x.coef[l], bn_ws, stream));
@@ -379,8 +379,8 @@ extern "C" int molclr_gin_encoder_bwd(const molclr_gin_model* m, const molclr_pl
 }
 
 // In-situ timing of the whole-pass calls (measurement aid of bench.py): molclr_step_timing(1) starts collecting CUDA event pairs around
-// the BatchNorm-fused aggregation launches (category 0), the forward MLP products (1), the backward row products (2) and the
-// weight-gradient products (3); molclr_step_timing(0) stops.  molclr_step_timing_read synchronises the events of a category and
+// the BatchNorm-fused aggregation launches (category 0), the first forward MLP products u = relu(a W1^T + b1) (1), the backward row
+// products (2), the weight-gradient products (3) and the second forward products z = u W2^T + b2 (4); molclr_step_timing(0) stops.  molclr_step_timing_read synchronises the events of a category and
 // returns their summed milliseconds and the number of timed launches.
 extern "C" int molclr_step_timing(int enable) {
   for (int c = 0; c < TIME_CATS; ++c) {

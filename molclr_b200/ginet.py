@@ -160,15 +160,32 @@ class _EncoderBase(nn.Module):
         if int(comp) == 2:
             self._fp16_range_check()
 
+    fp16_check_every = 8       # forwards between two looks at the status word (1: every forward)
+
+    def check_fp16_range(self):
+        """Blocking form of the range check of ``precision = "fp16x3"`` (drains the stream): raises ``FloatingPointError`` if any forward
+        product since the last check saw an activation beyond fp16's finite range.  The trainer calls it once per epoch."""
+        st = self.__dict__.get("_fp16_status")
+        if st is None:
+            return
+        st["ev"] = None
+        if int(st["dev"].item()) & _lib.STATUS_FP16_RANGE:
+            st["dev"].zero_()
+            raise FloatingPointError("molclr_b200: an activation exceeded fp16's finite range (65504) in a forward product of precision "
+                                     "'fp16x3' (the value was clamped: results since the last check are wrong); use model.precision = 'tf32x3'")
+
     def _fp16_range_check(self):
         """``precision = "fp16x3"``: the forward products report an activation beyond fp16's finite range through a sticky device
-        word (``molclr_gin_model.status``).  It is copied to pinned memory behind each forward and examined by the NEXT one -- no
-        stream drain; the error arrives one call late."""
+        word (``molclr_gin_model.status``).  Every ``fp16_check_every``-th forward copies it to pinned memory on a side stream and a
+        later forward examines the copy -- no stream drain; the error arrives a few calls late."""
         st = self.__dict__.get("_fp16_status")
         if st is None:
             dev = next(self.parameters()).device
             st = self.__dict__["_fp16_status"] = {"dev": torch.zeros(1, dtype=torch.int32, device=dev),
-                                                  "host": torch.zeros(1, dtype=torch.int32).pin_memory(), "ev": None}
+                                                  "host": torch.zeros(1, dtype=torch.int32).pin_memory(), "ev": None, "calls": 0}
+        st["calls"] += 1
+        if st["ev"] is None and st["calls"] % self.fp16_check_every:
+            return                       # (the device word is sticky: a later look still finds the violation)
         if st["ev"] is not None and st["ev"].query():
             st["ev"] = None
             if int(st["host"][0]) & _lib.STATUS_FP16_RANGE:

@@ -176,6 +176,7 @@ class MolCLR:
                 optimizer.step()
                 n_iter += 1
             poll_checks(block=True)                        # deferred batch validation (graph.py): raise here at the latest
+            model.check_fp16_range()                       # ... and the operand-range check of precision "fp16x3"
             if epoch % cfg["eval_every_n_epochs"] == 0:
                 valid_loss = self._validate(model, valid_loader)
                 print(epoch, valid_loss, "(validation)")

@@ -199,6 +199,7 @@ def test_fp16x3_range_violation_is_reported_by_the_next_forward():
     torch.manual_seed(0)
     m = GINet(2, 32, 16).to(DEV)
     m.precision = "fp16x3"
+    m.fp16_check_every = 1
     bi, _ = make_pair_batch(4, seed=1)
     h, _ = m(bi.to(DEV))                                    # in range: nothing is flagged
     torch.cuda.synchronize()
@@ -211,9 +212,13 @@ def test_fp16x3_range_violation_is_reported_by_the_next_forward():
     torch.cuda.synchronize()
     with pytest.raises(FloatingPointError):
         m(bi.to(DEV))                                       # ... and examined here at the latest
+    m(bi.to(DEV))                                           # still out of range: the blocking check finds it at once
+    with pytest.raises(FloatingPointError):
+        m.check_fp16_range()
     m.precision = "tf32x3"
     h, _ = m(bi.to(DEV))
     assert bool(torch.isfinite(h).all())
+    m.check_fp16_range()                                    # (nothing pending)
 
 
 def test_unknown_pool_and_cpu_input_fail_loudly():

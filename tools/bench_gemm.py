@@ -66,7 +66,7 @@ def case(name, M, N, K, comp=False, b_mn=False, relu=False, pad_k=0, dw=False, m
         B16 = ops.prepare_weights([(B.contiguous(), ops.W_H16)])[0]["b16"]
         A2 = ops.padded(M, K, dev); A2.copy_(A); A = A2
         bits = ops.relu_bits_buffer(M, N, dev)
-        out = ops.padded(M, N, dev)
+        out = ops.padded(M, N, dev) if not os.environ.get("UNPADDED_OUT") else torch.empty(M, N, device=dev)      # (row pitch 320 vs 300 floats)
         T = ops.colstat_tiles(M)
         part = torch.empty(T, 2 * N, device=dev) if stat else None
         fn = lambda: ops.gemm(A, None, M, N, K, compensate=2, B16=B16, out=out, bias=bias, relu=relu, relu_bits=bits if relu else None,
