@@ -184,8 +184,9 @@ class _EncoderBase(nn.Module):
             st = self.__dict__["_fp16_status"] = {"dev": torch.zeros(1, dtype=torch.int32, device=dev),
                                                   "host": torch.zeros(1, dtype=torch.int32).pin_memory(), "ev": None, "calls": 0}
         st["calls"] += 1
-        if st["ev"] is None and st["calls"] % self.fp16_check_every:
-            return                       # (the device word is sticky: a later look still finds the violation)
+        if st["ev"] is None and (st["calls"] - 1) % self.fp16_check_every:
+            return                       # (the device word is sticky: a later look still finds the violation; the first forward takes
+                                         #  a look, so that the side stream's one-time set-up cost falls into the warm-up of a run)
         if st["ev"] is not None and st["ev"].query():
             st["ev"] = None
             if int(st["host"][0]) & _lib.STATUS_FP16_RANGE:
