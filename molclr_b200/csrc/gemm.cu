@@ -297,6 +297,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // coordinates and addresses; one elected lane issues the copies)
     {
       uint32_t it = 0;                                  // global k-block counter -> ring slot / phase
+      // L2 prefetch cursor (p.pf > 0, an experiment that did not pay -- see gemm_run): runs p.pf k-blocks ahead of the loads through the
+      // same tile sequence.
+      int pf_t = worker, pf_i = 0, pf_ahead = 0;
       for (int t = worker; t < total; t += num_workers) {
         const int nb0 = (t % n_tiles) * BN;                                  // first column of the tile
         const int n0 = nb0 + (int)rank * Cfg::BN_CTA, m0 = ((t / n_tiles) % m_tiles) * TILE_M + (int)rank * GEMM_BM;
@@ -307,6 +310,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int s = it % Cfg::STAGES;
           ptx::mbar_wait(empty_bar + s, ((it / Cfg::STAGES) & 1) ^ 1);
           if (ptx::elect_one()) {
+            if (p.pf > 0) {
+              for (; pf_ahead < p.pf && pf_t < total; ++pf_ahead) {
+                const int pm0 = ((pf_t / n_tiles) % m_tiles) * TILE_M + (int)rank * GEMM_BM;
+                if (pm0 < p.M) ptx::tma_prefetch_2d(&tmA, pf_i * (H16 ? 2 * Cfg::BK : Cfg::BK), pm0);
+                if (++pf_i == p.num_kb) { pf_i = 0; pf_t += num_workers; }
+              }
+              --pf_ahead;
+            }
             // derive_lo: the fp32 A tile goes to a CTA-local barrier (the converter warps of THIS CTA consume it) and no A_lo is loaded
             // mixed: both raw tiles go to the CTA-local barrier and the MMA issuer waits for the converters only
             if (rank == 0 && !mixed) ptx::mbar_arrive_expect_tx(full_bar + s, derive ? (TWO ? 2 : 1) * 2 * Cfg::B_BYTES : Cfg::TX_BYTES);
@@ -1332,6 +1343,11 @@ int gemm_run(const GemmJob& job, cudaStream_t stream) {
     p.atomic_out = 3;
   }
   p.debug = gemm_debug_flags();
+  // L2 prefetch of the A operand 12 k-blocks ahead of the loads (row products with one K split and a K-major A): OFF.  Tried at the end
+  // of round 2 on the theory that the HBM-streamed A operands (u, g_u) make the ring latency-bound: the step got SLOWER, 10.31 ->
+  // 11.09 ms (backward row products 111 -> 141 us, forward 142 -> 152 us in situ; tools/gpu_r2_pf.sh).  Kept behind
+  // MOLCLR_GEMM_DEBUG bit 32 (debug-switch builds) for further experiments with the distance.
+  p.pf = (splits == 1 && !p.a_mn && (p.segments == 1 || job.compensate) && (p.debug & 32)) ? 12 : 0;
   // split-K weight gradients stay on single CTAs: their 300/600-wide outputs pad badly to 256-row pair tiles (MMA-bound)
   const bool wide = atomic && job.wide && gemm_pair() && !gemm_impl_simt();
   if (wide) MOLCLR_REQUIRE(p.a_mn && p.b_mn, "gemm: wide split-K tiles need both operands MN-major");

@@ -36,6 +36,8 @@ struct GemmParams {
   int stat_groups;             // number of 32-row groups the colstat buffer holds (filled by the launcher)
   int tma_store;               // plain epilogue, one output: staged 32 x 32 chunks leave through TMA stores (tensor map tmO) instead of ld.shared + st.global
   int atomic_out;
+  int pf;                      // > 0: the TMA producer prefetches the K-major A tile `pf` k-blocks ahead of its loads into L2 (debug-switch builds
+                               // only: measured slower, see gemm_run)
   int debug;                   // MOLCLR_GEMM_DEBUG bit 0: skip the generic epilogue (timing experiments only)
   float alpha;                 // out = alpha * acc (+ bias + addend ...)
   // ---- NT-Xent epilogues (nt_xent.py:47-65); logits l = acc * inv_tau
