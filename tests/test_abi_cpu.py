@@ -36,6 +36,20 @@ def test_library_loads_and_reports_version(lib_path):
     assert lib.molclr_gemm_colstat_tiles(129) == 8 and lib.molclr_gemm_colstat_tile_rows() == 32
 
 
+def test_programmatic_launch_switch_is_a_plain_host_toggle(lib_path):
+    """molclr_set_pdl: default on; returns the previous value; a negative argument only queries."""
+    from molclr_b200 import _lib
+    lib = _lib.load()
+    first = lib.molclr_set_pdl(-1)
+    try:
+        assert first in (0, 1)
+        assert lib.molclr_set_pdl(0) == first and lib.molclr_set_pdl(-1) == 0
+        assert lib.molclr_set_pdl(1) == 0 and lib.molclr_set_pdl(-1) == 1
+        assert lib.molclr_set_pdl(7) == 1 and lib.molclr_set_pdl(-1) == 1          # any non-zero value means "on"
+    finally:
+        lib.molclr_set_pdl(first)
+
+
 def test_ntxent_workspace_covers_both_backward_variants(lib_path):
     """Host-only sizing: one buffer serves the forward partials, the fp16 operand copies, the striped backward (W stripe +
     per-stripe partial gradients + cols^T) and the fused backward (32 split slots + column factors), for any shape."""
