@@ -374,8 +374,8 @@ extern "C" int molclr_augment_views(const int32_t* atom_ptr, const int32_t* atom
   if (B == 0) return 0;
   const int warps = 8;
   MOLCLR_LAUNCH(augment_views_kernel, dim3((unsigned)((B + warps - 1) / warps), 2), 32 * warps, 0, stream,
-      atom_ptr, atoms, bond_ptr, bonds, mol_ids, (int)B, node_off, edge_off, bond_off, seed, n_mols, x_i, edge_index_i, edge_attr_i,
-      batch_i, x_j, edge_index_j, edge_attr_j, batch_j, E_total, node_masked, bond_deleted, N_total, M_total, status);
+                atom_ptr, atoms, bond_ptr, bonds, mol_ids, (int)B, node_off, edge_off, bond_off, seed, n_mols, x_i, edge_index_i, edge_attr_i,
+                batch_i, x_j, edge_index_j, edge_attr_j, batch_j, E_total, node_masked, bond_deleted, N_total, M_total, status);
   MOLCLR_CHECK_LAUNCH("augment_views");
   return 0;
 }
@@ -399,8 +399,8 @@ extern "C" int molclr_subgraph_select(const int32_t* atom_ptr, const int32_t* at
   if (e != cudaSuccess) return cuda_fail(e, "subgraph_select memset");
   if (B == 0) return 0;
   MOLCLR_LAUNCH(subgraph_select_kernel, (unsigned)((2 * B + 127) / 128), 128, 0, stream, atom_ptr, atoms, bond_ptr, bonds, mol_ids, (int)B, node_off, bond_off, seed,
-                                                                              n_mols, mode, x_i, batch_i, x_j, batch_j, N_total, M_total, bond_keep,
-                                                                              edge_count, centers, percents, removed, extra_masked, status);
+                n_mols, mode, x_i, batch_i, x_j, batch_j, N_total, M_total, bond_keep,
+                edge_count, centers, percents, removed, extra_masked, status);
   MOLCLR_CHECK_LAUNCH("subgraph_select");
   MOLCLR_LAUNCH(subgraph_scan_kernel, 2, 1024, 0, stream, edge_count, (int)B, edge_off, totals);
   MOLCLR_CHECK_LAUNCH("subgraph_scan");
@@ -414,8 +414,8 @@ extern "C" int molclr_subgraph_fill(const int32_t* bond_ptr, const int32_t* bond
   if (B == 0) return 0;
   const int warps = 8;
   MOLCLR_LAUNCH(subgraph_fill_kernel, dim3((unsigned)((B + warps - 1) / warps), 2), 32 * warps, 0, stream,
-      bond_ptr, bonds, mol_ids, (int)B, node_off, bond_off, edge_off, bond_keep, M_total, n_mols, edge_index_i, edge_attr_i, E_i, edge_index_j,
-      edge_attr_j, E_j);
+                bond_ptr, bonds, mol_ids, (int)B, node_off, bond_off, edge_off, bond_keep, M_total, n_mols, edge_index_i, edge_attr_i, E_i, edge_index_j,
+                edge_attr_j, E_j);
   MOLCLR_CHECK_LAUNCH("subgraph_fill");
   return 0;
 }

@@ -1529,7 +1529,7 @@ extern "C" int molclr_gemm_dw_ordered(const float* dY, int64_t ldy, const float*
   MOLCLR_REQUIRE(S == pl.splits, "gemm_dw_ordered: internal: split count %d != planned %d", S, pl.splits);
   if (int rc = gemm_run(j, stream)) return rc;
   MOLCLR_LAUNCH(dw_reduce_kernel, dim3((unsigned)((pl.N + 31) / 32), (unsigned)((pl.M + 31) / 32), 1), dim3(32, 8, 1), 0, stream,
-      reinterpret_cast<const float*>(workspace), S, (int)pl.M, (int)pl.N, ldws, dW, ldw, pl.swap);
+                reinterpret_cast<const float*>(workspace), S, (int)pl.M, (int)pl.N, ldws, dW, ldw, pl.swap);
   MOLCLR_CHECK_LAUNCH("gemm_dw_ordered reduce");
   return 0;
 }

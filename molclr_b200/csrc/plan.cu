@@ -231,7 +231,7 @@ extern "C" int molclr_plan_build(const int64_t* x, const int64_t* edge_index, co
   int blocks = (int)((work + threads - 1) / threads);
   blocks = blocks < 1 ? 1 : (blocks > 8 * sm_count() ? 8 * sm_count() : blocks);
   MOLCLR_LAUNCH(plan_count_kernel, blocks, threads, 0, stream, x, edge_index, edge_attr, batch, N, E, G, xpacked,
-                                                    node2graph, deg_in, deg_out, gcount, status);
+                node2graph, deg_in, deg_out, gcount, status);
   MOLCLR_CHECK_LAUNCH("plan_count");
   ScanJobs jobs;
   jobs.j[0] = {deg_in, rowptr, N};
@@ -247,13 +247,13 @@ extern "C" int molclr_plan_build(const int64_t* x, const int64_t* edge_index, co
   MOLCLR_LAUNCH(plan_scan_apply_kernel, sgrid, kScanThreads, 0, stream, jobs);
   MOLCLR_CHECK_LAUNCH("plan_scan_apply");
   MOLCLR_LAUNCH(plan_fill_kernel, blocks, threads, 0, stream, edge_index, N, E, node2graph, rowptr, rowptr_t, gptr,
-                                                   deg_in, deg_out, gcount, col, col_t, gperm);
+                deg_in, deg_out, gcount, col, col_t, gperm);
   MOLCLR_CHECK_LAUNCH("plan_fill");
   int64_t work2 = N > G ? N : G;
   int blocks2 = (int)((work2 + threads - 1) / threads);
   blocks2 = blocks2 < 1 ? 1 : blocks2;
   MOLCLR_LAUNCH(plan_rows_kernel, blocks2, threads, 0, stream, edge_index, edge_attr, N, E, G, rowptr, rowptr_t, gptr,
-                                                    col, eattr, col_t, cnt, nbr, nbr_t, gperm, status);
+                col, eattr, col_t, cnt, nbr, nbr_t, gperm, status);
   MOLCLR_CHECK_LAUNCH("plan_rows");
   return 0;
 }

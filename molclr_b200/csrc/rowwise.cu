@@ -1227,7 +1227,7 @@ static void launch_fwd_tile(const float* src, const float* bn_coef, int relu, co
   const int64_t ntiles = (N + T - 1) / T;
   const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
   MOLCLR_LAUNCH(k, grid, kTileThreads, smem, stream, src, bn_coef, relu, rowptr, col, eattr, nbr, B1, B2, (int)N, D, T, stages, g_tile_store_cs, g_tile_blocked, out,
-                                          ld_out, round_out, out_lo, drop);
+                ld_out, round_out, out_lo, drop);
 }
 
 static int aggregate_fwd_launch(const float* src, const float* bn_coef, int relu, const int32_t* rowptr, const int32_t* col,
@@ -1258,19 +1258,19 @@ static int aggregate_fwd_launch(const float* src, const float* bn_coef, int relu
     if (scalar) {
       auto k = gine_aggregate_fwd_kernel<NCH, false, true, false>;
       MOLCLR_LAUNCH(k, persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream,
-          src, nullptr, 0, rowptr, col, eattr, B1, B2, bias, (int)N, D, out, ld_out, round_tf32_out, out_lo, drop);
+                    src, nullptr, 0, rowptr, col, eattr, B1, B2, bias, (int)N, D, out, ld_out, round_tf32_out, out_lo, drop);
     } else if (bn_coef && drop.thr) {
       auto k = gine_aggregate_fwd_kernel<NCH, true, false, true>;
       MOLCLR_LAUNCH(k, persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream,
-          src, bn_coef, relu, rowptr, col, eattr, B1, B2, nullptr, (int)N, D, out, ld_out, round_tf32_out, out_lo, drop);
+                    src, bn_coef, relu, rowptr, col, eattr, B1, B2, nullptr, (int)N, D, out, ld_out, round_tf32_out, out_lo, drop);
     } else if (bn_coef) {
       auto k = gine_aggregate_fwd_kernel<NCH, true, false, false>;
       MOLCLR_LAUNCH(k, persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream,
-          src, bn_coef, relu, rowptr, col, eattr, B1, B2, nullptr, (int)N, D, out, ld_out, round_tf32_out, out_lo, drop);
+                    src, bn_coef, relu, rowptr, col, eattr, B1, B2, nullptr, (int)N, D, out, ld_out, round_tf32_out, out_lo, drop);
     } else {
       auto k = gine_aggregate_fwd_kernel<NCH, false, false, false>;
       MOLCLR_LAUNCH(k, persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream,
-          src, nullptr, 0, rowptr, col, eattr, B1, B2, nullptr, (int)N, D, out, ld_out, round_tf32_out, out_lo, drop);
+                    src, nullptr, 0, rowptr, col, eattr, B1, B2, nullptr, (int)N, D, out, ld_out, round_tf32_out, out_lo, drop);
     }
   });
   MOLCLR_CHECK_LAUNCH("aggregate_fwd");
@@ -1353,7 +1353,7 @@ if (gather && drop.thr) grid = launch_bwd_fused<NCH, true, true>(ga, rowptr_t, c
       MOLCLR_REQUIRE(gather, "relu_bn_bwd_stats: z_prev is required");
       auto k = gine_aggregate_bwd_kernel<NCH, 0, true, false>;
       MOLCLR_LAUNCH(k, persistent_grid(k, kRowThreads, 0, kRowWarps, N), kRowThreads, 0, stream, ga, rowptr_t, col_t, nullptr, nullptr, 0,
-                                                                                        (int)N, D, gy, nullptr, round_out, drop);
+                    (int)N, D, gy, nullptr, round_out, drop);
     }
   });
   MOLCLR_CHECK_LAUNCH("aggregate_bwd");
@@ -1396,7 +1396,7 @@ extern "C" int molclr_bn_fwd_finalize(const float* tile_stats, int T, int tile_r
   MOLCLR_LAUNCH(bn_merge_tiles_kernel, dim3((D + 31) / 32, S), dim3(32, 16), 0, stream, tile_stats, T, tile_rows, (int)N, D, per, ws);
   MOLCLR_CHECK_LAUNCH("bn_merge_tiles");
   MOLCLR_LAUNCH(bn_fwd_finalize_kernel, (D + 7) / 8, 256, 0, stream, ws, S, D, gamma, beta, running_mean, running_var,
-                                                              reinterpret_cast<long long*>(num_batches_tracked), momentum, eps, coef);
+                reinterpret_cast<long long*>(num_batches_tracked), momentum, eps, coef);
   MOLCLR_CHECK_LAUNCH("bn_fwd_finalize");
   return 0;
 }
@@ -1411,7 +1411,7 @@ extern "C" int molclr_bn_eval_coef(const float* gamma, const float* beta, const 
 extern "C" int molclr_bn_bwd_finalize(const float* partials, int P, int64_t N, int D, const float* gamma, const float* coef,
                                       int use_batch_stats, float* dgamma, float* dbeta, float* bcoef, cudaStream_t stream) {
   MOLCLR_LAUNCH(bn_bwd_finalize_kernel, (D + 31) / 32, dim3(32, 16), 0, stream, partials, P, (int)N, D, gamma, coef, use_batch_stats, dgamma,
-                                                                       dbeta, bcoef);
+                dbeta, bcoef);
   MOLCLR_CHECK_LAUNCH("bn_bwd_finalize");
   return 0;
 }
@@ -1437,12 +1437,12 @@ extern "C" int molclr_bn_bwd_apply(const float* gy, const float* gp, const int32
       auto k = bn_bwd_apply_kernel<NCH, 1>;
       grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
       MOLCLR_LAUNCH(k, grid, kRowThreads, smem, stream, nullptr, gp, node2graph, gptr, pool_mode, argmax, z, bcoef, (int)N, D, gz, ld_gz, partials,
-                                             round_tf32_out, drop);
+                    round_tf32_out, drop);
     } else {
       auto k = bn_bwd_apply_kernel<NCH, 0>;
       grid = persistent_grid(k, kRowThreads, smem, kRowWarps, N);
       MOLCLR_LAUNCH(k, grid, kRowThreads, smem, stream, gy, nullptr, nullptr, nullptr, 0, nullptr, z, bcoef, (int)N, D, gz, ld_gz, partials,
-                                             round_tf32_out, drop);
+                    round_tf32_out, drop);
     }
   });
   MOLCLR_CHECK_LAUNCH("bn_bwd_apply");
@@ -1461,8 +1461,8 @@ extern "C" int molclr_pool_fwd(const float* z, const float* bn_coef, int relu, c
   NCH_DISPATCH(D / 4, {
     auto k = pool_fwd_kernel<NCH>;
     MOLCLR_LAUNCH(k, persistent_grid(k, kRowThreads, smem, kRowWarps, G), kRowThreads, smem, stream, z, bn_coef, relu, gptr, gperm,
-                                                                                          pool_mode, (int)G, D, out, ld_out, round_tf32_out, out_lo, argmax,
-                                                                                          make_drop(drop_seed, drop_p));
+                  pool_mode, (int)G, D, out, ld_out, round_tf32_out, out_lo, argmax,
+                  make_drop(drop_seed, drop_p));
   });
   MOLCLR_CHECK_LAUNCH("pool_fwd");
   return 0;
@@ -1497,7 +1497,7 @@ extern "C" int molclr_bn_apply_fwd(const float* z, const float* bn_coef, int rel
   NCH_DISPATCH(D / 4, {
     auto k = bn_apply_fwd_kernel<NCH>;
     MOLCLR_LAUNCH(k, persistent_grid(k, kRowThreads, smem, kRowWarps, N), kRowThreads, smem, stream, z, bn_coef, relu, (int)N, D, hi, lo, ld, round_hi,
-                                                                                          make_drop(drop_seed, bn_coef ? drop_p : 0.f));
+                  make_drop(drop_seed, bn_coef ? drop_p : 0.f));
   });
   MOLCLR_CHECK_LAUNCH("bn_apply_fwd");
   return 0;
@@ -1609,7 +1609,7 @@ extern "C" int molclr_ntxent_rows_fwd(const float* zA, const float* zB, int64_t 
   MOLCLR_REQUIRE(y16 == nullptr || (ld16 >= C && ld16 % 8 == 0), "ntxent_rows_fwd: ld16 must be >= C and a multiple of 8 halves");
   if (RA + RB == 0) return 0;
   MOLCLR_LAUNCH(l2_normalize_cat_fwd_kernel, (int)((RA + RB + 7) / 8), 256, 0, stream, zA, zB, (int)RA, (int)RB, C, eps, normalise, y, y_r, inv_norm,
-                                                                          reinterpret_cast<__half*>(y16), (int)ld16);
+                reinterpret_cast<__half*>(y16), (int)ld16);
   MOLCLR_CHECK_LAUNCH("ntxent_rows_fwd");
   return 0;
 }

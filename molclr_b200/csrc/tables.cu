@@ -325,7 +325,7 @@ extern "C" int molclr_embed_nodes_bwd(const int32_t* xpacked, const float* g, in
   int tx = (CW / 4 + 31) / 32 * 32;
   if (tx * kOhRY < kOhChunk) tx = kOhChunk / kOhRY;                       // the first 128 threads load / rank the chunk's keys
   MOLCLR_LAUNCH(onehot_colsum_kernel, dim3((unsigned)used, (unsigned)slices, 1), dim3((unsigned)tx, kOhRY, 1), smem, stream,
-      g, ld_g, xpacked, (int)N, D, CW, cpb, partials);
+                g, ld_g, xpacked, (int)N, D, CW, cpb, partials);
   MOLCLR_CHECK_LAUNCH("embed_nodes_bwd");
   return molclr_reduce_partials(partials, used, (kNumAtomType + kNumChirality) * D, 1.f, 0, dE, stream);
 }
