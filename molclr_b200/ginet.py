@@ -129,6 +129,16 @@ class _EncoderBase(nn.Module):
 
     deterministic = False      # True: weight gradients are summed in a fixed order (bit-reproducible run to run); see DESIGN.md
 
+    # per-instance caches of device state (weight-shadow buffers, the native model struct, the fp16 status word with its stream and
+    # event): rebuilt on demand, never copied or pickled with the module (copy.deepcopy(model), torch.save(model))
+    _TRANSIENT = ("_gemm_weight_specs", "_native_struct", "_fp16_status")
+
+    def __getstate__(self):
+        state = {k: v for k, v in self.__dict__.items() if k not in self._TRANSIENT}
+        if "_rounded" in state:
+            state["_rounded"] = _RoundedWeights()
+        return state
+
     def _gemm_weights(self, comp):
         """(parameter, ops.W_* operand forms) of every contraction of the model.  GINEConv MLP weights / GCNConv weights: hi
         (backward dX products, single-pass forward) and, for the compensated forward, the unrounded K-major copy + its bf16
@@ -179,8 +189,8 @@ class _EncoderBase(nn.Module):
         word (``molclr_gin_model.status``).  Every ``fp16_check_every``-th forward copies it to pinned memory on a side stream and a
         later forward examines the copy -- no stream drain; the error arrives a few calls late."""
         st = self.__dict__.get("_fp16_status")
-        if st is None:
-            dev = next(self.parameters()).device
+        dev = next(self.parameters()).device
+        if st is None or st["dev"].device != dev:            # (first use, or the model has moved to another device)
             st = self.__dict__["_fp16_status"] = {"dev": torch.zeros(1, dtype=torch.int32, device=dev),
                                                   "host": torch.zeros(1, dtype=torch.int32).pin_memory(), "ev": None, "calls": 0}
         st["calls"] += 1
