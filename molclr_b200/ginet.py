@@ -194,17 +194,16 @@ class _EncoderBase(nn.Module):
             st = self.__dict__["_fp16_status"] = {"dev": torch.zeros(1, dtype=torch.int32, device=dev),
                                                   "host": torch.zeros(1, dtype=torch.int32).pin_memory(), "ev": None, "calls": 0}
         st["calls"] += 1
-        if st["ev"] is None and (st["calls"] - 1) % self.fp16_check_every:
-            return                       # (the device word is sticky: a later look still finds the violation; the first forward takes
-                                         #  a look, so that the side stream's one-time set-up cost falls into the warm-up of a run)
-        if st["ev"] is not None and st["ev"].query():
+        if st["ev"] is not None and st["ev"].query():          # the last copy has arrived: examine it
             st["ev"] = None
             if int(st["host"][0]) & _lib.STATUS_FP16_RANGE:
                 st["dev"].zero_()
                 raise FloatingPointError("molclr_b200: an activation exceeded fp16's finite range (65504) in a forward product of "
                                          "precision 'fp16x3' (the value was clamped: results since the last check are wrong); "
                                          "use model.precision = 'tf32x3'")
-        if st["ev"] is None:
+        # a new copy on forwards 1, 1 + every, 1 + 2 every, ... (the device word is sticky: a later look still finds a violation; the
+        # first forward takes one, so that the side stream's one-time set-up cost falls into the warm-up of a run)
+        if st["ev"] is None and (st["calls"] - 1) % self.fp16_check_every == 0:
             # the 4-byte copy runs on a side stream behind everything enqueued so far: on the compute stream it would queue behind any
             # host-to-device batch copy in flight on the same copy engine (measured: 0.25 ms per step in bench.py's e2e loop)
             side = st.get("stream")
