@@ -360,7 +360,10 @@ def run_ours(args):
                                          "forward_u_to_z": fwd2_ms * 1e3 / max(n_fwd2, 1), "backward": bwd_ms * 1e3 / max(n_bwd, 1), "weight_gradient": dw_ms * 1e3 / max(n_dw, 1)},
                          "note": "useful FLOPs 2MNK per product (the compensated forward issues three products per K slice: fp16x3 = three kind::f16 "
                                  "passes, tf32x3 = one TF32 pass + two bf16 correction passes); per-call times are event pairs around single "
-                                 "launches and include their launch latency; see DESIGN.md section 6"}
+                                 "launches and include their launch latency; see DESIGN.md section 6",
+                         "bound_note": "the tensor peak is the nominal ceiling of these products; what the forward products actually sit on is the "
+                                       "shared-memory data pipe (ncu --set full, profiles/r2_ncu_fwd2_fp16x3.md: LSU wavefronts 59 % + tensor-core "
+                                       "operand wavefronts 29 % of peak, tensor pipe 48 %), the weight gradients on HBM"}
     ncu_traffic = os.path.join(ROOT, "profiles", "aggregate_traffic.json")
     if roof is not None and os.path.exists(ncu_traffic):
         try:      # DRAM bytes per launch of this kernel from an `ncu --set full` capture of the same command (cannot be measured outside a profiler)
