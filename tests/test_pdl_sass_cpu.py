@@ -17,10 +17,15 @@ CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
 GLOBAL_OP = re.compile(r"^(@!?U?P\d+\s+)?(LDG|STG|LD|ST|ATOM|ATOMG|RED|REDG|LDGSTS|UTMALDG|UTMASTG|UTMAPF|UTMAREDG|UBLKCP|UBLKRED|UBLKPF)\b")
 
 
-@pytest.mark.skipif(not os.path.exists(CUOBJDUMP), reason="cuobjdump (CUDA toolkit) not found")
-def test_every_kernel_waits_before_its_first_global_access():
+@pytest.fixture(scope="module")
+def sass():
+    if not os.path.exists(CUOBJDUMP):
+        pytest.skip("cuobjdump (CUDA toolkit) not found")
     from molclr_b200.build import build
-    sass = subprocess.run([CUOBJDUMP, "-sass", build()], capture_output=True, text=True, timeout=600).stdout
+    return subprocess.run([CUOBJDUMP, "-sass", build()], capture_output=True, text=True, timeout=600).stdout
+
+
+def test_every_kernel_waits_before_its_first_global_access(sass):
     funcs, cur = {}, None
     for line in sass.splitlines():
         m = re.search(r"Function : (\S+)", line)
@@ -41,3 +46,12 @@ def test_every_kernel_waits_before_its_first_global_access():
         if early:
             problems.append((name, "global access before the wait: " + early[0]))
     assert not problems, problems[:5]
+
+
+def test_tensor_core_and_tma_instructions_are_the_blackwell_ones(sass):
+    """The contraction and tile-movement kernels are written against tcgen05 / TMEM / TMA: the library's SASS holds UTCHMMA (incl. the
+    CTA-pair form), TMEM loads, TMA tensor loads and stores and bulk copies -- and no legacy warp-level MMA."""
+    count = lambda pat: len(re.findall(pat, sass))
+    assert count(r"\bUTCHMMA\b") > 100 and count(r"\bUTCHMMA\.2CTA\b") > 100
+    assert count(r"\bLDTM\b") > 50 and count(r"\bUTMALDG\.") > 300 and count(r"\bUTMASTG\.") > 10 and count(r"\bUBLKCP\b") > 5
+    assert count(r"\bHMMA\b") == 0 and count(r"\bHGMMA\b") == 0
