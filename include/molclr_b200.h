@@ -257,8 +257,9 @@ typedef struct {
                                  product runs as A_h B_h + A_l B_h + A_h B_l in three kind::f16 MMAs: 3/4 of the tensor time and
                                  2/3 of the operand bytes of form 1, smaller rounding error (hi halves rounded, not truncated;
                                  11-bit corrections).  Price: fp16's RANGE.  |a| > 65504 is clamped (the result is then wrong)
-                                 and reported through `status`; |a| < 6e-5 keeps an absolute error of 3e-8 (relative accuracy
-                                 degrades gracefully towards TF32's as a whole row of A falls below ~1e-3).  The activations of
+                                 and reported through `status`; halves below 6e-5 are fp16 subnormals with an absolute error of
+                                 3e-8, so the relative accuracy degrades gracefully towards TF32's when ALL of A is small
+                                 (2e-5 at |a| ~ 1e-3, 2e-4 at 1e-4; TF32: 8e-4).  The activations of
                                  the path (BatchNorm outputs and their neighbourhood sums) sit in the middle of that range.   */
   const void* B16;            /* compensate = 1, optional: the bf16 correction tiles of B pre-split once per optimizer step by
                                  molclr_prepare_weights -- bf16 [2][rows16][ld16]: bf16(B) then bf16(B - trunc_tf32(B)), zero padded;
